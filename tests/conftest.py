@@ -1,0 +1,24 @@
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run by the driver with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return torch.load(os.path.join(ROOT, "tests", "golden", "golden_v1.pt"), map_location="cpu", weights_only=False)
+
+
+def rel_err(a, b):
+    """max |a-b| / max(|b|, tiny): scale-free error used by all parity tests."""
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()

@@ -1,0 +1,235 @@
+// gtos_b200 -- extern "C" surface of libgtos_b200.so (declared in include/gtos_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include "../../include/gtos_b200.h"
+#include "elementwise.cuh"
+#include "gemm.cuh"
+
+namespace gtos {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace gtos
+
+using namespace gtos;
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+const char* gtos_last_error(void) { return g_err; }
+int gtos_abi_version(void) { return 1; }
+
+int gtos_device_check(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    set_error("no CUDA device");
+    return GTOS_ERR_NO_DEVICE;
+  }
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (major != 10) {
+    set_error("gtos_b200 kernels are built for sm_100a only (device is sm_%d0)", major);
+    return GTOS_ERR_NO_DEVICE;
+  }
+  CUtensorMap tm;
+  static __nv_bfloat16* probe = nullptr;
+  if (!probe) GTOS_CHECK_CUDA(cudaMalloc(&probe, 128 * 64 * 2));
+  return make_tmap_2d_bf16(&tm, probe, 128, 64, 64, 128);
+}
+
+int gtos_cast_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int32_t cols, void* stream) {
+  return cast_f32_bf16(src, lds, dst, ldd, rows, cols, S(stream));
+}
+
+int gtos_weight_prep(const float* W, int32_t R, int32_t C, void* Wb, int64_t ldw, void* Wt, int64_t ldt,
+                     int32_t rel_heads, void* stream) {
+  int perm_D = 0, perm_hd = 0;
+  if (rel_heads > 0) {
+    GTOS_REQUIRE(R == 2 * C && C % rel_heads == 0, "weight_prep: relation weight must be [2D, D] with D %% H == 0");
+    perm_D = C;
+    perm_hd = C / rel_heads;
+  }
+  return weight_prep(W, R, C, Wb, ldw, Wt, ldt, perm_D, perm_hd, S(stream));
+}
+
+int gtos_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, const float* bias, float* out_f32, int64_t ldo,
+                 void* out_bf16, int64_t ldob, int32_t M, int32_t N, int32_t K, int32_t relu, int32_t accumulate,
+                 void* stream) {
+  if (M == 0 || N == 0) return GTOS_OK;
+  GemmTnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.A = A; a.lda = lda; a.Bm = B; a.ldb = ldb; a.M = M; a.N = N; a.K = K;
+  a.bias = bias; a.out_f32 = out_f32; a.ldo = ldo; a.out_bf16 = out_bf16; a.ldob = ldob;
+  a.relu = relu; a.accumulate = accumulate;
+  return launch_gemm_tn(MODE_PLAIN, a, S(stream));
+}
+
+int64_t gtos_gemm_nn_workspace(int32_t M, int32_t N, int32_t Kd) { return gemm_nn_workspace_elems(M, N, Kd, 0); }
+
+int gtos_gemm_nn(const void* A, int64_t lda, const void* B, int64_t ldb, float* out, int64_t ldo, int32_t M, int32_t N,
+                 int32_t Kd, float* workspace, int64_t workspace_elems, void* stream) {
+  if (M == 0 || N == 0) return GTOS_OK;
+  GemmNnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.A = A; a.lda = lda; a.Bm = B; a.ldb = ldb; a.M = M; a.N = N; a.Kd = Kd; a.rel = 0;
+  a.out = out; a.ldo = ldo; a.workspace = workspace; a.workspace_elems = workspace_elems;
+  return launch_gemm_nn(a, S(stream));
+}
+
+int gtos_rel_tiling(int32_t N, int32_t B, int32_t D, int32_t H, int32_t* out5) {
+  RelTiling rt;
+  int e = choose_rel_tiling(&rt, N, B, D, H);
+  if (e) return e;
+  out5[0] = rt.bi; out5[1] = rt.bj; out5[2] = rt.ni_blk; out5[3] = rt.nj_blk; out5[4] = rt.tiles;
+  return GTOS_OK;
+}
+
+static int rel_args(GemmTnArgs* a, int32_t N, int32_t B, int32_t D, int32_t H) {
+  memset(a, 0, sizeof(*a));
+  int e = choose_rel_tiling(&a->rt, N, B, D, H);
+  if (e) return e;
+  a->N = 2 * D;
+  a->K = D;
+  a->M = a->rt.tiles * 128;
+  return GTOS_OK;
+}
+
+int gtos_rel_score(const void* relb, const void* Wperm, const float* q, const float* k, int64_t ldqk, float* scores,
+                   int32_t N, int32_t B, int32_t D, int32_t H, void* stream) {
+  GemmTnArgs a;
+  int e = rel_args(&a, N, B, D, H);
+  if (e) return e;
+  GTOS_REQUIRE(ldqk % 4 == 0, "rel_score: q/k row stride must be a multiple of 4 floats");
+  a.A = relb; a.lda = D; a.Bm = Wperm; a.ldb = D; a.q = q; a.k = k; a.ldqk = ldqk; a.scores = scores;
+  return launch_gemm_tn(MODE_SCORE, a, S(stream));
+}
+
+int gtos_rel_grad(const void* relb, const void* Wperm, const float* q, const float* k, int64_t ldqk,
+                  const float* dscores, void* G, int32_t N, int32_t B, int32_t D, int32_t H, void* stream) {
+  GemmTnArgs a;
+  int e = rel_args(&a, N, B, D, H);
+  if (e) return e;
+  GTOS_REQUIRE(ldqk % 4 == 0, "rel_grad: q/k row stride must be a multiple of 4 floats");
+  a.A = relb; a.lda = D; a.Bm = Wperm; a.ldb = D; a.q = q; a.k = k; a.ldqk = ldqk; a.dscores = dscores; a.G = G;
+  return launch_gemm_tn(MODE_GRAD, a, S(stream));
+}
+
+int gtos_rel_drel(const void* G, const void* WpermT, float* d_relation, int32_t accumulate, int32_t N, int32_t B,
+                  int32_t D, int32_t H, void* stream) {
+  GemmTnArgs a;
+  int e = rel_args(&a, N, B, D, H);
+  if (e) return e;
+  a.A = G; a.lda = 2 * D; a.Bm = WpermT; a.ldb = 2 * D;
+  a.N = D; a.K = 2 * D;
+  a.out_f32 = d_relation; a.ldo = D; a.accumulate = accumulate;
+  return launch_gemm_tn(MODE_DREL, a, S(stream));
+}
+
+int64_t gtos_rel_dw_workspace(int32_t N, int32_t B, int32_t D, int32_t H) {
+  RelTiling rt;
+  if (choose_rel_tiling(&rt, N, B, D, H)) return -1;
+  return gemm_nn_workspace_elems(2 * D, D, rt.tiles * 128, 1);
+}
+
+int gtos_rel_dw(const void* G, const void* relb, float* dW, float* workspace, int64_t workspace_elems, int32_t N,
+                int32_t B, int32_t D, int32_t H, void* stream) {
+  GemmNnArgs a;
+  memset(&a, 0, sizeof(a));
+  int e = choose_rel_tiling(&a.rt, N, B, D, H);
+  if (e) return e;
+  a.A = G; a.lda = 2 * D; a.Bm = relb; a.ldb = D; a.M = 2 * D; a.N = D; a.Kd = a.rt.tiles * 128; a.rel = 1;
+  a.out = dW; a.ldo = D; a.workspace = workspace; a.workspace_elems = workspace_elems;
+  return launch_gemm_nn(a, S(stream));
+}
+
+int gtos_rel_dqk(const void* G, float* dq, float* dk, int64_t ld, int32_t N, int32_t B, int32_t D, int32_t H,
+                 void* stream) {
+  RelTiling rt;
+  int e = choose_rel_tiling(&rt, N, B, D, H);
+  if (e) return e;
+  return rel_dqk(G, rt, dq, dk, ld, S(stream));
+}
+
+static void fill_attn(const gtos_attn_desc* d, AttnArgs* a) {
+  a->T = d->T; a->S = d->S; a->B = d->B; a->H = d->H; a->hd = d->hd;
+  a->q = d->q; a->ldq = d->ldq; a->k = d->k; a->ldk = d->ldk; a->v = d->v; a->ldv = d->ldv;
+  a->scale = d->scale; a->scores_jt = d->scores_jt; a->key_pad = d->key_pad; a->attn_mask = d->attn_mask;
+  a->p_drop = d->p_drop; a->seed_ptr = d->seed_ptr; a->seed_off = d->seed_off;
+  a->probs = d->probs; a->probs_dropped = d->probs_dropped; a->out = d->out; a->ldo = d->ldo; a->out_bf16 = d->out_bf16;
+}
+
+int gtos_attn_fwd(const gtos_attn_desc* d, void* stream) {
+  GTOS_REQUIRE(d && d->v && d->probs && d->out, "attn_fwd: null argument");
+  GTOS_REQUIRE(d->scores_jt || (d->q && d->k), "attn_fwd: need either scores or q/k");
+  AttnArgs a;
+  fill_attn(d, &a);
+  return attn_fwd(a, S(stream));
+}
+
+int gtos_attn_bwd(const gtos_attn_desc* d, void* stream) {
+  GTOS_REQUIRE(d && d->v && d->probs && d->dout && d->dscores_ts && d->dv, "attn_bwd: null argument");
+  AttnBwdArgs g;
+  fill_attn(d, &g.f);
+  g.dout = d->dout; g.lddo = d->lddo; g.dprobs_extra = d->dprobs_extra;
+  g.dscores_jt = d->dscores_jt; g.dscores_ts = d->dscores_ts;
+  g.dq = d->dq; g.lddq = d->lddq; g.dk = d->dk; g.lddk = d->lddk; g.dv = d->dv; g.lddv = d->lddv;
+  GTOS_REQUIRE(!g.dq || (d->q && d->k && g.dk), "attn_bwd: decoder mode needs q, k, dq and dk");
+  return attn_bwd(g, S(stream));
+}
+
+int gtos_add_ln_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* y, void* y_bf16,
+                    float* z, float* mean, float* rstd, int64_t rows, int32_t D, float p_drop, const void* seed_ptr,
+                    uint64_t seed_off, void* stream) {
+  return add_ln_fwd(x, res, gamma, beta, y, y_bf16, z, mean, rstd, rows, D, p_drop, seed_ptr, seed_off, S(stream));
+}
+int gtos_add_ln_bwd(const float* dy, const float* z, const float* mean, const float* rstd, const float* gamma,
+                    float* dres, float* dx, void* dx_bf16, float* dgamma, float* dbeta, int64_t rows, int32_t D,
+                    float p_drop, const void* seed_ptr, uint64_t seed_off, void* stream) {
+  return add_ln_bwd(dy, z, mean, rstd, gamma, dres, dx, dx_bf16, dgamma, dbeta, rows, D, p_drop, seed_ptr, seed_off,
+                    S(stream));
+}
+int gtos_colsum(const float* x, int64_t ld, float* out, int64_t rows, int32_t cols, void* stream) {
+  return colsum(x, ld, out, rows, cols, S(stream));
+}
+int gtos_colsum_bf16(const void* x, int64_t ld, float* out, int64_t rows, int32_t cols, void* stream) {
+  return colsum_bf16(x, ld, out, rows, cols, S(stream));
+}
+int gtos_dropout_bf16(void* h, int64_t n, float p, const void* seed_ptr, uint64_t seed_off, void* stream) {
+  return dropout_bf16(h, n, p, seed_ptr, seed_off, S(stream));
+}
+int gtos_dropout_f32(const float* x, float* out, int64_t n, float p, const void* seed_ptr, uint64_t seed_off,
+                     void* stream) {
+  return dropout_f32(x, out, n, p, seed_ptr, seed_off, S(stream));
+}
+int gtos_relu_drop_bwd(const float* dh_in, const void* act_bf16, float* dh_f32, void* dh_bf16, int64_t n, float p,
+                       void* stream) {
+  return relu_drop_bwd(dh_in, act_bf16, dh_f32, dh_bf16, n, p, S(stream));
+}
+int gtos_embed_gather(const float* table, const int64_t* idx, int64_t n, int32_t dim, float* out_f32, void* out_bf16,
+                      int64_t ldb, float p_drop, const void* seed_ptr, uint64_t seed_off, void* stream) {
+  return embed_gather(table, reinterpret_cast<const long long*>(idx), n, dim, out_f32, out_bf16, ldb, p_drop, seed_ptr,
+                      seed_off, S(stream));
+}
+int gtos_embed_scatter_add(const float* dx, const int64_t* idx, int64_t n, int32_t dim, float* dtable, float p_drop,
+                           const void* seed_ptr, uint64_t seed_off, void* stream) {
+  return embed_scatter_add(dx, reinterpret_cast<const long long*>(idx), n, dim, dtable, p_drop, seed_ptr, seed_off,
+                           S(stream));
+}
+int gtos_gru_gate_fwd(const float* gi, int64_t ldgi, const float* gh, int64_t ldgh, const float* h_prev,
+                      const int64_t* lengths, int32_t t, float* h_new, void* h_new_bf16, float* out_t, int64_t ldout,
+                      void* out_t_bf16, int64_t ldoutb, float* gates, int64_t R, int32_t Hh, void* stream) {
+  return gru_gate_fwd(gi, ldgi, gh, ldgh, h_prev, reinterpret_cast<const long long*>(lengths), t, h_new, h_new_bf16,
+                      out_t, ldout, out_t_bf16, ldoutb, gates, R, Hh, S(stream));
+}
+int gtos_gru_gate_bwd(const float* dh, const float* dout_t, int64_t lddout, const float* gates, const float* gh,
+                      int64_t ldgh, const float* h_prev, const int64_t* lengths, int32_t t, float* dh_prev,
+                      void* dgi_bf16, int64_t lddgi, void* dgh_bf16, int64_t lddgh, int64_t R, int32_t Hh, void* stream) {
+  return gru_gate_bwd(dh, dout_t, lddout, gates, gh, ldgh, h_prev, reinterpret_cast<const long long*>(lengths), t,
+                      dh_prev, dgi_bf16, lddgi, dgh_bf16, lddgh, R, Hh, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,405 @@
+// gtos_b200 -- memory-bound helper kernels: casts, weight preparation, residual+LayerNorm
+// (forward / backward), column sums, ReLU / dropout backward, relation dq/dk reduction.
+// All are HBM/L2-bound streaming kernels: vectorised, coalesced, one pass.
+#include "elementwise.cuh"
+
+namespace gtos {
+
+// ---------------------------------------------------------------------------------------
+// fp32 -> bf16 with optional row padding (dst row stride ldd >= cols, pad columns zeroed)
+// ---------------------------------------------------------------------------------------
+__global__ void cast_pad_kernel(const float* __restrict__ src, long lds, __nv_bfloat16* __restrict__ dst, long ldd,
+                                long rows, int cols) {
+  const long total = rows * (ldd / 2);
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const long r = idx / (ldd / 2);
+    const int c = (int)(idx % (ldd / 2)) * 2;
+    const float* s = src + r * lds + c;
+    float a = c < cols ? s[0] : 0.f;
+    float b = c + 1 < cols ? s[1] : 0.f;
+    *reinterpret_cast<uint32_t*>(dst + r * ldd + c) = pack_bf16x2(a, b);
+  }
+}
+
+__global__ void cast_vec_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, long n4) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    float4 v = src[i];
+    dst[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+}
+
+int cast_f32_bf16(const float* src, long lds, void* dst, long ldd, long rows, int cols, cudaStream_t st) {
+  if (rows == 0 || cols == 0) return GTOS_OK;
+  GTOS_REQUIRE(ldd % 2 == 0 && ldd >= cols, "cast: destination row stride must be even and >= cols");
+  if (lds == cols && ldd == cols && cols % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+    long n4 = rows * cols / 4;
+    int blocks = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
+    cast_vec_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<uint2*>(dst), n4);
+  } else {
+    long total = rows * (ldd / 2);
+    int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    cast_pad_kernel<<<blocks, 256, 0, st>>>(src, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldd, rows, cols);
+  }
+  GTOS_LAUNCH_CHECK();
+  return GTOS_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// weight prep: W f32 [R,C] -> Wb bf16 [R,ldw] (optional) and Wt bf16 [C,ldt] (optional)
+// optional row permutation for relation_in_proj (perm_D > 0): output row pr <- input row orig(pr)
+// ---------------------------------------------------------------------------------------
+__global__ void weight_prep_kernel(const float* __restrict__ W, int R, int C, __nv_bfloat16* __restrict__ Wb, long ldw,
+                                   __nv_bfloat16* __restrict__ Wt, long ldt, int perm_D, int perm_hd) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+    int pr = r0 + y, c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (pr < R && c < C) {
+      int ro = perm_D ? rel_perm_to_orig(pr, perm_D, perm_hd) : pr;
+      v = W[(long)ro * C + c];
+    }
+    tile[y][threadIdx.x] = v;
+    if (Wb && pr < R && c < ldw) Wb[(long)pr * ldw + c] = __float2bfloat16(v);
+  }
+  __syncthreads();
+  if (Wt) {
+    for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+      int c = c0 + y, pr = r0 + threadIdx.x;
+      if (c < C && pr < ldt) Wt[(long)c * ldt + pr] = __float2bfloat16(pr < R ? tile[threadIdx.x][y] : 0.f);
+    }
+  }
+}
+
+int weight_prep(const float* W, int R, int C, void* Wb, long ldw, void* Wt, long ldt, int perm_D, int perm_hd,
+                cudaStream_t st) {
+  // grid covers the padded extents so pad columns/rows are written as zeros
+  int cx = (int)(((Wb ? (ldw > C ? ldw : C) : C) + 31) / 32);
+  int ry = (int)(((Wt ? (ldt > R ? ldt : R) : R) + 31) / 32);
+  dim3 grid(cx, ry), block(32, 8);
+  weight_prep_kernel<<<grid, block, 0, st>>>(W, R, C, reinterpret_cast<__nv_bfloat16*>(Wb), ldw,
+                                             reinterpret_cast<__nv_bfloat16*>(Wt), ldt, perm_D, perm_hd);
+  GTOS_LAUNCH_CHECK();
+  return GTOS_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// z = res + dropout(x);  y = LayerNorm(z) * gamma + beta       (one warp per row, D <= 1024)
+// reference: generator/graph_transformer.py:57-58,64-65; transformer.py:56-57,63,70-71
+// ---------------------------------------------------------------------------------------
+constexpr int LN_MAX_PER_LANE = 32;
+
+__global__ void add_ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ res,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                  float* __restrict__ y, __nv_bfloat16* __restrict__ y_bf16, float* __restrict__ z_out,
+                                  float* __restrict__ mean_out, float* __restrict__ rstd_out, long rows, int D,
+                                  float p_drop, const unsigned long long* __restrict__ seed_ptr,
+                                  unsigned long long seed_off, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const unsigned long long seed = (p_drop > 0.f) ? (seed_ptr[0] + seed_off) : 0ull;
+  const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  float v[LN_MAX_PER_LANE];
+  float s = 0.f;
+  const int per = (D + 31) / 32;
+#pragma unroll
+  for (int t = 0; t < LN_MAX_PER_LANE; ++t) {
+    if (t < per) {
+      int c = t * 32 + lane;
+      float a = 0.f;
+      if (c < D) {
+        a = x[row * D + c];
+        if (p_drop > 0.f) a = (rng_uniform(seed, (unsigned long long)(row * D + c)) >= p_drop) ? a * keep_scale : 0.f;
+        if (res) a += res[row * D + c];
+      }
+      v[t] = a;
+      s += a;
+    }
+  }
+  const float mean = warp_sum(s) / D;
+  float q = 0.f;
+#pragma unroll
+  for (int t = 0; t < LN_MAX_PER_LANE; ++t) {
+    if (t < per) {
+      int c = t * 32 + lane;
+      float d = c < D ? v[t] - mean : 0.f;
+      q += d * d;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / D + eps);
+#pragma unroll
+  for (int t = 0; t < LN_MAX_PER_LANE; ++t) {
+    if (t < per) {
+      int c = t * 32 + lane;
+      if (c < D) {
+        float o = (v[t] - mean) * rstd * gamma[c] + beta[c];
+        y[row * D + c] = o;
+        if (y_bf16) y_bf16[row * D + c] = __float2bfloat16(o);
+        if (z_out) z_out[row * D + c] = v[t];
+      }
+    }
+  }
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+}
+
+int add_ln_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* y, void* y_bf16,
+               float* z, float* mean, float* rstd, long rows, int D, float p_drop, const void* seed_ptr,
+               unsigned long long seed_off, cudaStream_t st) {
+  GTOS_REQUIRE(D <= 32 * LN_MAX_PER_LANE, "LayerNorm width %d > %d unsupported", D, 32 * LN_MAX_PER_LANE);
+  GTOS_REQUIRE(p_drop == 0.f || seed_ptr, "dropout needs a device seed pointer");
+  if (rows == 0) return GTOS_OK;
+  const int wpb = 4;
+  add_ln_fwd_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(
+      x, res, gamma, beta, y, reinterpret_cast<__nv_bfloat16*>(y_bf16), z, mean, rstd, rows, D, p_drop,
+      reinterpret_cast<const unsigned long long*>(seed_ptr), seed_off, 1e-5f);
+  GTOS_LAUNCH_CHECK();
+  return GTOS_OK;
+}
+
+// backward: given dy, z (pre-norm), mean, rstd, gamma:
+//   xhat = (z-mean)*rstd ; g = dy*gamma ; dz = rstd*(g - mean(g) - xhat*mean(g*xhat))
+//   dres = dz ; dx = dz * dropmask/(1-p) ; dgamma += dy*xhat ; dbeta += dy   (atomics into zeroed [D])
+__global__ void add_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
+                                  const float* __restrict__ mean, const float* __restrict__ rstd,
+                                  const float* __restrict__ gamma, float* __restrict__ dres, float* __restrict__ dx,
+                                  __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma,
+                                  float* __restrict__ dbeta, long rows, int D, float p_drop,
+                                  const unsigned long long* __restrict__ seed_ptr, unsigned long long seed_off) {
+  extern __shared__ float sh[];  // [2][D] block partials of dgamma / dbeta
+  float* sg = sh;
+  float* sb = sh + D;
+  for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) sh[c] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const unsigned long long seed = (p_drop > 0.f) ? (seed_ptr[0] + seed_off) : 0ull;
+  const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  const int per = (D + 31) / 32;
+  for (long row = (long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long)gridDim.x * wpb) {
+    const float mu = mean[row], rs = rstd[row];
+    float g[LN_MAX_PER_LANE], xh[LN_MAX_PER_LANE];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int t = 0; t < LN_MAX_PER_LANE; ++t) {
+      if (t < per) {
+        int c = t * 32 + lane;
+        float gg = 0.f, xx = 0.f;
+        if (c < D) {
+          float d = dy[row * D + c];
+          xx = (z[row * D + c] - mu) * rs;
+          gg = d * gamma[c];
+          atomicAdd(&sg[c], d * xx);
+          atomicAdd(&sb[c], d);
+        }
+        g[t] = gg;
+        xh[t] = xx;
+        s1 += gg;
+        s2 += gg * xx;
+      }
+    }
+    s1 = warp_sum(s1) / D;
+    s2 = warp_sum(s2) / D;
+#pragma unroll
+    for (int t = 0; t < LN_MAX_PER_LANE; ++t) {
+      if (t < per) {
+        int c = t * 32 + lane;
+        if (c < D) {
+          float dz = rs * (g[t] - s1 - xh[t] * s2);
+          if (dres) dres[row * D + c] = dz;
+          float dxx = dz;
+          if (p_drop > 0.f)
+            dxx = (rng_uniform(seed, (unsigned long long)(row * D + c)) >= p_drop) ? dz * keep_scale : 0.f;
+          if (dx) dx[row * D + c] = dxx;
+          if (dx_bf16) dx_bf16[row * D + c] = __float2bfloat16(dxx);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    atomicAdd(&dgamma[c], sg[c]);
+    atomicAdd(&dbeta[c], sb[c]);
+  }
+}
+
+int add_ln_bwd(const float* dy, const float* z, const float* mean, const float* rstd, const float* gamma, float* dres,
+               float* dx, void* dx_bf16, float* dgamma, float* dbeta, long rows, int D, float p_drop,
+               const void* seed_ptr, unsigned long long seed_off, cudaStream_t st) {
+  GTOS_REQUIRE(D <= 32 * LN_MAX_PER_LANE, "LayerNorm width %d unsupported", D);
+  GTOS_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, sizeof(float) * D, st));
+  GTOS_CHECK_CUDA(cudaMemsetAsync(dbeta, 0, sizeof(float) * D, st));
+  if (rows == 0) return GTOS_OK;
+  const int wpb = 8;
+  long blocks = (rows + wpb - 1) / wpb;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  add_ln_bwd_kernel<<<(unsigned)blocks, wpb * 32, 2 * D * sizeof(float), st>>>(
+      dy, z, mean, rstd, gamma, dres, dx, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, rows, D, p_drop,
+      reinterpret_cast<const unsigned long long*>(seed_ptr), seed_off);
+  GTOS_LAUNCH_CHECK();
+  return GTOS_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// column sums: out[n] = sum_m x[m, n]  (bias gradients)
+// ---------------------------------------------------------------------------------------
+__global__ void colsum_kernel(const float* __restrict__ x, long ld, float* __restrict__ out, long rows, int cols,
+                              int rows_per_block) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  long r0 = (long)blockIdx.y * rows_per_block;
+  long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float s = 0.f;
+  for (long r = r0; r < r1; ++r) s += x[r * ld + c];
+  atomicAdd(&out[c], s);
+}
+
+__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long ld, float* __restrict__ out, long rows,
+                                   int cols, int rows_per_block) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  long r0 = (long)blockIdx.y * rows_per_block;
+  long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float s = 0.f;
+  for (long r = r0; r < r1; ++r) s += __bfloat162float(x[r * ld + c]);
+  atomicAdd(&out[c], s);
+}
+
+int colsum_bf16(const void* x, long ld, float* out, long rows, int cols, cudaStream_t st) {
+  GTOS_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, st));
+  if (rows == 0) return GTOS_OK;
+  int rpb = 64;
+  dim3 grid((cols + 127) / 128, (unsigned)((rows + rpb - 1) / rpb));
+  colsum_bf16_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, out, rows, cols, rpb);
+  GTOS_LAUNCH_CHECK();
+  return GTOS_OK;
+}
+
+int colsum(const float* x, long ld, float* out, long rows, int cols, cudaStream_t st) {
+  GTOS_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, st));
+  if (rows == 0) return GTOS_OK;
+  int rpb = 64;
+  dim3 grid((cols + 127) / 128, (unsigned)((rows + rpb - 1) / rpb));
+  colsum_kernel<<<grid, 128, 0, st>>>(x, ld, out, rows, cols, rpb);
+  GTOS_LAUNCH_CHECK();
+  return GTOS_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// elementwise dropout forward on a bf16 activation (FFN hidden), in place; and
+// dh = dh_in * (h > 0) * dropmask/(1-p) -> bf16 (+ optional fp32)      [ReLU/dropout backward]
+// ---------------------------------------------------------------------------------------
+__global__ void dropout_bf16_kernel(__nv_bfloat16* __restrict__ h, long n, float p, const unsigned long long* seed_ptr,
+                                    unsigned long long seed_off) {
+  const unsigned long long seed = seed_ptr[0] + seed_off;
+  const float ks = 1.f / (1.f - p);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    float v = __bfloat162float(h[i]);
+    h[i] = __float2bfloat16(rng_uniform(seed, (unsigned long long)i) >= p ? v * ks : 0.f);
+  }
+}
+
+int dropout_bf16(void* h, long n, float p, const void* seed_ptr, unsigned long long seed_off, cudaStream_t st) {
+  if (p <= 0.f || n == 0) return GTOS_OK;
+  GTOS_REQUIRE(seed_ptr, "dropout needs a device seed pointer");
+  long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  dropout_bf16_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(h), n, p,
+                                                        reinterpret_cast<const unsigned long long*>(seed_ptr), seed_off);
+  GTOS_LAUNCH_CHECK();
+  return GTOS_OK;
+}
+
+__global__ void dropout_f32_kernel(const float* __restrict__ x, float* __restrict__ out, long n, float p,
+                                   const unsigned long long* seed_ptr, unsigned long long seed_off) {
+  const unsigned long long seed = seed_ptr[0] + seed_off;
+  const float ks = 1.f / (1.f - p);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    out[i] = rng_uniform(seed, (unsigned long long)i) >= p ? x[i] * ks : 0.f;
+}
+
+int dropout_f32(const float* x, float* out, long n, float p, const void* seed_ptr, unsigned long long seed_off,
+                cudaStream_t st) {
+  if (n == 0) return GTOS_OK;
+  GTOS_REQUIRE(p > 0.f && p < 1.f && seed_ptr, "dropout_f32: need 0 < p < 1 and a device seed pointer");
+  long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  dropout_f32_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, out, n, p,
+                                                       reinterpret_cast<const unsigned long long*>(seed_ptr), seed_off);
+  GTOS_LAUNCH_CHECK();
+  return GTOS_OK;
+}
+
+// act = post-dropout hidden activation actually fed to fc2 (bf16): zero where relu OR dropout killed it
+__global__ void relu_drop_bwd_kernel(const float* __restrict__ dh_in, const __nv_bfloat16* __restrict__ act,
+                                     float* __restrict__ dh_f32, __nv_bfloat16* __restrict__ dh_bf16, long n, float p) {
+  const float ks = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    float v = (__bfloat162float(act[i]) > 0.f) ? dh_in[i] * ks : 0.f;
+    if (dh_f32) dh_f32[i] = v;
+    if (dh_bf16) dh_bf16[i] = __float2bfloat16(v);
+  }
+}
+
+int relu_drop_bwd(const float* dh_in, const void* act, float* dh_f32, void* dh_bf16, long n, float p,
+                  cudaStream_t st) {
+  if (n == 0) return GTOS_OK;
+  long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  relu_drop_bwd_kernel<<<(unsigned)blocks, 256, 0, st>>>(dh_in, reinterpret_cast<const __nv_bfloat16*>(act), dh_f32,
+                                                         reinterpret_cast<__nv_bfloat16*>(dh_bf16), n, p);
+  GTOS_LAUNCH_CHECK();
+  return GTOS_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// relation backward: dq[i,b,:] = sum_j G_x[(j,i,b)], dk[j,b,:] = sum_i G_y[(j,i,b)]
+// G is bf16 [tiles*128, 2D] in tile-major row order and head-interleaved column order
+// (per head: [d(q+ra) (hd) | d(k+rb) (hd)]).  Outputs are written into the [N*B, ld] grad buffer
+// of the fused QKV projection (dq at column 0, dk at column D).
+// ---------------------------------------------------------------------------------------
+__global__ void rel_dqk_kernel(const __nv_bfloat16* __restrict__ G, RelTiling rt, float* __restrict__ dq,
+                               float* __restrict__ dk, long ld) {
+  // block = (node index n, batch b); thread = feature f in [0, D); loops over the other node index
+  const int n = blockIdx.x, b = blockIdx.y;
+  const int D = rt.D, hd = rt.hd;
+  for (int f = threadIdx.x; f < D; f += blockDim.x) {
+    const int h = f / hd, w = f % hd;
+    const int colx = h * 2 * hd + w, coly = colx + hd;
+    float sq = 0.f, sk = 0.f;
+    // dq for query i = n: sum over keys j
+    {
+      const int ib = n / rt.bi, ii = n % rt.bi;
+      for (int j = 0; j < rt.N; ++j) {
+        const int jb = j / rt.bj, jj = j % rt.bj;
+        const long tile = ((long)b * rt.nj_blk + jb) * rt.ni_blk + ib;
+        sq += __bfloat162float(G[(tile * 128 + jj * rt.bi + ii) * (2L * D) + colx]);
+      }
+    }
+    // dk for key j = n: sum over queries i
+    {
+      const int jb = n / rt.bj, jj = n % rt.bj;
+      for (int i = 0; i < rt.N; ++i) {
+        const int ib = i / rt.bi, ii = i % rt.bi;
+        const long tile = ((long)b * rt.nj_blk + jb) * rt.ni_blk + ib;
+        sk += __bfloat162float(G[(tile * 128 + jj * rt.bi + ii) * (2L * D) + coly]);
+      }
+    }
+    dq[((long)n * rt.B + b) * ld + f] = sq;
+    dk[((long)n * rt.B + b) * ld + f] = sk;
+  }
+}
+
+int rel_dqk(const void* G, const RelTiling& rt, float* dq, float* dk, long ld, cudaStream_t st) {
+  dim3 grid(rt.N, rt.B);
+  int thr = rt.D < 256 ? rt.D : 256;
+  rel_dqk_kernel<<<grid, thr, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(G), rt, dq, dk, ld);
+  GTOS_LAUNCH_CHECK();
+  return GTOS_OK;
+}
+
+}  // namespace gtos

@@ -1,0 +1,70 @@
+// gtos_b200 -- declarations of the memory-bound helper kernels (elementwise.cu, attention.cu, gru.cu)
+#pragma once
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace gtos {
+
+int cast_f32_bf16(const float* src, long lds, void* dst, long ldd, long rows, int cols, cudaStream_t st);
+int weight_prep(const float* W, int R, int C, void* Wb, long ldw, void* Wt, long ldt, int perm_D, int perm_hd,
+                cudaStream_t st);
+int add_ln_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* y, void* y_bf16,
+               float* z, float* mean, float* rstd, long rows, int D, float p_drop, const void* seed_ptr,
+               unsigned long long seed_off, cudaStream_t st);
+int add_ln_bwd(const float* dy, const float* z, const float* mean, const float* rstd, const float* gamma, float* dres,
+               float* dx, void* dx_bf16, float* dgamma, float* dbeta, long rows, int D, float p_drop,
+               const void* seed_ptr, unsigned long long seed_off, cudaStream_t st);
+int colsum(const float* x, long ld, float* out, long rows, int cols, cudaStream_t st);
+int colsum_bf16(const void* x, long ld, float* out, long rows, int cols, cudaStream_t st);
+int dropout_bf16(void* h, long n, float p, const void* seed_ptr, unsigned long long seed_off, cudaStream_t st);
+int dropout_f32(const float* x, float* out, long n, float p, const void* seed_ptr, unsigned long long seed_off,
+                cudaStream_t st);
+int relu_drop_bwd(const float* dh_in, const void* act, float* dh_f32, void* dh_bf16, long n, float p, cudaStream_t st);
+int rel_dqk(const void* G, const RelTiling& rt, float* dq, float* dk, long ld, cudaStream_t st);
+
+// ---- attention core (attention.cu) ------------------------------------------------------
+struct AttnArgs {
+  int T, S, B, H, hd;
+  // projections, fp32, element (t, b, h, d) at ptr[(t*B + b)*ld + h*hd + d]
+  const float* q; long ldq;     // unscaled; `scale` applied inside (null in encoder mode)
+  const float* k; long ldk;
+  const float* v; long ldv;
+  float scale;
+  // encoder mode: scores precomputed by the fused relation kernel, layout [B,H,S(j),T(i)]
+  const float* scores_jt;
+  const unsigned char* key_pad;   // [S,B] 1 = padding, or null
+  const unsigned char* attn_mask; // [T,S] 1 = blocked, or null
+  float p_drop;                   // dropout on the attention weights (weights_dropout=True)
+  const void* seed_ptr; unsigned long long seed_off;
+  float* probs;                   // [B,H,T,S] softmax (pre-dropout), saved for backward
+  float* probs_dropped;           // optional [B,H,T,S] post-dropout weights (need_weights)
+  float* out; long ldo;           // [T,B,H*hd] fp32
+  void* out_bf16;                 // optional bf16 copy (same ld)
+};
+int attn_fwd(const AttnArgs& a, cudaStream_t st);
+
+struct AttnBwdArgs {
+  AttnArgs f;                     // forward description (q,k,v,probs,masks,...)
+  const float* dout; long lddo;   // [T,B,H*hd]
+  const float* dprobs_extra;      // optional gradient wrt returned (post-dropout) weights [B,H,T,S]
+  float* dscores_jt;              // encoder mode out: [B,H,S(j),T(i)]
+  float* dscores_ts;              // scratch/out [B,H,T,S] (always written)
+  float* dq; long lddq;           // decoder mode outs
+  float* dk; long lddk;
+  float* dv; long lddv;
+};
+int attn_bwd(const AttnBwdArgs& a, cudaStream_t st);
+
+// ---- GRU gate kernels (gru.cu) ------------------------------------------------------------
+int gru_gate_fwd(const float* gi, long ldgi, const float* gh, long ldgh, const float* h_prev, const long long* lengths,
+                 int t, float* h_new, void* h_new_bf16, float* out_t, long ldout, void* out_t_bf16, long ldoutb,
+                 float* gates, long R, int Hh, cudaStream_t st);
+int gru_gate_bwd(const float* dh, const float* dout_t, long lddout, const float* gates, const float* gh, long ldgh,
+                 const float* h_prev, const long long* lengths, int t, float* dh_prev, void* dgi_bf16, long lddgi,
+                 void* dgh_bf16, long lddgh, long R, int Hh, cudaStream_t st);
+int embed_gather(const float* table, const long long* idx, long n, int dim, float* out_f32, void* out_bf16, long ldb,
+                 float p_drop, const void* seed_ptr, unsigned long long seed_off, cudaStream_t st);
+int embed_scatter_add(const float* dx, const long long* idx, long n, int dim, float* dtable, float p_drop,
+                      const void* seed_ptr, unsigned long long seed_off, cudaStream_t st);
+
+}  // namespace gtos

@@ -1,0 +1,741 @@
+// gtos_b200 -- warp-specialised tcgen05 GEMMs for sm_100a.
+//
+//   gemm_tn_kernel<BN, MODE>   C[128 x BN tile] = A[M,K] * B[N,K]^T, bf16 operands staged by TMA
+//                              (128B swizzle, K-major), fp32 accumulators double-buffered in TMEM.
+//        warp 0    : TMA producer (one elected lane)
+//        warp 1    : TMEM allocator + tcgen05.mma issuer (one lane)
+//        warps 2-5 : epilogue, each owns the TMEM lane quarter (warp_idx % 4)
+//     MODE_SCORE / MODE_GRAD are the fused relation-attention kernels: A tiles are 4-D TMA boxes
+//     of relation[j][i][b][:], B is the head-interleaved relation_in_proj weight, and the
+//     epilogue combines the ra/rb accumulators with q_i / k_j slices that the producer also
+//     stages through TMA (reference: generator/graph_transformer.py:122-133).
+//
+//   gemm_nn_kernel<BN, REL>    C[M,N] = sum_k A[k,m] B[k,n] with MN-major UMMA descriptors
+//                              (weight gradients: contraction over rows), split-K partials.
+#include "gemm.cuh"
+
+namespace gtos {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;  // bf16 elements per k-block = one 128-byte swizzle row
+static constexpr int A_STAGE_BYTES = BM * BK * 2;
+static constexpr int GEMM_THREADS = 192;
+static constexpr int MAX_STAGES = 8;
+static constexpr uint64_t WATCHDOG_CYCLES = 8000000000ull;  // ~4 s: turn a pipeline hang into a trap
+
+struct PipeBars {
+  uint64_t full[MAX_STAGES];
+  uint64_t empty[MAX_STAGES];
+  uint64_t tfull[2];
+  uint64_t tempty[2];
+  uint64_t qfull[2];
+  uint64_t qempty[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+__device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  unsigned long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > WATCHDOG_CYCLES) {
+      printf("gtos_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+struct TnDev {
+  int M, N, K;
+  int m_tiles, n_tiles, k_blocks, units;
+  int stages;
+  const float* bias;
+  float* out_f32;
+  long ldo;
+  __nv_bfloat16* out_bf16;
+  long ldob;
+  int relu, accumulate;
+  RelTiling rt;
+  float* scores;
+  const float* dscores;
+  __nv_bfloat16* G;
+  int bi8, bj8;        // q / k box rows rounded up to 8 (1024-byte swizzle atoms)
+  int qk_stage_bytes;  // 4*(bi8+bj8)*128
+};
+
+__device__ __forceinline__ void rel_tile_decode(const RelTiling& t, int tile, int& b, int& j0, int& i0) {
+  int ib = tile % t.ni_blk;
+  int r = tile / t.ni_blk;
+  int jb = r % t.nj_blk;
+  b = r / t.nj_blk;
+  i0 = ib * t.bi;
+  j0 = jb * t.bj;
+}
+
+// 16 fp32 from a 128B-swizzled [rows x 32 float] TMA box: row `row`, floats [f0, f0+16), f0 % 16 == 0
+__device__ __forceinline__ void lds_sw128_16(const uint8_t* box, int row, int f0, float* out) {
+  const uint8_t* rp = box + row * 128;
+  int c0 = f0 >> 2;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    float4 v = *reinterpret_cast<const float4*>(rp + (((c0 + t) ^ (row & 7)) << 4));
+    out[4 * t + 0] = v.x;
+    out[4 * t + 1] = v.y;
+    out[4 * t + 2] = v.z;
+    out[4 * t + 3] = v.w;
+  }
+}
+
+template <int BN, int MODE>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const TnDev p) {
+  constexpr bool REL = (MODE == MODE_SCORE || MODE == MODE_GRAD);
+  constexpr int B_STAGE_BYTES = BN * BK * 2;
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  constexpr uint32_t IDESC = make_idesc_bf16(BM, BN, 0, 0);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* qk_base = smem + p.stages * STAGE_BYTES;
+  PipeBars* bars = reinterpret_cast<PipeBars*>(qk_base + (REL ? 2 * p.qk_stage_bytes : 0));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (REL) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmK);
+    }
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars->tfull[s], 1);
+      mbar_init(&bars->tempty[s], 4);
+      mbar_init(&bars->qfull[s], 1);
+      mbar_init(&bars->qempty[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&bars->tmem_base, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      int qs = 0;
+      uint32_t qph = 0;
+      for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
+        const int m_blk = unit / p.n_tiles, n_blk = unit % p.n_tiles;
+        int b = 0, j0 = 0, i0 = 0;
+        if (REL) {
+          rel_tile_decode(p.rt, m_blk, b, j0, i0);
+          // q / k slices for this (tile, head group): dims [n_blk*BN/2, +BN/2)
+          wait_bar(&bars->qempty[qs], qph ^ 1);
+          mbar_expect_tx(&bars->qfull[qs], (uint32_t)((BN / 64) * (p.rt.bi + p.rt.bj) * 128));
+          uint8_t* qb = qk_base + qs * p.qk_stage_bytes;
+          const int d0 = n_blk * (BN / 2);
+#pragma unroll
+          for (int c = 0; c < BN / 64; ++c) {
+            tma_load_3d(&tmQ, &bars->qfull[qs], qb + c * p.bi8 * 128, d0 + c * 32, b, i0);
+            tma_load_3d(&tmK, &bars->qfull[qs], qb + (BN / 64) * p.bi8 * 128 + c * p.bj8 * 128, d0 + c * 32, b, j0);
+          }
+          if (++qs == 2) { qs = 0; qph ^= 1; }
+        }
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          wait_bar(&bars->empty[s], ph ^ 1);
+          uint8_t* sa = smem + s * STAGE_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          if (REL) {
+            mbar_expect_tx(&bars->full[s], (uint32_t)(p.rt.bi * p.rt.bj * 128 + B_STAGE_BYTES));
+            tma_load_4d(&tmA, &bars->full[s], sa, kb * BK, b, i0, j0);
+          } else {
+            mbar_expect_tx(&bars->full[s], (uint32_t)STAGE_BYTES);
+            tma_load_2d(&tmA, &bars->full[s], sa, kb * BK, m_blk * BM);
+          }
+          tma_load_2d(&tmB, &bars->full[s], sb, kb * BK, n_blk * BN);
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      int as = 0;
+      uint32_t aph = 0;
+      for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
+        wait_bar(&bars->tempty[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + as * BN;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          wait_bar(&bars->full[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+          const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(sa + A_STAGE_BYTES, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes inside the 128B swizzle row: +2 in the (addr>>4) field
+            umma_bf16(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&bars->empty[s]);
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&bars->tfull[as]);
+        if (++as == 2) { as = 0; aph ^= 1; }
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..5) =================
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;  // accumulator row == TMEM lane
+    int as = 0;
+    uint32_t aph = 0;
+    int qs = 0;
+    uint32_t qph = 0;
+    for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
+      const int m_blk = unit / p.n_tiles, n_blk = unit % p.n_tiles;
+      wait_bar(&bars->tfull[as], aph);
+      if (REL) wait_bar(&bars->qfull[qs], qph);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + as * BN + ((uint32_t)(quarter * 32) << 16);
+
+      if constexpr (MODE == MODE_PLAIN || MODE == MODE_DREL) {
+        long out_row = (long)m_blk * BM + r;
+        bool row_ok = out_row < p.M;
+        if constexpr (MODE == MODE_DREL) {
+          int b, j0, i0;
+          rel_tile_decode(p.rt, m_blk, b, j0, i0);
+          int jj = r / p.rt.bi, ii = r - jj * p.rt.bi;
+          int i = i0 + ii, j = j0 + jj;
+          row_ok = (jj < p.rt.bj) && (i < p.rt.N) && (j < p.rt.N);
+          out_row = ((long)j * p.rt.N + i) * p.rt.B + b;
+        }
+        const int n0 = n_blk * BN;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 16) {
+          if (n0 + c >= p.N) break;
+          float v[16];
+          tmem_ld16(tacc + c, v);
+          tmem_ld_wait();
+          const int n = n0 + c;
+          if (row_ok) {
+            if (p.bias) {
+#pragma unroll
+              for (int t = 0; t < 16; ++t)
+                if (n + t < p.N) v[t] += __ldg(p.bias + n + t);
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int t = 0; t < 16; ++t) v[t] = fmaxf(v[t], 0.f);
+            }
+            const bool full = (n + 16 <= p.N);
+            if (p.out_f32) {
+              float* o = p.out_f32 + out_row * p.ldo + n;
+              if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  float4 w = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
+                  if (p.accumulate) {
+                    float4 old = *reinterpret_cast<float4*>(o + 4 * t);
+                    w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w;
+                  }
+                  *reinterpret_cast<float4*>(o + 4 * t) = w;
+                }
+              } else {
+#pragma unroll
+                for (int t = 0; t < 16; ++t)
+                  if (n + t < p.N) o[t] = p.accumulate ? o[t] + v[t] : v[t];
+              }
+            }
+            if (p.out_bf16) {
+              __nv_bfloat16* o = p.out_bf16 + out_row * p.ldob + n;
+              if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                uint4 w0 = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                      pack_bf16x2(v[6], v[7]));
+                uint4 w1 = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]),
+                                      pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+                *reinterpret_cast<uint4*>(o) = w0;
+                *reinterpret_cast<uint4*>(o + 8) = w1;
+              } else {
+#pragma unroll
+                for (int t = 0; t < 16; ++t)
+                  if (n + t < p.N) o[t] = __float2bfloat16(v[t]);
+              }
+            }
+          }
+        }
+      } else {
+        // ---- relation epilogues: thread owns pair (j0+jj, i0+ii, b) ----
+        int b, j0, i0;
+        rel_tile_decode(p.rt, m_blk, b, j0, i0);
+        const int bi = p.rt.bi;
+        const int jj = r / bi, ii = r - jj * bi;
+        const int i = i0 + ii, j = j0 + jj;
+        const bool valid = (jj < p.rt.bj) && (i < p.rt.N) && (j < p.rt.N);
+        const int jjc = jj < p.rt.bj ? jj : p.rt.bj - 1;  // keep smem reads inside the k boxes
+        const uint8_t* qb = qk_base + qs * p.qk_stage_bytes;
+        const uint8_t* kbx = qb + (BN / 64) * p.bi8 * 128;
+        const int hd = p.rt.hd;
+        const int heads_blk = (BN / 2) / hd;
+#pragma unroll 1
+        for (int hh = 0; hh < heads_blk; ++hh) {
+          const int h = n_blk * heads_blk + hh;
+          const long sidx = (((long)b * p.rt.H + h) * p.rt.N + j) * p.rt.N + i;
+          float acc = 0.f;
+          float g = 0.f;
+          if constexpr (MODE == MODE_GRAD) g = valid ? p.dscores[sidx] * p.rt.scale : 0.f;
+#pragma unroll 1
+          for (int c = 0; c < hd; c += 16) {
+            float ra[16], rb[16], qv[16], kv[16];
+            tmem_ld16(tacc + hh * 2 * hd + c, ra);
+            tmem_ld16(tacc + hh * 2 * hd + hd + c, rb);
+            const int dl = hh * hd + c;  // dim inside this unit's BN/2-wide slice
+            lds_sw128_16(qb + (dl >> 5) * p.bi8 * 128, ii, dl & 31, qv);
+            lds_sw128_16(kbx + (dl >> 5) * p.bj8 * 128, jjc, dl & 31, kv);
+            tmem_ld_wait();
+            if constexpr (MODE == MODE_SCORE) {
+#pragma unroll
+              for (int t = 0; t < 16; ++t) acc = fmaf(qv[t] + ra[t], kv[t] + rb[t], acc);
+            } else {
+              // G columns (permuted order): [d(q+ra) = g*(k+rb) | d(k+rb) = g*(q+ra)]
+              uint32_t wx[8], wy[8];
+#pragma unroll
+              for (int t = 0; t < 8; ++t) {
+                float x0 = qv[2 * t] + ra[2 * t], x1 = qv[2 * t + 1] + ra[2 * t + 1];
+                float y0 = kv[2 * t] + rb[2 * t], y1 = kv[2 * t + 1] + rb[2 * t + 1];
+                wx[t] = valid ? pack_bf16x2(g * y0, g * y1) : 0u;
+                wy[t] = valid ? pack_bf16x2(g * x0, g * x1) : 0u;
+              }
+              __nv_bfloat16* grow = p.G + ((long)m_blk * BM + r) * (2 * p.rt.D) + (long)n_blk * BN + hh * 2 * hd + c;
+              *reinterpret_cast<uint4*>(grow) = make_uint4(wx[0], wx[1], wx[2], wx[3]);
+              *reinterpret_cast<uint4*>(grow + 8) = make_uint4(wx[4], wx[5], wx[6], wx[7]);
+              *reinterpret_cast<uint4*>(grow + hd) = make_uint4(wy[0], wy[1], wy[2], wy[3]);
+              *reinterpret_cast<uint4*>(grow + hd + 8) = make_uint4(wy[4], wy[5], wy[6], wy[7]);
+            }
+          }
+          if constexpr (MODE == MODE_SCORE) {
+            if (valid) p.scores[sidx] = acc * p.rt.scale;
+          }
+        }
+      }
+
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&bars->tempty[as]);
+        if (REL) mbar_arrive(&bars->qempty[qs]);
+      }
+      if (++as == 2) { as = 0; aph ^= 1; }
+      if (REL) { if (++qs == 2) { qs = 0; qph ^= 1; } }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+int choose_rel_tiling(RelTiling* t, int N, int B, int D, int H) {
+  if (N <= 0 || B <= 0 || D <= 0 || H <= 0 || D % H != 0) {
+    set_error("bad relation-attention shape N=%d B=%d D=%d H=%d", N, B, D, H);
+    return GTOS_ERR_ARG;
+  }
+  int hd = D / H;
+  if (D % 128 != 0 || !(hd == 16 || hd == 32 || hd == 64 || hd == 128)) {
+    set_error("relation attention needs D %% 128 == 0 and head_dim in {16,32,64,128} (got D=%d hd=%d)", D, hd);
+    return GTOS_ERR_UNSUPPORTED;
+  }
+  long best_tiles = -1;
+  int best_bi = 1, best_bj = 1;
+  for (int bi = 1; bi <= 128 && bi <= N; ++bi) {
+    for (int bj = 1; bj * bi <= 128 && bj <= N; ++bj) {
+      int bi8 = (bi + 7) & ~7, bj8 = (bj + 7) & ~7;
+      if (bi8 + bj8 > 48) continue;  // q/k staging budget: 4*(bi8+bj8)*128 B per stage <= 24 KB
+      long tiles = (long)((N + bi - 1) / bi) * ((N + bj - 1) / bj);
+      if (best_tiles < 0 || tiles < best_tiles || (tiles == best_tiles && bi + bj < best_bi + best_bj)) {
+        best_tiles = tiles;
+        best_bi = bi;
+        best_bj = bj;
+      }
+    }
+  }
+  t->N = N; t->B = B; t->D = D; t->H = H; t->hd = hd;
+  t->bi = best_bi; t->bj = best_bj;
+  t->ni_blk = (N + best_bi - 1) / best_bi;
+  t->nj_blk = (N + best_bj - 1) / best_bj;
+  t->tiles = B * t->ni_blk * t->nj_blk;
+  t->scale = 1.0f / sqrtf((float)hd);
+  return GTOS_OK;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+int make_rel_tmaps(const RelTiling& rt, const void* relb, const float* q, const float* k, long ldqk,
+                   CUtensorMap* tmA, CUtensorMap* tmQ, CUtensorMap* tmK) {
+  {
+    uint64_t dims[4] = {(uint64_t)rt.D, (uint64_t)rt.B, (uint64_t)rt.N, (uint64_t)rt.N};
+    uint64_t str[4] = {0, (uint64_t)rt.D * 2, (uint64_t)rt.B * rt.D * 2, (uint64_t)rt.N * rt.B * rt.D * 2};
+    uint32_t box[4] = {64, 1, (uint32_t)rt.bi, (uint32_t)rt.bj};
+    int e = make_tmap_nd(tmA, relb, 2, 4, dims, str, box, true);
+    if (e) return e;
+  }
+  if (q) {
+    uint64_t dims[3] = {(uint64_t)rt.D, (uint64_t)rt.B, (uint64_t)rt.N};
+    uint64_t str[3] = {0, (uint64_t)ldqk * 4, (uint64_t)rt.B * ldqk * 4};
+    uint32_t boxq[3] = {32, 1, (uint32_t)rt.bi};
+    uint32_t boxk[3] = {32, 1, (uint32_t)rt.bj};
+    int e = make_tmap_nd(tmQ, q, 4, 3, dims, str, boxq, true);
+    if (e) return e;
+    e = make_tmap_nd(tmK, k, 4, 3, dims, str, boxk, true);
+    if (e) return e;
+  }
+  return GTOS_OK;
+}
+
+template <int BN, int MODE>
+static int launch_tn(const GemmTnArgs& a, cudaStream_t stream) {
+  constexpr bool REL = (MODE == MODE_SCORE || MODE == MODE_GRAD);
+  TnDev p;
+  memset(&p, 0, sizeof(p));
+  p.M = a.M; p.N = a.N; p.K = a.K;
+  p.n_tiles = (a.N + BN - 1) / BN;
+  p.k_blocks = (a.K + BK - 1) / BK;
+  p.bias = a.bias; p.out_f32 = a.out_f32; p.ldo = a.ldo;
+  p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a.out_bf16); p.ldob = a.ldob;
+  p.relu = a.relu; p.accumulate = a.accumulate;
+  p.rt = a.rt; p.scores = a.scores; p.dscores = a.dscores; p.G = reinterpret_cast<__nv_bfloat16*>(a.G);
+  CUtensorMap tmA, tmB, tmQ, tmK;
+  int e;
+  if (REL) {
+    p.m_tiles = a.rt.tiles;
+    p.bi8 = (a.rt.bi + 7) & ~7;
+    p.bj8 = (a.rt.bj + 7) & ~7;
+    p.qk_stage_bytes = (BN / 64) * (p.bi8 + p.bj8) * 128;
+    e = make_rel_tmaps(a.rt, a.A, a.q, a.k, a.ldqk, &tmA, &tmQ, &tmK);
+    if (e) return e;
+  } else {
+    p.m_tiles = (MODE == MODE_DREL) ? a.rt.tiles : (a.M + BM - 1) / BM;
+    e = make_tmap_2d_bf16(&tmA, a.A, (uint64_t)a.M, (uint64_t)a.K, (uint64_t)a.lda, BM);
+    if (e) return e;
+    tmQ = tmA;
+    tmK = tmA;
+  }
+  e = make_tmap_2d_bf16(&tmB, a.Bm, (uint64_t)a.N, (uint64_t)a.K, (uint64_t)a.ldb, BN);
+  if (e) return e;
+  p.units = p.m_tiles * p.n_tiles;
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + BN * BK * 2;
+  const int budget = 227 * 1024 - 1024 /*align*/ - (int)sizeof(PipeBars) - (REL ? 2 * p.qk_stage_bytes : 0);
+  int stages = budget / STAGE_BYTES;
+  if (stages > 6) stages = 6;
+  if (stages < 2) {
+    set_error("not enough shared memory for the GEMM pipeline");
+    return GTOS_ERR_UNSUPPORTED;
+  }
+  p.stages = stages;
+  const int smem_bytes = 1024 + stages * STAGE_BYTES + (REL ? 2 * p.qk_stage_bytes : 0) + (int)sizeof(PipeBars);
+  auto kern = gemm_tn_kernel<BN, MODE>;
+  GTOS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  int grid = p.units < num_sms() ? p.units : num_sms();
+  if (grid <= 0) return GTOS_OK;
+  kern<<<grid, GEMM_THREADS, smem_bytes, stream>>>(tmA, tmB, tmQ, tmK, p);
+  GTOS_LAUNCH_CHECK();
+  return GTOS_OK;
+}
+
+int launch_gemm_tn(int mode, const GemmTnArgs& a, cudaStream_t stream) {
+  GTOS_REQUIRE(a.K % 8 == 0 && a.lda % 8 == 0 && a.ldb % 8 == 0, "gemm_tn: K, lda, ldb must be multiples of 8 (K=%d lda=%ld ldb=%ld)",
+               a.K, a.lda, a.ldb);
+  if (mode == MODE_SCORE) return launch_tn<256, MODE_SCORE>(a, stream);
+  if (mode == MODE_GRAD) return launch_tn<256, MODE_GRAD>(a, stream);
+  if (mode == MODE_DREL) return launch_tn<256, MODE_DREL>(a, stream);
+  // plain: pick the widest N tile that still gives every SM a tile
+  const long mt = (a.M + BM - 1) / BM;
+  const int sms = num_sms();
+  if (a.N > 128 && mt * ((a.N + 255) / 256) >= sms) return launch_tn<256, MODE_PLAIN>(a, stream);
+  if (a.N > 64 && mt * ((a.N + 127) / 128) >= sms) return launch_tn<128, MODE_PLAIN>(a, stream);
+  return launch_tn<64, MODE_PLAIN>(a, stream);
+}
+
+// =======================================================================================
+// gemm_nn: C[M,N] = sum_k A[k,m] * B[k,n]   (contraction over rows; both operands MN-major)
+// =======================================================================================
+struct NnDev {
+  int M, N, Kd;
+  int m_tiles, n_tiles, k_blocks, splits, kb_per_split;
+  int stages;
+  float* ws;  // [splits][M][N]
+  RelTiling rt;
+};
+
+template <int BN, int KB, int REL>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const NnDev p) {
+  // smem stage: A = (BM/64) boxes of [KB rows x 128 B]; B = (BN/64) boxes of [KB rows x 128 B]
+  constexpr int BOX_BYTES = KB * 128;
+  constexpr int A_BYTES = (BM / 64) * BOX_BYTES;
+  constexpr int B_BYTES = (BN / 64) * BOX_BYTES;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  constexpr uint32_t IDESC = make_idesc_bf16(BM, BN, 1, 1);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  PipeBars* bars = reinterpret_cast<PipeBars*>(smem + p.stages * STAGE_BYTES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tile = blockIdx.x;
+  const int m_blk = tile / p.n_tiles, n_blk = tile % p.n_tiles;
+  const int split = blockIdx.y;
+  const int kb0 = split * p.kb_per_split;
+  int kb1 = kb0 + p.kb_per_split;
+  if (kb1 > p.k_blocks) kb1 = p.k_blocks;
+
+  if (REL) {
+    // relation tiles carry only bi*bj (< 128) rows per k-block: rows the TMA box never writes must be 0
+    uint4 z = make_uint4(0, 0, 0, 0);
+    for (int o = threadIdx.x * 16; o < p.stages * STAGE_BYTES; o += GEMM_THREADS * 16)
+      *reinterpret_cast<uint4*>(smem + o) = z;
+    fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->empty[s], 1);
+    }
+    mbar_init(&bars->tfull[0], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&bars->tmem_base, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        wait_bar(&bars->empty[s], ph ^ 1);
+        uint8_t* sa = smem + s * STAGE_BYTES;
+        uint8_t* sb = sa + A_BYTES;
+        int b = 0, j0 = 0, i0 = 0;
+        uint32_t bbytes = B_BYTES;
+        if (REL) {
+          rel_tile_decode(p.rt, kb, b, j0, i0);
+          bbytes = (uint32_t)((BN / 64) * p.rt.bi * p.rt.bj * 128);
+        }
+        mbar_expect_tx(&bars->full[s], (uint32_t)A_BYTES + bbytes);
+#pragma unroll
+        for (int c = 0; c < BM / 64; ++c) tma_load_2d(&tmA, &bars->full[s], sa + c * BOX_BYTES, m_blk * BM + c * 64, kb * KB);
+#pragma unroll
+        for (int c = 0; c < BN / 64; ++c) {
+          if (REL)
+            tma_load_4d(&tmB, &bars->full[s], sb + c * BOX_BYTES, n_blk * BN + c * 64, b, i0, j0);
+          else
+            tma_load_2d(&tmB, &bars->full[s], sb + c * BOX_BYTES, n_blk * BN + c * 64, kb * KB);
+        }
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        wait_bar(&bars->full[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+        // MN-major, 128B swizzle: LBO = next 64-element chunk along M/N (one box), SBO = next 8 k-rows
+        const uint64_t da = make_smem_desc_sw128(sa, BOX_BYTES, 1024);
+        const uint64_t db = make_smem_desc_sw128(sa + A_BYTES, BOX_BYTES, 1024);
+#pragma unroll
+        for (int k = 0; k < KB / 16; ++k) {
+          // 16 k-rows = 2048 bytes = +128 in the (addr>>4) field
+          umma_bf16(tmem_base, da + (uint64_t)(128 * k), db + (uint64_t)(128 * k), IDESC,
+                    (kb > kb0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&bars->empty[s]);
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+      umma_commit(&bars->tfull[0]);
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const bool any = kb1 > kb0;
+    if (any) {
+      wait_bar(&bars->tfull[0], 0);
+      tc_fence_after();
+    }
+    const uint32_t tacc = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const long m = (long)m_blk * BM + r;
+    float* wrow = p.ws + ((long)split * p.M + m) * p.N + (long)n_blk * BN;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 16) {
+      if (n_blk * BN + c >= p.N) break;
+      float v[16];
+      if (any) {
+        tmem_ld16(tacc + c, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int t = 0; t < 16; ++t) v[t] = 0.f;
+      }
+      if (m < p.M) {
+        const int n = n_blk * BN + c;
+        if (n + 16 <= p.N && ((reinterpret_cast<uintptr_t>(wrow + c) & 15) == 0)) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            *reinterpret_cast<float4*>(wrow + c + 4 * t) = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
+        } else {
+#pragma unroll
+          for (int t = 0; t < 16; ++t)
+            if (n + t < p.N) wrow[c + t] = v[t];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ out, long ldo, int M, int N,
+                                     int splits, int rel_D, int rel_hd) {
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long total = (long)M * N;
+  if (idx >= total) return;
+  int m = (int)(idx / N), n = (int)(idx % N);
+  float s = 0.f;
+  for (int k = 0; k < splits; ++k) s += ws[(long)k * total + idx];
+  int mo = rel_D ? rel_perm_to_orig(m, rel_D, rel_hd) : m;
+  out[(long)mo * ldo + n] = s;
+}
+
+static void nn_plan(int M, int N, int Kd, int rel, int* BN, int* KB, int* splits, int* kb_per) {
+  *BN = (N >= 256) ? 256 : ((N > 64 || rel) ? 128 : 64);
+  *KB = rel ? 128 : 64;
+  int tiles = ((M + BM - 1) / BM) * ((N + *BN - 1) / *BN);
+  int kblocks = (Kd + *KB - 1) / *KB;
+  int want = (num_sms() + tiles - 1) / tiles;
+  if (want > kblocks) want = kblocks;
+  if (want < 1) want = 1;
+  int per = (kblocks + want - 1) / want;
+  if (per < 1) per = 1;
+  *kb_per = per;
+  *splits = (kblocks + per - 1) / per;
+  if (*splits < 1) *splits = 1;
+}
+
+long gemm_nn_workspace_elems(int M, int N, int Kd, int rel) {
+  int BN, KB, splits, per;
+  nn_plan(M, N, Kd, rel, &BN, &KB, &splits, &per);
+  return (long)splits * M * N;
+}
+
+template <int BN, int KB, int REL>
+static int launch_nn(const GemmNnArgs& a, int splits, int per, cudaStream_t stream) {
+  NnDev p;
+  memset(&p, 0, sizeof(p));
+  p.M = a.M; p.N = a.N; p.Kd = a.Kd;
+  p.m_tiles = (a.M + BM - 1) / BM;
+  p.n_tiles = (a.N + BN - 1) / BN;
+  p.k_blocks = (a.Kd + KB - 1) / KB;
+  p.splits = splits; p.kb_per_split = per;
+  p.ws = a.workspace; p.rt = a.rt;
+  CUtensorMap tmA, tmB;
+  int e;
+  {
+    uint64_t dims[2] = {(uint64_t)a.M, (uint64_t)a.Kd};
+    uint64_t str[2] = {0, (uint64_t)a.lda * 2};
+    uint32_t box[2] = {64, (uint32_t)KB};
+    e = make_tmap_nd(&tmA, a.A, 2, 2, dims, str, box, true);
+    if (e) return e;
+  }
+  if (REL) {
+    const RelTiling& rt = a.rt;
+    uint64_t dims[4] = {(uint64_t)rt.D, (uint64_t)rt.B, (uint64_t)rt.N, (uint64_t)rt.N};
+    uint64_t str[4] = {0, (uint64_t)rt.D * 2, (uint64_t)rt.B * rt.D * 2, (uint64_t)rt.N * rt.B * rt.D * 2};
+    uint32_t box[4] = {64, 1, (uint32_t)rt.bi, (uint32_t)rt.bj};
+    e = make_tmap_nd(&tmB, a.Bm, 2, 4, dims, str, box, true);
+  } else {
+    uint64_t dims[2] = {(uint64_t)a.N, (uint64_t)a.Kd};
+    uint64_t str[2] = {0, (uint64_t)a.ldb * 2};
+    uint32_t box[2] = {64, (uint32_t)KB};
+    e = make_tmap_nd(&tmB, a.Bm, 2, 2, dims, str, box, true);
+  }
+  if (e) return e;
+  constexpr int STAGE_BYTES = (BM / 64 + BN / 64) * KB * 128;
+  int stages = (227 * 1024 - 1024 - (int)sizeof(PipeBars)) / STAGE_BYTES;
+  if (stages > 6) stages = 6;
+  if (stages < 2) {
+    set_error("gemm_nn: pipeline does not fit in shared memory");
+    return GTOS_ERR_UNSUPPORTED;
+  }
+  p.stages = stages;
+  const int smem_bytes = 1024 + stages * STAGE_BYTES + (int)sizeof(PipeBars);
+  auto kern = gemm_nn_kernel<BN, KB, REL>;
+  GTOS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  dim3 grid(p.m_tiles * p.n_tiles, splits);
+  kern<<<grid, GEMM_THREADS, smem_bytes, stream>>>(tmA, tmB, p);
+  GTOS_LAUNCH_CHECK();
+  long total = (long)a.M * a.N;
+  int thr = 256;
+  splitk_reduce_kernel<<<(unsigned)((total + thr - 1) / thr), thr, 0, stream>>>(
+      a.workspace, a.out, a.ldo, a.M, a.N, splits, a.rel ? a.rt.D : 0, a.rel ? a.rt.hd : 0);
+  GTOS_LAUNCH_CHECK();
+  return GTOS_OK;
+}
+
+int launch_gemm_nn(const GemmNnArgs& a, cudaStream_t stream) {
+  GTOS_REQUIRE(a.lda % 8 == 0 && (a.rel || a.ldb % 8 == 0), "gemm_nn: lda/ldb must be multiples of 8");
+  int BN, KB, splits, per;
+  nn_plan(a.M, a.N, a.Kd, a.rel, &BN, &KB, &splits, &per);
+  GTOS_REQUIRE(a.workspace_elems >= (long)splits * a.M * a.N, "gemm_nn: workspace too small");
+  if (a.rel) {
+    if (BN == 256) return launch_nn<256, 128, 1>(a, splits, per, stream);
+    return launch_nn<128, 128, 1>(a, splits, per, stream);
+  }
+  if (BN == 256) return launch_nn<256, 64, 0>(a, splits, per, stream);
+  if (BN == 128) return launch_nn<128, 64, 0>(a, splits, per, stream);
+  return launch_nn<64, 64, 0>(a, splits, per, stream);
+}
+
+}  // namespace gtos

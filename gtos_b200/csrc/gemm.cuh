@@ -1,0 +1,76 @@
+// gtos_b200 -- tcgen05 GEMM kernels (declarations shared between gemm.cu and api.cu)
+#pragma once
+#include "common.cuh"
+
+namespace gtos {
+
+// How the N x N x B pair grid of one encoder layer is cut into 128-row MMA tiles.
+// A tile is (bj keys j) x (bi queries i) of ONE batch element b, fetched with a single 4-D
+// TMA box from relation[j][i][b][:], so a tile touches only bi query rows and bj key rows
+// of q / k (they are staged in shared memory for the epilogue).
+struct RelTiling {
+  int N, B, D, H, hd;
+  int bi, bj;          // tile = bj x bi pairs, bi*bj <= 128
+  int ni_blk, nj_blk;  // ceil(N/bi), ceil(N/bj)
+  int tiles;           // B * nj_blk * ni_blk
+  float scale;         // hd^-1/2
+};
+int choose_rel_tiling(RelTiling* t, int N, int B, int D, int H);
+
+enum GemmMode : int {
+  MODE_PLAIN = 0,  // C = A * B^T (+bias, relu), A,B 2-D K-major
+  MODE_DREL = 1,   // like PLAIN, rows of A are tile-major pair rows, output rows scattered to relation layout
+  MODE_SCORE = 2,  // A = relation tile (4-D box), epilogue: s = scale * <q + ra, k + rb>
+  MODE_GRAD = 3,   // A = relation tile, epilogue: G = scale*ds * [k + rb | q + ra]  (bf16, tile-major)
+};
+
+struct GemmTnArgs {
+  // problem
+  const void* A;       // bf16; PLAIN/DREL: [M,K] row-major (lda); SCORE/GRAD: relation bf16 [N,N,B,D]
+  long lda;
+  const void* Bm;      // bf16 [N,K] row-major (ldb)
+  long ldb;
+  int M, N, K;
+  // plain epilogue
+  const float* bias;   // [N] or null
+  float* out_f32;      // [M,N] (ldo) or null
+  long ldo;
+  void* out_bf16;      // [M,N] (ldob) or null
+  long ldob;
+  int relu;
+  int accumulate;      // out_f32 += result
+  // relation modes
+  RelTiling rt;
+  const float* q;      // [N,B,D] fp32 (bias included, unscaled), row stride ldqk
+  const float* k;      // [N,B,D]
+  long ldqk;
+  float* scores;       // SCORE out: [B,H,N(j),N(i)]
+  const float* dscores;  // GRAD in : [B,H,N(j),N(i)]
+  void* G;             // GRAD out: bf16 [tiles*128, 2D] (permuted feature order)
+};
+int launch_gemm_tn(int mode, const GemmTnArgs& a, cudaStream_t stream);
+
+// out[M,N] = sum_k A[k,m] * B[k,n]   (both operands MN-major), split-K with fp32 partials
+struct GemmNnArgs {
+  const void* A;       // bf16 [Kd, M] row-major (lda)
+  long lda;
+  const void* Bm;      // bf16 [Kd, N] row-major (ldb), or relation bf16 [N,N,B,D] when rel != 0
+  long ldb;
+  int M, N, Kd;
+  int rel;             // B rows come from 4-D relation tiles (Kd = tiles*128)
+  RelTiling rt;
+  float* out;          // [M,N] fp32 (ldo)  (rel: rows un-permuted to the reference [2D,D] layout)
+  long ldo;
+  float* workspace;    // >= splits*M*N floats
+  long workspace_elems;
+};
+long gemm_nn_workspace_elems(int M, int N, int Kd, int rel);
+int launch_gemm_nn(const GemmNnArgs& a, cudaStream_t stream);
+
+// permuted row order of relation_in_proj.weight: per head h, [ra_h (hd rows) | rb_h (hd rows)]
+__host__ __device__ inline int rel_perm_to_orig(int pr, int D, int hd) {
+  int h = pr / (2 * hd), w = pr % (2 * hd);
+  return w < hd ? h * hd + w : D + h * hd + (w - hd);
+}
+
+}  // namespace gtos

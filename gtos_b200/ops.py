@@ -1,0 +1,469 @@
+"""Thin Python wrappers over the C ABI and the autograd Functions built from them.
+
+Everything here launches kernels from libgtos_b200.so on the current CUDA stream; PyTorch only
+owns the memory (torch.empty) and the autograd graph.  No torch math on the data path.
+"""
+import ctypes as C
+import itertools
+import math
+
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+
+_MASK64 = (1 << 64) - 1
+
+
+# --------------------------------------------------------------------------------------------
+# plumbing
+# --------------------------------------------------------------------------------------------
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.GtosLibraryError("gtos_b200 ops need CUDA tensors (B200 / sm_100a); there is no CPU path")
+
+
+def _up8(n):
+    return (n + 7) // 8 * 8
+
+
+def as_u8(mask):
+    """bool / uint8 mask -> contiguous uint8 view (no copy for bool)."""
+    if mask is None:
+        return None
+    m = mask.contiguous()
+    return m.view(torch.uint8) if m.dtype == torch.bool else m.to(torch.uint8)
+
+
+# ---- dropout RNG: one device-resident 64-bit seed + a per-call-site offset -----------------
+_rng_state = {}
+_rng_counter = itertools.count(1)
+
+
+def rng_state(device):
+    key = (device.type, device.index)
+    if key not in _rng_state:
+        _rng_state[key] = torch.tensor([torch.initial_seed() & ((1 << 62) - 1)], dtype=torch.int64, device=device)
+    return _rng_state[key]
+
+
+def reseed(seed, device):
+    rng_state(device).fill_(seed & ((1 << 62) - 1))
+
+
+def advance_rng(device):
+    """Bump the device seed (call once per step; capturable in a CUDA graph)."""
+    rng_state(device).add_(0x9E3779B97F4A7)
+
+
+def new_seed_off():
+    return (next(_rng_counter) * 0xD1B54A32D192ED03) & _MASK64
+
+
+# --------------------------------------------------------------------------------------------
+# primitive wrappers
+# --------------------------------------------------------------------------------------------
+def cast_bf16(x2d, ld=None):
+    """fp32 [rows, cols] -> bf16 [rows, ld] (zero padded)."""
+    _need_cuda(x2d)
+    x2d = x2d.contiguous()
+    rows, cols = x2d.shape
+    ld = _up8(cols) if ld is None else ld
+    out = torch.empty(rows, ld, dtype=torch.bfloat16, device=x2d.device)
+    _lib.check(_lib.load().gtos_cast_bf16(_p(x2d), cols, _p(out), ld, rows, cols, _st()), "cast_bf16")
+    return out
+
+
+def weight_prep(W, want_b=True, want_t=True, rel_heads=0):
+    """W fp32 [R,C] -> (Wb bf16 [R, up8(C)], Wt bf16 [C, up8(R)])."""
+    _need_cuda(W)
+    W = W.detach().contiguous()
+    R, Cc = W.shape
+    Wb = torch.empty(R, _up8(Cc), dtype=torch.bfloat16, device=W.device) if want_b else None
+    Wt = torch.empty(Cc, _up8(R), dtype=torch.bfloat16, device=W.device) if want_t else None
+    _lib.check(_lib.load().gtos_weight_prep(_p(W), R, Cc, _p(Wb), _up8(Cc), _p(Wt), _up8(R), rel_heads, _st()),
+               "weight_prep")
+    return Wb, Wt
+
+
+def gemm_tn(A, B, N, bias=None, f32=True, bf16=False, relu=False, out=None, accumulate=False, K=None, b_off=0,
+            a_off=0, M=None):
+    """C[M,N] = A[M,K] @ B[N,K]^T.  A, B are bf16 2-D (row stride = .stride(0)); offsets in elements."""
+    _need_cuda(A, B)
+    M = A.shape[0] if M is None else M
+    K = min(A.shape[1] - a_off, B.shape[1] - b_off) if K is None else K
+    dev = A.device
+    o32 = out if out is not None else (torch.empty(M, N, dtype=torch.float32, device=dev) if f32 else None)
+    o16 = torch.empty(M, _up8(N), dtype=torch.bfloat16, device=dev) if bf16 else None
+    if o16 is not None and _up8(N) != N:
+        o16.zero_()
+    _lib.check(_lib.load().gtos_gemm_tn(A.data_ptr() + 2 * a_off, A.stride(0), B.data_ptr() + 2 * b_off, B.stride(0),
+                                        _p(bias), _p(o32), o32.stride(0) if o32 is not None else 0, _p(o16),
+                                        o16.stride(0) if o16 is not None else 0, M, N, K, int(relu), int(accumulate),
+                                        _st()), "gemm_tn")
+    return o32, o16
+
+
+def gemm_nn(A, B, M, N, out=None, a_off=0, b_off=0):
+    """C[M,N] = sum_k A[k, m] B[k, n];  A [Kd, >=M], B [Kd, >=N] bf16."""
+    _need_cuda(A, B)
+    Kd = A.shape[0]
+    lib = _lib.load()
+    ws_elems = lib.gtos_gemm_nn_workspace(M, N, Kd)
+    ws = torch.empty(max(ws_elems, 1), dtype=torch.float32, device=A.device)
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=A.device)
+    _lib.check(lib.gtos_gemm_nn(A.data_ptr() + 2 * a_off, A.stride(0), B.data_ptr() + 2 * b_off, B.stride(0), _p(out),
+                                out.stride(0), M, N, Kd, _p(ws), ws_elems, _st()), "gemm_nn")
+    return out
+
+
+def colsum(x2d):
+    out = torch.empty(x2d.shape[1], dtype=torch.float32, device=x2d.device)
+    fn = _lib.load().gtos_colsum_bf16 if x2d.dtype == torch.bfloat16 else _lib.load().gtos_colsum
+    _lib.check(fn(_p(x2d), x2d.stride(0), _p(out), x2d.shape[0], x2d.shape[1], _st()), "colsum")
+    return out
+
+
+def rel_tiling(N, B, D, H):
+    out = (C.c_int32 * 5)()
+    _lib.check(_lib.load().gtos_rel_tiling(N, B, D, H, out), "rel_tiling")
+    return dict(bi=out[0], bj=out[1], ni_blk=out[2], nj_blk=out[3], tiles=out[4])
+
+
+def relation_to_bf16(relation):
+    """dense relation fp32 [N,N,B,D] -> bf16 copy, made once per encoder pass and shared by all layers."""
+    N1, N2, B, D = relation.shape
+    return cast_bf16(relation.reshape(N1 * N2 * B, D), ld=D).view(N1, N2, B, D)
+
+
+def dropout_f32(x, p, seed_ptr, seed_off, out=None):
+    x = x.contiguous()
+    out = torch.empty_like(x) if out is None else out
+    _lib.check(_lib.load().gtos_dropout_f32(_p(x), _p(out), x.numel(), p, _p(seed_ptr), seed_off, _st()), "dropout")
+    return out
+
+
+def _attn_desc(T, S, B, H, hd):
+    d = _lib.AttnDesc()
+    d.T, d.S, d.B, d.H, d.hd = T, S, B, H, hd
+    return d
+
+
+# --------------------------------------------------------------------------------------------
+# residual + dropout + LayerNorm
+# --------------------------------------------------------------------------------------------
+class AddLayerNormFn(torch.autograd.Function):
+    """y = LayerNorm(res + dropout(x)); returns (y fp32, y bf16 [non-differentiable operand copy])."""
+
+    @staticmethod
+    def forward(ctx, x, res, gamma, beta, p):
+        _need_cuda(x, res, gamma)
+        shape = x.shape
+        D = shape[-1]
+        x2 = x.contiguous().view(-1, D)
+        r2 = res.contiguous().view(-1, D) if res is not None else None
+        rows = x2.shape[0]
+        dev = x.device
+        y = torch.empty(rows, D, dtype=torch.float32, device=dev)
+        yb = torch.empty(rows, D, dtype=torch.bfloat16, device=dev)
+        z = torch.empty(rows, D, dtype=torch.float32, device=dev)
+        mean = torch.empty(rows, dtype=torch.float32, device=dev)
+        rstd = torch.empty(rows, dtype=torch.float32, device=dev)
+        seed, off = (rng_state(dev), new_seed_off()) if p > 0 else (None, 0)
+        _lib.check(_lib.load().gtos_add_ln_fwd(_p(x2), _p(r2), _p(gamma), _p(beta), _p(y), _p(yb), _p(z), _p(mean),
+                                               _p(rstd), rows, D, p, _p(seed), off, _st()), "add_ln_fwd")
+        ctx.save_for_backward(z, mean, rstd, gamma)
+        ctx.meta = (p, seed, off, shape, res is not None)
+        yb = yb.view(shape)
+        ctx.mark_non_differentiable(yb)
+        return y.view(shape), yb
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy, _dyb):
+        z, mean, rstd, gamma = ctx.saved_tensors
+        p, seed, off, shape, has_res = ctx.meta
+        rows, D = z.shape
+        dy2 = dy.contiguous().view(rows, D)
+        dres = torch.empty_like(z)
+        dx = torch.empty_like(z) if p > 0 else None
+        dgamma = torch.empty(D, dtype=torch.float32, device=z.device)
+        dbeta = torch.empty(D, dtype=torch.float32, device=z.device)
+        _lib.check(_lib.load().gtos_add_ln_bwd(_p(dy2), _p(z), _p(mean), _p(rstd), _p(gamma), _p(dres), _p(dx), None,
+                                               _p(dgamma), _p(dbeta), rows, D, p, _p(seed), off, _st()), "add_ln_bwd")
+        dres = dres.view(shape)
+        dxo = dres if dx is None else dx.view(shape)
+        return dxo, (dres if has_res else None), dgamma, dbeta, None
+
+
+def add_layer_norm(x, res, gamma, beta, p=0.0):
+    return AddLayerNormFn.apply(x, res, gamma, beta, float(p))
+
+
+# --------------------------------------------------------------------------------------------
+# position-wise feed-forward: fc2(dropout(relu(fc1 x)))
+# --------------------------------------------------------------------------------------------
+class FFNFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, xb, W1, b1, W2, b2, p):
+        _need_cuda(x, W1, W2)
+        shape = x.shape
+        D = shape[-1]
+        Fd = W1.shape[0]
+        xb2 = (xb if xb is not None else cast_bf16(x.contiguous().view(-1, D))).view(-1, _up8(D))
+        W1b, W1t = weight_prep(W1)
+        W2b, W2t = weight_prep(W2)
+        _, hb = gemm_tn(xb2, W1b, Fd, bias=b1, f32=False, bf16=True, relu=True)
+        seed, off = (rng_state(x.device), new_seed_off()) if p > 0 else (None, 0)
+        if p > 0:
+            _lib.check(_lib.load().gtos_dropout_bf16(_p(hb), hb.numel(), p, _p(seed), off, _st()), "dropout_bf16")
+        y, _ = gemm_tn(hb, W2b, D, bias=b2)
+        ctx.save_for_backward(xb2, hb, W1t, W2t)
+        ctx.meta = (p, shape, Fd)
+        return y.view(shape)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        xb2, hb, W1t, W2t = ctx.saved_tensors
+        p, shape, Fd = ctx.meta
+        D = shape[-1]
+        dy2 = dy.contiguous().view(-1, D)
+        M = dy2.shape[0]
+        dyb = cast_bf16(dy2)
+        dW2 = gemm_nn(dyb, hb, D, Fd)
+        db2 = colsum(dy2)
+        dh, _ = gemm_tn(dyb, W2t, Fd)                       # [M,F] = dy @ W2
+        dhb = torch.empty(M, _up8(Fd), dtype=torch.bfloat16, device=dy.device)
+        _lib.check(_lib.load().gtos_relu_drop_bwd(_p(dh), _p(hb), None, _p(dhb), dh.numel(), p, _st()), "relu_drop_bwd")
+        dW1 = gemm_nn(dhb, xb2, Fd, D)
+        db1 = colsum(dhb)[:Fd]
+        dx, _ = gemm_tn(dhb, W1t, D)
+        return dx.view(shape), None, dW1, db1, dW2, db2, None
+
+
+def ffn(x, xb, W1, b1, W2, b2, p=0.0):
+    return FFNFn.apply(x, xb, W1, b1, W2, b2, float(p))
+
+
+# --------------------------------------------------------------------------------------------
+# relation-aware multi-head self-attention (graph_transformer.py:93-174)
+# --------------------------------------------------------------------------------------------
+class RelAttnFn(torch.autograd.Function):
+    """inputs x [N,B,D], relation [N,N,B,D] (+ its shared bf16 copy relb); returns (out, weights[B,H,N,N] | None)."""
+
+    @staticmethod
+    def forward(ctx, x, xb, relation, relb, key_pad, attn_mask, W_in, b_in, W_rel, W_out, b_out, H, p, need_weights):
+        _need_cuda(x, relation, W_in)
+        lib = _lib.load()
+        N, B, D = x.shape
+        if tuple(relation.shape) != (N, N, B, D):
+            raise ValueError(f"relation must be [N,N,B,D]=[{N},{N},{B},{D}], got {tuple(relation.shape)}")
+        hd = D // H
+        dev = x.device
+        NB = N * B
+        xb2 = (xb if xb is not None else cast_bf16(x.contiguous().view(NB, D))).view(NB, D)
+        if relb is None:
+            relb = relation_to_bf16(relation.detach().contiguous())
+        Wib, Wit = weight_prep(W_in)
+        Wperm, WpermT = weight_prep(W_rel, rel_heads=H)
+        Wob, Wot = weight_prep(W_out)
+        qkv, _ = gemm_tn(xb2, Wib, 3 * D, bias=b_in)                               # [NB, 3D] fp32
+        scores = torch.empty(B, H, N, N, dtype=torch.float32, device=dev)          # [b,h,j,i]
+        _lib.check(lib.gtos_rel_score(_p(relb), _p(Wperm), qkv.data_ptr(), qkv.data_ptr() + 4 * D, 3 * D, _p(scores),
+                                      N, B, D, H, _st()), "rel_score")
+        probs = torch.empty(B, H, N, N, dtype=torch.float32, device=dev)           # [b,h,i,j]
+        wts = torch.empty(B, H, N, N, dtype=torch.float32, device=dev) if need_weights else None
+        att = torch.empty(NB, D, dtype=torch.float32, device=dev)
+        attb = torch.empty(NB, D, dtype=torch.bfloat16, device=dev)
+        seed, off = (rng_state(dev), new_seed_off()) if p > 0 else (None, 0)
+        d = _attn_desc(N, N, B, H, hd)
+        d.v, d.ldv = qkv.data_ptr() + 8 * D, 3 * D
+        d.scale, d.p_drop = 1.0, p
+        d.scores_jt, d.key_pad, d.attn_mask = _p(scores), _p(key_pad), _p(attn_mask)
+        d.seed_ptr, d.seed_off = _p(seed), off
+        d.probs, d.probs_dropped = _p(probs), _p(wts)
+        d.out, d.ldo, d.out_bf16 = _p(att), D, _p(attb)
+        _lib.check(lib.gtos_attn_fwd(C.byref(d), _st()), "attn_fwd(enc)")
+        out, _ = gemm_tn(attb, Wob, D, bias=b_out)
+        ctx.save_for_backward(xb2, relb, qkv, probs, attb, Wperm, WpermT, Wit, Wot, key_pad, attn_mask)
+        ctx.meta = (N, B, D, H, p, seed, off)
+        if wts is None:
+            return out.view(N, B, D), None
+        return out.view(N, B, D), wts
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout, dwts):
+        xb2, relb, qkv, probs, attb, Wperm, WpermT, Wit, Wot, key_pad, attn_mask = ctx.saved_tensors
+        N, B, D, H, p, seed, off = ctx.meta
+        lib = _lib.load()
+        hd = D // H
+        dev = dout.device
+        NB = N * B
+        dout2 = dout.contiguous().view(NB, D)
+        doutb = cast_bf16(dout2)
+        dW_out = gemm_nn(doutb, attb, D, D)
+        db_out = colsum(dout2)
+        datt, _ = gemm_tn(doutb, Wot, D)                                           # [NB, D]
+        dqkv = torch.empty(NB, 3 * D, dtype=torch.float32, device=dev)
+        ds_jt = torch.empty(B, H, N, N, dtype=torch.float32, device=dev)
+        ds_ts = torch.empty(B, H, N, N, dtype=torch.float32, device=dev)
+        d = _attn_desc(N, N, B, H, hd)
+        d.v, d.ldv = qkv.data_ptr() + 8 * D, 3 * D
+        d.scale, d.p_drop = 1.0, p
+        d.key_pad, d.attn_mask = _p(key_pad), _p(attn_mask)
+        d.seed_ptr, d.seed_off = _p(seed), off
+        d.probs = _p(probs)
+        d.dout, d.lddo = _p(datt), D
+        d.dprobs_extra = _p(dwts.contiguous()) if dwts is not None else None
+        d.dscores_jt, d.dscores_ts = _p(ds_jt), _p(ds_ts)
+        d.dv, d.lddv = dqkv.data_ptr() + 8 * D, 3 * D
+        _lib.check(lib.gtos_attn_bwd(C.byref(d), _st()), "attn_bwd(enc)")
+        tiles = rel_tiling(N, B, D, H)["tiles"]
+        G = torch.empty(tiles * 128, 2 * D, dtype=torch.bfloat16, device=dev)
+        _lib.check(lib.gtos_rel_grad(_p(relb), _p(Wperm), qkv.data_ptr(), qkv.data_ptr() + 4 * D, 3 * D, _p(ds_jt),
+                                     _p(G), N, B, D, H, _st()), "rel_grad")
+        _lib.check(lib.gtos_rel_dqk(_p(G), dqkv.data_ptr(), dqkv.data_ptr() + 4 * D, 3 * D, N, B, D, H, _st()),
+                   "rel_dqk")
+        d_rel = None
+        if ctx.needs_input_grad[2]:
+            d_rel = torch.empty(N, N, B, D, dtype=torch.float32, device=dev)
+            _lib.check(lib.gtos_rel_drel(_p(G), _p(WpermT), _p(d_rel), 0, N, B, D, H, _st()), "rel_drel")
+        ws_elems = lib.gtos_rel_dw_workspace(N, B, D, H)
+        ws = torch.empty(ws_elems, dtype=torch.float32, device=dev)
+        dW_rel = torch.empty(2 * D, D, dtype=torch.float32, device=dev)
+        _lib.check(lib.gtos_rel_dw(_p(G), _p(relb), _p(dW_rel), _p(ws), ws_elems, N, B, D, H, _st()), "rel_dw")
+        dqkvb = cast_bf16(dqkv)
+        dW_in = gemm_nn(dqkvb, xb2, 3 * D, D)
+        db_in = colsum(dqkv)
+        dx, _ = gemm_tn(dqkvb, Wit, D)
+        return (dx.view(N, B, D), None, d_rel, None, None, None, dW_in, db_in, dW_rel, dW_out, db_out, None, None,
+                None)
+
+
+# --------------------------------------------------------------------------------------------
+# vanilla multi-head attention (transformer.py:98-173)
+# --------------------------------------------------------------------------------------------
+class MHAFn(torch.autograd.Function):
+    """query [T,B,D]; key [S,B,D] (value is key); returns (out, weights[B,H,T,S] | None)."""
+
+    @staticmethod
+    def forward(ctx, query, qb, key, kb, self_attn, key_pad, attn_mask, W_in, b_in, W_out, b_out, H, p,
+                weights_dropout, need_weights):
+        _need_cuda(query, key, W_in)
+        lib = _lib.load()
+        T, B, D = query.shape
+        S = key.shape[0]
+        hd = D // H
+        dev = query.device
+        qb2 = (qb if qb is not None else cast_bf16(query.contiguous().view(T * B, D))).view(T * B, _up8(D))
+        Wib, Wit = weight_prep(W_in)
+        Wob, Wot = weight_prep(W_out)
+        if self_attn:
+            kb2 = qb2
+            proj, _ = gemm_tn(qb2, Wib, 3 * D, bias=b_in)                          # [TB, 3D]
+            qp, kp, vp, ldq, ldk = proj.data_ptr(), proj.data_ptr() + 4 * D, proj.data_ptr() + 8 * D, 3 * D, 3 * D
+            keep = (proj,)
+        else:
+            kb2 = (kb if kb is not None else cast_bf16(key.contiguous().view(S * B, D))).view(S * B, _up8(D))
+            pq, _ = gemm_tn(qb2, Wib, D, bias=b_in[:D], M=T * B)                    # rows 0..D of W_in
+            pkv = torch.empty(S * B, 2 * D, dtype=torch.float32, device=dev)
+            _lib.check(lib.gtos_gemm_tn(_p(kb2), kb2.stride(0), Wib.data_ptr() + 2 * D * Wib.stride(0), Wib.stride(0),
+                                        b_in.data_ptr() + 4 * D, _p(pkv), 2 * D, None, 0, S * B, 2 * D, _up8(D), 0, 0,
+                                        _st()), "gemm_tn(kv)")
+            qp, kp, vp, ldq, ldk = pq.data_ptr(), pkv.data_ptr(), pkv.data_ptr() + 4 * D, D, 2 * D
+            keep = (pq, pkv)
+        probs = torch.empty(B, H, T, S, dtype=torch.float32, device=dev)
+        p_w = p if weights_dropout else 0.0
+        wts = torch.empty(B, H, T, S, dtype=torch.float32, device=dev) if need_weights else None
+        att = torch.empty(T * B, D, dtype=torch.float32, device=dev)
+        attb = torch.empty(T * B, _up8(D), dtype=torch.bfloat16, device=dev)
+        seed, off = (rng_state(dev), new_seed_off()) if p > 0 else (None, 0)
+        d = _attn_desc(T, S, B, H, hd)
+        d.q, d.ldq, d.k, d.ldk, d.v, d.ldv = qp, ldq, kp, ldk, vp, ldk
+        d.scale, d.p_drop = hd ** -0.5, p_w
+        d.key_pad, d.attn_mask = _p(key_pad), _p(attn_mask)
+        d.seed_ptr, d.seed_off = _p(seed), off
+        d.probs, d.probs_dropped = _p(probs), _p(wts)
+        d.out, d.ldo = _p(att), D
+        d.out_bf16 = _p(attb) if (weights_dropout or p == 0) else None
+        _lib.check(lib.gtos_attn_fwd(C.byref(d), _st()), "attn_fwd(dec)")
+        off2 = 0
+        if not weights_dropout and p > 0:                                          # transformer.py:156-157
+            off2 = new_seed_off()
+            dropout_f32(att, p, seed, off2, out=att)
+            attb = cast_bf16(att)
+        out, _ = gemm_tn(attb, Wob, D, bias=b_out)
+        ctx.save_for_backward(qb2, kb2, probs, attb, Wit, Wot, key_pad, attn_mask, *keep)
+        ctx.meta = (T, S, B, D, H, p, p_w, seed, off, off2, self_attn)
+        if wts is None:
+            return out.view(T, B, D), None
+        return out.view(T, B, D), wts
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout, dwts):
+        qb2, kb2, probs, attb, Wit, Wot, key_pad, attn_mask, *keep = ctx.saved_tensors
+        T, S, B, D, H, p, p_w, seed, off, off2, self_attn = ctx.meta
+        lib = _lib.load()
+        hd = D // H
+        dev = dout.device
+        dout2 = dout.contiguous().view(T * B, D)
+        doutb = cast_bf16(dout2)
+        dW_out = gemm_nn(doutb, attb, D, D)
+        db_out = colsum(dout2)
+        datt, _ = gemm_tn(doutb, Wot, D)
+        if off2:
+            dropout_f32(datt, p, seed, off2, out=datt)
+        d = _attn_desc(T, S, B, H, hd)
+        if self_attn:
+            (proj,) = keep
+            dproj = torch.empty(T * B, 3 * D, dtype=torch.float32, device=dev)
+            d.q, d.ldq, d.k, d.ldk, d.v, d.ldv = (proj.data_ptr(), 3 * D, proj.data_ptr() + 4 * D, 3 * D,
+                                                  proj.data_ptr() + 8 * D, 3 * D)
+            d.dq, d.lddq, d.dk, d.lddk, d.dv, d.lddv = (dproj.data_ptr(), 3 * D, dproj.data_ptr() + 4 * D, 3 * D,
+                                                        dproj.data_ptr() + 8 * D, 3 * D)
+        else:
+            pq, pkv = keep
+            dpq = torch.empty(T * B, D, dtype=torch.float32, device=dev)
+            dpkv = torch.empty(S * B, 2 * D, dtype=torch.float32, device=dev)
+            d.q, d.ldq, d.k, d.ldk, d.v, d.ldv = pq.data_ptr(), D, pkv.data_ptr(), 2 * D, pkv.data_ptr() + 4 * D, 2 * D
+            d.dq, d.lddq, d.dk, d.lddk, d.dv, d.lddv = (dpq.data_ptr(), D, dpkv.data_ptr(), 2 * D,
+                                                        dpkv.data_ptr() + 4 * D, 2 * D)
+        ds_ts = torch.empty(B, H, T, S, dtype=torch.float32, device=dev)
+        d.scale, d.p_drop = hd ** -0.5, p_w
+        d.key_pad, d.attn_mask = _p(key_pad), _p(attn_mask)
+        d.seed_ptr, d.seed_off = _p(seed), off
+        d.probs = _p(probs)
+        d.dout, d.lddo = _p(datt), D
+        d.dprobs_extra = _p(dwts.contiguous()) if dwts is not None else None
+        d.dscores_ts = _p(ds_ts)
+        _lib.check(lib.gtos_attn_bwd(C.byref(d), _st()), "attn_bwd(dec)")
+        dW_in = torch.empty(3 * D, D, dtype=torch.float32, device=dev)
+        if self_attn:
+            dprojb = cast_bf16(dproj)
+            gemm_nn(dprojb, qb2, 3 * D, D, out=dW_in)
+            db_in = colsum(dproj)
+            dq_in, _ = gemm_tn(dprojb, Wit, D)
+            dk_in = None
+        else:
+            dpqb, dpkvb = cast_bf16(dpq), cast_bf16(dpkv)
+            gemm_nn(dpqb, qb2, D, D, out=dW_in[:D])
+            gemm_nn(dpkvb, kb2, 2 * D, D, out=dW_in[D:])
+            db_in = torch.cat([colsum(dpq), colsum(dpkv)])
+            dq_in, _ = gemm_tn(dpqb, Wit, D, K=D)                                   # Wt[:, :D]
+            dk_in, _ = gemm_tn(dpkvb, Wit, D, K=2 * D, b_off=D)                     # Wt[:, D:3D]
+            dk_in = dk_in.view(S, B, D)
+        return (dq_in.view(T, B, D), None, dk_in, None, None, None, None, dW_in, db_in, dW_out, db_out, None, None,
+                None, None)

@@ -1,0 +1,139 @@
+/* gtos_b200 -- C ABI of libgtos_b200.so: the B200 (sm_100a) kernels behind the gtos graph-transformer
+ * encode/decode hot path.
+ *
+ * The reference (jcyk/gtos) is pure PyTorch: its "FFI" for this path is the ATen call sites inside
+ * four nn.Module.forward methods.  Each entry point below names the reference lines it replaces
+ * (paths relative to /root/reference/generator; translator/ holds byte-identical copies).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error (see GTOS_ERR_*); the message is
+ *     available from gtos_last_error() (thread-local); nothing throws, nothing allocates;
+ *   - all pointers are DEVICE pointers unless noted; outputs and workspaces are caller-allocated;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no host sync;
+ *   - fp32 tensors are row-major with explicit row strides (`ld*`, in elements);
+ *     "bf16" buffers hold __nv_bfloat16; activations are time-major [len, batch, dim] as in the
+ *     reference (graph_transformer.py:50, transformer.py:99);
+ *   - dropout is counter-based: keep(idx) = hash(*seed_ptr + seed_off, idx) >= p, so backward
+ *     regenerates the mask from the same (seed_ptr, seed_off) and CUDA graphs can bump the seed.
+ */
+#ifndef GTOS_B200_H_
+#define GTOS_B200_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GTOS_OK 0
+#define GTOS_ERR_CUDA 1
+#define GTOS_ERR_ARG 2
+#define GTOS_ERR_UNSUPPORTED 3
+#define GTOS_ERR_NO_DEVICE 4
+
+const char* gtos_last_error(void);
+int gtos_abi_version(void);
+/* 0 if the current device is sm_100 and the TMA driver entry point resolves */
+int gtos_device_check(void);
+
+/* ---- operand staging -------------------------------------------------------------------------- */
+/* fp32 [rows, cols] (lds) -> bf16 [rows, ldd]; columns cols..ldd-1 are zero-filled (TMA needs 16 B rows) */
+int gtos_cast_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int32_t cols, void* stream);
+/* weight W fp32 [R,C] -> Wb bf16 [R, ldw] and/or Wt bf16 [C, ldt] (transpose, for input gradients).
+ * rel_heads > 0: rows are reordered head-interleaved, per head [ra_h | rb_h], for
+ * relation_in_proj.weight [2D, D] (graph_transformer.py:80,122) */
+int gtos_weight_prep(const float* W, int32_t R, int32_t C, void* Wb, int64_t ldw, void* Wt, int64_t ldt,
+                     int32_t rel_heads, void* stream);
+
+/* ---- dense projections (F.linear call sites: graph_transformer.py:191-197,165; transformer.py:175-196,162;
+ *      fc1/fc2 graph_transformer.py:60-63, transformer.py:66-69; nn.GRU / out_proj encoder.py:106,117) ------ */
+/* C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]) (ReLU);  A,B bf16;  writes fp32 and/or bf16;  accumulate: C_f32 += */
+int gtos_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, const float* bias, float* out_f32, int64_t ldo,
+                 void* out_bf16, int64_t ldob, int32_t M, int32_t N, int32_t K, int32_t relu, int32_t accumulate,
+                 void* stream);
+/* C[M,N] = sum_k A[k,m] * B[k,n]  (weight gradients, autograd of the call sites above) */
+int64_t gtos_gemm_nn_workspace(int32_t M, int32_t N, int32_t Kd);
+int gtos_gemm_nn(const void* A, int64_t lda, const void* B, int64_t ldb, float* out, int64_t ldo, int32_t M, int32_t N,
+                 int32_t Kd, float* workspace, int64_t workspace_elems, void* stream);
+
+/* ---- fused relation attention (RelationMultiheadAttention.forward, graph_transformer.py:93-174) ---- */
+/* tiling of the N x N x B pair grid into 128-row MMA tiles: out = {bi, bj, ni_blk, nj_blk, tiles} */
+int gtos_rel_tiling(int32_t N, int32_t B, int32_t D, int32_t H, int32_t* out5);
+/* scores[b,h,j,i] = hd^-1/2 < q[i,b,h] + Wa r[j,i,b] , k[j,b,h] + Wb r[j,i,b] >     (:122-133)
+ * relb: relation as bf16 [N,N,B,D]; Wperm: gtos_weight_prep(rel_heads=H) output [2D,D]; q,k fp32 with row stride ldqk */
+int gtos_rel_score(const void* relb, const void* Wperm, const float* q, const float* k, int64_t ldqk, float* scores,
+                   int32_t N, int32_t B, int32_t D, int32_t H, void* stream);
+/* backward of the above w.r.t. the per-pair projections: G[tile-major pair, 2D] (bf16) = hd^-1/2 dscores * [k+rb | q+ra] */
+int gtos_rel_grad(const void* relb, const void* Wperm, const float* q, const float* k, int64_t ldqk,
+                  const float* dscores, void* G, int32_t N, int32_t B, int32_t D, int32_t H, void* stream);
+/* d_relation[j,i,b,:] (+)= G * Wperm  (WpermT = transposed prep output [D,2D]) */
+int gtos_rel_drel(const void* G, const void* WpermT, float* d_relation, int32_t accumulate, int32_t N, int32_t B,
+                  int32_t D, int32_t H, void* stream);
+/* d relation_in_proj.weight [2D,D] (reference row order) = G^T * relation */
+int64_t gtos_rel_dw_workspace(int32_t N, int32_t B, int32_t D, int32_t H);
+int gtos_rel_dw(const void* G, const void* relb, float* dW, float* workspace, int64_t workspace_elems, int32_t N,
+                int32_t B, int32_t D, int32_t H, void* stream);
+/* dq[i,b,:] = sum_j G_x, dk[j,b,:] = sum_i G_y ; written with row stride ld (into the QKV grad buffer) */
+int gtos_rel_dqk(const void* G, float* dq, float* dk, int64_t ld, int32_t N, int32_t B, int32_t D, int32_t H,
+                 void* stream);
+
+/* ---- attention core: masks, softmax, dropout, PV (graph_transformer.py:136-159; transformer.py:131-155) ---- */
+typedef struct gtos_attn_desc {
+  int32_t T, S, B, H, hd;
+  int32_t pad0;
+  const float* q; int64_t ldq;          /* element (t,b,h,d) at q[(t*B+b)*ldq + h*hd + d]; NULL in encoder mode */
+  const float* k; int64_t ldk;
+  const float* v; int64_t ldv;
+  float scale; float p_drop;
+  const float* scores_jt;               /* encoder mode: scores from gtos_rel_score, [B,H,S,T] */
+  const uint8_t* key_pad;               /* [S,B], 1 = padding (may be NULL) */
+  const uint8_t* attn_mask;             /* [T,S], 1 = blocked (may be NULL) */
+  const void* seed_ptr; uint64_t seed_off;
+  float* probs;                         /* out (fwd) / in (bwd): softmax before dropout, [B,H,T,S] */
+  float* probs_dropped;                 /* optional out: weights after dropout, [B,H,T,S] */
+  float* out; int64_t ldo; void* out_bf16;
+  /* backward only */
+  const float* dout; int64_t lddo;
+  const float* dprobs_extra;            /* optional grad w.r.t. probs_dropped */
+  float* dscores_jt;                    /* encoder mode out [B,H,S,T] */
+  float* dscores_ts;                    /* out [B,H,T,S] */
+  float* dq; int64_t lddq;
+  float* dk; int64_t lddk;
+  float* dv; int64_t lddv;
+} gtos_attn_desc;
+int gtos_attn_fwd(const gtos_attn_desc* d, void* stream);
+int gtos_attn_bwd(const gtos_attn_desc* d, void* stream);
+
+/* ---- residual + dropout + LayerNorm (graph_transformer.py:57-58,64-65; transformer.py:56-57,63,70-71) ---- */
+int gtos_add_ln_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* y, void* y_bf16,
+                    float* z, float* mean, float* rstd, int64_t rows, int32_t D, float p_drop, const void* seed_ptr,
+                    uint64_t seed_off, void* stream);
+int gtos_add_ln_bwd(const float* dy, const float* z, const float* mean, const float* rstd, const float* gamma,
+                    float* dres, float* dx, void* dx_bf16, float* dgamma, float* dbeta, int64_t rows, int32_t D,
+                    float p_drop, const void* seed_ptr, uint64_t seed_off, void* stream);
+/* out[n] = sum_m x[m,n]  (bias gradients) */
+int gtos_colsum(const float* x, int64_t ld, float* out, int64_t rows, int32_t cols, void* stream);
+int gtos_colsum_bf16(const void* x, int64_t ld, float* out, int64_t rows, int32_t cols, void* stream);
+/* FFN hidden dropout (in place, bf16) and its ReLU/dropout backward (graph_transformer.py:60-61) */
+int gtos_dropout_bf16(void* h, int64_t n, float p, const void* seed_ptr, uint64_t seed_off, void* stream);
+/* generic fp32 dropout, out may alias x (decoder.py:82, transformer.py:156); same seed in backward */
+int gtos_dropout_f32(const float* x, float* out, int64_t n, float p, const void* seed_ptr, uint64_t seed_off,
+                     void* stream);
+int gtos_relu_drop_bwd(const float* dh_in, const void* act_bf16, float* dh_f32, void* dh_bf16, int64_t n, float p,
+                       void* stream);
+
+/* ---- RelationEncoder (encoder.py:90-119): embedding + GRU gate math; GEMMs via gtos_gemm_* ---- */
+int gtos_embed_gather(const float* table, const int64_t* idx, int64_t n, int32_t dim, float* out_f32, void* out_bf16,
+                      int64_t ldb, float p_drop, const void* seed_ptr, uint64_t seed_off, void* stream);
+int gtos_embed_scatter_add(const float* dx, const int64_t* idx, int64_t n, int32_t dim, float* dtable, float p_drop,
+                           const void* seed_ptr, uint64_t seed_off, void* stream);
+int gtos_gru_gate_fwd(const float* gi, int64_t ldgi, const float* gh, int64_t ldgh, const float* h_prev,
+                      const int64_t* lengths, int32_t t, float* h_new, void* h_new_bf16, float* out_t, int64_t ldout,
+                      void* out_t_bf16, int64_t ldoutb, float* gates, int64_t R, int32_t Hh, void* stream);
+int gtos_gru_gate_bwd(const float* dh, const float* dout_t, int64_t lddout, const float* gates, const float* gh,
+                      int64_t ldgh, const float* h_prev, const int64_t* lengths, int32_t t, float* dh_prev,
+                      void* dgi_bf16, int64_t lddgi, void* dgh_bf16, int64_t lddgh, int64_t R, int32_t Hh, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GTOS_B200_H_ */

@@ -1,0 +1,242 @@
+"""-m gpu: every C-ABI kernel of libgtos_b200.so against a plain PyTorch fp32 statement of the same
+op on the same seeded inputs (bf16-rounded where the kernel consumes bf16 operands, so the only
+difference is accumulation order).  Tolerances are stated per test."""
+import ctypes as C
+
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+SEED = 19940117
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a B200")
+    from gtos_b200 import _lib
+    lib = _lib.load()
+    _lib.check(lib.gtos_device_check(), "device_check")
+    torch.manual_seed(SEED)
+    return torch.device("cuda:0")
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 64, 128), (300, 512, 512), (2624, 1536, 512),
+                                   (77, 130, 104), (1000, 768, 256), (5, 16, 8)])
+def test_gemm_tn(dev, M, N, K):
+    from gtos_b200 import ops
+    A = bf(torch.randn(M, K, device=dev))
+    B = bf(torch.randn(N, K, device=dev))
+    bias = torch.randn(N, device=dev)
+    ref = A.float() @ B.float().t() + bias
+    out, outb = ops.gemm_tn(A, B, N, bias=bias, f32=True, bf16=True)
+    torch.cuda.synchronize()
+    assert rel_err(out, ref) < 2e-5 * max(1, K ** 0.5)
+    assert rel_err(outb[:, :N].float(), ref) < 1e-2
+    out2, _ = ops.gemm_tn(A, B, N, bias=None, relu=True, out=out.clone(), accumulate=True)
+    assert rel_err(out2, ref + torch.relu(ref - bias)) < 1e-4
+
+
+@pytest.mark.parametrize("Kd,M,N", [(64, 128, 256), (128, 128, 64), (2624, 1536, 512), (1000, 512, 1024),
+                                    (333, 200, 104), (4096, 768, 256)])
+def test_gemm_nn(dev, Kd, M, N):
+    from gtos_b200 import ops
+    A = bf(torch.randn(Kd, (M + 7) // 8 * 8, device=dev))
+    B = bf(torch.randn(Kd, (N + 7) // 8 * 8, device=dev))
+    ref = A.float()[:, :M].t() @ B.float()[:, :N]
+    out = ops.gemm_nn(A, B, M, N)
+    torch.cuda.synchronize()
+    assert rel_err(out, ref) < 2e-5 * max(1, Kd ** 0.5)
+
+
+def _rel_inputs(dev, N, B, D, H, wscale):
+    x_q = torch.randn(N * B, 3 * D, device=dev)                     # fused qkv projection buffer
+    rel = torch.randn(N, N, B, D, device=dev) * 0.5
+    Wr = torch.randn(2 * D, D, device=dev) * wscale
+    return x_q, rel, Wr
+
+
+def _rel_scores_ref(qkv, relb, Wr, N, B, D, H):
+    """scores[b,h,j,i] = hd^-1/2 < q_i + Wa r[j,i] , k_j + Wb r[j,i] >  from the bf16-rounded operands"""
+    hd = D // H
+    q = qkv[:, :D].view(N, B, H, hd)
+    k = qkv[:, D:2 * D].view(N, B, H, hd)
+    r = relb.float()
+    W = bf(Wr).float()
+    ra = (r @ W[:D].t()).view(N, N, B, H, hd)                        # [j,i,b,h,d]
+    rb = (r @ W[D:].t()).view(N, N, B, H, hd)
+    s = ((q.unsqueeze(0) + ra) * (k.unsqueeze(1) + rb)).sum(-1) * hd ** -0.5   # [j,i,b,h]
+    return s.permute(2, 3, 0, 1).contiguous()                        # [b,h,j,i]
+
+
+@pytest.mark.parametrize("N,B,D,H", [(17, 8, 128, 8), (41, 4, 512, 8), (9, 3, 256, 4), (130, 2, 128, 2)])
+def test_rel_score(dev, N, B, D, H):
+    from gtos_b200 import _lib, ops
+    qkv, rel, Wr = _rel_inputs(dev, N, B, D, H, 0.05)
+    relb = ops.relation_to_bf16(rel)
+    Wperm, _ = ops.weight_prep(Wr, rel_heads=H)
+    scores = torch.full((B, H, N, N), float("nan"), device=dev)
+    _lib.check(_lib.load().gtos_rel_score(relb.data_ptr(), Wperm.data_ptr(), qkv.data_ptr(), qkv.data_ptr() + 4 * D,
+                                          3 * D, scores.data_ptr(), N, B, D, H,
+                                          torch.cuda.current_stream().cuda_stream), "rel_score")
+    torch.cuda.synchronize()
+    ref = _rel_scores_ref(qkv, relb, Wr, N, B, D, H)
+    assert torch.isfinite(scores).all()
+    assert rel_err(scores, ref) < 1e-4
+
+
+@pytest.mark.parametrize("N,B,D,H", [(17, 8, 128, 8), (41, 4, 512, 8)])
+def test_rel_backward_pieces(dev, N, B, D, H):
+    """G, d_relation, dW_rel, dq, dk from the tcgen05 kernels vs autograd of the fp32 formula."""
+    from gtos_b200 import _lib, ops
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    qkv, rel, Wr = _rel_inputs(dev, N, B, D, H, 0.05)
+    relb = ops.relation_to_bf16(rel)
+    Wperm, WpermT = ops.weight_prep(Wr, rel_heads=H)
+    ds = torch.randn(B, H, N, N, device=dev)
+    # reference through autograd on the bf16-rounded operands
+    r32 = relb.float().requires_grad_()
+    W32 = bf(Wr).float().requires_grad_()
+    q32 = qkv.clone().requires_grad_()
+    hd = D // H
+    q = q32[:, :D].view(N, B, H, hd)
+    k = q32[:, D:2 * D].view(N, B, H, hd)
+    ra = (r32 @ W32[:D].t()).view(N, N, B, H, hd)
+    rb = (r32 @ W32[D:].t()).view(N, N, B, H, hd)
+    s = (((q.unsqueeze(0) + ra) * (k.unsqueeze(1) + rb)).sum(-1) * hd ** -0.5).permute(2, 3, 0, 1)
+    (s * ds).sum().backward()
+    tiles = ops.rel_tiling(N, B, D, H)["tiles"]
+    G = torch.empty(tiles * 128, 2 * D, dtype=torch.bfloat16, device=dev)
+    _lib.check(lib.gtos_rel_grad(relb.data_ptr(), Wperm.data_ptr(), qkv.data_ptr(), qkv.data_ptr() + 4 * D, 3 * D,
+                                 ds.data_ptr(), G.data_ptr(), N, B, D, H, st), "rel_grad")
+    dqkv = torch.zeros(N * B, 3 * D, device=dev)
+    _lib.check(lib.gtos_rel_dqk(G.data_ptr(), dqkv.data_ptr(), dqkv.data_ptr() + 4 * D, 3 * D, N, B, D, H, st), "dqk")
+    drel = torch.full((N, N, B, D), float("nan"), device=dev)
+    _lib.check(lib.gtos_rel_drel(G.data_ptr(), WpermT.data_ptr(), drel.data_ptr(), 0, N, B, D, H, st), "drel")
+    ws_n = lib.gtos_rel_dw_workspace(N, B, D, H)
+    ws = torch.empty(ws_n, device=dev)
+    dW = torch.full((2 * D, D), float("nan"), device=dev)
+    _lib.check(lib.gtos_rel_dw(G.data_ptr(), relb.data_ptr(), dW.data_ptr(), ws.data_ptr(), ws_n, N, B, D, H, st), "dw")
+    torch.cuda.synchronize()
+    assert torch.isfinite(G.float()).all()
+    # G is rounded to bf16 once, so downstream tolerances are bf16-level (1e-2 relative)
+    assert rel_err(dqkv[:, :D], q32.grad[:, :D]) < 1e-2
+    assert rel_err(dqkv[:, D:2 * D], q32.grad[:, D:2 * D]) < 1e-2
+    assert rel_err(drel, r32.grad) < 1e-2
+    assert rel_err(dW, W32.grad) < 1e-2
+
+
+def _attn_ref(q, k, v, scale, key_pad, attn_mask, H):
+    T, B, D = q.shape
+    S = k.shape[0]
+    hd = D // H
+    qh, kh, vh = (t.view(-1, B, H, hd) for t in (q, k, v))
+    s = torch.einsum("tbhd,sbhd->bhts", qh, kh) * scale
+    if attn_mask is not None:
+        s = s.masked_fill(attn_mask.bool()[None, None], float("-inf"))
+    if key_pad is not None:
+        s = s.masked_fill(key_pad.bool().t()[:, None, None, :], float("-inf"))
+    p = torch.softmax(s, -1)
+    return torch.einsum("bhts,sbhd->tbhd", p, vh).reshape(T, B, D), p
+
+
+@pytest.mark.parametrize("T,S,B,H,hd,causal", [(6, 8, 3, 4, 8, False), (40, 40, 16, 8, 64, True), (33, 70, 5, 1, 512, False),
+                                                (1, 40, 64, 8, 64, False)])
+def test_attention_core(dev, T, S, B, H, hd, causal):
+    from gtos_b200 import _lib, ops
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    D = H * hd
+    q = torch.randn(T, B, D, device=dev, requires_grad=True)
+    k = torch.randn(S, B, D, device=dev, requires_grad=True)
+    v = torch.randn(S, B, D, device=dev, requires_grad=True)
+    lens = torch.randint(max(1, S // 2), S + 1, (B,), device=dev)
+    key_pad = (torch.arange(S, device=dev).unsqueeze(1) >= lens.unsqueeze(0))
+    am = torch.ones(T, S, dtype=torch.bool, device=dev).triu_(1) if causal else None
+    if causal:
+        key_pad = None
+    scale = hd ** -0.5
+    ref, pref = _attn_ref(q, k, v, scale, key_pad, am, H)
+    dout = torch.randn_like(ref)
+    dw = torch.randn_like(pref)
+    (ref * dout).sum().backward(retain_graph=True)
+    gq, gk, gv = q.grad.clone(), k.grad.clone(), v.grad.clone()
+    probs = torch.empty(B, H, T, S, device=dev)
+    out = torch.empty(T * B, D, device=dev)
+    d = ops._attn_desc(T, S, B, H, hd)
+    d.q, d.ldq, d.k, d.ldk, d.v, d.ldv = q.data_ptr(), D, k.data_ptr(), D, v.data_ptr(), D
+    d.scale, d.p_drop = scale, 0.0
+    d.key_pad = ops.as_u8(key_pad).data_ptr() if key_pad is not None else None
+    d.attn_mask = ops.as_u8(am).data_ptr() if am is not None else None
+    d.probs, d.out, d.ldo = probs.data_ptr(), out.data_ptr(), D
+    _lib.check(lib.gtos_attn_fwd(C.byref(d), st), "attn_fwd")
+    torch.cuda.synchronize()
+    assert rel_err(probs, pref) < 1e-5
+    assert rel_err(out.view(T, B, D), ref) < 1e-5
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    ds = torch.empty(B, H, T, S, device=dev)
+    d.dout, d.lddo = dout.data_ptr(), D
+    d.dscores_ts = ds.data_ptr()
+    d.dq, d.lddq, d.dk, d.lddk, d.dv, d.lddv = dq.data_ptr(), D, dk.data_ptr(), D, dv.data_ptr(), D
+    _lib.check(lib.gtos_attn_bwd(C.byref(d), st), "attn_bwd")
+    torch.cuda.synchronize()
+    assert rel_err(dq, gq) < 1e-4 and rel_err(dk, gk) < 1e-4 and rel_err(dv, gv) < 1e-4
+    # extra gradient flowing into the returned weights
+    q.grad = k.grad = v.grad = None
+    ((ref * dout).sum() + (pref * dw).sum()).backward()
+    d.dprobs_extra = dw.data_ptr()
+    _lib.check(lib.gtos_attn_bwd(C.byref(d), st), "attn_bwd")
+    torch.cuda.synchronize()
+    assert rel_err(dq, q.grad) < 1e-4 and rel_err(dk, k.grad) < 1e-4 and rel_err(dv, v.grad) < 1e-4
+
+
+def test_add_ln_and_ffn(dev):
+    from gtos_b200 import ops
+    M, D, Fd = 300, 128, 256
+    x = torch.randn(M, D, device=dev, requires_grad=True)
+    res = torch.randn(M, D, device=dev, requires_grad=True)
+    g = (1 + 0.1 * torch.randn(D, device=dev)).requires_grad_()
+    b = (0.1 * torch.randn(D, device=dev)).requires_grad_()
+    y, yb = ops.add_layer_norm(x, res, g, b, 0.0)
+    ref = torch.nn.functional.layer_norm(x + res, (D,), g, b)
+    assert rel_err(y, ref) < 1e-5 and rel_err(yb.float(), ref) < 1e-2
+    w = torch.randn_like(y)
+    gs = torch.autograd.grad((y * w).sum(), [x, res, g, b])
+    rs = torch.autograd.grad((ref * w).sum(), [x, res, g, b])
+    for a, r in zip(gs, rs):
+        assert rel_err(a, r) < 1e-4
+    W1 = (torch.randn(Fd, D, device=dev) * 0.1).requires_grad_()
+    b1 = (torch.randn(Fd, device=dev) * 0.1).requires_grad_()
+    W2 = (torch.randn(D, Fd, device=dev) * 0.1).requires_grad_()
+    b2 = (torch.randn(D, device=dev) * 0.1).requires_grad_()
+    h = ops.ffn(x, None, W1, b1, W2, b2, 0.0)
+    href = torch.relu(x @ W1.t() + b1) @ W2.t() + b2
+    assert rel_err(h, href) < 1e-2
+    gs = torch.autograd.grad((h * w).sum(), [x, W1, b1, W2, b2])
+    rs = torch.autograd.grad((href * w).sum(), [x, W1, b1, W2, b2])
+    for a, r in zip(gs, rs):
+        assert rel_err(a, r) < 2e-2
+
+
+def test_dropout_statistics(dev):
+    """p > 0 can only be tested statistically: keep rate, 1/(1-p) scaling, determinism per seed."""
+    from gtos_b200 import ops
+    x = torch.ones(1 << 20, device=dev)
+    seed = ops.rng_state(dev)
+    off = ops.new_seed_off()
+    y = ops.dropout_f32(x, 0.2, seed, off)
+    y2 = ops.dropout_f32(x, 0.2, seed, off)
+    keep = (y != 0).float().mean().item()
+    assert abs(keep - 0.8) < 5e-3
+    assert torch.equal(y, y2)
+    assert abs(y.max().item() - 1.25) < 1e-6
+    y3 = ops.dropout_f32(x, 0.2, seed, ops.new_seed_off())
+    assert not torch.equal(y, y3)

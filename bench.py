@@ -1,0 +1,437 @@
+#!/usr/bin/env python
+"""bench.py -- gtos hot path on B200: encoder node-pairs/s (+ decoder tokens/s), roofline, CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2]
+
+One "step" = one pass of the hot path over one synthetic AMR-shaped batch per GPU (BASELINE.json config 2:
+4 graph layers + 1 sentence layer + 3 inference layers, 512 dim, 8 heads, batch 64 graphs of <= 40 nodes):
+RelationEncoder -> bank gather -> GraphTransformer -> snt Transformer -> DecodeLayer -> loss, forward and
+backward, training mode (dropout 0.2), plus the data-parallel gradient all-reduce when N > 1.  The
+optimizer step is outside the hot path.
+
+`value` is timed with the batch resident in HBM and the whole step replayed as one CUDA graph; `e2e` runs the
+same step from pinned HOST buffers through the public API (H2D of every input + D2H of the loss inside the
+timed region).  `--impl reference` times the reference's CPU implementation of the same path (the oracle
+port; the reference itself is Python and is not present on the GPU box) on a bounded sample of the workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (B per GPU, n_max nodes, T_max, T_min, max relation path len)
+    "cfg1": dict(B=8, n_max=16, T_max=20, T_min=10, path=4, D=128, F=256, H=8, gl=2, sl=1, il=1, rnn=64, V=2000),
+    "cfg2": dict(B=64, n_max=40, T_max=60, T_min=20, path=4, D=512, F=1024, H=8, gl=4, sl=1, il=3, rnn=256, V=10000),
+}
+METRIC = "encoder_node_pairs_per_sec"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
+    ap.add_argument("--dropout", type=float, default=0.2)
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of one CUDA graph")
+    ap.add_argument("--cpu-sample-graphs", type=int, default=4, help="graphs per CPU-baseline step")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def make_cfg(w, dropout):
+    from gtos_b200.hotpath import HotPathConfig
+    return HotPathConfig(embed_dim=w["D"], ff_embed_dim=w["F"], num_heads=w["H"], graph_layers=w["gl"],
+                         snt_layers=w["sl"], inference_layers=w["il"], rnn_hidden_size=w["rnn"], dropout=dropout,
+                         vocab_size=w["V"])
+
+
+def make_host_batch(w, B, seed):
+    from gtos_b200 import hotpath, synthetic
+    g = synthetic.make_batch(B, w["n_max"], w["D"], T_max=w["T_max"], T_min=w["T_min"], V=w["V"],
+                             max_path_len=w["path"], seed=seed)
+    b = hotpath.batch_tensors(g)
+    meta = dict(N=g["N"], T=g["T"], B=B, R=int(g["relation_bank"].shape[1]),
+                tokens=int(g["t_len"].sum()), pairs=B * g["N"] * g["N"],
+                valid_pairs=int(((g["node_counts"] + 1) ** 2).sum()), tot_ext=1 + int(g["copy_seq"].max()))
+    return b, meta
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md): nvidia-smi during the timed region
+# ------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(r[1]) for r in self.rows if len(r) >= 9 and r[1].isdigit())
+        mx = max([int(r[2]) for r in self.rows if len(r) >= 9 and r[2].isdigit()] or [0])
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower() == "active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(bf16_tflops=d["bf16_tflops"], bf16_tflops_sustained=d.get("bf16_tflops_sustained"),
+                    hbm_gbs=d["hbm_gbs"], source="MEASURED_PEAKS.json (measured)")
+    return dict(bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, hbm_gbs=6650.0, source="B200_PROFILING.md fallback")
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_step_fn(w, cfg, B, seed):
+    from gtos_b200 import hotpath
+    from oracle import hotpath_oracle as HO
+    torch.manual_seed(seed)
+    m = hotpath.HotPath(cfg)
+    P = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in m.state_dict().items()}
+    b, meta = make_host_batch(w, B, seed)
+    params = [v for v in P.values() if v.requires_grad]
+
+    def step():
+        for v in params:
+            v.grad = None
+        loss = HO.hotpath_loss(P, b, cfg, dropout=cfg.dropout, training=cfg.dropout > 0)
+        loss.backward()
+        return float(loss.detach())
+
+    return step, meta
+
+
+def run_cpu(w, cfg, B, steps, warmup, seed):
+    torch.set_num_threads(os.cpu_count())
+    step, meta = cpu_step_fn(w, cfg, B, seed)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return dt, meta
+
+
+def cpu_model_name():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = WORKLOADS[args.workload]
+    cfg = make_cfg(w, args.dropout)
+    B = args.cpu_sample_graphs
+    dt, meta = run_cpu(w, cfg, B, args.steps, max(1, min(args.warmup, 2)), 19940117)
+    val = meta["pairs"] / dt
+    cores = os.cpu_count()
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "node-pairs/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "decoder_tokens_per_sec": meta["tokens"] / dt,
+            "config": {"workload": f"{args.workload}: gtos generator/ default (4 graph + 1 snt + 3 inference layers, "
+                                   f"{w['D']} dim, {w['H']} heads), synthetic <= {w['n_max']}-node graphs, fwd+bwd, "
+                                   f"dropout {args.dropout}", "graphs_per_step": B, "nodes_incl_cls": meta["N"]},
+            "cpu_baseline": {"value": val, "unit": "node-pairs/s", "cores": cores, "kind": "port",
+                             "sample": f"{B} of {w['B']} graphs per step (CPU oracle port of the reference path, "
+                                       f"{cpu_model_name()})"},
+            "e2e": {"value": val, "unit": "node-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def main_ours(args):
+    import torch.distributed as dist
+    from gtos_b200 import _lib, hotpath, ops
+    from gtos_b200.dp import FlatGradBucket
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    _lib.check(lib.gtos_device_check(), "device_check")
+    w = WORKLOADS[args.workload]
+    cfg = make_cfg(w, args.dropout)
+    torch.manual_seed(19940117)                       # identical replicas on every rank
+    model = hotpath.HotPath(cfg).to(dev)
+    model.train(args.dropout > 0)
+    host, meta = make_host_batch(w, w["B"], 19940117 + rank)          # each rank owns its shard of the global batch
+    model.decoder.token_generator.static_tot_ext = meta["tot_ext"]   # known on the host: no .item() sync
+    pinned = {k: v.pin_memory() for k, v in host.items()}
+    static = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+    bucket = FlatGradBucket(model.parameters())
+    loss_buf = torch.zeros((), device=dev)
+    loss_host = torch.zeros((), pin_memory=True)
+
+    def upload():
+        for k in static:
+            static[k].copy_(pinned[k], non_blocking=True)
+
+    def compute():
+        bucket.zero()
+        ops.advance_rng(dev)
+        loss = model(static)
+        loss.backward()
+        loss_buf.copy_(loss.detach())
+
+    upload()
+    torch.cuda.synchronize()
+    # --- warm-up eagerly (also counts kernel launches of one step), then capture the step as one CUDA graph ---
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            compute()
+        side.synchronize()
+        l0 = lib.gtos_launch_count()
+        compute()
+        launches_per_step = lib.gtos_launch_count() - l0
+        side.synchronize()
+        graph = None
+        if not args.no_graph:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                compute()
+    torch.cuda.synchronize()
+
+    def step_device():
+        if graph is not None:
+            graph.replay()
+        else:
+            compute()
+        bucket.all_reduce_mean()
+
+    def step_e2e():
+        upload()
+        step_device()
+        loss_host.copy_(loss_buf, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, clocks=None):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        if clocks:
+            clocks.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ck = clocks.stop() if clocks else None
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, ck
+
+    ms, clocks = timed(step_device, args.steps, max(3, args.warmup), Clocks(local) if rank == 0 else None)
+    ms_e2e, _ = timed(step_e2e, args.steps, 3)
+    loss_val = float(loss_buf.item())
+
+    # --- breakdown on rank 0: encoder-only and decoder-only steps, and the dominant kernel alone ---
+    extra = {}
+    if rank == 0:
+        extra = breakdown(args, w, cfg, model, static, meta, dev, lib)
+    total_pairs = meta["pairs"] * world
+    total_tokens = meta["tokens"] * world
+    if world > 1:
+        t = torch.tensor([float(meta["pairs"]), float(meta["tokens"])], device=dev)
+        dist.all_reduce(t)
+        total_pairs, total_tokens = t[0].item(), t[1].item()
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    line = {
+        "metric": METRIC, "value": total_pairs / (ms * 1e-3), "unit": "node-pairs/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "decoder_tokens_per_sec": total_tokens / (ms * 1e-3),
+        "config": {"workload": f"{args.workload}: gtos generator/ default (4 graph + 1 snt + 3 inference layers, "
+                               f"{w['D']} dim, {w['H']} heads), synthetic <= {w['n_max']}-node graphs, fwd+bwd, "
+                               f"dropout {args.dropout}", "graphs_per_gpu": w["B"], "global_batch": w["B"] * world,
+                   "nodes_incl_cls": meta["N"], "tgt_len": meta["T"], "distinct_relation_paths": meta["R"],
+                   "parallelism": f"dp{world}", "step": "RelationEncoder+gather+GraphTransformer+snt+DecodeLayer "
+                   "fwd+bwd (+ flat-gradient all-reduce when dp>1); optimizer outside the hot path",
+                   "cuda_graph": graph is not None,
+                   "l2": "per-step working set (dense relation fp32+bf16 = %d MB) exceeds the 126 MB L2"
+                         % (meta["pairs"] * w["D"] * 6 // 2 ** 20)},
+        "e2e": {"value": total_pairs / (ms_e2e * 1e-3), "unit": "node-pairs/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                "decoder_tokens_per_sec": total_tokens / (ms_e2e * 1e-3)},
+        "gpu_launches": int(launches_per_step) * args.steps,
+        "gpu_launches_per_step": int(launches_per_step),
+        "loss": loss_val, "clocks": clocks, "peaks": pk,
+    }
+    line.update(extra)
+    if not args.skip_cpu_baseline and world == 1:
+        Bc = args.cpu_sample_graphs
+        dt, mc = run_cpu(w, cfg, Bc, 3, 1, 19940117)
+        line["cpu_baseline"] = {"value": mc["pairs"] / dt, "unit": "node-pairs/s", "cores": os.cpu_count(),
+                                "kind": "port", "ms_per_step": dt * 1e3,
+                                "decoder_tokens_per_sec": mc["tokens"] / dt,
+                                "sample": f"{Bc} of {w['B']} graphs per step, 3 steps after 1 warm-up "
+                                          f"(CPU oracle port of the reference path, {cpu_model_name()})"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def breakdown(args, w, cfg, model, static, meta, dev, lib):
+    """Encoder-only / decoder-only step times and the dominant kernel (fused relation projection+score) timed
+    alone with CUDA events on its launch stream -> roofline."""
+    from gtos_b200 import _lib, ops
+    N, B, D, H = meta["N"], meta["B"], w["D"], w["H"]
+    out = {}
+
+    def time_fn(fn, steps=10, warmup=3):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    # encoder only: GraphTransformer fwd+bwd on a dense relation tensor (the graded contract)
+    with torch.no_grad():
+        bank = model.relation_encoder(static["relation_bank"], static["relation_length"])
+        rel = bank.index_select(0, static["relation"].reshape(-1)).view(N, N, B, D).contiguous()
+    rel.requires_grad_()
+    x = static["x"].clone().requires_grad_()
+
+    def enc_step():
+        x.grad = rel.grad = None
+        y = model.graph_encoder(x, rel, self_padding_mask=static["node_mask"])
+        y.backward(y)                                   # d(0.5*||y||^2): a dense upstream gradient
+
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            enc_step()
+        s.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            enc_step()
+    torch.cuda.synchronize()
+    ms_enc = time_fn(g.replay)
+    L = w["gl"]
+    flops_pair_layer_fwd = 4 * D * D + 4 * D
+    flops_node_layer_fwd = 8 * D * D + 4 * D * w["F"]
+    enc_flops = L * 3 * (meta["pairs"] * flops_pair_layer_fwd + N * B * flops_node_layer_fwd)
+    out["encoder_only"] = {"ms_per_step": ms_enc, "node_pairs_per_sec": meta["pairs"] / (ms_enc * 1e-3),
+                           "algorithmic_tflops": enc_flops / (ms_enc * 1e-3) / 1e12,
+                           "note": "GraphTransformer (%d layers) fwd+bwd on the dense relation tensor" % L}
+
+    # dominant kernel alone: gtos_rel_score (relation projection + score epilogue), one layer's launch
+    relb = ops.relation_to_bf16(rel.detach())
+    Wr = model.graph_encoder.layers[0].self_attn.relation_in_proj.weight
+    Wperm, WpermT = ops.weight_prep(Wr, rel_heads=H)
+    qkv = torch.randn(N * B, 3 * D, device=dev)
+    scores = torch.empty(B, H, N, N, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def k_score():
+        _lib.check(lib.gtos_rel_score(relb.data_ptr(), Wperm.data_ptr(), qkv.data_ptr(), qkv.data_ptr() + 4 * D,
+                                      3 * D, scores.data_ptr(), N, B, D, H, st), "rel_score")
+
+    ms_k = time_fn(k_score, steps=20, warmup=3)
+    kflops = meta["pairs"] * (4 * D * D + 2 * D)
+    pk = peaks()
+    ach = kflops / (ms_k * 1e-3) / 1e12
+    out["roofline"] = {"kernel": "gemm_tn_kernel<256, MODE_SCORE> (gtos_rel_score: relation_in_proj GEMM + score epilogue)",
+                       "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                       "frac": ach / pk["bf16_tflops"], "traffic": None, "ms_per_launch": ms_k,
+                       "algorithmic_flops_per_launch": kflops,
+                       "algorithmic_bytes_per_launch": meta["pairs"] * D * 2,
+                       "peak_source": pk["source"] + ", burst bf16 cuBLAS (kernel timed alone)",
+                       "tile_utilisation": meta["pairs"] / (ops.rel_tiling(N, B, D, H)["tiles"] * 128)}
+    # the other three relation GEMMs of the backward
+    tiles = ops.rel_tiling(N, B, D, H)["tiles"]
+    G = torch.empty(tiles * 128, 2 * D, dtype=torch.bfloat16, device=dev)
+    ds = torch.randn(B, H, N, N, device=dev)
+    drel = torch.empty(N, N, B, D, device=dev)
+    ws_n = lib.gtos_rel_dw_workspace(N, B, D, H)
+    ws = torch.empty(ws_n, device=dev)
+    dW = torch.empty(2 * D, D, device=dev)
+    t_grad = time_fn(lambda: _lib.check(lib.gtos_rel_grad(relb.data_ptr(), Wperm.data_ptr(), qkv.data_ptr(),
+                                                          qkv.data_ptr() + 4 * D, 3 * D, ds.data_ptr(), G.data_ptr(), N, B,
+                                                          D, H, st)))
+    t_drel = time_fn(lambda: _lib.check(lib.gtos_rel_drel(G.data_ptr(), WpermT.data_ptr(), drel.data_ptr(), 0, N, B, D, H, st)))
+    t_dw = time_fn(lambda: _lib.check(lib.gtos_rel_dw(G.data_ptr(), relb.data_ptr(), dW.data_ptr(), ws.data_ptr(), ws_n,
+                                                      N, B, D, H, st)))
+    f = meta["pairs"] * 4 * D * D / 1e12
+    out["relation_kernels"] = {"rel_score_ms": ms_k, "rel_grad_ms": t_grad, "rel_drel_ms": t_drel, "rel_dw_ms": t_dw,
+                               "tflops": {"rel_score": f / (ms_k * 1e-3), "rel_grad": f / (t_grad * 1e-3),
+                                          "rel_drel": f / (t_drel * 1e-3), "rel_dw": f / (t_dw * 1e-3)}}
+    return out
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_ours(a)

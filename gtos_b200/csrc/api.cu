@@ -8,6 +8,7 @@
 
 namespace gtos {
 static thread_local char g_err[512] = "";
+unsigned long long g_kernel_launches = 0;
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -23,6 +24,7 @@ extern "C" {
 
 const char* gtos_last_error(void) { return g_err; }
 int gtos_abi_version(void) { return 1; }
+uint64_t gtos_launch_count(void) { return __atomic_load_n(&g_kernel_launches, __ATOMIC_RELAXED); }
 
 int gtos_device_check(void) {
   int dev = 0, major = 0;

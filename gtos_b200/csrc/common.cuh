@@ -16,6 +16,7 @@ namespace gtos {
 // ---------------------------------------------------------------------------------------
 // error codes: GTOS_OK / GTOS_ERR_* from the public header
 void set_error(const char* fmt, ...);
+extern unsigned long long g_kernel_launches;  // kernels enqueued through this library (api.cu)
 
 #define GTOS_CHECK_CUDA(expr)                                                        \
   do {                                                                               \
@@ -32,7 +33,11 @@ void set_error(const char* fmt, ...);
       return GTOS_ERR_ARG;                                                     \
     }                                                                                \
   } while (0)
-#define GTOS_LAUNCH_CHECK() GTOS_CHECK_CUDA(cudaGetLastError())
+#define GTOS_LAUNCH_CHECK()                                       \
+  do {                                                            \
+    __atomic_fetch_add(&gtos::g_kernel_launches, 1ull, __ATOMIC_RELAXED); \
+    GTOS_CHECK_CUDA(cudaGetLastError());                          \
+  } while (0)
 
 #if defined(__CUDACC__)
 // ---------------------------------------------------------------------------------------

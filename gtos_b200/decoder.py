@@ -1,0 +1,107 @@
+"""B200-native drop-in for the reference's ``decoder.py``: DecodeLayer (+ TokenGenerator).
+
+DecodeLayer's three attention layers (masked self-attn over the token states + cross-attn over the
+graph, generator/decoder.py:76-94) and the TokenGenerator's 1-head alignment attention run through the
+sm_100a kernels.  The vocabulary tail of TokenGenerator (tanh-Linear, two softmaxes, copy scatter, NLL;
+decoder.py:39-64) is SURVEY.md §8 row f-2 ("next") and is kept as PyTorch ops here.
+"""
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import ops
+from .transformer import MultiheadAttention, Transformer
+
+
+class TokenGenerator(nn.Module):
+    """reference: decoder.py:10-65"""
+
+    def __init__(self, vocabs, embed_dim, token_size, dropout):
+        super().__init__()
+        self.alignment_layer = MultiheadAttention(embed_dim, 1, dropout, weights_dropout=False)
+        self.alignment_layer_norm = nn.LayerNorm(embed_dim)
+        self.transfer = nn.Linear(embed_dim, token_size)
+        self.generator = nn.Linear(token_size, vocabs['predictable_token'].size)
+        self.diverter = nn.Linear(token_size, 2)
+        self.vocabs = vocabs
+        self.dropout = dropout
+        # size of the batch-extended vocabulary; the reference reads it back from the device every call
+        # (copy_seq.max().item(), decoder.py:46).  A caller that knows it on the host (the data loader
+        # does) can set it to avoid the sync and make the step CUDA-graph capturable.
+        self.static_tot_ext = None
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        nn.init.normal_(self.transfer.weight, std=0.02)
+        nn.init.normal_(self.diverter.weight, std=0.02)
+        nn.init.normal_(self.generator.weight, std=0.02)
+        nn.init.constant_(self.diverter.bias, 0.)
+        nn.init.constant_(self.transfer.bias, 0.)
+        nn.init.constant_(self.generator.bias, 0.)
+
+    def forward(self, outs, graph_state, graph_padding_mask, copy_seq, target=None, work=False):
+        p = self.dropout if self.training else 0.0
+        x, alignment_weight = self.alignment_layer(outs, graph_state, graph_state,
+                                                   key_padding_mask=graph_padding_mask, need_weights=True)
+        outs, _ = ops.add_layer_norm(x, outs, self.alignment_layer_norm.weight, self.alignment_layer_norm.bias, p)
+        seq_len, bsz, _ = outs.size()
+        # ---- vocabulary tail: PyTorch ops ----
+        outs_token = torch.tanh(self.transfer(outs))
+        outs_token = F.dropout(outs_token, p=self.dropout, training=self.training)
+        gen_gate, copy_gate = F.softmax(self.diverter(outs_token), -1).chunk(2, dim=-1)
+        probs = gen_gate * F.softmax(self.generator(outs_token), -1)
+        tot_ext = self.static_tot_ext if self.static_tot_ext is not None else 1 + copy_seq.max().item()
+        vocab_size = probs.size(-1)
+        if tot_ext - vocab_size > 0:
+            ext_probs = probs.new_zeros((1, 1, tot_ext - vocab_size)).expand(seq_len, bsz, -1)
+            probs = torch.cat([probs, ext_probs], -1)
+        index = copy_seq.transpose(0, 1).contiguous().view(1, bsz, -1).expand(seq_len, -1, -1)
+        copy_probs = (copy_gate * alignment_weight).view(seq_len, bsz, -1)
+        probs = probs.scatter_add(-1, index, copy_probs)
+        ll = torch.log(probs + 1e-12)
+        if work:
+            return ll
+        token_loss = -ll.gather(dim=-1, index=target.unsqueeze(-1)).squeeze(-1)
+        token_mask = torch.eq(target, self.vocabs['predictable_token'].padding_idx)
+        token_loss = token_loss.masked_fill(token_mask, 0.).sum(0)
+        return token_loss
+
+
+class DecodeLayer(nn.Module):
+    """reference: decoder.py:67-94"""
+
+    def __init__(self, vocabs, inference_layers, embed_dim, ff_embed_dim, num_heads, token_size, rel_size, dropout):
+        super().__init__()
+        self.inference_core = Transformer(inference_layers, embed_dim, ff_embed_dim, num_heads, dropout,
+                                          with_external=True)
+        self.token_generator = TokenGenerator(vocabs, embed_dim, token_size, dropout)
+        self.dropout = dropout
+        self.vocabs = vocabs
+
+    def forward(self, probe, graph_state, snt_state, graph_padding_mask, snt_padding_mask, attn_mask, copy_seq,
+                target=None, work=False):
+        # probe: tgt_len x bsz x embed_dim ; snt_state, graph_state: seq_len x bsz x embed_dim
+        outs = probe
+        if self.training and self.dropout > 0:                                     # decoder.py:82
+            outs = _DropoutFn.apply(probe, float(self.dropout))
+        outs = self.inference_core(outs, kv=snt_state, self_padding_mask=snt_padding_mask, self_attn_mask=attn_mask,
+                                   external_memories=graph_state, external_padding_mask=graph_padding_mask)
+        if work:
+            return self.token_generator(outs, graph_state, graph_padding_mask, copy_seq, work=True)
+        token_loss = self.token_generator(outs, graph_state, graph_padding_mask, copy_seq, target=target, work=False)
+        token_tot = snt_padding_mask.size(0) - snt_padding_mask.float().sum(0)
+        token_loss = token_loss / token_tot
+        return token_loss.mean()
+
+
+class _DropoutFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p):
+        seed, off = ops.rng_state(x.device), ops.new_seed_off()
+        ctx.meta = (p, seed, off)
+        return ops.dropout_f32(x.contiguous(), p, seed, off)
+
+    @staticmethod
+    def backward(ctx, dy):
+        p, seed, off = ctx.meta
+        return ops.dropout_f32(dy.contiguous(), p, seed, off), None

@@ -467,3 +467,128 @@ class MHAFn(torch.autograd.Function):
             dk_in = dk_in.view(S, B, D)
         return (dq_in.view(T, B, D), None, dk_in, None, None, None, None, dW_in, db_in, dW_out, db_out, None, None,
                 None, None)
+
+
+# --------------------------------------------------------------------------------------------
+# RelationEncoder: embedding -> packed 2-layer bidirectional GRU -> Linear  (encoder.py:90-119)
+# --------------------------------------------------------------------------------------------
+def _gate_fwd(gi_t, gh, h_prev, lengths, t, h_new, hb_new, out_t, outb_t, gates_t, R, Hh):
+    _lib.check(_lib.load().gtos_gru_gate_fwd(_p(gi_t), gi_t.stride(0), _p(gh), gh.stride(0), _p(h_prev), _p(lengths), t,
+                                             _p(h_new), _p(hb_new), _p(out_t),
+                                             out_t.stride(0) if out_t is not None else 0, _p(outb_t),
+                                             outb_t.stride(0) if outb_t is not None else 0, _p(gates_t), R, Hh, _st()),
+               "gru_gate_fwd")
+
+
+class GRUBankFn(torch.autograd.Function):
+    """tokens [Lmax,R] int64 (0 = pad), lengths [R] int64 -> [R, embed_dim].  `weights` is the flat list
+    (w_ih, w_hh, b_ih, b_hh) per (layer, direction) in nn.GRU order."""
+
+    @staticmethod
+    def forward(ctx, tokens, lengths, embed_w, out_w, out_b, num_layers, hidden, p, *weights):
+        _need_cuda(tokens, lengths, embed_w)
+        lib = _lib.load()
+        dev = embed_w.device
+        Lmax, R = tokens.shape
+        E = embed_w.shape[1]
+        Hh = hidden
+        rows = Lmax * R
+        tokens = tokens.contiguous()
+        lengths = lengths.contiguous()
+        seed = rng_state(dev) if p > 0 else None
+        off_e = new_seed_off() if p > 0 else 0
+        xb = torch.empty(rows, _up8(E), dtype=torch.bfloat16, device=dev)
+        _lib.check(lib.gtos_embed_gather(_p(embed_w), _p(tokens), rows, E, None, _p(xb), _up8(E), p, _p(seed), off_e,
+                                         _st()), "embed_gather")
+        saved, layer_offs = [], []
+        finals_b = torch.empty(R, 2 * Hh, dtype=torch.bfloat16, device=dev)
+        for l in range(num_layers):
+            outb = torch.empty(rows, 2 * Hh, dtype=torch.bfloat16, device=dev)
+            for d in range(2):
+                w_ih, w_hh, b_ih, b_hh = weights[(l * 2 + d) * 4:(l * 2 + d) * 4 + 4]
+                Wih_b, Wih_t = weight_prep(w_ih)
+                Whh_b, Whh_t = weight_prep(w_hh)
+                gi_all, _ = gemm_tn(xb, Wih_b, 3 * Hh, bias=b_ih)                  # [rows, 3H]
+                # per-direction state indexed by processing step s (time t = s forward, Lmax-1-s reverse):
+                # hs[s] = state before step s, hs[s+1] = state after it
+                gates = torch.empty(Lmax, R, 3 * Hh, dtype=torch.float32, device=dev)
+                gh_all = torch.empty(Lmax, R, 3 * Hh, dtype=torch.float32, device=dev)
+                hs = torch.empty(Lmax + 1, R, Hh, dtype=torch.float32, device=dev)
+                hsb = torch.empty(Lmax + 1, R, Hh, dtype=torch.bfloat16, device=dev)
+                hs[0].zero_()
+                hsb[0].zero_()
+                for s in range(Lmax):
+                    t = s if d == 0 else Lmax - 1 - s
+                    gemm_tn(hsb[s], Whh_b, 3 * Hh, bias=b_hh, out=gh_all[s])
+                    _gate_fwd(gi_all[t * R:(t + 1) * R], gh_all[s], hs[s], lengths, t, hs[s + 1], hsb[s + 1], None,
+                              outb[t * R:(t + 1) * R, d * Hh:(d + 1) * Hh], gates[s], R, Hh)
+                hb = hsb[Lmax]
+                if l == num_layers - 1:
+                    finals_b[:, d * Hh:(d + 1) * Hh].copy_(hb)
+                saved += [xb, gates, gh_all, hs, hsb, Wih_t, Whh_t]
+            off_l = 0
+            if l < num_layers - 1 and p > 0:                                       # nn.GRU inter-layer dropout
+                off_l = new_seed_off()
+                _lib.check(lib.gtos_dropout_bf16(_p(outb), outb.numel(), p, _p(seed), off_l, _st()), "dropout_bf16")
+            layer_offs.append(off_l)
+            xb = outb
+        Wo_b, Wo_t = weight_prep(out_w)
+        out, _ = gemm_tn(finals_b, Wo_b, out_w.shape[0], bias=out_b)
+        ctx.save_for_backward(tokens, lengths, finals_b, Wo_t, *saved)
+        ctx.meta = (Lmax, R, E, Hh, num_layers, p, seed, off_e, layer_offs, out_w.shape[0], embed_w.shape[0])
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        tokens, lengths, finals_b, Wo_t, *saved = ctx.saved_tensors
+        Lmax, R, E, Hh, num_layers, p, seed, off_e, layer_offs, Dout, V = ctx.meta
+        lib = _lib.load()
+        dev = dout.device
+        rows = Lmax * R
+        dout = dout.contiguous()
+        doutb = cast_bf16(dout)
+        dW_out = gemm_nn(doutb, finals_b, Dout, 2 * Hh)
+        db_out = colsum(dout)
+        dfinals, _ = gemm_tn(doutb, Wo_t, 2 * Hh)                                   # [R, 2H]
+        wgrads = [None] * (num_layers * 8)
+        d_layer_out = None                                                         # [rows, 2H] fp32
+        for l in range(num_layers - 1, -1, -1):
+            dx = None
+            for d in range(2):
+                xb, gates, gh_all, hs, hsb, Wih_t, Whh_t = saved[(l * 2 + d) * 7:(l * 2 + d) * 7 + 7]
+                Kin = Wih_t.shape[0]
+                dgi = torch.empty(rows, 3 * Hh, dtype=torch.bfloat16, device=dev)      # rows in time order t
+                dgh = torch.empty(rows, 3 * Hh, dtype=torch.bfloat16, device=dev)      # rows in step order s
+                if l == num_layers - 1:
+                    dh = dfinals[:, d * Hh:(d + 1) * Hh].contiguous()
+                else:
+                    dh = torch.zeros(R, Hh, dtype=torch.float32, device=dev)
+                for s in range(Lmax - 1, -1, -1):
+                    t = s if d == 0 else Lmax - 1 - s
+                    dout_t = d_layer_out[t * R:(t + 1) * R, d * Hh:(d + 1) * Hh] if d_layer_out is not None else None
+                    dh_prev = torch.empty_like(dh)
+                    _lib.check(lib.gtos_gru_gate_bwd(_p(dh), _p(dout_t), dout_t.stride(0) if dout_t is not None else 0,
+                                                     _p(gates[s]), _p(gh_all[s]), 3 * Hh, _p(hs[s]), _p(lengths), t,
+                                                     _p(dh_prev), _p(dgi[t * R:(t + 1) * R]), 3 * Hh,
+                                                     _p(dgh[s * R:(s + 1) * R]), 3 * Hh, R, Hh, _st()), "gru_gate_bwd")
+                    gemm_tn(dgh[s * R:(s + 1) * R], Whh_t, Hh, out=dh_prev, accumulate=True)
+                    dh = dh_prev
+                base = (l * 2 + d) * 4
+                wgrads[base + 0] = gemm_nn(dgi, xb, 3 * Hh, Kin)
+                wgrads[base + 1] = gemm_nn(dgh, hsb[:Lmax].view(rows, Hh), 3 * Hh, Hh)
+                wgrads[base + 2] = colsum(dgi)
+                wgrads[base + 3] = colsum(dgh)
+                if dx is None:
+                    dx, _ = gemm_tn(dgi, Wih_t, Kin)
+                else:
+                    gemm_tn(dgi, Wih_t, Kin, out=dx, accumulate=True)
+            if l > 0:
+                if layer_offs[l - 1]:
+                    dropout_f32(dx, p, seed, layer_offs[l - 1], out=dx)
+                d_layer_out = dx
+            else:
+                d_embed = torch.zeros(V, E, dtype=torch.float32, device=dev)
+                _lib.check(lib.gtos_embed_scatter_add(_p(dx), _p(tokens), rows, E, _p(d_embed), p, _p(seed), off_e,
+                                                      _st()), "embed_scatter_add")
+        return (None, None, d_embed, dW_out, db_out, None, None, None, *wgrads)

@@ -32,6 +32,8 @@ extern "C" {
 
 const char* gtos_last_error(void);
 int gtos_abi_version(void);
+/* number of CUDA kernels this library has enqueued so far in this process (bench.py's gpu_launches) */
+uint64_t gtos_launch_count(void);
 /* 0 if the current device is sm_100 and the TMA driver entry point resolves */
 int gtos_device_check(void);
 

@@ -34,8 +34,47 @@ import torch.nn.functional as F
 NEG_INF = float("-inf")
 
 
+# Matmul arithmetic of the oracle.  "fp32" is the reference's arithmetic.  "bf16" restates what the
+# sm_100a tensor cores compute: both operands of every Linear rounded to bfloat16, products accumulated in
+# fp32, and in backward the incoming gradient rounded to bfloat16 before the two gradient GEMMs.  It exists
+# so gradient parity can be asserted tightly against a same-rounding reference (ReLU-kink flips make a bf16
+# run differ from the fp32 one by several % in max-norm whatever the implementation).
+_PRECISION = "fp32"
+
+
+def set_matmul_precision(mode):
+    global _PRECISION
+    assert mode in ("fp32", "bf16")
+    _PRECISION = mode
+
+
+def _bf(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+class _LinBf16(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w):
+        xb, wb = _bf(x), _bf(w)
+        ctx.save_for_backward(xb, wb)
+        return xb @ wb.t()
+
+    @staticmethod
+    def backward(ctx, g):
+        xb, wb = ctx.saved_tensors
+        gb = _bf(g)
+        dx = gb @ wb
+        dw = gb.reshape(-1, gb.shape[-1]).t() @ xb.reshape(-1, xb.shape[-1])
+        return dx, dw
+
+
+def _lin32(x, w, b):
+    """always-fp32 Linear: the TokenGenerator vocabulary tail, which the B200 path keeps in fp32"""
+    return x @ w.t() + b
+
+
 def _lin(x, w, b=None):
-    y = x @ w.t()
+    y = _LinBf16.apply(x, w) if _PRECISION == "bf16" else x @ w.t()
     return y if b is None else y + b
 
 
@@ -236,11 +275,11 @@ def token_generator(P, pre, outs, graph_state, graph_padding_mask, copy_seq, pad
     outs = _layer_norm(outs + _drop(a, dropout, training),
                        P[pre + "alignment_layer_norm.weight"], P[pre + "alignment_layer_norm.bias"])
     T, B, _ = outs.shape
-    tok = torch.tanh(_lin(outs, P[pre + "transfer.weight"], P[pre + "transfer.bias"]))
+    tok = torch.tanh(_lin32(outs, P[pre + "transfer.weight"], P[pre + "transfer.bias"]))
     tok = _drop(tok, dropout, training)
-    gate = torch.softmax(_lin(tok, P[pre + "diverter.weight"], P[pre + "diverter.bias"]), -1)
+    gate = torch.softmax(_lin32(tok, P[pre + "diverter.weight"], P[pre + "diverter.bias"]), -1)
     gen_gate, copy_gate = gate[..., :1], gate[..., 1:]
-    probs = gen_gate * torch.softmax(_lin(tok, P[pre + "generator.weight"], P[pre + "generator.bias"]), -1)
+    probs = gen_gate * torch.softmax(_lin32(tok, P[pre + "generator.weight"], P[pre + "generator.bias"]), -1)
     V = probs.shape[-1]
     tot = 1 + int(copy_seq.max())
     if tot > V:

@@ -22,3 +22,9 @@ def rel_err(a, b):
     """max |a-b| / max(|b|, tiny): scale-free error used by all parity tests."""
     a, b = a.detach().float().cpu(), b.detach().float().cpu()
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+def l2_err(a, b):
+    """||a-b|| / ||b||: robust to the handful of ReLU-kink sign flips a different summation order can cause."""
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()

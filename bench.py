@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of one CUDA graph")
     ap.add_argument("--cpu-sample-graphs", type=int, default=4, help="graphs per CPU-baseline step")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="run ONE eager step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     return ap.parse_args()
 
 
@@ -136,8 +138,20 @@ def cpu_step_fn(w, cfg, B, seed):
     return step, meta
 
 
+def host_threads():
+    """threads the CPU arm may really use: affinity mask and cgroup CPU quota, not the box's core count"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(int(q) / int(per))))
+    except (OSError, ValueError):
+        pass
+    return max(1, min(n, 64))
+
+
 def run_cpu(w, cfg, B, steps, warmup, seed):
-    torch.set_num_threads(os.cpu_count())
+    torch.set_num_threads(host_threads())
     step, meta = cpu_step_fn(w, cfg, B, seed)
     for _ in range(warmup):
         step()
@@ -167,7 +181,7 @@ def main_reference(args):
     B = args.cpu_sample_graphs
     dt, meta = run_cpu(w, cfg, B, args.steps, max(1, min(args.warmup, 2)), 19940117)
     val = meta["pairs"] / dt
-    cores = os.cpu_count()
+    cores = host_threads()
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "node-pairs/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -226,6 +240,15 @@ def main_ours(args):
 
     upload()
     torch.cuda.synchronize()
+    if args.profile_step:
+        for _ in range(2):
+            compute()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        compute()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        return
     # --- warm-up eagerly (also counts kernel launches of one step), then capture the step as one CUDA graph ---
     side = torch.cuda.Stream()
     with torch.cuda.stream(side):
@@ -325,7 +348,7 @@ def main_ours(args):
     if not args.skip_cpu_baseline and world == 1:
         Bc = args.cpu_sample_graphs
         dt, mc = run_cpu(w, cfg, Bc, 3, 1, 19940117)
-        line["cpu_baseline"] = {"value": mc["pairs"] / dt, "unit": "node-pairs/s", "cores": os.cpu_count(),
+        line["cpu_baseline"] = {"value": mc["pairs"] / dt, "unit": "node-pairs/s", "cores": host_threads(),
                                 "kind": "port", "ms_per_step": dt * 1e3,
                                 "decoder_tokens_per_sec": mc["tokens"] / dt,
                                 "sample": f"{Bc} of {w['B']} graphs per step, 3 steps after 1 warm-up "

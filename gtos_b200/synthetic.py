@@ -130,7 +130,7 @@ def make_batch(B, n_max, D, T_max=60, T_min=20, V=10000, max_path_len=4, seed=SE
     tok = torch.nn.functional.layer_norm(torch.randn(T, B, D, generator=gen), (D,))
     tok_mask = torch.arange(T).unsqueeze(1) >= t_len.unsqueeze(0)
     copy_seq = torch.randint(2, V + 16, (N - 1, B), generator=gen)
-    target = torch.randint(2, V + 16, (T, B), generator=gen).masked_fill(tok_mask, 0)
+    target = torch.randint(2, V, (T, B), generator=gen).masked_fill(tok_mask, 0)       # always < tot_ext
     g.update(x=x, node_mask=node_mask, token_repr=tok, token_mask=tok_mask, copy_seq=copy_seq, target=target, T=T,
              t_len=t_len, V=V)
     return g

@@ -412,13 +412,13 @@ def breakdown(args, w, cfg, model, static, meta, dev, lib):
     relb = ops.relation_to_bf16(rel.detach())
     Wr = model.graph_encoder.layers[0].self_attn.relation_in_proj.weight
     Wperm, WpermT = ops.weight_prep(Wr, rel_heads=H)
-    qkv = torch.randn(N * B, 3 * D, device=dev)
+    qkv = torch.randn(N * B, 2 * D, device=dev).to(torch.bfloat16)   # projected [q | k] as the kernels stage them
     scores = torch.empty(B, H, N, N, device=dev)
     st = torch.cuda.current_stream().cuda_stream
 
     def k_score():
-        _lib.check(lib.gtos_rel_score(relb.data_ptr(), Wperm.data_ptr(), qkv.data_ptr(), qkv.data_ptr() + 4 * D,
-                                      3 * D, scores.data_ptr(), N, B, D, H, st), "rel_score")
+        _lib.check(lib.gtos_rel_score(relb.data_ptr(), Wperm.data_ptr(), qkv.data_ptr(), qkv.data_ptr() + 2 * D,
+                                      2 * D, scores.data_ptr(), N, B, D, H, st), "rel_score")
 
     ms_k = time_fn(k_score, steps=20, warmup=3)
     kflops = meta["pairs"] * (4 * D * D + 2 * D)
@@ -440,7 +440,7 @@ def breakdown(args, w, cfg, model, static, meta, dev, lib):
     ws = torch.empty(ws_n, device=dev)
     dW = torch.empty(2 * D, D, device=dev)
     t_grad = time_fn(lambda: _lib.check(lib.gtos_rel_grad(relb.data_ptr(), Wperm.data_ptr(), qkv.data_ptr(),
-                                                          qkv.data_ptr() + 4 * D, 3 * D, ds.data_ptr(), G.data_ptr(), N, B,
+                                                          qkv.data_ptr() + 2 * D, 2 * D, ds.data_ptr(), G.data_ptr(), N, B,
                                                           D, H, st)))
     t_drel = time_fn(lambda: _lib.check(lib.gtos_rel_drel(G.data_ptr(), WpermT.data_ptr(), drel.data_ptr(), 0, N, B, D, H, st)))
     t_dw = time_fn(lambda: _lib.check(lib.gtos_rel_dw(G.data_ptr(), relb.data_ptr(), dW.data_ptr(), ws.data_ptr(), ws_n,

@@ -100,22 +100,22 @@ static int rel_args(GemmTnArgs* a, int32_t N, int32_t B, int32_t D, int32_t H) {
   return GTOS_OK;
 }
 
-int gtos_rel_score(const void* relb, const void* Wperm, const float* q, const float* k, int64_t ldqk, float* scores,
+int gtos_rel_score(const void* relb, const void* Wperm, const void* q, const void* k, int64_t ldqk, float* scores,
                    int32_t N, int32_t B, int32_t D, int32_t H, void* stream) {
   GemmTnArgs a;
   int e = rel_args(&a, N, B, D, H);
   if (e) return e;
-  GTOS_REQUIRE(ldqk % 4 == 0, "rel_score: q/k row stride must be a multiple of 4 floats");
+  GTOS_REQUIRE(ldqk % 8 == 0, "rel_score: q/k row stride must be a multiple of 8 bf16 elements");
   a.A = relb; a.lda = D; a.Bm = Wperm; a.ldb = D; a.q = q; a.k = k; a.ldqk = ldqk; a.scores = scores;
   return launch_gemm_tn(MODE_SCORE, a, S(stream));
 }
 
-int gtos_rel_grad(const void* relb, const void* Wperm, const float* q, const float* k, int64_t ldqk,
+int gtos_rel_grad(const void* relb, const void* Wperm, const void* q, const void* k, int64_t ldqk,
                   const float* dscores, void* G, int32_t N, int32_t B, int32_t D, int32_t H, void* stream) {
   GemmTnArgs a;
   int e = rel_args(&a, N, B, D, H);
   if (e) return e;
-  GTOS_REQUIRE(ldqk % 4 == 0, "rel_grad: q/k row stride must be a multiple of 4 floats");
+  GTOS_REQUIRE(ldqk % 8 == 0, "rel_grad: q/k row stride must be a multiple of 8 bf16 elements");
   a.A = relb; a.lda = D; a.Bm = Wperm; a.ldb = D; a.q = q; a.k = k; a.ldqk = ldqk; a.dscores = dscores; a.G = G;
   return launch_gemm_tn(MODE_GRAD, a, S(stream));
 }

@@ -14,16 +14,16 @@ namespace gtos {
 
 static constexpr int AT_THREADS = 256;
 static constexpr int AT_WARPS = 8;
-static constexpr int AT_ROWS = 32;  // query (or key) rows per CTA
+static constexpr int AT_ROWS_MAX = 64;  // query (or key) rows per CTA: all rows when the sequence is short
 static constexpr int AT_DC = 64;    // feature chunk
 
 struct AttnSmem {
-  float* xs;  // [AT_ROWS][dc+1]
+  float* xs;  // [rows][dc+1]
   float* ys;  // [L][dc+1]
-  float* sc;  // [AT_ROWS][L+1]
+  float* sc;  // [rows][L+1]
 };
 
-__device__ __forceinline__ AttnSmem carve(float* base, int L, int dc) {
+__device__ __forceinline__ AttnSmem carve(float* base, int L, int dc, int AT_ROWS) {
   AttnSmem s;
   s.xs = base;
   s.ys = s.xs + AT_ROWS * (dc + 1);
@@ -76,10 +76,11 @@ __device__ __forceinline__ bool is_masked(const AttnArgs& a, int b, int t, int j
   return false;
 }
 
-__global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnArgs a) {
+__global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnArgs a, const int rows_per_cta) {
   extern __shared__ float smem_f[];
   const int dc = a.hd < AT_DC ? a.hd : AT_DC;
-  const AttnSmem s = carve(smem_f, a.S, dc);
+  const int AT_ROWS = rows_per_cta;
+  const AttnSmem s = carve(smem_f, a.S, dc, AT_ROWS);
   const int bh = blockIdx.x, b = bh / a.H, h = bh % a.H;
   const int t0 = blockIdx.y * AT_ROWS;
   const int nrows = (a.T - t0) < AT_ROWS ? (a.T - t0) : AT_ROWS;
@@ -151,20 +152,22 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnArgs a) 
   }
 }
 
-static size_t attn_smem_bytes(int L, int hd) {
+static int attn_rows(int len) { return len <= AT_ROWS_MAX ? (len < 8 ? 8 : len) : 32; }
+static size_t attn_smem_bytes(int L, int hd, int rows) {
   int dc = hd < AT_DC ? hd : AT_DC;
-  return sizeof(float) * ((size_t)AT_ROWS * (dc + 1) + (size_t)L * (dc + 1) + (size_t)AT_ROWS * (L + 1));
+  return sizeof(float) * ((size_t)rows * (dc + 1) + (size_t)L * (dc + 1) + (size_t)rows * (L + 1));
 }
 
 int attn_fwd(const AttnArgs& a, cudaStream_t st) {
   GTOS_REQUIRE(a.hd >= 1 && (a.hd <= AT_DC || a.hd % AT_DC == 0), "attention: unsupported head_dim %d", a.hd);
   GTOS_REQUIRE(a.p_drop == 0.f || a.seed_ptr, "attention dropout needs a device seed pointer");
   if (a.T == 0 || a.B == 0) return GTOS_OK;
-  size_t smem = attn_smem_bytes(a.S, a.hd);
+  const int rows = attn_rows(a.T);
+  size_t smem = attn_smem_bytes(a.S, a.hd, rows);
   GTOS_REQUIRE(smem <= 227 * 1024, "attention: source length %d too long for shared memory", a.S);
   GTOS_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(a.B * a.H, (a.T + AT_ROWS - 1) / AT_ROWS);
-  attn_fwd_kernel<<<grid, AT_THREADS, smem, st>>>(a);
+  dim3 grid(a.B * a.H, (a.T + rows - 1) / rows);
+  attn_fwd_kernel<<<grid, AT_THREADS, smem, st>>>(a, rows);
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
 }
@@ -172,11 +175,12 @@ int attn_fwd(const AttnArgs& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------
 // backward, query side: dS (and dq in decoder mode)
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(AT_THREADS) attn_bwd_q_kernel(const AttnBwdArgs g) {
+__global__ void __launch_bounds__(AT_THREADS) attn_bwd_q_kernel(const AttnBwdArgs g, const int rows_per_cta) {
   extern __shared__ float smem_f[];
   const AttnArgs& a = g.f;
   const int dc = a.hd < AT_DC ? a.hd : AT_DC;
-  const AttnSmem s = carve(smem_f, a.S, dc);
+  const int AT_ROWS = rows_per_cta;
+  const AttnSmem s = carve(smem_f, a.S, dc, AT_ROWS);
   const int bh = blockIdx.x, b = bh / a.H, h = bh % a.H;
   const int t0 = blockIdx.y * AT_ROWS;
   const int nrows = (a.T - t0) < AT_ROWS ? (a.T - t0) : AT_ROWS;
@@ -241,12 +245,13 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_q_kernel(const AttnBwdArg
 // ---------------------------------------------------------------------------------------
 // backward, key side: dV = Pd^T dO ; dK = scale * dS^T q      (CTA = 32 key rows of one (b,h))
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(AT_THREADS) attn_bwd_kv_kernel(const AttnBwdArgs g) {
+__global__ void __launch_bounds__(AT_THREADS) attn_bwd_kv_kernel(const AttnBwdArgs g, const int rows_per_cta) {
   extern __shared__ float smem_f[];
   const AttnArgs& a = g.f;
   const int dc = a.hd < AT_DC ? a.hd : AT_DC;
   const int T = a.T, S = a.S;
-  const AttnSmem s = carve(smem_f, T, dc);
+  const int AT_ROWS = rows_per_cta;
+  const AttnSmem s = carve(smem_f, T, dc, AT_ROWS);
   const int bh = blockIdx.x, b = bh / a.H, h = bh % a.H;
   const int j0 = blockIdx.y * AT_ROWS;
   const int nrows = (S - j0) < AT_ROWS ? (S - j0) : AT_ROWS;
@@ -294,15 +299,16 @@ int attn_bwd(const AttnBwdArgs& g, cudaStream_t st) {
   const AttnArgs& a = g.f;
   GTOS_REQUIRE(a.hd >= 1 && (a.hd <= AT_DC || a.hd % AT_DC == 0), "attention: unsupported head_dim %d", a.hd);
   if (a.T == 0 || a.B == 0) return GTOS_OK;
-  size_t smq = attn_smem_bytes(a.S, a.hd), smk = attn_smem_bytes(a.T, a.hd);
+  const int rq = attn_rows(a.T), rk = attn_rows(a.S);
+  size_t smq = attn_smem_bytes(a.S, a.hd, rq), smk = attn_smem_bytes(a.T, a.hd, rk);
   GTOS_REQUIRE(smq <= 227 * 1024 && smk <= 227 * 1024, "attention: sequence too long for shared memory");
   GTOS_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smq));
   GTOS_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smk));
-  dim3 gq(a.B * a.H, (a.T + AT_ROWS - 1) / AT_ROWS);
-  attn_bwd_q_kernel<<<gq, AT_THREADS, smq, st>>>(g);
+  dim3 gq(a.B * a.H, (a.T + rq - 1) / rq);
+  attn_bwd_q_kernel<<<gq, AT_THREADS, smq, st>>>(g, rq);
   GTOS_LAUNCH_CHECK();
-  dim3 gk(a.B * a.H, (a.S + AT_ROWS - 1) / AT_ROWS);
-  attn_bwd_kv_kernel<<<gk, AT_THREADS, smk, st>>>(g);
+  dim3 gk(a.B * a.H, (a.S + rk - 1) / rk);
+  attn_bwd_kv_kernel<<<gk, AT_THREADS, smk, st>>>(g, rk);
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
 }

@@ -364,39 +364,47 @@ int relu_drop_bwd(const float* dh_in, const void* act, float* dh_f32, void* dh_b
 // ---------------------------------------------------------------------------------------
 __global__ void rel_dqk_kernel(const __nv_bfloat16* __restrict__ G, RelTiling rt, float* __restrict__ dq,
                                float* __restrict__ dk, long ld) {
-  // block = (node index n, batch b); thread = feature f in [0, D); loops over the other node index
+  // block = (node n, batch b); thread = one 8-column (16-byte) chunk of the 2D-wide G row.
+  // chunks inside the d(q+ra) half of a head sum over keys j (-> dq[n]); chunks inside the d(k+rb) half sum
+  // over queries i (-> dk[n]).  Every G element is read exactly once, with 16-byte loads.
   const int n = blockIdx.x, b = blockIdx.y;
   const int D = rt.D, hd = rt.hd;
-  for (int f = threadIdx.x; f < D; f += blockDim.x) {
-    const int h = f / hd, w = f % hd;
-    const int colx = h * 2 * hd + w, coly = colx + hd;
-    float sq = 0.f, sk = 0.f;
-    // dq for query i = n: sum over keys j
-    {
-      const int ib = n / rt.bi, ii = n % rt.bi;
-      for (int j = 0; j < rt.N; ++j) {
-        const int jb = j / rt.bj, jj = j % rt.bj;
-        const long tile = ((long)b * rt.nj_blk + jb) * rt.ni_blk + ib;
-        sq += __bfloat162float(G[(tile * 128 + jj * rt.bi + ii) * (2L * D) + colx]);
-      }
+  const int c = threadIdx.x;                 // chunk index, 2D/8 chunks per row
+  const int col = c * 8;
+  const int h = col / (2 * hd), w = col % (2 * hd);
+  const bool is_x = w < hd;
+  float acc[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) acc[t] = 0.f;
+  const int nb = is_x ? n / rt.bi : n / rt.bj;       // block index of the fixed coordinate
+  const int nr = is_x ? n % rt.bi : n % rt.bj;
+  for (int o = 0; o < rt.N; ++o) {
+    long row;
+    if (is_x) {                                     // fixed query i = n, running key j = o
+      const int jb = o / rt.bj, jj = o % rt.bj;
+      row = (((long)b * rt.nj_blk + jb) * rt.ni_blk + nb) * 128 + jj * rt.bi + nr;
+    } else {                                        // fixed key j = n, running query i = o
+      const int ib = o / rt.bi, ii = o % rt.bi;
+      row = (((long)b * rt.nj_blk + nb) * rt.ni_blk + ib) * 128 + nr * rt.bi + ii;
     }
-    // dk for key j = n: sum over queries i
-    {
-      const int jb = n / rt.bj, jj = n % rt.bj;
-      for (int i = 0; i < rt.N; ++i) {
-        const int ib = i / rt.bi, ii = i % rt.bi;
-        const long tile = ((long)b * rt.nj_blk + jb) * rt.ni_blk + ib;
-        sk += __bfloat162float(G[(tile * 128 + jj * rt.bi + ii) * (2L * D) + coly]);
-      }
+    const uint4 v = *reinterpret_cast<const uint4*>(G + row * (2L * D) + col);
+    const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float2 f = __bfloat1622float2(p2[t]);
+      acc[2 * t] += f.x;
+      acc[2 * t + 1] += f.y;
     }
-    dq[((long)n * rt.B + b) * ld + f] = sq;
-    dk[((long)n * rt.B + b) * ld + f] = sk;
   }
+  float* dst = (is_x ? dq : dk) + ((long)n * rt.B + b) * ld + h * hd + (is_x ? w : w - hd);
+#pragma unroll
+  for (int t = 0; t < 8; ++t) dst[t] = acc[t];
 }
 
 int rel_dqk(const void* G, const RelTiling& rt, float* dq, float* dk, long ld, cudaStream_t st) {
   dim3 grid(rt.N, rt.B);
-  int thr = rt.D < 256 ? rt.D : 256;
+  const int thr = 2 * rt.D / 8;
+  GTOS_REQUIRE(thr <= 1024 && rt.hd % 8 == 0, "rel_dqk: unsupported D=%d hd=%d", rt.D, rt.hd);
   rel_dqk_kernel<<<grid, thr, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(G), rt, dq, dk, ld);
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;

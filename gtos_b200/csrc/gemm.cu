@@ -12,6 +12,8 @@
 //
 //   gemm_nn_kernel<BN, REL>    C[M,N] = sum_k A[k,m] B[k,n] with MN-major UMMA descriptors
 //                              (weight gradients: contraction over rows), split-K partials.
+#include <stdlib.h>
+
 #include "gemm.cuh"
 
 namespace gtos {
@@ -61,6 +63,7 @@ struct TnDev {
   __nv_bfloat16* G;
   int bi8, bj8;        // q / k box rows rounded up to 8 (1024-byte swizzle atoms)
   int qk_stage_bytes;  // 4*(bi8+bj8)*128
+  int tma_out;         // epilogue stages tiles in shared memory and writes them with TMA stores
 };
 
 __device__ __forceinline__ void rel_tile_decode(const RelTiling& t, int tile, int& b, int& j0, int& i0) {
@@ -86,11 +89,30 @@ __device__ __forceinline__ void lds_sw128_16(const uint8_t* box, int row, int f0
   }
 }
 
+// 16 bf16 (as fp32) from a 128B-swizzled [rows x 64 bf16] TMA box: row `row`, elements [e0, e0+16), e0 % 16 == 0
+__device__ __forceinline__ void lds_sw128_bf16x16(const uint8_t* box, int row, int e0, float* out) {
+  const uint8_t* rp = box + row * 128;
+  const int c0 = e0 >> 3;
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    uint4 v = *reinterpret_cast<const uint4*>(rp + (((c0 + t) ^ (row & 7)) << 4));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float2 f = __bfloat1622float2(h[u]);
+      out[8 * t + 2 * u] = f.x;
+      out[8 * t + 2 * u + 1] = f.y;
+    }
+  }
+}
+
 template <int BN, int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const TnDev p) {
+               const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+               const __grid_constant__ CUtensorMap tmO, const TnDev p) {
   constexpr bool REL = (MODE == MODE_SCORE || MODE == MODE_GRAD);
+  constexpr int OUT_STAGE_BYTES = 2 * BM * 128;  // two [128 rows x 128 B] swizzled staging tiles
   constexpr int B_STAGE_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
@@ -99,7 +121,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* qk_base = smem + p.stages * STAGE_BYTES;
-  PipeBars* bars = reinterpret_cast<PipeBars*>(qk_base + (REL ? 2 * p.qk_stage_bytes : 0));
+  uint8_t* out_stage = qk_base + (REL ? 2 * p.qk_stage_bytes : 0);  // 1024-aligned (all regions are multiples of 1 KB)
+  PipeBars* bars = reinterpret_cast<PipeBars*>(out_stage + (p.tma_out ? OUT_STAGE_BYTES : 0));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -107,6 +130,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.tma_out) tma_prefetch_desc(&tmO);
     if (REL) {
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmK);
@@ -143,13 +167,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           rel_tile_decode(p.rt, m_blk, b, j0, i0);
           // q / k slices for this (tile, head group): dims [n_blk*BN/2, +BN/2)
           wait_bar(&bars->qempty[qs], qph ^ 1);
-          mbar_expect_tx(&bars->qfull[qs], (uint32_t)((BN / 64) * (p.rt.bi + p.rt.bj) * 128));
+          mbar_expect_tx(&bars->qfull[qs], (uint32_t)((BN / 128) * (p.rt.bi + p.rt.bj) * 128));
           uint8_t* qb = qk_base + qs * p.qk_stage_bytes;
           const int d0 = n_blk * (BN / 2);
 #pragma unroll
-          for (int c = 0; c < BN / 64; ++c) {
-            tma_load_3d(&tmQ, &bars->qfull[qs], qb + c * p.bi8 * 128, d0 + c * 32, b, i0);
-            tma_load_3d(&tmK, &bars->qfull[qs], qb + (BN / 64) * p.bi8 * 128 + c * p.bj8 * 128, d0 + c * 32, b, j0);
+          for (int c = 0; c < BN / 128; ++c) {   // bf16 q/k: one 128-byte box row = 64 dims
+            tma_load_3d(&tmQ, &bars->qfull[qs], qb + c * p.bi8 * 128, d0 + c * 64, b, i0);
+            tma_load_3d(&tmK, &bars->qfull[qs], qb + (BN / 128) * p.bi8 * 128 + c * p.bj8 * 128, d0 + c * 64, b, j0);
           }
           if (++qs == 2) { qs = 0; qph ^= 1; }
         }
@@ -206,6 +230,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t aph = 0;
     int qs = 0;
     uint32_t qph = 0;
+    int kc = 0;  // running output-chunk counter: staging buffer = kc & 1
     for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
       const int m_blk = unit / p.n_tiles, n_blk = unit % p.n_tiles;
       wait_bar(&bars->tfull[as], aph);
@@ -214,6 +239,49 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t tacc = tmem_base + as * BN + ((uint32_t)(quarter * 32) << 16);
 
       if constexpr (MODE == MODE_PLAIN || MODE == MODE_DREL) {
+        if (p.tma_out) {
+          // fp32 tile -> swizzled smem staging tile [128 rows x 32 cols] -> one TMA store per 32-column chunk
+          // (double-buffered; OOB rows / columns are clipped by the tensor map)
+          const bool issuer = (warp == 2 && lane == 0);
+          int b0 = 0, j0 = 0, i0 = 0;
+          if constexpr (MODE == MODE_DREL) rel_tile_decode(p.rt, m_blk, b0, j0, i0);
+          const int n0 = n_blk * BN;
+#pragma unroll 1
+          for (int c = 0; c < BN; c += 32) {
+            if (n0 + c >= p.N) break;
+            float v[32];
+            tmem_ld16(tacc + c, v);
+            tmem_ld16(tacc + c + 16, v + 16);
+            tmem_ld_wait();
+            if (p.bias) {
+#pragma unroll
+              for (int t = 0; t < 32; ++t)
+                if (n0 + c + t < p.N) v[t] += __ldg(p.bias + n0 + c + t);
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int t = 0; t < 32; ++t) v[t] = fmaxf(v[t], 0.f);
+            }
+            uint8_t* buf = out_stage + (kc & 1) * (BM * 128);
+            ++kc;
+            if (issuer) tma_store_wait_read<1>();   // the store that last read this buffer has drained
+            named_bar_sync(1, 128);
+            uint8_t* rowp = buf + r * 128;
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+              *reinterpret_cast<float4*>(rowp + ((t ^ (r & 7)) << 4)) =
+                  make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
+            fence_proxy_async();
+            named_bar_sync(2, 128);
+            if (issuer) {
+              if constexpr (MODE == MODE_DREL)
+                tma_store_4d(&tmO, buf, n0 + c, b0, i0, j0);
+              else
+                tma_store_2d(&tmO, buf, n0 + c, m_blk * BM);
+              tma_store_commit();
+            }
+          }
+        } else {
         long out_row = (long)m_blk * BM + r;
         bool row_ok = out_row < p.M;
         if constexpr (MODE == MODE_DREL) {
@@ -278,6 +346,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
+        }  // !tma_out
       } else {
         // ---- relation epilogues: thread owns pair (j0+jj, i0+ii, b) ----
         int b, j0, i0;
@@ -288,7 +357,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool valid = (jj < p.rt.bj) && (i < p.rt.N) && (j < p.rt.N);
         const int jjc = jj < p.rt.bj ? jj : p.rt.bj - 1;  // keep smem reads inside the k boxes
         const uint8_t* qb = qk_base + qs * p.qk_stage_bytes;
-        const uint8_t* kbx = qb + (BN / 64) * p.bi8 * 128;
+        const uint8_t* kbx = qb + (BN / 128) * p.bi8 * 128;
         const int hd = p.rt.hd;
         const int heads_blk = (BN / 2) / hd;
 #pragma unroll 1
@@ -304,8 +373,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tmem_ld16(tacc + hh * 2 * hd + c, ra);
             tmem_ld16(tacc + hh * 2 * hd + hd + c, rb);
             const int dl = hh * hd + c;  // dim inside this unit's BN/2-wide slice
-            lds_sw128_16(qb + (dl >> 5) * p.bi8 * 128, ii, dl & 31, qv);
-            lds_sw128_16(kbx + (dl >> 5) * p.bj8 * 128, jjc, dl & 31, kv);
+            lds_sw128_bf16x16(qb + (dl >> 6) * p.bi8 * 128, ii, dl & 63, qv);
+            lds_sw128_bf16x16(kbx + (dl >> 6) * p.bj8 * 128, jjc, dl & 63, kv);
             tmem_ld_wait();
             if constexpr (MODE == MODE_SCORE) {
 #pragma unroll
@@ -320,11 +389,42 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 wx[t] = valid ? pack_bf16x2(g * y0, g * y1) : 0u;
                 wy[t] = valid ? pack_bf16x2(g * x0, g * x1) : 0u;
               }
+              const int gcx = hh * 2 * hd + c, gcy = gcx + hd;   // G columns inside this 256-wide block
+              if (p.tma_out) {
+                // stage 64-column (128-byte) spans of G in swizzled smem tiles, one TMA store per finished span
+                const bool wide = hd >= 64;                      // X and Y halves live in different spans
+                const bool issuer = (warp == 2 && lane == 0);
+                uint8_t* bx = out_stage + (wide ? 0 : ((gcx >> 6) & 1)) * (BM * 128);
+                uint8_t* by = out_stage + (wide ? 1 : ((gcy >> 6) & 1)) * (BM * 128);
+                if ((gcx & 63) == 0) {                           // first chunk of a span: buffer is reused
+                  if (issuer) {
+                    if (wide) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+                  }
+                  named_bar_sync(1, 128);
+                }
+                uint8_t* rx = bx + r * 128;
+                uint8_t* ry = by + r * 128;
+                const int cx = (gcx & 63) >> 3, cy = (gcy & 63) >> 3;
+                *reinterpret_cast<uint4*>(rx + (((cx) ^ (r & 7)) << 4)) = make_uint4(wx[0], wx[1], wx[2], wx[3]);
+                *reinterpret_cast<uint4*>(rx + (((cx + 1) ^ (r & 7)) << 4)) = make_uint4(wx[4], wx[5], wx[6], wx[7]);
+                *reinterpret_cast<uint4*>(ry + (((cy) ^ (r & 7)) << 4)) = make_uint4(wy[0], wy[1], wy[2], wy[3]);
+                *reinterpret_cast<uint4*>(ry + (((cy + 1) ^ (r & 7)) << 4)) = make_uint4(wy[4], wy[5], wy[6], wy[7]);
+                if (((gcy + 16) & 63) == 0) {                    // span(s) complete
+                  fence_proxy_async();
+                  named_bar_sync(2, 128);
+                  if (issuer) {
+                    if (wide) tma_store_2d(&tmO, bx, n_blk * BN + (gcx & ~63), m_blk * BM);
+                    tma_store_2d(&tmO, by, n_blk * BN + (gcy & ~63), m_blk * BM);
+                    tma_store_commit();
+                  }
+                }
+              } else {
               __nv_bfloat16* grow = p.G + ((long)m_blk * BM + r) * (2 * p.rt.D) + (long)n_blk * BN + hh * 2 * hd + c;
               *reinterpret_cast<uint4*>(grow) = make_uint4(wx[0], wx[1], wx[2], wx[3]);
               *reinterpret_cast<uint4*>(grow + 8) = make_uint4(wx[4], wx[5], wx[6], wx[7]);
               *reinterpret_cast<uint4*>(grow + hd) = make_uint4(wy[0], wy[1], wy[2], wy[3]);
               *reinterpret_cast<uint4*>(grow + hd + 8) = make_uint4(wy[4], wy[5], wy[6], wy[7]);
+              }
             }
           }
           if constexpr (MODE == MODE_SCORE) {
@@ -342,6 +442,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (++as == 2) { as = 0; aph ^= 1; }
       if (REL) { if (++qs == 2) { qs = 0; qph ^= 1; } }
     }
+    if (p.tma_out && warp == 2 && lane == 0) tma_store_wait_all();  // smem must outlive the bulk stores
   }
 
   tc_fence_before();
@@ -371,7 +472,7 @@ int choose_rel_tiling(RelTiling* t, int N, int B, int D, int H) {
   for (int bi = 1; bi <= 128 && bi <= N; ++bi) {
     for (int bj = 1; bj * bi <= 128 && bj <= N; ++bj) {
       int bi8 = (bi + 7) & ~7, bj8 = (bj + 7) & ~7;
-      if (bi8 + bj8 > 48) continue;  // q/k staging budget: 4*(bi8+bj8)*128 B per stage <= 24 KB
+      if (bi8 + bj8 > 48) continue;  // q/k staging budget: 2*(bi8+bj8)*128 B per stage <= 12 KB (bf16 q/k)
       long tiles = (long)((N + bi - 1) / bi) * ((N + bj - 1) / bj);
       if (best_tiles < 0 || tiles < best_tiles || (tiles == best_tiles && bi + bj < best_bi + best_bj)) {
         best_tiles = tiles;
@@ -399,7 +500,7 @@ static int num_sms() {
   return g_num_sms;
 }
 
-int make_rel_tmaps(const RelTiling& rt, const void* relb, const float* q, const float* k, long ldqk,
+int make_rel_tmaps(const RelTiling& rt, const void* relb, const void* q, const void* k, long ldqk,
                    CUtensorMap* tmA, CUtensorMap* tmQ, CUtensorMap* tmK) {
   {
     uint64_t dims[4] = {(uint64_t)rt.D, (uint64_t)rt.B, (uint64_t)rt.N, (uint64_t)rt.N};
@@ -410,12 +511,12 @@ int make_rel_tmaps(const RelTiling& rt, const void* relb, const float* q, const 
   }
   if (q) {
     uint64_t dims[3] = {(uint64_t)rt.D, (uint64_t)rt.B, (uint64_t)rt.N};
-    uint64_t str[3] = {0, (uint64_t)ldqk * 4, (uint64_t)rt.B * ldqk * 4};
-    uint32_t boxq[3] = {32, 1, (uint32_t)rt.bi};
-    uint32_t boxk[3] = {32, 1, (uint32_t)rt.bj};
-    int e = make_tmap_nd(tmQ, q, 4, 3, dims, str, boxq, true);
+    uint64_t str[3] = {0, (uint64_t)ldqk * 2, (uint64_t)rt.B * ldqk * 2};
+    uint32_t boxq[3] = {64, 1, (uint32_t)rt.bi};
+    uint32_t boxk[3] = {64, 1, (uint32_t)rt.bj};
+    int e = make_tmap_nd(tmQ, q, 2, 3, dims, str, boxq, true);
     if (e) return e;
-    e = make_tmap_nd(tmK, k, 4, 3, dims, str, boxk, true);
+    e = make_tmap_nd(tmK, k, 2, 3, dims, str, boxk, true);
     if (e) return e;
   }
   return GTOS_OK;
@@ -439,7 +540,7 @@ static int launch_tn(const GemmTnArgs& a, cudaStream_t stream) {
     p.m_tiles = a.rt.tiles;
     p.bi8 = (a.rt.bi + 7) & ~7;
     p.bj8 = (a.rt.bj + 7) & ~7;
-    p.qk_stage_bytes = (BN / 64) * (p.bi8 + p.bj8) * 128;
+    p.qk_stage_bytes = (BN / 128) * (p.bi8 + p.bj8) * 128;
     e = make_rel_tmaps(a.rt, a.A, a.q, a.k, a.ldqk, &tmA, &tmQ, &tmK);
     if (e) return e;
   } else {
@@ -452,8 +553,39 @@ static int launch_tn(const GemmTnArgs& a, cudaStream_t stream) {
   e = make_tmap_2d_bf16(&tmB, a.Bm, (uint64_t)a.N, (uint64_t)a.K, (uint64_t)a.ldb, BN);
   if (e) return e;
   p.units = p.m_tiles * p.n_tiles;
+  // ---- output path: TMA stores from swizzled staging tiles where the layout allows it ----
+  CUtensorMap tmO = tmB;
+  constexpr int OUT_STAGE_BYTES = 2 * BM * 128;
+  p.tma_out = 0;
+  static const bool tma_enabled = !(getenv("GTOS_TMA_OUT") && getenv("GTOS_TMA_OUT")[0] == '0');
+  if (!tma_enabled) {
+  } else if (MODE == MODE_PLAIN && a.out_f32 && !a.out_bf16 && !a.accumulate && a.ldo % 4 == 0 &&
+      (reinterpret_cast<uintptr_t>(a.out_f32) & 15) == 0) {
+    uint64_t dims[2] = {(uint64_t)a.N, (uint64_t)a.M};
+    uint64_t str[2] = {0, (uint64_t)a.ldo * 4};
+    uint32_t box[2] = {32, (uint32_t)BM};
+    e = make_tmap_nd(&tmO, a.out_f32, 4, 2, dims, str, box, true);
+    if (e) return e;
+    p.tma_out = 1;
+  } else if (MODE == MODE_DREL && !a.accumulate && a.ldo == a.rt.D) {
+    const RelTiling& rt = a.rt;
+    uint64_t dims[4] = {(uint64_t)rt.D, (uint64_t)rt.B, (uint64_t)rt.N, (uint64_t)rt.N};
+    uint64_t str[4] = {0, (uint64_t)rt.D * 4, (uint64_t)rt.B * rt.D * 4, (uint64_t)rt.N * rt.B * rt.D * 4};
+    uint32_t box[4] = {32, 1, (uint32_t)rt.bi, (uint32_t)rt.bj};
+    e = make_tmap_nd(&tmO, a.out_f32, 4, 4, dims, str, box, true);
+    if (e) return e;
+    p.tma_out = 1;
+  } else if (MODE == MODE_GRAD) {
+    uint64_t dims[2] = {(uint64_t)(2 * a.rt.D), (uint64_t)a.rt.tiles * BM};
+    uint64_t str[2] = {0, (uint64_t)(2 * a.rt.D) * 2};
+    uint32_t box[2] = {64, (uint32_t)BM};
+    e = make_tmap_nd(&tmO, a.G, 2, 2, dims, str, box, true);
+    if (e) return e;
+    p.tma_out = 1;
+  }
   constexpr int STAGE_BYTES = A_STAGE_BYTES + BN * BK * 2;
-  const int budget = 227 * 1024 - 1024 /*align*/ - (int)sizeof(PipeBars) - (REL ? 2 * p.qk_stage_bytes : 0);
+  const int budget = 227 * 1024 - 1024 /*align*/ - (int)sizeof(PipeBars) - (REL ? 2 * p.qk_stage_bytes : 0) -
+                     (p.tma_out ? OUT_STAGE_BYTES : 0);
   int stages = budget / STAGE_BYTES;
   if (stages > 6) stages = 6;
   if (stages < 2) {
@@ -461,12 +593,13 @@ static int launch_tn(const GemmTnArgs& a, cudaStream_t stream) {
     return GTOS_ERR_UNSUPPORTED;
   }
   p.stages = stages;
-  const int smem_bytes = 1024 + stages * STAGE_BYTES + (REL ? 2 * p.qk_stage_bytes : 0) + (int)sizeof(PipeBars);
+  const int smem_bytes = 1024 + stages * STAGE_BYTES + (REL ? 2 * p.qk_stage_bytes : 0) +
+                         (p.tma_out ? OUT_STAGE_BYTES : 0) + (int)sizeof(PipeBars);
   auto kern = gemm_tn_kernel<BN, MODE>;
   GTOS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   int grid = p.units < num_sms() ? p.units : num_sms();
   if (grid <= 0) return GTOS_OK;
-  kern<<<grid, GEMM_THREADS, smem_bytes, stream>>>(tmA, tmB, tmQ, tmK, p);
+  kern<<<grid, GEMM_THREADS, smem_bytes, stream>>>(tmA, tmB, tmQ, tmK, tmO, p);
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
 }
@@ -654,7 +787,7 @@ static void nn_plan(int M, int N, int Kd, int rel, int* BN, int* KB, int* splits
   *KB = rel ? 128 : 64;
   int tiles = ((M + BM - 1) / BM) * ((N + *BN - 1) / *BN);
   int kblocks = (Kd + *KB - 1) / *KB;
-  int want = (num_sms() + tiles - 1) / tiles;
+  int want = num_sms() / tiles;  // floor: one wave (ceil gave 160 CTAs on 148 SMs = 2 waves)
   if (want > kblocks) want = kblocks;
   if (want < 1) want = 1;
   int per = (kblocks + want - 1) / want;

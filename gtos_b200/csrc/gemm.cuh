@@ -41,8 +41,8 @@ struct GemmTnArgs {
   int accumulate;      // out_f32 += result
   // relation modes
   RelTiling rt;
-  const float* q;      // [N,B,D] fp32 (bias included, unscaled), row stride ldqk
-  const float* k;      // [N,B,D]
+  const void* q;       // bf16 [N,B,D] (bias included, unscaled), row stride ldqk elements
+  const void* k;       // bf16 [N,B,D]
   long ldqk;
   float* scores;       // SCORE out: [B,H,N(j),N(i)]
   const float* dscores;  // GRAD in : [B,H,N(j),N(i)]

@@ -45,11 +45,12 @@ class TokenGenerator(nn.Module):
                                                    key_padding_mask=graph_padding_mask, need_weights=True)
         outs, _ = ops.add_layer_norm(x, outs, self.alignment_layer_norm.weight, self.alignment_layer_norm.bias, p)
         seq_len, bsz, _ = outs.size()
-        # ---- vocabulary tail: PyTorch ops ----
-        outs_token = torch.tanh(self.transfer(outs))
+        # ---- vocabulary tail: the two wide projections run on the tcgen05 GEMM; the softmax / copy-scatter /
+        #      NLL elementwise passes are still PyTorch ops ----
+        outs_token = torch.tanh(ops.linear(outs, self.transfer.weight, self.transfer.bias))
         outs_token = F.dropout(outs_token, p=self.dropout, training=self.training)
         gen_gate, copy_gate = F.softmax(self.diverter(outs_token), -1).chunk(2, dim=-1)
-        probs = gen_gate * F.softmax(self.generator(outs_token), -1)
+        probs = gen_gate * F.softmax(ops.linear(outs_token, self.generator.weight, self.generator.bias), -1)
         tot_ext = self.static_tot_ext if self.static_tot_ext is not None else 1 + copy_seq.max().item()
         vocab_size = probs.size(-1)
         if tot_ext - vocab_size > 0:

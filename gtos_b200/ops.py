@@ -278,9 +278,11 @@ class RelAttnFn(torch.autograd.Function):
         Wib, Wit = weight_prep(W_in)
         Wperm, WpermT = weight_prep(W_rel, rel_heads=H)
         Wob, Wot = weight_prep(W_out)
-        qkv, _ = gemm_tn(xb2, Wib, 3 * D, bias=b_in)                               # [NB, 3D] fp32
+        # q,k feed only the fused relation kernels (staged there by TMA as bf16); v feeds the attention core
+        _, qkb = gemm_tn(xb2, Wib, 2 * D, bias=b_in[:2 * D], f32=False, bf16=True)  # [NB, 2D] bf16
+        vproj, _ = gemm_tn(xb2, Wib, D, bias=b_in[2 * D:], K=D, b_off=2 * D * Wib.stride(0))   # [NB, D] fp32
         scores = torch.empty(B, H, N, N, dtype=torch.float32, device=dev)          # [b,h,j,i]
-        _lib.check(lib.gtos_rel_score(_p(relb), _p(Wperm), qkv.data_ptr(), qkv.data_ptr() + 4 * D, 3 * D, _p(scores),
+        _lib.check(lib.gtos_rel_score(_p(relb), _p(Wperm), qkb.data_ptr(), qkb.data_ptr() + 2 * D, 2 * D, _p(scores),
                                       N, B, D, H, _st()), "rel_score")
         probs = torch.empty(B, H, N, N, dtype=torch.float32, device=dev)           # [b,h,i,j]
         wts = torch.empty(B, H, N, N, dtype=torch.float32, device=dev) if need_weights else None
@@ -288,7 +290,7 @@ class RelAttnFn(torch.autograd.Function):
         attb = torch.empty(NB, D, dtype=torch.bfloat16, device=dev)
         seed, off = (rng_state(dev), new_seed_off()) if p > 0 else (None, 0)
         d = _attn_desc(N, N, B, H, hd)
-        d.v, d.ldv = qkv.data_ptr() + 8 * D, 3 * D
+        d.v, d.ldv = vproj.data_ptr(), D
         d.scale, d.p_drop = 1.0, p
         d.scores_jt, d.key_pad, d.attn_mask = _p(scores), _p(key_pad), _p(attn_mask)
         d.seed_ptr, d.seed_off = _p(seed), off
@@ -296,7 +298,7 @@ class RelAttnFn(torch.autograd.Function):
         d.out, d.ldo, d.out_bf16 = _p(att), D, _p(attb)
         _lib.check(lib.gtos_attn_fwd(C.byref(d), _st()), "attn_fwd(enc)")
         out, _ = gemm_tn(attb, Wob, D, bias=b_out)
-        ctx.save_for_backward(xb2, relb, qkv, probs, attb, Wperm, WpermT, Wit, Wot, key_pad, attn_mask)
+        ctx.save_for_backward(xb2, relb, qkb, vproj, probs, attb, Wperm, WpermT, Wit, Wot, key_pad, attn_mask)
         ctx.meta = (N, B, D, H, p, seed, off)
         if wts is None:
             return out.view(N, B, D), None
@@ -305,7 +307,7 @@ class RelAttnFn(torch.autograd.Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, dout, dwts):
-        xb2, relb, qkv, probs, attb, Wperm, WpermT, Wit, Wot, key_pad, attn_mask = ctx.saved_tensors
+        xb2, relb, qkb, vproj, probs, attb, Wperm, WpermT, Wit, Wot, key_pad, attn_mask = ctx.saved_tensors
         N, B, D, H, p, seed, off = ctx.meta
         lib = _lib.load()
         hd = D // H
@@ -320,7 +322,7 @@ class RelAttnFn(torch.autograd.Function):
         ds_jt = torch.empty(B, H, N, N, dtype=torch.float32, device=dev)
         ds_ts = torch.empty(B, H, N, N, dtype=torch.float32, device=dev)
         d = _attn_desc(N, N, B, H, hd)
-        d.v, d.ldv = qkv.data_ptr() + 8 * D, 3 * D
+        d.v, d.ldv = vproj.data_ptr(), D
         d.scale, d.p_drop = 1.0, p
         d.key_pad, d.attn_mask = _p(key_pad), _p(attn_mask)
         d.seed_ptr, d.seed_off = _p(seed), off
@@ -332,7 +334,7 @@ class RelAttnFn(torch.autograd.Function):
         _lib.check(lib.gtos_attn_bwd(C.byref(d), _st()), "attn_bwd(enc)")
         tiles = rel_tiling(N, B, D, H)["tiles"]
         G = torch.empty(tiles * 128, 2 * D, dtype=torch.bfloat16, device=dev)
-        _lib.check(lib.gtos_rel_grad(_p(relb), _p(Wperm), qkv.data_ptr(), qkv.data_ptr() + 4 * D, 3 * D, _p(ds_jt),
+        _lib.check(lib.gtos_rel_grad(_p(relb), _p(Wperm), qkb.data_ptr(), qkb.data_ptr() + 2 * D, 2 * D, _p(ds_jt),
                                      _p(G), N, B, D, H, _st()), "rel_grad")
         _lib.check(lib.gtos_rel_dqk(_p(G), dqkv.data_ptr(), dqkv.data_ptr() + 4 * D, 3 * D, N, B, D, H, _st()),
                    "rel_dqk")
@@ -592,3 +594,37 @@ class GRUBankFn(torch.autograd.Function):
                 _lib.check(lib.gtos_embed_scatter_add(_p(dx), _p(tokens), rows, E, _p(d_embed), p, _p(seed), off_e,
                                                       _st()), "embed_scatter_add")
         return (None, None, d_embed, dW_out, db_out, None, None, None, *wgrads)
+
+
+# --------------------------------------------------------------------------------------------
+# plain Linear on the tcgen05 GEMM (TokenGenerator's transfer / vocabulary projection, decoder.py:39,44)
+# --------------------------------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, W, b):
+        _need_cuda(x, W)
+        shape = x.shape
+        K = shape[-1]
+        N = W.shape[0]
+        xb = cast_bf16(x.contiguous().view(-1, K))
+        Wb, Wt = weight_prep(W)
+        y, _ = gemm_tn(xb, Wb, N, bias=b)
+        ctx.save_for_backward(xb, Wt)
+        ctx.meta = (shape, N, K, b is not None)
+        return y.view(*shape[:-1], N)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        xb, Wt = ctx.saved_tensors
+        shape, N, K, has_b = ctx.meta
+        dy2 = dy.contiguous().view(-1, N)
+        dyb = cast_bf16(dy2)
+        dW = gemm_nn(dyb, xb, N, K)
+        db = colsum(dy2) if has_b else None
+        dx, _ = gemm_tn(dyb, Wt, K)
+        return dx.view(shape), dW, db
+
+
+def linear(x, W, b=None):
+    return LinearFn.apply(x, W, b)

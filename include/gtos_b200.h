@@ -61,11 +61,12 @@ int gtos_gemm_nn(const void* A, int64_t lda, const void* B, int64_t ldb, float* 
 /* tiling of the N x N x B pair grid into 128-row MMA tiles: out = {bi, bj, ni_blk, nj_blk, tiles} */
 int gtos_rel_tiling(int32_t N, int32_t B, int32_t D, int32_t H, int32_t* out5);
 /* scores[b,h,j,i] = hd^-1/2 < q[i,b,h] + Wa r[j,i,b] , k[j,b,h] + Wb r[j,i,b] >     (:122-133)
- * relb: relation as bf16 [N,N,B,D]; Wperm: gtos_weight_prep(rel_heads=H) output [2D,D]; q,k fp32 with row stride ldqk */
-int gtos_rel_score(const void* relb, const void* Wperm, const float* q, const float* k, int64_t ldqk, float* scores,
+ * relb: relation as bf16 [N,N,B,D]; Wperm: gtos_weight_prep(rel_heads=H) output [2D,D];
+ * q,k: the projected queries / keys as bf16 [N,B,D] with row stride ldqk elements (staged by TMA for the epilogue) */
+int gtos_rel_score(const void* relb, const void* Wperm, const void* q, const void* k, int64_t ldqk, float* scores,
                    int32_t N, int32_t B, int32_t D, int32_t H, void* stream);
 /* backward of the above w.r.t. the per-pair projections: G[tile-major pair, 2D] (bf16) = hd^-1/2 dscores * [k+rb | q+ra] */
-int gtos_rel_grad(const void* relb, const void* Wperm, const float* q, const float* k, int64_t ldqk,
+int gtos_rel_grad(const void* relb, const void* Wperm, const void* q, const void* k, int64_t ldqk,
                   const float* dscores, void* G, int32_t N, int32_t B, int32_t D, int32_t H, void* stream);
 /* d_relation[j,i,b,:] (+)= G * Wperm  (WpermT = transposed prep output [D,2D]) */
 int gtos_rel_drel(const void* G, const void* WpermT, float* d_relation, int32_t accumulate, int32_t N, int32_t B,

@@ -68,8 +68,20 @@ class _LinBf16(torch.autograd.Function):
         return dx, dw
 
 
+class _RoundSTE(torch.autograd.Function):
+    """bf16 rounding with a straight-through gradient (operands the kernels stage as bf16)"""
+
+    @staticmethod
+    def forward(ctx, x):
+        return _bf(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
 def _lin32(x, w, b):
-    """always-fp32 Linear: the TokenGenerator vocabulary tail, which the B200 path keeps in fp32"""
+    """always-fp32 Linear: the 2-way copy/generate gate (decoder.py:42), which the B200 path keeps in fp32"""
     return x @ w.t() + b
 
 
@@ -107,6 +119,8 @@ def rel_mha(P, pre, query, key, value, relation, num_heads, key_padding_mask=Non
     q = _lin(query, Win[:D], bin_[:D]).view(T, B, H, hd)
     k = _lin(key, Win[D:2 * D], bin_[D:2 * D]).view(S, B, H, hd)
     v = _lin(value, Win[2 * D:], bin_[2 * D:]).view(S, B, H, hd)
+    if _PRECISION == "bf16":                                      # the fused kernel stages q, k as bf16
+        q, k = _RoundSTE.apply(q), _RoundSTE.apply(k)
     Wr = P[pre + "relation_in_proj.weight"]                       # [2D, D], no bias (:80)
     ra = _lin(relation, Wr[:D]).view(relation.shape[0], relation.shape[1], B, H, hd)
     rb = _lin(relation, Wr[D:]).view(relation.shape[0], relation.shape[1], B, H, hd)
@@ -275,11 +289,11 @@ def token_generator(P, pre, outs, graph_state, graph_padding_mask, copy_seq, pad
     outs = _layer_norm(outs + _drop(a, dropout, training),
                        P[pre + "alignment_layer_norm.weight"], P[pre + "alignment_layer_norm.bias"])
     T, B, _ = outs.shape
-    tok = torch.tanh(_lin32(outs, P[pre + "transfer.weight"], P[pre + "transfer.bias"]))
+    tok = torch.tanh(_lin(outs, P[pre + "transfer.weight"], P[pre + "transfer.bias"]))
     tok = _drop(tok, dropout, training)
     gate = torch.softmax(_lin32(tok, P[pre + "diverter.weight"], P[pre + "diverter.bias"]), -1)
     gen_gate, copy_gate = gate[..., :1], gate[..., 1:]
-    probs = gen_gate * torch.softmax(_lin32(tok, P[pre + "generator.weight"], P[pre + "generator.bias"]), -1)
+    probs = gen_gate * torch.softmax(_lin(tok, P[pre + "generator.weight"], P[pre + "generator.bias"]), -1)
     V = probs.shape[-1]
     tot = 1 + int(copy_seq.max())
     if tot > V:

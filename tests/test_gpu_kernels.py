@@ -57,7 +57,7 @@ def test_gemm_nn(dev, Kd, M, N):
 
 
 def _rel_inputs(dev, N, B, D, H, wscale):
-    x_q = torch.randn(N * B, 3 * D, device=dev)                     # fused qkv projection buffer
+    x_q = bf(torch.randn(N * B, 2 * D, device=dev))                 # projected [q | k], staged as bf16
     rel = torch.randn(N, N, B, D, device=dev) * 0.5
     Wr = torch.randn(2 * D, D, device=dev) * wscale
     return x_q, rel, Wr
@@ -66,8 +66,8 @@ def _rel_inputs(dev, N, B, D, H, wscale):
 def _rel_scores_ref(qkv, relb, Wr, N, B, D, H):
     """scores[b,h,j,i] = hd^-1/2 < q_i + Wa r[j,i] , k_j + Wb r[j,i] >  from the bf16-rounded operands"""
     hd = D // H
-    q = qkv[:, :D].view(N, B, H, hd)
-    k = qkv[:, D:2 * D].view(N, B, H, hd)
+    q = qkv.float()[:, :D].reshape(N, B, H, hd)
+    k = qkv.float()[:, D:2 * D].reshape(N, B, H, hd)
     r = relb.float()
     W = bf(Wr).float()
     ra = (r @ W[:D].t()).view(N, N, B, H, hd)                        # [j,i,b,h,d]
@@ -83,8 +83,8 @@ def test_rel_score(dev, N, B, D, H):
     relb = ops.relation_to_bf16(rel)
     Wperm, _ = ops.weight_prep(Wr, rel_heads=H)
     scores = torch.full((B, H, N, N), float("nan"), device=dev)
-    _lib.check(_lib.load().gtos_rel_score(relb.data_ptr(), Wperm.data_ptr(), qkv.data_ptr(), qkv.data_ptr() + 4 * D,
-                                          3 * D, scores.data_ptr(), N, B, D, H,
+    _lib.check(_lib.load().gtos_rel_score(relb.data_ptr(), Wperm.data_ptr(), qkv.data_ptr(), qkv.data_ptr() + 2 * D,
+                                          2 * D, scores.data_ptr(), N, B, D, H,
                                           torch.cuda.current_stream().cuda_stream), "rel_score")
     torch.cuda.synchronize()
     ref = _rel_scores_ref(qkv, relb, Wr, N, B, D, H)
@@ -105,17 +105,17 @@ def test_rel_backward_pieces(dev, N, B, D, H):
     # reference through autograd on the bf16-rounded operands
     r32 = relb.float().requires_grad_()
     W32 = bf(Wr).float().requires_grad_()
-    q32 = qkv.clone().requires_grad_()
+    q32 = qkv.float().requires_grad_()
     hd = D // H
-    q = q32[:, :D].view(N, B, H, hd)
-    k = q32[:, D:2 * D].view(N, B, H, hd)
+    q = q32[:, :D].reshape(N, B, H, hd)
+    k = q32[:, D:2 * D].reshape(N, B, H, hd)
     ra = (r32 @ W32[:D].t()).view(N, N, B, H, hd)
     rb = (r32 @ W32[D:].t()).view(N, N, B, H, hd)
     s = (((q.unsqueeze(0) + ra) * (k.unsqueeze(1) + rb)).sum(-1) * hd ** -0.5).permute(2, 3, 0, 1)
     (s * ds).sum().backward()
     tiles = ops.rel_tiling(N, B, D, H)["tiles"]
     G = torch.empty(tiles * 128, 2 * D, dtype=torch.bfloat16, device=dev)
-    _lib.check(lib.gtos_rel_grad(relb.data_ptr(), Wperm.data_ptr(), qkv.data_ptr(), qkv.data_ptr() + 4 * D, 3 * D,
+    _lib.check(lib.gtos_rel_grad(relb.data_ptr(), Wperm.data_ptr(), qkv.data_ptr(), qkv.data_ptr() + 2 * D, 2 * D,
                                  ds.data_ptr(), G.data_ptr(), N, B, D, H, st), "rel_grad")
     dqkv = torch.zeros(N * B, 3 * D, device=dev)
     _lib.check(lib.gtos_rel_dqk(G.data_ptr(), dqkv.data_ptr(), dqkv.data_ptr() + 4 * D, 3 * D, N, B, D, H, st), "dqk")

@@ -223,7 +223,7 @@ def main_ours(args):
     pinned = {k: v.pin_memory() for k, v in host.items()}
     static = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
-    bucket = FlatGradBucket(model.parameters())
+    bucket = FlatGradBucket(model.parameters(), bind=False)
     loss_buf = torch.zeros((), device=dev)
     loss_host = torch.zeros((), pin_memory=True)
 
@@ -236,6 +236,8 @@ def main_ours(args):
         ops.advance_rng(dev)
         loss = model(static)
         loss.backward()
+        if world > 1:
+            bucket.pack()                             # one multi-tensor copy into the flat all-reduce buffer
         loss_buf.copy_(loss.detach())
 
     upload()

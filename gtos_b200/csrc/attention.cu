@@ -152,7 +152,15 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnArgs a, 
   }
 }
 
-static int attn_rows(int len) { return len <= AT_ROWS_MAX ? (len < 8 ? 8 : len) : 32; }
+// rows per CTA: the whole sequence when there are plenty of (batch, head) CTAs, otherwise split the rows so
+// that the grid still covers ~2 CTAs per SM (e.g. the 1-head alignment attention, decoder.py:13)
+static int attn_rows(int len, int bh) {
+  int want_y = (2 * 148 + bh - 1) / bh;
+  int rows = (len + want_y - 1) / want_y;
+  if (rows < 8) rows = 8;
+  if (rows > AT_ROWS_MAX) rows = 32;
+  return rows;
+}
 static size_t attn_smem_bytes(int L, int hd, int rows) {
   int dc = hd < AT_DC ? hd : AT_DC;
   return sizeof(float) * ((size_t)rows * (dc + 1) + (size_t)L * (dc + 1) + (size_t)rows * (L + 1));
@@ -162,7 +170,7 @@ int attn_fwd(const AttnArgs& a, cudaStream_t st) {
   GTOS_REQUIRE(a.hd >= 1 && (a.hd <= AT_DC || a.hd % AT_DC == 0), "attention: unsupported head_dim %d", a.hd);
   GTOS_REQUIRE(a.p_drop == 0.f || a.seed_ptr, "attention dropout needs a device seed pointer");
   if (a.T == 0 || a.B == 0) return GTOS_OK;
-  const int rows = attn_rows(a.T);
+  const int rows = attn_rows(a.T, a.B * a.H);
   size_t smem = attn_smem_bytes(a.S, a.hd, rows);
   GTOS_REQUIRE(smem <= 227 * 1024, "attention: source length %d too long for shared memory", a.S);
   GTOS_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -299,7 +307,7 @@ int attn_bwd(const AttnBwdArgs& g, cudaStream_t st) {
   const AttnArgs& a = g.f;
   GTOS_REQUIRE(a.hd >= 1 && (a.hd <= AT_DC || a.hd % AT_DC == 0), "attention: unsupported head_dim %d", a.hd);
   if (a.T == 0 || a.B == 0) return GTOS_OK;
-  const int rq = attn_rows(a.T), rk = attn_rows(a.S);
+  const int rq = attn_rows(a.T, a.B * a.H), rk = attn_rows(a.S, a.B * a.H);
   size_t smq = attn_smem_bytes(a.S, a.hd, rq), smk = attn_smem_bytes(a.T, a.hd, rk);
   GTOS_REQUIRE(smq <= 227 * 1024 && smk <= 227 * 1024, "attention: sequence too long for shared memory");
   GTOS_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smq));

@@ -180,6 +180,9 @@ __global__ void add_ln_bwd_kernel(const float* __restrict__ dy, const float* __r
   const unsigned long long seed = (p_drop > 0.f) ? (seed_ptr[0] + seed_off) : 0ull;
   const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
   const int per = (D + 31) / 32;
+  float pg[LN_MAX_PER_LANE], pb[LN_MAX_PER_LANE];  // this lane's running dgamma / dbeta for its columns
+#pragma unroll
+  for (int t = 0; t < LN_MAX_PER_LANE; ++t) pg[t] = pb[t] = 0.f;
   for (long row = (long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long)gridDim.x * wpb) {
     const float mu = mean[row], rs = rstd[row];
     float g[LN_MAX_PER_LANE], xh[LN_MAX_PER_LANE];
@@ -193,8 +196,8 @@ __global__ void add_ln_bwd_kernel(const float* __restrict__ dy, const float* __r
           float d = dy[row * D + c];
           xx = (z[row * D + c] - mu) * rs;
           gg = d * gamma[c];
-          atomicAdd(&sg[c], d * xx);
-          atomicAdd(&sb[c], d);
+          pg[t] += d * xx;
+          pb[t] += d;
         }
         g[t] = gg;
         xh[t] = xx;
@@ -220,6 +223,16 @@ __global__ void add_ln_bwd_kernel(const float* __restrict__ dy, const float* __r
       }
     }
   }
+#pragma unroll
+  for (int t = 0; t < LN_MAX_PER_LANE; ++t) {
+    if (t < per) {
+      int c = t * 32 + lane;
+      if (c < D) {
+        atomicAdd(&sg[c], pg[t]);
+        atomicAdd(&sb[c], pb[t]);
+      }
+    }
+  }
   __syncthreads();
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
     atomicAdd(&dgamma[c], sg[c]);
@@ -236,7 +249,7 @@ int add_ln_bwd(const float* dy, const float* z, const float* mean, const float* 
   if (rows == 0) return GTOS_OK;
   const int wpb = 8;
   long blocks = (rows + wpb - 1) / wpb;
-  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks > 148 * 2) blocks = 148 * 2;
   add_ln_bwd_kernel<<<(unsigned)blocks, wpb * 32, 2 * D * sizeof(float), st>>>(
       dy, z, mean, rstd, gamma, dres, dx, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, rows, D, p_drop,
       reinterpret_cast<const unsigned long long*>(seed_ptr), seed_off);

@@ -610,11 +610,25 @@ int launch_gemm_tn(int mode, const GemmTnArgs& a, cudaStream_t stream) {
   if (mode == MODE_SCORE) return launch_tn<256, MODE_SCORE>(a, stream);
   if (mode == MODE_GRAD) return launch_tn<256, MODE_GRAD>(a, stream);
   if (mode == MODE_DREL) return launch_tn<256, MODE_DREL>(a, stream);
-  // plain: pick the widest N tile that still gives every SM a tile
+  // plain: pick the N tile with the lowest estimated time = waves x (mainloop + epilogue + fixed cost), in SM cycles
   const long mt = (a.M + BM - 1) / BM;
   const int sms = num_sms();
-  if (a.N > 128 && mt * ((a.N + 255) / 256) >= sms) return launch_tn<256, MODE_PLAIN>(a, stream);
-  if (a.N > 64 && mt * ((a.N + 127) / 128) >= sms) return launch_tn<128, MODE_PLAIN>(a, stream);
+  const long kb = (a.K + BK - 1) / BK;
+  int best_bn = 64;
+  double best = 1e30;
+  const int cands[3] = {256, 128, 64};
+  for (int ci = 0; ci < 3; ++ci) {
+    const int bn = cands[ci];
+    if (bn > 64 && a.N <= bn / 2) continue;                       // tile mostly empty
+    const long units = mt * ((a.N + bn - 1) / bn);
+    const long waves = (units + sms - 1) / sms;
+    const double mma = (double)kb * 4 * (bn >= 128 ? bn / 2 : 48);  // UMMA floor M128: N/2 cycles per K=16; N=64 is smem-bound
+    const double epi = (bn / 32) * 350.0;
+    const double cost = waves * (mma > epi ? mma : epi) + 2500.0 + (mma > epi ? epi : mma);
+    if (cost < best) { best = cost; best_bn = bn; }
+  }
+  if (best_bn == 256) return launch_tn<256, MODE_PLAIN>(a, stream);
+  if (best_bn == 128) return launch_tn<128, MODE_PLAIN>(a, stream);
   return launch_tn<64, MODE_PLAIN>(a, stream);
 }
 

@@ -10,22 +10,46 @@ import torch.distributed as dist
 
 
 class FlatGradBucket:
-    def __init__(self, params):
+    """bind=True: every .grad is a view of the flat buffer (backward accumulates in place, no packing copy, but
+    autograd then issues one small add per parameter).  bind=False: backward writes fresh gradients and
+    pack() gathers them with ONE multi-tensor copy right before the collective - fewer launches per step."""
+
+    def __init__(self, params, bind=True):
         self.params = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("FlatGradBucket: no trainable parameters")
         dev, dt = self.params[0].device, self.params[0].dtype
         total = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(total, dtype=dt, device=dev)
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            p.grad = self.flat[off:off + n].view_as(p)
-            off += n
+        self.bound = bind
         self.numel = total
+        if bind:
+            off = 0
+            for p in self.params:
+                n = p.numel()
+                p.grad = self.flat[off:off + n].view_as(p)
+                off += n
 
     def zero(self):
-        self.flat.zero_()
+        if self.bound:
+            self.flat.zero_()
+        else:
+            for p in self.params:
+                p.grad = None
+
+    def pack(self):
+        """gather the per-parameter gradients into the flat buffer (no-op when bound)"""
+        if not self.bound:
+            torch.cat([p.grad.reshape(-1) for p in self.params], out=self.flat)
+
+    def unpack(self):
+        """scatter the (averaged) flat buffer back into the per-parameter gradients (no-op when bound)"""
+        if not self.bound:
+            off = 0
+            for p in self.params:
+                n = p.numel()
+                p.grad = self.flat[off:off + n].view_as(p)
+                off += n
 
     def rebind(self):
         """re-attach the views if something replaced .grad (e.g. zero_grad(set_to_none=True))."""

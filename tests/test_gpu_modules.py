@@ -100,7 +100,7 @@ def test_graph_transformer_vs_oracle(dev, N, B, D, H, F, L, wf):
     assert rel_err(out, ref) < TOL
     assert rel_err(out, ref16) < TOL / 2
     # inflated weights make the net ill-conditioned: a 1e-3 rounding difference is amplified ~10x
-    gtol = TOL if wf == 1.0 else 3 * TOL
+    gtol = TOL if wf == 1.0 else 4 * TOL
     compare_grads(m, P, (out * wo.to(dev)).sum(), (ref16 * wo).sum(), [xg, rg], [xc, rc], tol=gtol, tol_max=0.2)
     compare_grads(m, P, (out * wo.to(dev)).sum(), (ref * wo).sum(), [xg, rg], [xc, rc], tol=0.15, tol_max=0.5)
     with torch.no_grad():
@@ -161,14 +161,14 @@ def test_transformer_external_vs_oracle(dev, T, S, B, D, H, F, L):
     out = m(xg, kv=kg, self_padding_mask=tmask.to(dev), self_attn_mask=cm.to(dev), external_memories=mg,
             external_padding_mask=smask.to(dev))
     assert rel_err(out, ref) < TOL
-    compare_grads(m, P, (out * wo.to(dev)).sum(), (ref16 * wo).sum(), [xg, kg, mg], [xc, kc, mc], tol=3 * TOL, tol_max=0.2)
+    compare_grads(m, P, (out * wo.to(dev)).sum(), (ref16 * wo).sum(), [xg, kg, mg], [xc, kc, mc], tol=4 * TOL, tol_max=0.25)
     # self-attention path (kv=None), causal
     ref2 = O.transformer(P, "", xc, L, H, self_padding_mask=tmask, self_attn_mask=cm, external_memories=mc,
                          external_padding_mask=smask, with_external=True)
     out2 = m(xg, self_padding_mask=tmask.to(dev), self_attn_mask=cm.to(dev), external_memories=mg,
              external_padding_mask=smask.to(dev))
     assert rel_err(out2, ref2) < TOL
-    compare_grads(m, P, (out2 * wo.to(dev)).sum(), (ref2_16 * wo).sum(), [xg, mg], [xc, mc], tol=3 * TOL, tol_max=0.2)
+    compare_grads(m, P, (out2 * wo.to(dev)).sum(), (ref2_16 * wo).sum(), [xg, mg], [xc, mc], tol=4 * TOL, tol_max=0.25)
 
 
 def test_mha_golden_shapes_and_weights(dev, golden):

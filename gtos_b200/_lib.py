@@ -58,8 +58,10 @@ SIGNATURES = {
     "gtos_relu_drop_bwd": (i32, [vp, vp, vp, vp, i64, f32, vp]),
     "gtos_embed_gather": (i32, [vp, vp, i64, i32, vp, vp, i64, f32, vp, u64, vp]),
     "gtos_embed_scatter_add": (i32, [vp, vp, i64, i32, vp, f32, vp, u64, vp]),
-    "gtos_gru_gate_fwd": (i32, [vp, i64, vp, i64, vp, vp, i32, vp, vp, vp, i64, vp, i64, vp, i64, i32, vp]),
-    "gtos_gru_gate_bwd": (i32, [vp, vp, i64, vp, vp, i64, vp, vp, i32, vp, vp, i64, vp, i64, i64, i32, vp]),
+    "gtos_gru_weight_prep": (i32, [vp, vp, vp, vp, i32, i32, i32, vp, i64, vp, vp]),
+    "gtos_gru_step_fwd": (i32, [vp, i64, i32, vp, i64, vp, vp, i64, i32, vp, vp, i32, vp, vp, i64, vp, i64, vp, i64, i64,
+                                i32, vp]),
+    "gtos_gru_gate_bwd": (i32, [vp, vp, i64, vp, vp, vp, i32, vp, vp, i64, vp, i64, i64, i32, vp]),
 }
 
 _lib = None

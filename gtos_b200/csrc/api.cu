@@ -221,17 +221,25 @@ int gtos_embed_scatter_add(const float* dx, const int64_t* idx, int64_t n, int32
   return embed_scatter_add(dx, reinterpret_cast<const long long*>(idx), n, dim, dtable, p_drop, seed_ptr, seed_off,
                            S(stream));
 }
-int gtos_gru_gate_fwd(const float* gi, int64_t ldgi, const float* gh, int64_t ldgh, const float* h_prev,
-                      const int64_t* lengths, int32_t t, float* h_new, void* h_new_bf16, float* out_t, int64_t ldout,
-                      void* out_t_bf16, int64_t ldoutb, float* gates, int64_t R, int32_t Hh, void* stream) {
-  return gru_gate_fwd(gi, ldgi, gh, ldgh, h_prev, reinterpret_cast<const long long*>(lengths), t, h_new, h_new_bf16,
-                      out_t, ldout, out_t_bf16, ldoutb, gates, R, Hh, S(stream));
+int gtos_gru_weight_prep(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int32_t Kin,
+                         int32_t H, int32_t Kx, void* Wcat, int64_t ldw, float* bcat, void* stream) {
+  return gru_weight_prep(w_ih, w_hh, b_ih, b_hh, Kin, H, Kx, Wcat, ldw, bcat, S(stream));
 }
-int gtos_gru_gate_bwd(const float* dh, const float* dout_t, int64_t lddout, const float* gates, const float* gh,
-                      int64_t ldgh, const float* h_prev, const int64_t* lengths, int32_t t, float* dh_prev,
-                      void* dgi_bf16, int64_t lddgi, void* dgh_bf16, int64_t lddgh, int64_t R, int32_t Hh, void* stream) {
-  return gru_gate_bwd(dh, dout_t, lddout, gates, gh, ldgh, h_prev, reinterpret_cast<const long long*>(lengths), t,
-                      dh_prev, dgi_bf16, lddgi, dgh_bf16, lddgh, R, Hh, S(stream));
+int gtos_gru_step_fwd(const void* x, int64_t ldx, int32_t Kin, const void* hb, int64_t ldhb, const float* h_prev,
+                      const void* Wcat, int64_t ldw, int32_t Kx, const float* bcat, const int64_t* lengths, int32_t t,
+                      float* h_new, void* hb_new, int64_t ldhbn, void* out_t, int64_t ldout, void* gates, int64_t ldg,
+                      int64_t R, int32_t H, void* stream) {
+  GruStepArgs a;
+  a.x = x; a.ldx = ldx; a.Kin = Kin; a.hb = hb; a.ldhb = ldhb; a.h_prev = h_prev; a.Wcat = Wcat; a.ldw = ldw; a.Kx = Kx;
+  a.bcat = bcat; a.lengths = reinterpret_cast<const long long*>(lengths); a.t = t; a.h_new = h_new; a.hb_new = hb_new;
+  a.ldhbn = ldhbn; a.out_t = out_t; a.ldout = ldout; a.gates = gates; a.ldg = ldg; a.R = (int)R; a.H = H;
+  return launch_gru_step(a, S(stream));
+}
+int gtos_gru_gate_bwd(const float* dh, const float* dout_t, int64_t lddout, const void* gates, const float* h_prev,
+                      const int64_t* lengths, int32_t t, float* dh_prev, void* dgi_bf16, int64_t lddgi, void* dgh_bf16,
+                      int64_t lddgh, int64_t R, int32_t Hh, void* stream) {
+  return gru_gate_bwd(dh, dout_t, lddout, gates, h_prev, reinterpret_cast<const long long*>(lengths), t, dh_prev, dgi_bf16,
+                      lddgi, dgh_bf16, lddgh, R, Hh, S(stream));
 }
 
 }  // extern "C"

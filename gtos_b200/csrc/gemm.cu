@@ -64,6 +64,15 @@ struct TnDev {
   int bi8, bj8;        // q / k box rows rounded up to 8 (1024-byte swizzle atoms)
   int qk_stage_bytes;  // 4*(bi8+bj8)*128
   int tma_out;         // epilogue stages tiles in shared memory and writes them with TMA stores
+  // MODE_GRU
+  int kx_blocks;       // k-blocks that come from x_t (tmA); the rest come from h_prev (tmQ slot)
+  int gru_H, gru_t;
+  const float* gru_hprev;
+  const long long* gru_len;
+  float* gru_hnew;
+  __nv_bfloat16* gru_hbnew; long gru_ldhbn;
+  __nv_bfloat16* gru_out; long gru_ldout;
+  __nv_bfloat16* gru_gates; long gru_ldg;
 };
 
 __device__ __forceinline__ void rel_tile_decode(const RelTiling& t, int tile, int& b, int& j0, int& i0) {
@@ -184,6 +193,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (REL) {
             mbar_expect_tx(&bars->full[s], (uint32_t)(p.rt.bi * p.rt.bj * 128 + B_STAGE_BYTES));
             tma_load_4d(&tmA, &bars->full[s], sa, kb * BK, b, i0, j0);
+          } else if (MODE == MODE_GRU) {
+            mbar_expect_tx(&bars->full[s], (uint32_t)STAGE_BYTES);
+            if (kb < p.kx_blocks)
+              tma_load_2d(&tmA, &bars->full[s], sa, kb * BK, m_blk * BM);
+            else
+              tma_load_2d(&tmQ, &bars->full[s], sa, (kb - p.kx_blocks) * BK, m_blk * BM);
           } else {
             mbar_expect_tx(&bars->full[s], (uint32_t)STAGE_BYTES);
             tma_load_2d(&tmA, &bars->full[s], sa, kb * BK, m_blk * BM);
@@ -238,7 +253,64 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       const uint32_t tacc = tmem_base + as * BN + ((uint32_t)(quarter * 32) << 16);
 
-      if constexpr (MODE == MODE_PLAIN || MODE == MODE_DREL) {
+      if constexpr (MODE == MODE_GRU) {
+        // ---- GRU gate math: this unit owns hidden units [n_blk*UB, +UB) of rows [m_blk*128, +128) ----
+        constexpr int UB = BN / 4;
+        const long row = (long)m_blk * BM + r;
+        const bool row_ok = row < p.M;
+        const int H = p.gru_H;
+        const bool live = row_ok && (p.gru_len[row] > p.gru_t);
+        const float* bc = p.bias + n_blk * BN;
+#pragma unroll 1
+        for (int c = 0; c < UB; c += 16) {
+          float ar[16], az[16], ai[16], ah[16];
+          tmem_ld16(tacc + c, ar);
+          tmem_ld16(tacc + UB + c, az);
+          tmem_ld16(tacc + 2 * UB + c, ai);
+          tmem_ld16(tacc + 3 * UB + c, ah);
+          tmem_ld_wait();
+          const int u0 = n_blk * UB + c;  // first hidden unit of this chunk
+          if (row_ok && u0 < H) {
+            float hp[16];
+            const float4* hpp = reinterpret_cast<const float4*>(p.gru_hprev + row * H + u0);
+#pragma unroll
+            for (int t4 = 0; t4 < 4; ++t4) {
+              float4 v = hpp[t4];
+              hp[4 * t4] = v.x; hp[4 * t4 + 1] = v.y; hp[4 * t4 + 2] = v.z; hp[4 * t4 + 3] = v.w;
+            }
+            float hn[16], gr[16], gz[16], gn[16], hh[16];
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+              const float r_ = 1.f / (1.f + __expf(-(ar[t] + bc[c + t])));
+              const float z_ = 1.f / (1.f + __expf(-(az[t] + bc[UB + c + t])));
+              const float hn_ = ah[t] + bc[3 * UB + c + t];
+              const float n_ = tanhf(ai[t] + bc[2 * UB + c + t] + r_ * hn_);
+              gr[t] = live ? r_ : 0.f; gz[t] = live ? z_ : 0.f; gn[t] = live ? n_ : 0.f; hh[t] = live ? hn_ : 0.f;
+              hn[t] = live ? (1.f - z_) * n_ + z_ * hp[t] : hp[t];
+            }
+            float4* ho = reinterpret_cast<float4*>(p.gru_hnew + row * H + u0);
+#pragma unroll
+            for (int t4 = 0; t4 < 4; ++t4) ho[t4] = make_float4(hn[4 * t4], hn[4 * t4 + 1], hn[4 * t4 + 2], hn[4 * t4 + 3]);
+            uint4* hb = reinterpret_cast<uint4*>(p.gru_hbnew + row * p.gru_ldhbn + u0);
+            hb[0] = make_uint4(pack_bf16x2(hn[0], hn[1]), pack_bf16x2(hn[2], hn[3]), pack_bf16x2(hn[4], hn[5]), pack_bf16x2(hn[6], hn[7]));
+            hb[1] = make_uint4(pack_bf16x2(hn[8], hn[9]), pack_bf16x2(hn[10], hn[11]), pack_bf16x2(hn[12], hn[13]), pack_bf16x2(hn[14], hn[15]));
+            if (p.gru_out) {
+              uint4* oo = reinterpret_cast<uint4*>(p.gru_out + row * p.gru_ldout + u0);
+              oo[0] = live ? hb[0] : make_uint4(0, 0, 0, 0);
+              oo[1] = live ? hb[1] : make_uint4(0, 0, 0, 0);
+            }
+            __nv_bfloat16* gp = p.gru_gates + row * p.gru_ldg + (long)n_blk * BN + c;
+            const float* srcs[4] = {gr, gz, gn, hh};
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4) {
+              const float* v = srcs[g4];
+              uint4* go = reinterpret_cast<uint4*>(gp + g4 * UB);
+              go[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+              go[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+            }
+          }
+        }
+      } else if constexpr (MODE == MODE_PLAIN || MODE == MODE_DREL) {
         if (p.tma_out) {
           // fp32 tile -> swizzled smem staging tile [128 rows x 32 cols] -> one TMA store per 32-column chunk
           // (double-buffered; OOB rows / columns are clipped by the tensor map)
@@ -630,6 +702,51 @@ int launch_gemm_tn(int mode, const GemmTnArgs& a, cudaStream_t stream) {
   if (best_bn == 256) return launch_tn<256, MODE_PLAIN>(a, stream);
   if (best_bn == 128) return launch_tn<128, MODE_PLAIN>(a, stream);
   return launch_tn<64, MODE_PLAIN>(a, stream);
+}
+
+template <int BN>
+static int launch_gru_bn(const GruStepArgs& a, cudaStream_t stream) {
+  TnDev p;
+  memset(&p, 0, sizeof(p));
+  const int H = a.H;
+  p.M = a.R; p.N = 4 * H; p.K = a.Kx + H;
+  p.m_tiles = (a.R + BM - 1) / BM;
+  p.n_tiles = (4 * H + BN - 1) / BN;
+  p.kx_blocks = a.Kx / BK;
+  p.k_blocks = p.kx_blocks + (H + BK - 1) / BK;
+  p.units = p.m_tiles * p.n_tiles;
+  p.bias = a.bcat;
+  p.gru_H = H; p.gru_t = a.t; p.gru_hprev = a.h_prev; p.gru_len = a.lengths; p.gru_hnew = a.h_new;
+  p.gru_hbnew = reinterpret_cast<__nv_bfloat16*>(a.hb_new); p.gru_ldhbn = a.ldhbn;
+  p.gru_out = reinterpret_cast<__nv_bfloat16*>(a.out_t); p.gru_ldout = a.ldout;
+  p.gru_gates = reinterpret_cast<__nv_bfloat16*>(a.gates); p.gru_ldg = a.ldg;
+  CUtensorMap tmA, tmB, tmH;
+  int e = make_tmap_2d_bf16(&tmA, a.x, (uint64_t)a.R, (uint64_t)((a.Kin + 7) / 8 * 8), (uint64_t)a.ldx, BM);
+  if (e) return e;
+  e = make_tmap_2d_bf16(&tmH, a.hb, (uint64_t)a.R, (uint64_t)H, (uint64_t)a.ldhb, BM);
+  if (e) return e;
+  e = make_tmap_2d_bf16(&tmB, a.Wcat, (uint64_t)(4 * H), (uint64_t)(a.Kx + (H + 7) / 8 * 8), (uint64_t)a.ldw, BN);
+  if (e) return e;
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + BN * BK * 2;
+  int stages = (227 * 1024 - 1024 - (int)sizeof(PipeBars)) / STAGE_BYTES;
+  if (stages > 6) stages = 6;
+  p.stages = stages;
+  const int smem_bytes = 1024 + stages * STAGE_BYTES + (int)sizeof(PipeBars);
+  auto kern = gemm_tn_kernel<BN, MODE_GRU>;
+  GTOS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  int grid = p.units < num_sms() ? p.units : num_sms();
+  if (grid <= 0) return GTOS_OK;
+  kern<<<grid, GEMM_THREADS, smem_bytes, stream>>>(tmA, tmB, tmH, tmH, tmB, p);
+  GTOS_LAUNCH_CHECK();
+  return GTOS_OK;
+}
+
+int launch_gru_step(const GruStepArgs& a, cudaStream_t stream) {
+  GTOS_REQUIRE(a.H % 16 == 0 && a.Kx % 64 == 0 && a.Kx >= a.Kin && a.ldx % 8 == 0 && a.ldhb % 8 == 0 && a.ldw % 8 == 0,
+               "gru_step: need H %% 16 == 0, Kx = 64*ceil(Kin/64), 8-element row strides (H=%d Kx=%d Kin=%d)", a.H, a.Kx, a.Kin);
+  if (a.R == 0) return GTOS_OK;
+  if (a.H % 64 == 0) return launch_gru_bn<256>(a, stream);
+  return launch_gru_bn<64>(a, stream);
 }
 
 // =======================================================================================

@@ -22,6 +22,7 @@ enum GemmMode : int {
   MODE_DREL = 1,   // like PLAIN, rows of A are tile-major pair rows, output rows scattered to relation layout
   MODE_SCORE = 2,  // A = relation tile (4-D box), epilogue: s = scale * <q + ra, k + rb>
   MODE_GRAD = 3,   // A = relation tile, epilogue: G = scale*ds * [k + rb | q + ra]  (bf16, tile-major)
+  MODE_GRU = 4,    // one GRU time step: A = [x_t | h_prev], B = gate-interleaved weights, epilogue = gate math
 };
 
 struct GemmTnArgs {
@@ -49,6 +50,22 @@ struct GemmTnArgs {
   void* G;             // GRAD out: bf16 [tiles*128, 2D] (permuted feature order)
 };
 int launch_gemm_tn(int mode, const GemmTnArgs& a, cudaStream_t stream);
+
+// One packed-sequence GRU step (generator/encoder.py:105-106, nn.GRU cell) as a GEMM with a fused gate epilogue.
+// Wcat rows are interleaved per block of UB = BN/4 hidden units: [r | z | n_input | n_hidden], K = [x (Kx) | h (H)].
+struct GruStepArgs {
+  const void* x;  long ldx;  int Kin;     // bf16 [R, ldx] input of this time step (Kin valid columns)
+  const void* hb; long ldhb;              // bf16 [R, H] previous hidden state (MMA operand)
+  const float* h_prev;                    // fp32 [R, H]
+  const void* Wcat; long ldw; int Kx;     // bf16 [4H, Kx + H8], Kx = 64*ceil(Kin/64)
+  const float* bcat;                      // fp32 [4H] interleaved like Wcat rows
+  const long long* lengths; int t;        // packed-sequence masking: row live iff lengths[row] > t
+  float* h_new; void* hb_new; long ldhbn; // fp32 / bf16 [R, H]
+  void* out_t; long ldout;                // bf16 layer output at time t (zero for finished rows), may be null
+  void* gates; long ldg;                  // bf16 [R, 4H] saved (r, z, n, W_hn h + b_hn) for backward
+  int R, H;
+};
+int launch_gru_step(const GruStepArgs& a, cudaStream_t stream);
 
 // out[M,N] = sum_k A[k,m] * B[k,n]   (both operands MN-major), split-K with fp32 partials
 struct GemmNnArgs {

@@ -8,60 +8,53 @@ namespace gtos {
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
 
-__global__ void gru_gate_fwd_kernel(const float* __restrict__ gi, long ldgi, const float* __restrict__ gh, long ldgh,
-                                    const float* __restrict__ h_prev, const long long* __restrict__ lengths, int t,
-                                    float* __restrict__ h_new, __nv_bfloat16* __restrict__ h_new_bf16,
-                                    float* __restrict__ out_t, long ldout, __nv_bfloat16* __restrict__ out_t_bf16,
-                                    long ldoutb, float* __restrict__ gates, long R, int Hh) {
-  const long total = R * Hh;
-  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const long r = idx / Hh;
-    const int c = (int)(idx % Hh);
-    const bool live = lengths[r] > t;
-    const float hp = h_prev[idx];
-    float hn = hp, o = 0.f, gr = 0.f, gz = 0.f, gn = 0.f;
-    if (live) {
-      const float* a = gi + r * ldgi;
-      const float* bq = gh + r * ldgh;
-      gr = sigmoidf_(a[c] + bq[c]);
-      gz = sigmoidf_(a[Hh + c] + bq[Hh + c]);
-      gn = tanhf(a[2 * Hh + c] + gr * bq[2 * Hh + c]);
-      hn = (1.f - gz) * gn + gz * hp;
-      o = hn;
+// Gate-interleaved GRU weights for the fused step kernel (gemm.cu, MODE_GRU).
+// Wcat[4H, Kx + H8] rows, per block of UB hidden units: [r | z | n_input | n_hidden]; columns [x part (Kx) | h part].
+__global__ void gru_weight_prep_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh,
+                                       const float* __restrict__ b_ih, const float* __restrict__ b_hh, int Kin, int H,
+                                       int Kx, int UB, __nv_bfloat16* __restrict__ Wcat, long ldw,
+                                       float* __restrict__ bcat) {
+  const int pr = blockIdx.x;                 // permuted row in [0, 4H)
+  const int u = pr / (4 * UB), g = (pr / UB) & 3, cc = pr % UB;
+  const int c = u * UB + cc;                 // hidden unit
+  const int gate = g < 2 ? g : 2;            // r, z, n
+  const float* wi = w_ih + (long)(gate * H + c) * Kin;
+  const float* wh = w_hh + (long)(gate * H + c) * H;
+  for (int k = threadIdx.x; k < ldw; k += blockDim.x) {
+    float v = 0.f;
+    if (k < Kx) {
+      if (k < Kin && g != 3) v = wi[k];
+    } else if (k - Kx < H && g != 2) {
+      v = wh[k - Kx];
     }
-    h_new[idx] = hn;
-    if (h_new_bf16) h_new_bf16[idx] = __float2bfloat16(hn);
-    if (out_t) out_t[r * ldout + c] = o;
-    if (out_t_bf16) out_t_bf16[r * ldoutb + c] = __float2bfloat16(o);
-    if (gates) {
-      gates[r * 3 * Hh + c] = gr;
-      gates[r * 3 * Hh + Hh + c] = gz;
-      gates[r * 3 * Hh + 2 * Hh + c] = gn;
-    }
+    Wcat[(long)pr * ldw + k] = __float2bfloat16(v);
+  }
+  if (threadIdx.x == 0) {
+    float b = 0.f;
+    if (g != 3) b += b_ih[gate * H + c];
+    if (g != 2) b += b_hh[gate * H + c];
+    bcat[pr] = b;
   }
 }
 
-int gru_gate_fwd(const float* gi, long ldgi, const float* gh, long ldgh, const float* h_prev, const long long* lengths,
-                 int t, float* h_new, void* h_new_bf16, float* out_t, long ldout, void* out_t_bf16, long ldoutb,
-                 float* gates, long R, int Hh, cudaStream_t st) {
-  if (R == 0) return GTOS_OK;
-  long blocks = (R * Hh + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  gru_gate_fwd_kernel<<<(unsigned)blocks, 256, 0, st>>>(gi, ldgi, gh, ldgh, h_prev, lengths, t, h_new,
-                                                        reinterpret_cast<__nv_bfloat16*>(h_new_bf16), out_t, ldout,
-                                                        reinterpret_cast<__nv_bfloat16*>(out_t_bf16), ldoutb, gates, R,
-                                                        Hh);
+int gru_weight_prep(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int Kin, int H, int Kx,
+                    void* Wcat, long ldw, float* bcat, cudaStream_t st) {
+  GTOS_REQUIRE(H % 16 == 0 && Kx % 64 == 0 && Kx >= Kin && ldw >= Kx + H, "gru_weight_prep: bad shape");
+  const int UB = (H % 64 == 0) ? 64 : 16;
+  gru_weight_prep_kernel<<<4 * H, 128, 0, st>>>(w_ih, w_hh, b_ih, b_hh, Kin, H, Kx, UB,
+                                                reinterpret_cast<__nv_bfloat16*>(Wcat), ldw, bcat);
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
 }
 
 // dh_tot = dh + dout_t ;  n,z,r chain rule ; dh_prev = dh_tot * z (the W_hh^T dgh term is added by a
-// following GEMM with accumulate) ; inactive rows pass dh through untouched and emit zero gate grads.
+// following GEMM with accumulate) ; finished rows pass dh through untouched and emit zero gate grads.
+// gates: bf16 [R, 4H] as saved by the fused step kernel (blocks of UB units: [r | z | n | W_hn h + b_hn]).
 __global__ void gru_gate_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ dout_t, long lddout,
-                                    const float* __restrict__ gates, const float* __restrict__ gh, long ldgh,
-                                    const float* __restrict__ h_prev, const long long* __restrict__ lengths, int t,
-                                    float* __restrict__ dh_prev, __nv_bfloat16* __restrict__ dgi, long lddgi,
-                                    __nv_bfloat16* __restrict__ dgh, long lddgh, long R, int Hh) {
+                                    const __nv_bfloat16* __restrict__ gates, const float* __restrict__ h_prev,
+                                    const long long* __restrict__ lengths, int t, float* __restrict__ dh_prev,
+                                    __nv_bfloat16* __restrict__ dgi, long lddgi, __nv_bfloat16* __restrict__ dgh,
+                                    long lddgh, long R, int Hh, int UB) {
   const long total = R * Hh;
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
     const long r = idx / Hh;
@@ -71,8 +64,9 @@ __global__ void gru_gate_bwd_kernel(const float* __restrict__ dh, const float* _
     float dar = 0.f, daz = 0.f, dan = 0.f, dhn = 0.f, dprev = d;
     if (live) {
       if (dout_t) d += dout_t[r * lddout + c];
-      const float gr = gates[r * 3 * Hh + c], gz = gates[r * 3 * Hh + Hh + c], gn = gates[r * 3 * Hh + 2 * Hh + c];
-      const float hnn = gh[r * ldgh + 2 * Hh + c];  // W_hn h + b_hn
+      const __nv_bfloat16* gp = gates + r * 4L * Hh + (c / UB) * 4 * UB + (c % UB);
+      const float gr = __bfloat162float(gp[0]), gz = __bfloat162float(gp[UB]), gn = __bfloat162float(gp[2 * UB]);
+      const float hnn = __bfloat162float(gp[3 * UB]);
       const float hp = h_prev[idx];
       const float dn = d * (1.f - gz);
       const float dz = d * (hp - gn);
@@ -92,15 +86,18 @@ __global__ void gru_gate_bwd_kernel(const float* __restrict__ dh, const float* _
   }
 }
 
-int gru_gate_bwd(const float* dh, const float* dout_t, long lddout, const float* gates, const float* gh, long ldgh,
-                 const float* h_prev, const long long* lengths, int t, float* dh_prev, void* dgi_bf16, long lddgi,
-                 void* dgh_bf16, long lddgh, long R, int Hh, cudaStream_t st) {
+int gru_gate_bwd(const float* dh, const float* dout_t, long lddout, const void* gates, const float* h_prev,
+                 const long long* lengths, int t, float* dh_prev, void* dgi_bf16, long lddgi, void* dgh_bf16,
+                 long lddgh, long R, int Hh, cudaStream_t st) {
   if (R == 0) return GTOS_OK;
+  GTOS_REQUIRE(Hh % 16 == 0, "gru_gate_bwd: hidden size must be a multiple of 16");
   long blocks = (R * Hh + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  gru_gate_bwd_kernel<<<(unsigned)blocks, 256, 0, st>>>(dh, dout_t, lddout, gates, gh, ldgh, h_prev, lengths, t, dh_prev,
+  const int UB = (Hh % 64 == 0) ? 64 : 16;
+  gru_gate_bwd_kernel<<<(unsigned)blocks, 256, 0, st>>>(dh, dout_t, lddout, reinterpret_cast<const __nv_bfloat16*>(gates),
+                                                        h_prev, lengths, t, dh_prev,
                                                         reinterpret_cast<__nv_bfloat16*>(dgi_bf16), lddgi,
-                                                        reinterpret_cast<__nv_bfloat16*>(dgh_bf16), lddgh, R, Hh);
+                                                        reinterpret_cast<__nv_bfloat16*>(dgh_bf16), lddgh, R, Hh, UB);
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
 }

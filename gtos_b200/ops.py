@@ -474,17 +474,18 @@ class MHAFn(torch.autograd.Function):
 # --------------------------------------------------------------------------------------------
 # RelationEncoder: embedding -> packed 2-layer bidirectional GRU -> Linear  (encoder.py:90-119)
 # --------------------------------------------------------------------------------------------
-def _gate_fwd(gi_t, gh, h_prev, lengths, t, h_new, hb_new, out_t, outb_t, gates_t, R, Hh):
-    _lib.check(_lib.load().gtos_gru_gate_fwd(_p(gi_t), gi_t.stride(0), _p(gh), gh.stride(0), _p(h_prev), _p(lengths), t,
-                                             _p(h_new), _p(hb_new), _p(out_t),
-                                             out_t.stride(0) if out_t is not None else 0, _p(outb_t),
-                                             outb_t.stride(0) if outb_t is not None else 0, _p(gates_t), R, Hh, _st()),
-               "gru_gate_fwd")
+def _up64(n):
+    return (n + 63) // 64 * 64
 
 
 class GRUBankFn(torch.autograd.Function):
     """tokens [Lmax,R] int64 (0 = pad), lengths [R] int64 -> [R, embed_dim].  `weights` is the flat list
-    (w_ih, w_hh, b_ih, b_hh) per (layer, direction) in nn.GRU order."""
+    (w_ih, w_hh, b_ih, b_hh) per (layer, direction) in nn.GRU order.
+
+    Forward: per (layer, direction, time step) ONE tcgen05 GEMM [x_t | h] x Wcat^T whose epilogue does the gate
+    math, packed-sequence masking and writes h (fp32 + bf16 operand copy), the layer output and the saved gates
+    (gtos_gru_step_fwd) - no gi / gh round trips through HBM.  Backward: BPTT with a gate kernel + accumulate
+    GEMM per step, then three big GEMMs per (layer, direction) for dW_ih, dW_hh and dx."""
 
     @staticmethod
     def forward(ctx, tokens, lengths, embed_w, out_w, out_b, num_layers, hidden, p, *weights):
@@ -504,36 +505,44 @@ class GRUBankFn(torch.autograd.Function):
                                          _st()), "embed_gather")
         saved, layer_offs = [], []
         finals_b = torch.empty(R, 2 * Hh, dtype=torch.bfloat16, device=dev)
+        Kin = E
         for l in range(num_layers):
             outb = torch.empty(rows, 2 * Hh, dtype=torch.bfloat16, device=dev)
+            Kx = _up64(Kin)
             for d in range(2):
                 w_ih, w_hh, b_ih, b_hh = weights[(l * 2 + d) * 4:(l * 2 + d) * 4 + 4]
-                Wih_b, Wih_t = weight_prep(w_ih)
-                Whh_b, Whh_t = weight_prep(w_hh)
-                gi_all, _ = gemm_tn(xb, Wih_b, 3 * Hh, bias=b_ih)                  # [rows, 3H]
-                # per-direction state indexed by processing step s (time t = s forward, Lmax-1-s reverse):
-                # hs[s] = state before step s, hs[s+1] = state after it
-                gates = torch.empty(Lmax, R, 3 * Hh, dtype=torch.float32, device=dev)
-                gh_all = torch.empty(Lmax, R, 3 * Hh, dtype=torch.float32, device=dev)
+                _, Wih_t = weight_prep(w_ih, want_b=False)                         # for dx in backward
+                _, Whh_t = weight_prep(w_hh, want_b=False)                         # for dh in backward
+                ldw = Kx + _up8(Hh)
+                Wcat = torch.empty(4 * Hh, ldw, dtype=torch.bfloat16, device=dev)
+                bcat = torch.empty(4 * Hh, dtype=torch.float32, device=dev)
+                _lib.check(lib.gtos_gru_weight_prep(_p(w_ih.detach()), _p(w_hh.detach()), _p(b_ih.detach()),
+                                                    _p(b_hh.detach()), Kin, Hh, Kx, _p(Wcat), ldw, _p(bcat), _st()),
+                           "gru_weight_prep")
+                # state indexed by processing step s (time t = s forward, Lmax-1-s reverse): hs[s] -> hs[s+1]
+                gates = torch.empty(Lmax, R, 4 * Hh, dtype=torch.bfloat16, device=dev)
                 hs = torch.empty(Lmax + 1, R, Hh, dtype=torch.float32, device=dev)
                 hsb = torch.empty(Lmax + 1, R, Hh, dtype=torch.bfloat16, device=dev)
                 hs[0].zero_()
                 hsb[0].zero_()
                 for s in range(Lmax):
                     t = s if d == 0 else Lmax - 1 - s
-                    gemm_tn(hsb[s], Whh_b, 3 * Hh, bias=b_hh, out=gh_all[s])
-                    _gate_fwd(gi_all[t * R:(t + 1) * R], gh_all[s], hs[s], lengths, t, hs[s + 1], hsb[s + 1], None,
-                              outb[t * R:(t + 1) * R, d * Hh:(d + 1) * Hh], gates[s], R, Hh)
-                hb = hsb[Lmax]
+                    x_t = xb[t * R:(t + 1) * R]
+                    out_t = outb[t * R:(t + 1) * R, d * Hh:(d + 1) * Hh]
+                    _lib.check(lib.gtos_gru_step_fwd(_p(x_t), x_t.stride(0), Kin, _p(hsb[s]), Hh, _p(hs[s]), _p(Wcat), ldw,
+                                                     Kx, _p(bcat), _p(lengths), t, _p(hs[s + 1]), _p(hsb[s + 1]), Hh,
+                                                     _p(out_t), out_t.stride(0), _p(gates[s]), 4 * Hh, R, Hh, _st()),
+                               "gru_step_fwd")
                 if l == num_layers - 1:
-                    finals_b[:, d * Hh:(d + 1) * Hh].copy_(hb)
-                saved += [xb, gates, gh_all, hs, hsb, Wih_t, Whh_t]
+                    finals_b[:, d * Hh:(d + 1) * Hh].copy_(hsb[Lmax])
+                saved += [xb, gates, hs, hsb, Wih_t, Whh_t]
             off_l = 0
             if l < num_layers - 1 and p > 0:                                       # nn.GRU inter-layer dropout
                 off_l = new_seed_off()
                 _lib.check(lib.gtos_dropout_bf16(_p(outb), outb.numel(), p, _p(seed), off_l, _st()), "dropout_bf16")
             layer_offs.append(off_l)
             xb = outb
+            Kin = 2 * Hh
         Wo_b, Wo_t = weight_prep(out_w)
         out, _ = gemm_tn(finals_b, Wo_b, out_w.shape[0], bias=out_b)
         ctx.save_for_backward(tokens, lengths, finals_b, Wo_t, *saved)
@@ -558,7 +567,7 @@ class GRUBankFn(torch.autograd.Function):
         for l in range(num_layers - 1, -1, -1):
             dx = None
             for d in range(2):
-                xb, gates, gh_all, hs, hsb, Wih_t, Whh_t = saved[(l * 2 + d) * 7:(l * 2 + d) * 7 + 7]
+                xb, gates, hs, hsb, Wih_t, Whh_t = saved[(l * 2 + d) * 6:(l * 2 + d) * 6 + 6]
                 Kin = Wih_t.shape[0]
                 dgi = torch.empty(rows, 3 * Hh, dtype=torch.bfloat16, device=dev)      # rows in time order t
                 dgh = torch.empty(rows, 3 * Hh, dtype=torch.bfloat16, device=dev)      # rows in step order s
@@ -571,9 +580,9 @@ class GRUBankFn(torch.autograd.Function):
                     dout_t = d_layer_out[t * R:(t + 1) * R, d * Hh:(d + 1) * Hh] if d_layer_out is not None else None
                     dh_prev = torch.empty_like(dh)
                     _lib.check(lib.gtos_gru_gate_bwd(_p(dh), _p(dout_t), dout_t.stride(0) if dout_t is not None else 0,
-                                                     _p(gates[s]), _p(gh_all[s]), 3 * Hh, _p(hs[s]), _p(lengths), t,
-                                                     _p(dh_prev), _p(dgi[t * R:(t + 1) * R]), 3 * Hh,
-                                                     _p(dgh[s * R:(s + 1) * R]), 3 * Hh, R, Hh, _st()), "gru_gate_bwd")
+                                                     _p(gates[s]), _p(hs[s]), _p(lengths), t, _p(dh_prev),
+                                                     _p(dgi[t * R:(t + 1) * R]), 3 * Hh, _p(dgh[s * R:(s + 1) * R]),
+                                                     3 * Hh, R, Hh, _st()), "gru_gate_bwd")
                     gemm_tn(dgh[s * R:(s + 1) * R], Whh_t, Hh, out=dh_prev, accumulate=True)
                     dh = dh_prev
                 base = (l * 2 + d) * 4

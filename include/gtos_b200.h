@@ -129,12 +129,19 @@ int gtos_embed_gather(const float* table, const int64_t* idx, int64_t n, int32_t
                       int64_t ldb, float p_drop, const void* seed_ptr, uint64_t seed_off, void* stream);
 int gtos_embed_scatter_add(const float* dx, const int64_t* idx, int64_t n, int32_t dim, float* dtable, float p_drop,
                            const void* seed_ptr, uint64_t seed_off, void* stream);
-int gtos_gru_gate_fwd(const float* gi, int64_t ldgi, const float* gh, int64_t ldgh, const float* h_prev,
-                      const int64_t* lengths, int32_t t, float* h_new, void* h_new_bf16, float* out_t, int64_t ldout,
-                      void* out_t_bf16, int64_t ldoutb, float* gates, int64_t R, int32_t Hh, void* stream);
-int gtos_gru_gate_bwd(const float* dh, const float* dout_t, int64_t lddout, const float* gates, const float* gh,
-                      int64_t ldgh, const float* h_prev, const int64_t* lengths, int32_t t, float* dh_prev,
-                      void* dgi_bf16, int64_t lddgi, void* dgh_bf16, int64_t lddgh, int64_t R, int32_t Hh, void* stream);
+/* gate-interleaved weights for the fused step: Wcat bf16 [4H, Kx + H] (Kx = 64*ceil(Kin/64)), bcat fp32 [4H] */
+int gtos_gru_weight_prep(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int32_t Kin,
+                         int32_t H, int32_t Kx, void* Wcat, int64_t ldw, float* bcat, void* stream);
+/* ONE packed-sequence GRU time step (nn.GRU cell, gates r,z,n; encoder.py:105-106): tcgen05 GEMM
+ * [x_t | h_prev] x Wcat^T with the gate math, length masking and all stores fused in the epilogue.
+ * gates: bf16 [R,4H] saved for backward (r, z, n, W_hn h + b_hn).  out_t: bf16 layer output (0 for finished rows). */
+int gtos_gru_step_fwd(const void* x, int64_t ldx, int32_t Kin, const void* hb, int64_t ldhb, const float* h_prev,
+                      const void* Wcat, int64_t ldw, int32_t Kx, const float* bcat, const int64_t* lengths, int32_t t,
+                      float* h_new, void* hb_new, int64_t ldhbn, void* out_t, int64_t ldout, void* gates, int64_t ldg,
+                      int64_t R, int32_t H, void* stream);
+int gtos_gru_gate_bwd(const float* dh, const float* dout_t, int64_t lddout, const void* gates, const float* h_prev,
+                      const int64_t* lengths, int32_t t, float* dh_prev, void* dgi_bf16, int64_t lddgi, void* dgh_bf16,
+                      int64_t lddgh, int64_t R, int32_t Hh, void* stream);
 
 #ifdef __cplusplus
 }

@@ -211,6 +211,14 @@ int gtos_relu_drop_bwd(const float* dh_in, const void* act_bf16, float* dh_f32, 
                        void* stream) {
   return relu_drop_bwd(dh_in, act_bf16, dh_f32, dh_bf16, n, p, S(stream));
 }
+int gtos_bank_gather(const float* bank, const int64_t* idx, int64_t P, int32_t D, float* out_f32, void* out_bf16,
+                     void* stream) {
+  return bank_gather(bank, reinterpret_cast<const long long*>(idx), P, D, out_f32, out_bf16, S(stream));
+}
+int gtos_bank_scatter_add(const float* d_rel, const int64_t* idx, int64_t P, int32_t D, float* d_bank, int64_t R,
+                          void* stream) {
+  return bank_scatter_add(d_rel, reinterpret_cast<const long long*>(idx), P, D, d_bank, R, S(stream));
+}
 int gtos_embed_gather(const float* table, const int64_t* idx, int64_t n, int32_t dim, float* out_f32, void* out_bf16,
                       int64_t ldb, float p_drop, const void* seed_ptr, uint64_t seed_off, void* stream) {
   return embed_gather(table, reinterpret_cast<const long long*>(idx), n, dim, out_f32, out_bf16, ldb, p_drop, seed_ptr,

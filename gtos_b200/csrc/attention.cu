@@ -17,57 +17,110 @@ static constexpr int AT_WARPS = 8;
 static constexpr int AT_ROWS_MAX = 64;  // query (or key) rows per CTA: all rows when the sequence is short
 static constexpr int AT_DC = 64;    // feature chunk
 
+// shared-memory working set of one CTA.  Row strides are multiples of 4 floats (16-byte vector loads):
+//   xs [rows][dstr]  query-side chunk (q or dO)       dstr = round4(dc) + 4  (=68 for dc=64: conflict-free LDS.128)
+//   ys [L4][dstr]    key-side chunk (K, V, dO or q)   L4 = round4(L), pad rows zero
+//   sc [rows][lstr]  score block                      lstr = L4 + 4
 struct AttnSmem {
-  float* xs;  // [rows][dc+1]
-  float* ys;  // [L][dc+1]
-  float* sc;  // [rows][L+1]
+  float* xs;
+  float* ys;
+  float* sc;
+  int dstr, lstr, L4;
 };
+
+__host__ __device__ inline int r4(int n) { return (n + 3) & ~3; }
 
 __device__ __forceinline__ AttnSmem carve(float* base, int L, int dc, int AT_ROWS) {
   AttnSmem s;
+  s.dstr = r4(dc) + 4;
+  s.L4 = r4(L);
+  s.lstr = s.L4 + 4;
   s.xs = base;
-  s.ys = s.xs + AT_ROWS * (dc + 1);
-  s.sc = s.ys + (size_t)L * (dc + 1);
+  s.ys = s.xs + (size_t)AT_ROWS * s.dstr;
+  s.sc = s.ys + (size_t)s.L4 * s.dstr;
   return s;
 }
 
-// rows [r0, r0+nr) x dims [c0, c0+dc) of a [len, B, ld] projection for (b, h) -> dst[nr][dc+1]
-__device__ __forceinline__ void load_rows(float* dst, const float* src, long ld, int B, int b, int hoff, int r0, int nr,
-                                          int len, int c0, int dc) {
-  for (int idx = threadIdx.x; idx < nr * dc; idx += AT_THREADS) {
-    int r = idx / dc, d = idx - r * dc;
+// rows [r0, r0+nr) x dims [c0, c0+dc) of a [len, B, ld] projection for (b, h) -> dst[nr][dstr]; rows >= len and the
+// pad columns are zero-filled
+__device__ __forceinline__ void load_rows(float* dst, int dstr, const float* src, long ld, int B, int b, int hoff,
+                                          int r0, int nr, int len, int c0, int dc) {
+  const int dc4 = r4(dc);
+  for (int idx = threadIdx.x; idx < nr * dc4; idx += AT_THREADS) {
+    int r = idx / dc4, d = idx - r * dc4;
     int t = r0 + r;
-    dst[r * (dc + 1) + d] = (t < len) ? src[((long)t * B + b) * ld + hoff + c0 + d] : 0.f;
+    dst[r * dstr + d] = (t < len && d < dc) ? src[((long)t * B + b) * ld + hoff + c0 + d] : 0.f;
   }
 }
 
-// sc[r][j] += sum_d xs[r][d] * ys[j][d]     (lanes over j)
+constexpr int AT_RB = 8;  // rows per warp pass (register blocking)
+
+// sc[r][j] += sum_d xs[r][d] * ys[j][d]     lanes over j, AT_RB rows per pass, 16-byte smem loads along d
 __device__ __forceinline__ void nt_accumulate(const AttnSmem& s, int L, int dc, int nrows) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int r = warp; r < nrows; r += AT_WARPS) {
-    const float* x = s.xs + r * (dc + 1);
+  const int dq = r4(dc) >> 2;
+  for (int r0 = warp * AT_RB; r0 < nrows; r0 += AT_WARPS * AT_RB) {
     for (int j = lane; j < L; j += 32) {
-      const float* y = s.ys + (size_t)j * (dc + 1);
-      float acc = 0.f;
-#pragma unroll 8
-      for (int d = 0; d < dc; ++d) acc = fmaf(x[d], y[d], acc);
-      s.sc[r * (L + 1) + j] += acc;
+      const float4* y = reinterpret_cast<const float4*>(s.ys + (size_t)j * s.dstr);
+      float acc[AT_RB];
+#pragma unroll
+      for (int rr = 0; rr < AT_RB; ++rr) acc[rr] = 0.f;
+      for (int d4 = 0; d4 < dq; ++d4) {
+        const float4 yv = y[d4];
+#pragma unroll
+        for (int rr = 0; rr < AT_RB; ++rr) {
+          const float4 xv = reinterpret_cast<const float4*>(s.xs + (size_t)(r0 + rr) * s.dstr)[d4];
+          acc[rr] = fmaf(xv.x, yv.x, fmaf(xv.y, yv.y, fmaf(xv.z, yv.z, fmaf(xv.w, yv.w, acc[rr]))));
+        }
+      }
+#pragma unroll
+      for (int rr = 0; rr < AT_RB; ++rr)
+        if (r0 + rr < nrows) s.sc[(size_t)(r0 + rr) * s.lstr + j] += acc[rr];
     }
   }
 }
 
-// out[(row)*ld + d] = sum_j sc[r][j] * ys[j][d]   (lanes over d)
+// out[r][d] = sum_j sc[r][j] * ys[j][d]   lanes over d (two per lane for dc = 64), AT_RB rows per pass
 template <class F>
 __device__ __forceinline__ void nn_product(const AttnSmem& s, int L, int dc, int nrows, F&& store) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int r = warp; r < nrows; r += AT_WARPS) {
-    const float* w = s.sc + r * (L + 1);
-    for (int d = lane; d < dc; d += 32) {
-      float acc = 0.f;
-      for (int j = 0; j < L; ++j) acc = fmaf(w[j], s.ys[(size_t)j * (dc + 1) + d], acc);
-      store(r, d, acc);
+  const int d0 = lane, d1 = lane + 32;
+  const bool has1 = d1 < dc, has0 = d0 < dc;
+  for (int r0 = warp * AT_RB; r0 < nrows; r0 += AT_WARPS * AT_RB) {
+    float a0[AT_RB], a1[AT_RB];
+#pragma unroll
+    for (int rr = 0; rr < AT_RB; ++rr) a0[rr] = a1[rr] = 0.f;
+    for (int j4 = 0; j4 < s.L4; j4 += 4) {
+      float y0[4], y1[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float* yr = s.ys + (size_t)(j4 + u) * s.dstr;
+        y0[u] = has0 ? yr[d0] : 0.f;
+        y1[u] = has1 ? yr[d1] : 0.f;
+      }
+#pragma unroll
+      for (int rr = 0; rr < AT_RB; ++rr) {
+        const float4 w = *reinterpret_cast<const float4*>(s.sc + (size_t)(r0 + rr) * s.lstr + j4);
+        a0[rr] = fmaf(w.x, y0[0], fmaf(w.y, y0[1], fmaf(w.z, y0[2], fmaf(w.w, y0[3], a0[rr]))));
+        a1[rr] = fmaf(w.x, y1[0], fmaf(w.y, y1[1], fmaf(w.z, y1[2], fmaf(w.w, y1[3], a1[rr]))));
+      }
+    }
+#pragma unroll
+    for (int rr = 0; rr < AT_RB; ++rr) {
+      if (r0 + rr < nrows) {
+        if (has0) store(r0 + rr, d0, a0[rr]);
+        if (has1) store(r0 + rr, d1, a1[rr]);
+      }
     }
   }
+}
+
+// zero the pad columns [L, lstr) of every score row and the pad rows [L, L4) of ys (so vector loops can run to L4)
+__device__ __forceinline__ void zero_pads(const AttnSmem& s, int L, int rows) {
+  const int padc = s.lstr - L;
+  for (int idx = threadIdx.x; idx < rows * padc; idx += AT_THREADS) s.sc[(size_t)(idx / padc) * s.lstr + L + idx % padc] = 0.f;
+  const int padr = s.L4 - L;
+  for (int idx = threadIdx.x; idx < padr * s.dstr; idx += AT_THREADS) s.ys[(size_t)L * s.dstr + idx] = 0.f;
 }
 
 __device__ __forceinline__ bool is_masked(const AttnArgs& a, int b, int t, int j) {
@@ -87,19 +140,20 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnArgs a, 
   const int hoff = h * a.hd;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = a.S;
+  zero_pads(s, S, AT_ROWS);
 
   if (a.scores_jt) {
     for (int idx = threadIdx.x; idx < S * AT_ROWS; idx += AT_THREADS) {
       int j = idx / AT_ROWS, r = idx % AT_ROWS;
-      s.sc[r * (S + 1) + j] = (r < nrows) ? a.scores_jt[((long)bh * S + j) * a.T + t0 + r] : 0.f;
+      s.sc[(size_t)r * s.lstr + j] = (r < nrows) ? a.scores_jt[((long)bh * S + j) * a.T + t0 + r] : 0.f;
     }
     __syncthreads();
   } else {
-    for (int idx = threadIdx.x; idx < AT_ROWS * (S + 1); idx += AT_THREADS) s.sc[idx] = 0.f;
+    for (int idx = threadIdx.x; idx < AT_ROWS * s.lstr; idx += AT_THREADS) s.sc[idx] = 0.f;
     for (int c0 = 0; c0 < a.hd; c0 += dc) {
       __syncthreads();
-      load_rows(s.xs, a.q, a.ldq, a.B, b, hoff, t0, AT_ROWS, a.T, c0, dc);
-      load_rows(s.ys, a.k, a.ldk, a.B, b, hoff, 0, S, S, c0, dc);
+      load_rows(s.xs, s.dstr, a.q, a.ldq, a.B, b, hoff, t0, AT_ROWS, a.T, c0, dc);
+      load_rows(s.ys, s.dstr, a.k, a.ldk, a.B, b, hoff, 0, S, S, c0, dc);
       __syncthreads();
       nt_accumulate(s, S, dc, nrows);
     }
@@ -112,7 +166,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnArgs a, 
   const float sscale = a.scores_jt ? 1.f : a.scale;
   for (int r = warp; r < nrows; r += AT_WARPS) {
     const int t = t0 + r;
-    float* w = s.sc + r * (S + 1);
+    float* w = s.sc + (size_t)r * s.lstr;
     float mx = -INFINITY;
     for (int j = lane; j < S; j += 32) {
       float v = is_masked(a, b, t, j) ? -INFINITY : w[j] * sscale;
@@ -142,7 +196,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnArgs a, 
   __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(a.out_bf16);
   for (int c0 = 0; c0 < a.hd; c0 += dc) {
     __syncthreads();
-    load_rows(s.ys, a.v, a.ldv, a.B, b, hoff, 0, S, S, c0, dc);
+    load_rows(s.ys, s.dstr, a.v, a.ldv, a.B, b, hoff, 0, S, S, c0, dc);
     __syncthreads();
     nn_product(s, S, dc, nrows, [&](int r, int d, float acc) {
       long o = ((long)(t0 + r) * a.B + b) * a.ldo + hoff + c0 + d;
@@ -157,13 +211,14 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnArgs a, 
 static int attn_rows(int len, int bh) {
   int want_y = (2 * 148 + bh - 1) / bh;
   int rows = (len + want_y - 1) / want_y;
-  if (rows < 8) rows = 8;
+  rows = (rows + 7) & ~7;  // register blocking reads whole groups of AT_RB = 8 rows
   if (rows > AT_ROWS_MAX) rows = 32;
   return rows;
 }
 static size_t attn_smem_bytes(int L, int hd, int rows) {
   int dc = hd < AT_DC ? hd : AT_DC;
-  return sizeof(float) * ((size_t)rows * (dc + 1) + (size_t)L * (dc + 1) + (size_t)rows * (L + 1));
+  int dstr = r4(dc) + 4, L4 = r4(L);
+  return sizeof(float) * ((size_t)rows * dstr + (size_t)L4 * dstr + (size_t)rows * (L4 + 4));
 }
 
 int attn_fwd(const AttnArgs& a, cudaStream_t st) {
@@ -195,13 +250,15 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_q_kernel(const AttnBwdArg
   const int hoff = h * a.hd;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = a.S;
+  zero_pads(s, S, AT_ROWS);
+  __syncthreads();
 
   // dPd[t][j] = dO[t] . V[j]
-  for (int idx = threadIdx.x; idx < AT_ROWS * (S + 1); idx += AT_THREADS) s.sc[idx] = 0.f;
+  for (int idx = threadIdx.x; idx < AT_ROWS * s.lstr; idx += AT_THREADS) s.sc[idx] = 0.f;
   for (int c0 = 0; c0 < a.hd; c0 += dc) {
     __syncthreads();
-    load_rows(s.xs, g.dout, g.lddo, a.B, b, hoff, t0, AT_ROWS, a.T, c0, dc);
-    load_rows(s.ys, a.v, a.ldv, a.B, b, hoff, 0, S, S, c0, dc);
+    load_rows(s.xs, s.dstr, g.dout, g.lddo, a.B, b, hoff, t0, AT_ROWS, a.T, c0, dc);
+    load_rows(s.ys, s.dstr, a.v, a.ldv, a.B, b, hoff, 0, S, S, c0, dc);
     __syncthreads();
     nt_accumulate(s, S, dc, nrows);
   }
@@ -211,7 +268,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_q_kernel(const AttnBwdArg
   const float ks = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
   for (int r = warp; r < nrows; r += AT_WARPS) {
     const int t = t0 + r;
-    float* w = s.sc + r * (S + 1);
+    float* w = s.sc + (size_t)r * s.lstr;
     const long prow = ((long)bh * a.T + t) * S;
     float dot = 0.f;
     for (int j = lane; j < S; j += 32) {
@@ -235,13 +292,13 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_q_kernel(const AttnBwdArg
     // transposed store for the fused relation backward kernel: [B,H,S(j),T(i)], coalesced along i
     for (int idx = threadIdx.x; idx < S * AT_ROWS; idx += AT_THREADS) {
       int j = idx / AT_ROWS, r = idx % AT_ROWS;
-      if (r < nrows) g.dscores_jt[((long)bh * S + j) * a.T + t0 + r] = s.sc[r * (S + 1) + j];
+      if (r < nrows) g.dscores_jt[((long)bh * S + j) * a.T + t0 + r] = s.sc[(size_t)r * s.lstr + j];
     }
   }
   if (g.dq) {
     for (int c0 = 0; c0 < a.hd; c0 += dc) {
       __syncthreads();
-      load_rows(s.ys, a.k, a.ldk, a.B, b, hoff, 0, S, S, c0, dc);
+      load_rows(s.ys, s.dstr, a.k, a.ldk, a.B, b, hoff, 0, S, S, c0, dc);
       __syncthreads();
       nn_product(s, S, dc, nrows, [&](int r, int d, float acc) {
         g.dq[((long)(t0 + r) * a.B + b) * g.lddq + hoff + c0 + d] = acc * a.scale;
@@ -267,6 +324,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_kv_kernel(const AttnBwdAr
   const unsigned long long seed = a.p_drop > 0.f ? reinterpret_cast<const unsigned long long*>(a.seed_ptr)[0] + a.seed_off : 0ull;
   const float ks = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
 
+  zero_pads(s, T, AT_ROWS);
   // sc[jr][t] = Pd[t][j0+jr]
   for (int idx = threadIdx.x; idx < T * AT_ROWS; idx += AT_THREADS) {
     int t = idx / AT_ROWS, jr = idx % AT_ROWS;
@@ -276,11 +334,11 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_kv_kernel(const AttnBwdAr
       p = a.probs[pi];
       if (a.p_drop > 0.f) p = (rng_uniform(seed, (unsigned long long)pi) >= a.p_drop) ? p * ks : 0.f;
     }
-    s.sc[jr * (T + 1) + t] = p;
+    s.sc[(size_t)jr * s.lstr + t] = p;
   }
   for (int c0 = 0; c0 < a.hd; c0 += dc) {
     __syncthreads();
-    load_rows(s.ys, g.dout, g.lddo, a.B, b, hoff, 0, T, T, c0, dc);
+    load_rows(s.ys, s.dstr, g.dout, g.lddo, a.B, b, hoff, 0, T, T, c0, dc);
     __syncthreads();
     nn_product(s, T, dc, nrows, [&](int r, int d, float acc) {
       g.dv[((long)(j0 + r) * a.B + b) * g.lddv + hoff + c0 + d] = acc;
@@ -290,11 +348,11 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_kv_kernel(const AttnBwdAr
     __syncthreads();
     for (int idx = threadIdx.x; idx < T * AT_ROWS; idx += AT_THREADS) {
       int t = idx / AT_ROWS, jr = idx % AT_ROWS;
-      s.sc[jr * (T + 1) + t] = (jr < nrows) ? g.dscores_ts[((long)bh * T + t) * S + j0 + jr] * a.scale : 0.f;
+      s.sc[(size_t)jr * s.lstr + t] = (jr < nrows) ? g.dscores_ts[((long)bh * T + t) * S + j0 + jr] * a.scale : 0.f;
     }
     for (int c0 = 0; c0 < a.hd; c0 += dc) {
       __syncthreads();
-      load_rows(s.ys, a.q, a.ldq, a.B, b, hoff, 0, T, T, c0, dc);
+      load_rows(s.ys, s.dstr, a.q, a.ldq, a.B, b, hoff, 0, T, T, c0, dc);
       __syncthreads();
       nn_product(s, T, dc, nrows, [&](int r, int d, float acc) {
         g.dk[((long)(j0 + r) * a.B + b) * g.lddk + hoff + c0 + d] = acc;

@@ -167,77 +167,68 @@ int add_ln_fwd(const float* x, const float* res, const float* gamma, const float
 __global__ void add_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
                                   const float* __restrict__ mean, const float* __restrict__ rstd,
                                   const float* __restrict__ gamma, float* __restrict__ dres, float* __restrict__ dx,
-                                  __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma,
-                                  float* __restrict__ dbeta, long rows, int D, float p_drop,
+                                  __nv_bfloat16* __restrict__ dx_bf16, long rows, int D, float p_drop,
                                   const unsigned long long* __restrict__ seed_ptr, unsigned long long seed_off) {
-  extern __shared__ float sh[];  // [2][D] block partials of dgamma / dbeta
-  float* sg = sh;
-  float* sb = sh + D;
-  for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) sh[c] = 0.f;
-  __syncthreads();
+  // one warp per row (many warps in flight: the kernel is latency-bound on three dependent passes per row)
   const int lane = threadIdx.x & 31;
-  const int wpb = blockDim.x >> 5;
+  const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
   const unsigned long long seed = (p_drop > 0.f) ? (seed_ptr[0] + seed_off) : 0ull;
   const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
   const int per = (D + 31) / 32;
-  float pg[LN_MAX_PER_LANE], pb[LN_MAX_PER_LANE];  // this lane's running dgamma / dbeta for its columns
+  const float mu = mean[row], rs = rstd[row];
+  float g[LN_MAX_PER_LANE], xh[LN_MAX_PER_LANE];
+  float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-  for (int t = 0; t < LN_MAX_PER_LANE; ++t) pg[t] = pb[t] = 0.f;
-  for (long row = (long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long)gridDim.x * wpb) {
-    const float mu = mean[row], rs = rstd[row];
-    float g[LN_MAX_PER_LANE], xh[LN_MAX_PER_LANE];
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int t = 0; t < LN_MAX_PER_LANE; ++t) {
-      if (t < per) {
-        int c = t * 32 + lane;
-        float gg = 0.f, xx = 0.f;
-        if (c < D) {
-          float d = dy[row * D + c];
-          xx = (z[row * D + c] - mu) * rs;
-          gg = d * gamma[c];
-          pg[t] += d * xx;
-          pb[t] += d;
-        }
-        g[t] = gg;
-        xh[t] = xx;
-        s1 += gg;
-        s2 += gg * xx;
+  for (int t = 0; t < LN_MAX_PER_LANE; ++t) {
+    if (t < per) {
+      int c = t * 32 + lane;
+      float gg = 0.f, xx = 0.f;
+      if (c < D) {
+        xx = (z[row * D + c] - mu) * rs;
+        gg = dy[row * D + c] * gamma[c];
       }
-    }
-    s1 = warp_sum(s1) / D;
-    s2 = warp_sum(s2) / D;
-#pragma unroll
-    for (int t = 0; t < LN_MAX_PER_LANE; ++t) {
-      if (t < per) {
-        int c = t * 32 + lane;
-        if (c < D) {
-          float dz = rs * (g[t] - s1 - xh[t] * s2);
-          if (dres) dres[row * D + c] = dz;
-          float dxx = dz;
-          if (p_drop > 0.f)
-            dxx = (rng_uniform(seed, (unsigned long long)(row * D + c)) >= p_drop) ? dz * keep_scale : 0.f;
-          if (dx) dx[row * D + c] = dxx;
-          if (dx_bf16) dx_bf16[row * D + c] = __float2bfloat16(dxx);
-        }
-      }
+      g[t] = gg;
+      xh[t] = xx;
+      s1 += gg;
+      s2 += gg * xx;
     }
   }
+  s1 = warp_sum(s1) / D;
+  s2 = warp_sum(s2) / D;
 #pragma unroll
   for (int t = 0; t < LN_MAX_PER_LANE; ++t) {
     if (t < per) {
       int c = t * 32 + lane;
       if (c < D) {
-        atomicAdd(&sg[c], pg[t]);
-        atomicAdd(&sb[c], pb[t]);
+        float dz = rs * (g[t] - s1 - xh[t] * s2);
+        if (dres) dres[row * D + c] = dz;
+        float dxx = dz;
+        if (p_drop > 0.f) dxx = (rng_uniform(seed, (unsigned long long)(row * D + c)) >= p_drop) ? dz * keep_scale : 0.f;
+        if (dx) dx[row * D + c] = dxx;
+        if (dx_bf16) dx_bf16[row * D + c] = __float2bfloat16(dxx);
       }
     }
   }
-  __syncthreads();
-  for (int c = threadIdx.x; c < D; c += blockDim.x) {
-    atomicAdd(&dgamma[c], sg[c]);
-    atomicAdd(&dbeta[c], sb[c]);
+}
+
+// dgamma[c] = sum_rows dy * xhat, dbeta[c] = sum_rows dy : coalesced column reduction, one atomic per (column, row block)
+__global__ void ln_param_grad_kernel(const float* __restrict__ dy, const float* __restrict__ z,
+                                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                                     float* __restrict__ dgamma, float* __restrict__ dbeta, long rows, int D,
+                                     int rows_per_block) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= D) return;
+  long r0 = (long)blockIdx.y * rows_per_block;
+  long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float ag = 0.f, ab = 0.f;
+  for (long r = r0; r < r1; ++r) {
+    const float d = dy[r * D + c];
+    ag += d * (z[r * D + c] - mean[r]) * rstd[r];
+    ab += d;
   }
+  atomicAdd(&dgamma[c], ag);
+  atomicAdd(&dbeta[c], ab);
 }
 
 int add_ln_bwd(const float* dy, const float* z, const float* mean, const float* rstd, const float* gamma, float* dres,
@@ -247,12 +238,14 @@ int add_ln_bwd(const float* dy, const float* z, const float* mean, const float* 
   GTOS_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, sizeof(float) * D, st));
   GTOS_CHECK_CUDA(cudaMemsetAsync(dbeta, 0, sizeof(float) * D, st));
   if (rows == 0) return GTOS_OK;
-  const int wpb = 8;
-  long blocks = (rows + wpb - 1) / wpb;
-  if (blocks > 148 * 2) blocks = 148 * 2;
-  add_ln_bwd_kernel<<<(unsigned)blocks, wpb * 32, 2 * D * sizeof(float), st>>>(
-      dy, z, mean, rstd, gamma, dres, dx, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, rows, D, p_drop,
+  const int wpb = 4;
+  add_ln_bwd_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(
+      dy, z, mean, rstd, gamma, dres, dx, reinterpret_cast<__nv_bfloat16*>(dx_bf16), rows, D, p_drop,
       reinterpret_cast<const unsigned long long*>(seed_ptr), seed_off);
+  GTOS_LAUNCH_CHECK();
+  const int rpb = 32;
+  dim3 grid((D + 127) / 128, (unsigned)((rows + rpb - 1) / rpb));
+  ln_param_grad_kernel<<<grid, 128, 0, st>>>(dy, z, mean, rstd, dgamma, dbeta, rows, D, rpb);
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
 }
@@ -375,6 +368,63 @@ int relu_drop_bwd(const float* dh_in, const void* act, float* dh_f32, void* dh_b
 // (per head: [d(q+ra) (hd) | d(k+rb) (hd)]).  Outputs are written into the [N*B, ld] grad buffer
 // of the fused QKV projection (dq at column 0, dk at column D).
 // ---------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------
+// bank -> dense relation gather (generator/generator.py:79) and its backward scatter-add.
+// forward writes the fp32 tensor the caller's contract needs AND the bf16 copy the tensor-core kernels read.
+// ---------------------------------------------------------------------------------------
+__global__ void bank_gather_kernel(const float* __restrict__ bank, const long long* __restrict__ idx, long P, int D,
+                                   float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16) {
+  const int lane = threadIdx.x & 31;
+  const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+  for (long p = warp; p < P; p += nwarps) {
+    const float4* src = reinterpret_cast<const float4*>(bank + idx[p] * D);
+    for (int c = lane; c < D / 4; c += 32) {
+      float4 v = src[c];
+      if (out_f32) reinterpret_cast<float4*>(out_f32 + p * D)[c] = v;
+      if (out_bf16) reinterpret_cast<uint2*>(out_bf16 + p * D)[c] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    }
+  }
+}
+
+__global__ void bank_scatter_add_kernel(const float* __restrict__ d_rel, const long long* __restrict__ idx, long P, int D,
+                                        float* __restrict__ d_bank) {
+  const int lane = threadIdx.x & 31;
+  const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+  for (long p = warp; p < P; p += nwarps) {
+    float* dst = d_bank + idx[p] * D;
+    const float4* src = reinterpret_cast<const float4*>(d_rel + p * D);
+    for (int c = lane; c < D / 4; c += 32) {
+      float4 v = src[c];
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * c), "f"(v.x), "f"(v.y), "f"(v.z),
+                   "f"(v.w)
+                   : "memory");
+    }
+  }
+}
+
+int bank_gather(const float* bank, const long long* idx, long P, int D, float* out_f32, void* out_bf16, cudaStream_t st) {
+  GTOS_REQUIRE(D % 4 == 0, "bank_gather: D must be a multiple of 4");
+  if (P == 0) return GTOS_OK;
+  long blocks = (P * 32 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  bank_gather_kernel<<<(unsigned)blocks, 256, 0, st>>>(bank, idx, P, D, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  GTOS_LAUNCH_CHECK();
+  return GTOS_OK;
+}
+
+int bank_scatter_add(const float* d_rel, const long long* idx, long P, int D, float* d_bank, long R, cudaStream_t st) {
+  GTOS_REQUIRE(D % 4 == 0, "bank_scatter_add: D must be a multiple of 4");
+  GTOS_CHECK_CUDA(cudaMemsetAsync(d_bank, 0, sizeof(float) * R * D, st));
+  if (P == 0) return GTOS_OK;
+  long blocks = (P * 32 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  bank_scatter_add_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_rel, idx, P, D, d_bank);
+  GTOS_LAUNCH_CHECK();
+  return GTOS_OK;
+}
+
 __global__ void rel_dqk_kernel(const __nv_bfloat16* __restrict__ G, RelTiling rt, float* __restrict__ dq,
                                float* __restrict__ dk, long ld) {
   // block = (node n, batch b); thread = one 8-column (16-byte) chunk of the 2D-wide G row.

@@ -20,6 +20,8 @@ int dropout_bf16(void* h, long n, float p, const void* seed_ptr, unsigned long l
 int dropout_f32(const float* x, float* out, long n, float p, const void* seed_ptr, unsigned long long seed_off,
                 cudaStream_t st);
 int relu_drop_bwd(const float* dh_in, const void* act, float* dh_f32, void* dh_bf16, long n, float p, cudaStream_t st);
+int bank_gather(const float* bank, const long long* idx, long P, int D, float* out_f32, void* out_bf16, cudaStream_t st);
+int bank_scatter_add(const float* d_rel, const long long* idx, long P, int D, float* d_bank, long R, cudaStream_t st);
 int rel_dqk(const void* G, const RelTiling& rt, float* dq, float* dk, long ld, cudaStream_t st);
 
 // ---- attention core (attention.cu) ------------------------------------------------------

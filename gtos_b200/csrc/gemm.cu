@@ -131,7 +131,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* qk_base = smem + p.stages * STAGE_BYTES;
   uint8_t* out_stage = qk_base + (REL ? 2 * p.qk_stage_bytes : 0);  // 1024-aligned (all regions are multiples of 1 KB)
-  PipeBars* bars = reinterpret_cast<PipeBars*>(out_stage + (p.tma_out ? OUT_STAGE_BYTES : 0));
+  PipeBars* bars = reinterpret_cast<PipeBars*>(out_stage + (p.tma_out ? OUT_STAGE_BYTES : (MODE == MODE_GRU ? 2 * BN * 4 : 0)));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -248,6 +248,28 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int kc = 0;  // running output-chunk counter: staging buffer = kc & 1
     for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
       const int m_blk = unit / p.n_tiles, n_blk = unit % p.n_tiles;
+      // MODE_GRU: fetch this thread's slice of the previous state, the bias block and the length flag while the
+      // tensor core is still producing the accumulator (4 epilogue warps cannot hide DRAM latency otherwise)
+      [[maybe_unused]] float gru_hp[MODE == MODE_GRU ? BN / 4 : 1];
+      [[maybe_unused]] bool gru_live = false;
+      [[maybe_unused]] const float* gru_bias = nullptr;
+      if constexpr (MODE == MODE_GRU) {
+        constexpr int UB = BN / 4;
+        const long row = (long)m_blk * BM + r;
+        float* sb = reinterpret_cast<float*>(out_stage) + (as * BN);     // bias block of this unit, per accumulator stage
+        for (int t = r; t < BN; t += 128) sb[t] = p.bias[n_blk * BN + t];
+        gru_bias = sb;
+        if (row < p.M) {
+          gru_live = p.gru_len[row] > p.gru_t;
+          const float4* hpp = reinterpret_cast<const float4*>(p.gru_hprev + row * p.gru_H + n_blk * UB);
+#pragma unroll
+          for (int t4 = 0; t4 < UB / 4; ++t4) {
+            float4 v = (n_blk * UB + 4 * t4 < p.gru_H) ? hpp[t4] : make_float4(0.f, 0.f, 0.f, 0.f);
+            gru_hp[4 * t4] = v.x; gru_hp[4 * t4 + 1] = v.y; gru_hp[4 * t4 + 2] = v.z; gru_hp[4 * t4 + 3] = v.w;
+          }
+        }
+        named_bar_sync(1, 128);  // bias block visible to all epilogue warps
+      }
       wait_bar(&bars->tfull[as], aph);
       if (REL) wait_bar(&bars->qfull[qs], qph);
       tc_fence_after();
@@ -255,13 +277,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
       if constexpr (MODE == MODE_GRU) {
         // ---- GRU gate math: this unit owns hidden units [n_blk*UB, +UB) of rows [m_blk*128, +128) ----
+        // (the previous-state loads for the unit are issued BEFORE waiting on the accumulator, see gru_prefetch)
         constexpr int UB = BN / 4;
         const long row = (long)m_blk * BM + r;
         const bool row_ok = row < p.M;
         const int H = p.gru_H;
-        const bool live = row_ok && (p.gru_len[row] > p.gru_t);
-        const float* bc = p.bias + n_blk * BN;
-#pragma unroll 1
+        const bool live = row_ok && gru_live;
+#pragma unroll
         for (int c = 0; c < UB; c += 16) {
           float ar[16], az[16], ai[16], ah[16];
           tmem_ld16(tacc + c, ar);
@@ -271,43 +293,43 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tmem_ld_wait();
           const int u0 = n_blk * UB + c;  // first hidden unit of this chunk
           if (row_ok && u0 < H) {
-            float hp[16];
-            const float4* hpp = reinterpret_cast<const float4*>(p.gru_hprev + row * H + u0);
-#pragma unroll
-            for (int t4 = 0; t4 < 4; ++t4) {
-              float4 v = hpp[t4];
-              hp[4 * t4] = v.x; hp[4 * t4 + 1] = v.y; hp[4 * t4 + 2] = v.z; hp[4 * t4 + 3] = v.w;
-            }
+            const float* hp = gru_hp + c;
             float hn[16], gr[16], gz[16], gn[16], hh[16];
 #pragma unroll
             for (int t = 0; t < 16; ++t) {
-              const float r_ = 1.f / (1.f + __expf(-(ar[t] + bc[c + t])));
-              const float z_ = 1.f / (1.f + __expf(-(az[t] + bc[UB + c + t])));
-              const float hn_ = ah[t] + bc[3 * UB + c + t];
-              const float n_ = tanhf(ai[t] + bc[2 * UB + c + t] + r_ * hn_);
+              const float r_ = __fdividef(1.f, 1.f + __expf(-(ar[t] + gru_bias[c + t])));
+              const float z_ = __fdividef(1.f, 1.f + __expf(-(az[t] + gru_bias[UB + c + t])));
+              const float hn_ = ah[t] + gru_bias[3 * UB + c + t];
+              const float pre = ai[t] + gru_bias[2 * UB + c + t] + r_ * hn_;
+              const float n_ = 1.f - __fdividef(2.f, 1.f + __expf(2.f * pre));   // tanh
               gr[t] = live ? r_ : 0.f; gz[t] = live ? z_ : 0.f; gn[t] = live ? n_ : 0.f; hh[t] = live ? hn_ : 0.f;
               hn[t] = live ? (1.f - z_) * n_ + z_ * hp[t] : hp[t];
             }
             float4* ho = reinterpret_cast<float4*>(p.gru_hnew + row * H + u0);
 #pragma unroll
             for (int t4 = 0; t4 < 4; ++t4) ho[t4] = make_float4(hn[4 * t4], hn[4 * t4 + 1], hn[4 * t4 + 2], hn[4 * t4 + 3]);
+            const uint4 hb0 = make_uint4(pack_bf16x2(hn[0], hn[1]), pack_bf16x2(hn[2], hn[3]), pack_bf16x2(hn[4], hn[5]), pack_bf16x2(hn[6], hn[7]));
+            const uint4 hb1 = make_uint4(pack_bf16x2(hn[8], hn[9]), pack_bf16x2(hn[10], hn[11]), pack_bf16x2(hn[12], hn[13]), pack_bf16x2(hn[14], hn[15]));
             uint4* hb = reinterpret_cast<uint4*>(p.gru_hbnew + row * p.gru_ldhbn + u0);
-            hb[0] = make_uint4(pack_bf16x2(hn[0], hn[1]), pack_bf16x2(hn[2], hn[3]), pack_bf16x2(hn[4], hn[5]), pack_bf16x2(hn[6], hn[7]));
-            hb[1] = make_uint4(pack_bf16x2(hn[8], hn[9]), pack_bf16x2(hn[10], hn[11]), pack_bf16x2(hn[12], hn[13]), pack_bf16x2(hn[14], hn[15]));
+            hb[0] = hb0;
+            hb[1] = hb1;
             if (p.gru_out) {
               uint4* oo = reinterpret_cast<uint4*>(p.gru_out + row * p.gru_ldout + u0);
-              oo[0] = live ? hb[0] : make_uint4(0, 0, 0, 0);
-              oo[1] = live ? hb[1] : make_uint4(0, 0, 0, 0);
+              oo[0] = live ? hb0 : make_uint4(0, 0, 0, 0);
+              oo[1] = live ? hb1 : make_uint4(0, 0, 0, 0);
             }
             __nv_bfloat16* gp = p.gru_gates + row * p.gru_ldg + (long)n_blk * BN + c;
-            const float* srcs[4] = {gr, gz, gn, hh};
-#pragma unroll
-            for (int g4 = 0; g4 < 4; ++g4) {
-              const float* v = srcs[g4];
-              uint4* go = reinterpret_cast<uint4*>(gp + g4 * UB);
-              go[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-              go[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
-            }
+#define GTOS_STORE16(dst, v)                                                                                          \
+  do {                                                                                                                \
+    uint4* _g = reinterpret_cast<uint4*>(dst);                                                                        \
+    _g[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));       \
+    _g[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15])); \
+  } while (0)
+            GTOS_STORE16(gp, gr);
+            GTOS_STORE16(gp + UB, gz);
+            GTOS_STORE16(gp + 2 * UB, gn);
+            GTOS_STORE16(gp + 3 * UB, hh);
+#undef GTOS_STORE16
           }
         }
       } else if constexpr (MODE == MODE_PLAIN || MODE == MODE_DREL) {
@@ -728,10 +750,10 @@ static int launch_gru_bn(const GruStepArgs& a, cudaStream_t stream) {
   e = make_tmap_2d_bf16(&tmB, a.Wcat, (uint64_t)(4 * H), (uint64_t)(a.Kx + (H + 7) / 8 * 8), (uint64_t)a.ldw, BN);
   if (e) return e;
   constexpr int STAGE_BYTES = A_STAGE_BYTES + BN * BK * 2;
-  int stages = (227 * 1024 - 1024 - (int)sizeof(PipeBars)) / STAGE_BYTES;
+  int stages = (227 * 1024 - 1024 - (int)sizeof(PipeBars) - 2 * BN * 4) / STAGE_BYTES;
   if (stages > 6) stages = 6;
   p.stages = stages;
-  const int smem_bytes = 1024 + stages * STAGE_BYTES + (int)sizeof(PipeBars);
+  const int smem_bytes = 1024 + stages * STAGE_BYTES + 2 * BN * 4 + (int)sizeof(PipeBars);
   auto kern = gemm_tn_kernel<BN, MODE_GRU>;
   GTOS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   int grid = p.units < num_sms() ? p.units : num_sms();

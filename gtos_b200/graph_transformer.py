@@ -22,20 +22,28 @@ class GraphTransformer(nn.Module):
             self.layers.append(GraphTransformerLayer(embed_dim, ff_embed_dim, num_heads, dropout, weights_dropout))
 
     def forward(self, x, relation, kv=None, self_padding_mask=None, self_attn_mask=None):
-        # every layer reads the SAME relation tensor (:16-17): stage its bf16 copy once
-        relb = ops.relation_to_bf16(relation.detach().contiguous())
+        # every layer reads the SAME relation tensor (:16-17): stage its bf16 copy once (or reuse the one
+        # ops.bank_gather made while building the tensor)
+        relb = _staged_bf16(relation)
         xb = None
         for layer in self.layers:
             x, xb, _ = layer._forward(x, xb, relation, relb, kv, self_padding_mask, self_attn_mask, False)
         return x
 
     def get_attn_weights(self, x, relation, kv=None, self_padding_mask=None, self_attn_mask=None):
-        relb = ops.relation_to_bf16(relation.detach().contiguous())
+        relb = _staged_bf16(relation)
         attns, xb = [], None
         for layer in self.layers:
             x, xb, attn = layer._forward(x, xb, relation, relb, kv, self_padding_mask, self_attn_mask, True)
             attns.append(attn)
         return torch.stack(attns)
+
+
+def _staged_bf16(relation):
+    relb = getattr(relation, "_gtos_bf16", None)
+    if relb is not None and relb.shape == relation.shape and relb.device == relation.device:
+        return relb
+    return ops.relation_to_bf16(relation.detach().contiguous())
 
 
 class GraphTransformerLayer(nn.Module):

@@ -10,6 +10,7 @@ import math
 import torch
 from torch import nn
 
+from . import ops
 from .decoder import DecodeLayer
 from .encoder import RelationEncoder
 from .graph_transformer import GraphTransformer
@@ -52,7 +53,7 @@ class HotPath(nn.Module):
         """generator.py:76-94: relation bank -> dense relation -> graph encoder -> probe / node states."""
         bank = self.relation_encoder(batch["relation_bank"], batch["relation_length"])
         idx = batch["relation"]
-        relation = bank.index_select(0, idx.reshape(-1)).view(*idx.shape, -1)       # generator.py:79
+        relation = ops.bank_gather(bank, idx)                                       # generator.py:79 (+ bf16 copy)
         h = self.graph_encoder(batch["x"], relation, self_padding_mask=batch["node_mask"])
         probe = torch.tanh(self.probe_generator(h[:1]))
         return h[1:], batch["node_mask"][1:], probe

@@ -637,3 +637,41 @@ class LinearFn(torch.autograd.Function):
 
 def linear(x, W, b=None):
     return LinearFn.apply(x, W, b)
+
+
+# --------------------------------------------------------------------------------------------
+# bank -> dense relation gather (generator.py:79) with the bf16 operand copy made in the same pass
+# --------------------------------------------------------------------------------------------
+class BankGatherFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, bank, idx):
+        _need_cuda(bank, idx)
+        bank = bank.contiguous()
+        idx = idx.contiguous()
+        R, D = bank.shape
+        P = idx.numel()
+        rel = torch.empty(*idx.shape, D, dtype=torch.float32, device=bank.device)
+        relb = torch.empty(*idx.shape, D, dtype=torch.bfloat16, device=bank.device)
+        _lib.check(_lib.load().gtos_bank_gather(_p(bank), _p(idx), P, D, _p(rel), _p(relb), _st()), "bank_gather")
+        ctx.save_for_backward(idx)
+        ctx.meta = (R, D, P)
+        ctx.mark_non_differentiable(relb)
+        return rel, relb
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_rel, _d_relb):
+        (idx,) = ctx.saved_tensors
+        R, D, P = ctx.meta
+        d_rel = d_rel.contiguous()
+        d_bank = torch.empty(R, D, dtype=torch.float32, device=d_rel.device)
+        _lib.check(_lib.load().gtos_bank_scatter_add(_p(d_rel), _p(idx), P, D, _p(d_bank), R, _st()), "bank_scatter_add")
+        return d_bank, None
+
+
+def bank_gather(bank, idx):
+    """relation = bank[idx] as (fp32 dense tensor, bf16 copy).  The dense tensor carries the bf16 copy as
+    `._gtos_bf16` so GraphTransformer.forward does not stage it again."""
+    rel, relb = BankGatherFn.apply(bank, idx)
+    rel._gtos_bf16 = relb
+    return rel

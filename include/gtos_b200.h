@@ -124,6 +124,14 @@ int gtos_dropout_f32(const float* x, float* out, int64_t n, float p, const void*
 int gtos_relu_drop_bwd(const float* dh_in, const void* act_bf16, float* dh_f32, void* dh_bf16, int64_t n, float p,
                        void* stream);
 
+/* ---- bank -> dense relation gather (generator.py:79: relation = bank.index_select(0, idx)) and its backward ----
+ * forward emits the fp32 [P,D] tensor of the caller's contract and (optionally) the bf16 copy the fused kernels read;
+ * backward zero-fills d_bank [R,D] and scatter-adds the dense gradient with 16-byte vector reductions. */
+int gtos_bank_gather(const float* bank, const int64_t* idx, int64_t P, int32_t D, float* out_f32, void* out_bf16,
+                     void* stream);
+int gtos_bank_scatter_add(const float* d_rel, const int64_t* idx, int64_t P, int32_t D, float* d_bank, int64_t R,
+                          void* stream);
+
 /* ---- RelationEncoder (encoder.py:90-119): embedding + GRU gate math; GEMMs via gtos_gemm_* ---- */
 int gtos_embed_gather(const float* table, const int64_t* idx, int64_t n, int32_t dim, float* out_f32, void* out_bf16,
                       int64_t ldb, float p_drop, const void* seed_ptr, uint64_t seed_off, void* stream);

@@ -1,0 +1,100 @@
+"""-m gpu: BASELINE.json config-2 sizes (N=41 nodes incl. <CLS>, B=64 graphs, D=512, H=8, 4 layers), where the CPU
+oracle is too slow to be the checker.  Parity is shown through size-independent properties of the path:
+  * graphs in a batch are independent (attention is per graph): permuting the batch permutes the outputs, bit-exact;
+  * padded nodes are inert: growing the padding does not change any valid node's output;
+  * attention weights are a distribution over the un-padded keys;
+  * the synthetic-batch relation bank round-trips through bank_gather / index_select exactly;
+and one sampled graph of the full batch is checked against the oracle run on that graph alone."""
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import gtos_oracle as O
+
+pytestmark = pytest.mark.gpu
+SEED = 19940117
+
+
+@pytest.fixture(scope="module")
+def setup():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a B200")
+    from gtos_b200 import _lib, synthetic
+    from gtos_b200.graph_transformer import GraphTransformer
+    _lib.check(_lib.load().gtos_device_check(), "device_check")
+    dev = torch.device("cuda:0")
+    torch.manual_seed(SEED)
+    g = synthetic.make_batch(64, 40, 512, seed=SEED)
+    N, B, D = g["N"], 64, 512
+    model = GraphTransformer(4, D, 1024, 8, 0.0)
+    gen = torch.Generator().manual_seed(SEED)
+    bank = torch.randn(g["relation_bank"].shape[1], D, generator=gen) * 0.5
+    return dict(dev=dev, g=g, N=N, B=B, D=D, model_cpu=model, model=GraphTransformer(4, D, 1024, 8, 0.0).to(dev), bank=bank)
+
+
+def _dense(s, perm=None):
+    from gtos_b200 import ops
+    g, dev = s["g"], s["dev"]
+    idx = g["relation"] if perm is None else g["relation"][:, :, perm]
+    return ops.bank_gather(s["bank"].to(dev), idx.to(dev)), idx
+
+
+def test_bank_gather_matches_index_select_at_full_size(setup):
+    s = setup
+    rel, idx = _dense(s)
+    ref = s["bank"].index_select(0, idx.reshape(-1)).view(*idx.shape, -1)
+    assert torch.equal(rel.cpu(), ref)
+
+
+def test_batch_permutation_equivariance_bit_exact(setup):
+    s = setup
+    g, dev, m = s["g"], s["dev"], s["model"]
+    m.load_state_dict(s["model_cpu"].state_dict())
+    x, mask = g["x"].to(dev), g["node_mask"].to(dev)
+    rel, _ = _dense(s)
+    with torch.no_grad():
+        out = m(x, rel, self_padding_mask=mask)
+        perm = torch.randperm(s["B"], generator=torch.Generator().manual_seed(1))
+        relp, _ = _dense(s, perm)
+        outp = m(x[:, perm.to(dev)], relp, self_padding_mask=mask[:, perm.to(dev)])
+    assert torch.isfinite(out).all()
+    assert torch.equal(out[:, perm.to(dev)], outp)
+
+
+def test_padding_is_inert_and_weights_are_distributions(setup):
+    s = setup
+    g, dev, m = s["g"], s["dev"], s["model"]
+    m.load_state_dict(s["model_cpu"].state_dict())
+    N, B, D = s["N"], s["B"], s["D"]
+    x, mask = g["x"].to(dev), g["node_mask"].to(dev)
+    rel, _ = _dense(s)
+    pad = 7
+    xp = torch.cat([x, torch.randn(pad, B, D, device=dev)], 0)
+    maskp = torch.cat([mask, torch.ones(pad, B, dtype=torch.bool, device=dev)], 0)
+    relp = torch.randn(N + pad, N + pad, B, D, device=dev)
+    relp[:N, :N] = rel
+    with torch.no_grad():
+        out = m(x, rel, self_padding_mask=mask)
+        outp = m(xp, relp, self_padding_mask=maskp)
+        attn = m.get_attn_weights(x, rel, self_padding_mask=mask)          # [L, tgt, src, B, H]
+    valid = ~mask                                                           # [N,B]
+    assert rel_err(outp[:N][valid], out[valid]) < 1e-5
+    assert torch.allclose(attn.sum(2), torch.ones_like(attn.sum(2)), atol=1e-5)
+    assert attn.permute(0, 1, 4, 2, 3)[:, :, :, mask].abs().max().item() == 0.0
+
+
+def test_one_graph_of_the_full_batch_vs_oracle(setup):
+    """graph b of the B=64 batch == the oracle run on that graph alone (batch independence makes this a full-size check)"""
+    s = setup
+    g, dev, m = s["g"], s["dev"], s["model"]
+    m.load_state_dict(s["model_cpu"].state_dict())
+    x, mask = g["x"].to(dev), g["node_mask"].to(dev)
+    rel, idx = _dense(s)
+    with torch.no_grad():
+        out = m(x, rel, self_padding_mask=mask)
+    P = {k: v.clone() for k, v in s["model_cpu"].state_dict().items()}
+    for b in (0, 37):
+        relb = s["bank"].index_select(0, idx[:, :, b].reshape(-1)).view(s["N"], s["N"], 1, -1)
+        with torch.no_grad():
+            ref = O.graph_transformer(P, "", g["x"][:, b:b + 1], relb, 4, 8, self_padding_mask=g["node_mask"][:, b:b + 1])
+        assert rel_err(out[:, b:b + 1], ref) < 1e-2

@@ -245,3 +245,19 @@ def test_dropout_statistics(dev):
     assert abs(y.max().item() - 1.25) < 1e-6
     y3 = ops.dropout_f32(x, 0.2, seed, ops.new_seed_off())
     assert not torch.equal(y, y3)
+
+
+def test_bank_gather_and_scatter(dev):
+    from gtos_b200 import ops
+    R, D, N, B = 300, 128, 9, 4
+    bank = torch.randn(R, D, device=dev, requires_grad=True)
+    idx = torch.randint(0, R, (N, N, B), device=dev)
+    idx[0, :, :] = 2                                     # a heavily repeated row (contended reductions)
+    rel = ops.bank_gather(bank, idx)
+    ref = bank.index_select(0, idx.reshape(-1)).view(N, N, B, D)
+    assert torch.equal(rel, ref)
+    assert torch.equal(rel._gtos_bf16, ref.to(torch.bfloat16))
+    w = torch.randn_like(ref)
+    (g,) = torch.autograd.grad((rel * w).sum(), bank)
+    (gr,) = torch.autograd.grad((ref * w).sum(), bank)
+    assert rel_err(g, gr) < 1e-5

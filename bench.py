@@ -410,6 +410,50 @@ def breakdown(args, w, cfg, model, static, meta, dev, lib):
                            "algorithmic_tflops": enc_flops / (ms_enc * 1e-3) / 1e12,
                            "note": "GraphTransformer (%d layers) fwd+bwd on the dense relation tensor" % L}
 
+    def graphed(fn):
+        s2 = torch.cuda.Stream()
+        with torch.cuda.stream(s2):
+            for _ in range(2):
+                fn()
+            s2.synchronize()
+            gg = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gg, stream=s2):
+                fn()
+        torch.cuda.synchronize()
+        return gg
+
+    # relation encoder only (RelationEncoder fwd+bwd over the batch's distinct paths)
+    def relenc_step():
+        for prm in model.relation_encoder.parameters():
+            prm.grad = None
+        bk = model.relation_encoder(static["relation_bank"], static["relation_length"])
+        bk.backward(bk)
+
+    ms_re = time_fn(graphed(relenc_step).replay)
+    out["relation_encoder_only"] = {"ms_per_step": ms_re, "paths_per_sec": meta["R"] / (ms_re * 1e-3),
+                                    "note": "2-layer bi-GRU bank encoder fwd+bwd, %d distinct paths" % meta["R"]}
+
+    # decoder only: snt Transformer + DecodeLayer fwd+bwd on fixed graph states
+    with torch.no_grad():
+        cr, cm, pr = model.encode(static)
+    cr = cr.detach().clone().requires_grad_()
+    pr = pr.detach().clone().requires_grad_()
+    dec_params = list(model.snt_encoder.parameters()) + list(model.decoder.parameters())
+
+    def dec_step():
+        for prm in dec_params:
+            prm.grad = None
+        cr.grad = pr.grad = None
+        tok = model.snt_encoder(static["token_repr"], self_padding_mask=static["token_mask"],
+                                self_attn_mask=static["causal_mask"], external_memories=cr, external_padding_mask=cm)
+        loss = model.decoder(pr.expand_as(tok), cr, tok, cm, static["token_mask"], static["causal_mask"],
+                             static["copy_seq"], target=static["target"])
+        loss.backward()
+
+    ms_dec = time_fn(graphed(dec_step).replay)
+    out["decoder_only"] = {"ms_per_step": ms_dec, "tokens_per_sec": meta["tokens"] / (ms_dec * 1e-3),
+                           "note": "snt Transformer (1 layer) + DecodeLayer (3 layers + TokenGenerator) fwd+bwd"}
+
     # dominant kernel alone: gtos_rel_score (relation projection + score epilogue), one layer's launch
     relb = ops.relation_to_bf16(rel.detach())
     Wr = model.graph_encoder.layers[0].self_attn.relation_in_proj.weight
@@ -439,7 +483,7 @@ def breakdown(args, w, cfg, model, static, meta, dev, lib):
     ds = torch.randn(B, H, N, N, device=dev)
     drel = torch.empty(N, N, B, D, device=dev)
     ws_n = lib.gtos_rel_dw_workspace(N, B, D, H)
-    ws = torch.empty(ws_n, device=dev)
+    ws = torch.empty(max(ws_n, 1), device=dev)
     dW = torch.empty(2 * D, D, device=dev)
     t_grad = time_fn(lambda: _lib.check(lib.gtos_rel_grad(relb.data_ptr(), Wperm.data_ptr(), qkv.data_ptr(),
                                                           qkv.data_ptr() + 2 * D, 2 * D, ds.data_ptr(), G.data_ptr(), N, B,

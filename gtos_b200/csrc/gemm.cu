@@ -778,7 +778,9 @@ struct NnDev {
   int M, N, Kd;
   int m_tiles, n_tiles, k_blocks, splits, kb_per_split;
   int stages;
-  float* ws;  // [splits][M][N]
+  float* out;  // [M][N] fp32, zero-initialised: every split reduces into it with vector atomics
+  long ldo;
+  int perm_D, perm_hd;  // rel: accumulator row m is permuted row -> reference row order
   RelTiling rt;
 };
 
@@ -888,28 +890,28 @@ gemm_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     const uint32_t tacc = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const long m = (long)m_blk * BM + r;
-    float* wrow = p.ws + ((long)split * p.M + m) * p.N + (long)n_blk * BN;
+    const long mo = (p.perm_D && m < p.M) ? rel_perm_to_orig((int)m, p.perm_D, p.perm_hd) : m;
+    float* orow = p.out + mo * p.ldo + (long)n_blk * BN;
+    if (any) {
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 16) {
-      if (n_blk * BN + c >= p.N) break;
-      float v[16];
-      if (any) {
+      for (int c = 0; c < BN; c += 16) {
+        if (n_blk * BN + c >= p.N) break;
+        float v[16];
         tmem_ld16(tacc + c, v);
         tmem_ld_wait();
-      } else {
+        if (m < p.M) {
+          const int n = n_blk * BN + c;
+          if (n + 16 <= p.N && ((reinterpret_cast<uintptr_t>(orow + c) & 15) == 0)) {
 #pragma unroll
-        for (int t = 0; t < 16; ++t) v[t] = 0.f;
-      }
-      if (m < p.M) {
-        const int n = n_blk * BN + c;
-        if (n + 16 <= p.N && ((reinterpret_cast<uintptr_t>(wrow + c) & 15) == 0)) {
+            for (int t = 0; t < 4; ++t)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(orow + c + 4 * t), "f"(v[4 * t]),
+                           "f"(v[4 * t + 1]), "f"(v[4 * t + 2]), "f"(v[4 * t + 3])
+                           : "memory");
+          } else {
 #pragma unroll
-          for (int t = 0; t < 4; ++t)
-            *reinterpret_cast<float4*>(wrow + c + 4 * t) = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
-        } else {
-#pragma unroll
-          for (int t = 0; t < 16; ++t)
-            if (n + t < p.N) wrow[c + t] = v[t];
+            for (int t = 0; t < 16; ++t)
+              if (n + t < p.N) atomicAdd(orow + c + t, v[t]);
+          }
         }
       }
     }
@@ -921,18 +923,6 @@ gemm_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
-}
-
-__global__ void splitk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ out, long ldo, int M, int N,
-                                     int splits, int rel_D, int rel_hd) {
-  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  long total = (long)M * N;
-  if (idx >= total) return;
-  int m = (int)(idx / N), n = (int)(idx % N);
-  float s = 0.f;
-  for (int k = 0; k < splits; ++k) s += ws[(long)k * total + idx];
-  int mo = rel_D ? rel_perm_to_orig(m, rel_D, rel_hd) : m;
-  out[(long)mo * ldo + n] = s;
 }
 
 static void nn_plan(int M, int N, int Kd, int rel, int* BN, int* KB, int* splits, int* kb_per) {
@@ -951,9 +941,8 @@ static void nn_plan(int M, int N, int Kd, int rel, int* BN, int* KB, int* splits
 }
 
 long gemm_nn_workspace_elems(int M, int N, int Kd, int rel) {
-  int BN, KB, splits, per;
-  nn_plan(M, N, Kd, rel, &BN, &KB, &splits, &per);
-  return (long)splits * M * N;
+  (void)M; (void)N; (void)Kd; (void)rel;
+  return 0;  // split-K now reduces in place (vector atomics); kept in the ABI for callers that size a workspace
 }
 
 template <int BN, int KB, int REL>
@@ -965,7 +954,8 @@ static int launch_nn(const GemmNnArgs& a, int splits, int per, cudaStream_t stre
   p.n_tiles = (a.N + BN - 1) / BN;
   p.k_blocks = (a.Kd + KB - 1) / KB;
   p.splits = splits; p.kb_per_split = per;
-  p.ws = a.workspace; p.rt = a.rt;
+  p.out = a.out; p.ldo = a.ldo; p.rt = a.rt;
+  p.perm_D = a.rel ? a.rt.D : 0; p.perm_hd = a.rel ? a.rt.hd : 0;
   CUtensorMap tmA, tmB;
   int e;
   {
@@ -999,13 +989,13 @@ static int launch_nn(const GemmNnArgs& a, int splits, int per, cudaStream_t stre
   const int smem_bytes = 1024 + stages * STAGE_BYTES + (int)sizeof(PipeBars);
   auto kern = gemm_nn_kernel<BN, KB, REL>;
   GTOS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  // the split-K partial sums are reduced straight into the (zeroed) output with 16-byte vector atomics
+  if (a.ldo == a.N)
+    GTOS_CHECK_CUDA(cudaMemsetAsync(a.out, 0, sizeof(float) * (size_t)a.M * a.N, stream));
+  else
+    GTOS_CHECK_CUDA(cudaMemset2DAsync(a.out, sizeof(float) * a.ldo, 0, sizeof(float) * a.N, a.M, stream));
   dim3 grid(p.m_tiles * p.n_tiles, splits);
   kern<<<grid, GEMM_THREADS, smem_bytes, stream>>>(tmA, tmB, p);
-  GTOS_LAUNCH_CHECK();
-  long total = (long)a.M * a.N;
-  int thr = 256;
-  splitk_reduce_kernel<<<(unsigned)((total + thr - 1) / thr), thr, 0, stream>>>(
-      a.workspace, a.out, a.ldo, a.M, a.N, splits, a.rel ? a.rt.D : 0, a.rel ? a.rt.hd : 0);
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
 }
@@ -1014,7 +1004,6 @@ int launch_gemm_nn(const GemmNnArgs& a, cudaStream_t stream) {
   GTOS_REQUIRE(a.lda % 8 == 0 && (a.rel || a.ldb % 8 == 0), "gemm_nn: lda/ldb must be multiples of 8");
   int BN, KB, splits, per;
   nn_plan(a.M, a.N, a.Kd, a.rel, &BN, &KB, &splits, &per);
-  GTOS_REQUIRE(a.workspace_elems >= (long)splits * a.M * a.N, "gemm_nn: workspace too small");
   if (a.rel) {
     if (BN == 256) return launch_nn<256, 128, 1>(a, splits, per, stream);
     return launch_nn<128, 128, 1>(a, splits, per, stream);

@@ -119,7 +119,7 @@ def gemm_nn(A, B, M, N, out=None, a_off=0, b_off=0):
     Kd = A.shape[0]
     lib = _lib.load()
     ws_elems = lib.gtos_gemm_nn_workspace(M, N, Kd)
-    ws = torch.empty(max(ws_elems, 1), dtype=torch.float32, device=A.device)
+    ws = None
     if out is None:
         out = torch.empty(M, N, dtype=torch.float32, device=A.device)
     _lib.check(lib.gtos_gemm_nn(A.data_ptr() + 2 * a_off, A.stride(0), B.data_ptr() + 2 * b_off, B.stride(0), _p(out),
@@ -343,7 +343,7 @@ class RelAttnFn(torch.autograd.Function):
             d_rel = torch.empty(N, N, B, D, dtype=torch.float32, device=dev)
             _lib.check(lib.gtos_rel_drel(_p(G), _p(WpermT), _p(d_rel), 0, N, B, D, H, _st()), "rel_drel")
         ws_elems = lib.gtos_rel_dw_workspace(N, B, D, H)
-        ws = torch.empty(ws_elems, dtype=torch.float32, device=dev)
+        ws = None
         dW_rel = torch.empty(2 * D, D, dtype=torch.float32, device=dev)
         _lib.check(lib.gtos_rel_dw(_p(G), _p(relb), _p(dW_rel), _p(ws), ws_elems, N, B, D, H, _st()), "rel_dw")
         dqkvb = cast_bf16(dqkv)

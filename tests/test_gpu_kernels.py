@@ -122,7 +122,7 @@ def test_rel_backward_pieces(dev, N, B, D, H):
     drel = torch.full((N, N, B, D), float("nan"), device=dev)
     _lib.check(lib.gtos_rel_drel(G.data_ptr(), WpermT.data_ptr(), drel.data_ptr(), 0, N, B, D, H, st), "drel")
     ws_n = lib.gtos_rel_dw_workspace(N, B, D, H)
-    ws = torch.empty(ws_n, device=dev)
+    ws = torch.empty(max(ws_n, 1), device=dev)
     dW = torch.full((2 * D, D), float("nan"), device=dev)
     _lib.check(lib.gtos_rel_dw(G.data_ptr(), relb.data_ptr(), dW.data_ptr(), ws.data_ptr(), ws_n, N, B, D, H, st), "dw")
     torch.cuda.synchronize()

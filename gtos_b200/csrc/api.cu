@@ -19,6 +19,7 @@ void set_error(const char* fmt, ...) {
 
 using namespace gtos;
 static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline cudaStream_t S_(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 extern "C" {
 
@@ -210,6 +211,20 @@ int gtos_dropout_f32(const float* x, float* out, int64_t n, float p, const void*
 int gtos_relu_drop_bwd(const float* dh_in, const void* act_bf16, float* dh_f32, void* dh_bf16, int64_t n, float p,
                        void* stream) {
   return relu_drop_bwd(dh_in, act_bf16, dh_f32, dh_bf16, n, p, S(stream));
+}
+int gtos_token_nll_fwd(const float* logits, int64_t ldl, int32_t V, const float* gate_logits, const float* align,
+                       int32_t S, const int64_t* copy_seq, const int64_t* target, int64_t rows, int32_t B, int64_t pad_idx,
+                       float* loss_row, float* stats, void* stream) {
+  return token_nll_fwd(logits, ldl, V, gate_logits, align, S, reinterpret_cast<const long long*>(copy_seq),
+                       reinterpret_cast<const long long*>(target), rows, B, pad_idx, loss_row, stats, S_(stream));
+}
+int gtos_token_nll_bwd(const float* dloss_row, const float* logits, int64_t ldl, int32_t V, const float* align, int32_t S,
+                       const int64_t* copy_seq, const int64_t* target, int64_t rows, int32_t B, int64_t pad_idx,
+                       const float* stats, float* dlogits, int64_t lddl, float* dgate_logits, float* dalign,
+                       void* stream) {
+  return token_nll_bwd(dloss_row, logits, ldl, V, align, S, reinterpret_cast<const long long*>(copy_seq),
+                       reinterpret_cast<const long long*>(target), rows, B, pad_idx, stats, dlogits, lddl, dgate_logits,
+                       dalign, S_(stream));
 }
 int gtos_bank_gather(const float* bank, const int64_t* idx, int64_t P, int32_t D, float* out_f32, void* out_bf16,
                      void* stream) {

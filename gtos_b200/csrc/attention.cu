@@ -46,6 +46,21 @@ __device__ __forceinline__ AttnSmem carve(float* base, int L, int dc, int AT_ROW
 __device__ __forceinline__ void load_rows(float* dst, int dstr, const float* src, long ld, int B, int b, int hoff,
                                           int r0, int nr, int len, int c0, int dc) {
   const int dc4 = r4(dc);
+  const bool vec = ((dc & 3) == 0) && ((ld & 3) == 0) && (((hoff + c0) & 3) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  if (vec) {
+    // 16-byte loads, all of a thread's loads in flight before the first store (latency-bound otherwise)
+    const int q = dc4 >> 2, total = nr * q;
+#pragma unroll 4
+    for (int idx = threadIdx.x; idx < total; idx += AT_THREADS) {
+      const int r = idx / q, d4 = idx - r * q;
+      const int t = r0 + r;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t < len) v = *reinterpret_cast<const float4*>(src + ((long)t * B + b) * ld + hoff + c0 + 4 * d4);
+      *reinterpret_cast<float4*>(dst + r * dstr + 4 * d4) = v;
+    }
+    return;
+  }
   for (int idx = threadIdx.x; idx < nr * dc4; idx += AT_THREADS) {
     int r = idx / dc4, d = idx - r * dc4;
     int t = r0 + r;
@@ -129,6 +144,17 @@ __device__ __forceinline__ bool is_masked(const AttnArgs& a, int b, int t, int j
   return false;
 }
 
+// -inf the masked entries of the score block in one cooperative, coalesced pass (instead of dependent byte loads
+// inside every softmax row loop)
+__device__ __forceinline__ void apply_masks(const AttnArgs& a, const AttnSmem& s, int b, int t0, int nrows, float sscale) {
+  const int S = a.S;
+  for (int idx = threadIdx.x; idx < nrows * S; idx += AT_THREADS) {
+    const int r = idx / S, j = idx - r * S;
+    float* p = s.sc + (size_t)r * s.lstr + j;
+    *p = is_masked(a, b, t0 + r, j) ? -INFINITY : *p * sscale;
+  }
+}
+
 __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnArgs a, const int rows_per_cta) {
   extern __shared__ float smem_f[];
   const int dc = a.hd < AT_DC ? a.hd : AT_DC;
@@ -164,15 +190,13 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnArgs a, 
   const unsigned long long seed = a.p_drop > 0.f ? reinterpret_cast<const unsigned long long*>(a.seed_ptr)[0] + a.seed_off : 0ull;
   const float ks = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
   const float sscale = a.scores_jt ? 1.f : a.scale;
+  apply_masks(a, s, b, t0, nrows, sscale);
+  __syncthreads();
   for (int r = warp; r < nrows; r += AT_WARPS) {
     const int t = t0 + r;
     float* w = s.sc + (size_t)r * s.lstr;
     float mx = -INFINITY;
-    for (int j = lane; j < S; j += 32) {
-      float v = is_masked(a, b, t, j) ? -INFINITY : w[j] * sscale;
-      w[j] = v;
-      mx = fmaxf(mx, v);
-    }
+    for (int j = lane; j < S; j += 32) mx = fmaxf(mx, w[j]);
     mx = warp_max(mx);
     float sum = 0.f;
     for (int j = lane; j < S; j += 32) {

@@ -369,6 +369,106 @@ int relu_drop_bwd(const float* dh_in, const void* act, float* dh_f32, void* dh_b
 // of the fused QKV projection (dq at column 0, dk at column D).
 // ---------------------------------------------------------------------------------------
 // ---------------------------------------------------------------------------------------
+// TokenGenerator training tail (generator/decoder.py:42-64) in one pass over the vocabulary logits:
+//   p[target] = gen * softmax(logits)[target] + copy * sum_s align[s] * [copy_seq[s] == target]
+//   loss_row  = -log(p + 1e-12), 0 where target == pad
+// replaces softmax / zero-extension cat / scatter_add / log / gather and their autograd (8 passes over [T*B, V]).
+// One CTA per (t, b) row.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_reduce(float v, float* sh, bool is_max) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = is_max ? warp_max(v) : warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  float r = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : (is_max ? -INFINITY : 0.f);
+  r = is_max ? warp_max(r) : warp_sum(r);
+  return __shfl_sync(0xffffffffu, r, 0);
+}
+
+__global__ void token_nll_fwd_kernel(const float* __restrict__ logits, long ldl, int V, const float* __restrict__ gate_logits,
+                                     const float* __restrict__ align, int S, const long long* __restrict__ copy_seq,
+                                     const long long* __restrict__ target, int B, long long pad_idx,
+                                     float* __restrict__ loss_row, float* __restrict__ stats) {
+  __shared__ float sh[32];
+  const long row = blockIdx.x;
+  const int b = (int)(row % B);
+  const float* lr = logits + row * ldl;
+  float mx = -INFINITY;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) mx = fmaxf(mx, lr[v]);
+  mx = block_reduce(mx, sh, true);
+  float se = 0.f;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) se += __expf(lr[v] - mx);
+  se = block_reduce(se, sh, false);
+  const long long tgt = target[row];
+  float cp = 0.f;
+  for (int s = threadIdx.x; s < S; s += blockDim.x)
+    if (copy_seq[(long)s * B + b] == tgt) cp += align[row * S + s];
+  cp = block_reduce(cp, sh, false);
+  if (threadIdx.x == 0) {
+    const float g0 = gate_logits[row * 2], g1 = gate_logits[row * 2 + 1];
+    const float gm = fmaxf(g0, g1);
+    const float e0 = __expf(g0 - gm), e1 = __expf(g1 - gm);
+    const float gen = e0 / (e0 + e1), cpy = e1 / (e0 + e1);
+    const float sm_t = (tgt >= 0 && tgt < V) ? __expf(lr[tgt] - mx) / se : 0.f;
+    const float p = gen * sm_t + cpy * cp;
+    loss_row[row] = (tgt == pad_idx) ? 0.f : -logf(p + 1e-12f);
+    stats[row * 6 + 0] = mx; stats[row * 6 + 1] = se; stats[row * 6 + 2] = gen; stats[row * 6 + 3] = cpy;
+    stats[row * 6 + 4] = sm_t; stats[row * 6 + 5] = cp;
+  }
+}
+
+__global__ void token_nll_bwd_kernel(const float* __restrict__ dloss_row, const float* __restrict__ logits, long ldl, int V,
+                                     const float* __restrict__ align, int S, const long long* __restrict__ copy_seq,
+                                     const long long* __restrict__ target, int B, long long pad_idx,
+                                     const float* __restrict__ stats, float* __restrict__ dlogits, long lddl,
+                                     float* __restrict__ dgate_logits, float* __restrict__ dalign) {
+  const long row = blockIdx.x;
+  const int b = (int)(row % B);
+  const long long tgt = target[row];
+  const float mx = stats[row * 6], se = stats[row * 6 + 1], gen = stats[row * 6 + 2], cpy = stats[row * 6 + 3];
+  const float sm_t = stats[row * 6 + 4], cp = stats[row * 6 + 5];
+  const float p = gen * sm_t + cpy * cp;
+  const float dp = (tgt == pad_idx) ? 0.f : -dloss_row[row] / (p + 1e-12f);   // dL/dp
+  const float* lr = logits + row * ldl;
+  float* dl = dlogits + row * lddl;
+  const float coef = dp * gen;
+  const float inv = 1.f / se;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    const float sm = __expf(lr[v] - mx) * inv;
+    dl[v] = coef * sm * ((v == tgt ? 1.f : 0.f) - sm_t);
+  }
+  for (int s = threadIdx.x; s < S; s += blockDim.x)
+    dalign[row * S + s] = (copy_seq[(long)s * B + b] == tgt) ? dp * cpy : 0.f;
+  if (threadIdx.x == 0) {
+    const float dgen = dp * sm_t, dcpy = dp * cp;
+    const float dot = gen * dgen + cpy * dcpy;
+    dgate_logits[row * 2] = gen * (dgen - dot);
+    dgate_logits[row * 2 + 1] = cpy * (dcpy - dot);
+  }
+}
+
+int token_nll_fwd(const float* logits, long ldl, int V, const float* gate_logits, const float* align, int S,
+                  const long long* copy_seq, const long long* target, long rows, int B, long long pad_idx,
+                  float* loss_row, float* stats, cudaStream_t st) {
+  if (rows == 0) return GTOS_OK;
+  token_nll_fwd_kernel<<<(unsigned)rows, 256, 0, st>>>(logits, ldl, V, gate_logits, align, S, copy_seq, target, B, pad_idx,
+                                                       loss_row, stats);
+  GTOS_LAUNCH_CHECK();
+  return GTOS_OK;
+}
+
+int token_nll_bwd(const float* dloss_row, const float* logits, long ldl, int V, const float* align, int S,
+                  const long long* copy_seq, const long long* target, long rows, int B, long long pad_idx,
+                  const float* stats, float* dlogits, long lddl, float* dgate_logits, float* dalign, cudaStream_t st) {
+  if (rows == 0) return GTOS_OK;
+  token_nll_bwd_kernel<<<(unsigned)rows, 256, 0, st>>>(dloss_row, logits, ldl, V, align, S, copy_seq, target, B, pad_idx,
+                                                       stats, dlogits, lddl, dgate_logits, dalign);
+  GTOS_LAUNCH_CHECK();
+  return GTOS_OK;
+}
+
+// ---------------------------------------------------------------------------------------
 // bank -> dense relation gather (generator/generator.py:79) and its backward scatter-add.
 // forward writes the fp32 tensor the caller's contract needs AND the bf16 copy the tensor-core kernels read.
 // ---------------------------------------------------------------------------------------

@@ -20,6 +20,12 @@ int dropout_bf16(void* h, long n, float p, const void* seed_ptr, unsigned long l
 int dropout_f32(const float* x, float* out, long n, float p, const void* seed_ptr, unsigned long long seed_off,
                 cudaStream_t st);
 int relu_drop_bwd(const float* dh_in, const void* act, float* dh_f32, void* dh_bf16, long n, float p, cudaStream_t st);
+int token_nll_fwd(const float* logits, long ldl, int V, const float* gate_logits, const float* align, int S,
+                  const long long* copy_seq, const long long* target, long rows, int B, long long pad_idx,
+                  float* loss_row, float* stats, cudaStream_t st);
+int token_nll_bwd(const float* dloss_row, const float* logits, long ldl, int V, const float* align, int S,
+                  const long long* copy_seq, const long long* target, long rows, int B, long long pad_idx,
+                  const float* stats, float* dlogits, long lddl, float* dgate_logits, float* dalign, cudaStream_t st);
 int bank_gather(const float* bank, const long long* idx, long P, int D, float* out_f32, void* out_bf16, cudaStream_t st);
 int bank_scatter_add(const float* d_rel, const long long* idx, long P, int D, float* d_bank, long R, cudaStream_t st);
 int rel_dqk(const void* G, const RelTiling& rt, float* dq, float* dk, long ld, cudaStream_t st);

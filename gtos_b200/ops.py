@@ -675,3 +675,45 @@ def bank_gather(bank, idx):
     rel, relb = BankGatherFn.apply(bank, idx)
     rel._gtos_bf16 = relb
     return rel
+
+
+# --------------------------------------------------------------------------------------------
+# TokenGenerator training tail (decoder.py:42-64): fused copy/generate NLL over the vocabulary logits
+# --------------------------------------------------------------------------------------------
+class TokenNLLFn(torch.autograd.Function):
+    """logits [T,B,V], gate_logits [T,B,2], align [T,B,S] fp32; copy_seq [S,B], target [T,B] int64 -> loss [T,B]."""
+
+    @staticmethod
+    def forward(ctx, logits, gate_logits, align, copy_seq, target, pad_idx):
+        _need_cuda(logits, gate_logits, align)
+        T, B, V = logits.shape
+        S = align.shape[-1]
+        logits, gate_logits, align = logits.contiguous(), gate_logits.contiguous(), align.contiguous()
+        copy_seq, target = copy_seq.contiguous(), target.contiguous()
+        rows = T * B
+        loss = torch.empty(T, B, dtype=torch.float32, device=logits.device)
+        stats = torch.empty(rows, 6, dtype=torch.float32, device=logits.device)
+        _lib.check(_lib.load().gtos_token_nll_fwd(_p(logits), V, V, _p(gate_logits), _p(align), S, _p(copy_seq), _p(target),
+                                                  rows, B, int(pad_idx), _p(loss), _p(stats), _st()), "token_nll_fwd")
+        ctx.save_for_backward(logits, align, copy_seq, target, stats)
+        ctx.meta = (T, B, V, S, int(pad_idx))
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dloss):
+        logits, align, copy_seq, target, stats = ctx.saved_tensors
+        T, B, V, S, pad_idx = ctx.meta
+        dev = dloss.device
+        dloss = dloss.contiguous()
+        dlogits = torch.empty(T, B, V, dtype=torch.float32, device=dev)
+        dgate = torch.empty(T, B, 2, dtype=torch.float32, device=dev)
+        dalign = torch.empty(T, B, S, dtype=torch.float32, device=dev)
+        _lib.check(_lib.load().gtos_token_nll_bwd(_p(dloss), _p(logits), V, V, _p(align), S, _p(copy_seq), _p(target), T * B,
+                                                  B, pad_idx, _p(stats), _p(dlogits), V, _p(dgate), _p(dalign), _st()),
+                   "token_nll_bwd")
+        return dlogits, dgate, dalign, None, None, None
+
+
+def token_nll(logits, gate_logits, align, copy_seq, target, pad_idx):
+    return TokenNLLFn.apply(logits, gate_logits, align, copy_seq, target, pad_idx)

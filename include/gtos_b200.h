@@ -124,6 +124,19 @@ int gtos_dropout_f32(const float* x, float* out, int64_t n, float p, const void*
 int gtos_relu_drop_bwd(const float* dh_in, const void* act_bf16, float* dh_f32, void* dh_bf16, int64_t n, float p,
                        void* stream);
 
+/* ---- TokenGenerator training tail (decoder.py:42-64): copy/generate mixture NLL of the target token in ONE pass over
+ * the vocabulary logits [rows = T*B, V] (row = t*B + b):
+ *   p = softmax(gate_logits)[0] * softmax(logits)[target] + softmax(gate_logits)[1] * sum_s align[row,s] * [copy_seq[s,b] == target]
+ *   loss_row = -log(p + 1e-12), 0 where target == pad_idx;   stats: 6 floats per row kept for backward.
+ * backward writes dlogits [rows, V], dgate_logits [rows, 2], dalign [rows, S]. */
+int gtos_token_nll_fwd(const float* logits, int64_t ldl, int32_t V, const float* gate_logits, const float* align,
+                       int32_t S, const int64_t* copy_seq, const int64_t* target, int64_t rows, int32_t B, int64_t pad_idx,
+                       float* loss_row, float* stats, void* stream);
+int gtos_token_nll_bwd(const float* dloss_row, const float* logits, int64_t ldl, int32_t V, const float* align, int32_t S,
+                       const int64_t* copy_seq, const int64_t* target, int64_t rows, int32_t B, int64_t pad_idx,
+                       const float* stats, float* dlogits, int64_t lddl, float* dgate_logits, float* dalign,
+                       void* stream);
+
 /* ---- bank -> dense relation gather (generator.py:79: relation = bank.index_select(0, idx)) and its backward ----
  * forward emits the fp32 [P,D] tensor of the caller's contract and (optionally) the bf16 copy the fused kernels read;
  * backward zero-fills d_bank [R,D] and scatter-adds the dense gradient with 16-byte vector reductions. */

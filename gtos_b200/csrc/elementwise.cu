@@ -381,9 +381,10 @@ __device__ __forceinline__ float block_reduce(float v, float* sh, bool is_max) {
   __syncthreads();
   if (lane == 0) sh[w] = v;
   __syncthreads();
-  float r = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : (is_max ? -INFINITY : 0.f);
+  const int nw = blockDim.x >> 5;
+  float r = (lane < nw) ? sh[lane] : (is_max ? -INFINITY : 0.f);   // every warp reduces the per-warp partials itself
   r = is_max ? warp_max(r) : warp_sum(r);
-  return __shfl_sync(0xffffffffu, r, 0);
+  return r;
 }
 
 __global__ void token_nll_fwd_kernel(const float* __restrict__ logits, long ldl, int V, const float* __restrict__ gate_logits,

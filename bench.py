@@ -469,10 +469,15 @@ def breakdown(args, w, cfg, model, static, meta, dev, lib):
     ms_k = time_fn(k_score, steps=20, warmup=3)
     kflops = meta["pairs"] * (4 * D * D + 2 * D)
     pk = peaks()
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tp) and args.workload == "cfg2":
+        tj = json.load(open(tp))
+        traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
     ach = kflops / (ms_k * 1e-3) / 1e12
     out["roofline"] = {"kernel": "gemm_tn_kernel<256, MODE_SCORE> (gtos_rel_score: relation_in_proj GEMM + score epilogue)",
                        "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                       "frac": ach / pk["bf16_tflops"], "traffic": None, "ms_per_launch": ms_k,
+                       "frac": ach / pk["bf16_tflops"], "traffic": traffic, "ms_per_launch": ms_k,
                        "algorithmic_flops_per_launch": kflops,
                        "algorithmic_bytes_per_launch": meta["pairs"] * D * 2,
                        "peak_source": pk["source"] + ", burst bf16 cuBLAS (kernel timed alone)",

@@ -38,6 +38,7 @@ SIGNATURES = {
     "gtos_cast_bf16": (i32, [vp, i64, vp, i64, i64, i32, vp]),
     "gtos_weight_prep": (i32, [vp, i32, i32, vp, i64, vp, i64, i32, vp]),
     "gtos_gemm_tn": (i32, [vp, i64, vp, i64, vp, vp, i64, vp, i64, i32, i32, i32, i32, i32, vp]),
+    "gtos_gemm_tn_add": (i32, [vp, i64, vp, i64, vp, vp, i64, vp, i64, i32, i32, i32, vp]),
     "gtos_gemm_nn_workspace": (i64, [i32, i32, i32]),
     "gtos_gemm_nn": (i32, [vp, i64, vp, i64, vp, i64, i32, i32, i32, vp, i64, vp]),
     "gtos_rel_tiling": (i32, [i32, i32, i32, i32, C.POINTER(i32)]),
@@ -65,7 +66,7 @@ SIGNATURES = {
     "gtos_gru_weight_prep": (i32, [vp, vp, vp, vp, i32, i32, i32, vp, i64, vp, vp]),
     "gtos_gru_step_fwd": (i32, [vp, i64, i32, vp, i64, vp, vp, i64, i32, vp, vp, i32, vp, vp, i64, vp, i64, vp, i64, i64,
                                 i32, vp]),
-    "gtos_gru_gate_bwd": (i32, [vp, vp, i64, vp, vp, vp, i32, vp, vp, i64, vp, i64, i64, i32, vp]),
+    "gtos_gru_gate_bwd": (i32, [vp, vp, i64, vp, vp, vp, i32, vp, vp, i64, vp, i64, vp, vp, i64, i32, vp]),
 }
 
 _lib = None

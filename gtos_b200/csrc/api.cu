@@ -71,6 +71,16 @@ int gtos_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, const f
   return launch_gemm_tn(MODE_PLAIN, a, S(stream));
 }
 
+int gtos_gemm_tn_add(const void* A, int64_t lda, const void* B, int64_t ldb, const float* bias, const float* addend,
+                     int64_t ldadd, float* out_f32, int64_t ldo, int32_t M, int32_t N, int32_t K, void* stream) {
+  if (M == 0 || N == 0) return GTOS_OK;
+  GemmTnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.A = A; a.lda = lda; a.Bm = B; a.ldb = ldb; a.M = M; a.N = N; a.K = K;
+  a.bias = bias; a.addend = addend; a.ldadd = ldadd; a.out_f32 = out_f32; a.ldo = ldo;
+  return launch_gemm_tn(MODE_PLAIN, a, S(stream));
+}
+
 int64_t gtos_gemm_nn_workspace(int32_t M, int32_t N, int32_t Kd) { return gemm_nn_workspace_elems(M, N, Kd, 0); }
 
 int gtos_gemm_nn(const void* A, int64_t lda, const void* B, int64_t ldb, float* out, int64_t ldo, int32_t M, int32_t N,
@@ -260,9 +270,9 @@ int gtos_gru_step_fwd(const void* x, int64_t ldx, int32_t Kin, const void* hb, i
 }
 int gtos_gru_gate_bwd(const float* dh, const float* dout_t, int64_t lddout, const void* gates, const float* h_prev,
                       const int64_t* lengths, int32_t t, float* dh_prev, void* dgi_bf16, int64_t lddgi, void* dgh_bf16,
-                      int64_t lddgh, int64_t R, int32_t Hh, void* stream) {
+                      int64_t lddgh, float* db_ih, float* db_hh, int64_t R, int32_t Hh, void* stream) {
   return gru_gate_bwd(dh, dout_t, lddout, gates, h_prev, reinterpret_cast<const long long*>(lengths), t, dh_prev, dgi_bf16,
-                      lddgi, dgh_bf16, lddgh, R, Hh, S(stream));
+                      lddgi, dgh_bf16, lddgh, db_ih, db_hh, R, Hh, S(stream));
 }
 
 }  // extern "C"

@@ -68,7 +68,7 @@ int gru_weight_prep(const float* w_ih, const float* w_hh, const float* b_ih, con
                     void* Wcat, long ldw, float* bcat, cudaStream_t st);
 int gru_gate_bwd(const float* dh, const float* dout_t, long lddout, const void* gates, const float* h_prev,
                  const long long* lengths, int t, float* dh_prev, void* dgi_bf16, long lddgi, void* dgh_bf16,
-                 long lddgh, long R, int Hh, cudaStream_t st);
+                 long lddgh, float* db_ih, float* db_hh, long R, int Hh, cudaStream_t st);
 int embed_gather(const float* table, const long long* idx, long n, int dim, float* out_f32, void* out_bf16, long ldb,
                  float p_drop, const void* seed_ptr, unsigned long long seed_off, cudaStream_t st);
 int embed_scatter_add(const float* dx, const long long* idx, long n, int dim, float* dtable, float p_drop,

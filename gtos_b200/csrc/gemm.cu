@@ -57,6 +57,8 @@ struct TnDev {
   __nv_bfloat16* out_bf16;
   long ldob;
   int relu, accumulate;
+  const float* addend;
+  long ldadd;
   RelTiling rt;
   float* scores;
   const float* dscores;
@@ -352,6 +354,23 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int t = 0; t < 32; ++t)
                 if (n0 + c + t < p.N) v[t] += __ldg(p.bias + n0 + c + t);
             }
+            if (p.addend) {
+              const long arow = (long)m_blk * BM + r;
+              if (arow < p.M) {
+                const float* ap = p.addend + arow * p.ldadd + n0 + c;
+                if (n0 + c + 32 <= p.N && ((reinterpret_cast<uintptr_t>(ap) & 15) == 0)) {
+#pragma unroll
+                  for (int t4 = 0; t4 < 8; ++t4) {
+                    const float4 a4 = *reinterpret_cast<const float4*>(ap + 4 * t4);
+                    v[4 * t4] += a4.x; v[4 * t4 + 1] += a4.y; v[4 * t4 + 2] += a4.z; v[4 * t4 + 3] += a4.w;
+                  }
+                } else {
+#pragma unroll
+                  for (int t = 0; t < 32; ++t)
+                    if (n0 + c + t < p.N) v[t] += ap[t];
+                }
+              }
+            }
             if (p.relu) {
 #pragma unroll
               for (int t = 0; t < 32; ++t) v[t] = fmaxf(v[t], 0.f);
@@ -626,7 +645,7 @@ static int launch_tn(const GemmTnArgs& a, cudaStream_t stream) {
   p.k_blocks = (a.K + BK - 1) / BK;
   p.bias = a.bias; p.out_f32 = a.out_f32; p.ldo = a.ldo;
   p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a.out_bf16); p.ldob = a.ldob;
-  p.relu = a.relu; p.accumulate = a.accumulate;
+  p.relu = a.relu; p.accumulate = a.accumulate; p.addend = a.addend; p.ldadd = a.ldadd;
   p.rt = a.rt; p.scores = a.scores; p.dscores = a.dscores; p.G = reinterpret_cast<__nv_bfloat16*>(a.G);
   CUtensorMap tmA, tmB, tmQ, tmK;
   int e;
@@ -701,6 +720,8 @@ static int launch_tn(const GemmTnArgs& a, cudaStream_t stream) {
 int launch_gemm_tn(int mode, const GemmTnArgs& a, cudaStream_t stream) {
   GTOS_REQUIRE(a.K % 8 == 0 && a.lda % 8 == 0 && a.ldb % 8 == 0, "gemm_tn: K, lda, ldb must be multiples of 8 (K=%d lda=%ld ldb=%ld)",
                a.K, a.lda, a.ldb);
+  GTOS_REQUIRE(!a.addend || (mode == MODE_PLAIN && a.out_f32 && !a.out_bf16 && !a.accumulate && a.ldo % 4 == 0),
+               "gemm_tn: addend needs the fp32 TMA-store epilogue");
   if (mode == MODE_SCORE) return launch_tn<256, MODE_SCORE>(a, stream);
   if (mode == MODE_GRAD) return launch_tn<256, MODE_GRAD>(a, stream);
   if (mode == MODE_DREL) return launch_tn<256, MODE_DREL>(a, stream);

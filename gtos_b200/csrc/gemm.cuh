@@ -40,6 +40,8 @@ struct GemmTnArgs {
   long ldob;
   int relu;
   int accumulate;      // out_f32 += result
+  const float* addend; // optional fp32 [M,N] (ldadd) added in the epilogue: out = A*B^T + bias + addend
+  long ldadd;
   // relation modes
   RelTiling rt;
   const void* q;       // bf16 [N,B,D] (bias included, unscaled), row stride ldqk elements

@@ -54,17 +54,24 @@ __global__ void gru_gate_bwd_kernel(const float* __restrict__ dh, const float* _
                                     const __nv_bfloat16* __restrict__ gates, const float* __restrict__ h_prev,
                                     const long long* __restrict__ lengths, int t, float* __restrict__ dh_prev,
                                     __nv_bfloat16* __restrict__ dgi, long lddgi, __nv_bfloat16* __restrict__ dgh,
-                                    long lddgh, long R, int Hh, int UB) {
-  const long total = R * Hh;
-  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const long r = idx / Hh;
-    const int c = (int)(idx % Hh);
+                                    long lddgh, float* __restrict__ db_ih, float* __restrict__ db_hh, long R, int Hh,
+                                    int UB, int rows_per_block) {
+  // thread = hidden unit c (coalesced across c), loop over this block's rows; the bias gradients (column sums of the
+  // gate gradients) are accumulated in registers and flushed with one atomic per (block, column)
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Hh) return;
+  const long r0 = (long)blockIdx.y * rows_per_block;
+  const long r1 = r0 + rows_per_block < R ? r0 + rows_per_block : R;
+  float s_r = 0.f, s_z = 0.f, s_n = 0.f, s_h = 0.f;
+  const int goff = (c / UB) * 4 * UB + (c % UB);
+  for (long r = r0; r < r1; ++r) {
+    const long idx = r * Hh + c;
     const bool live = lengths[r] > t;
     float d = dh ? dh[idx] : 0.f;
     float dar = 0.f, daz = 0.f, dan = 0.f, dhn = 0.f, dprev = d;
     if (live) {
       if (dout_t) d += dout_t[r * lddout + c];
-      const __nv_bfloat16* gp = gates + r * 4L * Hh + (c / UB) * 4 * UB + (c % UB);
+      const __nv_bfloat16* gp = gates + r * 4L * Hh + goff;
       const float gr = __bfloat162float(gp[0]), gz = __bfloat162float(gp[UB]), gn = __bfloat162float(gp[2 * UB]);
       const float hnn = __bfloat162float(gp[3 * UB]);
       const float hp = h_prev[idx];
@@ -83,21 +90,28 @@ __global__ void gru_gate_bwd_kernel(const float* __restrict__ dh, const float* _
     dgh[r * lddgh + c] = __float2bfloat16(dar);
     dgh[r * lddgh + Hh + c] = __float2bfloat16(daz);
     dgh[r * lddgh + 2 * Hh + c] = __float2bfloat16(dhn);
+    s_r += dar; s_z += daz; s_n += dan; s_h += dhn;
+  }
+  if (db_ih) {
+    atomicAdd(&db_ih[c], s_r); atomicAdd(&db_ih[Hh + c], s_z); atomicAdd(&db_ih[2 * Hh + c], s_n);
+  }
+  if (db_hh) {
+    atomicAdd(&db_hh[c], s_r); atomicAdd(&db_hh[Hh + c], s_z); atomicAdd(&db_hh[2 * Hh + c], s_h);
   }
 }
 
 int gru_gate_bwd(const float* dh, const float* dout_t, long lddout, const void* gates, const float* h_prev,
                  const long long* lengths, int t, float* dh_prev, void* dgi_bf16, long lddgi, void* dgh_bf16,
-                 long lddgh, long R, int Hh, cudaStream_t st) {
+                 long lddgh, float* db_ih, float* db_hh, long R, int Hh, cudaStream_t st) {
   if (R == 0) return GTOS_OK;
   GTOS_REQUIRE(Hh % 16 == 0, "gru_gate_bwd: hidden size must be a multiple of 16");
-  long blocks = (R * Hh + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
   const int UB = (Hh % 64 == 0) ? 64 : 16;
-  gru_gate_bwd_kernel<<<(unsigned)blocks, 256, 0, st>>>(dh, dout_t, lddout, reinterpret_cast<const __nv_bfloat16*>(gates),
-                                                        h_prev, lengths, t, dh_prev,
-                                                        reinterpret_cast<__nv_bfloat16*>(dgi_bf16), lddgi,
-                                                        reinterpret_cast<__nv_bfloat16*>(dgh_bf16), lddgh, R, Hh, UB);
+  const int thr = Hh < 256 ? ((Hh + 31) / 32 * 32) : 256;
+  const int rpb = 32;
+  dim3 grid((Hh + thr - 1) / thr, (unsigned)((R + rpb - 1) / rpb));
+  gru_gate_bwd_kernel<<<grid, thr, 0, st>>>(dh, dout_t, lddout, reinterpret_cast<const __nv_bfloat16*>(gates), h_prev,
+                                            lengths, t, dh_prev, reinterpret_cast<__nv_bfloat16*>(dgi_bf16), lddgi,
+                                            reinterpret_cast<__nv_bfloat16*>(dgh_bf16), lddgh, db_ih, db_hh, R, Hh, UB, rpb);
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
 }

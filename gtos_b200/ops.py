@@ -507,7 +507,7 @@ class GRUBankFn(torch.autograd.Function):
         finals_b = torch.empty(R, 2 * Hh, dtype=torch.bfloat16, device=dev)
         Kin = E
         for l in range(num_layers):
-            outb = torch.empty(rows, 2 * Hh, dtype=torch.bfloat16, device=dev)
+            outb = torch.empty(rows, 2 * Hh, dtype=torch.bfloat16, device=dev) if l < num_layers - 1 else None
             Kx = _up64(Kin)
             for d in range(2):
                 w_ih, w_hh, b_ih, b_hh = weights[(l * 2 + d) * 4:(l * 2 + d) * 4 + 4]
@@ -528,10 +528,10 @@ class GRUBankFn(torch.autograd.Function):
                 for s in range(Lmax):
                     t = s if d == 0 else Lmax - 1 - s
                     x_t = xb[t * R:(t + 1) * R]
-                    out_t = outb[t * R:(t + 1) * R, d * Hh:(d + 1) * Hh]
+                    out_t = outb[t * R:(t + 1) * R, d * Hh:(d + 1) * Hh] if l < num_layers - 1 else None
                     _lib.check(lib.gtos_gru_step_fwd(_p(x_t), x_t.stride(0), Kin, _p(hsb[s]), Hh, _p(hs[s]), _p(Wcat), ldw,
                                                      Kx, _p(bcat), _p(lengths), t, _p(hs[s + 1]), _p(hsb[s + 1]), Hh,
-                                                     _p(out_t), out_t.stride(0), _p(gates[s]), 4 * Hh, R, Hh, _st()),
+                                                     _p(out_t), 2 * Hh, _p(gates[s]), 4 * Hh, R, Hh, _st()),
                                "gru_step_fwd")
                 if l == num_layers - 1:
                     finals_b[:, d * Hh:(d + 1) * Hh].copy_(hsb[Lmax])
@@ -565,35 +565,45 @@ class GRUBankFn(torch.autograd.Function):
         wgrads = [None] * (num_layers * 8)
         d_layer_out = None                                                         # [rows, 2H] fp32
         for l in range(num_layers - 1, -1, -1):
-            dx = None
+            dgi_cat = torch.empty(rows, 6 * Hh, dtype=torch.bfloat16, device=dev)      # [dgi_fwd | dgi_rev], time order
+            Wih_t_cat = []
             for d in range(2):
                 xb, gates, hs, hsb, Wih_t, Whh_t = saved[(l * 2 + d) * 6:(l * 2 + d) * 6 + 6]
                 Kin = Wih_t.shape[0]
-                dgi = torch.empty(rows, 3 * Hh, dtype=torch.bfloat16, device=dev)      # rows in time order t
                 dgh = torch.empty(rows, 3 * Hh, dtype=torch.bfloat16, device=dev)      # rows in step order s
                 if l == num_layers - 1:
                     dh = dfinals[:, d * Hh:(d + 1) * Hh].contiguous()
                 else:
                     dh = torch.zeros(R, Hh, dtype=torch.float32, device=dev)
+                db_ih = torch.zeros(3 * Hh, dtype=torch.float32, device=dev)
+                db_hh = torch.zeros(3 * Hh, dtype=torch.float32, device=dev)
+                dgi = dgi_cat[:, d * 3 * Hh:(d + 1) * 3 * Hh]                          # rows in time order t
                 for s in range(Lmax - 1, -1, -1):
                     t = s if d == 0 else Lmax - 1 - s
                     dout_t = d_layer_out[t * R:(t + 1) * R, d * Hh:(d + 1) * Hh] if d_layer_out is not None else None
-                    dh_prev = torch.empty_like(dh)
+                    dh_part = torch.empty_like(dh)                                     # dh * z (pass-through for finished rows)
+                    dgi_t, dgh_s = dgi[t * R:(t + 1) * R], dgh[s * R:(s + 1) * R]
                     _lib.check(lib.gtos_gru_gate_bwd(_p(dh), _p(dout_t), dout_t.stride(0) if dout_t is not None else 0,
-                                                     _p(gates[s]), _p(hs[s]), _p(lengths), t, _p(dh_prev),
-                                                     _p(dgi[t * R:(t + 1) * R]), 3 * Hh, _p(dgh[s * R:(s + 1) * R]),
-                                                     3 * Hh, R, Hh, _st()), "gru_gate_bwd")
-                    gemm_tn(dgh[s * R:(s + 1) * R], Whh_t, Hh, out=dh_prev, accumulate=True)
+                                                     _p(gates[s]), _p(hs[s]), _p(lengths), t, _p(dh_part),
+                                                     _p(dgi_t), dgi_t.stride(0), _p(dgh_s), 3 * Hh, _p(db_ih), _p(db_hh),
+                                                     R, Hh, _st()), "gru_gate_bwd")
+                    dh_prev = torch.empty_like(dh)                                     # = dgh @ W_hh + dh * z
+                    _lib.check(lib.gtos_gemm_tn_add(_p(dgh_s), 3 * Hh, _p(Whh_t), Whh_t.stride(0), None, _p(dh_part), Hh,
+                                                    _p(dh_prev), Hh, R, Hh, 3 * Hh, _st()), "gemm_tn_add")
                     dh = dh_prev
                 base = (l * 2 + d) * 4
                 wgrads[base + 0] = gemm_nn(dgi, xb, 3 * Hh, Kin)
                 wgrads[base + 1] = gemm_nn(dgh, hsb[:Lmax].view(rows, Hh), 3 * Hh, Hh)
-                wgrads[base + 2] = colsum(dgi)
-                wgrads[base + 3] = colsum(dgh)
-                if dx is None:
-                    dx, _ = gemm_tn(dgi, Wih_t, Kin)
-                else:
-                    gemm_tn(dgi, Wih_t, Kin, out=dx, accumulate=True)
+                wgrads[base + 2] = db_ih
+                wgrads[base + 3] = db_hh
+                Wih_t_cat.append(Wih_t)
+            # dx of both directions in ONE GEMM: [dgi_fwd | dgi_rev] x [Wih_fwd^T ; Wih_rev^T]
+            Wcat_t = torch.cat(Wih_t_cat, dim=1) if Wih_t_cat[0].shape[1] == 3 * Hh else None
+            if Wcat_t is not None:
+                dx, _ = gemm_tn(dgi_cat, Wcat_t, Kin)
+            else:                                                                      # padded 3H: keep two GEMMs
+                dx, _ = gemm_tn(dgi_cat[:, :3 * Hh], Wih_t_cat[0], Kin, K=3 * Hh)
+                gemm_tn(dgi_cat[:, 3 * Hh:], Wih_t_cat[1], Kin, K=3 * Hh, out=dx, accumulate=True)
             if l > 0:
                 if layer_offs[l - 1]:
                     dropout_f32(dx, p, seed, layer_offs[l - 1], out=dx)

@@ -52,6 +52,9 @@ int gtos_weight_prep(const float* W, int32_t R, int32_t C, void* Wb, int64_t ldw
 int gtos_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, const float* bias, float* out_f32, int64_t ldo,
                  void* out_bf16, int64_t ldob, int32_t M, int32_t N, int32_t K, int32_t relu, int32_t accumulate,
                  void* stream);
+/* C[M,N] (fp32) = A * B^T + bias[N] + addend[M,N]   (e.g. dh_prev = dgh * W_hh + dh * z in the GRU backward) */
+int gtos_gemm_tn_add(const void* A, int64_t lda, const void* B, int64_t ldb, const float* bias, const float* addend,
+                     int64_t ldadd, float* out_f32, int64_t ldo, int32_t M, int32_t N, int32_t K, void* stream);
 /* C[M,N] = sum_k A[k,m] * B[k,n]  (weight gradients, autograd of the call sites above) */
 int64_t gtos_gemm_nn_workspace(int32_t M, int32_t N, int32_t Kd);
 int gtos_gemm_nn(const void* A, int64_t lda, const void* B, int64_t ldb, float* out, int64_t ldo, int32_t M, int32_t N,
@@ -160,9 +163,10 @@ int gtos_gru_step_fwd(const void* x, int64_t ldx, int32_t Kin, const void* hb, i
                       const void* Wcat, int64_t ldw, int32_t Kx, const float* bcat, const int64_t* lengths, int32_t t,
                       float* h_new, void* hb_new, int64_t ldhbn, void* out_t, int64_t ldout, void* gates, int64_t ldg,
                       int64_t R, int32_t H, void* stream);
+/* db_ih / db_hh (fp32 [3H], may be NULL): bias gradients, ACCUMULATED over the calls of one (layer, direction) */
 int gtos_gru_gate_bwd(const float* dh, const float* dout_t, int64_t lddout, const void* gates, const float* h_prev,
                       const int64_t* lengths, int32_t t, float* dh_prev, void* dgi_bf16, int64_t lddgi, void* dgh_bf16,
-                      int64_t lddgh, int64_t R, int32_t Hh, void* stream);
+                      int64_t lddgh, float* db_ih, float* db_hh, int64_t R, int32_t Hh, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,141 +1,122 @@
-// gtos_b200 -- attention core kernels (softmax + masks + dropout + PV and their backward).
+// gtos_b200 -- attention core kernels (masks + softmax + dropout + PV and their backward).
 //
 // Two users:
 //   * encoder (generator/graph_transformer.py:136-159): the scores already contain the relation
 //     terms and arrive from the fused tcgen05 kernel as [B,H,S(j),T(i)];
 //   * decoder / vanilla MHA (generator/transformer.py:131-155): scores = scale * q k^T computed here.
-// Sequences are short (<= ~260), so each CTA owns one (batch, head) and a block of 32 query (or
-// key) rows, stages 64-wide feature chunks of the other operand in shared memory and keeps the
-// [32 x S] score block in shared memory.  fp32 throughout; the contraction sizes here are <1% of
-// the layer FLOPs.
+// Sequences are short (<= ~260 keys), so one CTA owns one (batch, head) and a block of <= 64 query (or key)
+// rows.  The three small products of each kernel (QK^T / dO V^T, PV / dS K, P^T dO / dS^T q) run on the
+// tensor cores as 16x16x16 bf16 tiles with fp32 accumulation (warp-level mma; these are 60x60x64-sized
+// problems, far below a 128-row tcgen05 tile), operands converted to bf16 while they are staged in shared
+// memory in 64-wide feature chunks.  Softmax, masks, dropout and the dS algebra stay in fp32 on the score
+// block in shared memory.  This is < 1 % of the layer FLOPs: the kernels are
+// latency-bound, so the design goal is few instructions and few dependent global round trips.
+#include <mma.h>
+
 #include "elementwise.cuh"
 
 namespace gtos {
 
+using namespace nvcuda;
+
 static constexpr int AT_THREADS = 256;
 static constexpr int AT_WARPS = 8;
-static constexpr int AT_ROWS_MAX = 64;  // query (or key) rows per CTA: all rows when the sequence is short
-static constexpr int AT_DC = 64;    // feature chunk
+static constexpr int AT_ROWS_MAX = 64;  // query (or key) rows per CTA
+static constexpr int AT_DC = 64;        // feature chunk
 
-// shared-memory working set of one CTA.  Row strides are multiples of 4 floats (16-byte vector loads):
-//   xs [rows][dstr]  query-side chunk (q or dO)       dstr = round4(dc) + 4  (=68 for dc=64: conflict-free LDS.128)
-//   ys [L4][dstr]    key-side chunk (K, V, dO or q)   L4 = round4(L), pad rows zero
-//   sc [rows][lstr]  score block                      lstr = L4 + 4
+__host__ __device__ inline int r16(int n) { return (n + 15) & ~15; }
+
+// shared-memory working set of one CTA (all tile extents rounded up to 16, pads zero-filled):
+//   sc [R16][lstr]  fp32  score block (also the fp32 staging tile of the second product)
+//   xb [R16][dstr]  bf16  query-side chunk (q or dO)
+//   yb [L16][dstr]  bf16  key-side chunk (K, V, dO or q)
+//   pb [R16][lstr]  bf16  probabilities / dS as MMA operand
 struct AttnSmem {
-  float* xs;
-  float* ys;
+  __nv_bfloat16* xb;
+  __nv_bfloat16* yb;
+  __nv_bfloat16* pb;
   float* sc;
-  int dstr, lstr, L4;
+  int dstr, lstr, L16, R16;
 };
 
-__host__ __device__ inline int r4(int n) { return (n + 3) & ~3; }
+__host__ __device__ inline size_t attn_smem_layout(int L, int dc, int rows, int* dstr, int* lstr, int* L16, int* R16) {
+  *dstr = r16(dc) + 8;
+  *L16 = r16(L);
+  *R16 = r16(rows);
+  int ls = *L16 > r16(dc) ? *L16 : r16(dc);   // sc doubles as the [R16 x dc16] output staging tile
+  *lstr = ls + 8;
+  return (size_t)(*R16) * (*dstr) * 2 + (size_t)(*L16) * (*dstr) * 2 + (size_t)(*R16) * (*lstr) * 2 +
+         (size_t)(*R16) * (*lstr) * 4;
+}
 
-__device__ __forceinline__ AttnSmem carve(float* base, int L, int dc, int AT_ROWS) {
+__device__ __forceinline__ AttnSmem carve(uint8_t* base, int L, int dc, int rows) {
   AttnSmem s;
-  s.dstr = r4(dc) + 4;
-  s.L4 = r4(L);
-  s.lstr = s.L4 + 4;
-  s.xs = base;
-  s.ys = s.xs + (size_t)AT_ROWS * s.dstr;
-  s.sc = s.ys + (size_t)s.L4 * s.dstr;
+  attn_smem_layout(L, dc, rows, &s.dstr, &s.lstr, &s.L16, &s.R16);
+  s.sc = reinterpret_cast<float*>(base);
+  s.xb = reinterpret_cast<__nv_bfloat16*>(s.sc + (size_t)s.R16 * s.lstr);
+  s.yb = s.xb + (size_t)s.R16 * s.dstr;
+  s.pb = s.yb + (size_t)s.L16 * s.dstr;
   return s;
 }
 
-// rows [r0, r0+nr) x dims [c0, c0+dc) of a [len, B, ld] projection for (b, h) -> dst[nr][dstr]; rows >= len and the
-// pad columns are zero-filled
-__device__ __forceinline__ void load_rows(float* dst, int dstr, const float* src, long ld, int B, int b, int hoff,
-                                          int r0, int nr, int len, int c0, int dc) {
-  const int dc4 = r4(dc);
+// rows [r0, r0+nr16) x dims [c0, c0+dc) of a [len, B, ld] fp32 projection for (b, h) -> bf16 dst[nr16][dstr];
+// rows >= len and columns >= dc (up to r16(dc)) are zero-filled.  16-byte global loads when alignment allows.
+__device__ __forceinline__ void load_rows_bf16(__nv_bfloat16* dst, int dstr, const float* src, long ld, int B, int b,
+                                               int hoff, int r0, int nr16, int len, int c0, int dc) {
+  const int dc16 = r16(dc);
   const bool vec = ((dc & 3) == 0) && ((ld & 3) == 0) && (((hoff + c0) & 3) == 0) &&
                    ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
-  if (vec) {
-    // 16-byte loads, all of a thread's loads in flight before the first store (latency-bound otherwise)
-    const int q = dc4 >> 2, total = nr * q;
+  const int q = dc16 >> 2, total = nr16 * q;
 #pragma unroll 4
-    for (int idx = threadIdx.x; idx < total; idx += AT_THREADS) {
-      const int r = idx / q, d4 = idx - r * q;
-      const int t = r0 + r;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (t < len) v = *reinterpret_cast<const float4*>(src + ((long)t * B + b) * ld + hoff + c0 + 4 * d4);
-      *reinterpret_cast<float4*>(dst + r * dstr + 4 * d4) = v;
-    }
-    return;
-  }
-  for (int idx = threadIdx.x; idx < nr * dc4; idx += AT_THREADS) {
-    int r = idx / dc4, d = idx - r * dc4;
-    int t = r0 + r;
-    dst[r * dstr + d] = (t < len && d < dc) ? src[((long)t * B + b) * ld + hoff + c0 + d] : 0.f;
-  }
-}
-
-constexpr int AT_RB = 8;  // rows per warp pass (register blocking)
-
-// sc[r][j] += sum_d xs[r][d] * ys[j][d]     lanes over j, AT_RB rows per pass, 16-byte smem loads along d
-__device__ __forceinline__ void nt_accumulate(const AttnSmem& s, int L, int dc, int nrows) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int dq = r4(dc) >> 2;
-  for (int r0 = warp * AT_RB; r0 < nrows; r0 += AT_WARPS * AT_RB) {
-    for (int j = lane; j < L; j += 32) {
-      const float4* y = reinterpret_cast<const float4*>(s.ys + (size_t)j * s.dstr);
-      float acc[AT_RB];
-#pragma unroll
-      for (int rr = 0; rr < AT_RB; ++rr) acc[rr] = 0.f;
-      for (int d4 = 0; d4 < dq; ++d4) {
-        const float4 yv = y[d4];
-#pragma unroll
-        for (int rr = 0; rr < AT_RB; ++rr) {
-          const float4 xv = reinterpret_cast<const float4*>(s.xs + (size_t)(r0 + rr) * s.dstr)[d4];
-          acc[rr] = fmaf(xv.x, yv.x, fmaf(xv.y, yv.y, fmaf(xv.z, yv.z, fmaf(xv.w, yv.w, acc[rr]))));
-        }
+  for (int idx = threadIdx.x; idx < total; idx += AT_THREADS) {
+    const int r = idx / q, d = (idx - r * q) * 4;
+    const int t = r0 + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < len && d < dc) {
+      const float* p = src + ((long)t * B + b) * ld + hoff + c0 + d;
+      if (vec) {
+        v = *reinterpret_cast<const float4*>(p);
+      } else {
+        v.x = p[0];
+        if (d + 1 < dc) v.y = p[1];
+        if (d + 2 < dc) v.z = p[2];
+        if (d + 3 < dc) v.w = p[3];
       }
-#pragma unroll
-      for (int rr = 0; rr < AT_RB; ++rr)
-        if (r0 + rr < nrows) s.sc[(size_t)(r0 + rr) * s.lstr + j] += acc[rr];
     }
+    *reinterpret_cast<uint2*>(dst + (size_t)r * dstr + d) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
   }
 }
 
-// out[r][d] = sum_j sc[r][j] * ys[j][d]   lanes over d (two per lane for dc = 64), AT_RB rows per pass
-template <class F>
-__device__ __forceinline__ void nn_product(const AttnSmem& s, int L, int dc, int nrows, F&& store) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int d0 = lane, d1 = lane + 32;
-  const bool has1 = d1 < dc, has0 = d0 < dc;
-  for (int r0 = warp * AT_RB; r0 < nrows; r0 += AT_WARPS * AT_RB) {
-    float a0[AT_RB], a1[AT_RB];
-#pragma unroll
-    for (int rr = 0; rr < AT_RB; ++rr) a0[rr] = a1[rr] = 0.f;
-    for (int j4 = 0; j4 < s.L4; j4 += 4) {
-      float y0[4], y1[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float* yr = s.ys + (size_t)(j4 + u) * s.dstr;
-        y0[u] = has0 ? yr[d0] : 0.f;
-        y1[u] = has1 ? yr[d1] : 0.f;
-      }
-#pragma unroll
-      for (int rr = 0; rr < AT_RB; ++rr) {
-        const float4 w = *reinterpret_cast<const float4*>(s.sc + (size_t)(r0 + rr) * s.lstr + j4);
-        a0[rr] = fmaf(w.x, y0[0], fmaf(w.y, y0[1], fmaf(w.z, y0[2], fmaf(w.w, y0[3], a0[rr]))));
-        a1[rr] = fmaf(w.x, y1[0], fmaf(w.y, y1[1], fmaf(w.z, y1[2], fmaf(w.w, y1[3], a1[rr]))));
-      }
-    }
-#pragma unroll
-    for (int rr = 0; rr < AT_RB; ++rr) {
-      if (r0 + rr < nrows) {
-        if (has0) store(r0 + rr, d0, a0[rr]);
-        if (has1) store(r0 + rr, d1, a1[rr]);
+// C[M16 x N16] (fp32, ldc) (+)= A[M16 x K16] (bf16 row-major, lda) * B
+//   B_COL = true : B given as Y[N16 x K16] row-major (i.e. C = A * Y^T)
+//   B_COL = false: B given as Y[K16 x N16] row-major
+template <bool B_COL>
+__device__ __forceinline__ void tile_mm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* Bm, int ldb, float* C, int ldc,
+                                        int M16, int N16, int K16, bool accumulate) {
+  const int warp = threadIdx.x >> 5;
+  const int nt = N16 >> 4, tiles = (M16 >> 4) * nt;
+  for (int tile = warp; tile < tiles; tile += AT_WARPS) {
+    const int m0 = (tile / nt) << 4, n0 = (tile % nt) << 4;
+    wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc;
+    if (accumulate)
+      wmma::load_matrix_sync(acc, C + (size_t)m0 * ldc + n0, ldc, wmma::mem_row_major);
+    else
+      wmma::fill_fragment(acc, 0.f);
+    for (int k0 = 0; k0 < K16; k0 += 16) {
+      wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::row_major> fa;
+      wmma::load_matrix_sync(fa, A + (size_t)m0 * lda + k0, lda);
+      if (B_COL) {
+        wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::col_major> fb;
+        wmma::load_matrix_sync(fb, Bm + (size_t)n0 * ldb + k0, ldb);
+        wmma::mma_sync(acc, fa, fb, acc);
+      } else {
+        wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::row_major> fb;
+        wmma::load_matrix_sync(fb, Bm + (size_t)k0 * ldb + n0, ldb);
+        wmma::mma_sync(acc, fa, fb, acc);
       }
     }
+    wmma::store_matrix_sync(C + (size_t)m0 * ldc + n0, acc, ldc, wmma::mem_row_major);
   }
-}
-
-// zero the pad columns [L, lstr) of every score row and the pad rows [L, L4) of ys (so vector loops can run to L4)
-__device__ __forceinline__ void zero_pads(const AttnSmem& s, int L, int rows) {
-  const int padc = s.lstr - L;
-  for (int idx = threadIdx.x; idx < rows * padc; idx += AT_THREADS) s.sc[(size_t)(idx / padc) * s.lstr + L + idx % padc] = 0.f;
-  const int padr = s.L4 - L;
-  for (int idx = threadIdx.x; idx < padr * s.dstr; idx += AT_THREADS) s.ys[(size_t)L * s.dstr + idx] = 0.f;
 }
 
 __device__ __forceinline__ bool is_masked(const AttnArgs& a, int b, int t, int j) {
@@ -144,57 +125,56 @@ __device__ __forceinline__ bool is_masked(const AttnArgs& a, int b, int t, int j
   return false;
 }
 
-// -inf the masked entries of the score block in one cooperative, coalesced pass (instead of dependent byte loads
-// inside every softmax row loop)
-__device__ __forceinline__ void apply_masks(const AttnArgs& a, const AttnSmem& s, int b, int t0, int nrows, float sscale) {
+// ============================================================================================
+// forward
+// ============================================================================================
+__global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnArgs a, const int rows) {
+  extern __shared__ __align__(128) uint8_t smem_u8[];
+  const int dc = a.hd < AT_DC ? a.hd : AT_DC;
+  const int dc16 = r16(dc);
+  const AttnSmem s = carve(smem_u8, a.S, dc, rows);
+  const int bh = blockIdx.x, b = bh / a.H, h = bh % a.H;
+  const int t0 = blockIdx.y * rows;
+  const int nrows = (a.T - t0) < rows ? (a.T - t0) : rows;
+  const int hoff = h * a.hd;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = a.S;
+
+  // ---- scores into sc ----
+  if (a.scores_jt) {
+    for (int idx = threadIdx.x; idx < s.L16 * s.R16; idx += AT_THREADS) {
+      const int j = idx / s.R16, r = idx % s.R16;
+      s.sc[(size_t)r * s.lstr + j] = (r < nrows && j < S) ? a.scores_jt[((long)bh * S + j) * a.T + t0 + r] : 0.f;
+    }
+  } else {
+    for (int c0 = 0; c0 < a.hd; c0 += dc) {
+      __syncthreads();
+      load_rows_bf16(s.xb, s.dstr, a.q, a.ldq, a.B, b, hoff, t0, s.R16, a.T, c0, dc);
+      load_rows_bf16(s.yb, s.dstr, a.k, a.ldk, a.B, b, hoff, 0, s.L16, S, c0, dc);
+      __syncthreads();
+      tile_mm<true>(s.xb, s.dstr, s.yb, s.dstr, s.sc, s.lstr, s.R16, s.L16, dc16, c0 > 0);
+    }
+  }
+  __syncthreads();
+
+  // ---- masks, softmax, dropout; probabilities -> global (fp32) and pb (bf16 operand) ----
+  const unsigned long long seed = a.p_drop > 0.f ? reinterpret_cast<const unsigned long long*>(a.seed_ptr)[0] + a.seed_off : 0ull;
+  const float ks = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
+  const float sscale = a.scores_jt ? 1.f : a.scale;
   for (int idx = threadIdx.x; idx < nrows * S; idx += AT_THREADS) {
     const int r = idx / S, j = idx - r * S;
     float* p = s.sc + (size_t)r * s.lstr + j;
     *p = is_masked(a, b, t0 + r, j) ? -INFINITY : *p * sscale;
   }
-}
-
-__global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnArgs a, const int rows_per_cta) {
-  extern __shared__ float smem_f[];
-  const int dc = a.hd < AT_DC ? a.hd : AT_DC;
-  const int AT_ROWS = rows_per_cta;
-  const AttnSmem s = carve(smem_f, a.S, dc, AT_ROWS);
-  const int bh = blockIdx.x, b = bh / a.H, h = bh % a.H;
-  const int t0 = blockIdx.y * AT_ROWS;
-  const int nrows = (a.T - t0) < AT_ROWS ? (a.T - t0) : AT_ROWS;
-  const int hoff = h * a.hd;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int S = a.S;
-  zero_pads(s, S, AT_ROWS);
-
-  if (a.scores_jt) {
-    for (int idx = threadIdx.x; idx < S * AT_ROWS; idx += AT_THREADS) {
-      int j = idx / AT_ROWS, r = idx % AT_ROWS;
-      s.sc[(size_t)r * s.lstr + j] = (r < nrows) ? a.scores_jt[((long)bh * S + j) * a.T + t0 + r] : 0.f;
-    }
-    __syncthreads();
-  } else {
-    for (int idx = threadIdx.x; idx < AT_ROWS * s.lstr; idx += AT_THREADS) s.sc[idx] = 0.f;
-    for (int c0 = 0; c0 < a.hd; c0 += dc) {
-      __syncthreads();
-      load_rows(s.xs, s.dstr, a.q, a.ldq, a.B, b, hoff, t0, AT_ROWS, a.T, c0, dc);
-      load_rows(s.ys, s.dstr, a.k, a.ldk, a.B, b, hoff, 0, S, S, c0, dc);
-      __syncthreads();
-      nt_accumulate(s, S, dc, nrows);
-    }
-    __syncthreads();
-  }
-
-  // ---- masked softmax (+ dropout) per row ----
-  const unsigned long long seed = a.p_drop > 0.f ? reinterpret_cast<const unsigned long long*>(a.seed_ptr)[0] + a.seed_off : 0ull;
-  const float ks = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
-  const float sscale = a.scores_jt ? 1.f : a.scale;
-  apply_masks(a, s, b, t0, nrows, sscale);
   __syncthreads();
-  for (int r = warp; r < nrows; r += AT_WARPS) {
-    const int t = t0 + r;
+  for (int r = warp; r < s.R16; r += AT_WARPS) {
     float* w = s.sc + (size_t)r * s.lstr;
+    __nv_bfloat16* pw = s.pb + (size_t)r * s.lstr;
+    if (r >= nrows) {
+      for (int j = lane; j < s.L16; j += 32) pw[j] = __float2bfloat16(0.f);
+      continue;
+    }
+    const int t = t0 + r;
     float mx = -INFINITY;
     for (int j = lane; j < S; j += 32) mx = fmaxf(mx, w[j]);
     mx = warp_max(mx);
@@ -207,26 +187,33 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnArgs a, 
     sum = warp_sum(sum);
     const float inv = sum > 0.f ? 1.f / sum : 0.f;
     const long prow = ((long)bh * a.T + t) * S;
-    for (int j = lane; j < S; j += 32) {
-      float p = w[j] * inv;
-      a.probs[prow + j] = p;
-      if (a.p_drop > 0.f) p = (rng_uniform(seed, (unsigned long long)(prow + j)) >= a.p_drop) ? p * ks : 0.f;
-      if (a.probs_dropped) a.probs_dropped[prow + j] = p;
-      w[j] = p;
+    for (int j = lane; j < s.L16; j += 32) {
+      float p = 0.f;
+      if (j < S) {
+        p = w[j] * inv;
+        a.probs[prow + j] = p;
+        if (a.p_drop > 0.f) p = (rng_uniform(seed, (unsigned long long)(prow + j)) >= a.p_drop) ? p * ks : 0.f;
+        if (a.probs_dropped) a.probs_dropped[prow + j] = p;
+      }
+      pw[j] = __float2bfloat16(p);
     }
   }
 
-  // ---- PV ----
+  // ---- PV: out[r][d] = sum_j pb[r][j] * V[j][d], staged in sc, written coalesced ----
   __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(a.out_bf16);
   for (int c0 = 0; c0 < a.hd; c0 += dc) {
     __syncthreads();
-    load_rows(s.ys, s.dstr, a.v, a.ldv, a.B, b, hoff, 0, S, S, c0, dc);
+    load_rows_bf16(s.yb, s.dstr, a.v, a.ldv, a.B, b, hoff, 0, s.L16, S, c0, dc);
     __syncthreads();
-    nn_product(s, S, dc, nrows, [&](int r, int d, float acc) {
-      long o = ((long)(t0 + r) * a.B + b) * a.ldo + hoff + c0 + d;
-      a.out[o] = acc;
-      if (ob) ob[o] = __float2bfloat16(acc);
-    });
+    tile_mm<false>(s.pb, s.lstr, s.yb, s.dstr, s.sc, s.lstr, s.R16, dc16, s.L16, false);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nrows * dc; idx += AT_THREADS) {
+      const int r = idx / dc, d = idx - r * dc;
+      const float v = s.sc[(size_t)r * s.lstr + d];
+      const long o = ((long)(t0 + r) * a.B + b) * a.ldo + hoff + c0 + d;
+      a.out[o] = v;
+      if (ob) ob[o] = __float2bfloat16(v);
+    }
   }
 }
 
@@ -235,14 +222,14 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnArgs a, 
 static int attn_rows(int len, int bh) {
   int want_y = (2 * 148 + bh - 1) / bh;
   int rows = (len + want_y - 1) / want_y;
-  rows = (rows + 7) & ~7;  // register blocking reads whole groups of AT_RB = 8 rows
+  rows = r16(rows);
   if (rows > AT_ROWS_MAX) rows = 32;
   return rows;
 }
 static size_t attn_smem_bytes(int L, int hd, int rows) {
   int dc = hd < AT_DC ? hd : AT_DC;
-  int dstr = r4(dc) + 4, L4 = r4(L);
-  return sizeof(float) * ((size_t)rows * dstr + (size_t)L4 * dstr + (size_t)rows * (L4 + 4));
+  int a, b2, c, d;
+  return attn_smem_layout(L, dc, rows, &a, &b2, &c, &d) + 128;
 }
 
 int attn_fwd(const AttnArgs& a, cudaStream_t st) {
@@ -259,40 +246,45 @@ int attn_fwd(const AttnArgs& a, cudaStream_t st) {
   return GTOS_OK;
 }
 
-// ---------------------------------------------------------------------------------------
+// ============================================================================================
 // backward, query side: dS (and dq in decoder mode)
-// ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(AT_THREADS) attn_bwd_q_kernel(const AttnBwdArgs g, const int rows_per_cta) {
-  extern __shared__ float smem_f[];
+// ============================================================================================
+__global__ void __launch_bounds__(AT_THREADS) attn_bwd_q_kernel(const AttnBwdArgs g, const int rows) {
+  extern __shared__ __align__(128) uint8_t smem_u8[];
   const AttnArgs& a = g.f;
   const int dc = a.hd < AT_DC ? a.hd : AT_DC;
-  const int AT_ROWS = rows_per_cta;
-  const AttnSmem s = carve(smem_f, a.S, dc, AT_ROWS);
+  const int dc16 = r16(dc);
+  const AttnSmem s = carve(smem_u8, a.S, dc, rows);
   const int bh = blockIdx.x, b = bh / a.H, h = bh % a.H;
-  const int t0 = blockIdx.y * AT_ROWS;
-  const int nrows = (a.T - t0) < AT_ROWS ? (a.T - t0) : AT_ROWS;
+  const int t0 = blockIdx.y * rows;
+  const int nrows = (a.T - t0) < rows ? (a.T - t0) : rows;
   const int hoff = h * a.hd;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = a.S;
-  zero_pads(s, S, AT_ROWS);
-  __syncthreads();
 
   // dPd[t][j] = dO[t] . V[j]
-  for (int idx = threadIdx.x; idx < AT_ROWS * s.lstr; idx += AT_THREADS) s.sc[idx] = 0.f;
   for (int c0 = 0; c0 < a.hd; c0 += dc) {
     __syncthreads();
-    load_rows(s.xs, s.dstr, g.dout, g.lddo, a.B, b, hoff, t0, AT_ROWS, a.T, c0, dc);
-    load_rows(s.ys, s.dstr, a.v, a.ldv, a.B, b, hoff, 0, S, S, c0, dc);
+    load_rows_bf16(s.xb, s.dstr, g.dout, g.lddo, a.B, b, hoff, t0, s.R16, a.T, c0, dc);
+    load_rows_bf16(s.yb, s.dstr, a.v, a.ldv, a.B, b, hoff, 0, s.L16, S, c0, dc);
     __syncthreads();
-    nt_accumulate(s, S, dc, nrows);
+    tile_mm<true>(s.xb, s.dstr, s.yb, s.dstr, s.sc, s.lstr, s.R16, s.L16, dc16, c0 > 0);
   }
   __syncthreads();
 
   const unsigned long long seed = a.p_drop > 0.f ? reinterpret_cast<const unsigned long long*>(a.seed_ptr)[0] + a.seed_off : 0ull;
   const float ks = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
-  for (int r = warp; r < nrows; r += AT_WARPS) {
-    const int t = t0 + r;
+  for (int r = warp; r < s.R16; r += AT_WARPS) {
     float* w = s.sc + (size_t)r * s.lstr;
+    __nv_bfloat16* pw = s.pb + (size_t)r * s.lstr;
+    if (r >= nrows) {
+      for (int j = lane; j < s.L16; j += 32) {
+        pw[j] = __float2bfloat16(0.f);
+        w[j] = 0.f;
+      }
+      continue;
+    }
+    const int t = t0 + r;
     const long prow = ((long)bh * a.T + t) * S;
     float dot = 0.f;
     for (int j = lane; j < S; j += 32) {
@@ -304,83 +296,95 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_q_kernel(const AttnBwdArg
       dot += dp * p;
     }
     dot = warp_sum(dot);
-    for (int j = lane; j < S; j += 32) {
-      float p = a.probs[prow + j];
-      float ds = p * (w[j] - dot);
-      g.dscores_ts[prow + j] = ds;
+    for (int j = lane; j < s.L16; j += 32) {
+      float ds = 0.f;
+      if (j < S) {
+        ds = a.probs[prow + j] * (w[j] - dot);
+        g.dscores_ts[prow + j] = ds;
+      }
       w[j] = ds;
+      pw[j] = __float2bfloat16(ds);
     }
   }
   __syncthreads();
   if (g.dscores_jt) {
     // transposed store for the fused relation backward kernel: [B,H,S(j),T(i)], coalesced along i
-    for (int idx = threadIdx.x; idx < S * AT_ROWS; idx += AT_THREADS) {
-      int j = idx / AT_ROWS, r = idx % AT_ROWS;
+    for (int idx = threadIdx.x; idx < S * s.R16; idx += AT_THREADS) {
+      const int j = idx / s.R16, r = idx % s.R16;
       if (r < nrows) g.dscores_jt[((long)bh * S + j) * a.T + t0 + r] = s.sc[(size_t)r * s.lstr + j];
     }
   }
   if (g.dq) {
     for (int c0 = 0; c0 < a.hd; c0 += dc) {
       __syncthreads();
-      load_rows(s.ys, s.dstr, a.k, a.ldk, a.B, b, hoff, 0, S, S, c0, dc);
+      load_rows_bf16(s.yb, s.dstr, a.k, a.ldk, a.B, b, hoff, 0, s.L16, S, c0, dc);
       __syncthreads();
-      nn_product(s, S, dc, nrows, [&](int r, int d, float acc) {
-        g.dq[((long)(t0 + r) * a.B + b) * g.lddq + hoff + c0 + d] = acc * a.scale;
-      });
+      tile_mm<false>(s.pb, s.lstr, s.yb, s.dstr, s.sc, s.lstr, s.R16, dc16, s.L16, false);
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < nrows * dc; idx += AT_THREADS) {
+        const int r = idx / dc, d = idx - r * dc;
+        g.dq[((long)(t0 + r) * a.B + b) * g.lddq + hoff + c0 + d] = s.sc[(size_t)r * s.lstr + d] * a.scale;
+      }
     }
   }
 }
 
-// ---------------------------------------------------------------------------------------
-// backward, key side: dV = Pd^T dO ; dK = scale * dS^T q      (CTA = 32 key rows of one (b,h))
-// ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(AT_THREADS) attn_bwd_kv_kernel(const AttnBwdArgs g, const int rows_per_cta) {
-  extern __shared__ float smem_f[];
+// ============================================================================================
+// backward, key side: dV = Pd^T dO ; dK = scale * dS^T q      (CTA = `rows` key rows of one (b,h))
+// ============================================================================================
+__global__ void __launch_bounds__(AT_THREADS) attn_bwd_kv_kernel(const AttnBwdArgs g, const int rows) {
+  extern __shared__ __align__(128) uint8_t smem_u8[];
   const AttnArgs& a = g.f;
   const int dc = a.hd < AT_DC ? a.hd : AT_DC;
+  const int dc16 = r16(dc);
   const int T = a.T, S = a.S;
-  const int AT_ROWS = rows_per_cta;
-  const AttnSmem s = carve(smem_f, T, dc, AT_ROWS);
+  const AttnSmem s = carve(smem_u8, T, dc, rows);   // L = T: the contraction runs over the queries
   const int bh = blockIdx.x, b = bh / a.H, h = bh % a.H;
-  const int j0 = blockIdx.y * AT_ROWS;
-  const int nrows = (S - j0) < AT_ROWS ? (S - j0) : AT_ROWS;
+  const int j0 = blockIdx.y * rows;
+  const int nrows = (S - j0) < rows ? (S - j0) : rows;
   const int hoff = h * a.hd;
   const unsigned long long seed = a.p_drop > 0.f ? reinterpret_cast<const unsigned long long*>(a.seed_ptr)[0] + a.seed_off : 0ull;
   const float ks = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
 
-  zero_pads(s, T, AT_ROWS);
-  // sc[jr][t] = Pd[t][j0+jr]
-  for (int idx = threadIdx.x; idx < T * AT_ROWS; idx += AT_THREADS) {
-    int t = idx / AT_ROWS, jr = idx % AT_ROWS;
+  // pb[jr][t] = Pd[t][j0+jr]  (transposed while loading; coalesced over jr in global)
+  for (int idx = threadIdx.x; idx < s.L16 * s.R16; idx += AT_THREADS) {
+    const int t = idx / s.R16, jr = idx % s.R16;
     float p = 0.f;
-    if (jr < nrows) {
-      long pi = ((long)bh * T + t) * S + j0 + jr;
+    if (jr < nrows && t < T) {
+      const long pi = ((long)bh * T + t) * S + j0 + jr;
       p = a.probs[pi];
       if (a.p_drop > 0.f) p = (rng_uniform(seed, (unsigned long long)pi) >= a.p_drop) ? p * ks : 0.f;
     }
-    s.sc[(size_t)jr * s.lstr + t] = p;
+    s.pb[(size_t)jr * s.lstr + t] = __float2bfloat16(p);
   }
   for (int c0 = 0; c0 < a.hd; c0 += dc) {
     __syncthreads();
-    load_rows(s.ys, s.dstr, g.dout, g.lddo, a.B, b, hoff, 0, T, T, c0, dc);
+    load_rows_bf16(s.yb, s.dstr, g.dout, g.lddo, a.B, b, hoff, 0, s.L16, T, c0, dc);
     __syncthreads();
-    nn_product(s, T, dc, nrows, [&](int r, int d, float acc) {
-      g.dv[((long)(j0 + r) * a.B + b) * g.lddv + hoff + c0 + d] = acc;
-    });
+    tile_mm<false>(s.pb, s.lstr, s.yb, s.dstr, s.sc, s.lstr, s.R16, dc16, s.L16, false);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nrows * dc; idx += AT_THREADS) {
+      const int r = idx / dc, d = idx - r * dc;
+      g.dv[((long)(j0 + r) * a.B + b) * g.lddv + hoff + c0 + d] = s.sc[(size_t)r * s.lstr + d];
+    }
   }
   if (g.dk) {
     __syncthreads();
-    for (int idx = threadIdx.x; idx < T * AT_ROWS; idx += AT_THREADS) {
-      int t = idx / AT_ROWS, jr = idx % AT_ROWS;
-      s.sc[(size_t)jr * s.lstr + t] = (jr < nrows) ? g.dscores_ts[((long)bh * T + t) * S + j0 + jr] * a.scale : 0.f;
+    for (int idx = threadIdx.x; idx < s.L16 * s.R16; idx += AT_THREADS) {
+      const int t = idx / s.R16, jr = idx % s.R16;
+      const float v = (jr < nrows && t < T) ? g.dscores_ts[((long)bh * T + t) * S + j0 + jr] * a.scale : 0.f;
+      s.pb[(size_t)jr * s.lstr + t] = __float2bfloat16(v);
     }
     for (int c0 = 0; c0 < a.hd; c0 += dc) {
       __syncthreads();
-      load_rows(s.ys, s.dstr, a.q, a.ldq, a.B, b, hoff, 0, T, T, c0, dc);
+      load_rows_bf16(s.yb, s.dstr, a.q, a.ldq, a.B, b, hoff, 0, s.L16, T, c0, dc);
       __syncthreads();
-      nn_product(s, T, dc, nrows, [&](int r, int d, float acc) {
-        g.dk[((long)(j0 + r) * a.B + b) * g.lddk + hoff + c0 + d] = acc;
-      });
+      tile_mm<false>(s.pb, s.lstr, s.yb, s.dstr, s.sc, s.lstr, s.R16, dc16, s.L16, false);
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < nrows * dc; idx += AT_THREADS) {
+        const int r = idx / dc, d = idx - r * dc;
+        g.dk[((long)(j0 + r) * a.B + b) * g.lddk + hoff + c0 + d] = s.sc[(size_t)r * s.lstr + d];
+      }
     }
   }
 }

@@ -80,6 +80,27 @@ class _RoundSTE(torch.autograd.Function):
         return g
 
 
+class _MatmulBf16(torch.autograd.Function):
+    """a @ b with both operands (and, in backward, the incoming gradient) rounded to bf16, fp32 accumulation:
+    what the attention-core kernels do for Q K^T, P V and their gradients (gtos_b200/csrc/attention.cu)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        ab, bb = _bf(a), _bf(b)
+        ctx.save_for_backward(ab, bb)
+        return ab @ bb
+
+    @staticmethod
+    def backward(ctx, g):
+        ab, bb = ctx.saved_tensors
+        gb = _bf(g)
+        return gb @ bb.transpose(-1, -2), ab.transpose(-1, -2) @ gb
+
+
+def _mm(a, b):
+    return _MatmulBf16.apply(a, b) if _PRECISION == "bf16" else a @ b
+
+
 def _lin32(x, w, b):
     """always-fp32 Linear: the 2-way copy/generate gate (decoder.py:42), which the B200 path keeps in fp32"""
     return x @ w.t() + b
@@ -136,7 +157,7 @@ def rel_mha(P, pre, query, key, value, relation, num_heads, key_padding_mask=Non
     w = torch.softmax(score, dim=1)                               # over keys j (:152)
     if weights_dropout:
         w = _drop(w, dropout, training)
-    out = torch.einsum("ijbh,jbhd->ibhd", w, v)                   # (:159)
+    out = _mm(w.permute(2, 3, 0, 1), v.permute(1, 2, 0, 3)).permute(2, 0, 1, 3)   # [b,h,i,j]@[b,h,j,d] (:159)
     if not weights_dropout:
         out = _drop(out, dropout, training)
     out = _lin(out.reshape(T, B, D), P[pre + "out_proj.weight"], P[pre + "out_proj.bias"])
@@ -184,7 +205,7 @@ def mha(P, pre, query, key, value, num_heads, key_padding_mask=None, attn_mask=N
     q = _lin(query, Win[:D], bin_[:D]).view(T, B, H, hd) * (hd ** -0.5)
     k = _lin(key, Win[D:2 * D], bin_[D:2 * D]).view(S, B, H, hd)
     v = _lin(value, Win[2 * D:], bin_[2 * D:]).view(S, B, H, hd)
-    score = torch.einsum("tbhd,sbhd->bhts", q, k)
+    score = _mm(q.permute(1, 2, 0, 3), k.permute(1, 2, 3, 0))     # [b,h,t,d] @ [b,h,d,s]
     if attn_mask is not None:                                     # [T,S]
         score = score.masked_fill(attn_mask.bool()[None, None], NEG_INF)
     if key_padding_mask is not None:                              # [S,B]
@@ -192,7 +213,7 @@ def mha(P, pre, query, key, value, num_heads, key_padding_mask=None, attn_mask=N
     w = torch.softmax(score, dim=-1)
     if weights_dropout:
         w = _drop(w, dropout, training)
-    out = torch.einsum("bhts,sbhd->tbhd", w, v)
+    out = _mm(w, v.permute(1, 2, 0, 3)).permute(2, 0, 1, 3)         # [b,h,t,s] @ [b,h,s,d] -> [t,b,h,d]
     if not weights_dropout:
         out = _drop(out, dropout, training)
     out = _lin(out.reshape(T, B, D), P[pre + "out_proj.weight"], P[pre + "out_proj.bias"])

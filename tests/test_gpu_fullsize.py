@@ -98,3 +98,34 @@ def test_one_graph_of_the_full_batch_vs_oracle(setup):
         with torch.no_grad():
             ref = O.graph_transformer(P, "", g["x"][:, b:b + 1], relb, 4, 8, self_padding_mask=g["node_mask"][:, b:b + 1])
         assert rel_err(out[:, b:b + 1], ref) < 1e-2
+
+
+def test_large_graph_257_nodes(setup):
+    """BASELINE.json config-4 graph size (256 nodes + <CLS>, relation paths <= 8): one layer fwd+bwd runs, is finite,
+    keeps graphs independent bit-exactly, and graph 0 matches the oracle run on that graph alone."""
+    from gtos_b200 import ops, synthetic
+    from gtos_b200.graph_transformer import GraphTransformer
+    dev = setup["dev"]
+    D, H, B = 512, 8, 3
+    g = synthetic.make_batch(B, 256, D, max_path_len=8, seed=SEED + 7)
+    N = g["N"]
+    gen = torch.Generator().manual_seed(SEED + 7)
+    bank = torch.randn(g["relation_bank"].shape[1], D, generator=gen) * 0.5
+    cpu = GraphTransformer(1, D, 1024, H, 0.0)
+    m = GraphTransformer(1, D, 1024, H, 0.0).to(dev)
+    m.load_state_dict(cpu.state_dict())
+    x = g["x"].to(dev).requires_grad_()
+    mask = g["node_mask"].to(dev)
+    rel = ops.bank_gather(bank.to(dev), g["relation"].to(dev)).detach().requires_grad_()
+    out = m(x, rel, self_padding_mask=mask)
+    out.square().sum().backward()
+    assert torch.isfinite(out).all() and torch.isfinite(x.grad).all() and torch.isfinite(rel.grad).all()
+    perm = torch.tensor([2, 0, 1], device=dev)
+    with torch.no_grad():
+        outp = m(x[:, perm], rel[:, :, perm].contiguous(), self_padding_mask=mask[:, perm])
+    assert torch.equal(out[:, perm], outp)
+    P = {k: v.clone() for k, v in cpu.state_dict().items()}
+    relc = bank.index_select(0, g["relation"][:, :, 0].reshape(-1)).view(N, N, 1, D)
+    with torch.no_grad():
+        ref = O.graph_transformer(P, "", g["x"][:, :1], relc, 1, H, self_padding_mask=g["node_mask"][:, :1])
+    assert rel_err(out[:, :1], ref) < 1e-2

@@ -149,7 +149,7 @@ def _attn_ref(q, k, v, scale, key_pad, attn_mask, H):
 
 
 @pytest.mark.parametrize("T,S,B,H,hd,causal", [(6, 8, 3, 4, 8, False), (40, 40, 16, 8, 64, True), (33, 70, 5, 1, 512, False),
-                                                (1, 40, 64, 8, 64, False)])
+                                                (1, 40, 64, 8, 64, False), (1, 40, 2048, 8, 64, False)])
 def test_attention_core(dev, T, S, B, H, hd, causal):
     from gtos_b200 import _lib, ops
     lib = _lib.load()
@@ -179,8 +179,9 @@ def test_attention_core(dev, T, S, B, H, hd, causal):
     d.probs, d.out, d.ldo = probs.data_ptr(), out.data_ptr(), D
     _lib.check(lib.gtos_attn_fwd(C.byref(d), st), "attn_fwd")
     torch.cuda.synchronize()
-    assert rel_err(probs, pref) < 1e-5
-    assert rel_err(out.view(T, B, D), ref) < 1e-5
+    # the three products run on bf16 tensor-core tiles (fp32 accumulate): bf16-level tolerances
+    assert rel_err(probs, pref) < 1e-2
+    assert rel_err(out.view(T, B, D), ref) < 1e-2
     dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
     ds = torch.empty(B, H, T, S, device=dev)
     d.dout, d.lddo = dout.data_ptr(), D
@@ -188,14 +189,14 @@ def test_attention_core(dev, T, S, B, H, hd, causal):
     d.dq, d.lddq, d.dk, d.lddk, d.dv, d.lddv = dq.data_ptr(), D, dk.data_ptr(), D, dv.data_ptr(), D
     _lib.check(lib.gtos_attn_bwd(C.byref(d), st), "attn_bwd")
     torch.cuda.synchronize()
-    assert rel_err(dq, gq) < 1e-4 and rel_err(dk, gk) < 1e-4 and rel_err(dv, gv) < 1e-4
+    assert rel_err(dq, gq) < 2e-2 and rel_err(dk, gk) < 2e-2 and rel_err(dv, gv) < 2e-2
     # extra gradient flowing into the returned weights
     q.grad = k.grad = v.grad = None
     ((ref * dout).sum() + (pref * dw).sum()).backward()
     d.dprobs_extra = dw.data_ptr()
     _lib.check(lib.gtos_attn_bwd(C.byref(d), st), "attn_bwd")
     torch.cuda.synchronize()
-    assert rel_err(dq, q.grad) < 1e-4 and rel_err(dk, k.grad) < 1e-4 and rel_err(dv, v.grad) < 1e-4
+    assert rel_err(dq, q.grad) < 2e-2 and rel_err(dk, k.grad) < 2e-2 and rel_err(dv, v.grad) < 2e-2
 
 
 def test_add_ln_and_ffn(dev):

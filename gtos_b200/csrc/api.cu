@@ -48,6 +48,11 @@ int gtos_cast_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_
   return cast_f32_bf16(src, lds, dst, ldd, rows, cols, S(stream));
 }
 
+int gtos_cast_colsum(const float* src, int64_t lds, void* dst, int64_t ldd, float* sums, int64_t rows, int32_t cols,
+                     void* stream) {
+  return cast_colsum(src, lds, dst, ldd, sums, rows, cols, S(stream));
+}
+
 int gtos_weight_prep(const float* W, int32_t R, int32_t C, void* Wb, int64_t ldw, void* Wt, int64_t ldt,
                      int32_t rel_heads, void* stream) {
   int perm_D = 0, perm_hd = 0;

@@ -45,6 +45,38 @@ int cast_f32_bf16(const float* src, long lds, void* dst, long ldd, long rows, in
   return GTOS_OK;
 }
 
+// fp32 [rows, cols] -> bf16 copy AND column sums in the same pass (every Linear backward needs both:
+// the bf16 operand of the two gradient GEMMs and the bias gradient)
+__global__ void cast_colsum_kernel(const float* __restrict__ src, long lds, __nv_bfloat16* __restrict__ dst, long ldd,
+                                   float* __restrict__ sums, long rows, int cols, int rows_per_block) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ldd) return;
+  const long r0 = (long)blockIdx.y * rows_per_block;
+  const long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float s = 0.f;
+  if (c < cols) {
+    for (long r = r0; r < r1; ++r) {
+      const float v = src[r * lds + c];
+      dst[r * ldd + c] = __float2bfloat16(v);
+      s += v;
+    }
+    atomicAdd(&sums[c], s);
+  } else {
+    for (long r = r0; r < r1; ++r) dst[r * ldd + c] = __float2bfloat16(0.f);
+  }
+}
+
+int cast_colsum(const float* src, long lds, void* dst, long ldd, float* sums, long rows, int cols, cudaStream_t st) {
+  GTOS_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * cols, st));
+  if (rows == 0 || cols == 0) return GTOS_OK;
+  GTOS_REQUIRE(ldd >= cols, "cast_colsum: destination row stride must be >= cols");
+  const int rpb = 32;
+  dim3 grid((unsigned)((ldd + 127) / 128), (unsigned)((rows + rpb - 1) / rpb));
+  cast_colsum_kernel<<<grid, 128, 0, st>>>(src, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldd, sums, rows, cols, rpb);
+  GTOS_LAUNCH_CHECK();
+  return GTOS_OK;
+}
+
 // ---------------------------------------------------------------------------------------
 // weight prep: W f32 [R,C] -> Wb bf16 [R,ldw] (optional) and Wt bf16 [C,ldt] (optional)
 // optional row permutation for relation_in_proj (perm_D > 0): output row pr <- input row orig(pr)

@@ -6,6 +6,7 @@
 namespace gtos {
 
 int cast_f32_bf16(const float* src, long lds, void* dst, long ldd, long rows, int cols, cudaStream_t st);
+int cast_colsum(const float* src, long lds, void* dst, long ldd, float* sums, long rows, int cols, cudaStream_t st);
 int weight_prep(const float* W, int R, int C, void* Wb, long ldw, void* Wt, long ldt, int perm_D, int perm_hd,
                 cudaStream_t st);
 int add_ln_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* y, void* y_bf16,

@@ -387,9 +387,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             fence_proxy_async();
             named_bar_sync(2, 128);
             if (issuer) {
-              if constexpr (MODE == MODE_DREL)
-                tma_store_4d(&tmO, buf, n0 + c, b0, i0, j0);
-              else
+              if constexpr (MODE == MODE_DREL) {
+                if (p.accumulate)
+                  tma_reduce_add_4d(&tmO, buf, n0 + c, b0, i0, j0);
+                else
+                  tma_store_4d(&tmO, buf, n0 + c, b0, i0, j0);
+              } else
                 tma_store_2d(&tmO, buf, n0 + c, m_blk * BM);
               tma_store_commit();
             }
@@ -680,7 +683,7 @@ static int launch_tn(const GemmTnArgs& a, cudaStream_t stream) {
     e = make_tmap_nd(&tmO, a.out_f32, 4, 2, dims, str, box, true);
     if (e) return e;
     p.tma_out = 1;
-  } else if (MODE == MODE_DREL && !a.accumulate && a.ldo == a.rt.D) {
+  } else if (MODE == MODE_DREL && a.ldo == a.rt.D) {
     const RelTiling& rt = a.rt;
     uint64_t dims[4] = {(uint64_t)rt.D, (uint64_t)rt.B, (uint64_t)rt.N, (uint64_t)rt.N};
     uint64_t str[4] = {0, (uint64_t)rt.D * 4, (uint64_t)rt.B * rt.D * 4, (uint64_t)rt.N * rt.B * rt.D * 4};

@@ -25,9 +25,15 @@ class GraphTransformer(nn.Module):
         # every layer reads the SAME relation tensor (:16-17): stage its bf16 copy once (or reuse the one
         # ops.bank_gather made while building the tensor)
         relb = _staged_bf16(relation)
+        # one shared gradient buffer for the relation tensor instead of L per-layer tensors summed by autograd
+        acc, token = None, None
+        if torch.is_grad_enabled() and relation.requires_grad:
+            acc = ops.RelGradAcc()
+            token = ops.RelTokenFn.apply(relation, acc)
         xb = None
         for layer in self.layers:
-            x, xb, _ = layer._forward(x, xb, relation, relb, kv, self_padding_mask, self_attn_mask, False)
+            x, xb, _ = layer._forward(x, xb, relation, relb, kv, self_padding_mask, self_attn_mask, False,
+                                      rel_token=token, rel_acc=acc)
         return x
 
     def get_attn_weights(self, x, relation, kv=None, self_padding_mask=None, self_attn_mask=None):
@@ -65,11 +71,13 @@ class GraphTransformerLayer(nn.Module):
         nn.init.constant_(self.fc1.bias, 0.)
         nn.init.constant_(self.fc2.bias, 0.)
 
-    def _forward(self, x, xb, relation, relb, kv, self_padding_mask, self_attn_mask, need_weights):
+    def _forward(self, x, xb, relation, relb, kv, self_padding_mask, self_attn_mask, need_weights, rel_token=None,
+                 rel_acc=None):
         p = self.dropout if self.training else 0.0
         if kv is not None and kv is not x:
             raise NotImplementedError("GraphTransformerLayer: kv != x is never used by gtos (generator.py:90)")
-        a, w = self.self_attn._forward(x, xb, relation, relb, self_padding_mask, self_attn_mask, need_weights)
+        a, w = self.self_attn._forward(x, xb, relation, relb, self_padding_mask, self_attn_mask, need_weights,
+                                       rel_token, rel_acc)
         x, xb = ops.add_layer_norm(a, x, self.attn_layer_norm.weight, self.attn_layer_norm.bias, p)
         h = ops.ffn(x, xb, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, p)
         x, xb = ops.add_layer_norm(h, x, self.ff_layer_norm.weight, self.ff_layer_norm.bias, p)
@@ -105,14 +113,14 @@ class RelationMultiheadAttention(nn.Module):
         nn.init.constant_(self.in_proj_bias, 0.)
         nn.init.constant_(self.out_proj.bias, 0.)
 
-    def _forward(self, x, xb, relation, relb, key_padding_mask, attn_mask, need_weights):
+    def _forward(self, x, xb, relation, relb, key_padding_mask, attn_mask, need_weights, rel_token=None, rel_acc=None):
         if not self.weights_dropout:
             raise NotImplementedError("RelationMultiheadAttention(weights_dropout=False) is never built by gtos")
         p = self.dropout if self.training else 0.0
         out, w = ops.RelAttnFn.apply(x, xb, relation, relb, ops.as_u8(key_padding_mask), ops.as_u8(attn_mask),
                                      self.in_proj_weight, self.in_proj_bias, self.relation_in_proj.weight,
                                      self.out_proj.weight, self.out_proj.bias, self.num_heads, float(p),
-                                     bool(need_weights))
+                                     bool(need_weights), rel_token, rel_acc)
         if w is not None:
             w = w.permute(2, 3, 0, 1)           # [B,H,T,S] -> [tgt, src, bsz, heads]   (:168-170)
         return out, w

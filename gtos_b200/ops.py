@@ -83,6 +83,18 @@ def cast_bf16(x2d, ld=None):
     return out
 
 
+def cast_colsum(x2d):
+    """fp32 [rows, cols] -> (bf16 [rows, up8(cols)], column sums fp32 [cols]) in one pass."""
+    _need_cuda(x2d)
+    x2d = x2d.contiguous()
+    rows, cols = x2d.shape
+    ld = _up8(cols)
+    out = torch.empty(rows, ld, dtype=torch.bfloat16, device=x2d.device)
+    sums = torch.empty(cols, dtype=torch.float32, device=x2d.device)
+    _lib.check(_lib.load().gtos_cast_colsum(_p(x2d), cols, _p(out), ld, _p(sums), rows, cols, _st()), "cast_colsum")
+    return out, sums
+
+
 def weight_prep(W, want_b=True, want_t=True, rel_heads=0):
     """W fp32 [R,C] -> (Wb bf16 [R, up8(C)], Wt bf16 [C, up8(R)])."""
     _need_cuda(W)
@@ -240,9 +252,8 @@ class FFNFn(torch.autograd.Function):
         D = shape[-1]
         dy2 = dy.contiguous().view(-1, D)
         M = dy2.shape[0]
-        dyb = cast_bf16(dy2)
+        dyb, db2 = cast_colsum(dy2)
         dW2 = gemm_nn(dyb, hb, D, Fd)
-        db2 = colsum(dy2)
         dh, _ = gemm_tn(dyb, W2t, Fd)                       # [M,F] = dy @ W2
         dhb = torch.empty(M, _up8(Fd), dtype=torch.bfloat16, device=dy.device)
         _lib.check(_lib.load().gtos_relu_drop_bwd(_p(dh), _p(hb), None, _p(dhb), dh.numel(), p, _st()), "relu_drop_bwd")
@@ -263,7 +274,8 @@ class RelAttnFn(torch.autograd.Function):
     """inputs x [N,B,D], relation [N,N,B,D] (+ its shared bf16 copy relb); returns (out, weights[B,H,N,N] | None)."""
 
     @staticmethod
-    def forward(ctx, x, xb, relation, relb, key_pad, attn_mask, W_in, b_in, W_rel, W_out, b_out, H, p, need_weights):
+    def forward(ctx, x, xb, relation, relb, key_pad, attn_mask, W_in, b_in, W_rel, W_out, b_out, H, p, need_weights,
+                rel_token=None, rel_acc=None):
         _need_cuda(x, relation, W_in)
         lib = _lib.load()
         N, B, D = x.shape
@@ -300,6 +312,7 @@ class RelAttnFn(torch.autograd.Function):
         out, _ = gemm_tn(attb, Wob, D, bias=b_out)
         ctx.save_for_backward(xb2, relb, qkb, vproj, probs, attb, Wperm, WpermT, Wit, Wot, key_pad, attn_mask)
         ctx.meta = (N, B, D, H, p, seed, off)
+        ctx.rel_acc = rel_acc if (rel_token is not None and rel_token.requires_grad) else None
         if wts is None:
             return out.view(N, B, D), None
         return out.view(N, B, D), wts
@@ -314,9 +327,8 @@ class RelAttnFn(torch.autograd.Function):
         dev = dout.device
         NB = N * B
         dout2 = dout.contiguous().view(NB, D)
-        doutb = cast_bf16(dout2)
+        doutb, db_out = cast_colsum(dout2)
         dW_out = gemm_nn(doutb, attb, D, D)
-        db_out = colsum(dout2)
         datt, _ = gemm_tn(doutb, Wot, D)                                           # [NB, D]
         dqkv = torch.empty(NB, 3 * D, dtype=torch.float32, device=dev)
         ds_jt = torch.empty(B, H, N, N, dtype=torch.float32, device=dev)
@@ -339,19 +351,49 @@ class RelAttnFn(torch.autograd.Function):
         _lib.check(lib.gtos_rel_dqk(_p(G), dqkv.data_ptr(), dqkv.data_ptr() + 4 * D, 3 * D, N, B, D, H, _st()),
                    "rel_dqk")
         d_rel = None
-        if ctx.needs_input_grad[2]:
+        if ctx.rel_acc is not None:
+            # all layers share one relation tensor: reduce this layer's gradient straight into the shared buffer
+            # (TMA reduce-add), which RelTokenFn hands to autograd once
+            acc = ctx.rel_acc
+            first = acc.buf is None
+            if first:
+                acc.buf = torch.empty(N, N, B, D, dtype=torch.float32, device=dev)
+            _lib.check(lib.gtos_rel_drel(_p(G), _p(WpermT), _p(acc.buf), 0 if first else 1, N, B, D, H, _st()), "rel_drel")
+        elif ctx.needs_input_grad[2]:
             d_rel = torch.empty(N, N, B, D, dtype=torch.float32, device=dev)
             _lib.check(lib.gtos_rel_drel(_p(G), _p(WpermT), _p(d_rel), 0, N, B, D, H, _st()), "rel_drel")
         ws_elems = lib.gtos_rel_dw_workspace(N, B, D, H)
         ws = None
         dW_rel = torch.empty(2 * D, D, dtype=torch.float32, device=dev)
         _lib.check(lib.gtos_rel_dw(_p(G), _p(relb), _p(dW_rel), _p(ws), ws_elems, N, B, D, H, _st()), "rel_dw")
-        dqkvb = cast_bf16(dqkv)
+        dqkvb, db_in = cast_colsum(dqkv)
         dW_in = gemm_nn(dqkvb, xb2, 3 * D, D)
-        db_in = colsum(dqkv)
         dx, _ = gemm_tn(dqkvb, Wit, D)
         return (dx.view(N, B, D), None, d_rel, None, None, None, dW_in, db_in, dW_rel, dW_out, db_out, None, None,
-                None)
+                None, None, None)
+
+
+class RelGradAcc:
+    """holds the shared d_relation buffer of one GraphTransformer pass"""
+
+    def __init__(self):
+        self.buf = None
+
+
+class RelTokenFn(torch.autograd.Function):
+    """relation -> scalar token consumed by every layer's RelAttnFn; its backward runs after all of them and returns
+    the gradient they accumulated in `acc.buf` (one [N,N,B,D] tensor instead of L tensors + L-1 adds)."""
+
+    @staticmethod
+    def forward(ctx, relation, acc):
+        ctx.acc = acc
+        ctx.set_materialize_grads(False)
+        return relation.new_zeros(())
+
+    @staticmethod
+    def backward(ctx, _g):
+        buf, ctx.acc.buf = ctx.acc.buf, None
+        return buf, None
 
 
 # --------------------------------------------------------------------------------------------
@@ -422,9 +464,8 @@ class MHAFn(torch.autograd.Function):
         hd = D // H
         dev = dout.device
         dout2 = dout.contiguous().view(T * B, D)
-        doutb = cast_bf16(dout2)
+        doutb, db_out = cast_colsum(dout2)
         dW_out = gemm_nn(doutb, attb, D, D)
-        db_out = colsum(dout2)
         datt, _ = gemm_tn(doutb, Wot, D)
         if off2:
             dropout_f32(datt, p, seed, off2, out=datt)
@@ -454,16 +495,15 @@ class MHAFn(torch.autograd.Function):
         _lib.check(lib.gtos_attn_bwd(C.byref(d), _st()), "attn_bwd(dec)")
         dW_in = torch.empty(3 * D, D, dtype=torch.float32, device=dev)
         if self_attn:
-            dprojb = cast_bf16(dproj)
+            dprojb, db_in = cast_colsum(dproj)
             gemm_nn(dprojb, qb2, 3 * D, D, out=dW_in)
-            db_in = colsum(dproj)
             dq_in, _ = gemm_tn(dprojb, Wit, D)
             dk_in = None
         else:
-            dpqb, dpkvb = cast_bf16(dpq), cast_bf16(dpkv)
+            (dpqb, dbq), (dpkvb, dbkv) = cast_colsum(dpq), cast_colsum(dpkv)
             gemm_nn(dpqb, qb2, D, D, out=dW_in[:D])
             gemm_nn(dpkvb, kb2, 2 * D, D, out=dW_in[D:])
-            db_in = torch.cat([colsum(dpq), colsum(dpkv)])
+            db_in = torch.cat([dbq, dbkv])
             dq_in, _ = gemm_tn(dpqb, Wit, D, K=D)                                   # Wt[:, :D]
             dk_in, _ = gemm_tn(dpkvb, Wit, D, K=2 * D, b_off=D)                     # Wt[:, D:3D]
             dk_in = dk_in.view(S, B, D)
@@ -558,9 +598,8 @@ class GRUBankFn(torch.autograd.Function):
         dev = dout.device
         rows = Lmax * R
         dout = dout.contiguous()
-        doutb = cast_bf16(dout)
+        doutb, db_out = cast_colsum(dout)
         dW_out = gemm_nn(doutb, finals_b, Dout, 2 * Hh)
-        db_out = colsum(dout)
         dfinals, _ = gemm_tn(doutb, Wo_t, 2 * Hh)                                   # [R, 2H]
         wgrads = [None] * (num_layers * 8)
         d_layer_out = None                                                         # [rows, 2H] fp32
@@ -638,9 +677,9 @@ class LinearFn(torch.autograd.Function):
         xb, Wt = ctx.saved_tensors
         shape, N, K, has_b = ctx.meta
         dy2 = dy.contiguous().view(-1, N)
-        dyb = cast_bf16(dy2)
+        dyb, db = cast_colsum(dy2)
         dW = gemm_nn(dyb, xb, N, K)
-        db = colsum(dy2) if has_b else None
+        db = db if has_b else None
         dx, _ = gemm_tn(dyb, Wt, K)
         return dx.view(shape), dW, db
 

@@ -40,6 +40,9 @@ int gtos_device_check(void);
 /* ---- operand staging -------------------------------------------------------------------------- */
 /* fp32 [rows, cols] (lds) -> bf16 [rows, ldd]; columns cols..ldd-1 are zero-filled (TMA needs 16 B rows) */
 int gtos_cast_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int32_t cols, void* stream);
+/* same cast plus sums[c] = sum_r src[r,c] in one pass (operand copy + bias gradient of a Linear backward) */
+int gtos_cast_colsum(const float* src, int64_t lds, void* dst, int64_t ldd, float* sums, int64_t rows, int32_t cols,
+                     void* stream);
 /* weight W fp32 [R,C] -> Wb bf16 [R, ldw] and/or Wt bf16 [C, ldt] (transpose, for input gradients).
  * rel_heads > 0: rows are reordered head-interleaved, per head [ra_h | rb_h], for
  * relation_in_proj.weight [2D, D] (graph_transformer.py:80,122) */

@@ -116,6 +116,12 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint64_t* bar,
       : "memory");
 }
 
+// ---- programmatic dependent launch (no-ops unless the kernel was launched with the PSS attribute) ------------
+// launch_dependents: the next kernel in the stream may start its prologue (barrier init, TMEM alloc, descriptor
+// prefetch) on SMs this grid has vacated;  wait: block until every prerequisite grid has completed and flushed.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- TMA stores (shared -> global), bulk-group completion -------------------------------
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(

@@ -163,6 +163,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  pdl_launch_dependents();  // our successor may begin its own prologue as SMs free up
+  pdl_wait();               // everything below touches global memory written by predecessors
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -606,6 +608,24 @@ int choose_rel_tiling(RelTiling* t, int N, int B, int D, int H) {
   return GTOS_OK;
 }
 
+// launch with programmatic stream serialization (PDL) unless GTOS_PDL=0
+template <class... KArgs, class... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  static const bool pdl = !(getenv("GTOS_PDL") && getenv("GTOS_PDL")[0] == '0');
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 static int g_num_sms = 0;
 static int num_sms() {
   if (g_num_sms == 0) {
@@ -715,7 +735,7 @@ static int launch_tn(const GemmTnArgs& a, cudaStream_t stream) {
   GTOS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   int grid = p.units < num_sms() ? p.units : num_sms();
   if (grid <= 0) return GTOS_OK;
-  kern<<<grid, GEMM_THREADS, smem_bytes, stream>>>(tmA, tmB, tmQ, tmK, tmO, p);
+  GTOS_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)smem_bytes, stream, tmA, tmB, tmQ, tmK, tmO, p));
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
 }
@@ -782,7 +802,7 @@ static int launch_gru_bn(const GruStepArgs& a, cudaStream_t stream) {
   GTOS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   int grid = p.units < num_sms() ? p.units : num_sms();
   if (grid <= 0) return GTOS_OK;
-  kern<<<grid, GEMM_THREADS, smem_bytes, stream>>>(tmA, tmB, tmH, tmH, tmB, p);
+  GTOS_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)smem_bytes, stream, tmA, tmB, tmH, tmH, tmB, p));
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
 }
@@ -854,6 +874,8 @@ gemm_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -1019,7 +1041,7 @@ static int launch_nn(const GemmNnArgs& a, int splits, int per, cudaStream_t stre
   else
     GTOS_CHECK_CUDA(cudaMemset2DAsync(a.out, sizeof(float) * a.ldo, 0, sizeof(float) * a.N, a.M, stream));
   dim3 grid(p.m_tiles * p.n_tiles, splits);
-  kern<<<grid, GEMM_THREADS, smem_bytes, stream>>>(tmA, tmB, p);
+  GTOS_CHECK_CUDA(launch_pdl(kern, grid, dim3(GEMM_THREADS), (size_t)smem_bytes, stream, tmA, tmB, p));
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
 }

@@ -32,12 +32,10 @@ class TokenGenerator(nn.Module):
         self.reset_parameters()
 
     def reset_parameters(self):
-        nn.init.normal_(self.transfer.weight, std=0.02)
-        nn.init.normal_(self.diverter.weight, std=0.02)
-        nn.init.normal_(self.generator.weight, std=0.02)
-        nn.init.constant_(self.diverter.bias, 0.)
-        nn.init.constant_(self.transfer.bias, 0.)
-        nn.init.constant_(self.generator.bias, 0.)
+        # N(0, 0.02) weights, zero biases (decoder.py:21-27)
+        for lin in (self.transfer, self.diverter, self.generator):
+            nn.init.normal_(lin.weight, std=0.02)
+            nn.init.zeros_(lin.bias)
 
     def forward(self, outs, graph_state, graph_padding_mask, copy_seq, target=None, work=False):
         p = self.dropout if self.training else 0.0
@@ -57,23 +55,18 @@ class TokenGenerator(nn.Module):
             token_loss = ops.token_nll(logits, gate_logits, alignment_weight, copy_seq, target,
                                        self.vocabs['predictable_token'].padding_idx)
             return token_loss.sum(0)
-        gen_gate, copy_gate = F.softmax(gate_logits, -1).chunk(2, dim=-1)
-        probs = gen_gate * F.softmax(logits, -1)
-        tot_ext = self.static_tot_ext if self.static_tot_ext is not None else 1 + copy_seq.max().item()
-        vocab_size = probs.size(-1)
-        if tot_ext - vocab_size > 0:
-            ext_probs = probs.new_zeros((1, 1, tot_ext - vocab_size)).expand(seq_len, bsz, -1)
-            probs = torch.cat([probs, ext_probs], -1)
-        index = copy_seq.transpose(0, 1).contiguous().view(1, bsz, -1).expand(seq_len, -1, -1)
-        copy_probs = (copy_gate * alignment_weight).view(seq_len, bsz, -1)
-        probs = probs.scatter_add(-1, index, copy_probs)
-        ll = torch.log(probs + 1e-12)
-        if work:
-            return ll
-        token_loss = -ll.gather(dim=-1, index=target.unsqueeze(-1)).squeeze(-1)
-        token_mask = torch.eq(target, self.vocabs['predictable_token'].padding_idx)
-        token_loss = token_loss.masked_fill(token_mask, 0.).sum(0)
-        return token_loss
+        # work=True (beam search): full log-probability table over the batch-extended vocabulary (decoder.py:44-59)
+        return self._log_prob_table(logits, gate_logits, alignment_weight, copy_seq)
+
+    def _log_prob_table(self, logits, gate_logits, align, copy_seq):
+        T, B, V = logits.shape
+        gate = torch.softmax(gate_logits, dim=-1)
+        width = self.static_tot_ext if self.static_tot_ext is not None else int(copy_seq.max()) + 1
+        table = logits.new_zeros(T, B, max(width, V))
+        table[..., :V] = torch.softmax(logits, dim=-1) * gate[..., :1]             # generate mass
+        slots = copy_seq.t().unsqueeze(0).expand(T, B, copy_seq.size(0))           # node s of graph b -> vocabulary slot
+        table.scatter_add_(-1, slots, align * gate[..., 1:])                       # copy mass
+        return (table + 1e-12).log()
 
 
 class DecodeLayer(nn.Module):

@@ -149,57 +149,5 @@ class MultiheadAttention(nn.Module):
         return self._in_proj(value, start=2 * self.embed_dim)
 
 
-# ---- host-side glue the reference callers import from this module (kept as plain PyTorch) ----
-def Embedding(num_embeddings, embedding_dim, padding_idx):
-    """reference: transformer.py:198-202"""
-    m = nn.Embedding(num_embeddings, embedding_dim, padding_idx=padding_idx)
-    nn.init.normal_(m.weight, std=0.02)
-    nn.init.constant_(m.weight[padding_idx], 0)
-    return m
-
-
-class SelfAttentionMask(nn.Module):
-    """reference: transformer.py:204-219 (bool instead of the torch-1.1 uint8 mask)"""
-
-    def __init__(self, device, init_size=100):
-        super().__init__()
-        self.weights = SelfAttentionMask.get_mask(init_size)
-        self.device = device
-
-    @staticmethod
-    def get_mask(size):
-        return torch.ones((size, size), dtype=torch.bool).triu_(1)
-
-    def forward(self, size):
-        if self.weights is None or size > self.weights.size(0):
-            self.weights = SelfAttentionMask.get_mask(size)
-        return self.weights[:size, :size].detach().to(self.device)
-
-
-class SinusoidalPositionalEmbedding(nn.Module):
-    """reference: transformer.py:240-281"""
-
-    def __init__(self, embedding_dim, device, init_size=512):
-        super().__init__()
-        self.embedding_dim = embedding_dim
-        self.weights = SinusoidalPositionalEmbedding.get_embedding(init_size, embedding_dim)
-        self.device = device
-
-    @staticmethod
-    def get_embedding(num_embeddings, embedding_dim):
-        half_dim = embedding_dim // 2
-        emb = math.log(10000) / (half_dim - 1)
-        emb = torch.exp(torch.arange(half_dim, dtype=torch.float) * -emb)
-        emb = torch.arange(num_embeddings, dtype=torch.float).unsqueeze(1) * emb.unsqueeze(0)
-        emb = torch.cat([torch.sin(emb), torch.cos(emb)], dim=1).view(num_embeddings, -1)
-        if embedding_dim % 2 == 1:
-            emb = torch.cat([emb, torch.zeros(num_embeddings, 1)], dim=1)
-        return emb
-
-    def forward(self, input, offset=0):
-        seq_len, bsz = input.size()
-        mx_position = seq_len + offset
-        if self.weights is None or mx_position > self.weights.size(0):
-            self.weights = SinusoidalPositionalEmbedding.get_embedding(mx_position, self.embedding_dim)
-        positions = offset + torch.arange(seq_len)
-        return self.weights.index_select(0, positions).unsqueeze(1).expand(-1, bsz, -1).detach().to(self.device)
+# ---- host-side glue the reference callers import from this module (plain PyTorch, not on the hot path) ----
+from .host_glue import Embedding, SelfAttentionMask, SinusoidalPositionalEmbedding  # noqa: E402,F401

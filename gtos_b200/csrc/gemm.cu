@@ -86,20 +86,6 @@ __device__ __forceinline__ void rel_tile_decode(const RelTiling& t, int tile, in
   j0 = jb * t.bj;
 }
 
-// 16 fp32 from a 128B-swizzled [rows x 32 float] TMA box: row `row`, floats [f0, f0+16), f0 % 16 == 0
-__device__ __forceinline__ void lds_sw128_16(const uint8_t* box, int row, int f0, float* out) {
-  const uint8_t* rp = box + row * 128;
-  int c0 = f0 >> 2;
-#pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    float4 v = *reinterpret_cast<const float4*>(rp + (((c0 + t) ^ (row & 7)) << 4));
-    out[4 * t + 0] = v.x;
-    out[4 * t + 1] = v.y;
-    out[4 * t + 2] = v.z;
-    out[4 * t + 3] = v.w;
-  }
-}
-
 // 16 bf16 (as fp32) from a 128B-swizzled [rows x 64 bf16] TMA box: row `row`, elements [e0, e0+16), e0 % 16 == 0
 __device__ __forceinline__ void lds_sw128_bf16x16(const uint8_t* box, int row, int e0, float* out) {
   const uint8_t* rp = box + row * 128;

@@ -11,6 +11,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = "/root/reference/generator"
+REFS = {"generator": "/root/reference/generator", "translator": "/root/reference/translator"}
 
 SCRIPT = r'''
 import sys, json, torch
@@ -28,19 +29,21 @@ m = G.Generator(vocabs, 32, 300, 32, 300, [(3, 256)], 128, 128, 100, 64, 2, 128,
 print(json.dumps({"mods": [type(m.graph_encoder).__module__, type(m.relation_encoder).__module__, type(m.decoder).__module__,
                            type(m.snt_encoder).__module__, type(m.concept_encoder).__module__],
                   "sd": {k: list(v.shape) for k, v in m.state_dict().items()}}))
-''' % dict(root=ROOT, ref=REF)
+'''
 
 
-def _run(mode):
-    out = subprocess.run([sys.executable, "-c", SCRIPT, mode], capture_output=True, text=True, timeout=300)
+def _run(mode, ref):
+    out = subprocess.run([sys.executable, "-c", SCRIPT % dict(root=ROOT, ref=ref), mode], capture_output=True, text=True,
+                         timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     import json
     return json.loads(out.stdout.strip().splitlines()[-1])
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (GPU box)")
-def test_reference_generator_builds_from_dropin_modules():
-    ours, ref = _run("dropin"), _run("reference")
+@pytest.mark.parametrize("task", ["generator", "translator"])
+def test_reference_generator_builds_from_dropin_modules(task):
+    ours, ref = _run("dropin", REFS[task]), _run("reference", REFS[task])
     assert ours["mods"][:4] == ["gtos_b200.graph_transformer", "gtos_b200.encoder", "gtos_b200.decoder",
                                 "gtos_b200.transformer"]
     assert ours["mods"][4] != "gtos_b200.encoder"          # TokenEncoder stays the reference's (out of scope)

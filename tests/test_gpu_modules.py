@@ -285,3 +285,23 @@ def test_dropout_training_mode_runs_and_is_unbiased(dev):
     assert not torch.equal(out, out2)              # new seed offset per call
     m.eval()
     assert torch.equal(m(x, rel), m(x, rel))
+
+
+def test_incremental_decode_step_matches_teacher_forced_pass(dev):
+    """generator/generator.py:133-142 drives the sentence layer one token at a time with kv = the prefix; a causal
+    full pass must give the same rows (the decode-time use of MultiheadAttention / TransformerLayer, T_q = 1)."""
+    from gtos_b200.transformer import TransformerLayer
+    gen = torch.Generator().manual_seed(SEED + 9)
+    T, S, B, D, H, F = 7, 12, 5, 128, 8, 256
+    layer = TransformerLayer(D, F, H, 0.0, with_external=True)
+    boost(layer, 2.0, gen)
+    layer = layer.to(dev).eval()
+    x = torch.randn(T, B, D, generator=gen).to(dev)
+    mem = torch.randn(S, B, D, generator=gen).to(dev)
+    smask = pad_mask([S, 7, 9, 12, 6], S).to(dev)
+    cm = O.causal_mask(T).to(dev)
+    with torch.no_grad():
+        full, _, _ = layer(x, self_attn_mask=cm, external_memories=mem, external_padding_mask=smask)
+        for t in range(T):
+            step, _, _ = layer(x[t:t + 1], kv=x[:t + 1], external_memories=mem, external_padding_mask=smask)
+            assert rel_err(step[0], full[t]) < 2e-3, t

@@ -103,17 +103,27 @@ __device__ __forceinline__ void lds_sw128_bf16x16(const uint8_t* box, int row, i
   }
 }
 
-template <int BN, int MODE>
+// CG = 1: one CTA per 128 x BN tile.  CG = 2 (relation modes): a CTA PAIR (cluster of 2, cta_group::2) works on two
+// relation tiles at once: each CTA stages its own 128-row A tile and HALF of the BN weight rows, the leader issues
+// M=256 MMAs that read both CTAs' shared memory, and each CTA's TMEM receives the accumulator of its own 128 rows.
+// Halves the weight traffic per FLOP and the shared-memory operand traffic per SM.
+template <int BN, int MODE, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmO, const TnDev p) {
   constexpr bool REL = (MODE == MODE_SCORE || MODE == MODE_GRAD);
+  static_assert(CG == 1 || REL, "CTA pairs are only wired up for the relation modes");
   constexpr int OUT_STAGE_BYTES = 2 * BM * 128;  // two [128 rows x 128 B] swizzled staging tiles
-  constexpr int B_STAGE_BYTES = BN * BK * 2;
+  constexpr int B_STAGE_BYTES = (BN / CG) * BK * 2;
   constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  constexpr uint32_t IDESC = make_idesc_bf16(BM, BN, 0, 0);
+  constexpr uint32_t IDESC = make_idesc_bf16(BM * CG, BN, 0, 0);
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = (rank == 0);
+  // pair scheduling: both CTAs of a pair walk the same unit list; CTA `rank` owns relation tile 2*pair_tile + rank
+  const int sched_id = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int sched_n = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -133,20 +143,23 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tma_prefetch_desc(&tmK);
     }
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->full[s], CG);      // pair: leader's arrive.expect_tx + the peer producer's remote arrive
       mbar_init(&bars->empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bars->tfull[s], 1);
-      mbar_init(&bars->tempty[s], 4);
+      mbar_init(&bars->tempty[s], 4 * CG);  // pair: epilogue warps of BOTH CTAs release the leader's accumulator stage
       mbar_init(&bars->qfull[s], 1);
       mbar_init(&bars->qempty[s], 4);
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(&bars->tmem_base, TMEM_COLS);
+  if (warp == 1) {
+    if (CG == 2) tmem_alloc_2cta(&bars->tmem_base, TMEM_COLS); else tmem_alloc(&bars->tmem_base, TMEM_COLS);
+  }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();        // peer barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
   pdl_launch_dependents();  // our successor may begin its own prologue as SMs free up
@@ -159,11 +172,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t ph = 0;
       int qs = 0;
       uint32_t qph = 0;
-      for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
-        const int m_blk = unit / p.n_tiles, n_blk = unit % p.n_tiles;
+      for (int unit = sched_id; unit < p.units; unit += sched_n) {
+        const int m_blk = (unit / p.n_tiles) * CG + (int)rank, n_blk = unit % p.n_tiles;
         int b = 0, j0 = 0, i0 = 0;
         if (REL) {
-          rel_tile_decode(p.rt, m_blk, b, j0, i0);
+          rel_tile_decode(p.rt, m_blk, b, j0, i0);   // a dummy tile past the end decodes to b == B: TMA zero-fills it
           // q / k slices for this (tile, head group): dims [n_blk*BN/2, +BN/2)
           wait_bar(&bars->qempty[qs], qph ^ 1);
           mbar_expect_tx(&bars->qfull[qs], (uint32_t)((BN / 128) * (p.rt.bi + p.rt.bj) * 128));
@@ -180,7 +193,16 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           wait_bar(&bars->empty[s], ph ^ 1);
           uint8_t* sa = smem + s * STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
-          if (REL) {
+          if (REL && CG == 2) {
+            if (leader)
+              mbar_expect_tx(&bars->full[s], (uint32_t)(2 * (p.rt.bi * p.rt.bj * 128 + B_STAGE_BYTES)));
+            else
+              mbar_arrive_remote(&bars->full[s], 0);
+            tma_load_4d_2cta(&tmA, &bars->full[s], sa, kb * BK, b, i0, j0);
+            tma_load_2d_2cta(&tmB, &bars->full[s], sb, kb * BK, n_blk * BN + (int)rank * (BN / 2));
+            if (++s == p.stages) { s = 0; ph ^= 1; }
+            continue;
+          } else if (REL) {
             mbar_expect_tx(&bars->full[s], (uint32_t)(p.rt.bi * p.rt.bj * 128 + B_STAGE_BYTES));
             tma_load_4d(&tmA, &bars->full[s], sa, kb * BK, b, i0, j0);
           } else if (MODE == MODE_GRU) {
@@ -200,12 +222,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
+    if (lane == 0 && leader) {
       int s = 0;
       uint32_t ph = 0;
       int as = 0;
       uint32_t aph = 0;
-      for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
+      for (int unit = sched_id; unit < p.units; unit += sched_n) {
         wait_bar(&bars->tempty[as], aph ^ 1);
         tc_fence_after();
         const uint32_t tacc = tmem_base + as * BN;
@@ -218,12 +240,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 bf16 = 32 bytes inside the 128B swizzle row: +2 in the (addr>>4) field
-            umma_bf16(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) != 0 ? 1u : 0u);
+            if (CG == 2)
+              umma_bf16_2cta(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) != 0 ? 1u : 0u);
+            else
+              umma_bf16(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&bars->empty[s]);
+          if (CG == 2) umma_commit_2cta(&bars->empty[s]); else umma_commit(&bars->empty[s]);
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
-        umma_commit(&bars->tfull[as]);
+        if (CG == 2) umma_commit_2cta(&bars->tfull[as]); else umma_commit(&bars->tfull[as]);
         if (++as == 2) { as = 0; aph ^= 1; }
       }
     }
@@ -236,8 +261,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int qs = 0;
     uint32_t qph = 0;
     int kc = 0;  // running output-chunk counter: staging buffer = kc & 1
-    for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
-      const int m_blk = unit / p.n_tiles, n_blk = unit % p.n_tiles;
+    for (int unit = sched_id; unit < p.units; unit += sched_n) {
+      const int m_blk = (unit / p.n_tiles) * CG + (int)rank, n_blk = unit % p.n_tiles;
       // MODE_GRU: fetch this thread's slice of the previous state, the bias block and the length flag while the
       // tensor core is still producing the accumulator (4 epilogue warps cannot hide DRAM latency otherwise)
       [[maybe_unused]] float gru_hp[MODE == MODE_GRU ? BN / 4 : 1];
@@ -458,7 +483,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int bi = p.rt.bi;
         const int jj = r / bi, ii = r - jj * bi;
         const int i = i0 + ii, j = j0 + jj;
-        const bool valid = (jj < p.rt.bj) && (i < p.rt.N) && (j < p.rt.N);
+        const bool valid = (jj < p.rt.bj) && (i < p.rt.N) && (j < p.rt.N) && (m_blk < p.m_tiles);
         const int jjc = jj < p.rt.bj ? jj : p.rt.bj - 1;  // keep smem reads inside the k boxes
         const uint8_t* qb = qk_base + qs * p.qk_stage_bytes;
         const uint8_t* kbx = qb + (BN / 128) * p.bi8 * 128;
@@ -540,7 +565,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(&bars->tempty[as]);
+        if (CG == 2 && !leader) mbar_arrive_remote(&bars->tempty[as], 0); else mbar_arrive(&bars->tempty[as]);
         if (REL) mbar_arrive(&bars->qempty[qs]);
       }
       if (++as == 2) { as = 0; aph ^= 1; }
@@ -551,10 +576,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();   // the peer may still multicast into our barriers / read our smem until here
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (CG == 2) tmem_dealloc_2cta(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -596,7 +622,8 @@ int choose_rel_tiling(RelTiling* t, int N, int B, int D, int H) {
 
 // launch with programmatic stream serialization (PDL) unless GTOS_PDL=0
 template <class... KArgs, class... Args>
-static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              int cluster, Args... args) {
   static const bool pdl = !(getenv("GTOS_PDL") && getenv("GTOS_PDL")[0] == '0');
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -604,11 +631,22 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (pdl) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
+  cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
@@ -644,7 +682,7 @@ int make_rel_tmaps(const RelTiling& rt, const void* relb, const void* q, const v
   return GTOS_OK;
 }
 
-template <int BN, int MODE>
+template <int BN, int MODE, int CG = 1>
 static int launch_tn(const GemmTnArgs& a, cudaStream_t stream) {
   constexpr bool REL = (MODE == MODE_SCORE || MODE == MODE_GRAD);
   TnDev p;
@@ -672,9 +710,9 @@ static int launch_tn(const GemmTnArgs& a, cudaStream_t stream) {
     tmQ = tmA;
     tmK = tmA;
   }
-  e = make_tmap_2d_bf16(&tmB, a.Bm, (uint64_t)a.N, (uint64_t)a.K, (uint64_t)a.ldb, BN);
+  e = make_tmap_2d_bf16(&tmB, a.Bm, (uint64_t)a.N, (uint64_t)a.K, (uint64_t)a.ldb, BN / CG);
   if (e) return e;
-  p.units = p.m_tiles * p.n_tiles;
+  p.units = ((p.m_tiles + CG - 1) / CG) * p.n_tiles;   // CG = 2: units are (tile pair, n block)
   // ---- output path: TMA stores from swizzled staging tiles where the layout allows it ----
   CUtensorMap tmO = tmB;
   constexpr int OUT_STAGE_BYTES = 2 * BM * 128;
@@ -705,7 +743,7 @@ static int launch_tn(const GemmTnArgs& a, cudaStream_t stream) {
     if (e) return e;
     p.tma_out = 1;
   }
-  constexpr int STAGE_BYTES = A_STAGE_BYTES + BN * BK * 2;
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + (BN / CG) * BK * 2;
   const int budget = 227 * 1024 - 1024 /*align*/ - (int)sizeof(PipeBars) - (REL ? 2 * p.qk_stage_bytes : 0) -
                      (p.tma_out ? OUT_STAGE_BYTES : 0);
   int stages = budget / STAGE_BYTES;
@@ -717,11 +755,11 @@ static int launch_tn(const GemmTnArgs& a, cudaStream_t stream) {
   p.stages = stages;
   const int smem_bytes = 1024 + stages * STAGE_BYTES + (REL ? 2 * p.qk_stage_bytes : 0) +
                          (p.tma_out ? OUT_STAGE_BYTES : 0) + (int)sizeof(PipeBars);
-  auto kern = gemm_tn_kernel<BN, MODE>;
+  auto kern = gemm_tn_kernel<BN, MODE, CG>;
   GTOS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-  int grid = p.units < num_sms() ? p.units : num_sms();
+  int grid = p.units * CG < num_sms() ? p.units * CG : (num_sms() / CG) * CG;
   if (grid <= 0) return GTOS_OK;
-  GTOS_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)smem_bytes, stream, tmA, tmB, tmQ, tmK, tmO, p));
+  GTOS_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)smem_bytes, stream, CG, tmA, tmB, tmQ, tmK, tmO, p));
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
 }
@@ -731,8 +769,9 @@ int launch_gemm_tn(int mode, const GemmTnArgs& a, cudaStream_t stream) {
                a.K, a.lda, a.ldb);
   GTOS_REQUIRE(!a.addend || (mode == MODE_PLAIN && a.out_f32 && !a.out_bf16 && !a.accumulate && a.ldo % 4 == 0),
                "gemm_tn: addend needs the fp32 TMA-store epilogue");
-  if (mode == MODE_SCORE) return launch_tn<256, MODE_SCORE>(a, stream);
-  if (mode == MODE_GRAD) return launch_tn<256, MODE_GRAD>(a, stream);
+  static const bool pair = !(getenv("GTOS_REL_2CTA") && getenv("GTOS_REL_2CTA")[0] == '0');
+  if (mode == MODE_SCORE) return pair ? launch_tn<256, MODE_SCORE, 2>(a, stream) : launch_tn<256, MODE_SCORE, 1>(a, stream);
+  if (mode == MODE_GRAD) return pair ? launch_tn<256, MODE_GRAD, 2>(a, stream) : launch_tn<256, MODE_GRAD, 1>(a, stream);
   if (mode == MODE_DREL) return launch_tn<256, MODE_DREL>(a, stream);
   // plain: pick the N tile with the lowest estimated time = waves x (mainloop + epilogue + fixed cost), in SM cycles
   const long mt = (a.M + BM - 1) / BM;
@@ -784,11 +823,11 @@ static int launch_gru_bn(const GruStepArgs& a, cudaStream_t stream) {
   if (stages > 6) stages = 6;
   p.stages = stages;
   const int smem_bytes = 1024 + stages * STAGE_BYTES + 2 * BN * 4 + (int)sizeof(PipeBars);
-  auto kern = gemm_tn_kernel<BN, MODE_GRU>;
+  auto kern = gemm_tn_kernel<BN, MODE_GRU, 1>;
   GTOS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   int grid = p.units < num_sms() ? p.units : num_sms();
   if (grid <= 0) return GTOS_OK;
-  GTOS_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)smem_bytes, stream, tmA, tmB, tmH, tmH, tmB, p));
+  GTOS_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)smem_bytes, stream, 1, tmA, tmB, tmH, tmH, tmB, p));
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
 }
@@ -1027,7 +1066,7 @@ static int launch_nn(const GemmNnArgs& a, int splits, int per, cudaStream_t stre
   else
     GTOS_CHECK_CUDA(cudaMemset2DAsync(a.out, sizeof(float) * a.ldo, 0, sizeof(float) * a.N, a.M, stream));
   dim3 grid(p.m_tiles * p.n_tiles, splits);
-  GTOS_CHECK_CUDA(launch_pdl(kern, grid, dim3(GEMM_THREADS), (size_t)smem_bytes, stream, tmA, tmB, p));
+  GTOS_CHECK_CUDA(launch_pdl(kern, grid, dim3(GEMM_THREADS), (size_t)smem_bytes, stream, 1, tmA, tmB, p));
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
 }

@@ -143,7 +143,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tma_prefetch_desc(&tmK);
     }
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&bars->full[s], CG);      // pair: leader's arrive.expect_tx + the peer producer's remote arrive
+      mbar_init(&bars->full[s], 1);       // pair: only the leader arrives (expect_tx covers both CTAs' bytes)
       mbar_init(&bars->empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -194,10 +194,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* sa = smem + s * STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
           if (REL && CG == 2) {
-            if (leader)
-              mbar_expect_tx(&bars->full[s], (uint32_t)(2 * (p.rt.bi * p.rt.bj * 128 + B_STAGE_BYTES)));
-            else
-              mbar_arrive_remote(&bars->full[s], 0);
+            // the peer's loads complete_tx on the leader's barrier too; it cannot run ahead of the leader's phase because
+            // it only reuses a stage after the leader's MMA committed it (multicast) - so a cluster-scope arrive
+            // (a membar per k-block) is not needed
+            if (leader) mbar_expect_tx(&bars->full[s], (uint32_t)(2 * (p.rt.bi * p.rt.bj * 128 + B_STAGE_BYTES)));
             tma_load_4d_2cta(&tmA, &bars->full[s], sa, kb * BK, b, i0, j0);
             tma_load_2d_2cta(&tmB, &bars->full[s], sb, kb * BK, n_blk * BN + (int)rank * (BN / 2));
             if (++s == p.stages) { s = 0; ph ^= 1; }

@@ -103,8 +103,15 @@ class Clocks:
         mx = max([int(r[2]) for r in self.rows if len(r) >= 9 and r[2].isdigit()] or [0])
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower() == "active"})
+        pw = []
+        for r in self.rows:
+            try:
+                pw.append(float(r[3]))
+            except (ValueError, IndexError):
+                pass
+        pw.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "power_w": pw[len(pw) // 2] if pw else None}
 
 
 def peaks():
@@ -497,7 +504,24 @@ def breakdown(args, w, cfg, model, static, meta, dev, lib):
     t_dw = time_fn(lambda: _lib.check(lib.gtos_rel_dw(G.data_ptr(), relb.data_ptr(), dW.data_ptr(), ws.data_ptr(), ws_n,
                                                       N, B, D, H, st)))
     f = meta["pairs"] * 4 * D * D / 1e12
-    out["relation_kernels"] = {"rel_score_ms": ms_k, "rel_grad_ms": t_grad, "rel_drel_ms": t_drel, "rel_dw_ms": t_dw,
+    # the same score kernel launched back to back for ~1.5 s with the clocks sampler on: the burst number above is
+    # taken over 20 launches (2 ms); this one shows what power / clock management leaves of it
+    n_sus = max(50, int(1500.0 / ms_k))
+    ck = Clocks(torch.cuda.current_device())
+    for _ in range(20):
+        k_score()
+    torch.cuda.synchronize()
+    ck.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n_sus):
+        k_score()
+    e1.record()
+    torch.cuda.synchronize()
+    sus_ms = e0.elapsed_time(e1) / n_sus
+    sus = ck.stop()
+    sus.update({"launches": n_sus, "ms_per_launch": sus_ms, "tflops": kflops / (sus_ms * 1e-3) / 1e12})
+    out["relation_kernels"] = {"rel_score_sustained": sus,"rel_score_ms": ms_k, "rel_grad_ms": t_grad, "rel_drel_ms": t_drel, "rel_dw_ms": t_dw,
                                "tflops": {"rel_score": f / (ms_k * 1e-3), "rel_grad": f / (t_grad * 1e-3),
                                           "rel_drel": f / (t_drel * 1e-3), "rel_dw": f / (t_dw * 1e-3)}}
     return out

@@ -66,6 +66,7 @@ struct TnDev {
   int bi8, bj8;        // q / k box rows rounded up to 8 (1024-byte swizzle atoms)
   int qk_stage_bytes;  // 4*(bi8+bj8)*128
   int tma_out;         // epilogue stages tiles in shared memory and writes them with TMA stores
+  int dbg;             // GTOS_DBG bit 0: relation epilogues skip their body (pipeline-rate experiment, wrong results)
   // MODE_GRU
   int kx_blocks;       // k-blocks that come from x_t (tmA); the rest come from h_prev (tmQ slot)
   int gru_H, gru_t;
@@ -107,14 +108,24 @@ __device__ __forceinline__ void lds_sw128_bf16x16(const uint8_t* box, int row, i
 // relation tiles at once: each CTA stages its own 128-row A tile and HALF of the BN weight rows, the leader issues
 // M=256 MMAs that read both CTAs' shared memory, and each CTA's TMEM receives the accumulator of its own 128 rows.
 // Halves the weight traffic per FLOP and the shared-memory operand traffic per SM.
+// relation modes run TWO epilogue warpgroups (warps 2-5 and 6-9; both map onto TMEM lane quarters warp & 3): each
+// takes half of the unit's heads, so the score / gradient math of a unit takes half as long as its MMAs
+template <int MODE>
+constexpr int tn_epi_wgs() { return (MODE == MODE_SCORE || MODE == MODE_GRAD) ? 2 : 1; }
+template <int MODE>
+constexpr int tn_threads() { return 64 + 128 * tn_epi_wgs<MODE>(); }
+template <int MODE>
+constexpr int tn_out_stage_bytes() { return (MODE == MODE_GRAD ? 4 : 2) * BM * 128; }  // [128 rows x 128 B] swizzled tiles
+
 template <int BN, int MODE, int CG>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(tn_threads<MODE>(), 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmO, const TnDev p) {
   constexpr bool REL = (MODE == MODE_SCORE || MODE == MODE_GRAD);
   static_assert(CG == 1 || REL, "CTA pairs are only wired up for the relation modes");
-  constexpr int OUT_STAGE_BYTES = 2 * BM * 128;  // two [128 rows x 128 B] swizzled staging tiles
+  constexpr int OUT_STAGE_BYTES = tn_out_stage_bytes<MODE>();  // two staging tiles per epilogue warpgroup
+  constexpr int EPI_WGS = tn_epi_wgs<MODE>();
   constexpr int B_STAGE_BYTES = (BN / CG) * BK * 2;
   constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
@@ -148,9 +159,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bars->tfull[s], 1);
-      mbar_init(&bars->tempty[s], 4 * CG);  // pair: epilogue warps of BOTH CTAs release the leader's accumulator stage
+      mbar_init(&bars->tempty[s], 4 * CG * EPI_WGS);  // pair: epilogue warps of BOTH CTAs release the leader's accumulator stage
       mbar_init(&bars->qfull[s], 1);
-      mbar_init(&bars->qempty[s], 4);
+      mbar_init(&bars->qempty[s], 4 * EPI_WGS);
     }
     fence_barrier_init();
   }
@@ -253,8 +264,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ================= epilogue (warps 2..5) =================
+    // ================= epilogue (warps 2..5, relation modes: also 6..9) =================
     const int quarter = warp & 3;
+    [[maybe_unused]] const int wg = (warp - 2) >> 2;
     const int r = quarter * 32 + lane;  // accumulator row == TMEM lane
     int as = 0;
     uint32_t aph = 0;
@@ -284,6 +296,32 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         named_bar_sync(1, 128);  // bias block visible to all epilogue warps
+      }
+      // relation modes: decode the tile and (MODE_GRAD) fetch this thread's d(score) values of the warpgroup's heads
+      // while the tensor core is still producing the accumulator
+      [[maybe_unused]] int rb_ = 0, rj0 = 0, ri0 = 0, rjj = 0, rii = 0, rch0 = 0, rnch = 0;
+      [[maybe_unused]] bool rvalid = false;
+      [[maybe_unused]] long rs0 = 0;          // scores index of (b, head 0 of this unit, j, i)
+      [[maybe_unused]] float gpre[4] = {0.f, 0.f, 0.f, 0.f};
+      if constexpr (REL) {
+        constexpr int NCH = (BN / 2) / 16;    // 16-dim chunks per unit
+        rel_tile_decode(p.rt, m_blk, rb_, rj0, ri0);
+        const int bi = p.rt.bi;
+        rjj = r / bi; rii = r - rjj * bi;
+        const int i = ri0 + rii, j = rj0 + rjj;
+        rvalid = (rjj < p.rt.bj) && (i < p.rt.N) && (j < p.rt.N) && (m_blk < p.m_tiles);
+        const int hd = p.rt.hd;
+        const int heads_blk = (BN / 2) / hd;
+        rch0 = heads_blk >= 2 ? wg * (NCH / 2) : 0;
+        rnch = (p.dbg & 1) ? 0 : (heads_blk >= 2 ? NCH / 2 : (wg == 0 ? NCH : 0));
+        rs0 = (((long)rb_ * p.rt.H + n_blk * heads_blk) * p.rt.N + j) * p.rt.N + i;
+        if constexpr (MODE == MODE_GRAD) {
+          const int h0 = (rch0 * 16) / hd;                  // first head of this warpgroup inside the unit
+          const int nh = (rnch * 16 + hd - 1) / hd;         // heads it owns (<= 4)
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (rvalid && q < nh) gpre[q] = p.dscores[rs0 + (long)(h0 + q) * p.rt.N * p.rt.N] * p.rt.scale;
+        }
       }
       wait_bar(&bars->tfull[as], aph);
       if (REL) wait_bar(&bars->qfull[qs], qph);
@@ -477,59 +515,74 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         }  // !tma_out
       } else {
-        // ---- relation epilogues: thread owns pair (j0+jj, i0+ii, b) ----
-        int b, j0, i0;
-        rel_tile_decode(p.rt, m_blk, b, j0, i0);
-        const int bi = p.rt.bi;
-        const int jj = r / bi, ii = r - jj * bi;
-        const int i = i0 + ii, j = j0 + jj;
-        const bool valid = (jj < p.rt.bj) && (i < p.rt.N) && (j < p.rt.N) && (m_blk < p.m_tiles);
-        const int jjc = jj < p.rt.bj ? jj : p.rt.bj - 1;  // keep smem reads inside the k boxes
+        // ---- relation epilogues: thread owns pair (j0+jj, i0+ii, b); warpgroup wg owns chunks [rch0, rch0+rnch) ----
+        constexpr int NCH = (BN / 2) / 16;
+        const int jjc = rjj < p.rt.bj ? rjj : p.rt.bj - 1;  // keep smem reads inside the k boxes
         const uint8_t* qb = qk_base + qs * p.qk_stage_bytes;
         const uint8_t* kbx = qb + (BN / 128) * p.bi8 * 128;
         const int hd = p.rt.hd;
-        const int heads_blk = (BN / 2) / hd;
-#pragma unroll 1
-        for (int hh = 0; hh < heads_blk; ++hh) {
-          const int h = n_blk * heads_blk + hh;
-          const long sidx = (((long)b * p.rt.H + h) * p.rt.N + j) * p.rt.N + i;
-          float acc = 0.f;
-          float g = 0.f;
-          if constexpr (MODE == MODE_GRAD) g = valid ? p.dscores[sidx] * p.rt.scale : 0.f;
-#pragma unroll 1
-          for (int c = 0; c < hd; c += 16) {
-            float ra[16], rb[16], qv[16], kv[16];
-            tmem_ld16(tacc + hh * 2 * hd + c, ra);
-            tmem_ld16(tacc + hh * 2 * hd + hd + c, rb);
-            const int dl = hh * hd + c;  // dim inside this unit's BN/2-wide slice
-            lds_sw128_bf16x16(qb + (dl >> 6) * p.bi8 * 128, ii, dl & 63, qv);
+        const int h0 = (rch0 * 16) / hd;
+        const long hstride = (long)p.rt.N * p.rt.N;
+        const bool valid = rvalid;
+        [[maybe_unused]] uint8_t* stage_wg = out_stage + wg * (2 * BM * 128);
+        [[maybe_unused]] const bool issuer = (quarter == 2 && lane == 0);   // first warp of each warpgroup
+        float acc = 0.f;
+        float g = 0.f;
+        float ra[2][16], rb[2][16];
+        // software pipeline: the TMEM loads of chunk t+1 are in flight while chunk t is being computed
+        auto issue_ld = [&](int it, float* a_, float* b_) {
+          const int dl = it * 16;
+          const int hh = dl / hd, c = dl - hh * hd;
+          tmem_ld16(tacc + hh * 2 * hd + c, a_);
+          tmem_ld16(tacc + hh * 2 * hd + hd + c, b_);
+        };
+        if (rnch > 0) issue_ld(rch0, ra[0], rb[0]);
+#pragma unroll
+        for (int t = 0; t < NCH; ++t) {
+          if (t < rnch) {
+            const int it = rch0 + t;
+            const int dl = it * 16;                  // dim inside this unit's BN/2-wide slice
+            const int hh = dl / hd, c = dl - hh * hd;
+            float qv[16], kv[16];
+            lds_sw128_bf16x16(qb + (dl >> 6) * p.bi8 * 128, rii, dl & 63, qv);
             lds_sw128_bf16x16(kbx + (dl >> 6) * p.bj8 * 128, jjc, dl & 63, kv);
             tmem_ld_wait();
+            if (t + 1 < rnch) issue_ld(it + 1, ra[(t + 1) & 1], rb[(t + 1) & 1]);
+            const float* ra_ = ra[t & 1];
+            const float* rb__ = rb[t & 1];
+            if (c == 0) {
+              acc = 0.f;
+              if constexpr (MODE == MODE_GRAD) {
+                const int hq = hh - h0;
+                g = hq == 0 ? gpre[0] : hq == 1 ? gpre[1] : hq == 2 ? gpre[2] : gpre[3];
+              }
+            }
             if constexpr (MODE == MODE_SCORE) {
 #pragma unroll
-              for (int t = 0; t < 16; ++t) acc = fmaf(qv[t] + ra[t], kv[t] + rb[t], acc);
+              for (int u = 0; u < 16; ++u) acc = fmaf(qv[u] + ra_[u], kv[u] + rb__[u], acc);
+              if (c + 16 == hd && valid) p.scores[rs0 + (long)hh * hstride] = acc * p.rt.scale;
             } else {
               // G columns (permuted order): [d(q+ra) = g*(k+rb) | d(k+rb) = g*(q+ra)]
               uint32_t wx[8], wy[8];
 #pragma unroll
-              for (int t = 0; t < 8; ++t) {
-                float x0 = qv[2 * t] + ra[2 * t], x1 = qv[2 * t + 1] + ra[2 * t + 1];
-                float y0 = kv[2 * t] + rb[2 * t], y1 = kv[2 * t + 1] + rb[2 * t + 1];
-                wx[t] = valid ? pack_bf16x2(g * y0, g * y1) : 0u;
-                wy[t] = valid ? pack_bf16x2(g * x0, g * x1) : 0u;
+              for (int u = 0; u < 8; ++u) {
+                float x0 = qv[2 * u] + ra_[2 * u], x1 = qv[2 * u + 1] + ra_[2 * u + 1];
+                float y0 = kv[2 * u] + rb__[2 * u], y1 = kv[2 * u + 1] + rb__[2 * u + 1];
+                wx[u] = valid ? pack_bf16x2(g * y0, g * y1) : 0u;
+                wy[u] = valid ? pack_bf16x2(g * x0, g * x1) : 0u;
               }
               const int gcx = hh * 2 * hd + c, gcy = gcx + hd;   // G columns inside this 256-wide block
               if (p.tma_out) {
-                // stage 64-column (128-byte) spans of G in swizzled smem tiles, one TMA store per finished span
+                // stage 64-column (128-byte) spans of G in this warpgroup's two swizzled smem tiles, one TMA store
+                // per finished span
                 const bool wide = hd >= 64;                      // X and Y halves live in different spans
-                const bool issuer = (warp == 2 && lane == 0);
-                uint8_t* bx = out_stage + (wide ? 0 : ((gcx >> 6) & 1)) * (BM * 128);
-                uint8_t* by = out_stage + (wide ? 1 : ((gcy >> 6) & 1)) * (BM * 128);
+                uint8_t* bx = stage_wg + (wide ? 0 : ((gcx >> 6) & 1)) * (BM * 128);
+                uint8_t* by = stage_wg + (wide ? 1 : ((gcy >> 6) & 1)) * (BM * 128);
                 if ((gcx & 63) == 0) {                           // first chunk of a span: buffer is reused
                   if (issuer) {
                     if (wide) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
                   }
-                  named_bar_sync(1, 128);
+                  named_bar_sync(1 + 2 * wg, 128);
                 }
                 uint8_t* rx = bx + r * 128;
                 uint8_t* ry = by + r * 128;
@@ -540,7 +593,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 *reinterpret_cast<uint4*>(ry + (((cy + 1) ^ (r & 7)) << 4)) = make_uint4(wy[4], wy[5], wy[6], wy[7]);
                 if (((gcy + 16) & 63) == 0) {                    // span(s) complete
                   fence_proxy_async();
-                  named_bar_sync(2, 128);
+                  named_bar_sync(2 + 2 * wg, 128);
                   if (issuer) {
                     if (wide) tma_store_2d(&tmO, bx, n_blk * BN + (gcx & ~63), m_blk * BM);
                     tma_store_2d(&tmO, by, n_blk * BN + (gcy & ~63), m_blk * BM);
@@ -548,16 +601,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   }
                 }
               } else {
-              __nv_bfloat16* grow = p.G + ((long)m_blk * BM + r) * (2 * p.rt.D) + (long)n_blk * BN + hh * 2 * hd + c;
-              *reinterpret_cast<uint4*>(grow) = make_uint4(wx[0], wx[1], wx[2], wx[3]);
-              *reinterpret_cast<uint4*>(grow + 8) = make_uint4(wx[4], wx[5], wx[6], wx[7]);
-              *reinterpret_cast<uint4*>(grow + hd) = make_uint4(wy[0], wy[1], wy[2], wy[3]);
-              *reinterpret_cast<uint4*>(grow + hd + 8) = make_uint4(wy[4], wy[5], wy[6], wy[7]);
+                __nv_bfloat16* grow = p.G + ((long)m_blk * BM + r) * (2 * p.rt.D) + (long)n_blk * BN + gcx;
+                *reinterpret_cast<uint4*>(grow) = make_uint4(wx[0], wx[1], wx[2], wx[3]);
+                *reinterpret_cast<uint4*>(grow + 8) = make_uint4(wx[4], wx[5], wx[6], wx[7]);
+                *reinterpret_cast<uint4*>(grow + hd) = make_uint4(wy[0], wy[1], wy[2], wy[3]);
+                *reinterpret_cast<uint4*>(grow + hd + 8) = make_uint4(wy[4], wy[5], wy[6], wy[7]);
               }
             }
-          }
-          if constexpr (MODE == MODE_SCORE) {
-            if (valid) p.scores[sidx] = acc * p.rt.scale;
           }
         }
       }
@@ -571,7 +621,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (++as == 2) { as = 0; aph ^= 1; }
       if (REL) { if (++qs == 2) { qs = 0; qph ^= 1; } }
     }
-    if (p.tma_out && warp == 2 && lane == 0) tma_store_wait_all();  // smem must outlive the bulk stores
+    if (p.tma_out && quarter == 2 && lane == 0) tma_store_wait_all();  // smem must outlive the bulk stores
   }
 
   tc_fence_before();
@@ -694,6 +744,8 @@ static int launch_tn(const GemmTnArgs& a, cudaStream_t stream) {
   p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a.out_bf16); p.ldob = a.ldob;
   p.relu = a.relu; p.accumulate = a.accumulate; p.addend = a.addend; p.ldadd = a.ldadd;
   p.rt = a.rt; p.scores = a.scores; p.dscores = a.dscores; p.G = reinterpret_cast<__nv_bfloat16*>(a.G);
+  static const int dbg = getenv("GTOS_DBG") ? atoi(getenv("GTOS_DBG")) : 0;
+  p.dbg = dbg;
   CUtensorMap tmA, tmB, tmQ, tmK;
   int e;
   if (REL) {
@@ -715,8 +767,9 @@ static int launch_tn(const GemmTnArgs& a, cudaStream_t stream) {
   p.units = ((p.m_tiles + CG - 1) / CG) * p.n_tiles;   // CG = 2: units are (tile pair, n block)
   // ---- output path: TMA stores from swizzled staging tiles where the layout allows it ----
   CUtensorMap tmO = tmB;
-  constexpr int OUT_STAGE_BYTES = 2 * BM * 128;
+  constexpr int OUT_STAGE_BYTES = tn_out_stage_bytes<MODE>();
   p.tma_out = 0;
+  static const bool grad_tma = !(getenv("GTOS_GRAD_TMA") && getenv("GTOS_GRAD_TMA")[0] == '0');
   static const bool tma_enabled = !(getenv("GTOS_TMA_OUT") && getenv("GTOS_TMA_OUT")[0] == '0');
   if (!tma_enabled) {
   } else if (MODE == MODE_PLAIN && a.out_f32 && !a.out_bf16 && !a.accumulate && a.ldo % 4 == 0 &&
@@ -735,7 +788,7 @@ static int launch_tn(const GemmTnArgs& a, cudaStream_t stream) {
     e = make_tmap_nd(&tmO, a.out_f32, 4, 4, dims, str, box, true);
     if (e) return e;
     p.tma_out = 1;
-  } else if (MODE == MODE_GRAD) {
+  } else if (MODE == MODE_GRAD && grad_tma) {
     uint64_t dims[2] = {(uint64_t)(2 * a.rt.D), (uint64_t)a.rt.tiles * BM};
     uint64_t str[2] = {0, (uint64_t)(2 * a.rt.D) * 2};
     uint32_t box[2] = {64, (uint32_t)BM};
@@ -759,7 +812,7 @@ static int launch_tn(const GemmTnArgs& a, cudaStream_t stream) {
   GTOS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   int grid = p.units * CG < num_sms() ? p.units * CG : (num_sms() / CG) * CG;
   if (grid <= 0) return GTOS_OK;
-  GTOS_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)smem_bytes, stream, CG, tmA, tmB, tmQ, tmK, tmO, p));
+  GTOS_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(tn_threads<MODE>()), (size_t)smem_bytes, stream, CG, tmA, tmB, tmQ, tmK, tmO, p));
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
 }

@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of one CUDA graph")
     ap.add_argument("--cpu-sample-graphs", type=int, default=4, help="graphs per CPU-baseline step")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--dense-relation", action="store_true",
+                    help="build relation = bank[idx] as a dense fp32 tensor exactly as generator.py:79 does "
+                         "(default: keep it factorised, SURVEY §8 f-0)")
     ap.add_argument("--profile-step", action="store_true",
                     help="run ONE eager step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     return ap.parse_args()
@@ -224,6 +227,7 @@ def main_ours(args):
     cfg = make_cfg(w, args.dropout)
     torch.manual_seed(19940117)                       # identical replicas on every rank
     model = hotpath.HotPath(cfg).to(dev)
+    model.banked_relation = not args.dense_relation
     model.train(args.dropout > 0)
     host, meta = make_host_batch(w, w["B"], 19940117 + rank)          # each rank owns its shard of the global batch
     model.decoder.token_generator.static_tot_ext = meta["tot_ext"]   # known on the host: no .item() sync
@@ -341,7 +345,9 @@ def main_ours(args):
                                f"{w['D']} dim, {w['H']} heads), synthetic <= {w['n_max']}-node graphs, fwd+bwd, "
                                f"dropout {args.dropout}", "graphs_per_gpu": w["B"], "global_batch": w["B"] * world,
                    "nodes_incl_cls": meta["N"], "tgt_len": meta["T"], "distinct_relation_paths": meta["R"],
-                   "parallelism": f"dp{world}", "step": "RelationEncoder+gather+GraphTransformer+snt+DecodeLayer "
+                   "parallelism": f"dp{world}", "relation": "dense fp32 bank[idx] (generator.py:79)" if args.dense_relation else
+                   "bank-factorised (SURVEY 8 f-0): bf16 gather fwd, bank-row GEMMs bwd",
+                   "step": "RelationEncoder+gather+GraphTransformer+snt+DecodeLayer "
                    "fwd+bwd (+ flat-gradient all-reduce when dp>1); optimizer outside the hot path",
                    "cuda_graph": graph is not None,
                    "l2": "per-step working set (dense relation fp32+bf16 = %d MB) exceeds the 126 MB L2"
@@ -416,6 +422,29 @@ def breakdown(args, w, cfg, model, static, meta, dev, lib):
     out["encoder_only"] = {"ms_per_step": ms_enc, "node_pairs_per_sec": meta["pairs"] / (ms_enc * 1e-3),
                            "algorithmic_tflops": enc_flops / (ms_enc * 1e-3) / 1e12,
                            "note": "GraphTransformer (%d layers) fwd+bwd on the dense relation tensor" % L}
+
+    # same pass with the relation kept factorised (bank [R,D] + idx [N,N,B]): includes the bf16 gather
+    # and the per-batch pair sort; the backward runs bank-row GEMMs instead of pair-row GEMMs
+    bank_p = bank.detach().clone().requires_grad_()
+
+    def enc_banked_step():
+        x.grad = bank_p.grad = None
+        y = model.graph_encoder(x, ops.BankedRelation(bank_p, static["relation"]), self_padding_mask=static["node_mask"])
+        y.backward(y)
+
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            enc_banked_step()
+        s.synchronize()
+        g2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g2, stream=s):
+            enc_banked_step()
+    torch.cuda.synchronize()
+    ms_encb = time_fn(g2.replay)
+    out["encoder_only_banked"] = {"ms_per_step": ms_encb, "node_pairs_per_sec": meta["pairs"] / (ms_encb * 1e-3),
+                                  "note": "GraphTransformer fwd+bwd from (bank, idx): bf16 gather + pair sort + "
+                                          "bank-row backward GEMMs (f-0); gradient lands on the bank"}
 
     def graphed(fn):
         s2 = torch.cuda.Stream()

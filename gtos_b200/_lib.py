@@ -49,6 +49,9 @@ SIGNATURES = {
     "gtos_rel_dw_workspace": (i64, [i32, i32, i32, i32]),
     "gtos_rel_dw": (i32, [vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]),
     "gtos_rel_dqk": (i32, [vp, vp, vp, i64, i32, i32, i32, i32, vp]),
+    "gtos_rel_pair_keys": (i32, [vp, i32, i32, i32, i32, i32, vp, vp]),
+    "gtos_rel_segsum": (i32, [vp, vp, vp, i64, i32, vp, i64, vp, vp]),
+    "gtos_rel_dw_bank": (i32, [vp, i64, vp, vp, i32, i32, i32, vp]),
     "gtos_attn_fwd": (i32, [C.POINTER(AttnDesc), vp]),
     "gtos_attn_bwd": (i32, [C.POINTER(AttnDesc), vp]),
     "gtos_add_ln_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, f32, vp, u64, vp]),

@@ -164,6 +164,31 @@ int gtos_rel_dw(const void* G, const void* relb, float* dW, float* workspace, in
   return launch_gemm_nn(a, S(stream));
 }
 
+int gtos_rel_pair_keys(const int64_t* idx, int32_t N, int32_t B, int32_t D, int32_t H, int32_t R, int32_t* keys,
+                       void* stream) {
+  RelTiling rt;
+  int e = choose_rel_tiling(&rt, N, B, D, H);
+  if (e) return e;
+  return rel_pair_keys(reinterpret_cast<const long long*>(idx), rt, R, keys, S(stream));
+}
+
+int gtos_rel_segsum(const void* G, const int32_t* order, const int32_t* keys, int64_t n, int32_t C, void* out_bf16,
+                    int64_t ldo, float* spill, void* stream) {
+  return rel_segsum(G, order, keys, n, C, out_bf16, ldo, spill, S(stream));
+}
+
+int gtos_rel_dw_bank(const void* Sb, int64_t lds, const void* bankb, float* dW, int32_t R, int32_t D, int32_t H,
+                     void* stream) {
+  GTOS_REQUIRE(H > 0 && D % H == 0, "rel_dw_bank: D=%d not divisible by H=%d", D, H);
+  if (R == 0) return GTOS_OK;
+  GemmNnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.A = Sb; a.lda = lds; a.Bm = bankb; a.ldb = D; a.M = 2 * D; a.N = D; a.Kd = R; a.rel = 0;
+  a.perm_D = D; a.perm_hd = D / H;
+  a.out = dW; a.ldo = D;
+  return launch_gemm_nn(a, S(stream));
+}
+
 int gtos_rel_dqk(const void* G, float* dq, float* dk, int64_t ld, int32_t N, int32_t B, int32_t D, int32_t H,
                  void* stream) {
   RelTiling rt;

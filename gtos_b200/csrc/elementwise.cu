@@ -606,4 +606,217 @@ int rel_dqk(const void* G, const RelTiling& rt, float* dq, float* dk, long ld, c
   return GTOS_OK;
 }
 
+// ---------------------------------------------------------------------------------------
+// bank-factorised backward of the relation terms (caller generator.py:76-79).
+// relation = bank[idx] and relation_in_proj has no bias (graph_transformer.py:80), so
+//   d relation_in_proj.weight = sum_pairs G_p^T bank[idx_p] = (sum over bank rows r of S_r^T bank_r),
+//   d bank[r]                 = S_r * W,          S_r = sum_{p : idx_p = r} G_p
+// i.e. ONE segmented sum of the per-pair gradient rows G (bf16, written by gtos_rel_grad) followed by two GEMMs
+// over R bank rows instead of two GEMMs over P pair rows + a [N,N,B,D] fp32 d_relation + an atomic scatter.
+// ---------------------------------------------------------------------------------------
+__global__ void rel_pair_keys_kernel(const long long* __restrict__ idx, RelTiling rt, int R, int* __restrict__ keys) {
+  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;     // G row = tile * 128 + r
+  if (g >= (long)rt.tiles * 128) return;
+  const int tile = (int)(g >> 7), r = (int)(g & 127);
+  const int ib = tile % rt.ni_blk, t2 = tile / rt.ni_blk;
+  const int jb = t2 % rt.nj_blk, b = t2 / rt.nj_blk;
+  const int jj = r / rt.bi, ii = r - jj * rt.bi;
+  const int j = jb * rt.bj + jj, i = ib * rt.bi + ii;
+  const bool valid = jj < rt.bj && i < rt.N && j < rt.N && b < rt.B;
+  int key = R;                                                    // padding rows of a tile sort to the end
+  if (valid) {
+    const long long v = idx[((long)j * rt.N + i) * rt.B + b];
+    key = (v >= 0 && v < R) ? (int)v : R;
+  }
+  keys[g] = key;
+}
+
+int rel_pair_keys(const long long* idx, const RelTiling& rt, int R, int* keys, cudaStream_t st) {
+  const long rows = (long)rt.tiles * 128;
+  if (rows == 0) return GTOS_OK;
+  rel_pair_keys_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(idx, rt, R, keys);
+  GTOS_LAUNCH_CHECK();
+  return GTOS_OK;
+}
+
+static constexpr int SEG_CH = 32;    // sorted pairs per warp
+static constexpr int SEG_COLS = 512; // columns per warp (grid.y splits wider rows): keeps SEG_RIF rows in flight per lane at 2 blocks per SM
+static constexpr int SEG_RIF = 6;
+
+// one warp per 32 consecutive positions of the row-sorted pair list and per 512-column slice of the C-wide row; lane l
+// owns the 8-column (16-byte) chunks l, l+32 of the slice.  A bank row whose pairs all lie inside the warp's window
+// is written once (bf16); a row that crosses a window boundary is reduced into the fp32 `spill` row with vector
+// atomics and converted by rel_segsum_span_kernel afterwards.
+template <int NCH>
+__global__ void __launch_bounds__(256, 2) rel_segsum_kernel(const __nv_bfloat16* __restrict__ G, const int* __restrict__ order,
+                                                            const int* __restrict__ keys, long n, int C,
+                                                            __nv_bfloat16* __restrict__ out, long ldo,
+                                                            float* __restrict__ spill) {
+  __shared__ int s_row[8], s_ok[8];
+  __shared__ float s_part[8 * NCH * 256];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const long warp = (long)blockIdx.x * 8 + wib;
+  const int col0 = blockIdx.y * SEG_COLS;                      // first column of this slice
+  const int ncols = (C - col0) < SEG_COLS ? (C - col0) : SEG_COLS;
+  const long p0 = warp * SEG_CH;
+  const bool active = p0 < n;
+  const int cnt = active ? (int)((n - p0) < SEG_CH ? (n - p0) : SEG_CH) : 0;
+  const int my_key = lane < cnt ? keys[p0 + lane] : -1;
+  const int my_row = lane < cnt ? order[p0 + lane] : 0;
+  const int nchunks = ncols >> 3;
+  float acc[NCH][8];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc[c][t] = 0.f;
+  int cur = __shfl_sync(0xffffffffu, my_key, 0);
+  bool open_left = active && p0 > 0 && keys[p0 - 1] == cur;
+  bool single = true;                           // the whole window belongs to one bank row
+
+  auto flush = [&](int r, bool spanning) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nchunks) {
+        if (spanning) {
+          float* d = spill + (long)r * C + col0 + ch * 8;
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(acc[c][0]), "f"(acc[c][1]),
+                       "f"(acc[c][2]), "f"(acc[c][3]) : "memory");
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + 4), "f"(acc[c][4]), "f"(acc[c][5]),
+                       "f"(acc[c][6]), "f"(acc[c][7]) : "memory");
+        } else {
+          *reinterpret_cast<uint4*>(out + (long)r * ldo + col0 + ch * 8) =
+              make_uint4(pack_bf16x2(acc[c][0], acc[c][1]), pack_bf16x2(acc[c][2], acc[c][3]),
+                         pack_bf16x2(acc[c][4], acc[c][5]), pack_bf16x2(acc[c][6], acc[c][7]));
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 8; ++t) acc[c][t] = 0.f;
+    }
+  };
+
+  for (int q0 = 0; q0 < cnt; q0 += SEG_RIF) {
+    // SEG_RIF rows in flight per lane
+    uint4 v[SEG_RIF][NCH];
+#pragma unroll
+    for (int u = 0; u < SEG_RIF; ++u) {
+      const int row = __shfl_sync(0xffffffffu, my_row, (q0 + u) & 31);
+      const uint4* src = reinterpret_cast<const uint4*>(G + (long)row * C + col0);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int ch = lane + 32 * c;
+        v[u][c] = (q0 + u < cnt && ch < nchunks) ? src[ch] : make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < SEG_RIF; ++u) {
+      if (q0 + u < cnt) {
+        const int key = __shfl_sync(0xffffffffu, my_key, (q0 + u) & 31);
+        if (key != cur) {
+          flush(cur, open_left);
+          open_left = false;
+          single = false;
+          cur = key;
+        }
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v[u][c]);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 f = __bfloat1622float2(h[t]);
+            acc[c][2 * t] += f.x;
+            acc[c][2 * t + 1] += f.y;
+          }
+        }
+      }
+    }
+  }
+  const bool open_right = active && (p0 + cnt < n) && keys[p0 + cnt] == cur;
+  const bool spanning = open_left || open_right;
+  // a bank row with thousands of pairs (e.g. the <TL> path, data.py:151-154) fills whole blocks: combine the eight
+  // windows in shared memory and issue ONE reduction per block instead of eight contended ones
+  if (lane == 0) {
+    s_row[wib] = cur;
+    s_ok[wib] = active && single && spanning;
+  }
+  __syncthreads();
+  bool all = true;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) all = all && s_ok[w] && (s_row[w] == s_row[0]);
+  if (all) {
+    float* mine = s_part + wib * (NCH * 256);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nchunks) {
+        *reinterpret_cast<float4*>(mine + ch * 8) = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+        *reinterpret_cast<float4*>(mine + ch * 8 + 4) = make_float4(acc[c][4], acc[c][5], acc[c][6], acc[c][7]);
+      }
+    }
+    __syncthreads();
+    for (int c4 = threadIdx.x; c4 < ncols / 4; c4 += 256) {
+      float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        const float4 t4 = *reinterpret_cast<const float4*>(s_part + w * (NCH * 256) + c4 * 4);
+        sum.x += t4.x; sum.y += t4.y; sum.z += t4.z; sum.w += t4.w;
+      }
+      float* d = spill + (long)s_row[0] * C + col0 + c4 * 4;
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(sum.x), "f"(sum.y), "f"(sum.z),
+                   "f"(sum.w) : "memory");
+    }
+  } else if (active) {
+    flush(cur, spanning);
+  }
+}
+
+// mode 0: zero the spill rows of bank rows that cross a window boundary; mode 1: convert them to bf16 (one warp per
+// boundary; the first boundary inside a row does the conversion)
+__global__ void rel_segsum_span_kernel(const int* __restrict__ keys, long n, int C, float* __restrict__ spill,
+                                       __nv_bfloat16* __restrict__ out, long ldo, int mode) {
+  const int lane = threadIdx.x & 31;
+  const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long b = (warp + 1) * SEG_CH;
+  if (b >= n) return;
+  const int r = keys[b];
+  if (keys[b - 1] != r) return;
+  if (mode == 0) {
+    float4* d = reinterpret_cast<float4*>(spill + (long)r * C);
+    for (int c = lane; c < C / 4; c += 32) d[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    if (b - SEG_CH >= 1 && keys[b - SEG_CH - 1] == r) return;   // an earlier boundary of the same row converts it
+    const float4* s4 = reinterpret_cast<const float4*>(spill + (long)r * C);
+    uint2* d = reinterpret_cast<uint2*>(out + (long)r * ldo);
+    for (int c = lane; c < C / 4; c += 32) {
+      const float4 v = s4[c];
+      d[c] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    }
+  }
+}
+
+int rel_segsum(const void* G, const int* order, const int* keys, long n, int C, void* out_bf16, long ldo, float* spill,
+               cudaStream_t st) {
+  GTOS_REQUIRE(C % 8 == 0 && C <= 2048 && ldo % 8 == 0 && ldo >= C,
+               "rel_segsum: row width %d must be a multiple of 8 and <= 2048 (ldo %ld)", C, ldo);
+  if (n == 0) return GTOS_OK;
+  const long warps = (n + SEG_CH - 1) / SEG_CH;
+  const unsigned blocks = (unsigned)((warps * 32 + 255) / 256);
+  const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(G);
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  if (warps > 1) {
+    rel_segsum_span_kernel<<<blocks, 256, 0, st>>>(keys, n, C, spill, o, ldo, 0);
+    GTOS_LAUNCH_CHECK();
+  }
+  const dim3 grid((unsigned)((warps + 7) / 8), (unsigned)((C + SEG_COLS - 1) / SEG_COLS));
+  if (C <= 256) rel_segsum_kernel<1><<<grid, 256, 0, st>>>(g, order, keys, n, C, o, ldo, spill);
+  else rel_segsum_kernel<2><<<grid, 256, 0, st>>>(g, order, keys, n, C, o, ldo, spill);
+  GTOS_LAUNCH_CHECK();
+  if (warps > 1) {
+    rel_segsum_span_kernel<<<blocks, 256, 0, st>>>(keys, n, C, spill, o, ldo, 1);
+    GTOS_LAUNCH_CHECK();
+  }
+  return GTOS_OK;
+}
+
+
 }  // namespace gtos

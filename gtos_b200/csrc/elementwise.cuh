@@ -30,6 +30,9 @@ int token_nll_bwd(const float* dloss_row, const float* logits, long ldl, int V, 
 int bank_gather(const float* bank, const long long* idx, long P, int D, float* out_f32, void* out_bf16, cudaStream_t st);
 int bank_scatter_add(const float* d_rel, const long long* idx, long P, int D, float* d_bank, long R, cudaStream_t st);
 int rel_dqk(const void* G, const RelTiling& rt, float* dq, float* dk, long ld, cudaStream_t st);
+int rel_pair_keys(const long long* idx, const RelTiling& rt, int R, int* keys, cudaStream_t st);
+int rel_segsum(const void* G, const int* order, const int* keys, long n, int C, void* out_bf16, long ldo, float* spill,
+               cudaStream_t st);
 
 // ---- attention core (attention.cu) ------------------------------------------------------
 struct AttnArgs {

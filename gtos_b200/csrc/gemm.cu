@@ -1079,7 +1079,7 @@ static int launch_nn(const GemmNnArgs& a, int splits, int per, cudaStream_t stre
   p.k_blocks = (a.Kd + KB - 1) / KB;
   p.splits = splits; p.kb_per_split = per;
   p.out = a.out; p.ldo = a.ldo; p.rt = a.rt;
-  p.perm_D = a.rel ? a.rt.D : 0; p.perm_hd = a.rel ? a.rt.hd : 0;
+  p.perm_D = a.rel ? a.rt.D : a.perm_D; p.perm_hd = a.rel ? a.rt.hd : a.perm_hd;
   CUtensorMap tmA, tmB;
   int e;
   {

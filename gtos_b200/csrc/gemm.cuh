@@ -77,6 +77,7 @@ struct GemmNnArgs {
   long ldb;
   int M, N, Kd;
   int rel;             // B rows come from 4-D relation tiles (Kd = tiles*128)
+  int perm_D, perm_hd; // != 0 (or rel): accumulator row m is a permuted relation_in_proj row -> written to its reference row
   RelTiling rt;
   float* out;          // [M,N] fp32 (ldo)  (rel: rows un-permuted to the reference [2D,D] layout)
   long ldo;

@@ -24,12 +24,21 @@ class GraphTransformer(nn.Module):
     def forward(self, x, relation, kv=None, self_padding_mask=None, self_attn_mask=None):
         # every layer reads the SAME relation tensor (:16-17): stage its bf16 copy once (or reuse the one
         # ops.bank_gather made while building the tensor)
-        relb = _staged_bf16(relation)
-        # one shared gradient buffer for the relation tensor instead of L per-layer tensors summed by autograd
         acc, token = None, None
-        if torch.is_grad_enabled() and relation.requires_grad:
-            acc = ops.RelGradAcc()
-            token = ops.RelTokenFn.apply(relation, acc)
+        if isinstance(relation, ops.BankedRelation):
+            # bank-factorised relation: dense bf16 operand for the fused kernels, bank-row GEMMs
+            # in the backward
+            banked, relation, relb = relation, None, relation.relb
+            if torch.is_grad_enabled() and banked.requires_grad:
+                banked.prepare(self.layers[0].self_attn.num_heads)
+                acc = ops.RelGradAcc(banked, len(self.layers))
+                token = ops.BankTokenFn.apply(banked.bank, acc)
+        else:
+            relb = _staged_bf16(relation)
+            # one shared gradient buffer for the relation tensor instead of L per-layer tensors summed by autograd
+            if torch.is_grad_enabled() and relation.requires_grad:
+                acc = ops.RelGradAcc()
+                token = ops.RelTokenFn.apply(relation, acc)
         xb = None
         for layer in self.layers:
             x, xb, _ = layer._forward(x, xb, relation, relb, kv, self_padding_mask, self_attn_mask, False,
@@ -37,7 +46,10 @@ class GraphTransformer(nn.Module):
         return x
 
     def get_attn_weights(self, x, relation, kv=None, self_padding_mask=None, self_attn_mask=None):
-        relb = _staged_bf16(relation)
+        if isinstance(relation, ops.BankedRelation):
+            relation, relb = None, relation.relb
+        else:
+            relb = _staged_bf16(relation)
         attns, xb = [], None
         for layer in self.layers:
             x, xb, attn = layer._forward(x, xb, relation, relb, kv, self_padding_mask, self_attn_mask, True)

@@ -45,6 +45,7 @@ class HotPath(nn.Module):
                                        with_external=True)
         self.decoder = DecodeLayer(vocabs, c.inference_layers, c.embed_dim, c.ff_embed_dim, c.num_heads,
                                    c.concept_dim, c.rel_dim, c.dropout)
+        self.banked_relation = True      # False: dense `relation_bank[idx]` exactly as generator.py:79 builds it
         self.probe_generator = nn.Linear(c.embed_dim, c.embed_dim)
         nn.init.normal_(self.probe_generator.weight, std=0.02)
         nn.init.constant_(self.probe_generator.bias, 0.)
@@ -53,7 +54,12 @@ class HotPath(nn.Module):
         """generator.py:76-94: relation bank -> dense relation -> graph encoder -> probe / node states."""
         bank = self.relation_encoder(batch["relation_bank"], batch["relation_length"])
         idx = batch["relation"]
-        relation = ops.bank_gather(bank, idx)                                       # generator.py:79 (+ bf16 copy)
+        if self.banked_relation:
+            # §8 f-0: keep relation = bank[idx] factorised (the 2-line caller change, INTEGRATION.md): no fp32
+            # [N,N,B,D] tensor, bank-row GEMMs in the backward
+            relation = ops.BankedRelation(bank, idx)
+        else:
+            relation = ops.bank_gather(bank, idx)                                   # generator.py:79 (+ bf16 copy)
         h = self.graph_encoder(batch["x"], relation, self_padding_mask=batch["node_mask"])
         probe = torch.tanh(self.probe_generator(h[:1]))
         return h[1:], batch["node_mask"][1:], probe

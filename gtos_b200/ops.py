@@ -276,11 +276,12 @@ class RelAttnFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, xb, relation, relb, key_pad, attn_mask, W_in, b_in, W_rel, W_out, b_out, H, p, need_weights,
                 rel_token=None, rel_acc=None):
-        _need_cuda(x, relation, W_in)
+        _need_cuda(x, relation if relation is not None else relb, W_in)
         lib = _lib.load()
         N, B, D = x.shape
-        if tuple(relation.shape) != (N, N, B, D):
-            raise ValueError(f"relation must be [N,N,B,D]=[{N},{N},{B},{D}], got {tuple(relation.shape)}")
+        rshape = tuple((relation if relation is not None else relb).shape)
+        if rshape != (N, N, B, D):
+            raise ValueError(f"relation must be [N,N,B,D]=[{N},{N},{B},{D}], got {rshape}")
         hd = D // H
         dev = x.device
         NB = N * B
@@ -351,6 +352,34 @@ class RelAttnFn(torch.autograd.Function):
         _lib.check(lib.gtos_rel_dqk(_p(G), dqkv.data_ptr(), dqkv.data_ptr() + 4 * D, 3 * D, N, B, D, H, _st()),
                    "rel_dqk")
         d_rel = None
+        if ctx.rel_acc is not None and ctx.rel_acc.banked is not None:
+            # relation = bank[idx]: segmented sum of G over bank rows, then R-row GEMMs instead of
+            # P-row GEMMs; no [N,N,B,D] gradient tensor, no atomic scatter
+            acc = ctx.rel_acc
+            bk = acc.banked
+            R = bk.bankb.shape[0]
+            L = acc.n_layers
+            if acc.S is None:
+                # the layers' segment sums sit side by side: d bank = [S_1|..|S_L] [Wperm_1;..;Wperm_L] is one GEMM
+                acc.S = torch.zeros(R, L * 2 * D, dtype=torch.bfloat16, device=dev)  # rows without pairs stay zero
+                acc.Wcat = torch.zeros(D, L * 2 * D, dtype=torch.bfloat16, device=dev)
+                acc.spill = torch.empty(R, 2 * D, dtype=torch.float32, device=dev)
+                acc.slot = 0
+            if acc.slot >= L:
+                raise RuntimeError("RelGradAcc: more relation-attention backward passes than layers")
+            c0 = acc.slot * 2 * D
+            acc.slot += 1
+            s_ptr = acc.S.data_ptr() + 2 * c0
+            _lib.check(lib.gtos_rel_segsum(_p(G), _p(bk.order), _p(bk.keys), N * N * B, 2 * D, s_ptr, L * 2 * D,
+                                           _p(acc.spill), _st()), "rel_segsum")
+            dW_rel = torch.empty(2 * D, D, dtype=torch.float32, device=dev)
+            _lib.check(lib.gtos_rel_dw_bank(s_ptr, L * 2 * D, _p(bk.bankb), _p(dW_rel), R, D, H, _st()), "rel_dw_bank")
+            acc.Wcat[:, c0:c0 + 2 * D].copy_(WpermT[:, :2 * D])
+            dqkvb, db_in = cast_colsum(dqkv)
+            dW_in = gemm_nn(dqkvb, xb2, 3 * D, D)
+            dx, _ = gemm_tn(dqkvb, Wit, D)
+            return (dx.view(N, B, D), None, None, None, None, None, dW_in, db_in, dW_rel, dW_out, db_out, None, None,
+                    None, None, None)
         if ctx.rel_acc is not None:
             # all layers share one relation tensor: reduce this layer's gradient straight into the shared buffer
             # (TMA reduce-add), which RelTokenFn hands to autograd once
@@ -374,10 +403,86 @@ class RelAttnFn(torch.autograd.Function):
 
 
 class RelGradAcc:
-    """holds the shared d_relation buffer of one GraphTransformer pass"""
+    """holds the shared d_relation buffer of one GraphTransformer pass (dense relation), or - when the relation is a
+    BankedRelation - the shared d_bank buffer and the segment-sum scratch"""
 
-    def __init__(self):
+    def __init__(self, banked=None, n_layers=1):
         self.buf = None
+        self.banked = banked
+        self.n_layers = n_layers
+        self.S = self.Wcat = self.spill = None
+        self.slot = 0
+
+
+class BankedRelation:
+    """relation = bank[idx] kept factorised (caller generator/generator.py:76-79).
+
+    bank [R,D] fp32 (output of RelationEncoder, may require grad), idx [N,N,B] int64 with idx[j][i][b] = bank row of
+    the path i -> j (data.py:164-176).  The forward still feeds the dense bf16 tensor to the fused tcgen05 score
+    kernel; the backward uses the bank structure: d bank and d relation_in_proj come from R-row GEMMs after one
+    segmented sum of the per-pair gradients, so no fp32 [N,N,B,D] tensor (forward or backward) ever exists.
+    Pass it as the `relation` argument of gtos_b200.GraphTransformer."""
+
+    def __init__(self, bank, idx):
+        _need_cuda(bank, idx)
+        if bank.dim() != 2 or idx.dim() != 3 or idx.shape[0] != idx.shape[1]:
+            raise ValueError(f"BankedRelation: bank [R,D] and idx [N,N,B] expected, got {tuple(bank.shape)}, {tuple(idx.shape)}")
+        self.bank = bank
+        self.idx = idx.contiguous()
+        R, D = bank.shape
+        with torch.no_grad():
+            bank_c = bank.detach().contiguous()
+            self.bankb = cast_bf16(bank_c)
+            self.relb = torch.empty(*idx.shape, D, dtype=torch.bfloat16, device=bank.device)
+            _lib.check(_lib.load().gtos_bank_gather(_p(bank_c), _p(self.idx), self.idx.numel(), D, None, _p(self.relb),
+                                                    _st()), "bank_gather")
+        self.keys = self.order = None
+        self._heads = None
+
+    @property
+    def requires_grad(self):
+        return self.bank.requires_grad
+
+    @property
+    def shape(self):
+        return (*self.idx.shape, self.bank.shape[1])
+
+    def prepare(self, H):
+        """sort the G rows (tile-major pair rows of gtos_rel_grad) by bank row - once per batch"""
+        if self._heads == H:
+            return
+        N, _, B = self.idx.shape
+        R, D = self.bank.shape
+        tiles = rel_tiling(N, B, D, H)["tiles"]
+        raw = torch.empty(tiles * 128, dtype=torch.int32, device=self.idx.device)
+        _lib.check(_lib.load().gtos_rel_pair_keys(_p(self.idx), N, B, D, H, R, _p(raw), _st()), "rel_pair_keys")
+        keys, order = torch.sort(raw)
+        self.keys, self.order = keys.contiguous(), order.to(torch.int32).contiguous()
+        self._heads = H
+
+    def dense(self):
+        """the fp32 tensor the reference would build (bank[idx]) - for callers that need it materialised"""
+        return self.bank[self.idx]
+
+
+class BankTokenFn(torch.autograd.Function):
+    """bank -> scalar token consumed by every layer's RelAttnFn; its backward runs after all of them and returns
+    the d_bank they accumulated"""
+
+    @staticmethod
+    def forward(ctx, bank, acc):
+        ctx.acc = acc
+        ctx.set_materialize_grads(False)
+        return bank.new_zeros(())
+
+    @staticmethod
+    def backward(ctx, _g):
+        acc = ctx.acc
+        if acc.S is None:
+            return None, None
+        d, _ = gemm_tn(acc.S, acc.Wcat, acc.Wcat.shape[0])          # [R, L*2D] x [D, L*2D]^T -> d bank [R, D]
+        acc.S = acc.Wcat = acc.spill = None
+        return d, None
 
 
 class RelTokenFn(torch.autograd.Function):

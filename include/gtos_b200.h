@@ -85,6 +85,24 @@ int gtos_rel_dw(const void* G, const void* relb, float* dW, float* workspace, in
 int gtos_rel_dqk(const void* G, float* dq, float* dk, int64_t ld, int32_t N, int32_t B, int32_t D, int32_t H,
                  void* stream);
 
+/* ---- bank-factorised backward of the relation terms (caller generator/generator.py:76-79) ----
+ * When relation = bank[idx] (bank [R,D], idx [N,N,B] int64, layout idx[j][i][b]) the two P-row GEMMs of the backward
+ * collapse to R-row GEMMs after ONE segmented sum of the per-pair gradient rows G (from gtos_rel_grad):
+ *   S[r,:] = sum_{pairs p : idx_p = r} G[p,:]      d relation_in_proj.weight = S^T bank      d bank = S * Wperm
+ * gtos_rel_pair_keys: keys[g] = bank row of G row g (tile-major pair rows, gtos_rel_tiling), R for tile padding rows.
+ *   The caller sorts (keys, g) once per batch -> `keys` ascending, `order` = the matching G rows; n = N*N*B.
+ * gtos_rel_segsum: S (bf16 [R,C], row stride ldo >= C = 2D) from the sorted lists; rows without pairs are NOT
+ *   written (zero them once); spill = fp32 scratch [R,C] (only rows whose pairs straddle a 32-pair window are touched).
+ *   The row stride lets the L layers of an encoder write side by side, so d bank = [S_1|..|S_L] * [Wperm_1;..;Wperm_L]
+ *   is ONE gtos_gemm_tn at the end of the backward.
+ * gtos_rel_dw_bank: dW [2D,D] fp32 (reference row order) = S^T * bank_bf16 [R,D]; S row stride lds. */
+int gtos_rel_pair_keys(const int64_t* idx, int32_t N, int32_t B, int32_t D, int32_t H, int32_t R, int32_t* keys,
+                       void* stream);
+int gtos_rel_segsum(const void* G, const int32_t* order, const int32_t* keys, int64_t n, int32_t C, void* out_bf16,
+                    int64_t ldo, float* spill, void* stream);
+int gtos_rel_dw_bank(const void* S, int64_t lds, const void* bankb, float* dW, int32_t R, int32_t D, int32_t H,
+                     void* stream);
+
 /* ---- attention core: masks, softmax, dropout, PV (graph_transformer.py:136-159; transformer.py:131-155) ---- */
 typedef struct gtos_attn_desc {
   int32_t T, S, B, H, hd;

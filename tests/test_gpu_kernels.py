@@ -262,3 +262,55 @@ def test_bank_gather_and_scatter(dev):
     (g,) = torch.autograd.grad((rel * w).sum(), bank)
     (gr,) = torch.autograd.grad((ref * w).sum(), bank)
     assert rel_err(g, gr) < 1e-5
+
+
+@pytest.mark.parametrize("N,B,D,H,R", [(9, 4, 128, 8, 300), (41, 6, 512, 8, 5000), (17, 3, 128, 4, 40)])
+def test_rel_segsum_and_bank_weight_grad(dev, N, B, D, H, R):
+    """§8 f-0 backward pieces: keys of the tile-major G rows, segmented sum over the row-sorted pair list
+    (S_r = sum of the G rows whose pair uses bank row r) and dW = S^T bank in reference row order, against
+    index_add / matmul in fp32 on the same bf16 inputs.  Hot rows (thousands of pairs), rows without pairs and
+    tile padding rows are all present."""
+    from gtos_b200 import _lib, ops
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator(device="cpu").manual_seed(SEED)
+    idx = torch.randint(0, R // 2, (N, N, B), generator=g)              # rows >= R/2 never used
+    idx[torch.rand(N, N, B, generator=g) < 0.3] = 5                       # one very hot row
+    idx[0] = 2
+    idx = idx.to(dev)
+    til = ops.rel_tiling(N, B, D, H)
+    rows = til["tiles"] * 128
+    raw = torch.empty(rows, dtype=torch.int32, device=dev)
+    _lib.check(lib.gtos_rel_pair_keys(idx.data_ptr(), N, B, D, H, R, raw.data_ptr(), st), "pair_keys")
+    assert int((raw < R).sum()) == N * N * B
+    # the key of G row (tile, jj*bi+ii) is idx[j, i, b]: rebuild the expected map from the tiling
+    bi, bj, ni, nj = til["bi"], til["bj"], til["ni_blk"], til["nj_blk"]
+    gidx = torch.arange(rows, device=dev)
+    tile, r = gidx // 128, gidx % 128
+    ib, jb, b = tile % ni, (tile // ni) % nj, tile // (ni * nj)
+    jj, ii = r // bi, r % bi
+    j, i = jb * bj + jj, ib * bi + ii
+    valid = (jj < bj) & (i < N) & (j < N)
+    exp = torch.full((rows,), R, dtype=torch.int64, device=dev)
+    exp[valid] = idx[j[valid], i[valid], b[valid]]
+    assert torch.equal(raw.long(), exp)
+    keys, order = torch.sort(raw)
+    order = order.to(torch.int32)
+    G = (torch.randn(rows, 2 * D, device=dev) * 0.3).to(torch.bfloat16)
+    S = torch.zeros(R, 2 * D, dtype=torch.bfloat16, device=dev)
+    spill = torch.full((R, 2 * D), float("nan"), device=dev)             # must be zeroed by the kernel where used
+    _lib.check(lib.gtos_rel_segsum(G.data_ptr(), order.data_ptr(), keys.data_ptr(), N * N * B, 2 * D, S.data_ptr(),
+                                   2 * D, spill.data_ptr(), st), "segsum")
+    ref = torch.zeros(R + 1, 2 * D, device=dev).index_add_(0, exp, G.float())[:R]
+    assert torch.isfinite(S.float()).all()
+    assert rel_err(S.float(), ref) < 2 ** -8                               # one bf16 rounding of an fp32 sum
+    assert (S[R // 2:] == 0).all()
+    bank = torch.randn(R, D, device=dev).to(torch.bfloat16)
+    dW = torch.empty(2 * D, D, device=dev)
+    _lib.check(lib.gtos_rel_dw_bank(S.data_ptr(), 2 * D, bank.data_ptr(), dW.data_ptr(), R, D, H, st), "dw_bank")
+    hd = D // H
+    perm = torch.tensor([(p // (2 * hd)) * hd + (p % (2 * hd)) if (p % (2 * hd)) < hd
+                         else D + (p // (2 * hd)) * hd + (p % (2 * hd)) - hd for p in range(2 * D)], device=dev)
+    dref = torch.zeros(2 * D, D, device=dev)
+    dref[perm] = S.float().t() @ bank.float()
+    assert rel_err(dW, dref) < 1e-4

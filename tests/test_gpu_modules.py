@@ -109,6 +109,52 @@ def test_graph_transformer_vs_oracle(dev, N, B, D, H, F, L, wf):
     assert attn.shape == aref.shape and rel_err(attn, aref) < TOL
 
 
+@pytest.mark.parametrize("N,B,D,H,F,L,R", [(17, 8, 128, 8, 256, 2, 200), (41, 6, 512, 8, 1024, 2, 3000)])
+def test_graph_transformer_banked_relation_vs_oracle(dev, N, B, D, H, F, L, R):
+    """§8 f-0: relation = bank[idx] passed factorised (ops.BankedRelation).  Output and every gradient (incl. d bank,
+    d relation_in_proj of each layer) against the oracle run on the dense bank[idx] tensor, and against this repo's own
+    dense path (same forward kernels: outputs bit-identical; gradients differ only by the bf16 rounding of the
+    per-bank-row sums)."""
+    from gtos_b200 import ops
+    from gtos_b200.graph_transformer import GraphTransformer
+    gen = torch.Generator().manual_seed(SEED)
+    m = GraphTransformer(L, D, F, H, 0.0)
+    boost(m, 2.0, gen)
+    x = torch.randn(N, B, D, generator=gen)
+    bank = torch.randn(R, D, generator=gen) * 0.5
+    idx = torch.randint(0, R - 7, (N, N, B), generator=gen)
+    idx[torch.rand(N, N, B, generator=gen) < 0.25] = 4                     # a hot bank row; rows >= R-7 unused
+    idx[0], idx[:, 0] = 0, 1                                               # <CLS> row / column (data.py:138-147)
+    lens = [N] + [int(v) for v in torch.randint(N // 2, N + 1, (B - 1,), generator=gen)]
+    mask = pad_mask(lens, N)
+    wo = torch.randn(N, B, D, generator=gen)
+    P = oracle_params(m)
+    xc, bc = x.clone().requires_grad_(), bank.clone().requires_grad_()
+    ref = O.graph_transformer(P, "", xc, O.bank_to_dense(bc, idx), L, H, self_padding_mask=mask)
+    with oracle_bf16():
+        ref16 = O.graph_transformer(P, "", xc, O.bank_to_dense(bc, idx), L, H, self_padding_mask=mask)
+    m = m.to(dev)
+    xg, bg = x.to(dev).requires_grad_(), bank.to(dev).requires_grad_()
+    out = m(xg, ops.BankedRelation(bg, idx.to(dev)), self_padding_mask=mask.to(dev))
+    assert rel_err(out, ref) < TOL
+    compare_grads(m, P, (out * wo.to(dev)).sum(), (ref16 * wo).sum(), [xg, bg], [xc, bc], tol=4 * TOL, tol_max=0.2)
+    compare_grads(m, P, (out * wo.to(dev)).sum(), (ref * wo).sum(), [xg, bg], [xc, bc], tol=0.15, tol_max=0.5)
+    # dense path of this repo on the same operands
+    xd, bd = x.to(dev).requires_grad_(), bank.to(dev).requires_grad_()
+    out_d = m(xd, ops.bank_gather(bd, idx.to(dev)), self_padding_mask=mask.to(dev))
+    assert torch.equal(out, out_d)
+    names = [n for n, _ in m.named_parameters()]
+    params = [p for _, p in m.named_parameters()]
+    ga = torch.autograd.grad((out * wo.to(dev)).sum(), [xg, bg] + params)
+    gb = torch.autograd.grad((out_d * wo.to(dev)).sum(), [xd, bd] + params)
+    for lab, a, b in zip(["x", "bank"] + names, ga, gb):
+        assert l2_err(a, b) < 5e-3, f"banked vs dense grad {lab}: {l2_err(a, b):.3e}"
+    with torch.no_grad():
+        attn = m.get_attn_weights(xg, ops.BankedRelation(bg, idx.to(dev)), self_padding_mask=mask.to(dev))
+        attn_d = m.get_attn_weights(xg, bg[idx.to(dev)], self_padding_mask=mask.to(dev))
+    assert torch.equal(attn, attn_d)
+
+
 def test_rel_mha_weights_grad(dev):
     """RelationMultiheadAttention.forward with need_weights and a gradient flowing into the weights."""
     from gtos_b200.graph_transformer import RelationMultiheadAttention

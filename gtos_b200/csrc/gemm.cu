@@ -108,10 +108,11 @@ __device__ __forceinline__ void lds_sw128_bf16x16(const uint8_t* box, int row, i
 // relation tiles at once: each CTA stages its own 128-row A tile and HALF of the BN weight rows, the leader issues
 // M=256 MMAs that read both CTAs' shared memory, and each CTA's TMEM receives the accumulator of its own 128 rows.
 // Halves the weight traffic per FLOP and the shared-memory operand traffic per SM.
-// relation modes run TWO epilogue warpgroups (warps 2-5 and 6-9; both map onto TMEM lane quarters warp & 3): each
-// takes half of the unit's heads, so the score / gradient math of a unit takes half as long as its MMAs
+// relation and GRU modes run TWO epilogue warpgroups (warps 2-5 and 6-9; both map onto TMEM lane quarters warp & 3):
+// each takes half of the unit's heads / hidden units - their epilogues (score / gradient / gate math) cost more
+// issue slots per unit than the unit's MMAs take cycles, and one warp per SM sub-partition cannot hide that
 template <int MODE>
-constexpr int tn_epi_wgs() { return (MODE == MODE_SCORE || MODE == MODE_GRAD) ? 2 : 1; }
+constexpr int tn_epi_wgs() { return (MODE == MODE_SCORE || MODE == MODE_GRAD || MODE == MODE_GRU) ? 2 : 1; }
 template <int MODE>
 constexpr int tn_threads() { return 64 + 128 * tn_epi_wgs<MODE>(); }
 template <int MODE>
@@ -140,7 +141,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* qk_base = smem + p.stages * STAGE_BYTES;
   uint8_t* out_stage = qk_base + (REL ? 2 * p.qk_stage_bytes : 0);  // 1024-aligned (all regions are multiples of 1 KB)
-  PipeBars* bars = reinterpret_cast<PipeBars*>(out_stage + (p.tma_out ? OUT_STAGE_BYTES : (MODE == MODE_GRU ? 2 * BN * 4 : 0)));
+  [[maybe_unused]] uint8_t* gru_stage = out_stage + 2 * BN * 4;   // MODE_GRU: 8 warp-private 8 KB store-staging tiles
+  PipeBars* bars = reinterpret_cast<PipeBars*>(out_stage + (p.tma_out ? OUT_STAGE_BYTES : (MODE == MODE_GRU ? 2 * BN * 4 + 8 * 8192 : 0)));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -277,25 +279,28 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m_blk = (unit / p.n_tiles) * CG + (int)rank, n_blk = unit % p.n_tiles;
       // MODE_GRU: fetch this thread's slice of the previous state, the bias block and the length flag while the
       // tensor core is still producing the accumulator (4 epilogue warps cannot hide DRAM latency otherwise)
-      [[maybe_unused]] float gru_hp[MODE == MODE_GRU ? BN / 4 : 1];
-      [[maybe_unused]] bool gru_live = false;
+      [[maybe_unused]] float gru_hp[MODE == MODE_GRU ? (BN >= 128 ? BN / 8 : BN / 4) : 1];   // this warpgroup's half of the unit's hidden units
+      [[maybe_unused]] long long gru_len_v = 0;   // compared with the time step only after the accumulator wait
       [[maybe_unused]] const float* gru_bias = nullptr;
       if constexpr (MODE == MODE_GRU) {
         constexpr int UB = BN / 4;
         const long row = (long)m_blk * BM + r;
         float* sb = reinterpret_cast<float*>(out_stage) + (as * BN);     // bias block of this unit, per accumulator stage
-        for (int t = r; t < BN; t += 128) sb[t] = p.bias[n_blk * BN + t];
+        for (int t = r + 128 * wg; t < BN; t += 128 * EPI_WGS) sb[t] = p.bias[n_blk * BN + t];
         gru_bias = sb;
-        if (row < p.M) {
-          gru_live = p.gru_len[row] > p.gru_t;
-          const float4* hpp = reinterpret_cast<const float4*>(p.gru_hprev + row * p.gru_H + n_blk * UB);
+        constexpr int UW = (UB >= 32) ? UB / 2 : UB;   // hidden units per warpgroup (a 16-unit tile is not split)
+        if (row < p.M && (UB >= 32 || wg == 0)) {
+          gru_len_v = p.gru_len[row];
+          const int uw = n_blk * UB + wg * UW;         // first hidden unit of this warpgroup
+          const float4* hpp = reinterpret_cast<const float4*>(p.gru_hprev + row * p.gru_H + uw);
 #pragma unroll
-          for (int t4 = 0; t4 < UB / 4; ++t4) {
-            float4 v = (n_blk * UB + 4 * t4 < p.gru_H) ? hpp[t4] : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int t4 = 0; t4 < UW / 4; ++t4) {
+            float4 v = (uw + 4 * t4 < p.gru_H) ? hpp[t4] : make_float4(0.f, 0.f, 0.f, 0.f);
             gru_hp[4 * t4] = v.x; gru_hp[4 * t4 + 1] = v.y; gru_hp[4 * t4 + 2] = v.z; gru_hp[4 * t4 + 3] = v.w;
           }
         }
-        named_bar_sync(1, 128);  // bias block visible to all epilogue warps
+        named_bar_sync(1, 128 * EPI_WGS);  // bias block visible to all epilogue warps (also keeps the warpgroups within
+                                           // one unit of each other, so the per-stage bias block is never overwritten early)
       }
       // relation modes: decode the tile and (MODE_GRAD) fetch this thread's d(score) values of the warpgroup's heads
       // while the tensor core is still producing the accumulator
@@ -335,9 +340,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const long row = (long)m_blk * BM + r;
         const bool row_ok = row < p.M;
         const int H = p.gru_H;
-        const bool live = row_ok && gru_live;
+        const bool live = row_ok && gru_len_v > p.gru_t;
+        constexpr int UW = (UB >= 32) ? UB / 2 : UB;
+        const int c_end = (UB >= 32 || wg == 0) ? wg * UW + UW : 0;
 #pragma unroll
-        for (int c = 0; c < UB; c += 16) {
+        for (int c = wg * UW; c < c_end; c += 16) {
           float ar[16], az[16], ai[16], ah[16];
           tmem_ld16(tacc + c, ar);
           tmem_ld16(tacc + UB + c, az);
@@ -345,44 +352,71 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tmem_ld16(tacc + 3 * UB + c, ah);
           tmem_ld_wait();
           const int u0 = n_blk * UB + c;  // first hidden unit of this chunk
-          if (row_ok && u0 < H) {
-            const float* hp = gru_hp + c;
-            float hn[16], gr[16], gz[16], gn[16], hh[16];
+          if (u0 < H) {                   // warp-uniform
+            // Results go through a warp-private swizzled smem tile so that every global store instruction writes whole
+            // 32/64-byte row pieces of 8-16 rows (full sectors) instead of 16 bytes of 32 different rows: the epilogue
+            // was bound by the number of L2 store requests, not by bytes (ncu: long-scoreboard stalls behind STG.128)
+            uint8_t* wst = gru_stage + ((warp - 2) * 8192);
+            if (row_ok) {
+              const float* hp = gru_hp + (c - wg * UW);
+              float hn[16], gr[16], gz[16], gn[16], hh[16];
 #pragma unroll
-            for (int t = 0; t < 16; ++t) {
-              const float r_ = __fdividef(1.f, 1.f + __expf(-(ar[t] + gru_bias[c + t])));
-              const float z_ = __fdividef(1.f, 1.f + __expf(-(az[t] + gru_bias[UB + c + t])));
-              const float hn_ = ah[t] + gru_bias[3 * UB + c + t];
-              const float pre = ai[t] + gru_bias[2 * UB + c + t] + r_ * hn_;
-              const float n_ = 1.f - __fdividef(2.f, 1.f + __expf(2.f * pre));   // tanh
-              gr[t] = live ? r_ : 0.f; gz[t] = live ? z_ : 0.f; gn[t] = live ? n_ : 0.f; hh[t] = live ? hn_ : 0.f;
-              hn[t] = live ? (1.f - z_) * n_ + z_ * hp[t] : hp[t];
-            }
-            float4* ho = reinterpret_cast<float4*>(p.gru_hnew + row * H + u0);
+              for (int t = 0; t < 16; ++t) {
+                const float r_ = __fdividef(1.f, 1.f + __expf(-(ar[t] + gru_bias[c + t])));
+                const float z_ = __fdividef(1.f, 1.f + __expf(-(az[t] + gru_bias[UB + c + t])));
+                const float hn_ = ah[t] + gru_bias[3 * UB + c + t];
+                const float pre = ai[t] + gru_bias[2 * UB + c + t] + r_ * hn_;
+                const float n_ = 1.f - __fdividef(2.f, 1.f + __expf(2.f * pre));   // tanh
+                gr[t] = live ? r_ : 0.f; gz[t] = live ? z_ : 0.f; gn[t] = live ? n_ : 0.f; hh[t] = live ? hn_ : 0.f;
+                hn[t] = live ? (1.f - z_) * n_ + z_ * hp[t] : hp[t];
+              }
+              const int sw4 = (lane >> 1) & 3, sw2 = (lane >> 2) & 1;
 #pragma unroll
-            for (int t4 = 0; t4 < 4; ++t4) ho[t4] = make_float4(hn[4 * t4], hn[4 * t4 + 1], hn[4 * t4 + 2], hn[4 * t4 + 3]);
-            const uint4 hb0 = make_uint4(pack_bf16x2(hn[0], hn[1]), pack_bf16x2(hn[2], hn[3]), pack_bf16x2(hn[4], hn[5]), pack_bf16x2(hn[6], hn[7]));
-            const uint4 hb1 = make_uint4(pack_bf16x2(hn[8], hn[9]), pack_bf16x2(hn[10], hn[11]), pack_bf16x2(hn[12], hn[13]), pack_bf16x2(hn[14], hn[15]));
-            uint4* hb = reinterpret_cast<uint4*>(p.gru_hbnew + row * p.gru_ldhbn + u0);
-            hb[0] = hb0;
-            hb[1] = hb1;
-            if (p.gru_out) {
-              uint4* oo = reinterpret_cast<uint4*>(p.gru_out + row * p.gru_ldout + u0);
-              oo[0] = live ? hb0 : make_uint4(0, 0, 0, 0);
-              oo[1] = live ? hb1 : make_uint4(0, 0, 0, 0);
-            }
-            __nv_bfloat16* gp = p.gru_gates + row * p.gru_ldg + (long)n_blk * BN + c;
-#define GTOS_STORE16(dst, v)                                                                                          \
+              for (int k = 0; k < 4; ++k)
+                *reinterpret_cast<float4*>(wst + lane * 64 + ((k ^ sw4) << 4)) =
+                    make_float4(hn[4 * k], hn[4 * k + 1], hn[4 * k + 2], hn[4 * k + 3]);
+#define GTOS_STAGE16(off, v, zero)                                                                                     \
   do {                                                                                                                \
-    uint4* _g = reinterpret_cast<uint4*>(dst);                                                                        \
-    _g[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));       \
-    _g[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15])); \
+    uint8_t* _b = wst + (off) + lane * 32;                                                                            \
+    *reinterpret_cast<uint4*>(_b + ((0 ^ sw2) << 4)) = (zero) ? make_uint4(0, 0, 0, 0) :                              \
+        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])); \
+    *reinterpret_cast<uint4*>(_b + ((1 ^ sw2) << 4)) = (zero) ? make_uint4(0, 0, 0, 0) :                              \
+        make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15])); \
   } while (0)
-            GTOS_STORE16(gp, gr);
-            GTOS_STORE16(gp + UB, gz);
-            GTOS_STORE16(gp + 2 * UB, gn);
-            GTOS_STORE16(gp + 3 * UB, hh);
-#undef GTOS_STORE16
+              GTOS_STAGE16(2048, hn, false);
+              if (p.gru_out) GTOS_STAGE16(3072, hn, !live);
+              GTOS_STAGE16(4096, gr, false);
+              GTOS_STAGE16(5120, gz, false);
+              GTOS_STAGE16(6144, gn, false);
+              GTOS_STAGE16(7168, hh, false);
+#undef GTOS_STAGE16
+            }
+            __syncwarp();
+            const long row0 = (long)m_blk * BM + quarter * 32;     // first row of this warp
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {                          // h (fp32): 8 rows x 64 B per instruction
+              const int rr = i * 8 + (lane >> 2), k = lane & 3;
+              const float4 v = *reinterpret_cast<const float4*>(wst + rr * 64 + ((k ^ ((rr >> 1) & 3)) << 4));
+              if (row0 + rr < p.M) *reinterpret_cast<float4*>(p.gru_hnew + (row0 + rr) * H + u0 + k * 4) = v;
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {                          // bf16 pieces: 16 rows x 32 B per instruction
+              const int rr = i * 16 + (lane >> 1), k = lane & 1;
+              const int so = rr * 32 + ((k ^ ((rr >> 2) & 1)) << 4);
+              if (row0 + rr < p.M) {
+                const long grow = row0 + rr;
+                *reinterpret_cast<uint4*>(p.gru_hbnew + grow * p.gru_ldhbn + u0 + k * 8) =
+                    *reinterpret_cast<const uint4*>(wst + 2048 + so);
+                if (p.gru_out)
+                  *reinterpret_cast<uint4*>(p.gru_out + grow * p.gru_ldout + u0 + k * 8) =
+                      *reinterpret_cast<const uint4*>(wst + 3072 + so);
+                __nv_bfloat16* gp = p.gru_gates + grow * p.gru_ldg + (long)n_blk * BN + c + k * 8;
+#pragma unroll
+                for (int g4 = 0; g4 < 4; ++g4)
+                  *reinterpret_cast<uint4*>(gp + g4 * UB) = *reinterpret_cast<const uint4*>(wst + 4096 + g4 * 1024 + so);
+              }
+            }
+            __syncwarp();
           }
         }
       } else if constexpr (MODE == MODE_PLAIN || MODE == MODE_DREL) {
@@ -872,15 +906,16 @@ static int launch_gru_bn(const GruStepArgs& a, cudaStream_t stream) {
   e = make_tmap_2d_bf16(&tmB, a.Wcat, (uint64_t)(4 * H), (uint64_t)(a.Kx + (H + 7) / 8 * 8), (uint64_t)a.ldw, BN);
   if (e) return e;
   constexpr int STAGE_BYTES = A_STAGE_BYTES + BN * BK * 2;
-  int stages = (227 * 1024 - 1024 - (int)sizeof(PipeBars) - 2 * BN * 4) / STAGE_BYTES;
+  constexpr int GRU_STAGE_BYTES = 8 * 8192;   // warp-private store-staging tiles of the epilogue
+  int stages = (227 * 1024 - 1024 - (int)sizeof(PipeBars) - 2 * BN * 4 - GRU_STAGE_BYTES) / STAGE_BYTES;
   if (stages > 6) stages = 6;
   p.stages = stages;
-  const int smem_bytes = 1024 + stages * STAGE_BYTES + 2 * BN * 4 + (int)sizeof(PipeBars);
+  const int smem_bytes = 1024 + stages * STAGE_BYTES + 2 * BN * 4 + GRU_STAGE_BYTES + (int)sizeof(PipeBars);
   auto kern = gemm_tn_kernel<BN, MODE_GRU, 1>;
   GTOS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   int grid = p.units < num_sms() ? p.units : num_sms();
   if (grid <= 0) return GTOS_OK;
-  GTOS_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)smem_bytes, stream, 1, tmA, tmB, tmH, tmH, tmB, p));
+  GTOS_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(tn_threads<MODE_GRU>()), (size_t)smem_bytes, stream, 1, tmA, tmB, tmH, tmH, tmB, p));
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
 }

@@ -50,53 +50,111 @@ int gru_weight_prep(const float* w_ih, const float* w_hh, const float* b_ih, con
 // dh_tot = dh + dout_t ;  n,z,r chain rule ; dh_prev = dh_tot * z (the W_hh^T dgh term is added by a
 // following GEMM with accumulate) ; finished rows pass dh through untouched and emit zero gate grads.
 // gates: bf16 [R, 4H] as saved by the fused step kernel (blocks of UB units: [r | z | n | W_hn h + b_hn]).
-__global__ void gru_gate_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ dout_t, long lddout,
-                                    const __nv_bfloat16* __restrict__ gates, const float* __restrict__ h_prev,
-                                    const long long* __restrict__ lengths, int t, float* __restrict__ dh_prev,
-                                    __nv_bfloat16* __restrict__ dgi, long lddgi, __nv_bfloat16* __restrict__ dgh,
-                                    long lddgh, float* __restrict__ db_ih, float* __restrict__ db_hh, long R, int Hh,
-                                    int UB, int rows_per_block) {
-  // thread = hidden unit c (coalesced across c), loop over this block's rows; the bias gradients (column sums of the
-  // gate gradients) are accumulated in registers and flushed with one atomic per (block, column)
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= Hh) return;
+__global__ void __launch_bounds__(256) gru_gate_bwd_kernel(
+    const float* __restrict__ dh, const float* __restrict__ dout_t, long lddout, const __nv_bfloat16* __restrict__ gates,
+    const float* __restrict__ h_prev, const long long* __restrict__ lengths, int t, float* __restrict__ dh_prev,
+    __nv_bfloat16* __restrict__ dgi, long lddgi, __nv_bfloat16* __restrict__ dgh, long lddgh, float* __restrict__ db_ih,
+    float* __restrict__ db_hh, long R, int Hh, int UB, int rows_per_block) {
+  // lane = 8 consecutive hidden units (16-byte bf16 / 32-byte fp32 accesses), warp = one row at a time, 8 rows of the
+  // block in flight; the bias gradients (column sums of the gate gradients) are accumulated in registers, combined
+  // across the block's warps in shared memory and flushed with one atomic per (block, column)
+  __shared__ float s_sum[8][4][256 + 8];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int c0 = (blockIdx.x * 32 + lane) * 8;               // first hidden unit of this lane
+  const bool on = c0 < Hh;
   const long r0 = (long)blockIdx.y * rows_per_block;
   const long r1 = r0 + rows_per_block < R ? r0 + rows_per_block : R;
-  float s_r = 0.f, s_z = 0.f, s_n = 0.f, s_h = 0.f;
-  const int goff = (c / UB) * 4 * UB + (c % UB);
-  for (long r = r0; r < r1; ++r) {
-    const long idx = r * Hh + c;
-    const bool live = lengths[r] > t;
-    float d = dh ? dh[idx] : 0.f;
-    float dar = 0.f, daz = 0.f, dan = 0.f, dhn = 0.f, dprev = d;
-    if (live) {
-      if (dout_t) d += dout_t[r * lddout + c];
-      const __nv_bfloat16* gp = gates + r * 4L * Hh + goff;
-      const float gr = __bfloat162float(gp[0]), gz = __bfloat162float(gp[UB]), gn = __bfloat162float(gp[2 * UB]);
-      const float hnn = __bfloat162float(gp[3 * UB]);
-      const float hp = h_prev[idx];
-      const float dn = d * (1.f - gz);
-      const float dz = d * (hp - gn);
-      dan = dn * (1.f - gn * gn);
-      daz = dz * gz * (1.f - gz);
-      dar = dan * hnn * gr * (1.f - gr);
-      dhn = dan * gr;
-      dprev = d * gz;
+  float s_r[8], s_z[8], s_n[8], s_h[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) s_r[u] = s_z[u] = s_n[u] = s_h[u] = 0.f;
+  const int goff = on ? (c0 / UB) * 4 * UB + (c0 % UB) : 0;
+  if (on) {
+    for (long r = r0 + wib; r < r1; r += 8) {
+      const long idx = r * Hh + c0;
+      const bool live = lengths[r] > t;
+      float d[8], dar[8], daz[8], dan[8], dhn[8], dprev[8];
+      {
+        const float4 a = dh ? *reinterpret_cast<const float4*>(dh + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 b = dh ? *reinterpret_cast<const float4*>(dh + idx + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { dar[u] = daz[u] = dan[u] = dhn[u] = 0.f; dprev[u] = d[u]; }
+      if (live) {
+        if (dout_t) {
+          const float4 a = *reinterpret_cast<const float4*>(dout_t + r * lddout + c0);
+          const float4 b = *reinterpret_cast<const float4*>(dout_t + r * lddout + c0 + 4);
+          d[0] += a.x; d[1] += a.y; d[2] += a.z; d[3] += a.w; d[4] += b.x; d[5] += b.y; d[6] += b.z; d[7] += b.w;
+        }
+        const __nv_bfloat16* gp = gates + r * 4L * Hh + goff;
+        const uint4 vr = *reinterpret_cast<const uint4*>(gp), vz = *reinterpret_cast<const uint4*>(gp + UB);
+        const uint4 vn = *reinterpret_cast<const uint4*>(gp + 2 * UB), vh = *reinterpret_cast<const uint4*>(gp + 3 * UB);
+        const float4 ha = *reinterpret_cast<const float4*>(h_prev + idx);
+        const float4 hb = *reinterpret_cast<const float4*>(h_prev + idx + 4);
+        const float hp[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+        const __nv_bfloat162* pr = reinterpret_cast<const __nv_bfloat162*>(&vr);
+        const __nv_bfloat162* pz = reinterpret_cast<const __nv_bfloat162*>(&vz);
+        const __nv_bfloat162* pn = reinterpret_cast<const __nv_bfloat162*>(&vn);
+        const __nv_bfloat162* ph = reinterpret_cast<const __nv_bfloat162*>(&vh);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 fr = __bfloat1622float2(pr[q]), fz = __bfloat1622float2(pz[q]);
+          const float2 fn = __bfloat1622float2(pn[q]), fh = __bfloat1622float2(ph[q]);
+          const float gr2[2] = {fr.x, fr.y}, gz2[2] = {fz.x, fz.y}, gn2[2] = {fn.x, fn.y}, hn2[2] = {fh.x, fh.y};
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int u = 2 * q + e;
+            const float gr = gr2[e], gz = gz2[e], gn = gn2[e], hnn = hn2[e];
+            const float dn = d[u] * (1.f - gz);
+            const float dz = d[u] * (hp[u] - gn);
+            dan[u] = dn * (1.f - gn * gn);
+            daz[u] = dz * gz * (1.f - gz);
+            dar[u] = dan[u] * hnn * gr * (1.f - gr);
+            dhn[u] = dan[u] * gr;
+            dprev[u] = d[u] * gz;
+          }
+        }
+      }
+      *reinterpret_cast<float4*>(dh_prev + idx) = make_float4(dprev[0], dprev[1], dprev[2], dprev[3]);
+      *reinterpret_cast<float4*>(dh_prev + idx + 4) = make_float4(dprev[4], dprev[5], dprev[6], dprev[7]);
+#define GTOS_PK8(v) make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]))
+      const uint4 ur = GTOS_PK8(dar), uz = GTOS_PK8(daz), un = GTOS_PK8(dan), uh = GTOS_PK8(dhn);
+#undef GTOS_PK8
+      *reinterpret_cast<uint4*>(dgi + r * lddgi + c0) = ur;
+      *reinterpret_cast<uint4*>(dgi + r * lddgi + Hh + c0) = uz;
+      *reinterpret_cast<uint4*>(dgi + r * lddgi + 2 * Hh + c0) = un;
+      *reinterpret_cast<uint4*>(dgh + r * lddgh + c0) = ur;
+      *reinterpret_cast<uint4*>(dgh + r * lddgh + Hh + c0) = uz;
+      *reinterpret_cast<uint4*>(dgh + r * lddgh + 2 * Hh + c0) = uh;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { s_r[u] += dar[u]; s_z[u] += daz[u]; s_n[u] += dan[u]; s_h[u] += dhn[u]; }
     }
-    dh_prev[idx] = dprev;
-    dgi[r * lddgi + c] = __float2bfloat16(dar);
-    dgi[r * lddgi + Hh + c] = __float2bfloat16(daz);
-    dgi[r * lddgi + 2 * Hh + c] = __float2bfloat16(dan);
-    dgh[r * lddgh + c] = __float2bfloat16(dar);
-    dgh[r * lddgh + Hh + c] = __float2bfloat16(daz);
-    dgh[r * lddgh + 2 * Hh + c] = __float2bfloat16(dhn);
-    s_r += dar; s_z += daz; s_n += dan; s_h += dhn;
   }
-  if (db_ih) {
-    atomicAdd(&db_ih[c], s_r); atomicAdd(&db_ih[Hh + c], s_z); atomicAdd(&db_ih[2 * Hh + c], s_n);
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    s_sum[wib][0][lane * 8 + u] = s_r[u];
+    s_sum[wib][1][lane * 8 + u] = s_z[u];
+    s_sum[wib][2][lane * 8 + u] = s_n[u];
+    s_sum[wib][3][lane * 8 + u] = s_h[u];
   }
-  if (db_hh) {
-    atomicAdd(&db_hh[c], s_r); atomicAdd(&db_hh[Hh + c], s_z); atomicAdd(&db_hh[2 * Hh + c], s_h);
+  __syncthreads();
+  // thread = one of the block's 256 columns
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < Hh) {
+    float tot[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += s_sum[w][k][threadIdx.x];
+      tot[k] = v;
+    }
+    if (db_ih) {
+      atomicAdd(&db_ih[c], tot[0]); atomicAdd(&db_ih[Hh + c], tot[1]); atomicAdd(&db_ih[2 * Hh + c], tot[2]);
+    }
+    if (db_hh) {
+      atomicAdd(&db_hh[c], tot[0]); atomicAdd(&db_hh[Hh + c], tot[1]); atomicAdd(&db_hh[2 * Hh + c], tot[3]);
+    }
   }
 }
 
@@ -104,12 +162,12 @@ int gru_gate_bwd(const float* dh, const float* dout_t, long lddout, const void* 
                  const long long* lengths, int t, float* dh_prev, void* dgi_bf16, long lddgi, void* dgh_bf16,
                  long lddgh, float* db_ih, float* db_hh, long R, int Hh, cudaStream_t st) {
   if (R == 0) return GTOS_OK;
-  GTOS_REQUIRE(Hh % 16 == 0, "gru_gate_bwd: hidden size must be a multiple of 16");
+  GTOS_REQUIRE(Hh % 16 == 0 && lddgi % 8 == 0 && lddgh % 8 == 0 && (!dout_t || lddout % 4 == 0),
+               "gru_gate_bwd: hidden size must be a multiple of 16 and the row strides 16-byte aligned");
   const int UB = (Hh % 64 == 0) ? 64 : 16;
-  const int thr = Hh < 256 ? ((Hh + 31) / 32 * 32) : 256;
-  const int rpb = 32;
-  dim3 grid((Hh + thr - 1) / thr, (unsigned)((R + rpb - 1) / rpb));
-  gru_gate_bwd_kernel<<<grid, thr, 0, st>>>(dh, dout_t, lddout, reinterpret_cast<const __nv_bfloat16*>(gates), h_prev,
+  const int rpb = 64;
+  dim3 grid((Hh + 255) / 256, (unsigned)((R + rpb - 1) / rpb));
+  gru_gate_bwd_kernel<<<grid, 256, 0, st>>>(dh, dout_t, lddout, reinterpret_cast<const __nv_bfloat16*>(gates), h_prev,
                                             lengths, t, dh_prev, reinterpret_cast<__nv_bfloat16*>(dgi_bf16), lddgi,
                                             reinterpret_cast<__nv_bfloat16*>(dgh_bf16), lddgh, db_ih, db_hh, R, Hh, UB, rpb);
   GTOS_LAUNCH_CHECK();

@@ -59,6 +59,11 @@ __device__ __forceinline__ AttnSmem carve(uint8_t* base, int L, int dc, int rows
   return s;
 }
 
+// These kernels are instruction-bound (ncu: ~14 M warp instructions per launch, 40 % of them integer division of
+// a flat thread index).  All 2-D loops therefore split the thread index with shifts: `qs` = log2 of the number
+// of lanes per row rounded up to a power of two (lanes beyond the row width idle).
+__device__ __forceinline__ int log2_ceil(int n) { return n <= 1 ? 0 : 32 - __clz(n - 1); }
+
 // rows [r0, r0+nr16) x dims [c0, c0+dc) of a [len, B, ld] fp32 projection for (b, h) -> bf16 dst[nr16][dstr];
 // rows >= len and columns >= dc (up to r16(dc)) are zero-filled.  16-byte global loads when alignment allows.
 __device__ __forceinline__ void load_rows_bf16(__nv_bfloat16* dst, int dstr, const float* src, long ld, int B, int b,
@@ -66,14 +71,18 @@ __device__ __forceinline__ void load_rows_bf16(__nv_bfloat16* dst, int dstr, con
   const int dc16 = r16(dc);
   const bool vec = ((dc & 3) == 0) && ((ld & 3) == 0) && (((hoff + c0) & 3) == 0) &&
                    ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
-  const int q = dc16 >> 2, total = nr16 * q;
-#pragma unroll 4
-  for (int idx = threadIdx.x; idx < total; idx += AT_THREADS) {
-    const int r = idx / q, d = (idx - r * q) * 4;
+  const int q = dc16 >> 2;                       // float4 groups per row
+  const int qs = log2_ceil(q);
+  const int rstep = AT_THREADS >> qs;
+  const int d = (threadIdx.x & ((1 << qs) - 1)) * 4;
+  if (d >= dc16) return;
+  const float* colp = src + (long)b * ld + hoff + c0 + d;
+#pragma unroll 2
+  for (int r = threadIdx.x >> qs; r < nr16; r += rstep) {
     const int t = r0 + r;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (t < len && d < dc) {
-      const float* p = src + ((long)t * B + b) * ld + hoff + c0 + d;
+      const float* p = colp + (long)t * B * ld;
       if (vec) {
         v = *reinterpret_cast<const float4*>(p);
       } else {
@@ -84,6 +93,36 @@ __device__ __forceinline__ void load_rows_bf16(__nv_bfloat16* dst, int dstr, con
       }
     }
     *reinterpret_cast<uint2*>(dst + (size_t)r * dstr + d) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+}
+
+// sc[r][0..dc) (fp32, smem, row stride lstr) * scale -> dst[((row0 + r) * B + b) * ld + col + d] (+ optional bf16 copy)
+__device__ __forceinline__ void store_rows_f32(float* dst, __nv_bfloat16* dst_b, long ld, int B, int b, int col, int row0,
+                                               int nrows, int dc, const float* sc, int lstr, float scale) {
+  const bool vec = ((dc & 3) == 0) && ((ld & 3) == 0) && ((col & 3) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
+                   (!dst_b || (reinterpret_cast<uintptr_t>(dst_b) & 7) == 0);
+  if (vec) {
+    const int q = dc >> 2;
+    const int qs = log2_ceil(q);
+    const int rstep = AT_THREADS >> qs;
+    const int d = (threadIdx.x & ((1 << qs) - 1)) * 4;
+    if (d >= dc) return;
+    for (int r = threadIdx.x >> qs; r < nrows; r += rstep) {
+      float4 v = *reinterpret_cast<const float4*>(sc + (size_t)r * lstr + d);
+      v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+      const long o = ((long)(row0 + r) * B + b) * ld + col + d;
+      *reinterpret_cast<float4*>(dst + o) = v;
+      if (dst_b) *reinterpret_cast<uint2*>(dst_b + o) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    }
+  } else {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = warp; r < nrows; r += AT_WARPS)
+      for (int d = lane; d < dc; d += 32) {
+        const float v = sc[(size_t)r * lstr + d] * scale;
+        const long o = ((long)(row0 + r) * B + b) * ld + col + d;
+        dst[o] = v;
+        if (dst_b) dst_b[o] = __float2bfloat16(v);
+      }
   }
 }
 
@@ -142,10 +181,9 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnArgs a, 
 
   // ---- scores into sc ----
   if (a.scores_jt) {
-    for (int idx = threadIdx.x; idx < s.L16 * s.R16; idx += AT_THREADS) {
-      const int j = idx / s.R16, r = idx % s.R16;
-      s.sc[(size_t)r * s.lstr + j] = (r < nrows && j < S) ? a.scores_jt[((long)bh * S + j) * a.T + t0 + r] : 0.f;
-    }
+    for (int j = warp; j < s.L16; j += AT_WARPS)
+      for (int r = lane; r < s.R16; r += 32)
+        s.sc[(size_t)r * s.lstr + j] = (r < nrows && j < S) ? a.scores_jt[((long)bh * S + j) * a.T + t0 + r] : 0.f;
   } else {
     for (int c0 = 0; c0 < a.hd; c0 += dc) {
       __syncthreads();
@@ -161,12 +199,6 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnArgs a, 
   const unsigned long long seed = a.p_drop > 0.f ? reinterpret_cast<const unsigned long long*>(a.seed_ptr)[0] + a.seed_off : 0ull;
   const float ks = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
   const float sscale = a.scores_jt ? 1.f : a.scale;
-  for (int idx = threadIdx.x; idx < nrows * S; idx += AT_THREADS) {
-    const int r = idx / S, j = idx - r * S;
-    float* p = s.sc + (size_t)r * s.lstr + j;
-    *p = is_masked(a, b, t0 + r, j) ? -INFINITY : *p * sscale;
-  }
-  __syncthreads();
   for (int r = warp; r < s.R16; r += AT_WARPS) {
     float* w = s.sc + (size_t)r * s.lstr;
     __nv_bfloat16* pw = s.pb + (size_t)r * s.lstr;
@@ -176,7 +208,11 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnArgs a, 
     }
     const int t = t0 + r;
     float mx = -INFINITY;
-    for (int j = lane; j < S; j += 32) mx = fmaxf(mx, w[j]);
+    for (int j = lane; j < S; j += 32) {         // masks + scale fused into the max pass (same lane owns w[j] below)
+      const float v = is_masked(a, b, t, j) ? -INFINITY : w[j] * sscale;
+      w[j] = v;
+      mx = fmaxf(mx, v);
+    }
     mx = warp_max(mx);
     float sum = 0.f;
     for (int j = lane; j < S; j += 32) {
@@ -207,13 +243,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnArgs a, 
     __syncthreads();
     tile_mm<false>(s.pb, s.lstr, s.yb, s.dstr, s.sc, s.lstr, s.R16, dc16, s.L16, false);
     __syncthreads();
-    for (int idx = threadIdx.x; idx < nrows * dc; idx += AT_THREADS) {
-      const int r = idx / dc, d = idx - r * dc;
-      const float v = s.sc[(size_t)r * s.lstr + d];
-      const long o = ((long)(t0 + r) * a.B + b) * a.ldo + hoff + c0 + d;
-      a.out[o] = v;
-      if (ob) ob[o] = __float2bfloat16(v);
-    }
+    store_rows_f32(a.out, ob, a.ldo, a.B, b, hoff + c0, t0, nrows, dc, s.sc, s.lstr, 1.f);
   }
 }
 
@@ -309,10 +339,9 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_q_kernel(const AttnBwdArg
   __syncthreads();
   if (g.dscores_jt) {
     // transposed store for the fused relation backward kernel: [B,H,S(j),T(i)], coalesced along i
-    for (int idx = threadIdx.x; idx < S * s.R16; idx += AT_THREADS) {
-      const int j = idx / s.R16, r = idx % s.R16;
-      if (r < nrows) g.dscores_jt[((long)bh * S + j) * a.T + t0 + r] = s.sc[(size_t)r * s.lstr + j];
-    }
+    for (int j = warp; j < S; j += AT_WARPS)
+      for (int r = lane; r < nrows; r += 32)
+        g.dscores_jt[((long)bh * S + j) * a.T + t0 + r] = s.sc[(size_t)r * s.lstr + j];
   }
   if (g.dq) {
     for (int c0 = 0; c0 < a.hd; c0 += dc) {
@@ -321,10 +350,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_q_kernel(const AttnBwdArg
       __syncthreads();
       tile_mm<false>(s.pb, s.lstr, s.yb, s.dstr, s.sc, s.lstr, s.R16, dc16, s.L16, false);
       __syncthreads();
-      for (int idx = threadIdx.x; idx < nrows * dc; idx += AT_THREADS) {
-        const int r = idx / dc, d = idx - r * dc;
-        g.dq[((long)(t0 + r) * a.B + b) * g.lddq + hoff + c0 + d] = s.sc[(size_t)r * s.lstr + d] * a.scale;
-      }
+      store_rows_f32(g.dq, nullptr, g.lddq, a.B, b, hoff + c0, t0, nrows, dc, s.sc, s.lstr, a.scale);
     }
   }
 }
@@ -347,44 +373,39 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_kv_kernel(const AttnBwdAr
   const float ks = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
 
   // pb[jr][t] = Pd[t][j0+jr]  (transposed while loading; coalesced over jr in global)
-  for (int idx = threadIdx.x; idx < s.L16 * s.R16; idx += AT_THREADS) {
-    const int t = idx / s.R16, jr = idx % s.R16;
-    float p = 0.f;
-    if (jr < nrows && t < T) {
-      const long pi = ((long)bh * T + t) * S + j0 + jr;
-      p = a.probs[pi];
-      if (a.p_drop > 0.f) p = (rng_uniform(seed, (unsigned long long)pi) >= a.p_drop) ? p * ks : 0.f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int t = warp; t < s.L16; t += AT_WARPS)
+    for (int jr = lane; jr < s.R16; jr += 32) {
+      float p = 0.f;
+      if (jr < nrows && t < T) {
+        const long pi = ((long)bh * T + t) * S + j0 + jr;
+        p = a.probs[pi];
+        if (a.p_drop > 0.f) p = (rng_uniform(seed, (unsigned long long)pi) >= a.p_drop) ? p * ks : 0.f;
+      }
+      s.pb[(size_t)jr * s.lstr + t] = __float2bfloat16(p);
     }
-    s.pb[(size_t)jr * s.lstr + t] = __float2bfloat16(p);
-  }
   for (int c0 = 0; c0 < a.hd; c0 += dc) {
     __syncthreads();
     load_rows_bf16(s.yb, s.dstr, g.dout, g.lddo, a.B, b, hoff, 0, s.L16, T, c0, dc);
     __syncthreads();
     tile_mm<false>(s.pb, s.lstr, s.yb, s.dstr, s.sc, s.lstr, s.R16, dc16, s.L16, false);
     __syncthreads();
-    for (int idx = threadIdx.x; idx < nrows * dc; idx += AT_THREADS) {
-      const int r = idx / dc, d = idx - r * dc;
-      g.dv[((long)(j0 + r) * a.B + b) * g.lddv + hoff + c0 + d] = s.sc[(size_t)r * s.lstr + d];
-    }
+    store_rows_f32(g.dv, nullptr, g.lddv, a.B, b, hoff + c0, j0, nrows, dc, s.sc, s.lstr, 1.f);
   }
   if (g.dk) {
     __syncthreads();
-    for (int idx = threadIdx.x; idx < s.L16 * s.R16; idx += AT_THREADS) {
-      const int t = idx / s.R16, jr = idx % s.R16;
-      const float v = (jr < nrows && t < T) ? g.dscores_ts[((long)bh * T + t) * S + j0 + jr] * a.scale : 0.f;
-      s.pb[(size_t)jr * s.lstr + t] = __float2bfloat16(v);
-    }
+    for (int t = warp; t < s.L16; t += AT_WARPS)
+      for (int jr = lane; jr < s.R16; jr += 32) {
+        const float v = (jr < nrows && t < T) ? g.dscores_ts[((long)bh * T + t) * S + j0 + jr] * a.scale : 0.f;
+        s.pb[(size_t)jr * s.lstr + t] = __float2bfloat16(v);
+      }
     for (int c0 = 0; c0 < a.hd; c0 += dc) {
       __syncthreads();
       load_rows_bf16(s.yb, s.dstr, a.q, a.ldq, a.B, b, hoff, 0, s.L16, T, c0, dc);
       __syncthreads();
       tile_mm<false>(s.pb, s.lstr, s.yb, s.dstr, s.sc, s.lstr, s.R16, dc16, s.L16, false);
       __syncthreads();
-      for (int idx = threadIdx.x; idx < nrows * dc; idx += AT_THREADS) {
-        const int r = idx / dc, d = idx - r * dc;
-        g.dk[((long)(j0 + r) * a.B + b) * g.lddk + hoff + c0 + d] = s.sc[(size_t)r * s.lstr + d];
-      }
+      store_rows_f32(g.dk, nullptr, g.lddk, a.B, b, hoff + c0, j0, nrows, dc, s.sc, s.lstr, 1.f);
     }
   }
 }

@@ -5,6 +5,7 @@ owns the memory (torch.empty) and the autograd graph.  No torch math on the data
 """
 import ctypes as C
 import itertools
+import os
 import math
 
 import torch
@@ -42,6 +43,56 @@ def as_u8(mask):
         return None
     m = mask.contiguous()
     return m.view(torch.uint8) if m.dtype == torch.bool else m.to(torch.uint8)
+
+
+# ---- second stream for work that is off the critical path of a backward pass -----------------
+# The weight-gradient GEMM of a Linear (dW = dY^T X) and its input-gradient GEMM (dX = dY W) are independent and
+# each is latency-bound at this path's sizes (M = 2.6-3.8 k rows: 120 CTAs, 8 k-blocks).  `fork()` lets the dW side
+# run on a second stream; `join()` before the Function returns makes the caller's stream wait for it, so nothing
+# escapes a Function unfinished (under CUDA-graph capture these are plain fork/join edges of the graph).
+_side_streams = {}
+# Measured on config 2 (bench.py, CUDA-graph step): 10.12 ms with, 10.34 ms without - inside run-to-run noise, because
+# every tcgen05 GEMM CTA owns its SM (~200 KB of shared memory), so two GEMMs interleave rather than overlap.  Off by
+# default (GTOS_SIDE_STREAM=1 enables it); the GPU tests pass in both modes.
+_side_enabled = os.environ.get("GTOS_SIDE_STREAM", "0") == "1"
+
+
+class _Fork:
+    def __init__(self):
+        self.main = torch.cuda.current_stream()
+        self.side = None
+        if _side_enabled:
+            key = self.main.device.index
+            if key not in _side_streams:
+                _side_streams[key] = torch.cuda.Stream(device=self.main.device)
+            self.side = _side_streams[key]
+        self._ctx = None
+        self.used = False
+
+    def __enter__(self):
+        if self.side is not None:
+            self.side.wait_stream(self.main)          # everything queued so far (the operands) is visible
+            self._ctx = torch.cuda.stream(self.side)
+            self._ctx.__enter__()
+            self.used = True
+        return self
+
+    def __exit__(self, *exc):
+        if self._ctx is not None:
+            self._ctx.__exit__(*exc)
+            self._ctx = None
+        return False
+
+    def join(self):
+        if self.used:
+            self.main.wait_stream(self.side)
+            self.used = False
+
+
+def fork():
+    """with fork() as f: <launches on the side stream> ... f.join() before the results are handed on.
+    Outputs written inside the block must be allocated BEFORE it (on the caller's stream)."""
+    return _Fork()
 
 
 # ---- dropout RNG: one device-resident 64-bit seed + a per-call-site offset -----------------
@@ -139,8 +190,9 @@ def gemm_nn(A, B, M, N, out=None, a_off=0, b_off=0):
     return out
 
 
-def colsum(x2d):
-    out = torch.empty(x2d.shape[1], dtype=torch.float32, device=x2d.device)
+def colsum(x2d, out=None):
+    if out is None:
+        out = torch.empty(x2d.shape[1], dtype=torch.float32, device=x2d.device)
     fn = _lib.load().gtos_colsum_bf16 if x2d.dtype == torch.bfloat16 else _lib.load().gtos_colsum
     _lib.check(fn(_p(x2d), x2d.stride(0), _p(out), x2d.shape[0], x2d.shape[1], _st()), "colsum")
     return out
@@ -253,14 +305,22 @@ class FFNFn(torch.autograd.Function):
         dy2 = dy.contiguous().view(-1, D)
         M = dy2.shape[0]
         dyb, db2 = cast_colsum(dy2)
-        dW2 = gemm_nn(dyb, hb, D, Fd)
+        dev = dy.device
+        dW2 = torch.empty(D, Fd, dtype=torch.float32, device=dev)
+        dW1 = torch.empty(Fd, D, dtype=torch.float32, device=dev)
+        db1f = torch.empty(_up8(Fd), dtype=torch.float32, device=dev)
+        with fork() as f2:
+            gemm_nn(dyb, hb, D, Fd, out=dW2)
         dh, _ = gemm_tn(dyb, W2t, Fd)                       # [M,F] = dy @ W2
-        dhb = torch.empty(M, _up8(Fd), dtype=torch.bfloat16, device=dy.device)
+        dhb = torch.empty(M, _up8(Fd), dtype=torch.bfloat16, device=dev)
         _lib.check(_lib.load().gtos_relu_drop_bwd(_p(dh), _p(hb), None, _p(dhb), dh.numel(), p, _st()), "relu_drop_bwd")
-        dW1 = gemm_nn(dhb, xb2, Fd, D)
-        db1 = colsum(dhb)[:Fd]
+        with fork() as f1:
+            gemm_nn(dhb, xb2, Fd, D, out=dW1)
+            colsum(dhb, out=db1f)
         dx, _ = gemm_tn(dhb, W1t, D)
-        return dx.view(shape), None, dW1, db1, dW2, db2, None
+        f2.join()
+        f1.join()
+        return dx.view(shape), None, dW1, db1f[:Fd], dW2, db2, None
 
 
 def ffn(x, xb, W1, b1, W2, b2, p=0.0):
@@ -329,7 +389,9 @@ class RelAttnFn(torch.autograd.Function):
         NB = N * B
         dout2 = dout.contiguous().view(NB, D)
         doutb, db_out = cast_colsum(dout2)
-        dW_out = gemm_nn(doutb, attb, D, D)
+        dW_out = torch.empty(D, D, dtype=torch.float32, device=dev)
+        with fork() as f_out:
+            gemm_nn(doutb, attb, D, D, out=dW_out)
         datt, _ = gemm_tn(doutb, Wot, D)                                           # [NB, D]
         dqkv = torch.empty(NB, 3 * D, dtype=torch.float32, device=dev)
         ds_jt = torch.empty(B, H, N, N, dtype=torch.float32, device=dev)
@@ -373,11 +435,17 @@ class RelAttnFn(torch.autograd.Function):
             _lib.check(lib.gtos_rel_segsum(_p(G), _p(bk.order), _p(bk.keys), N * N * B, 2 * D, s_ptr, L * 2 * D,
                                            _p(acc.spill), _st()), "rel_segsum")
             dW_rel = torch.empty(2 * D, D, dtype=torch.float32, device=dev)
-            _lib.check(lib.gtos_rel_dw_bank(s_ptr, L * 2 * D, _p(bk.bankb), _p(dW_rel), R, D, H, _st()), "rel_dw_bank")
-            acc.Wcat[:, c0:c0 + 2 * D].copy_(WpermT[:, :2 * D])
+            dW_in = torch.empty(3 * D, D, dtype=torch.float32, device=dev)
+            with fork() as f_rel:
+                _lib.check(lib.gtos_rel_dw_bank(s_ptr, L * 2 * D, _p(bk.bankb), _p(dW_rel), R, D, H, _st()), "rel_dw_bank")
+                acc.Wcat[:, c0:c0 + 2 * D].copy_(WpermT[:, :2 * D])
             dqkvb, db_in = cast_colsum(dqkv)
-            dW_in = gemm_nn(dqkvb, xb2, 3 * D, D)
+            with fork() as f_in:
+                gemm_nn(dqkvb, xb2, 3 * D, D, out=dW_in)
             dx, _ = gemm_tn(dqkvb, Wit, D)
+            f_out.join()
+            f_rel.join()
+            f_in.join()
             return (dx.view(N, B, D), None, None, None, None, None, dW_in, db_in, dW_rel, dW_out, db_out, None, None,
                     None, None, None)
         if ctx.rel_acc is not None:
@@ -398,6 +466,7 @@ class RelAttnFn(torch.autograd.Function):
         dqkvb, db_in = cast_colsum(dqkv)
         dW_in = gemm_nn(dqkvb, xb2, 3 * D, D)
         dx, _ = gemm_tn(dqkvb, Wit, D)
+        f_out.join()
         return (dx.view(N, B, D), None, d_rel, None, None, None, dW_in, db_in, dW_rel, dW_out, db_out, None, None,
                 None, None, None)
 
@@ -570,7 +639,9 @@ class MHAFn(torch.autograd.Function):
         dev = dout.device
         dout2 = dout.contiguous().view(T * B, D)
         doutb, db_out = cast_colsum(dout2)
-        dW_out = gemm_nn(doutb, attb, D, D)
+        dW_out = torch.empty(D, D, dtype=torch.float32, device=dev)
+        with fork() as f_out:
+            gemm_nn(doutb, attb, D, D, out=dW_out)
         datt, _ = gemm_tn(doutb, Wot, D)
         if off2:
             dropout_f32(datt, p, seed, off2, out=datt)
@@ -601,17 +672,21 @@ class MHAFn(torch.autograd.Function):
         dW_in = torch.empty(3 * D, D, dtype=torch.float32, device=dev)
         if self_attn:
             dprojb, db_in = cast_colsum(dproj)
-            gemm_nn(dprojb, qb2, 3 * D, D, out=dW_in)
+            with fork() as f_in:
+                gemm_nn(dprojb, qb2, 3 * D, D, out=dW_in)
             dq_in, _ = gemm_tn(dprojb, Wit, D)
             dk_in = None
         else:
             (dpqb, dbq), (dpkvb, dbkv) = cast_colsum(dpq), cast_colsum(dpkv)
-            gemm_nn(dpqb, qb2, D, D, out=dW_in[:D])
-            gemm_nn(dpkvb, kb2, 2 * D, D, out=dW_in[D:])
             db_in = torch.cat([dbq, dbkv])
+            with fork() as f_in:
+                gemm_nn(dpqb, qb2, D, D, out=dW_in[:D])
+                gemm_nn(dpkvb, kb2, 2 * D, D, out=dW_in[D:])
             dq_in, _ = gemm_tn(dpqb, Wit, D, K=D)                                   # Wt[:, :D]
             dk_in, _ = gemm_tn(dpkvb, Wit, D, K=2 * D, b_off=D)                     # Wt[:, D:3D]
             dk_in = dk_in.view(S, B, D)
+        f_out.join()
+        f_in.join()
         return (dq_in.view(T, B, D), None, dk_in, None, None, None, None, dW_in, db_in, dW_out, db_out, None, None,
                 None, None)
 
@@ -783,9 +858,12 @@ class LinearFn(torch.autograd.Function):
         shape, N, K, has_b = ctx.meta
         dy2 = dy.contiguous().view(-1, N)
         dyb, db = cast_colsum(dy2)
-        dW = gemm_nn(dyb, xb, N, K)
+        dW = torch.empty(N, K, dtype=torch.float32, device=dy.device)
+        with fork() as f:
+            gemm_nn(dyb, xb, N, K, out=dW)
         db = db if has_b else None
         dx, _ = gemm_tn(dyb, Wt, K)
+        f.join()
         return dx.view(shape), dW, db
 
 

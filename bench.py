@@ -553,7 +553,122 @@ def breakdown(args, w, cfg, model, static, meta, dev, lib):
     out["relation_kernels"] = {"rel_score_sustained": sus,"rel_score_ms": ms_k, "rel_grad_ms": t_grad, "rel_drel_ms": t_drel, "rel_dw_ms": t_dw,
                                "tflops": {"rel_score": f / (ms_k * 1e-3), "rel_grad": f / (t_grad * 1e-3),
                                           "rel_drel": f / (t_drel * 1e-3), "rel_dw": f / (t_dw * 1e-3)}}
+    try:
+        out["decode_cfg5"] = decode_bench(args, w, cfg, model, dev, lib)
+    except Exception as e:                                   # the headline line must survive a failure of an extra leg
+        out["decode_cfg5"] = {"error": repr(e)[:300]}
+    try:
+        out["optimizer_step"] = optimizer_bench(model, dev, lib, pk)
+    except Exception as e:
+        out["optimizer_step"] = {"error": repr(e)[:300]}
     return out
+
+
+def decode_bench(args, w, cfg, model, dev, lib, B=256, K=8, S=40, steps=32):
+    """BASELINE.json config 5: beam-search decode, beam 8 x batch 256 = 2048 live hypotheses over pre-encoded ~40-node
+    graphs.  Times (a) gtos_b200.decode (K/V caches, ancestry table, device-side beam step, one CUDA graph per position)
+    and (b) the same step through the drop-in modules wired as the unchanged caller does (generator.py:120-167 with
+    search.py's index_select-ed memory, K/V re-projected every step) at the middle position."""
+    from gtos_b200.decode import BeamSearchDevice, DecodeEngine
+    D, V = w["D"], w["V"]
+    Hyp = B * K
+    was_training = model.training
+    model.eval()
+    try:
+        gen = torch.Generator().manual_seed(19940117)
+        graph = torch.randn(S, B, D, generator=gen).to(dev)
+        lens = torch.randint(S // 2, S + 1, (B,), generator=gen)
+        gmask = (torch.arange(S).unsqueeze(1) >= lens.unsqueeze(0)).to(dev)
+        probe = torch.tanh(torch.randn(1, B, D, generator=gen)).to(dev)
+        copy_seq = torch.randint(2, V + 16, (S, B), generator=gen).to(dev)
+        Wt = V + 16
+        emb = torch.randn(Wt, D, generator=gen).to(dev)
+        pos = torch.randn(steps, D, generator=gen).to(dev)
+
+        def embed_fn(tok, t):
+            return torch.nn.functional.layer_norm(emb[tok] + pos[t], (D,))
+
+        eng = DecodeEngine(model.snt_encoder, model.decoder, max_hyp=Hyp, max_steps=steps)
+        t0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0[0].record()
+        eng.set_memory(graph, gmask, probe, copy_seq, table_width=Wt)
+        t0[1].record()
+        bs = BeamSearchDevice(eng, K, steps, 1, end_id=3, unk_id=1, start_id=2, embed_fn=embed_fn, use_graphs=True)
+        l0 = lib.gtos_launch_count()
+        bs.capture()
+        launches = (lib.gtos_launch_count() - l0) / (steps + 2)
+        torch.cuda.synchronize()
+        ms_mem = t0[0].elapsed_time(t0[1])
+        best = None
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            bs.run(early_exit=False)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            best = ms if best is None else min(best, ms)
+        # (b) module path at position t_mid: prefix of t_mid + 1 rows, graph memory index_select-ed per hypothesis
+        t_mid = steps // 2
+        src = torch.arange(B, device=dev).repeat_interleave(K)
+        x = torch.nn.functional.layer_norm(torch.randn(t_mid + 1, Hyp, D, generator=gen), (D,)).to(dev)
+        ts = torch.nn.functional.layer_norm(torch.randn(t_mid + 1, Hyp, D, generator=gen), (D,)).to(dev)
+        model.decoder.token_generator.static_tot_ext, keep = Wt, model.decoder.token_generator.static_tot_ext
+
+        def module_step():
+            with torch.no_grad():
+                g_sel, m_sel = graph.index_select(1, src), gmask.index_select(1, src)
+                y, _, _ = model.snt_encoder.layers[0](x[-1:], kv=x, external_memories=g_sel, external_padding_mask=m_sel)
+                st = torch.cat([ts[:-1], y], 0)
+                return model.decoder(probe.index_select(1, src), g_sel, st, m_sel, None, None, copy_seq.index_select(1, src),
+                                     work=True)
+
+        for _ in range(2):
+            module_step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            module_step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_mod = e0.elapsed_time(e1) / 5
+        model.decoder.token_generator.static_tot_ext = keep
+        return {"workload": f"cfg5: beam {K} x batch {B} = {Hyp} live hypotheses, {S}-node graph memory, {steps} positions, "
+                            f"V={V}; whole search step (embed + snt layer + DecodeLayer + log-prob table + top-k/merge)",
+                "ms_per_step": best, "hyp_steps_per_sec": Hyp / (best * 1e-3), "graph_memory_projection_ms": ms_mem,
+                "gtos_launches_per_step": launches, "cuda_graph_per_position": True,
+                "module_path_ms_per_step_at_t%d" % t_mid: ms_mod,
+                "module_path_hyp_steps_per_sec": Hyp / (ms_mod * 1e-3),
+                "note": "module path = drop-in modules called as generator.py:120-167 does (K/V of the graph memory and of "
+                        "the prefix re-projected every step); engine = gtos_b200.decode (SURVEY 8 f-1)"}
+    finally:
+        model.train(was_training)
+
+
+def optimizer_bench(model, dev, lib, pk):
+    """global-norm clip + Adam over flat buffers of the model's size (3 launches) vs HBM roofline"""
+    from gtos_b200.optim import FlatAdam
+    n = sum(p.numel() for p in model.parameters())
+    w_ = torch.nn.Parameter(torch.randn(n - 4096, device=dev) * 0.02)
+    b_ = torch.nn.Parameter(torch.zeros(4096, device=dev))
+    opt = FlatAdam([("w.weight", w_), ("w.bias", b_)], lr=1e-3, max_norm=1.0)
+    opt.bucket.flat.normal_(0, 1e-3)
+    for _ in range(3):
+        opt.step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        opt.step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 20
+    byts = 32 * n                                             # sumsq: read g; adam: read p,g,m,v + write p,m,v
+    return {"params": n, "ms_per_step": ms, "launches": 3, "algorithmic_bytes": byts, "GBps": byts / (ms * 1e-3) / 1e9,
+            "hbm_frac": byts / (ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+            "note": "clip_grad_norm_ + AdamWeightDecayOptimizer.step of the reference (train.py:151-153) as gtos_grad_sumsq + "
+                    "gtos_adam_step; not part of the timed hot-path step"}
 
 
 if __name__ == "__main__":

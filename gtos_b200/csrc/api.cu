@@ -24,7 +24,7 @@ static inline cudaStream_t S_(void* s) { return reinterpret_cast<cudaStream_t>(s
 extern "C" {
 
 const char* gtos_last_error(void) { return g_err; }
-int gtos_abi_version(void) { return 1; }
+int gtos_abi_version(void) { return 2; }
 uint64_t gtos_launch_count(void) { return __atomic_load_n(&g_kernel_launches, __ATOMIC_RELAXED); }
 
 int gtos_device_check(void) {
@@ -303,6 +303,32 @@ int gtos_gru_gate_bwd(const float* dh, const float* dout_t, int64_t lddout, cons
                       int64_t lddgh, float* db_ih, float* db_hh, int64_t R, int32_t Hh, void* stream) {
   return gru_gate_bwd(dh, dout_t, lddout, gates, h_prev, reinterpret_cast<const long long*>(lengths), t, dh_prev, dgi_bf16,
                       lddgi, dgh_bf16, lddgh, db_ih, db_hh, R, Hh, S(stream));
+}
+
+int gtos_attn_decode(int32_t Hyp, int32_t L, int32_t H, int32_t hd, const float* q, int64_t ldq, const void* kv,
+                     int64_t ld_kv, int32_t v_off, int64_t row_stride, const int32_t* slot, int64_t slot_ld,
+                     const uint8_t* key_pad, int64_t pad_ld, float scale, float* out, int64_t ldo, void* out_bf16,
+                     int64_t ldob, float* probs, void* stream) {
+  return attn_decode(Hyp, L, H, hd, q, ldq, kv, ld_kv, v_off, row_stride, slot, slot_ld, key_pad, pad_ld, scale, out, ldo,
+                     out_bf16, ldob, probs, S(stream));
+}
+int gtos_beam_ancestry(const int32_t* old_anc, int32_t* new_anc, int64_t ld, const int32_t* parent, int32_t t, int32_t Hyp,
+                       void* stream) {
+  return beam_ancestry(old_anc, new_anc, ld, parent, t, Hyp, S(stream));
+}
+int gtos_token_logprob(const float* logits, int64_t ldl, int32_t V, const float* gate_logits, const float* align, int32_t S,
+                       const int64_t* copy_seq, int32_t Bsrc, const int32_t* src_index, int64_t rows, int32_t B,
+                       float* table, int64_t ldt, int32_t W, void* stream) {
+  return token_logprob(logits, ldl, V, gate_logits, align, S, reinterpret_cast<const long long*>(copy_seq), Bsrc, src_index,
+                       rows, B, table, ldt, W, S_(stream));
+}
+int64_t gtos_grad_sumsq_workspace(void) { return grad_sumsq_workspace(); }
+int gtos_grad_sumsq(const float* g, int64_t n, float* out, float* workspace, void* stream) {
+  return grad_sumsq(g, n, out, workspace, S(stream));
+}
+int gtos_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int64_t n_decay, const float* lr_ptr, float beta1,
+                   float beta2, float eps, float weight_decay, const float* norm_sq, float max_norm, void* stream) {
+  return adam_step(p, g, m, v, n, n_decay, lr_ptr, beta1, beta2, eps, weight_decay, norm_sq, max_norm, S(stream));
 }
 
 }  // extern "C"

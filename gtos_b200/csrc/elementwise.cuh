@@ -78,4 +78,18 @@ int embed_gather(const float* table, const long long* idx, long n, int dim, floa
 int embed_scatter_add(const float* dx, const long long* idx, long n, int dim, float* dtable, float p_drop,
                       const void* seed_ptr, unsigned long long seed_off, cudaStream_t st);
 
+
+// ---- incremental beam decode, log-prob table, flat Adam (decode.cu) -----------------
+int attn_decode(int Hyp, int L, int H, int hd, const float* q, long ldq, const void* kv, long ld_kv, int v_off,
+                long row_stride, const int* slot, long slot_ld, const unsigned char* key_pad, long pad_ld, float scale,
+                float* out, long ldo, void* out_bf16, long ldob, float* probs, cudaStream_t st);
+int token_logprob(const float* logits, long ldl, int V, const float* gate_logits, const float* align, int S,
+                  const long long* copy_seq, int Bsrc, const int* src_index, long rows, int B, float* table, long ldt, int W,
+                  cudaStream_t st);
+long grad_sumsq_workspace();
+int grad_sumsq(const float* g, long n, float* out, float* workspace, cudaStream_t st);
+int adam_step(float* p, const float* g, float* m, float* v, long n, long n_decay, const float* lr_ptr, float b1, float b2,
+              float eps, float wd, const float* norm_sq, float max_norm, cudaStream_t st);
+int beam_ancestry(const int* old_anc, int* new_anc, long ld, const int* parent, int t, int Hyp, cudaStream_t st);
+
 }  // namespace gtos

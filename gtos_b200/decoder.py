@@ -2,8 +2,8 @@
 
 DecodeLayer's three attention layers (masked self-attn over the token states + cross-attn over the
 graph, generator/decoder.py:76-94) and the TokenGenerator's 1-head alignment attention run through the
-sm_100a kernels.  The vocabulary tail of TokenGenerator (tanh-Linear, two softmaxes, copy scatter, NLL;
-decoder.py:39-64) is SURVEY.md §8 row f-2 ("next") and is kept as PyTorch ops here.
+sm_100a kernels.  The vocabulary tail of TokenGenerator (two softmaxes, copy scatter, log / NLL; decoder.py:42-64,
+SURVEY.md §8 row f-2) is one fused kernel for the training loss and one for the work=True log-prob table.
 """
 import torch
 import torch.nn.functional as F
@@ -43,8 +43,8 @@ class TokenGenerator(nn.Module):
                                                    key_padding_mask=graph_padding_mask, need_weights=True)
         outs, _ = ops.add_layer_norm(x, outs, self.alignment_layer_norm.weight, self.alignment_layer_norm.bias, p)
         seq_len, bsz, _ = outs.size()
-        # ---- vocabulary tail: both wide projections on the tcgen05 GEMM; the training NLL is one
-        #      fused kernel; only the work=True (beam search) log-prob table is still assembled with PyTorch ops ----
+        # ---- vocabulary tail: both wide projections on the tcgen05 GEMM; the training NLL and the
+        #      work=True (beam search) log-prob table are one fused kernel each ----
         outs_token = torch.tanh(ops.linear(outs, self.transfer.weight, self.transfer.bias))
         outs_token = F.dropout(outs_token, p=self.dropout, training=self.training)
         gate_logits = self.diverter(outs_token)
@@ -59,14 +59,14 @@ class TokenGenerator(nn.Module):
         return self._log_prob_table(logits, gate_logits, alignment_weight, copy_seq)
 
     def _log_prob_table(self, logits, gate_logits, align, copy_seq):
+        """decoder.py:44-59 as one fused kernel (inference only: the table carries no autograd graph, like the
+        reference's use of work=True under torch.no_grad(), generator.py:97-98)."""
         T, B, V = logits.shape
-        gate = torch.softmax(gate_logits, dim=-1)
+        S = copy_seq.size(0)
         width = self.static_tot_ext if self.static_tot_ext is not None else int(copy_seq.max()) + 1
-        table = logits.new_zeros(T, B, max(width, V))
-        table[..., :V] = torch.softmax(logits, dim=-1) * gate[..., :1]             # generate mass
-        slots = copy_seq.t().unsqueeze(0).expand(T, B, copy_seq.size(0))           # node s of graph b -> vocabulary slot
-        table.scatter_add_(-1, slots, align * gate[..., 1:])                       # copy mass
-        return (table + 1e-12).log()
+        table = ops.token_logprob(logits.detach().reshape(T * B, V), gate_logits.detach().reshape(T * B, 2),
+                                  align.detach().reshape(T * B, S), copy_seq, None, max(width, V), B=B)
+        return table.view(T, B, -1)
 
 
 class DecodeLayer(nn.Module):

@@ -949,3 +949,20 @@ class TokenNLLFn(torch.autograd.Function):
 
 def token_nll(logits, gate_logits, align, copy_seq, target, pad_idx):
     return TokenNLLFn.apply(logits, gate_logits, align, copy_seq, target, pad_idx)
+
+
+# --------------------------------------------------------------------------------------------
+# TokenGenerator work=True tail (decoder.py:42-59): log-prob table over the batch-extended vocabulary, one kernel
+# --------------------------------------------------------------------------------------------
+def token_logprob(logits, gate_logits, align, copy_seq, src_index, width, B=None):
+    """log-prob table [rows, width] (decoder.py:42-59).  logits [rows,V], gate_logits [rows,2], align [rows,S] fp32;
+    copy_seq [S,Bsrc] int64; row -> graph through src_index (int32) or row % B."""
+    _need_cuda(logits, gate_logits, align, copy_seq)
+    rows, V = logits.shape
+    S, Bsrc = copy_seq.shape
+    logits, gate_logits, align = logits.contiguous(), gate_logits.contiguous(), align.contiguous()
+    table = torch.empty(rows, width, dtype=torch.float32, device=logits.device)
+    _lib.check(_lib.load().gtos_token_logprob(_p(logits), V, V, _p(gate_logits), _p(align), S, _p(copy_seq.contiguous()), Bsrc,
+                                              _p(src_index), rows, B if B is not None else Bsrc, _p(table), width, width,
+                                              _st()), "token_logprob")
+    return table

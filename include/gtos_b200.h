@@ -189,6 +189,40 @@ int gtos_gru_gate_bwd(const float* dh, const float* dout_t, int64_t lddout, cons
                       const int64_t* lengths, int32_t t, float* dh_prev, void* dgi_bf16, int64_t lddgi, void* dgh_bf16,
                       int64_t lddgh, float* db_ih, float* db_hh, int64_t R, int32_t Hh, void* stream);
 
+/* ---- incremental beam decode (callers generator/generator.py:120-167, generator/search.py:57-168) ----
+ * Single-query attention over a bf16 K/V cache (MultiheadAttention.forward with T_q = 1, transformer.py:98-173).
+ * Cache row of (position l, slot s) = l * row_stride + s; a row holds K at column 0 and V at column v_off (elements),
+ * row pitch ld_kv.  Hypothesis h reads slot = slot[l * slot_ld + h] (NULL: slot = h):
+ *   graph cross-attention: slot = source graph of h, slot_ld = 0  (K/V of the graph memory projected once per graph);
+ *   token self-attention : slot = ancestry table anc[l][h] (gtos_beam_ancestry), slot_ld = its row pitch.
+ * key_pad[l * pad_ld + slot] = 1 masks a key.  q fp32 [Hyp, H*hd] unscaled; out fp32 and/or bf16; probs optional
+ * fp32 [Hyp, H, L] (the alignment weights of TokenGenerator, decoder.py:32-36). */
+int gtos_attn_decode(int32_t Hyp, int32_t L, int32_t H, int32_t hd, const float* q, int64_t ldq, const void* kv,
+                     int64_t ld_kv, int32_t v_off, int64_t row_stride, const int32_t* slot, int64_t slot_ld,
+                     const uint8_t* key_pad, int64_t pad_ld, float scale, float* out, int64_t ldo, void* out_bf16,
+                     int64_t ldob, float* probs, void* stream);
+/* new_anc[l][h] = old_anc[l][parent[h]] for l < t, new_anc[t][h] = h  (tables int32 [Tmax, ld]; parent NULL = identity).
+ * Replaces the per-step index_select of every cached state tensor (search.py:72-76). */
+int gtos_beam_ancestry(const int32_t* old_anc, int32_t* new_anc, int64_t ld, const int32_t* parent, int32_t t, int32_t Hyp,
+                       void* stream);
+/* work=True tail of TokenGenerator (decoder.py:42-59): table[row, 0..W) = log(gen * softmax(logits) (+0 beyond V)
+ * + copy * scatter(align by copy_seq[:, b(row)]) + 1e-12);  b(row) = src_index[row], or row % B when src_index is NULL.
+ * copy_seq int64 [S, Bsrc]. */
+int gtos_token_logprob(const float* logits, int64_t ldl, int32_t V, const float* gate_logits, const float* align, int32_t S,
+                       const int64_t* copy_seq, int32_t Bsrc, const int32_t* src_index, int64_t rows, int32_t B,
+                       float* table, int64_t ldt, int32_t W, void* stream);
+
+/* ---- optimizer step on flat buffers (generator/adam.py:28-87, generator/train.py:123-132,151-153) ----
+ * gtos_grad_sumsq: out[0] = sum g^2 (deterministic two-stage reduction; workspace = gtos_grad_sumsq_workspace() floats).
+ * gtos_adam_step: g' = g * min(1, max_norm / (sqrt(*norm_sq) + 1e-6)) (norm_sq NULL: no clip);
+ *   m = b1 m + (1-b1) g';  v = b2 v + (1-b2) g'^2;  p -= lr * (m / (sqrt(v) + eps) + wd_i p), wd_i = wd for the first
+ *   n_decay elements and 0 for the rest (no bias correction, as the reference).  lr is read from DEVICE memory so a
+ *   captured CUDA graph can follow the schedule (train.py:81-83). */
+int64_t gtos_grad_sumsq_workspace(void);
+int gtos_grad_sumsq(const float* g, int64_t n, float* out, float* workspace, void* stream);
+int gtos_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int64_t n_decay, const float* lr_ptr, float beta1,
+                   float beta2, float eps, float weight_decay, const float* norm_sq, float max_norm, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -89,3 +89,48 @@ def test_decode_layer(golden):
     ll = O.decode_layer(P, "", probe, graph, snt, g["smask"], g["tmask"], g["cm"], g["copy_seq"], c["L"], c["H"],
                         0, work=True)
     assert rel_err(ll, g["ll"]) < TOL
+
+
+# ---- optimizer step (f-4) and one-token decode step (f-1) ----------------------------------
+import os                                           # noqa: E402
+import types                                        # noqa: E402
+
+import pytest                                       # noqa: E402
+
+GDIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_optim_oracle_matches_reference_adam_and_clip():
+    """oracle/optim_oracle.py vs the reference's AdamWeightDecayOptimizer + clip_grad_norm_ + update_lr, 4 steps"""
+    from oracle import optim_oracle as OO
+    g = torch.load(os.path.join(GDIR, "golden_optim_v1.pt"), map_location="cpu", weights_only=False)
+    params = {n: v.clone() for n, v in g["init"].items()}
+    m = {n: torch.zeros_like(v) for n, v in params.items()}
+    v2 = {n: torch.zeros_like(v) for n, v in params.items()}
+    wd = {n: 0.0 if OO.no_decay(n) else 1e-4 for n in params}
+    for k, st in enumerate(g["steps"], start=1):
+        lr = OO.update_lr(g["embed_size"], k, g["warmup"])
+        assert lr == pytest.approx(st["lr"], rel=1e-12)
+        total, _ = OO.clip_coef(list(st["grads"].values()), 1.0)
+        assert float(total) == pytest.approx(st["total_norm"], rel=1e-6)
+        OO.adam_step(params, st["grads"], m, v2, lr, wd, eps=1e-6, max_norm=1.0)
+        for n in params:
+            assert rel_err(params[n], st["params"][n]) < 1e-6, (k, n)
+            assert rel_err(m[n], st["exp_avg"][n]) < 1e-6 and rel_err(v2[n], st["exp_avg_sq"][n]) < 1e-6, (k, n)
+
+
+@pytest.mark.parametrize("case", ["one_snt_layer", "two_snt_layers"])
+def test_decode_step_oracle_matches_reference_generator(case):
+    """oracle/decode_oracle.py vs Generator.decode_step driven with search.py's re-parenting, every step's full table"""
+    from oracle import decode_oracle as DO
+    g = torch.load(os.path.join(GDIR, "golden_decode_v1.pt"), map_location="cpu", weights_only=False)[case]
+    c = g["cfg"]
+    cfg = types.SimpleNamespace(snt_layers=c["snt_layers"], inference_layers=c["inference_layers"], num_heads=c["H"])
+    mem = dict(g["mem"], copy_seq=g["mem"]["cp_seq"])
+    state = {}
+    with torch.no_grad():
+        for st in g["steps"]:
+            ll, state = DO.decode_step(g["state"], cfg, mem, st["token_repr"], state, st["src"], st["parent"])
+            assert ll.shape == st["ll"].shape
+            assert (ll - st["ll"]).abs().max() < 2e-4          # log-probs down to log(1e-12) = -27.6
+            assert rel_err(ll.exp(), st["ll"].exp()) < TOL

@@ -305,6 +305,9 @@ int gtos_gru_gate_bwd(const float* dh, const float* dout_t, int64_t lddout, cons
                       lddgi, dgh_bf16, lddgh, db_ih, db_hh, R, Hh, S(stream));
 }
 
+int gtos_debug_read_trace(uint64_t* host_out, int32_t n) {
+  return debug_read_trace(reinterpret_cast<unsigned long long*>(host_out), n);
+}
 int gtos_attn_decode(int32_t Hyp, int32_t L, int32_t H, int32_t hd, const float* q, int64_t ldq, const void* kv,
                      int64_t ld_kv, int32_t v_off, int64_t row_stride, const int32_t* slot, int64_t slot_ld,
                      const uint8_t* key_pad, int64_t pad_ld, float scale, float* out, int64_t ldo, void* out_bf16,

@@ -47,6 +47,10 @@ __device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// GTOS_DBG bit 1: per-CTA clock64 timestamps of the pipeline phases (gtos_debug_read_trace); timing experiment only
+__device__ unsigned long long g_trace[148 * 16];
+#define GTOS_TRACE(slot) do { if ((p.dbg & 2) && blockIdx.x < 148) g_trace[blockIdx.x * 16 + (slot)] = clock64(); } while (0)
+
 struct TnDev {
   int M, N, K;
   int m_tiles, n_tiles, k_blocks, units;
@@ -146,6 +150,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) GTOS_TRACE(0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -176,7 +181,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
   pdl_launch_dependents();  // our successor may begin its own prologue as SMs free up
+  if (threadIdx.x == 0) GTOS_TRACE(1);
   pdl_wait();               // everything below touches global memory written by predecessors
+  if (threadIdx.x == 0) GTOS_TRACE(2);
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -232,6 +239,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
+      GTOS_TRACE(3);
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
@@ -247,6 +255,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           wait_bar(&bars->full[s], ph);
           tc_fence_after();
+          if (kb == 0 && unit == sched_id) GTOS_TRACE(4);
           const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
           const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
           const uint64_t db = make_smem_desc_sw128(sa + A_STAGE_BYTES, 16, 1024);
@@ -264,6 +273,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (CG == 2) umma_commit_2cta(&bars->tfull[as]); else umma_commit(&bars->tfull[as]);
         if (++as == 2) { as = 0; aph ^= 1; }
       }
+      GTOS_TRACE(5);
     }
   } else {
     // ================= epilogue (warps 2..5, relation modes: also 6..9) =================
@@ -331,6 +341,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       wait_bar(&bars->tfull[as], aph);
       if (REL) wait_bar(&bars->qfull[qs], qph);
       tc_fence_after();
+      if (warp == 2 && lane == 0 && unit == sched_id) GTOS_TRACE(6);
       const uint32_t tacc = tmem_base + as * BN + ((uint32_t)(quarter * 32) << 16);
 
       if constexpr (MODE == MODE_GRU) {
@@ -431,13 +442,31 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int c = 0; c < BN; c += 32) {
             if (n0 + c >= p.N) break;
             float v[32];
+            const bool trc = (warp == 2 && lane == 0 && unit == sched_id && c == 32);
+            if (trc) GTOS_TRACE(10);
             tmem_ld16(tacc + c, v);
             tmem_ld16(tacc + c + 16, v + 16);
+            // bias of this chunk: 8 independent 16-byte loads issued BEFORE the TMEM wait (the scalar predicated form
+            // compiled to 32 loads into ONE register, each waiting out its own L1 latency: 1800 cycles per chunk)
+            float bv[32];
+            if (p.bias) {
+              const float* bp = p.bias + n0 + c;
+              if (n0 + c + 32 <= p.N && ((reinterpret_cast<uintptr_t>(bp) & 15) == 0)) {
+#pragma unroll
+                for (int t4 = 0; t4 < 8; ++t4) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp) + t4);
+                  bv[4 * t4] = b4.x; bv[4 * t4 + 1] = b4.y; bv[4 * t4 + 2] = b4.z; bv[4 * t4 + 3] = b4.w;
+                }
+              } else {
+#pragma unroll
+                for (int t = 0; t < 32; ++t) bv[t] = (n0 + c + t < p.N) ? __ldg(bp + t) : 0.f;
+              }
+            }
             tmem_ld_wait();
+            if (trc) GTOS_TRACE(11);
             if (p.bias) {
 #pragma unroll
-              for (int t = 0; t < 32; ++t)
-                if (n0 + c + t < p.N) v[t] += __ldg(p.bias + n0 + c + t);
+              for (int t = 0; t < 32; ++t) v[t] += bv[t];
             }
             if (p.addend) {
               const long arow = (long)m_blk * BM + r;
@@ -460,10 +489,40 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int t = 0; t < 32; ++t) v[t] = fmaxf(v[t], 0.f);
             }
+            if constexpr (MODE == MODE_PLAIN) {
+              if (p.tma_out == 2) {
+                // bf16 output: two 32-column chunks fill one [128 rows x 64 bf16] swizzled tile, one TMA store per tile
+                const int half = (c >> 5) & 1;
+                uint8_t* buf = out_stage + (kc & 1) * (BM * 128);
+                if (half == 0) {
+                  if (issuer) tma_store_wait_read<1>();
+                  named_bar_sync(1, 128);
+                }
+                uint8_t* rowp = buf + r * 128;
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                  *reinterpret_cast<uint4*>(rowp + (((half * 4 + t) ^ (r & 7)) << 4)) =
+                      make_uint4(pack_bf16x2(v[8 * t], v[8 * t + 1]), pack_bf16x2(v[8 * t + 2], v[8 * t + 3]),
+                                 pack_bf16x2(v[8 * t + 4], v[8 * t + 5]), pack_bf16x2(v[8 * t + 6], v[8 * t + 7]));
+                if (half == 1 || c + 32 >= BN || n0 + c + 32 >= p.N) {      // tile complete (or last chunk of the unit)
+                  fence_proxy_async();
+                  named_bar_sync(2, 128);
+                  if (issuer) {
+                    tma_store_2d(&tmO, buf, n0 + (c & ~63), m_blk * BM);
+                    tma_store_commit();
+                  }
+                  ++kc;
+                }
+                continue;
+              }
+            }
             uint8_t* buf = out_stage + (kc & 1) * (BM * 128);
             ++kc;
+            if (trc) GTOS_TRACE(12);
             if (issuer) tma_store_wait_read<1>();   // the store that last read this buffer has drained
+            if (trc) GTOS_TRACE(13);
             named_bar_sync(1, 128);
+            if (trc) GTOS_TRACE(14);
             uint8_t* rowp = buf + r * 128;
 #pragma unroll
             for (int t = 0; t < 8; ++t)
@@ -481,6 +540,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tma_store_2d(&tmO, buf, n0 + c, m_blk * BM);
               tma_store_commit();
             }
+            if (trc) GTOS_TRACE(15);
           }
         } else {
         long out_row = (long)m_blk * BM + r;
@@ -499,13 +559,26 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (n0 + c >= p.N) break;
           float v[16];
           tmem_ld16(tacc + c, v);
-          tmem_ld_wait();
           const int n = n0 + c;
+          float bv[16];
+          if (p.bias) {                         // independent loads, in flight during the TMEM wait (see the TMA path)
+            const float* bp = p.bias + n;
+            if (n + 16 <= p.N && ((reinterpret_cast<uintptr_t>(bp) & 15) == 0)) {
+#pragma unroll
+              for (int t4 = 0; t4 < 4; ++t4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp) + t4);
+                bv[4 * t4] = b4.x; bv[4 * t4 + 1] = b4.y; bv[4 * t4 + 2] = b4.z; bv[4 * t4 + 3] = b4.w;
+              }
+            } else {
+#pragma unroll
+              for (int t = 0; t < 16; ++t) bv[t] = (n + t < p.N) ? __ldg(bp + t) : 0.f;
+            }
+          }
+          tmem_ld_wait();
           if (row_ok) {
             if (p.bias) {
 #pragma unroll
-              for (int t = 0; t < 16; ++t)
-                if (n + t < p.N) v[t] += __ldg(p.bias + n + t);
+              for (int t = 0; t < 16; ++t) v[t] += bv[t];
             }
             if (p.relu) {
 #pragma unroll
@@ -655,7 +728,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (++as == 2) { as = 0; aph ^= 1; }
       if (REL) { if (++qs == 2) { qs = 0; qph ^= 1; } }
     }
+    if (warp == 2 && lane == 0) GTOS_TRACE(7);
     if (p.tma_out && quarter == 2 && lane == 0) tma_store_wait_all();  // smem must outlive the bulk stores
+    if (warp == 2 && lane == 0) GTOS_TRACE(8);
   }
 
   tc_fence_before();
@@ -666,6 +741,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     if (CG == 2) tmem_dealloc_2cta(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
   }
+  if (threadIdx.x == 0) GTOS_TRACE(9);
+}
+
+int debug_read_trace(unsigned long long* host_out, int n) {
+  if (n > 148 * 16) n = 148 * 16;
+  GTOS_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_trace, sizeof(unsigned long long) * n));
+  return GTOS_OK;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -814,6 +896,14 @@ static int launch_tn(const GemmTnArgs& a, cudaStream_t stream) {
     e = make_tmap_nd(&tmO, a.out_f32, 4, 2, dims, str, box, true);
     if (e) return e;
     p.tma_out = 1;
+  } else if (MODE == MODE_PLAIN && a.out_bf16 && !a.out_f32 && !a.accumulate && !a.addend && a.ldob % 8 == 0 &&
+             (reinterpret_cast<uintptr_t>(a.out_bf16) & 15) == 0) {
+    uint64_t dims[2] = {(uint64_t)a.N, (uint64_t)a.M};
+    uint64_t str[2] = {0, (uint64_t)a.ldob * 2};
+    uint32_t box[2] = {64, (uint32_t)BM};
+    e = make_tmap_nd(&tmO, a.out_bf16, 2, 2, dims, str, box, true);
+    if (e) return e;
+    p.tma_out = 2;
   } else if (MODE == MODE_DREL && a.ldo == a.rt.D) {
     const RelTiling& rt = a.rt;
     uint64_t dims[4] = {(uint64_t)rt.D, (uint64_t)rt.B, (uint64_t)rt.N, (uint64_t)rt.N};

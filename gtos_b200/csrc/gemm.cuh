@@ -52,6 +52,7 @@ struct GemmTnArgs {
   void* G;             // GRAD out: bf16 [tiles*128, 2D] (permuted feature order)
 };
 int launch_gemm_tn(int mode, const GemmTnArgs& a, cudaStream_t stream);
+int debug_read_trace(unsigned long long* host_out, int n);   // GTOS_DBG=2 timestamps, 16 slots per CTA
 
 // One packed-sequence GRU step (generator/encoder.py:105-106, nn.GRU cell) as a GEMM with a fused gate epilogue.
 // Wcat rows are interleaved per block of UB = BN/4 hidden units: [r | z | n_input | n_hidden], K = [x (Kx) | h (H)].

@@ -36,6 +36,9 @@ int gtos_abi_version(void);
 uint64_t gtos_launch_count(void);
 /* 0 if the current device is sm_100 and the TMA driver entry point resolves */
 int gtos_device_check(void);
+/* timing experiments only: with GTOS_DBG=2 in the environment the plain GEMM records 16 clock64 timestamps per CTA
+ * (phases of its pipeline); copies the first n of them (148 x 16) to HOST memory */
+int gtos_debug_read_trace(uint64_t* host_out, int32_t n);
 
 /* ---- operand staging -------------------------------------------------------------------------- */
 /* fp32 [rows, cols] (lds) -> bf16 [rows, ldd]; columns cols..ldd-1 are zero-filled (TMA needs 16 B rows) */

@@ -42,6 +42,19 @@ def test_gemm_tn(dev, M, N, K):
     assert rel_err(outb[:, :N].float(), ref) < 1e-2
     out2, _ = ops.gemm_tn(A, B, N, bias=None, relu=True, out=out.clone(), accumulate=True)
     assert rel_err(out2, ref + torch.relu(ref - bias)) < 1e-4
+    # single-output calls take the TMA-store epilogues (fp32 tiles / bf16 tiles); a bias that is only 4-byte aligned
+    # takes the scalar bias path
+    o32, _ = ops.gemm_tn(A, B, N, bias=bias)
+    assert rel_err(o32, ref) < 2e-5 * max(1, K ** 0.5)
+    _, o16 = ops.gemm_tn(A, B, N, bias=bias, f32=False, bf16=True, relu=True)
+    assert rel_err(o16[:, :N].float(), torch.relu(ref)) < 1e-2
+    if o16.shape[1] > N:
+        assert float(o16[:, N:].float().abs().max()) == 0.0          # padding columns stay zero
+    bias_u = torch.randn(N + 1, device=dev)[1:]
+    ref_u = A.float() @ B.float().t() + bias_u
+    o32u, _ = ops.gemm_tn(A, B, N, bias=bias_u)
+    _, o16u = ops.gemm_tn(A, B, N, bias=bias_u, f32=False, bf16=True)
+    assert rel_err(o32u, ref_u) < 2e-5 * max(1, K ** 0.5) and rel_err(o16u[:, :N].float(), ref_u) < 1e-2
 
 
 @pytest.mark.parametrize("Kd,M,N", [(64, 128, 256), (128, 128, 64), (2624, 1536, 512), (1000, 512, 1024),

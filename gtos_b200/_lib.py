@@ -76,6 +76,8 @@ SIGNATURES = {
                                vp]),
     "gtos_beam_ancestry": (i32, [vp, vp, i64, vp, i32, i32, vp]),
     "gtos_token_logprob": (i32, [vp, i64, i32, vp, vp, i32, vp, i32, vp, i64, i32, vp, i64, i32, vp]),
+    "gtos_token_topk": (i32, [vp, i64, i32, vp, vp, i32, vp, i32, vp, i64, i32, i32, i32, vp, vp, vp, i64, vp]),
+    "gtos_beam_update": (i32, [i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "gtos_grad_sumsq_workspace": (i64, []),
     "gtos_grad_sumsq": (i32, [vp, i64, vp, vp, vp]),
     "gtos_adam_step": (i32, [vp, vp, vp, vp, i64, i64, vp, f32, f32, f32, f32, vp, f32, vp]),

@@ -325,6 +325,19 @@ int gtos_token_logprob(const float* logits, int64_t ldl, int32_t V, const float*
   return token_logprob(logits, ldl, V, gate_logits, align, S, reinterpret_cast<const long long*>(copy_seq), Bsrc, src_index,
                        rows, B, table, ldt, W, S_(stream));
 }
+int gtos_token_topk(const float* logits, int64_t ldl, int32_t V, const float* gate_logits, const float* align, int32_t S,
+                    const int64_t* copy_seq, int32_t Bsrc, const int32_t* src_index, int64_t rows, int32_t B, int32_t W,
+                    int32_t K, float* top_val, int32_t* top_idx, float* table, int64_t ldt, void* stream) {
+  return token_topk(logits, ldl, V, gate_logits, align, S, reinterpret_cast<const long long*>(copy_seq), Bsrc, src_index, rows,
+                    B, W, K, top_val, top_idx, table, ldt, S_(stream));
+}
+int gtos_beam_update(int32_t B, int32_t K, int32_t t, int32_t Tmin, int32_t Tmax, int32_t end_id, int32_t unk_id,
+                     const float* top_val, const int32_t* top_idx, float* score, uint8_t* live, int32_t* n_done,
+                     int32_t* steps, int32_t* tok, int32_t* par, float* done_score, int32_t* done_step, int32_t* done_par,
+                     int32_t* parent_out, int64_t* last_tok, void* stream) {
+  return beam_update_c(B, K, t, Tmin, Tmax, end_id, unk_id, top_val, top_idx, score, live, n_done, steps, tok, par, done_score,
+                       done_step, done_par, parent_out, reinterpret_cast<long long*>(last_tok), S(stream));
+}
 int64_t gtos_grad_sumsq_workspace(void) { return grad_sumsq_workspace(); }
 int gtos_grad_sumsq(const float* g, int64_t n, float* out, float* workspace, void* stream) {
   return grad_sumsq(g, n, out, workspace, S(stream));

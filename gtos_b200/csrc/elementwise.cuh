@@ -86,6 +86,12 @@ int attn_decode(int Hyp, int L, int H, int hd, const float* q, long ldq, const v
 int token_logprob(const float* logits, long ldl, int V, const float* gate_logits, const float* align, int S,
                   const long long* copy_seq, int Bsrc, const int* src_index, long rows, int B, float* table, long ldt, int W,
                   cudaStream_t st);
+int token_topk(const float* logits, long ldl, int V, const float* gate_logits, const float* align, int S,
+               const long long* copy_seq, int Bsrc, const int* src_index, long rows, int B, int W, int K, float* top_val,
+               int* top_idx, float* table, long ldt, cudaStream_t st);
+int beam_update_c(int B, int K, int t, int Tmin, int Tmax, int end_id, int unk_id, const float* top_val, const int* top_idx,
+                  float* score, unsigned char* live, int* n_done, int* steps, int* tok, int* par, float* done_score,
+                  int* done_step, int* done_par, int* parent_out, long long* last_tok, cudaStream_t st);
 long grad_sumsq_workspace();
 int grad_sumsq(const float* g, long n, float* out, float* workspace, cudaStream_t st);
 int adam_step(float* p, const float* g, float* m, float* v, long n, long n_decay, const float* lr_ptr, float b1, float b2,

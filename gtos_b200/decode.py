@@ -180,10 +180,12 @@ class DecodeEngine:
 
     # ---- one decode step -------------------------------------------------------------------------------------
     @torch.no_grad()
-    def step(self, token_repr, src_index, parent, t):
+    def step(self, token_repr, src_index, parent, t, topk=None):
         """token_repr [Hyp, D] fp32 (embedded last token of every live hypothesis, generator.py:131-132);
         src_index int32 [Hyp]: source graph of each hypothesis; parent int32 [Hyp] or None: row of the hypothesis'
-        prefix in the PREVIOUS step (search.py:72-76); t: position (0-based).  Returns the log-prob table [Hyp, W]."""
+        prefix in the PREVIOUS step (search.py:72-76); t: position (0-based).  Returns the log-prob table [Hyp, W], or -
+        with topk=k - only (values [Hyp,k], token ids int32 [Hyp,k]) of the k best tokens (generator.py:157), in which
+        case the table never exists in HBM."""
         if self.mem is None:
             raise RuntimeError("DecodeEngine.step before set_memory")
         Hyp, D = token_repr.shape
@@ -201,9 +203,9 @@ class DecodeEngine:
         ob = ops.cast_bf16(outs)
         for li in range(self.n_snt, len(self.layers)):  # inference_core: query = probe stream, kv = token states
             outs, ob = self._layer(li, outs, ob, state_b, t, new, src_index)
-        return self._token_table(outs, ob.view(Hyp, -1), src_index)
+        return self._token_table(outs, ob.view(Hyp, -1), src_index, topk)
 
-    def _token_table(self, outs, ob, src_index):
+    def _token_table(self, outs, ob, src_index, topk=None):
         """TokenGenerator.forward(work=True), decoder.py:30-59."""
         m = self.mem
         Hyp = outs.shape[0]
@@ -216,13 +218,89 @@ class DecodeEngine:
         tokb = ops.cast_bf16(tok)
         logits = torch.empty(Hyp, self.V, dtype=torch.float32, device=self.dev)
         _gemm(tokb, self.Wgen, 0, self.V, self.bgen, Hyp, out32=logits)
+        if topk is not None:
+            return ops.token_topk(logits, gate_logits, align.view(Hyp, m["S"]), m["copy_seq"], src_index, m["W"], topk)
         return ops.token_logprob(logits, gate_logits, align.view(Hyp, m["S"]), m["copy_seq"], src_index, m["W"])
 
 
 # ------------------------------------------------------------------------------------------------------------
 # device-side beam step (generator/search.py:35-111 Beam, :114-168 search_by_batch) with fixed shapes
 # ------------------------------------------------------------------------------------------------------------
-class BeamState:
+class _BeamReadout:
+    """host-side read-out shared by the two beam-state implementations (once per batch)"""
+
+    @staticmethod
+    def _trace(tok, par, t_last, b, slot):
+        seq = []
+        for t in range(t_last, -1, -1):
+            seq.append(int(tok[t, b, slot]))
+            slot = int(par[t, b, slot])
+        return seq[::-1]
+
+    def k_best(self, k, alpha):
+        """`Beam.get_k_best` (search.py:98-102) for every beam -> list (B) of lists of (token ids without <STR>, score)."""
+        tok, par = self.tok.cpu(), self.par.cpu()
+        n_done, steps = self.n_done.cpu(), self.steps.cpu()
+        d_score, d_step, d_par = self.done_score.cpu(), self.done_step.cpu(), self.done_par.cpu()
+        score, live = self.score.cpu(), self.live.cpu()
+        out = []
+        for b in range(self.B):
+            hyps = []
+            if int(n_done[b]) > 0:
+                for r in range(min(int(n_done[b]), self.K)):
+                    t_e = int(d_step[b, r])
+                    prefix = self._trace(tok, par, t_e - 1, b, int(d_par[b, r])) if t_e > 0 else []
+                    hyps.append((prefix + [self.end_id], float(d_score[b, r])))
+            else:                                                              # search.py:99-100
+                t_last = int(steps[b]) - 1
+                for s in range(self.K):
+                    if bool(live[b, s]):
+                        hyps.append((self._trace(tok, par, t_last, b, s), float(score[b, s])))
+            # score / (1 + len(seq)) ** alpha, where the reference's seq also holds <STR>
+            hyps.sort(key=lambda x: x[1] / ((2 + len(x[0])) ** alpha), reverse=True)
+            out.append(hyps[:k])
+        return out
+
+    def active(self):
+        """beams that still submit hypotheses (search.py:93-96: not completed())"""
+        return (self.n_done < self.K) & (self.steps < self.Tmax)
+
+
+class BeamStateFused(_BeamReadout):
+    """BeamState whose update is ONE kernel (`gtos_beam_update`, one CTA per beam) fed by the fused top-k of
+    `gtos_token_topk`; int32 / uint8 state on the device.  Same semantics as BeamState.update (tests compare them)."""
+
+    def __init__(self, B, K, max_time_step, min_time_step, end_id, unk_id, device):
+        if K > 16:
+            raise ValueError("BeamStateFused: beam size <= 16")
+        self.B, self.K, self.Tmax, self.Tmin = B, K, int(max_time_step), int(min_time_step)
+        self.end_id, self.unk_id, self.dev = int(end_id), int(unk_id), device
+        f = dict(device=device)
+        i = dict(dtype=torch.int32, device=device)
+        self.score = torch.empty(B, K, **f)
+        self.live = torch.empty(B, K, dtype=torch.uint8, device=device)
+        self.n_done, self.steps = torch.empty(B, **i), torch.empty(B, **i)
+        self.tok, self.par = torch.empty(self.Tmax, B, K, **i), torch.empty(self.Tmax, B, K, **i)
+        self.done_score = torch.empty(B, K, **f)
+        self.done_step, self.done_par = torch.empty(B, K, **i), torch.empty(B, K, **i)
+        self.reset()
+
+    def reset(self):
+        for x in (self.score, self.live, self.n_done, self.steps, self.tok, self.par, self.done_step, self.done_par):
+            x.zero_()
+        self.live[:, 0] = 1
+        self.done_score.fill_(float("-inf"))
+
+    def update(self, t, top_val, top_idx, parent_out, last_tok):
+        """top_val f32 / top_idx i32 [B*K, K]; writes parent_out i32 [B*K] and last_tok i64 [B*K] for the next step"""
+        _lib.check(_lib.load().gtos_beam_update(self.B, self.K, t, self.Tmin, self.Tmax, self.end_id, self.unk_id,
+                                                _p(top_val), _p(top_idx), _p(self.score), _p(self.live), _p(self.n_done),
+                                                _p(self.steps), _p(self.tok), _p(self.par), _p(self.done_score),
+                                                _p(self.done_step), _p(self.done_par), _p(parent_out), _p(last_tok), _st()),
+                   "beam_update")
+
+
+class BeamState(_BeamReadout):
     """All beams of a batch as fixed-shape tensors (B source graphs x K slots), updated IN PLACE so a step can be
     captured in a CUDA graph.  Mirrors `Beam`: live hypotheses occupy slots 0..n_live-1 in candidate-rank order
     (search.py:66-92), completed ones are kept in a [B, K] table in completion order.  Sequences are stored as
@@ -256,10 +334,6 @@ class BeamState:
         self.done_score.fill_(float("-inf"))
         self.done_step.zero_()
         self.done_par.zero_()
-
-    def active(self):
-        """beams that still submit hypotheses (search.py:93-96: not completed())"""
-        return (self.n_done < self.K) & (self.steps < self.Tmax)
 
     def update(self, t, table):
         """One `Beam.update` for every beam (search.py:57-92) from the log-prob table [B*K, W] of step t (0-based).
@@ -313,39 +387,6 @@ class BeamState:
         self.steps.add_(active.to(torch.int64))
         return self.par[t], self.tok[t]
 
-    # ---- read-out (host side, once per batch) ------------------------------------------------------------------
-    @staticmethod
-    def _trace(tok, par, t_last, b, slot):
-        seq = []
-        for t in range(t_last, -1, -1):
-            seq.append(int(tok[t, b, slot]))
-            slot = int(par[t, b, slot])
-        return seq[::-1]
-
-    def k_best(self, k, alpha):
-        """`Beam.get_k_best` (search.py:98-102) for every beam -> list (B) of lists of (token ids without <STR>, score)."""
-        tok, par = self.tok.cpu(), self.par.cpu()
-        n_done, steps = self.n_done.cpu(), self.steps.cpu()
-        d_score, d_step, d_par = self.done_score.cpu(), self.done_step.cpu(), self.done_par.cpu()
-        score, live = self.score.cpu(), self.live.cpu()
-        out = []
-        for b in range(self.B):
-            hyps = []
-            if int(n_done[b]) > 0:
-                for r in range(min(int(n_done[b]), self.K)):
-                    t_e = int(d_step[b, r])
-                    prefix = self._trace(tok, par, t_e - 1, b, int(d_par[b, r])) if t_e > 0 else []
-                    hyps.append((prefix + [self.end_id], float(d_score[b, r])))
-            else:                                                              # search.py:99-100
-                t_last = int(steps[b]) - 1
-                for s in range(self.K):
-                    if bool(live[b, s]):
-                        hyps.append((self._trace(tok, par, t_last, b, s), float(score[b, s])))
-            # score / (1 + len(seq)) ** alpha, where the reference's seq also holds <STR>
-            hyps.sort(key=lambda x: x[1] / ((2 + len(x[0])) ** alpha), reverse=True)
-            out.append(hyps[:k])
-        return out
-
 
 class BeamSearchDevice:
     """`search_by_batch` (search.py:114-168) on the DecodeEngine: every step runs all B*K rows (dead rows are masked),
@@ -356,8 +397,9 @@ class BeamSearchDevice:
     when use_graphs=True."""
 
     def __init__(self, engine, beam_size, max_time_step, min_time_step, end_id, unk_id, start_id, embed_fn,
-                 use_graphs=False, check_every=8):
+                 use_graphs=False, check_every=8, fused=True):
         self.eng, self.K = engine, int(beam_size)
+        self.fused = bool(fused) and self.K <= 16     # fused: gtos_token_topk + gtos_beam_update (2 kernels per step)
         self.Tmax, self.Tmin = int(max_time_step), int(min_time_step)
         self.end_id, self.unk_id, self.start_id = end_id, unk_id, start_id
         self.embed_fn = embed_fn
@@ -370,7 +412,8 @@ class BeamSearchDevice:
         dev, K = self.eng.dev, self.K
         if B * K > self.eng.max_hyp or self.Tmax > self.eng.max_steps:
             raise ValueError("BeamSearchDevice: engine caches too small for this batch / beam / max_time_step")
-        self.state = BeamState(B, K, self.Tmax, self.Tmin, self.end_id, self.unk_id, dev)
+        cls = BeamStateFused if self.fused else BeamState
+        self.state = cls(B, K, self.Tmax, self.Tmin, self.end_id, self.unk_id, dev)
         self.src_index = torch.arange(B, device=dev, dtype=torch.int32).repeat_interleave(K)
         self.row_base = (torch.arange(B, device=dev, dtype=torch.int64) * K).unsqueeze(1)
         self.parent = torch.zeros(B * K, dtype=torch.int32, device=dev)
@@ -384,6 +427,10 @@ class BeamSearchDevice:
 
     def _step(self, t):
         x = self.embed_fn(self.last_tok.view(-1), t)
+        if self.fused:
+            top_val, top_idx = self.eng.step(x, self.src_index, self.parent if t > 0 else None, t, topk=self.K)
+            self.state.update(t, top_val, top_idx, self.parent, self.last_tok)
+            return
         table = self.eng.step(x, self.src_index, self.parent if t > 0 else None, t)
         par, tok = self.state.update(t, table)
         self.parent.copy_((par + self.row_base).view(-1))

@@ -966,3 +966,20 @@ def token_logprob(logits, gate_logits, align, copy_seq, src_index, width, B=None
                                               _p(src_index), rows, B if B is not None else Bsrc, _p(table), width, width,
                                               _st()), "token_logprob")
     return table
+
+
+def token_topk(logits, gate_logits, align, copy_seq, src_index, width, k, B=None, want_table=False):
+    """the k best entries of every row of the log-prob table (generator.py:157), computed without materialising it:
+    returns (values fp32 [rows,k], token ids int32 [rows,k]) (+ the table when want_table)."""
+    _need_cuda(logits, gate_logits, align, copy_seq)
+    rows, V = logits.shape
+    S, Bsrc = copy_seq.shape
+    logits, gate_logits, align = logits.contiguous(), gate_logits.contiguous(), align.contiguous()
+    dev = logits.device
+    top_val = torch.empty(rows, k, dtype=torch.float32, device=dev)
+    top_idx = torch.empty(rows, k, dtype=torch.int32, device=dev)
+    table = torch.empty(rows, width, dtype=torch.float32, device=dev) if want_table else None
+    _lib.check(_lib.load().gtos_token_topk(_p(logits), V, V, _p(gate_logits), _p(align), S, _p(copy_seq.contiguous()), Bsrc,
+                                           _p(src_index), rows, B if B is not None else Bsrc, width, k, _p(top_val),
+                                           _p(top_idx), _p(table), width, _st()), "token_topk")
+    return (top_val, top_idx, table) if want_table else (top_val, top_idx)

@@ -214,6 +214,20 @@ int gtos_beam_ancestry(const int32_t* old_anc, int32_t* new_anc, int64_t ld, con
 int gtos_token_logprob(const float* logits, int64_t ldl, int32_t V, const float* gate_logits, const float* align, int32_t S,
                        const int64_t* copy_seq, int32_t Bsrc, const int32_t* src_index, int64_t rows, int32_t B,
                        float* table, int64_t ldt, int32_t W, void* stream);
+/* Same row computed in shared memory with the k best tokens taken in the same kernel (generator.py:157 torch.topk):
+ * top_val / top_idx [rows, K] (log-probs best first, ties -> lowest id); table optional (NULL: never written to HBM). */
+int gtos_token_topk(const float* logits, int64_t ldl, int32_t V, const float* gate_logits, const float* align, int32_t S,
+                    const int64_t* copy_seq, int32_t Bsrc, const int32_t* src_index, int64_t rows, int32_t B, int32_t W,
+                    int32_t K, float* top_val, int32_t* top_idx, float* table, int64_t ldt, void* stream);
+/* One Beam.update (search.py:57-92) for all B beams of K slots from the top-k lists of step t: candidates = live slot x
+ * rank, stable descending merge, keep K - n_done, <END> completes when t >= Tmin (else dropped), UNK scores -inf.
+ * State (updated in place): score f32 [B,K], live u8 [B,K], n_done / steps i32 [B], back-pointers tok / par i32
+ * [Tmax,B,K], completed table done_score f32 / done_step / done_par i32 [B,K].  Outputs for the next step:
+ * parent_out i32 [B*K] (row of the prefix in this step's arrangement), last_tok i64 [B*K]. */
+int gtos_beam_update(int32_t B, int32_t K, int32_t t, int32_t Tmin, int32_t Tmax, int32_t end_id, int32_t unk_id,
+                     const float* top_val, const int32_t* top_idx, float* score, uint8_t* live, int32_t* n_done,
+                     int32_t* steps, int32_t* tok, int32_t* par, float* done_score, int32_t* done_step, int32_t* done_par,
+                     int32_t* parent_out, int64_t* last_tok, void* stream);
 
 /* ---- optimizer step on flat buffers (generator/adam.py:28-87, generator/train.py:123-132,151-153) ----
  * gtos_grad_sumsq: out[0] = sum g^2 (deterministic two-stage reduction; workspace = gtos_grad_sumsq_workspace() floats).

@@ -52,7 +52,8 @@ def _modules(c, dev, state=None, seed=SEED):
 # ---------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("Hyp,L,H,hd,Bc,mode", [(7, 5, 4, 8, 3, "cross"), (64, 40, 8, 64, 9, "cross"), (33, 17, 1, 512, 5, "cross"),
                                                 (50, 23, 8, 64, 50, "self"), (2048, 40, 8, 64, 256, "cross"),
-                                                (16, 300, 2, 16, 16, "self")])
+                                                (16, 300, 2, 16, 16, "self"), (40, 33, 8, 16, 7, "cross"), (20, 9, 4, 64, 20, "self"),
+                                                (24, 50, 2, 128, 6, "cross"), (9, 600, 8, 64, 9, "self")])
 def test_attn_decode_kernel(dev, Hyp, L, H, hd, Bc, mode):
     from gtos_b200 import decode
     gen = torch.Generator().manual_seed(SEED + Hyp + L)
@@ -104,6 +105,61 @@ def test_token_logprob_kernel(dev, rows, V, S, Bsrc, ext):
         ref = (p + 1e-12).log()
         assert (table - ref).abs().max() < 1e-4
         assert rel_err(table.exp(), p) < 1e-5
+
+
+@pytest.mark.parametrize("rows,V,S,Bsrc,ext,K", [(5, 19, 6, 3, 4, 3), (64, 1000, 40, 8, 16, 8), (33, 10000, 40, 9, 16, 8),
+                                                  (12, 50, 9, 12, 0, 1), (7, 40, 5, 2, 3, 16)])
+def test_token_topk_kernel(dev, rows, V, S, Bsrc, ext, K):
+    """fused log-prob row + top-k (generator.py:157) vs the table kernel + torch.topk"""
+    from gtos_b200 import ops
+    gen = torch.Generator().manual_seed(SEED + rows + K)
+    logits = (torch.randn(rows, V, generator=gen) * 3).to(dev)
+    gate = torch.randn(rows, 2, generator=gen).to(dev)
+    align = torch.softmax(torch.randn(rows, S, generator=gen) * 2, -1).to(dev)
+    copy_seq = torch.randint(2, V + max(ext, 1), (S, Bsrc), generator=gen).to(dev)
+    src = torch.randint(0, Bsrc, (rows,), generator=gen).to(torch.int32).to(dev)
+    W = max(V, int(copy_seq.max()) + 1)
+    ref = ops.token_logprob(logits, gate, align, copy_seq, src, W)
+    val, idx, table = ops.token_topk(logits, gate, align, copy_seq, src, W, K, want_table=True)
+    assert (table - ref).abs().max() < 1e-5
+    rv, ri = torch.topk(ref, K, dim=1)
+    assert (val - rv).abs().max() < 1e-5                                   # same k best values, best first
+    assert (ref.gather(1, idx.long()) - val).abs().max() < 1e-5            # and the ids point at them
+    assert all(len(set(r)) == K for r in idx.tolist())                     # no token twice
+    val2, idx2 = ops.token_topk(logits, gate, align, copy_seq, src, W, K)
+    assert torch.equal(val2, val) and torch.equal(idx2, idx)
+
+
+@pytest.mark.parametrize("B,K,W,Tmin,Tmax", [(7, 4, 30, 2, 10), (5, 8, 80, 1, 12), (9, 1, 12, 1, 9), (3, 16, 300, 3, 8)])
+def test_beam_update_kernel_matches_beam_state(dev, B, K, W, Tmin, Tmax):
+    """gtos_beam_update (one kernel) vs BeamState.update (the torch implementation pinned to the reference's Beam class by
+    tests/test_beam_cpu.py): identical state after every step, driven by the same top-k lists"""
+    from gtos_b200.decode import BeamState, BeamStateFused
+    END, UNK = 3, 1
+    gen = torch.Generator().manual_seed(SEED + B * K)
+    a = BeamState(B, K, Tmax, Tmin, END, UNK, dev)
+    f = BeamStateFused(B, K, Tmax, Tmin, END, UNK, dev)
+    parent = torch.zeros(B * K, dtype=torch.int32, device=dev)
+    last = torch.zeros(B * K, dtype=torch.int64, device=dev)
+    base = (torch.arange(B, device=dev) * K).unsqueeze(1)
+    for t in range(Tmax):
+        logits = torch.randn(B * K, W, generator=gen) * 2
+        logits[:, END] += 0.6 * t
+        logits[:, UNK] += 1.5
+        table = torch.log_softmax(logits, -1).to(dev)
+        tv, ti = torch.topk(table.view(B, K, -1), K, dim=-1)
+        # BeamState.update runs the same torch.topk internally
+        par, tok = a.update(t, table)
+        f.update(t, tv.reshape(B * K, K).contiguous(), ti.reshape(B * K, K).to(torch.int32).contiguous(), parent, last)
+        torch.cuda.synchronize()
+        assert torch.equal(f.score, a.score), t
+        assert torch.equal(f.live.bool(), a.live) and torch.equal(f.n_done.long(), a.n_done) and torch.equal(f.steps.long(), a.steps)
+        assert torch.equal(f.tok[t].long(), a.tok[t]) and torch.equal(f.par[t].long(), a.par[t]), t
+        assert torch.equal(f.done_score, a.done_score) and torch.equal(f.done_step.long(), a.done_step)
+        assert torch.equal(f.done_par.long(), a.done_par)
+        assert torch.equal(parent.long().view(B, K), par + base) and torch.equal(last.view(B, K), tok)
+    assert int(a.n_done.sum()) > 0 or Tmin >= Tmax
+    assert a.k_best(K, 0.6) == f.k_best(K, 0.6)
 
 
 def test_token_generator_work_mode_vs_oracle(dev):
@@ -243,6 +299,13 @@ def test_beam_search_device_scores_are_consistent_and_graphs_are_exact(dev):
     bs2.capture()
     best2 = bs2.run().k_best(K, 0.6)
     assert best2 == best
+    # the unfused bookkeeping (full table + torch.topk + BeamState) finds the same hypotheses
+    bs3 = BeamSearchDevice(eng, K, Tmax, 1, END, UNK, START, _embed_fn(emb, pos), fused=False)
+    best3 = bs3.run().k_best(K, 0.6)
+    assert [[h[0] for h in b] for b in best3] == [[h[0] for h in b] for b in best]
+    for b3, b1 in zip(best3, best):
+        for h3, h1 in zip(b3, b1):
+            assert h3[1] == pytest.approx(h1[1], abs=1e-4) or h3[1] == h1[1]
 
 
 def test_flat_adam_matches_reference_optimizer(dev):

@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of one CUDA graph")
     ap.add_argument("--cpu-sample-graphs", type=int, default=4, help="graphs per CPU-baseline step")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--no-breakdown", action="store_true", help="only the headline step timing (quick A/B runs)")
     ap.add_argument("--dense-relation", action="store_true",
                     help="build relation = bank[idx] as a dense fp32 tensor exactly as generator.py:79 does "
                          "(default: keep it factorised, SURVEY §8 f-0)")
@@ -322,7 +323,7 @@ def main_ours(args):
 
     # --- breakdown on rank 0: encoder-only and decoder-only steps, and the dominant kernel alone ---
     extra = {}
-    if rank == 0:
+    if rank == 0 and not args.no_breakdown:
         extra = breakdown(args, w, cfg, model, static, meta, dev, lib)
     total_pairs = meta["pairs"] * world
     total_tokens = meta["tokens"] * world

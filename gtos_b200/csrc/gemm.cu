@@ -887,6 +887,7 @@ static int launch_tn(const GemmTnArgs& a, cudaStream_t stream) {
   p.tma_out = 0;
   static const bool grad_tma = !(getenv("GTOS_GRAD_TMA") && getenv("GTOS_GRAD_TMA")[0] == '0');
   static const bool tma_enabled = !(getenv("GTOS_TMA_OUT") && getenv("GTOS_TMA_OUT")[0] == '0');
+  static const bool bf16_tma = !(getenv("GTOS_TMA_BF16") && getenv("GTOS_TMA_BF16")[0] == '0');
   if (!tma_enabled) {
   } else if (MODE == MODE_PLAIN && a.out_f32 && !a.out_bf16 && !a.accumulate && a.ldo % 4 == 0 &&
       (reinterpret_cast<uintptr_t>(a.out_f32) & 15) == 0) {
@@ -896,7 +897,7 @@ static int launch_tn(const GemmTnArgs& a, cudaStream_t stream) {
     e = make_tmap_nd(&tmO, a.out_f32, 4, 2, dims, str, box, true);
     if (e) return e;
     p.tma_out = 1;
-  } else if (MODE == MODE_PLAIN && a.out_bf16 && !a.out_f32 && !a.accumulate && !a.addend && a.ldob % 8 == 0 &&
+  } else if (MODE == MODE_PLAIN && bf16_tma && a.out_bf16 && !a.out_f32 && !a.accumulate && !a.addend && a.ldob % 8 == 0 &&
              (reinterpret_cast<uintptr_t>(a.out_bf16) & 15) == 0) {
     uint64_t dims[2] = {(uint64_t)a.N, (uint64_t)a.M};
     uint64_t str[2] = {0, (uint64_t)a.ldob * 2};

@@ -77,3 +77,95 @@ def shard_range(total, rank, world):
         raise ValueError(f"global batch {total} must divide evenly over {world} ranks (per-sequence loss mean, decoder.py:92-94)")
     per = total // world
     return rank * per, (rank + 1) * per
+
+
+class OverlappedGradBuckets:
+    """The flat gradient exchange split into a few buckets that are all-reduced WHILE the backward pass is still running
+    ("optionally 2-3 buckets launched from backward hooks to hide it").
+
+    groups: list of parameter lists in the order their gradients become final during backward (e.g. decoder + sentence
+    encoder, graph encoder, relation encoder).  Each group owns a contiguous slice of one flat buffer.  A
+    post-accumulate-grad hook counts the group's parameters down; when the last gradient of a group lands, the group is
+    packed into its slice (one multi-tensor copy) and its all-reduce(mean) is issued asynchronously - the collective runs
+    on the process group's own stream while the caller's stream continues with the rest of the backward.  `finish()`
+    joins the outstanding collectives (and flushes groups some of whose parameters received no gradient).
+    Everything is stream-ordered, so the whole step - hooks included - can be captured in one CUDA graph."""
+
+    def __init__(self, groups, group=None):
+        self.groups = [[p for p in g if p.requires_grad] for g in groups]
+        self.groups = [g for g in self.groups if g]
+        if not self.groups:
+            raise ValueError("OverlappedGradBuckets: no trainable parameters")
+        dev, dt = self.groups[0][0].device, self.groups[0][0].dtype
+        self.numel = sum(p.numel() for g in self.groups for p in g)
+        self.flat = torch.zeros(self.numel, dtype=dt, device=dev)
+        self.slices, off = [], 0
+        for g in self.groups:
+            n = sum(p.numel() for p in g)
+            self.slices.append(self.flat[off:off + n])
+            off += n
+        self.pg = group
+        self._left = [0] * len(self.groups)
+        self._done = [False] * len(self.groups)
+        self._works = []
+        self._hooks = []
+        self.enabled = True
+        for gi, g in enumerate(self.groups):
+            for p in g:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(gi)))
+        self.zero()
+
+    def _make_hook(self, gi):
+        def hook(_p):
+            if not self.enabled:
+                return
+            self._left[gi] -= 1
+            if self._left[gi] == 0:
+                self._launch(gi)
+        return hook
+
+    def zero(self):
+        """call before every backward: forget the gradients and re-arm the countdowns"""
+        for gi, g in enumerate(self.groups):
+            for p in g:
+                p.grad = None
+            self._left[gi] = len(g)
+            self._done[gi] = False
+        self._works = []
+
+    def _launch(self, gi):
+        g = self.groups[gi]
+        parts = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in g]
+        torch.cat(parts, out=self.slices[gi])
+        self._done[gi] = True
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.pg) == 1:
+            return
+        if dist.get_backend(self.pg) == "nccl":
+            self._works.append((gi, dist.all_reduce(self.slices[gi], op=dist.ReduceOp.AVG, group=self.pg, async_op=True), False))
+        else:
+            self._works.append((gi, dist.all_reduce(self.slices[gi], op=dist.ReduceOp.SUM, group=self.pg, async_op=True), True))
+
+    def finish(self):
+        """after backward: flush groups that never completed, then make the current stream wait for every collective"""
+        for gi in range(len(self.groups)):
+            if not self._done[gi]:
+                self._launch(gi)
+        for gi, w, divide in self._works:
+            w.wait()
+            if divide:
+                self.slices[gi].div_(dist.get_world_size(self.pg))
+        self._works = []
+
+    def unpack(self):
+        """point every .grad at its (averaged) slice of the flat buffer"""
+        for g, sl in zip(self.groups, self.slices):
+            off = 0
+            for p in g:
+                n = p.numel()
+                p.grad = sl[off:off + n].view_as(p)
+                off += n
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []

@@ -36,6 +36,7 @@ SIGNATURES = {
     "gtos_launch_count": (u64, []),
     "gtos_device_check": (i32, []),
     "gtos_debug_read_trace": (i32, [vp, i32]),
+    "gtos_debug_attn_trace": (i32, [vp, i32]),
     "gtos_cast_bf16": (i32, [vp, i64, vp, i64, i64, i32, vp]),
     "gtos_cast_colsum": (i32, [vp, i64, vp, i64, vp, i64, i32, vp]),
     "gtos_weight_prep": (i32, [vp, i32, i32, vp, i64, vp, i64, i32, vp]),

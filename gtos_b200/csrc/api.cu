@@ -305,6 +305,9 @@ int gtos_gru_gate_bwd(const float* dh, const float* dout_t, int64_t lddout, cons
                       lddgi, dgh_bf16, lddgh, db_ih, db_hh, R, Hh, S(stream));
 }
 
+int gtos_debug_attn_trace(uint64_t* host_out, int32_t enable) {
+  return attn_debug_read_trace(reinterpret_cast<unsigned long long*>(host_out), enable);
+}
 int gtos_debug_read_trace(uint64_t* host_out, int32_t n) {
   return debug_read_trace(reinterpret_cast<unsigned long long*>(host_out), n);
 }

@@ -19,6 +19,11 @@ namespace gtos {
 
 using namespace nvcuda;
 
+// GTOS_DBG=2: clock64 timestamps of the phases of CTA 0 (timing experiments; attn_debug_read_trace)
+__device__ unsigned long long g_attn_trace[3 * 16];
+__device__ int g_attn_trace_on = 0;
+#define ATT_TRACE(k, slot) do { if (g_attn_trace_on && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) g_attn_trace[(k) * 16 + (slot)] = clock64(); } while (0)
+
 static constexpr int AT_THREADS = 256;
 static constexpr int AT_WARPS = 8;
 static constexpr int AT_ROWS_MAX = 64;  // query (or key) rows per CTA
@@ -178,6 +183,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnArgs a, 
   const int hoff = h * a.hd;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = a.S;
+  ATT_TRACE(0, 0);
 
   // ---- scores into sc ----
   if (a.scores_jt) {
@@ -194,6 +200,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnArgs a, 
     }
   }
   __syncthreads();
+  ATT_TRACE(0, 1);
 
   // ---- masks, softmax, dropout; probabilities -> global (fp32) and pb (bf16 operand) ----
   const unsigned long long seed = a.p_drop > 0.f ? reinterpret_cast<const unsigned long long*>(a.seed_ptr)[0] + a.seed_off : 0ull;
@@ -237,14 +244,18 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnArgs a, 
 
   // ---- PV: out[r][d] = sum_j pb[r][j] * V[j][d], staged in sc, written coalesced ----
   __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(a.out_bf16);
+  ATT_TRACE(0, 2);
   for (int c0 = 0; c0 < a.hd; c0 += dc) {
     __syncthreads();
     load_rows_bf16(s.yb, s.dstr, a.v, a.ldv, a.B, b, hoff, 0, s.L16, S, c0, dc);
     __syncthreads();
+    ATT_TRACE(0, 3);
     tile_mm<false>(s.pb, s.lstr, s.yb, s.dstr, s.sc, s.lstr, s.R16, dc16, s.L16, false);
     __syncthreads();
+    ATT_TRACE(0, 4);
     store_rows_f32(a.out, ob, a.ldo, a.B, b, hoff + c0, t0, nrows, dc, s.sc, s.lstr, 1.f);
   }
+  ATT_TRACE(0, 5);
 }
 
 // rows per CTA: the whole sequence when there are plenty of (batch, head) CTAs, otherwise split the rows so
@@ -260,6 +271,12 @@ static size_t attn_smem_bytes(int L, int hd, int rows) {
   int dc = hd < AT_DC ? hd : AT_DC;
   int a, b2, c, d;
   return attn_smem_layout(L, dc, rows, &a, &b2, &c, &d) + 128;
+}
+
+int attn_debug_read_trace(unsigned long long* host_out, int enable) {
+  GTOS_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_attn_trace, sizeof(unsigned long long) * 48));
+  GTOS_CHECK_CUDA(cudaMemcpyToSymbol(g_attn_trace_on, &enable, sizeof(int)));
+  return GTOS_OK;
 }
 
 int attn_fwd(const AttnArgs& a, cudaStream_t st) {
@@ -293,14 +310,17 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_q_kernel(const AttnBwdArg
   const int S = a.S;
 
   // dPd[t][j] = dO[t] . V[j]
+  ATT_TRACE(1, 0);
   for (int c0 = 0; c0 < a.hd; c0 += dc) {
     __syncthreads();
     load_rows_bf16(s.xb, s.dstr, g.dout, g.lddo, a.B, b, hoff, t0, s.R16, a.T, c0, dc);
     load_rows_bf16(s.yb, s.dstr, a.v, a.ldv, a.B, b, hoff, 0, s.L16, S, c0, dc);
     __syncthreads();
+    ATT_TRACE(1, 1);
     tile_mm<true>(s.xb, s.dstr, s.yb, s.dstr, s.sc, s.lstr, s.R16, s.L16, dc16, c0 > 0);
   }
   __syncthreads();
+  ATT_TRACE(1, 2);
 
   const unsigned long long seed = a.p_drop > 0.f ? reinterpret_cast<const unsigned long long*>(a.seed_ptr)[0] + a.seed_off : 0ull;
   const float ks = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
@@ -337,12 +357,14 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_q_kernel(const AttnBwdArg
     }
   }
   __syncthreads();
+  ATT_TRACE(1, 3);
   if (g.dscores_jt) {
     // transposed store for the fused relation backward kernel: [B,H,S(j),T(i)], coalesced along i
     for (int j = warp; j < S; j += AT_WARPS)
       for (int r = lane; r < nrows; r += 32)
         g.dscores_jt[((long)bh * S + j) * a.T + t0 + r] = s.sc[(size_t)r * s.lstr + j];
   }
+  ATT_TRACE(1, 4);
   if (g.dq) {
     for (int c0 = 0; c0 < a.hd; c0 += dc) {
       __syncthreads();
@@ -374,6 +396,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_kv_kernel(const AttnBwdAr
 
   // pb[jr][t] = Pd[t][j0+jr]  (transposed while loading; coalesced over jr in global)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  ATT_TRACE(2, 0);
   for (int t = warp; t < s.L16; t += AT_WARPS)
     for (int jr = lane; jr < s.R16; jr += 32) {
       float p = 0.f;
@@ -384,14 +407,18 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_kv_kernel(const AttnBwdAr
       }
       s.pb[(size_t)jr * s.lstr + t] = __float2bfloat16(p);
     }
+  ATT_TRACE(2, 1);
   for (int c0 = 0; c0 < a.hd; c0 += dc) {
     __syncthreads();
     load_rows_bf16(s.yb, s.dstr, g.dout, g.lddo, a.B, b, hoff, 0, s.L16, T, c0, dc);
     __syncthreads();
+    ATT_TRACE(2, 2);
     tile_mm<false>(s.pb, s.lstr, s.yb, s.dstr, s.sc, s.lstr, s.R16, dc16, s.L16, false);
     __syncthreads();
+    ATT_TRACE(2, 3);
     store_rows_f32(g.dv, nullptr, g.lddv, a.B, b, hoff + c0, j0, nrows, dc, s.sc, s.lstr, 1.f);
   }
+  ATT_TRACE(2, 4);
   if (g.dk) {
     __syncthreads();
     for (int t = warp; t < s.L16; t += AT_WARPS)

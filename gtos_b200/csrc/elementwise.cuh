@@ -66,6 +66,7 @@ struct AttnBwdArgs {
   float* dv; long lddv;
 };
 int attn_bwd(const AttnBwdArgs& a, cudaStream_t st);
+int attn_debug_read_trace(unsigned long long* host_out, int enable);   // 3 kernels x 16 clock64 slots of CTA 0
 
 // ---- GRU gate kernels (gru.cu) ------------------------------------------------------------
 int gru_weight_prep(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int Kin, int H, int Kx,

@@ -116,7 +116,7 @@ __device__ __forceinline__ void lds_sw128_bf16x16(const uint8_t* box, int row, i
 // each takes half of the unit's heads / hidden units - their epilogues (score / gradient / gate math) cost more
 // issue slots per unit than the unit's MMAs take cycles, and one warp per SM sub-partition cannot hide that
 template <int MODE>
-constexpr int tn_epi_wgs() { return (MODE == MODE_SCORE || MODE == MODE_GRAD || MODE == MODE_GRU) ? 2 : 1; }
+constexpr int tn_epi_wgs() { return 2; }   // plain / d_relation too: the warpgroups alternate over the 32-column output chunks
 template <int MODE>
 constexpr int tn_threads() { return 64 + 128 * tn_epi_wgs<MODE>(); }
 template <int MODE>
@@ -278,13 +278,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ================= epilogue (warps 2..5, relation modes: also 6..9) =================
     const int quarter = warp & 3;
-    [[maybe_unused]] const int wg = (warp - 2) >> 2;
+    const int wg = (warp - 2) >> 2;
     const int r = quarter * 32 + lane;  // accumulator row == TMEM lane
     int as = 0;
     uint32_t aph = 0;
     int qs = 0;
     uint32_t qph = 0;
-    int kc = 0;  // running output-chunk counter: staging buffer = kc & 1
     for (int unit = sched_id; unit < p.units; unit += sched_n) {
       const int m_blk = (unit / p.n_tiles) * CG + (int)rank, n_blk = unit % p.n_tiles;
       // MODE_GRU: fetch this thread's slice of the previous state, the bias block and the length flag while the
@@ -434,15 +433,19 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.tma_out) {
           // fp32 tile -> swizzled smem staging tile [128 rows x 32 cols] -> one TMA store per 32-column chunk
           // (double-buffered; OOB rows / columns are clipped by the tensor map)
-          const bool issuer = (warp == 2 && lane == 0);
+          // two epilogue warpgroups: wg owns staging buffer wg and every second output chunk (fp32: 32 columns, bf16: 64)
+          const bool issuer = (quarter == 2 && lane == 0);       // first warp of each warpgroup
           int b0 = 0, j0 = 0, i0 = 0;
           if constexpr (MODE == MODE_DREL) rel_tile_decode(p.rt, m_blk, b0, j0, i0);
           const int n0 = n_blk * BN;
+          const int own_shift = (MODE == MODE_PLAIN && p.tma_out == 2) ? 6 : 5;
+          uint8_t* const wbuf = out_stage + wg * (BM * 128);
 #pragma unroll 1
           for (int c = 0; c < BN; c += 32) {
             if (n0 + c >= p.N) break;
+            if (((c >> own_shift) & 1) != wg) continue;
             float v[32];
-            const bool trc = (warp == 2 && lane == 0 && unit == sched_id && c == 32);
+            const bool trc = (warp == 2 && lane == 0 && unit == sched_id && c == 0);
             if (trc) GTOS_TRACE(10);
             tmem_ld16(tacc + c, v);
             tmem_ld16(tacc + c + 16, v + 16);
@@ -493,10 +496,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (p.tma_out == 2) {
                 // bf16 output: two 32-column chunks fill one [128 rows x 64 bf16] swizzled tile, one TMA store per tile
                 const int half = (c >> 5) & 1;
-                uint8_t* buf = out_stage + (kc & 1) * (BM * 128);
+                uint8_t* buf = wbuf;
                 if (half == 0) {
-                  if (issuer) tma_store_wait_read<1>();
-                  named_bar_sync(1, 128);
+                  if (issuer) tma_store_wait_read<0>();
+                  named_bar_sync(1 + 2 * wg, 128);
                 }
                 uint8_t* rowp = buf + r * 128;
 #pragma unroll
@@ -506,22 +509,20 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                  pack_bf16x2(v[8 * t + 4], v[8 * t + 5]), pack_bf16x2(v[8 * t + 6], v[8 * t + 7]));
                 if (half == 1 || c + 32 >= BN || n0 + c + 32 >= p.N) {      // tile complete (or last chunk of the unit)
                   fence_proxy_async();
-                  named_bar_sync(2, 128);
+                  named_bar_sync(2 + 2 * wg, 128);
                   if (issuer) {
                     tma_store_2d(&tmO, buf, n0 + (c & ~63), m_blk * BM);
                     tma_store_commit();
                   }
-                  ++kc;
                 }
                 continue;
               }
             }
-            uint8_t* buf = out_stage + (kc & 1) * (BM * 128);
-            ++kc;
+            uint8_t* buf = wbuf;
             if (trc) GTOS_TRACE(12);
-            if (issuer) tma_store_wait_read<1>();   // the store that last read this buffer has drained
+            if (issuer) tma_store_wait_read<0>();   // this warpgroup's previous store has finished reading the buffer
             if (trc) GTOS_TRACE(13);
-            named_bar_sync(1, 128);
+            named_bar_sync(1 + 2 * wg, 128);
             if (trc) GTOS_TRACE(14);
             uint8_t* rowp = buf + r * 128;
 #pragma unroll
@@ -529,7 +530,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               *reinterpret_cast<float4*>(rowp + ((t ^ (r & 7)) << 4)) =
                   make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
             fence_proxy_async();
-            named_bar_sync(2, 128);
+            named_bar_sync(2 + 2 * wg, 128);
             if (issuer) {
               if constexpr (MODE == MODE_DREL) {
                 if (p.accumulate)
@@ -557,6 +558,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
         for (int c = 0; c < BN; c += 16) {
           if (n0 + c >= p.N) break;
+          if (((c >> 4) & 1) != wg) continue;     // the two warpgroups alternate over the 16-column chunks
           float v[16];
           tmem_ld16(tacc + c, v);
           const int n = n0 + c;

@@ -39,6 +39,9 @@ int gtos_device_check(void);
 /* timing experiments only: with GTOS_DBG=2 in the environment the plain GEMM records 16 clock64 timestamps per CTA
  * (phases of its pipeline); copies the first n of them (148 x 16) to HOST memory */
 int gtos_debug_read_trace(uint64_t* host_out, int32_t n);
+/* same for the attention core: copies 3 x 16 timestamps (fwd, bwd_q, bwd_kv; CTA 0) to HOST memory, then switches the
+ * recording on (enable != 0) or off */
+int gtos_debug_attn_trace(uint64_t* host_out, int32_t enable);
 
 /* ---- operand staging -------------------------------------------------------------------------- */
 /* fp32 [rows, cols] (lds) -> bf16 [rows, ldd]; columns cols..ldd-1 are zero-filled (TMA needs 16 B rows) */

@@ -57,11 +57,19 @@ _side_streams = {}
 _side_enabled = os.environ.get("GTOS_SIDE_STREAM", "0") == "1"
 
 
+# The two directions of a bidirectional GRU layer are independent chains of launches whose tile counts do not fill
+# whole waves (config 2: 193 row tiles of 128 on 148 SMs = two waves, the second 30 % full).  Issued on two streams the
+# second direction's CTAs take the SMs the first one leaves idle (386 tiles = 2.6 waves per pair of steps instead of
+# 4).  GTOS_GRU_STREAMS=0 keeps both directions on the caller's stream.
+_gru_streams = os.environ.get("GTOS_GRU_STREAMS", "1") == "1"
+_rel_streams = os.environ.get("GTOS_REL_STREAMS", "1") == "1"
+
+
 class _Fork:
-    def __init__(self):
+    def __init__(self, enabled=None):
         self.main = torch.cuda.current_stream()
         self.side = None
-        if _side_enabled:
+        if _side_enabled if enabled is None else enabled:
             key = self.main.device.index
             if key not in _side_streams:
                 _side_streams[key] = torch.cuda.Stream(device=self.main.device)
@@ -89,10 +97,10 @@ class _Fork:
             self.used = False
 
 
-def fork():
+def fork(enabled=None):
     """with fork() as f: <launches on the side stream> ... f.join() before the results are handed on.
     Outputs written inside the block must be allocated BEFORE it (on the caller's stream)."""
-    return _Fork()
+    return _Fork(enabled)
 
 
 # ---- dropout RNG: one device-resident 64-bit seed + a per-call-site offset -----------------
@@ -411,8 +419,6 @@ class RelAttnFn(torch.autograd.Function):
         G = torch.empty(tiles * 128, 2 * D, dtype=torch.bfloat16, device=dev)
         _lib.check(lib.gtos_rel_grad(_p(relb), _p(Wperm), qkb.data_ptr(), qkb.data_ptr() + 2 * D, 2 * D, _p(ds_jt),
                                      _p(G), N, B, D, H, _st()), "rel_grad")
-        _lib.check(lib.gtos_rel_dqk(_p(G), dqkv.data_ptr(), dqkv.data_ptr() + 4 * D, 3 * D, N, B, D, H, _st()),
-                   "rel_dqk")
         d_rel = None
         if ctx.rel_acc is not None and ctx.rel_acc.banked is not None:
             # relation = bank[idx]: segmented sum of G over bank rows, then R-row GEMMs instead of
@@ -432,13 +438,17 @@ class RelAttnFn(torch.autograd.Function):
             c0 = acc.slot * 2 * D
             acc.slot += 1
             s_ptr = acc.S.data_ptr() + 2 * c0
-            _lib.check(lib.gtos_rel_segsum(_p(G), _p(bk.order), _p(bk.keys), N * N * B, 2 * D, s_ptr, L * 2 * D,
-                                           _p(acc.spill), _st()), "rel_segsum")
             dW_rel = torch.empty(2 * D, D, dtype=torch.float32, device=dev)
             dW_in = torch.empty(3 * D, D, dtype=torch.float32, device=dev)
-            with fork() as f_rel:
+            # The bank side (segmented sum -> dW_rel, both off the critical path) and the node side (dq/dk segment sums ->
+            # in_proj backward -> dx) both stream G from HBM and are independent: two streams (GTOS_REL_STREAMS=0: one).
+            with fork(_rel_streams or None) as f_rel:
+                _lib.check(lib.gtos_rel_segsum(_p(G), _p(bk.order), _p(bk.keys), N * N * B, 2 * D, s_ptr, L * 2 * D,
+                                               _p(acc.spill), _st()), "rel_segsum")
                 _lib.check(lib.gtos_rel_dw_bank(s_ptr, L * 2 * D, _p(bk.bankb), _p(dW_rel), R, D, H, _st()), "rel_dw_bank")
                 acc.Wcat[:, c0:c0 + 2 * D].copy_(WpermT[:, :2 * D])
+            _lib.check(lib.gtos_rel_dqk(_p(G), dqkv.data_ptr(), dqkv.data_ptr() + 4 * D, 3 * D, N, B, D, H, _st()),
+                       "rel_dqk")
             dqkvb, db_in = cast_colsum(dqkv)
             with fork() as f_in:
                 gemm_nn(dqkvb, xb2, 3 * D, D, out=dW_in)
@@ -448,6 +458,8 @@ class RelAttnFn(torch.autograd.Function):
             f_in.join()
             return (dx.view(N, B, D), None, None, None, None, None, dW_in, db_in, dW_rel, dW_out, db_out, None, None,
                     None, None, None)
+        _lib.check(lib.gtos_rel_dqk(_p(G), dqkv.data_ptr(), dqkv.data_ptr() + 4 * D, 3 * D, N, B, D, H, _st()),
+                   "rel_dqk")
         if ctx.rel_acc is not None:
             # all layers share one relation tensor: reduce this layer's gradient straight into the shared buffer
             # (TMA reduce-add), which RelTokenFn hands to autograd once
@@ -729,11 +741,12 @@ class GRUBankFn(torch.autograd.Function):
         for l in range(num_layers):
             outb = torch.empty(rows, 2 * Hh, dtype=torch.bfloat16, device=dev) if l < num_layers - 1 else None
             Kx = _up64(Kin)
-            for d in range(2):
+            ldw = Kx + _up8(Hh)
+            per_dir = []
+            for d in range(2):                                                     # operands of both directions first
                 w_ih, w_hh, b_ih, b_hh = weights[(l * 2 + d) * 4:(l * 2 + d) * 4 + 4]
                 _, Wih_t = weight_prep(w_ih, want_b=False)                         # for dx in backward
                 _, Whh_t = weight_prep(w_hh, want_b=False)                         # for dh in backward
-                ldw = Kx + _up8(Hh)
                 Wcat = torch.empty(4 * Hh, ldw, dtype=torch.bfloat16, device=dev)
                 bcat = torch.empty(4 * Hh, dtype=torch.float32, device=dev)
                 _lib.check(lib.gtos_gru_weight_prep(_p(w_ih.detach()), _p(w_hh.detach()), _p(b_ih.detach()),
@@ -745,17 +758,26 @@ class GRUBankFn(torch.autograd.Function):
                 hsb = torch.empty(Lmax + 1, R, Hh, dtype=torch.bfloat16, device=dev)
                 hs[0].zero_()
                 hsb[0].zero_()
+                per_dir.append((Wcat, bcat, gates, hs, hsb))
+                saved += [xb, gates, hs, hsb, Wih_t, Whh_t]
+
+            def run_dir(d, xb=xb, outb=outb, Kin=Kin, Kx=Kx, ldw=ldw, per_dir=per_dir, last=(l == num_layers - 1)):
+                Wcat, bcat, gates, hs, hsb = per_dir[d]
                 for s in range(Lmax):
                     t = s if d == 0 else Lmax - 1 - s
                     x_t = xb[t * R:(t + 1) * R]
-                    out_t = outb[t * R:(t + 1) * R, d * Hh:(d + 1) * Hh] if l < num_layers - 1 else None
+                    out_t = outb[t * R:(t + 1) * R, d * Hh:(d + 1) * Hh] if not last else None
                     _lib.check(lib.gtos_gru_step_fwd(_p(x_t), x_t.stride(0), Kin, _p(hsb[s]), Hh, _p(hs[s]), _p(Wcat), ldw,
                                                      Kx, _p(bcat), _p(lengths), t, _p(hs[s + 1]), _p(hsb[s + 1]), Hh,
                                                      _p(out_t), 2 * Hh, _p(gates[s]), 4 * Hh, R, Hh, _st()),
                                "gru_step_fwd")
-                if l == num_layers - 1:
+                if last:
                     finals_b[:, d * Hh:(d + 1) * Hh].copy_(hsb[Lmax])
-                saved += [xb, gates, hs, hsb, Wih_t, Whh_t]
+
+            with fork(_gru_streams) as f_rev:                                      # reverse direction on the second stream
+                run_dir(1)
+            run_dir(0)
+            f_rev.join()
             off_l = 0
             if l < num_layers - 1 and p > 0:                                       # nn.GRU inter-layer dropout
                 off_l = new_seed_off()
@@ -786,16 +808,28 @@ class GRUBankFn(torch.autograd.Function):
         for l in range(num_layers - 1, -1, -1):
             dgi_cat = torch.empty(rows, 6 * Hh, dtype=torch.bfloat16, device=dev)      # [dgi_fwd | dgi_rev], time order
             Wih_t_cat = []
-            for d in range(2):
+            per_dir = []
+            for d in range(2):                                                         # outputs of both directions first
                 xb, gates, hs, hsb, Wih_t, Whh_t = saved[(l * 2 + d) * 6:(l * 2 + d) * 6 + 6]
                 Kin = Wih_t.shape[0]
+                base = (l * 2 + d) * 4
+                wgrads[base + 0] = torch.empty(3 * Hh, Kin, dtype=torch.float32, device=dev)
+                wgrads[base + 1] = torch.empty(3 * Hh, Hh, dtype=torch.float32, device=dev)
+                wgrads[base + 2] = torch.zeros(3 * Hh, dtype=torch.float32, device=dev)
+                wgrads[base + 3] = torch.zeros(3 * Hh, dtype=torch.float32, device=dev)
                 dgh = torch.empty(rows, 3 * Hh, dtype=torch.bfloat16, device=dev)      # rows in step order s
+                per_dir.append(dgh)
+                Wih_t_cat.append(Wih_t)
+
+            def run_dir(d, l=l, per_dir=per_dir, dgi_cat=dgi_cat, d_layer_out=d_layer_out):
+                xb, gates, hs, hsb, Wih_t, Whh_t = saved[(l * 2 + d) * 6:(l * 2 + d) * 6 + 6]
+                Kin = Wih_t.shape[0]
+                base = (l * 2 + d) * 4
+                dgh, db_ih, db_hh = per_dir[d], wgrads[base + 2], wgrads[base + 3]
                 if l == num_layers - 1:
                     dh = dfinals[:, d * Hh:(d + 1) * Hh].contiguous()
                 else:
                     dh = torch.zeros(R, Hh, dtype=torch.float32, device=dev)
-                db_ih = torch.zeros(3 * Hh, dtype=torch.float32, device=dev)
-                db_hh = torch.zeros(3 * Hh, dtype=torch.float32, device=dev)
                 dgi = dgi_cat[:, d * 3 * Hh:(d + 1) * 3 * Hh]                          # rows in time order t
                 for s in range(Lmax - 1, -1, -1):
                     t = s if d == 0 else Lmax - 1 - s
@@ -810,12 +844,14 @@ class GRUBankFn(torch.autograd.Function):
                     _lib.check(lib.gtos_gemm_tn_add(_p(dgh_s), 3 * Hh, _p(Whh_t), Whh_t.stride(0), None, _p(dh_part), Hh,
                                                     _p(dh_prev), Hh, R, Hh, 3 * Hh, _st()), "gemm_tn_add")
                     dh = dh_prev
-                base = (l * 2 + d) * 4
-                wgrads[base + 0] = gemm_nn(dgi, xb, 3 * Hh, Kin)
-                wgrads[base + 1] = gemm_nn(dgh, hsb[:Lmax].view(rows, Hh), 3 * Hh, Hh)
-                wgrads[base + 2] = db_ih
-                wgrads[base + 3] = db_hh
-                Wih_t_cat.append(Wih_t)
+                gemm_nn(dgi, xb, 3 * Hh, Kin, out=wgrads[base + 0])
+                gemm_nn(dgh, hsb[:Lmax].view(rows, Hh), 3 * Hh, Hh, out=wgrads[base + 1])
+
+            with fork(_gru_streams) as f_rev:                                          # reverse direction on the second stream
+                run_dir(1)
+            run_dir(0)
+            f_rev.join()
+            Kin = Wih_t_cat[0].shape[0]
             # dx of both directions in ONE GEMM: [dgi_fwd | dgi_rev] x [Wih_fwd^T ; Wih_rev^T]
             Wcat_t = torch.cat(Wih_t_cat, dim=1) if Wih_t_cat[0].shape[1] == 3 * Hh else None
             if Wcat_t is not None:

@@ -173,6 +173,7 @@ __device__ __forceinline__ bool is_masked(const AttnArgs& a, int b, int t, int j
 // forward
 // ============================================================================================
 __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnArgs a, const int rows) {
+  GTOS_PDL_PROLOGUE();
   extern __shared__ __align__(128) uint8_t smem_u8[];
   const int dc = a.hd < AT_DC ? a.hd : AT_DC;
   const int dc16 = r16(dc);
@@ -288,7 +289,7 @@ int attn_fwd(const AttnArgs& a, cudaStream_t st) {
   GTOS_REQUIRE(smem <= 227 * 1024, "attention: source length %d too long for shared memory", a.S);
   GTOS_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(a.B * a.H, (a.T + rows - 1) / rows);
-  attn_fwd_kernel<<<grid, AT_THREADS, smem, st>>>(a, rows);
+  GTOS_KLAUNCH(attn_fwd_kernel, dim3(grid), dim3(AT_THREADS), smem, st, a, rows);
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
 }
@@ -297,6 +298,7 @@ int attn_fwd(const AttnArgs& a, cudaStream_t st) {
 // backward, query side: dS (and dq in decoder mode)
 // ============================================================================================
 __global__ void __launch_bounds__(AT_THREADS) attn_bwd_q_kernel(const AttnBwdArgs g, const int rows) {
+  GTOS_PDL_PROLOGUE();
   extern __shared__ __align__(128) uint8_t smem_u8[];
   const AttnArgs& a = g.f;
   const int dc = a.hd < AT_DC ? a.hd : AT_DC;
@@ -381,6 +383,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_q_kernel(const AttnBwdArg
 // backward, key side: dV = Pd^T dO ; dK = scale * dS^T q      (CTA = `rows` key rows of one (b,h))
 // ============================================================================================
 __global__ void __launch_bounds__(AT_THREADS) attn_bwd_kv_kernel(const AttnBwdArgs g, const int rows) {
+  GTOS_PDL_PROLOGUE();
   extern __shared__ __align__(128) uint8_t smem_u8[];
   const AttnArgs& a = g.f;
   const int dc = a.hd < AT_DC ? a.hd : AT_DC;
@@ -447,10 +450,10 @@ int attn_bwd(const AttnBwdArgs& g, cudaStream_t st) {
   GTOS_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smq));
   GTOS_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smk));
   dim3 gq(a.B * a.H, (a.T + rq - 1) / rq);
-  attn_bwd_q_kernel<<<gq, AT_THREADS, smq, st>>>(g, rq);
+  GTOS_KLAUNCH(attn_bwd_q_kernel, dim3(gq), dim3(AT_THREADS), smq, st, g, rq);
   GTOS_LAUNCH_CHECK();
   dim3 gk(a.B * a.H, (a.S + rk - 1) / rk);
-  attn_bwd_kv_kernel<<<gk, AT_THREADS, smk, st>>>(g, rk);
+  GTOS_KLAUNCH(attn_bwd_kv_kernel, dim3(gk), dim3(AT_THREADS), smk, st, g, rk);
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
 }

@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "../../include/gtos_b200.h"
 
@@ -40,6 +42,55 @@ extern unsigned long long g_kernel_launches;  // kernels enqueued through this l
   } while (0)
 
 #if defined(__CUDACC__)
+// ---------------------------------------------------------------------------------------
+// kernel launch: every kernel of the library goes through launch_pdl.  With programmatic stream serialization the next
+// kernel of a stream (or of a captured graph) is scheduled while its predecessor still runs; its CTAs become resident,
+// execute GTOS_PDL_PROLOGUE() and block in griddepcontrol.wait until the predecessor grid has completed and flushed.
+// Every kernel begins with GTOS_PDL_PROLOGUE() and touches no global memory before it.
+// The tcgen05 GEMM family always launches this way (its prologue - barrier init, TMEM allocation, descriptor prefetch -
+// is worth hiding).  For the elementwise / attention / GRU-gate kernels it measured NEUTRAL on the config-2 step
+// (9.777 ms with, 9.776 ms without, CUDA-graph replay on B200): their prologues are empty and the graph already issues
+// dependent kernel nodes back to back.  So cluster == 0 (those kernels) uses plain stream order unless GTOS_PDL_EW=1.
+// ---------------------------------------------------------------------------------------
+template <class... KArgs, class... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              int cluster, Args... args) {
+  static const bool pdl_all = !(getenv("GTOS_PDL") && getenv("GTOS_PDL")[0] == '0');
+  static const bool pdl_ew = getenv("GTOS_PDL_EW") && getenv("GTOS_PDL_EW")[0] == '1';
+  const bool pdl = pdl_all && (cluster != 0 || pdl_ew);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (pdl) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
+#define GTOS_KLAUNCH(kern, grid, block, smem, st, ...) \
+  GTOS_CHECK_CUDA(gtos::launch_pdl(kern, grid, block, (size_t)(smem), st, 0, __VA_ARGS__))
+#define GTOS_PDL_PROLOGUE()      \
+  do {                           \
+    pdl_launch_dependents();     \
+    pdl_wait();                  \
+  } while (0)
+
 // ---------------------------------------------------------------------------------------
 // small device utilities
 // ---------------------------------------------------------------------------------------

@@ -51,6 +51,7 @@ __device__ __forceinline__ float dot8_bf16(const float* q, uint4 u) {
 //   3. P.V: a lane owns EPL consecutive features (one 4/8/16-byte load per row), 4 rows unrolled.
 template <int EPL>
 __global__ void attn_decode_kernel(const DecodeAttn a) {
+  GTOS_PDL_PROLOGUE();
   extern __shared__ float sm[];
   const int wpb = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int hyp = blockIdx.x * wpb + w, head = blockIdx.y;
@@ -195,6 +196,7 @@ __device__ __forceinline__ void ld_chunk(const char* p, uint32_t* w) {
 
 template <int DPL>
 __global__ void attn_decode_wide_kernel(const DecodeAttn a) {
+  GTOS_PDL_PROLOGUE();
   extern __shared__ float sm[];
   constexpr int NW = DPL / 2, U = 8;
   const int wpb = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -306,7 +308,7 @@ static int launch_attn_decode_wide(const DecodeAttn& a, cudaStream_t st) {
   const size_t smem = per_warp * wpb;
   auto kern = attn_decode_wide_kernel<DPL>;
   if (smem > 48 * 1024) GTOS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  kern<<<(unsigned)((a.Hyp + wpb - 1) / wpb), wpb * 32, smem, st>>>(a);
+  GTOS_KLAUNCH(kern, dim3((unsigned)((a.Hyp + wpb - 1) / wpb)), dim3(wpb * 32), smem, st, a);
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
 }
@@ -352,7 +354,7 @@ int attn_decode(int Hyp, int L, int H, int hd, const float* q, long ldq, const v
       if (rc >= 0) return rc;
     }
   }
-  kern<<<dim3((unsigned)((Hyp + wpb - 1) / wpb), (unsigned)H), wpb * 32, smem, st>>>(a);
+  GTOS_KLAUNCH(kern, dim3(dim3((unsigned)((Hyp + wpb - 1) / wpb), (unsigned)H)), dim3(wpb * 32), smem, st, a);
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
 }
@@ -378,6 +380,7 @@ __global__ void token_logprob_kernel(const float* __restrict__ logits, long ldl,
                                      const float* __restrict__ align, int S, const long long* __restrict__ copy_seq,
                                      int Bsrc, const int* __restrict__ src_index, int B, float* __restrict__ table, long ldt,
                                      int W) {
+  GTOS_PDL_PROLOGUE();
   __shared__ float sh[32];
   const long row = blockIdx.x;
   const int b = src_index ? src_index[row] : (int)(row % B);
@@ -409,7 +412,7 @@ int token_logprob(const float* logits, long ldl, int V, const float* gate_logits
                   cudaStream_t st) {
   if (rows == 0) return GTOS_OK;
   GTOS_REQUIRE(W >= V && ldt >= W && Bsrc > 0 && B > 0, "token_logprob: need W >= V, ldt >= W (V=%d, W=%d, ldt=%ld)", V, W, ldt);
-  token_logprob_kernel<<<(unsigned)rows, 256, 0, st>>>(logits, ldl, V, gate_logits, align, S, copy_seq, Bsrc, src_index, B,
+  GTOS_KLAUNCH(token_logprob_kernel, dim3((unsigned)rows), dim3(256), 0, st, logits, ldl, V, gate_logits, align, S, copy_seq, Bsrc, src_index, B,
                                                        table, ldt, W);
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
@@ -443,6 +446,7 @@ __global__ void token_topk_kernel(const float* __restrict__ logits, long ldl, in
                                   const float* __restrict__ align, int S, const long long* __restrict__ copy_seq, int Bsrc,
                                   const int* __restrict__ src_index, int B, int W, int K, float* __restrict__ top_val,
                                   int* __restrict__ top_idx, float* __restrict__ table, long ldt) {
+  GTOS_PDL_PROLOGUE();
   extern __shared__ float prow[];                     // W probabilities
   __shared__ float sh[32];
   __shared__ unsigned long long shu[32];
@@ -528,7 +532,7 @@ int token_topk(const float* logits, long ldl, int V, const float* gate_logits, c
   GTOS_REQUIRE(smem <= 200 * 1024, "token_topk: vocabulary row of %d entries does not fit in shared memory", W);
   if (smem > 40 * 1024)
     GTOS_CHECK_CUDA(cudaFuncSetAttribute(token_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  token_topk_kernel<<<(unsigned)rows, 256, smem, st>>>(logits, ldl, V, gate_logits, align, S, copy_seq, Bsrc, src_index, B, W, K,
+  GTOS_KLAUNCH(token_topk_kernel, dim3((unsigned)rows), dim3(256), smem, st, logits, ldl, V, gate_logits, align, S, copy_seq, Bsrc, src_index, B, W, K,
                                                        top_val, top_idx, table, ldt);
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
@@ -549,6 +553,7 @@ struct BeamUpd {
 };
 
 __global__ void beam_update_kernel(const BeamUpd a) {
+  GTOS_PDL_PROLOGUE();
   __shared__ float s_val[256];
   __shared__ unsigned char s_valid[256];
   __shared__ int s_rank_c[16];       // candidate id holding rank r (r < K)
@@ -641,7 +646,7 @@ int beam_update(const BeamUpd& a, cudaStream_t st) {
   GTOS_REQUIRE(a.t >= 0 && a.t < a.Tmax, "beam_update: step %d outside [0, %d)", a.t, a.Tmax);
   int threads = ((a.K * a.K + 31) / 32) * 32;
   if (threads < 32) threads = 32;
-  beam_update_kernel<<<(unsigned)a.B, threads, 0, st>>>(a);
+  GTOS_KLAUNCH(beam_update_kernel, dim3((unsigned)a.B), dim3(threads), 0, st, a);
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
 }
@@ -654,6 +659,7 @@ int beam_update(const BeamUpd& a, cudaStream_t st) {
 // launches there, two launches here.  Elements [0, n_decay) take the weight decay, [n_decay, n) do not.
 // ---------------------------------------------------------------------------------------
 __global__ void sumsq_partial_kernel(const float* __restrict__ g, long n, float* __restrict__ partials) {
+  GTOS_PDL_PROLOGUE();
   __shared__ float sh[32];
   const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long)gridDim.x * blockDim.x;
   const long n4 = n / 4;
@@ -668,6 +674,7 @@ __global__ void sumsq_partial_kernel(const float* __restrict__ g, long n, float*
 }
 
 __global__ void sumsq_final_kernel(const float* __restrict__ partials, int n, float* __restrict__ out) {
+  GTOS_PDL_PROLOGUE();
   __shared__ double shd[32];
   double s = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) s += (double)partials[i];
@@ -688,9 +695,9 @@ long grad_sumsq_workspace() { return kSumsqBlocks; }
 int grad_sumsq(const float* g, long n, float* out, float* workspace, cudaStream_t st) {
   GTOS_REQUIRE(g && out && workspace, "grad_sumsq: null argument");
   GTOS_REQUIRE((reinterpret_cast<uintptr_t>(g) & 15) == 0, "grad_sumsq: buffer must be 16-byte aligned");
-  sumsq_partial_kernel<<<kSumsqBlocks, 256, 0, st>>>(g, n, workspace);
+  GTOS_KLAUNCH(sumsq_partial_kernel, dim3(kSumsqBlocks), dim3(256), 0, st, g, n, workspace);
   GTOS_LAUNCH_CHECK();
-  sumsq_final_kernel<<<1, 256, 0, st>>>(workspace, kSumsqBlocks, out);
+  GTOS_KLAUNCH(sumsq_final_kernel, dim3(1), dim3(256), 0, st, workspace, kSumsqBlocks, out);
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
 }
@@ -707,6 +714,7 @@ __device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v,
 __global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                  float* __restrict__ v, long n, long n_decay, const float* __restrict__ lr_ptr, float b1,
                                  float b2, float eps, float wd, const float* __restrict__ norm_sq, float max_norm) {
+  GTOS_PDL_PROLOGUE();
   const float lr = lr_ptr[0];
   float clip = 1.f;
   if (norm_sq) {
@@ -738,7 +746,7 @@ int adam_step(float* p, const float* g, float* m, float* v, long n, long n_decay
                  reinterpret_cast<uintptr_t>(v)) & 15) == 0, "adam_step: buffers must be 16-byte aligned");
   long blocks = (n / 4 + 255) / 256 + 1;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  adam_step_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, g, m, v, n, n_decay, lr_ptr, b1, b2, eps, wd, norm_sq, max_norm);
+  GTOS_KLAUNCH(adam_step_kernel, dim3((unsigned)blocks), dim3(256), 0, st, p, g, m, v, n, n_decay, lr_ptr, b1, b2, eps, wd, norm_sq, max_norm);
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
 }
@@ -750,6 +758,7 @@ int adam_step(float* p, const float* g, float* m, float* v, long n, long n_decay
 // ---------------------------------------------------------------------------------------
 __global__ void beam_ancestry_kernel(const int* __restrict__ old_anc, int* __restrict__ new_anc, long ld,
                                      const int* __restrict__ parent, int t, int Hyp) {
+  GTOS_PDL_PROLOGUE();
   const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long total = (long)(t + 1) * Hyp;
   if (tid >= total) return;
@@ -761,7 +770,7 @@ int beam_ancestry(const int* old_anc, int* new_anc, long ld, const int* parent, 
   if (Hyp == 0) return GTOS_OK;
   GTOS_REQUIRE(new_anc && (t == 0 || old_anc) && old_anc != new_anc, "beam_ancestry: need distinct old / new tables");
   const long total = (long)(t + 1) * Hyp;
-  beam_ancestry_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(old_anc, new_anc, ld, parent, t, Hyp);
+  GTOS_KLAUNCH(beam_ancestry_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, old_anc, new_anc, ld, parent, t, Hyp);
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
 }

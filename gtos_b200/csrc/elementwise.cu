@@ -10,6 +10,7 @@ namespace gtos {
 // ---------------------------------------------------------------------------------------
 __global__ void cast_pad_kernel(const float* __restrict__ src, long lds, __nv_bfloat16* __restrict__ dst, long ldd,
                                 long rows, int cols) {
+  GTOS_PDL_PROLOGUE();
   const long total = rows * (ldd / 2);
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
     const long r = idx / (ldd / 2);
@@ -22,6 +23,7 @@ __global__ void cast_pad_kernel(const float* __restrict__ src, long lds, __nv_bf
 }
 
 __global__ void cast_vec_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, long n4) {
+  GTOS_PDL_PROLOGUE();
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
     float4 v = src[i];
     dst[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
@@ -35,11 +37,11 @@ int cast_f32_bf16(const float* src, long lds, void* dst, long ldd, long rows, in
       (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
     long n4 = rows * cols / 4;
     int blocks = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
-    cast_vec_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<uint2*>(dst), n4);
+    GTOS_KLAUNCH(cast_vec_kernel, dim3(blocks), dim3(256), 0, st, reinterpret_cast<const float4*>(src), reinterpret_cast<uint2*>(dst), n4);
   } else {
     long total = rows * (ldd / 2);
     int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-    cast_pad_kernel<<<blocks, 256, 0, st>>>(src, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldd, rows, cols);
+    GTOS_KLAUNCH(cast_pad_kernel, dim3(blocks), dim3(256), 0, st, src, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldd, rows, cols);
   }
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
@@ -49,6 +51,7 @@ int cast_f32_bf16(const float* src, long lds, void* dst, long ldd, long rows, in
 // the bf16 operand of the two gradient GEMMs and the bias gradient)
 __global__ void cast_colsum_kernel(const float* __restrict__ src, long lds, __nv_bfloat16* __restrict__ dst, long ldd,
                                    float* __restrict__ sums, long rows, int cols, int rows_per_block) {
+  GTOS_PDL_PROLOGUE();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ldd) return;
   const long r0 = (long)blockIdx.y * rows_per_block;
@@ -69,6 +72,7 @@ __global__ void cast_colsum_kernel(const float* __restrict__ src, long lds, __nv
 // 4 columns per thread (16-byte loads, 8-byte stores), 4 rows in flight
 __global__ void cast_colsum_vec4_kernel(const float* __restrict__ src, long lds, __nv_bfloat16* __restrict__ dst, long ldd,
                                         float* __restrict__ sums, long rows, int cols, int rows_per_block) {
+  GTOS_PDL_PROLOGUE();
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (c >= ldd) return;
   const long r0 = (long)blockIdx.y * rows_per_block;
@@ -105,13 +109,13 @@ int cast_colsum(const float* src, long lds, void* dst, long ldd, float* sums, lo
       (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
     const int rpb = 32;
     dim3 grid((unsigned)((ldd / 4 + 127) / 128), (unsigned)((rows + rpb - 1) / rpb));
-    cast_colsum_vec4_kernel<<<grid, 128, 0, st>>>(src, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldd, sums, rows, cols, rpb);
+    GTOS_KLAUNCH(cast_colsum_vec4_kernel, dim3(grid), dim3(128), 0, st, src, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldd, sums, rows, cols, rpb);
     GTOS_LAUNCH_CHECK();
     return GTOS_OK;
   }
   const int rpb = 32;
   dim3 grid((unsigned)((ldd + 127) / 128), (unsigned)((rows + rpb - 1) / rpb));
-  cast_colsum_kernel<<<grid, 128, 0, st>>>(src, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldd, sums, rows, cols, rpb);
+  GTOS_KLAUNCH(cast_colsum_kernel, dim3(grid), dim3(128), 0, st, src, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldd, sums, rows, cols, rpb);
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
 }
@@ -122,6 +126,7 @@ int cast_colsum(const float* src, long lds, void* dst, long ldd, float* sums, lo
 // ---------------------------------------------------------------------------------------
 __global__ void weight_prep_kernel(const float* __restrict__ W, int R, int C, __nv_bfloat16* __restrict__ Wb, long ldw,
                                    __nv_bfloat16* __restrict__ Wt, long ldt, int perm_D, int perm_hd) {
+  GTOS_PDL_PROLOGUE();
   __shared__ float tile[32][33];
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
   for (int y = threadIdx.y; y < 32; y += blockDim.y) {
@@ -149,7 +154,7 @@ int weight_prep(const float* W, int R, int C, void* Wb, long ldw, void* Wt, long
   int cx = (int)(((Wb ? (ldw > C ? ldw : C) : C) + 31) / 32);
   int ry = (int)(((Wt ? (ldt > R ? ldt : R) : R) + 31) / 32);
   dim3 grid(cx, ry), block(32, 8);
-  weight_prep_kernel<<<grid, block, 0, st>>>(W, R, C, reinterpret_cast<__nv_bfloat16*>(Wb), ldw,
+  GTOS_KLAUNCH(weight_prep_kernel, dim3(grid), dim3(block), 0, st, W, R, C, reinterpret_cast<__nv_bfloat16*>(Wb), ldw,
                                              reinterpret_cast<__nv_bfloat16*>(Wt), ldt, perm_D, perm_hd);
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
@@ -167,6 +172,7 @@ __global__ void add_ln_fwd_kernel(const float* __restrict__ x, const float* __re
                                   float* __restrict__ mean_out, float* __restrict__ rstd_out, long rows, int D,
                                   float p_drop, const unsigned long long* __restrict__ seed_ptr,
                                   unsigned long long seed_off, float eps) {
+  GTOS_PDL_PROLOGUE();
   const int lane = threadIdx.x & 31;
   const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -226,6 +232,7 @@ __global__ void __launch_bounds__(128) add_ln_fwd_vec_kernel(
     const float* __restrict__ beta, float* __restrict__ y, __nv_bfloat16* __restrict__ y_bf16, float* __restrict__ z_out,
     float* __restrict__ mean_out, float* __restrict__ rstd_out, long rows, float p_drop,
     const unsigned long long* __restrict__ seed_ptr, unsigned long long seed_off, float eps) {
+  GTOS_PDL_PROLOGUE();
   constexpr int D = NV * 128;
   const int lane = threadIdx.x & 31;
   const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -296,7 +303,7 @@ int add_ln_fwd(const float* x, const float* res, const float* gamma, const float
     __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(y_bf16);
     const unsigned long long* sp = reinterpret_cast<const unsigned long long*>(seed_ptr);
 #define GTOS_LN_FWD(NV)                                                                                               \
-  add_ln_fwd_vec_kernel<NV><<<blocks, 128, 0, st>>>(x, res, gamma, beta, y, yb, z, mean, rstd, rows, p_drop, sp,      \
+  GTOS_KLAUNCH(add_ln_fwd_vec_kernel<NV>, dim3(blocks), dim3(128), 0, st, x, res, gamma, beta, y, yb, z, mean, rstd, rows, p_drop, sp,      \
                                                     seed_off, 1e-5f)
     switch (D / 128) {
       case 1: GTOS_LN_FWD(1); break;
@@ -313,7 +320,7 @@ int add_ln_fwd(const float* x, const float* res, const float* gamma, const float
     return GTOS_OK;
   }
   const int wpb = 4;
-  add_ln_fwd_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(
+  GTOS_KLAUNCH(add_ln_fwd_kernel, dim3((unsigned)((rows + wpb - 1) / wpb)), dim3(wpb * 32), 0, st, 
       x, res, gamma, beta, y, reinterpret_cast<__nv_bfloat16*>(y_bf16), z, mean, rstd, rows, D, p_drop,
       reinterpret_cast<const unsigned long long*>(seed_ptr), seed_off, 1e-5f);
   GTOS_LAUNCH_CHECK();
@@ -328,6 +335,7 @@ __global__ void add_ln_bwd_kernel(const float* __restrict__ dy, const float* __r
                                   const float* __restrict__ gamma, float* __restrict__ dres, float* __restrict__ dx,
                                   __nv_bfloat16* __restrict__ dx_bf16, long rows, int D, float p_drop,
                                   const unsigned long long* __restrict__ seed_ptr, unsigned long long seed_off) {
+  GTOS_PDL_PROLOGUE();
   // one warp per row (many warps in flight: the kernel is latency-bound on three dependent passes per row)
   const int lane = threadIdx.x & 31;
   const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -376,6 +384,7 @@ __global__ void ln_param_grad_kernel(const float* __restrict__ dy, const float* 
                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                      float* __restrict__ dgamma, float* __restrict__ dbeta, long rows, int D,
                                      int rows_per_block) {
+  GTOS_PDL_PROLOGUE();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= D) return;
   long r0 = (long)blockIdx.y * rows_per_block;
@@ -396,6 +405,7 @@ __global__ void __launch_bounds__(128) add_ln_bwd_vec_kernel(
     const float* __restrict__ rstd, const float* __restrict__ gamma, float* __restrict__ dres, float* __restrict__ dx,
     __nv_bfloat16* __restrict__ dx_bf16, long rows, float p_drop, const unsigned long long* __restrict__ seed_ptr,
     unsigned long long seed_off) {
+  GTOS_PDL_PROLOGUE();
   constexpr int D = NV * 128;
   const int lane = threadIdx.x & 31;
   const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -452,7 +462,7 @@ int add_ln_bwd(const float* dy, const float* z, const float* mean, const float* 
     const unsigned blocks = (unsigned)((rows + 3) / 4);
     __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
     const unsigned long long* sp = reinterpret_cast<const unsigned long long*>(seed_ptr);
-#define GTOS_LN_BWD(NV) add_ln_bwd_vec_kernel<NV><<<blocks, 128, 0, st>>>(dy, z, mean, rstd, gamma, dres, dx, xb, rows, p_drop, sp, seed_off)
+#define GTOS_LN_BWD(NV) GTOS_KLAUNCH(add_ln_bwd_vec_kernel<NV>, dim3(blocks), dim3(128), 0, st, dy, z, mean, rstd, gamma, dres, dx, xb, rows, p_drop, sp, seed_off)
     switch (D / 128) {
       case 1: GTOS_LN_BWD(1); break;
       case 2: GTOS_LN_BWD(2); break;
@@ -467,18 +477,18 @@ int add_ln_bwd(const float* dy, const float* z, const float* mean, const float* 
     GTOS_LAUNCH_CHECK();
     const int rpb = 32;   // thread per column: 4 x more threads in flight than a float4-per-thread variant, which measured slower
     dim3 grid((D + 127) / 128, (unsigned)((rows + rpb - 1) / rpb));
-    ln_param_grad_kernel<<<grid, 128, 0, st>>>(dy, z, mean, rstd, dgamma, dbeta, rows, D, rpb);
+    GTOS_KLAUNCH(ln_param_grad_kernel, dim3(grid), dim3(128), 0, st, dy, z, mean, rstd, dgamma, dbeta, rows, D, rpb);
     GTOS_LAUNCH_CHECK();
     return GTOS_OK;
   }
   const int wpb = 4;
-  add_ln_bwd_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(
+  GTOS_KLAUNCH(add_ln_bwd_kernel, dim3((unsigned)((rows + wpb - 1) / wpb)), dim3(wpb * 32), 0, st, 
       dy, z, mean, rstd, gamma, dres, dx, reinterpret_cast<__nv_bfloat16*>(dx_bf16), rows, D, p_drop,
       reinterpret_cast<const unsigned long long*>(seed_ptr), seed_off);
   GTOS_LAUNCH_CHECK();
   const int rpb = 32;
   dim3 grid((D + 127) / 128, (unsigned)((rows + rpb - 1) / rpb));
-  ln_param_grad_kernel<<<grid, 128, 0, st>>>(dy, z, mean, rstd, dgamma, dbeta, rows, D, rpb);
+  GTOS_KLAUNCH(ln_param_grad_kernel, dim3(grid), dim3(128), 0, st, dy, z, mean, rstd, dgamma, dbeta, rows, D, rpb);
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
 }
@@ -488,6 +498,7 @@ int add_ln_bwd(const float* dy, const float* z, const float* mean, const float* 
 // ---------------------------------------------------------------------------------------
 __global__ void colsum_kernel(const float* __restrict__ x, long ld, float* __restrict__ out, long rows, int cols,
                               int rows_per_block) {
+  GTOS_PDL_PROLOGUE();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cols) return;
   long r0 = (long)blockIdx.y * rows_per_block;
@@ -499,6 +510,7 @@ __global__ void colsum_kernel(const float* __restrict__ x, long ld, float* __res
 
 __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long ld, float* __restrict__ out, long rows,
                                    int cols, int rows_per_block) {
+  GTOS_PDL_PROLOGUE();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cols) return;
   long r0 = (long)blockIdx.y * rows_per_block;
@@ -513,7 +525,7 @@ int colsum_bf16(const void* x, long ld, float* out, long rows, int cols, cudaStr
   if (rows == 0) return GTOS_OK;
   int rpb = 64;
   dim3 grid((cols + 127) / 128, (unsigned)((rows + rpb - 1) / rpb));
-  colsum_bf16_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, out, rows, cols, rpb);
+  GTOS_KLAUNCH(colsum_bf16_kernel, dim3(grid), dim3(128), 0, st, reinterpret_cast<const __nv_bfloat16*>(x), ld, out, rows, cols, rpb);
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
 }
@@ -523,7 +535,7 @@ int colsum(const float* x, long ld, float* out, long rows, int cols, cudaStream_
   if (rows == 0) return GTOS_OK;
   int rpb = 64;
   dim3 grid((cols + 127) / 128, (unsigned)((rows + rpb - 1) / rpb));
-  colsum_kernel<<<grid, 128, 0, st>>>(x, ld, out, rows, cols, rpb);
+  GTOS_KLAUNCH(colsum_kernel, dim3(grid), dim3(128), 0, st, x, ld, out, rows, cols, rpb);
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
 }
@@ -534,6 +546,7 @@ int colsum(const float* x, long ld, float* out, long rows, int cols, cudaStream_
 // ---------------------------------------------------------------------------------------
 __global__ void dropout_bf16_kernel(__nv_bfloat16* __restrict__ h, long n, float p, const unsigned long long* seed_ptr,
                                     unsigned long long seed_off) {
+  GTOS_PDL_PROLOGUE();
   const unsigned long long seed = seed_ptr[0] + seed_off;
   const float ks = 1.f / (1.f - p);
   const long stride = (long)gridDim.x * blockDim.x;
@@ -563,7 +576,7 @@ int dropout_bf16(void* h, long n, float p, const void* seed_ptr, unsigned long l
   GTOS_REQUIRE(seed_ptr, "dropout needs a device seed pointer");
   long blocks = (n / 8 + 255) / 256 + 1;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  dropout_bf16_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(h), n, p,
+  GTOS_KLAUNCH(dropout_bf16_kernel, dim3((unsigned)blocks), dim3(256), 0, st, reinterpret_cast<__nv_bfloat16*>(h), n, p,
                                                         reinterpret_cast<const unsigned long long*>(seed_ptr), seed_off);
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
@@ -571,6 +584,7 @@ int dropout_bf16(void* h, long n, float p, const void* seed_ptr, unsigned long l
 
 __global__ void dropout_f32_kernel(const float* __restrict__ x, float* __restrict__ out, long n, float p,
                                    const unsigned long long* seed_ptr, unsigned long long seed_off) {
+  GTOS_PDL_PROLOGUE();
   const unsigned long long seed = seed_ptr[0] + seed_off;
   const float ks = 1.f / (1.f - p);
   const long stride = (long)gridDim.x * blockDim.x;
@@ -594,7 +608,7 @@ int dropout_f32(const float* x, float* out, long n, float p, const void* seed_pt
   GTOS_REQUIRE(p > 0.f && p < 1.f && seed_ptr, "dropout_f32: need 0 < p < 1 and a device seed pointer");
   long blocks = (n / 4 + 255) / 256 + 1;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  dropout_f32_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, out, n, p,
+  GTOS_KLAUNCH(dropout_f32_kernel, dim3((unsigned)blocks), dim3(256), 0, st, x, out, n, p,
                                                        reinterpret_cast<const unsigned long long*>(seed_ptr), seed_off);
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
@@ -603,6 +617,7 @@ int dropout_f32(const float* x, float* out, long n, float p, const void* seed_pt
 // act = post-dropout hidden activation actually fed to fc2 (bf16): zero where relu OR dropout killed it
 __global__ void relu_drop_bwd_kernel(const float* __restrict__ dh_in, const __nv_bfloat16* __restrict__ act,
                                      float* __restrict__ dh_f32, __nv_bfloat16* __restrict__ dh_bf16, long n, float p) {
+  GTOS_PDL_PROLOGUE();
   const float ks = p > 0.f ? 1.f / (1.f - p) : 1.f;
   const long stride = (long)gridDim.x * blockDim.x;
   const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -634,7 +649,7 @@ int relu_drop_bwd(const float* dh_in, const void* act, float* dh_f32, void* dh_b
   if (n == 0) return GTOS_OK;
   long blocks = (n / 4 + 255) / 256 + 1;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  relu_drop_bwd_kernel<<<(unsigned)blocks, 256, 0, st>>>(dh_in, reinterpret_cast<const __nv_bfloat16*>(act), dh_f32,
+  GTOS_KLAUNCH(relu_drop_bwd_kernel, dim3((unsigned)blocks), dim3(256), 0, st, dh_in, reinterpret_cast<const __nv_bfloat16*>(act), dh_f32,
                                                          reinterpret_cast<__nv_bfloat16*>(dh_bf16), n, p);
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
@@ -669,6 +684,7 @@ __global__ void token_nll_fwd_kernel(const float* __restrict__ logits, long ldl,
                                      const float* __restrict__ align, int S, const long long* __restrict__ copy_seq,
                                      const long long* __restrict__ target, int B, long long pad_idx,
                                      float* __restrict__ loss_row, float* __restrict__ stats) {
+  GTOS_PDL_PROLOGUE();
   __shared__ float sh[32];
   const long row = blockIdx.x;
   const int b = (int)(row % B);
@@ -702,6 +718,7 @@ __global__ void token_nll_bwd_kernel(const float* __restrict__ dloss_row, const 
                                      const long long* __restrict__ target, int B, long long pad_idx,
                                      const float* __restrict__ stats, float* __restrict__ dlogits, long lddl,
                                      float* __restrict__ dgate_logits, float* __restrict__ dalign) {
+  GTOS_PDL_PROLOGUE();
   const long row = blockIdx.x;
   const int b = (int)(row % B);
   const long long tgt = target[row];
@@ -731,7 +748,7 @@ int token_nll_fwd(const float* logits, long ldl, int V, const float* gate_logits
                   const long long* copy_seq, const long long* target, long rows, int B, long long pad_idx,
                   float* loss_row, float* stats, cudaStream_t st) {
   if (rows == 0) return GTOS_OK;
-  token_nll_fwd_kernel<<<(unsigned)rows, 256, 0, st>>>(logits, ldl, V, gate_logits, align, S, copy_seq, target, B, pad_idx,
+  GTOS_KLAUNCH(token_nll_fwd_kernel, dim3((unsigned)rows), dim3(256), 0, st, logits, ldl, V, gate_logits, align, S, copy_seq, target, B, pad_idx,
                                                        loss_row, stats);
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
@@ -741,7 +758,7 @@ int token_nll_bwd(const float* dloss_row, const float* logits, long ldl, int V, 
                   const long long* copy_seq, const long long* target, long rows, int B, long long pad_idx,
                   const float* stats, float* dlogits, long lddl, float* dgate_logits, float* dalign, cudaStream_t st) {
   if (rows == 0) return GTOS_OK;
-  token_nll_bwd_kernel<<<(unsigned)rows, 256, 0, st>>>(dloss_row, logits, ldl, V, align, S, copy_seq, target, B, pad_idx,
+  GTOS_KLAUNCH(token_nll_bwd_kernel, dim3((unsigned)rows), dim3(256), 0, st, dloss_row, logits, ldl, V, align, S, copy_seq, target, B, pad_idx,
                                                        stats, dlogits, lddl, dgate_logits, dalign);
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
@@ -753,6 +770,7 @@ int token_nll_bwd(const float* dloss_row, const float* logits, long ldl, int V, 
 // ---------------------------------------------------------------------------------------
 __global__ void bank_gather_kernel(const float* __restrict__ bank, const long long* __restrict__ idx, long P, int D,
                                    float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16) {
+  GTOS_PDL_PROLOGUE();
   const int lane = threadIdx.x & 31;
   const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
@@ -768,6 +786,7 @@ __global__ void bank_gather_kernel(const float* __restrict__ bank, const long lo
 
 __global__ void bank_scatter_add_kernel(const float* __restrict__ d_rel, const long long* __restrict__ idx, long P, int D,
                                         float* __restrict__ d_bank) {
+  GTOS_PDL_PROLOGUE();
   const int lane = threadIdx.x & 31;
   const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
@@ -788,7 +807,7 @@ int bank_gather(const float* bank, const long long* idx, long P, int D, float* o
   if (P == 0) return GTOS_OK;
   long blocks = (P * 32 + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  bank_gather_kernel<<<(unsigned)blocks, 256, 0, st>>>(bank, idx, P, D, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  GTOS_KLAUNCH(bank_gather_kernel, dim3((unsigned)blocks), dim3(256), 0, st, bank, idx, P, D, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16));
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
 }
@@ -799,13 +818,14 @@ int bank_scatter_add(const float* d_rel, const long long* idx, long P, int D, fl
   if (P == 0) return GTOS_OK;
   long blocks = (P * 32 + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  bank_scatter_add_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_rel, idx, P, D, d_bank);
+  GTOS_KLAUNCH(bank_scatter_add_kernel, dim3((unsigned)blocks), dim3(256), 0, st, d_rel, idx, P, D, d_bank);
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
 }
 
 __global__ void rel_dqk_kernel(const __nv_bfloat16* __restrict__ G, RelTiling rt, float* __restrict__ dq,
                                float* __restrict__ dk, long ld) {
+  GTOS_PDL_PROLOGUE();
   // block = (node n, batch b); thread = one 8-column (16-byte) chunk of the 2D-wide G row.
   // chunks inside the d(q+ra) half of a head sum over keys j (-> dq[n]); chunks inside the d(k+rb) half sum
   // over queries i (-> dk[n]).  Every G element is read exactly once, with 16-byte loads.
@@ -847,7 +867,7 @@ int rel_dqk(const void* G, const RelTiling& rt, float* dq, float* dk, long ld, c
   dim3 grid(rt.N, rt.B);
   const int thr = 2 * rt.D / 8;
   GTOS_REQUIRE(thr <= 1024 && rt.hd % 8 == 0, "rel_dqk: unsupported D=%d hd=%d", rt.D, rt.hd);
-  rel_dqk_kernel<<<grid, thr, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(G), rt, dq, dk, ld);
+  GTOS_KLAUNCH(rel_dqk_kernel, dim3(grid), dim3(thr), 0, st, reinterpret_cast<const __nv_bfloat16*>(G), rt, dq, dk, ld);
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
 }
@@ -861,6 +881,7 @@ int rel_dqk(const void* G, const RelTiling& rt, float* dq, float* dk, long ld, c
 // over R bank rows instead of two GEMMs over P pair rows + a [N,N,B,D] fp32 d_relation + an atomic scatter.
 // ---------------------------------------------------------------------------------------
 __global__ void rel_pair_keys_kernel(const long long* __restrict__ idx, RelTiling rt, int R, int* __restrict__ keys) {
+  GTOS_PDL_PROLOGUE();
   const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;     // G row = tile * 128 + r
   if (g >= (long)rt.tiles * 128) return;
   const int tile = (int)(g >> 7), r = (int)(g & 127);
@@ -880,7 +901,7 @@ __global__ void rel_pair_keys_kernel(const long long* __restrict__ idx, RelTilin
 int rel_pair_keys(const long long* idx, const RelTiling& rt, int R, int* keys, cudaStream_t st) {
   const long rows = (long)rt.tiles * 128;
   if (rows == 0) return GTOS_OK;
-  rel_pair_keys_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(idx, rt, R, keys);
+  GTOS_KLAUNCH(rel_pair_keys_kernel, dim3((unsigned)((rows + 255) / 256)), dim3(256), 0, st, idx, rt, R, keys);
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
 }
@@ -898,6 +919,7 @@ __global__ void __launch_bounds__(256, 2) rel_segsum_kernel(const __nv_bfloat16*
                                                             const int* __restrict__ keys, long n, int C,
                                                             __nv_bfloat16* __restrict__ out, long ldo,
                                                             float* __restrict__ spill) {
+  GTOS_PDL_PROLOGUE();
   __shared__ int s_row[8], s_ok[8];
   __shared__ float s_part[8 * NCH * 256];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -1020,6 +1042,7 @@ __global__ void __launch_bounds__(256, 2) rel_segsum_kernel(const __nv_bfloat16*
 // boundary; the first boundary inside a row does the conversion)
 __global__ void rel_segsum_span_kernel(const int* __restrict__ keys, long n, int C, float* __restrict__ spill,
                                        __nv_bfloat16* __restrict__ out, long ldo, int mode) {
+  GTOS_PDL_PROLOGUE();
   const int lane = threadIdx.x & 31;
   const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long b = (warp + 1) * SEG_CH;
@@ -1050,15 +1073,15 @@ int rel_segsum(const void* G, const int* order, const int* keys, long n, int C, 
   const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(G);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_bf16);
   if (warps > 1) {
-    rel_segsum_span_kernel<<<blocks, 256, 0, st>>>(keys, n, C, spill, o, ldo, 0);
+    GTOS_KLAUNCH(rel_segsum_span_kernel, dim3(blocks), dim3(256), 0, st, keys, n, C, spill, o, ldo, 0);
     GTOS_LAUNCH_CHECK();
   }
   const dim3 grid((unsigned)((warps + 7) / 8), (unsigned)((C + SEG_COLS - 1) / SEG_COLS));
-  if (C <= 256) rel_segsum_kernel<1><<<grid, 256, 0, st>>>(g, order, keys, n, C, o, ldo, spill);
-  else rel_segsum_kernel<2><<<grid, 256, 0, st>>>(g, order, keys, n, C, o, ldo, spill);
+  if (C <= 256) GTOS_KLAUNCH(rel_segsum_kernel<1>, dim3(grid), dim3(256), 0, st, g, order, keys, n, C, o, ldo, spill);
+  else GTOS_KLAUNCH(rel_segsum_kernel<2>, dim3(grid), dim3(256), 0, st, g, order, keys, n, C, o, ldo, spill);
   GTOS_LAUNCH_CHECK();
   if (warps > 1) {
-    rel_segsum_span_kernel<<<blocks, 256, 0, st>>>(keys, n, C, spill, o, ldo, 1);
+    GTOS_KLAUNCH(rel_segsum_span_kernel, dim3(blocks), dim3(256), 0, st, keys, n, C, spill, o, ldo, 1);
     GTOS_LAUNCH_CHECK();
   }
   return GTOS_OK;

@@ -788,36 +788,6 @@ int choose_rel_tiling(RelTiling* t, int N, int B, int D, int H) {
   return GTOS_OK;
 }
 
-// launch with programmatic stream serialization (PDL) unless GTOS_PDL=0
-template <class... KArgs, class... Args>
-static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                              int cluster, Args... args) {
-  static const bool pdl = !(getenv("GTOS_PDL") && getenv("GTOS_PDL")[0] == '0');
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[2];
-  int n = 0;
-  if (pdl) {
-    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[n].val.programmaticStreamSerializationAllowed = 1;
-    ++n;
-  }
-  if (cluster > 1) {
-    attr[n].id = cudaLaunchAttributeClusterDimension;
-    attr[n].val.clusterDim.x = cluster;
-    attr[n].val.clusterDim.y = 1;
-    attr[n].val.clusterDim.z = 1;
-    ++n;
-  }
-  cfg.attrs = attr;
-  cfg.numAttrs = n;
-  return cudaLaunchKernelEx(&cfg, kern, args...);
-}
-
 static int g_num_sms = 0;
 static int num_sms() {
   if (g_num_sms == 0) {

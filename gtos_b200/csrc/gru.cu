@@ -14,6 +14,7 @@ __global__ void gru_weight_prep_kernel(const float* __restrict__ w_ih, const flo
                                        const float* __restrict__ b_ih, const float* __restrict__ b_hh, int Kin, int H,
                                        int Kx, int UB, __nv_bfloat16* __restrict__ Wcat, long ldw,
                                        float* __restrict__ bcat) {
+  GTOS_PDL_PROLOGUE();
   const int pr = blockIdx.x;                 // permuted row in [0, 4H)
   const int u = pr / (4 * UB), g = (pr / UB) & 3, cc = pr % UB;
   const int c = u * UB + cc;                 // hidden unit
@@ -41,7 +42,7 @@ int gru_weight_prep(const float* w_ih, const float* w_hh, const float* b_ih, con
                     void* Wcat, long ldw, float* bcat, cudaStream_t st) {
   GTOS_REQUIRE(H % 16 == 0 && Kx % 64 == 0 && Kx >= Kin && ldw >= Kx + H, "gru_weight_prep: bad shape");
   const int UB = (H % 64 == 0) ? 64 : 16;
-  gru_weight_prep_kernel<<<4 * H, 128, 0, st>>>(w_ih, w_hh, b_ih, b_hh, Kin, H, Kx, UB,
+  GTOS_KLAUNCH(gru_weight_prep_kernel, dim3(4 * H), dim3(128), 0, st, w_ih, w_hh, b_ih, b_hh, Kin, H, Kx, UB,
                                                 reinterpret_cast<__nv_bfloat16*>(Wcat), ldw, bcat);
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
@@ -55,6 +56,7 @@ __global__ void __launch_bounds__(256) gru_gate_bwd_kernel(
     const float* __restrict__ h_prev, const long long* __restrict__ lengths, int t, float* __restrict__ dh_prev,
     __nv_bfloat16* __restrict__ dgi, long lddgi, __nv_bfloat16* __restrict__ dgh, long lddgh, float* __restrict__ db_ih,
     float* __restrict__ db_hh, long R, int Hh, int UB, int rows_per_block) {
+  GTOS_PDL_PROLOGUE();
   // lane = 8 consecutive hidden units (16-byte bf16 / 32-byte fp32 accesses), warp = one row at a time, 8 rows of the
   // block in flight; the bias gradients (column sums of the gate gradients) are accumulated in registers, combined
   // across the block's warps in shared memory and flushed with one atomic per (block, column)
@@ -167,7 +169,7 @@ int gru_gate_bwd(const float* dh, const float* dout_t, long lddout, const void* 
   const int UB = (Hh % 64 == 0) ? 64 : 16;
   const int rpb = 64;
   dim3 grid((Hh + 255) / 256, (unsigned)((R + rpb - 1) / rpb));
-  gru_gate_bwd_kernel<<<grid, 256, 0, st>>>(dh, dout_t, lddout, reinterpret_cast<const __nv_bfloat16*>(gates), h_prev,
+  GTOS_KLAUNCH(gru_gate_bwd_kernel, dim3(grid), dim3(256), 0, st, dh, dout_t, lddout, reinterpret_cast<const __nv_bfloat16*>(gates), h_prev,
                                             lengths, t, dh_prev, reinterpret_cast<__nv_bfloat16*>(dgi_bf16), lddgi,
                                             reinterpret_cast<__nv_bfloat16*>(dgh_bf16), lddgh, db_ih, db_hh, R, Hh, UB, rpb);
   GTOS_LAUNCH_CHECK();
@@ -178,6 +180,7 @@ int gru_gate_bwd(const float* dh, const float* dout_t, long lddout, const void* 
 __global__ void embed_gather_kernel(const float* __restrict__ table, const long long* __restrict__ idx, long n, int dim,
                                     float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, long ldb,
                                     float p, const unsigned long long* seed_ptr, unsigned long long seed_off) {
+  GTOS_PDL_PROLOGUE();
   const unsigned long long seed = p > 0.f ? seed_ptr[0] + seed_off : 0ull;
   const float ks = p > 0.f ? 1.f / (1.f - p) : 1.f;
   const long total = n * ldb;
@@ -200,7 +203,7 @@ int embed_gather(const float* table, const long long* idx, long n, int dim, floa
   GTOS_REQUIRE(ldb >= dim, "embed_gather: ldb < dim");
   long blocks = (n * ldb + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  embed_gather_kernel<<<(unsigned)blocks, 256, 0, st>>>(table, idx, n, dim, out_f32,
+  GTOS_KLAUNCH(embed_gather_kernel, dim3((unsigned)blocks), dim3(256), 0, st, table, idx, n, dim, out_f32,
                                                         reinterpret_cast<__nv_bfloat16*>(out_bf16), ldb, p_drop,
                                                         reinterpret_cast<const unsigned long long*>(seed_ptr), seed_off);
   GTOS_LAUNCH_CHECK();
@@ -210,6 +213,7 @@ int embed_gather(const float* table, const long long* idx, long n, int dim, floa
 __global__ void embed_scatter_kernel(const float* __restrict__ dx, long lddx, const long long* __restrict__ idx, long n,
                                      int dim, float* __restrict__ dtable, float p, const unsigned long long* seed_ptr,
                                      unsigned long long seed_off) {
+  GTOS_PDL_PROLOGUE();
   const unsigned long long seed = p > 0.f ? seed_ptr[0] + seed_off : 0ull;
   const float ks = p > 0.f ? 1.f / (1.f - p) : 1.f;
   const long total = n * dim;
@@ -227,7 +231,7 @@ int embed_scatter_add(const float* dx, const long long* idx, long n, int dim, fl
   if (n == 0) return GTOS_OK;
   long blocks = (n * dim + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  embed_scatter_kernel<<<(unsigned)blocks, 256, 0, st>>>(dx, dim, idx, n, dim, dtable, p_drop,
+  GTOS_KLAUNCH(embed_scatter_kernel, dim3((unsigned)blocks), dim3(256), 0, st, dx, dim, idx, n, dim, dtable, p_drop,
                                                          reinterpret_cast<const unsigned long long*>(seed_ptr), seed_off);
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;

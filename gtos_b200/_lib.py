@@ -58,6 +58,7 @@ SIGNATURES = {
     "gtos_attn_bwd": (i32, [C.POINTER(AttnDesc), vp]),
     "gtos_add_ln_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, f32, vp, u64, vp]),
     "gtos_add_ln_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, f32, vp, u64, vp]),
+    "gtos_ln_param_grad": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, vp]),
     "gtos_colsum": (i32, [vp, i64, vp, i64, i32, vp]),
     "gtos_colsum_bf16": (i32, [vp, i64, vp, i64, i32, vp]),
     "gtos_dropout_bf16": (i32, [vp, i64, f32, vp, u64, vp]),

@@ -235,6 +235,10 @@ int gtos_add_ln_bwd(const float* dy, const float* z, const float* mean, const fl
   return add_ln_bwd(dy, z, mean, rstd, gamma, dres, dx, dx_bf16, dgamma, dbeta, rows, D, p_drop, seed_ptr, seed_off,
                     S(stream));
 }
+int gtos_ln_param_grad(const float* dy, const float* z, const float* mean, const float* rstd, float* dgamma, float* dbeta,
+                       int64_t rows, int32_t D, void* stream) {
+  return ln_param_grad(dy, z, mean, rstd, dgamma, dbeta, rows, D, S(stream));
+}
 int gtos_colsum(const float* x, int64_t ld, float* out, int64_t rows, int32_t cols, void* stream) {
   return colsum(x, ld, out, rows, cols, S(stream));
 }

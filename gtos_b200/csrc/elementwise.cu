@@ -451,45 +451,53 @@ __global__ void __launch_bounds__(128) add_ln_bwd_vec_kernel(
   }
 }
 
+// dgamma / dbeta over all rows (one thread per column, rows_per_block rows per CTA, atomics into the zeroed outputs).  A
+// separate entry point so the host can run it on a second stream: nothing on the critical path of a backward pass reads it.
+int ln_param_grad(const float* dy, const float* z, const float* mean, const float* rstd, float* dgamma, float* dbeta,
+                  long rows, int D, cudaStream_t st) {
+  GTOS_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, sizeof(float) * D, st));
+  GTOS_CHECK_CUDA(cudaMemsetAsync(dbeta, 0, sizeof(float) * D, st));
+  if (rows == 0) return GTOS_OK;
+  const int rpb = 32;   // thread per column: 4 x more threads in flight than a float4-per-thread variant, which measured slower
+  dim3 grid((D + 127) / 128, (unsigned)((rows + rpb - 1) / rpb));
+  GTOS_KLAUNCH(ln_param_grad_kernel, dim3(grid), dim3(128), 0, st, dy, z, mean, rstd, dgamma, dbeta, rows, D, rpb);
+  GTOS_LAUNCH_CHECK();
+  return GTOS_OK;
+}
+
+// dgamma == nullptr: input gradients only (the caller computes the parameter gradients with ln_param_grad)
 int add_ln_bwd(const float* dy, const float* z, const float* mean, const float* rstd, const float* gamma, float* dres,
                float* dx, void* dx_bf16, float* dgamma, float* dbeta, long rows, int D, float p_drop,
                const void* seed_ptr, unsigned long long seed_off, cudaStream_t st) {
   GTOS_REQUIRE(D <= 32 * LN_MAX_PER_LANE, "LayerNorm width %d unsupported", D);
-  GTOS_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, sizeof(float) * D, st));
-  GTOS_CHECK_CUDA(cudaMemsetAsync(dbeta, 0, sizeof(float) * D, st));
-  if (rows == 0) return GTOS_OK;
-  if (D % 128 == 0 && al16(dy) && al16(z) && al16(gamma) && al16(dres) && al16(dx) && al16(dx_bf16)) {
-    const unsigned blocks = (unsigned)((rows + 3) / 4);
-    __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
-    const unsigned long long* sp = reinterpret_cast<const unsigned long long*>(seed_ptr);
+  GTOS_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "add_ln_bwd: dgamma and dbeta go together");
+  if (rows > 0) {
+    if (D % 128 == 0 && al16(dy) && al16(z) && al16(gamma) && al16(dres) && al16(dx) && al16(dx_bf16)) {
+      const unsigned blocks = (unsigned)((rows + 3) / 4);
+      __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
+      const unsigned long long* sp = reinterpret_cast<const unsigned long long*>(seed_ptr);
 #define GTOS_LN_BWD(NV) GTOS_KLAUNCH(add_ln_bwd_vec_kernel<NV>, dim3(blocks), dim3(128), 0, st, dy, z, mean, rstd, gamma, dres, dx, xb, rows, p_drop, sp, seed_off)
-    switch (D / 128) {
-      case 1: GTOS_LN_BWD(1); break;
-      case 2: GTOS_LN_BWD(2); break;
-      case 3: GTOS_LN_BWD(3); break;
-      case 4: GTOS_LN_BWD(4); break;
-      case 5: GTOS_LN_BWD(5); break;
-      case 6: GTOS_LN_BWD(6); break;
-      case 7: GTOS_LN_BWD(7); break;
-      default: GTOS_LN_BWD(8); break;
-    }
+      switch (D / 128) {
+        case 1: GTOS_LN_BWD(1); break;
+        case 2: GTOS_LN_BWD(2); break;
+        case 3: GTOS_LN_BWD(3); break;
+        case 4: GTOS_LN_BWD(4); break;
+        case 5: GTOS_LN_BWD(5); break;
+        case 6: GTOS_LN_BWD(6); break;
+        case 7: GTOS_LN_BWD(7); break;
+        default: GTOS_LN_BWD(8); break;
+      }
 #undef GTOS_LN_BWD
-    GTOS_LAUNCH_CHECK();
-    const int rpb = 32;   // thread per column: 4 x more threads in flight than a float4-per-thread variant, which measured slower
-    dim3 grid((D + 127) / 128, (unsigned)((rows + rpb - 1) / rpb));
-    GTOS_KLAUNCH(ln_param_grad_kernel, dim3(grid), dim3(128), 0, st, dy, z, mean, rstd, dgamma, dbeta, rows, D, rpb);
-    GTOS_LAUNCH_CHECK();
-    return GTOS_OK;
+      GTOS_LAUNCH_CHECK();
+    } else {
+      const int wpb = 4;
+      GTOS_KLAUNCH(add_ln_bwd_kernel, dim3((unsigned)((rows + wpb - 1) / wpb)), dim3(wpb * 32), 0, st,
+                   dy, z, mean, rstd, gamma, dres, dx, reinterpret_cast<__nv_bfloat16*>(dx_bf16), rows, D, p_drop,
+                   reinterpret_cast<const unsigned long long*>(seed_ptr), seed_off);
+      GTOS_LAUNCH_CHECK();
+    }
   }
-  const int wpb = 4;
-  GTOS_KLAUNCH(add_ln_bwd_kernel, dim3((unsigned)((rows + wpb - 1) / wpb)), dim3(wpb * 32), 0, st, 
-      dy, z, mean, rstd, gamma, dres, dx, reinterpret_cast<__nv_bfloat16*>(dx_bf16), rows, D, p_drop,
-      reinterpret_cast<const unsigned long long*>(seed_ptr), seed_off);
-  GTOS_LAUNCH_CHECK();
-  const int rpb = 32;
-  dim3 grid((D + 127) / 128, (unsigned)((rows + rpb - 1) / rpb));
-  GTOS_KLAUNCH(ln_param_grad_kernel, dim3(grid), dim3(128), 0, st, dy, z, mean, rstd, dgamma, dbeta, rows, D, rpb);
-  GTOS_LAUNCH_CHECK();
+  if (dgamma) return ln_param_grad(dy, z, mean, rstd, dgamma, dbeta, rows, D, st);
   return GTOS_OK;
 }
 

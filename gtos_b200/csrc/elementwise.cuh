@@ -15,6 +15,8 @@ int add_ln_fwd(const float* x, const float* res, const float* gamma, const float
 int add_ln_bwd(const float* dy, const float* z, const float* mean, const float* rstd, const float* gamma, float* dres,
                float* dx, void* dx_bf16, float* dgamma, float* dbeta, long rows, int D, float p_drop,
                const void* seed_ptr, unsigned long long seed_off, cudaStream_t st);
+int ln_param_grad(const float* dy, const float* z, const float* mean, const float* rstd, float* dgamma, float* dbeta,
+                  long rows, int D, cudaStream_t st);
 int colsum(const float* x, long ld, float* out, long rows, int cols, cudaStream_t st);
 int colsum_bf16(const void* x, long ld, float* out, long rows, int cols, cudaStream_t st);
 int dropout_bf16(void* h, long n, float p, const void* seed_ptr, unsigned long long seed_off, cudaStream_t st);

@@ -45,6 +45,7 @@ class HotPath(nn.Module):
                                        with_external=True)
         self.decoder = DecodeLayer(vocabs, c.inference_layers, c.embed_dim, c.ff_embed_dim, c.num_heads,
                                    c.concept_dim, c.rel_dim, c.dropout)
+        self._prep_plan = ops.WeightPrepPlan()
         self.banked_relation = True      # False: dense `relation_bank[idx]` exactly as generator.py:79 builds it
         self.probe_generator = nn.Linear(c.embed_dim, c.embed_dim)
         nn.init.normal_(self.probe_generator.weight, std=0.02)
@@ -66,6 +67,10 @@ class HotPath(nn.Module):
 
     def forward(self, batch):
         """generator.py:169-182 -> scalar loss."""
+        with self._prep_plan.step():             # weight operand copies issued ahead, beside the RelationEncoder
+            return self._forward(batch)
+
+    def _forward(self, batch):
         concept_repr, concept_mask, probe = self.encode(batch)
         token_repr = batch["token_repr"]
         attn_mask = batch["causal_mask"]

@@ -51,10 +51,12 @@ def as_u8(mask):
 # run on a second stream; `join()` before the Function returns makes the caller's stream wait for it, so nothing
 # escapes a Function unfinished (under CUDA-graph capture these are plain fork/join edges of the graph).
 _side_streams = {}
-# Measured on config 2 (bench.py, CUDA-graph step): 10.12 ms with, 10.34 ms without - inside run-to-run noise, because
-# every tcgen05 GEMM CTA owns its SM (~200 KB of shared memory), so two GEMMs interleave rather than overlap.  Off by
-# default (GTOS_SIDE_STREAM=1 enables it); the GPU tests pass in both modes.
-_side_enabled = os.environ.get("GTOS_SIDE_STREAM", "0") == "1"
+# Measured on config 2 (bench.py, CUDA-graph step, B200): 9.61 ms with, 9.78 ms without (earlier build: 10.12 vs 10.34).
+# Every tcgen05 GEMM CTA owns its SM (~200 KB of shared memory), so two GEMMs interleave rather than overlap; the gain
+# comes from the SMs a 84-120-tile GEMM leaves idle.  (Capping the TMA ring at 2 stages so that two CTAs fit one SM made
+# the step 0.7 ms SLOWER - the main loop is ingest-latency bound.)  GTOS_SIDE_STREAM=0 disables it; the GPU tests pass
+# in both modes.
+_side_enabled = os.environ.get("GTOS_SIDE_STREAM", "1") == "1"
 
 
 # The two directions of a bidirectional GRU layer are independent chains of launches whose tile counts do not fill
@@ -66,11 +68,11 @@ _rel_streams = os.environ.get("GTOS_REL_STREAMS", "1") == "1"
 
 
 class _Fork:
-    def __init__(self, enabled=None):
+    def __init__(self, enabled=None, which=0):
         self.main = torch.cuda.current_stream()
         self.side = None
         if _side_enabled if enabled is None else enabled:
-            key = self.main.device.index
+            key = (self.main.device.index, which)
             if key not in _side_streams:
                 _side_streams[key] = torch.cuda.Stream(device=self.main.device)
             self.side = _side_streams[key]
@@ -97,10 +99,10 @@ class _Fork:
             self.used = False
 
 
-def fork(enabled=None):
+def fork(enabled=None, which=0):
     """with fork() as f: <launches on the side stream> ... f.join() before the results are handed on.
     Outputs written inside the block must be allocated BEFORE it (on the caller's stream)."""
-    return _Fork(enabled)
+    return _Fork(enabled, which)
 
 
 # ---- dropout RNG: one device-resident 64-bit seed + a per-call-site offset -----------------
@@ -154,16 +156,118 @@ def cast_colsum(x2d):
     return out, sums
 
 
-def weight_prep(W, want_b=True, want_t=True, rel_heads=0):
-    """W fp32 [R,C] -> (Wb bf16 [R, up8(C)], Wt bf16 [C, up8(R)])."""
-    _need_cuda(W)
-    W = W.detach().contiguous()
+def _weight_prep_launch(W, Wb, Wt, rel_heads):
     R, Cc = W.shape
-    Wb = torch.empty(R, _up8(Cc), dtype=torch.bfloat16, device=W.device) if want_b else None
-    Wt = torch.empty(Cc, _up8(R), dtype=torch.bfloat16, device=W.device) if want_t else None
     _lib.check(_lib.load().gtos_weight_prep(_p(W), R, Cc, _p(Wb), _up8(Cc), _p(Wt), _up8(R), rel_heads, _st()),
                "weight_prep")
+
+
+def weight_prep(W, want_b=True, want_t=True, rel_heads=0, plan=True):
+    """W fp32 [R,C] -> (Wb bf16 [R, up8(C)], Wt bf16 [C, up8(R)]).  Inside a WeightPrepPlan.step() block the copies
+    may already have been made ahead of time on another stream (plan=False: always cast here, now)."""
+    _need_cuda(W)
+    Wd = W.detach()
+    if plan and _prep_active is not None:
+        key = (Wd.data_ptr(), tuple(Wd.shape), rel_heads)
+        hit = _prep_active.lookup(key, want_b, want_t)
+        if hit is not None:
+            return hit
+        _prep_active.note(key, W, want_b, want_t, rel_heads)
+    Wd = Wd.contiguous()
+    R, Cc = Wd.shape
+    Wb = torch.empty(R, _up8(Cc), dtype=torch.bfloat16, device=W.device) if want_b else None
+    Wt = torch.empty(Cc, _up8(R), dtype=torch.bfloat16, device=W.device) if want_t else None
+    _weight_prep_launch(Wd, Wb, Wt, rel_heads)
     return Wb, Wt
+
+
+_prep_active = None
+_prep_ahead = os.environ.get("GTOS_PREP_AHEAD", "1") == "1"
+
+
+class WeightPrepPlan:
+    """The bf16 operand copies of the weights (cast, transpose, relation-weight row permutation: ~60 small launches per
+    step at config 2) depend on nothing but the parameters, so they need not sit in the dependent chain of the forward
+    pass.  The first `with plan.step():` block records which copies the model asks for; every later block issues all of
+    them up front on a third stream - beside the RelationEncoder's GRU steps, which leave room on every SM for these
+    4 KB CTAs - and weight_prep() hands them out, joining that stream on first use.  The copies are made from the
+    parameters' current values at the start of each block and dropped at its end, so an optimizer step between blocks is
+    always seen.  GTOS_PREP_AHEAD=0 turns the plan into a no-op."""
+
+    def __init__(self):
+        self.items = None          # [(parameter, want_b, want_t, rel_heads)]
+        self._log = None
+        self._ready = None
+        self._fork = None
+
+    # -- used by weight_prep --
+    def lookup(self, key, want_b, want_t):
+        if self._ready is None:
+            return None
+        hit = self._ready.get(key)
+        if hit is None or (want_b and hit[0] is None) or (want_t and hit[1] is None):
+            return None
+        if self._fork is not None:
+            self._fork.join()
+            self._fork = None
+        return (hit[0] if want_b else None), (hit[1] if want_t else None)
+
+    def note(self, key, W, want_b, want_t, rel_heads):
+        if self._log is not None:
+            prev = self._log.get(key)
+            if prev is not None:
+                want_b, want_t = want_b or prev[1], want_t or prev[2]
+            self._log[key] = (W, want_b, want_t, rel_heads)
+
+    def step(self):
+        return _PrepStep(self)
+
+
+class _PrepStep:
+    def __init__(self, plan):
+        self.plan = plan
+
+    def __enter__(self):
+        global _prep_active
+        pl = self.plan
+        if not _prep_ahead or _prep_active is not None:
+            self.plan = None
+            return self
+        _prep_active = pl
+        if pl.items is None:
+            pl._log = {}
+            return self
+        outs = []
+        for W, want_b, want_t, rel_heads in pl.items:                  # allocate on the caller's stream
+            Wd = W.detach()
+            R, Cc = Wd.shape
+            outs.append((Wd, torch.empty(R, _up8(Cc), dtype=torch.bfloat16, device=W.device) if want_b else None,
+                         torch.empty(Cc, _up8(R), dtype=torch.bfloat16, device=W.device) if want_t else None, rel_heads))
+        pl._ready = {}
+        with fork(True, which=1) as f:
+            for Wd, Wb, Wt, rel_heads in outs:
+                if not Wd.is_contiguous():
+                    continue
+                _weight_prep_launch(Wd, Wb, Wt, rel_heads)
+                pl._ready[(Wd.data_ptr(), tuple(Wd.shape), rel_heads)] = (Wb, Wt)
+        pl._fork = f
+        return self
+
+    def __exit__(self, *exc):
+        global _prep_active
+        pl = self.plan
+        if pl is None:
+            return False
+        if pl._log is not None:
+            if exc[0] is None:
+                pl.items = list(pl._log.values())
+            pl._log = None
+        if pl._fork is not None:                                       # nothing asked for the copies: still rejoin
+            pl._fork.join()
+            pl._fork = None
+        pl._ready = None
+        _prep_active = None
+        return False
 
 
 def gemm_tn(A, B, N, bias=None, f32=True, bf16=False, relu=False, out=None, accumulate=False, K=None, b_off=0,
@@ -271,8 +375,12 @@ class AddLayerNormFn(torch.autograd.Function):
         dx = torch.empty_like(z) if p > 0 else None
         dgamma = torch.empty(D, dtype=torch.float32, device=z.device)
         dbeta = torch.empty(D, dtype=torch.float32, device=z.device)
+        with fork() as f_par:                       # dgamma / dbeta: nothing downstream in this backward pass reads them
+            _lib.check(_lib.load().gtos_ln_param_grad(_p(dy2), _p(z), _p(mean), _p(rstd), _p(dgamma), _p(dbeta), rows, D,
+                                                      _st()), "ln_param_grad")
         _lib.check(_lib.load().gtos_add_ln_bwd(_p(dy2), _p(z), _p(mean), _p(rstd), _p(gamma), _p(dres), _p(dx), None,
-                                               _p(dgamma), _p(dbeta), rows, D, p, _p(seed), off, _st()), "add_ln_bwd")
+                                               None, None, rows, D, p, _p(seed), off, _st()), "add_ln_bwd")
+        f_par.join()
         dres = dres.view(shape)
         dxo = dres if dx is None else dx.view(shape)
         return dxo, (dres if has_res else None), dgamma, dbeta, None
@@ -361,10 +469,13 @@ class RelAttnFn(torch.autograd.Function):
         Wob, Wot = weight_prep(W_out)
         # q,k feed only the fused relation kernels (staged there by TMA as bf16); v feeds the attention core
         _, qkb = gemm_tn(xb2, Wib, 2 * D, bias=b_in[:2 * D], f32=False, bf16=True)  # [NB, 2D] bf16
-        vproj, _ = gemm_tn(xb2, Wib, D, bias=b_in[2 * D:], K=D, b_off=2 * D * Wib.stride(0))   # [NB, D] fp32
+        vproj = torch.empty(NB, D, dtype=torch.float32, device=dev)
+        with fork() as f_v:                         # v is first read by the attention core, after the score kernel
+            gemm_tn(xb2, Wib, D, bias=b_in[2 * D:], K=D, b_off=2 * D * Wib.stride(0), out=vproj)   # [NB, D] fp32
         scores = torch.empty(B, H, N, N, dtype=torch.float32, device=dev)          # [b,h,j,i]
         _lib.check(lib.gtos_rel_score(_p(relb), _p(Wperm), qkb.data_ptr(), qkb.data_ptr() + 2 * D, 2 * D, _p(scores),
                                       N, B, D, H, _st()), "rel_score")
+        f_v.join()
         probs = torch.empty(B, H, N, N, dtype=torch.float32, device=dev)           # [b,h,i,j]
         wts = torch.empty(B, H, N, N, dtype=torch.float32, device=dev) if need_weights else None
         att = torch.empty(NB, D, dtype=torch.float32, device=dev)
@@ -606,12 +717,17 @@ class MHAFn(torch.autograd.Function):
             qp, kp, vp, ldq, ldk = proj.data_ptr(), proj.data_ptr() + 4 * D, proj.data_ptr() + 8 * D, 3 * D, 3 * D
             keep = (proj,)
         else:
-            kb2 = (kb if kb is not None else cast_bf16(key.contiguous().view(S * B, D))).view(S * B, _up8(D))
-            pq, _ = gemm_tn(qb2, Wib, D, bias=b_in[:D], M=T * B)                    # rows 0..D of W_in
+            key2 = key.contiguous().view(S * B, D)
+            kb2 = kb.view(S * B, _up8(D)) if kb is not None else torch.empty(S * B, _up8(D), dtype=torch.bfloat16, device=dev)
             pkv = torch.empty(S * B, 2 * D, dtype=torch.float32, device=dev)
-            _lib.check(lib.gtos_gemm_tn(_p(kb2), kb2.stride(0), Wib.data_ptr() + 2 * D * Wib.stride(0), Wib.stride(0),
-                                        b_in.data_ptr() + 4 * D, _p(pkv), 2 * D, None, 0, S * B, 2 * D, _up8(D), 0, 0,
-                                        _st()), "gemm_tn(kv)")
+            with fork() as f_kv:                    # the memory side (cast + K/V projection) runs beside the query projection
+                if kb is None:
+                    _lib.check(lib.gtos_cast_bf16(_p(key2), D, _p(kb2), _up8(D), S * B, D, _st()), "cast_bf16")
+                _lib.check(lib.gtos_gemm_tn(_p(kb2), kb2.stride(0), Wib.data_ptr() + 2 * D * Wib.stride(0), Wib.stride(0),
+                                            b_in.data_ptr() + 4 * D, _p(pkv), 2 * D, None, 0, S * B, 2 * D, _up8(D), 0, 0,
+                                            _st()), "gemm_tn(kv)")
+            pq, _ = gemm_tn(qb2, Wib, D, bias=b_in[:D], M=T * B)                    # rows 0..D of W_in
+            f_kv.join()
             qp, kp, vp, ldq, ldk = pq.data_ptr(), pkv.data_ptr(), pkv.data_ptr() + 4 * D, D, 2 * D
             keep = (pq, pkv)
         probs = torch.empty(B, H, T, S, dtype=torch.float32, device=dev)
@@ -745,8 +861,8 @@ class GRUBankFn(torch.autograd.Function):
             per_dir = []
             for d in range(2):                                                     # operands of both directions first
                 w_ih, w_hh, b_ih, b_hh = weights[(l * 2 + d) * 4:(l * 2 + d) * 4 + 4]
-                _, Wih_t = weight_prep(w_ih, want_b=False)                         # for dx in backward
-                _, Whh_t = weight_prep(w_hh, want_b=False)                         # for dh in backward
+                _, Wih_t = weight_prep(w_ih, want_b=False, plan=False)                         # for dx in backward
+                _, Whh_t = weight_prep(w_hh, want_b=False, plan=False)                         # for dh in backward
                 Wcat = torch.empty(4 * Hh, ldw, dtype=torch.bfloat16, device=dev)
                 bcat = torch.empty(4 * Hh, dtype=torch.float32, device=dev)
                 _lib.check(lib.gtos_gru_weight_prep(_p(w_ih.detach()), _p(w_hh.detach()), _p(b_ih.detach()),

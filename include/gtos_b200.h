@@ -143,6 +143,11 @@ int gtos_add_ln_fwd(const float* x, const float* res, const float* gamma, const 
 int gtos_add_ln_bwd(const float* dy, const float* z, const float* mean, const float* rstd, const float* gamma,
                     float* dres, float* dx, void* dx_bf16, float* dgamma, float* dbeta, int64_t rows, int32_t D,
                     float p_drop, const void* seed_ptr, uint64_t seed_off, void* stream);
+/* LayerNorm parameter gradients alone (the weight / bias gradients torch's LayerNorm backward returns for
+ * graph_transformer.py:58,65): dgamma[d] = sum_rows dy * (z - mean) * rstd, dbeta[d] = sum_rows dy.  gtos_add_ln_bwd
+ * with dgamma = dbeta = NULL computes the input gradients only, so the host can run this on a second stream. */
+int gtos_ln_param_grad(const float* dy, const float* z, const float* mean, const float* rstd, float* dgamma, float* dbeta,
+                       int64_t rows, int32_t D, void* stream);
 /* out[n] = sum_m x[m,n]  (bias gradients) */
 int gtos_colsum(const float* x, int64_t ld, float* out, int64_t rows, int32_t cols, void* stream);
 int gtos_colsum_bf16(const void* x, int64_t ld, float* out, int64_t rows, int32_t cols, void* stream);

@@ -69,16 +69,21 @@ __global__ void cast_colsum_kernel(const float* __restrict__ src, long lds, __nv
   }
 }
 
-// 4 columns per thread (16-byte loads, 8-byte stores), 4 rows in flight
+// 4 columns per thread (16-byte loads, 8-byte stores), 4 rows in flight per thread; blockDim.y row groups per CTA whose
+// partial sums meet in shared memory, so a CTA issues ONE atomic per column whatever its depth (more CTAs instead -
+// 8 rows each - measured 0.4 ms per step SLOWER: 480 atomics per column address serialise in L2)
 __global__ void cast_colsum_vec4_kernel(const float* __restrict__ src, long lds, __nv_bfloat16* __restrict__ dst, long ldd,
                                         float* __restrict__ sums, long rows, int cols, int rows_per_block) {
   GTOS_PDL_PROLOGUE();
+  __shared__ float4 red[3][128];
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (c >= ldd) return;
-  const long r0 = (long)blockIdx.y * rows_per_block;
-  const long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  const int ty = threadIdx.y, ny = blockDim.y;
+  const int rpg = rows_per_block / ny;                       // rows per row group
+  const long rb = (long)blockIdx.y * rows_per_block;
+  const long r0 = rb + (long)ty * rpg;
+  const long r1 = r0 + rpg < rows ? r0 + rpg : rows;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   if (c < cols) {     // cols % 4 == 0: a thread's 4 columns are all inside or all outside
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     long r = r0;
     for (; r + 4 <= r1; r += 4) {
       float4 v[4];
@@ -95,9 +100,20 @@ __global__ void cast_colsum_vec4_kernel(const float* __restrict__ src, long lds,
       *reinterpret_cast<uint2*>(dst + r * ldd + c) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
-    atomicAdd(&sums[c], s.x); atomicAdd(&sums[c + 1], s.y); atomicAdd(&sums[c + 2], s.z); atomicAdd(&sums[c + 3], s.w);
-  } else {
+  } else if (c < ldd) {
     for (long r = r0; r < r1; ++r) *reinterpret_cast<uint2*>(dst + r * ldd + c) = make_uint2(0u, 0u);
+  }
+  if (ny > 1) {
+    if (ty > 0) red[ty - 1][threadIdx.x] = s;
+    __syncthreads();
+    if (ty == 0)
+      for (int g = 0; g < ny - 1; ++g) {
+        const float4 o = red[g][threadIdx.x];
+        s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+      }
+  }
+  if (ty == 0 && c < cols) {
+    atomicAdd(&sums[c], s.x); atomicAdd(&sums[c + 1], s.y); atomicAdd(&sums[c + 2], s.z); atomicAdd(&sums[c + 3], s.w);
   }
 }
 
@@ -108,8 +124,9 @@ int cast_colsum(const float* src, long lds, void* dst, long ldd, float* sums, lo
   if (cols % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
     const int rpb = 32;
+    static const int ny = getenv("GTOS_CC_NY") ? atoi(getenv("GTOS_CC_NY")) : 4;   // 1, 2 or 4 row groups per CTA
     dim3 grid((unsigned)((ldd / 4 + 127) / 128), (unsigned)((rows + rpb - 1) / rpb));
-    GTOS_KLAUNCH(cast_colsum_vec4_kernel, dim3(grid), dim3(128), 0, st, src, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldd, sums, rows, cols, rpb);
+    GTOS_KLAUNCH(cast_colsum_vec4_kernel, dim3(grid), dim3(128, ny), 0, st, src, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldd, sums, rows, cols, rpb);
     GTOS_LAUNCH_CHECK();
     return GTOS_OK;
   }
@@ -848,16 +865,28 @@ __global__ void rel_dqk_kernel(const __nv_bfloat16* __restrict__ G, RelTiling rt
   for (int t = 0; t < 8; ++t) acc[t] = 0.f;
   const int nb = is_x ? n / rt.bi : n / rt.bj;       // block index of the fixed coordinate
   const int nr = is_x ? n % rt.bi : n % rt.bj;
+  // G row of (running coordinate o = ob * blk + oo):  base + ob * blk_stride + oo * in_stride.  Same loop for both
+  // halves (lanes of one warp hold both kinds of chunk) and no division inside it: the first version spent most of
+  // its issue slots on four integer divisions per 16-byte load.
+  //   fixed query i = n, running key j:   row = ((b * nj_blk + jb) * ni_blk + nb) * 128 + jj * bi + nr
+  //   fixed key j = n, running query i:   row = ((b * nj_blk + nb) * ni_blk + ib) * 128 + nr * bi + ii
+  const int blk = is_x ? rt.bj : rt.bi;
+  const long in_stride = is_x ? rt.bi : 1;
+  const long blk_stride = is_x ? (long)rt.ni_blk * 128 : 128;
+  const long base = is_x ? ((long)b * rt.nj_blk * rt.ni_blk + nb) * 128 + nr
+                         : (((long)b * rt.nj_blk + nb) * rt.ni_blk) * 128 + (long)nr * rt.bi;
+  const long wrap = blk_stride - (long)blk * in_stride;
+  const __nv_bfloat16* gp = G + col;
+  long row = base;
+  int oo = 0;
+#pragma unroll 4
   for (int o = 0; o < rt.N; ++o) {
-    long row;
-    if (is_x) {                                     // fixed query i = n, running key j = o
-      const int jb = o / rt.bj, jj = o % rt.bj;
-      row = (((long)b * rt.nj_blk + jb) * rt.ni_blk + nb) * 128 + jj * rt.bi + nr;
-    } else {                                        // fixed key j = n, running query i = o
-      const int ib = o / rt.bi, ii = o % rt.bi;
-      row = (((long)b * rt.nj_blk + nb) * rt.ni_blk + ib) * 128 + nr * rt.bi + ii;
+    const uint4 v = *reinterpret_cast<const uint4*>(gp + row * (2L * D));
+    row += in_stride;
+    if (++oo == blk) {
+      oo = 0;
+      row += wrap;
     }
-    const uint4 v = *reinterpret_cast<const uint4*>(G + row * (2L * D) + col);
     const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&v);
 #pragma unroll
     for (int t = 0; t < 4; ++t) {

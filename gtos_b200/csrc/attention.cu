@@ -26,6 +26,9 @@ __device__ int g_attn_trace_on = 0;
 
 static constexpr int AT_THREADS = 256;
 static constexpr int AT_WARPS = 8;
+// 64 registers per thread: four CTAs per SM, so the 512 (batch, head) CTAs of this path are resident in ONE wave.  The
+// compiler otherwise takes 128 registers (ncu: occupancy limit 2 CTAs per SM, 23 % of the warp slots active, two waves).
+static constexpr int AT_MIN_CTAS = 4;
 static constexpr int AT_ROWS_MAX = 64;  // query (or key) rows per CTA
 static constexpr int AT_DC = 64;        // feature chunk
 
@@ -172,7 +175,7 @@ __device__ __forceinline__ bool is_masked(const AttnArgs& a, int b, int t, int j
 // ============================================================================================
 // forward
 // ============================================================================================
-__global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnArgs a, const int rows) {
+__global__ void __launch_bounds__(AT_THREADS, AT_MIN_CTAS) attn_fwd_kernel(const AttnArgs a, const int rows) {
   GTOS_PDL_PROLOGUE();
   extern __shared__ __align__(128) uint8_t smem_u8[];
   const int dc = a.hd < AT_DC ? a.hd : AT_DC;
@@ -297,7 +300,7 @@ int attn_fwd(const AttnArgs& a, cudaStream_t st) {
 // ============================================================================================
 // backward, query side: dS (and dq in decoder mode)
 // ============================================================================================
-__global__ void __launch_bounds__(AT_THREADS) attn_bwd_q_kernel(const AttnBwdArgs g, const int rows) {
+__global__ void __launch_bounds__(AT_THREADS, AT_MIN_CTAS) attn_bwd_q_kernel(const AttnBwdArgs g, const int rows) {
   GTOS_PDL_PROLOGUE();
   extern __shared__ __align__(128) uint8_t smem_u8[];
   const AttnArgs& a = g.f;
@@ -382,7 +385,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_q_kernel(const AttnBwdArg
 // ============================================================================================
 // backward, key side: dV = Pd^T dO ; dK = scale * dS^T q      (CTA = `rows` key rows of one (b,h))
 // ============================================================================================
-__global__ void __launch_bounds__(AT_THREADS) attn_bwd_kv_kernel(const AttnBwdArgs g, const int rows) {
+__global__ void __launch_bounds__(AT_THREADS, AT_MIN_CTAS) attn_bwd_kv_kernel(const AttnBwdArgs g, const int rows) {
   GTOS_PDL_PROLOGUE();
   extern __shared__ __align__(128) uint8_t smem_u8[];
   const AttnArgs& a = g.f;

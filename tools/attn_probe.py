@@ -75,6 +75,12 @@ def main():
                 d.dq, d.lddq, d.dk, d.lddk = dq.data_ptr(), D, dkv.data_ptr(), 2 * D
             _lib.check(lib.gtos_attn_bwd(ctypes.byref(d), torch.cuda.current_stream().cuda_stream))
 
+        once = os.environ.get("ATTN_PROBE_ONCE")       # "<shape substring>": one fwd + bwd of that shape (for ncu)
+        if once is not None:
+            if once in name:
+                fwd(); bwd()
+                torch.cuda.synchronize()
+            continue
         tf, tb = timeit(fwd), timeit(bwd)
         lib.gtos_debug_attn_trace(ctypes.cast(buf, ctypes.c_void_p), 1)
         fwd(); bwd()

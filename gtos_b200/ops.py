@@ -156,6 +156,33 @@ def cast_colsum(x2d):
     return out, sums
 
 
+class _NoFork:
+    def join(self):
+        pass
+
+
+stats = {"grad_operand_tagged": 0, "grad_operand_cast": 0}      # which path incoming gradients took (tests, tools)
+
+
+def grad_operand(dy, dy2):
+    """(bf16 operand copy, fp32 column sums, fork to join) of an incoming gradient dy, viewed as dy2 [rows, cols].
+    The LayerNorm backward that produced dy already wrote the bf16 copy (AddLayerNormFn.backward tags its result with
+    `_gtos_bf16 = (copy, tensor version)`), so the cast drops out of the critical path and the bias-gradient column sums
+    run on the side stream; any other gradient (an autograd accumulation, a user tensor) takes the fused cast_colsum."""
+    tag = getattr(dy, "_gtos_bf16", None)
+    rows, cols = dy2.shape
+    if (_side_enabled and tag is not None and tag[1] == dy._version and tuple(tag[0].shape) == (rows, cols)
+            and cols % 8 == 0 and dy2.data_ptr() == dy.data_ptr()):
+        sums = torch.empty(cols, dtype=torch.float32, device=dy2.device)
+        with fork() as f:
+            colsum(dy2, out=sums)
+        stats["grad_operand_tagged"] += 1
+        return tag[0], sums, f
+    dyb, sums = cast_colsum(dy2)
+    stats["grad_operand_cast"] += 1
+    return dyb, sums, _NoFork()
+
+
 def _weight_prep_launch(W, Wb, Wt, rel_heads):
     R, Cc = W.shape
     _lib.check(_lib.load().gtos_weight_prep(_p(W), R, Cc, _p(Wb), _up8(Cc), _p(Wt), _up8(R), rel_heads, _st()),
@@ -362,6 +389,7 @@ class AddLayerNormFn(torch.autograd.Function):
         ctx.meta = (p, seed, off, shape, res is not None)
         yb = yb.view(shape)
         ctx.mark_non_differentiable(yb)
+        ctx.set_materialize_grads(False)            # no zero-filled "gradient" for the bf16 operand copy
         return y.view(shape), yb
 
     @staticmethod
@@ -370,6 +398,8 @@ class AddLayerNormFn(torch.autograd.Function):
         z, mean, rstd, gamma = ctx.saved_tensors
         p, seed, off, shape, has_res = ctx.meta
         rows, D = z.shape
+        if dy is None:
+            dy = torch.zeros(shape, dtype=torch.float32, device=z.device)
         dy2 = dy.contiguous().view(rows, D)
         dres = torch.empty_like(z)
         dx = torch.empty_like(z) if p > 0 else None
@@ -378,11 +408,14 @@ class AddLayerNormFn(torch.autograd.Function):
         with fork() as f_par:                       # dgamma / dbeta: nothing downstream in this backward pass reads them
             _lib.check(_lib.load().gtos_ln_param_grad(_p(dy2), _p(z), _p(mean), _p(rstd), _p(dgamma), _p(dbeta), rows, D,
                                                       _st()), "ln_param_grad")
-        _lib.check(_lib.load().gtos_add_ln_bwd(_p(dy2), _p(z), _p(mean), _p(rstd), _p(gamma), _p(dres), _p(dx), None,
+        dxb = torch.empty(rows, D, dtype=torch.bfloat16, device=z.device) if D % 8 == 0 else None
+        _lib.check(_lib.load().gtos_add_ln_bwd(_p(dy2), _p(z), _p(mean), _p(rstd), _p(gamma), _p(dres), _p(dx), _p(dxb),
                                                None, None, rows, D, p, _p(seed), off, _st()), "add_ln_bwd")
         f_par.join()
         dres = dres.view(shape)
         dxo = dres if dx is None else dx.view(shape)
+        if dxb is not None:
+            dxo._gtos_bf16 = (dxb, dxo._version)    # operand copy for the sublayer's backward GEMMs (ops.grad_operand)
         return dxo, (dres if has_res else None), dgamma, dbeta, None
 
 
@@ -420,7 +453,7 @@ class FFNFn(torch.autograd.Function):
         D = shape[-1]
         dy2 = dy.contiguous().view(-1, D)
         M = dy2.shape[0]
-        dyb, db2 = cast_colsum(dy2)
+        dyb, db2, f_db = grad_operand(dy, dy2)
         dev = dy.device
         dW2 = torch.empty(D, Fd, dtype=torch.float32, device=dev)
         dW1 = torch.empty(Fd, D, dtype=torch.float32, device=dev)
@@ -436,6 +469,7 @@ class FFNFn(torch.autograd.Function):
         dx, _ = gemm_tn(dhb, W1t, D)
         f2.join()
         f1.join()
+        f_db.join()
         return dx.view(shape), None, dW1, db1f[:Fd], dW2, db2, None
 
 
@@ -493,6 +527,7 @@ class RelAttnFn(torch.autograd.Function):
         ctx.save_for_backward(xb2, relb, qkb, vproj, probs, attb, Wperm, WpermT, Wit, Wot, key_pad, attn_mask)
         ctx.meta = (N, B, D, H, p, seed, off)
         ctx.rel_acc = rel_acc if (rel_token is not None and rel_token.requires_grad) else None
+        ctx.set_materialize_grads(False)            # unused attention weights: no zero-filled [B,H,N,N] gradient
         if wts is None:
             return out.view(N, B, D), None
         return out.view(N, B, D), wts
@@ -504,10 +539,12 @@ class RelAttnFn(torch.autograd.Function):
         N, B, D, H, p, seed, off = ctx.meta
         lib = _lib.load()
         hd = D // H
+        if dout is None:
+            dout = torch.zeros(N, B, D, dtype=torch.float32, device=xb2.device)
         dev = dout.device
         NB = N * B
         dout2 = dout.contiguous().view(NB, D)
-        doutb, db_out = cast_colsum(dout2)
+        doutb, db_out, f_db = grad_operand(dout, dout2)
         dW_out = torch.empty(D, D, dtype=torch.float32, device=dev)
         with fork() as f_out:
             gemm_nn(doutb, attb, D, D, out=dW_out)
@@ -567,6 +604,7 @@ class RelAttnFn(torch.autograd.Function):
             f_out.join()
             f_rel.join()
             f_in.join()
+            f_db.join()
             return (dx.view(N, B, D), None, None, None, None, None, dW_in, db_in, dW_rel, dW_out, db_out, None, None,
                     None, None, None)
         _lib.check(lib.gtos_rel_dqk(_p(G), dqkv.data_ptr(), dqkv.data_ptr() + 4 * D, 3 * D, N, B, D, H, _st()),
@@ -590,6 +628,7 @@ class RelAttnFn(torch.autograd.Function):
         dW_in = gemm_nn(dqkvb, xb2, 3 * D, D)
         dx, _ = gemm_tn(dqkvb, Wit, D)
         f_out.join()
+        f_db.join()
         return (dx.view(N, B, D), None, d_rel, None, None, None, dW_in, db_in, dW_rel, dW_out, db_out, None, None,
                 None, None, None)
 
@@ -753,6 +792,7 @@ class MHAFn(torch.autograd.Function):
         out, _ = gemm_tn(attb, Wob, D, bias=b_out)
         ctx.save_for_backward(qb2, kb2, probs, attb, Wit, Wot, key_pad, attn_mask, *keep)
         ctx.meta = (T, S, B, D, H, p, p_w, seed, off, off2, self_attn)
+        ctx.set_materialize_grads(False)            # unused attention weights: no zero-filled [B,H,T,S] gradient
         if wts is None:
             return out.view(T, B, D), None
         return out.view(T, B, D), wts
@@ -764,9 +804,11 @@ class MHAFn(torch.autograd.Function):
         T, S, B, D, H, p, p_w, seed, off, off2, self_attn = ctx.meta
         lib = _lib.load()
         hd = D // H
+        if dout is None:
+            dout = torch.zeros(T, B, D, dtype=torch.float32, device=qb2.device)
         dev = dout.device
         dout2 = dout.contiguous().view(T * B, D)
-        doutb, db_out = cast_colsum(dout2)
+        doutb, db_out, f_db = grad_operand(dout, dout2)
         dW_out = torch.empty(D, D, dtype=torch.float32, device=dev)
         with fork() as f_out:
             gemm_nn(doutb, attb, D, D, out=dW_out)
@@ -815,6 +857,7 @@ class MHAFn(torch.autograd.Function):
             dk_in = dk_in.view(S, B, D)
         f_out.join()
         f_in.join()
+        f_db.join()
         return (dq_in.view(T, B, D), None, dk_in, None, None, None, None, dW_in, db_in, dW_out, db_out, None, None,
                 None, None)
 
@@ -1040,6 +1083,7 @@ class BankGatherFn(torch.autograd.Function):
         ctx.save_for_backward(idx)
         ctx.meta = (R, D, P)
         ctx.mark_non_differentiable(relb)
+        ctx.set_materialize_grads(False)            # no zero-filled [N,N,B,D] "gradient" for the bf16 copy
         return rel, relb
 
     @staticmethod
@@ -1047,6 +1091,8 @@ class BankGatherFn(torch.autograd.Function):
     def backward(ctx, d_rel, _d_relb):
         (idx,) = ctx.saved_tensors
         R, D, P = ctx.meta
+        if d_rel is None:
+            return torch.zeros(R, D, dtype=torch.float32, device=idx.device), None
         d_rel = d_rel.contiguous()
         d_bank = torch.empty(R, D, dtype=torch.float32, device=d_rel.device)
         _lib.check(_lib.load().gtos_bank_scatter_add(_p(d_rel), _p(idx), P, D, _p(d_bank), R, _st()), "bank_scatter_add")

@@ -26,6 +26,7 @@ class AttnDesc(C.Structure):
         ("dout", vp), ("lddo", i64), ("dprobs_extra", vp),
         ("dscores_jt", vp), ("dscores_ts", vp),
         ("dq", vp), ("lddq", i64), ("dk", vp), ("lddk", i64), ("dv", vp), ("lddv", i64),
+        ("dq_bf16", vp), ("dk_bf16", vp), ("dv_bf16", vp),
     ]
 
 
@@ -50,7 +51,7 @@ SIGNATURES = {
     "gtos_rel_drel": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "gtos_rel_dw_workspace": (i64, [i32, i32, i32, i32]),
     "gtos_rel_dw": (i32, [vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]),
-    "gtos_rel_dqk": (i32, [vp, vp, vp, i64, i32, i32, i32, i32, vp]),
+    "gtos_rel_dqk": (i32, [vp, vp, vp, i64, vp, vp, i32, i32, i32, i32, vp]),
     "gtos_rel_pair_keys": (i32, [vp, i32, i32, i32, i32, i32, vp, vp]),
     "gtos_rel_segsum": (i32, [vp, vp, vp, i64, i32, vp, i64, vp, vp]),
     "gtos_rel_dw_bank": (i32, [vp, i64, vp, vp, i32, i32, i32, vp]),

@@ -24,7 +24,7 @@ static inline cudaStream_t S_(void* s) { return reinterpret_cast<cudaStream_t>(s
 extern "C" {
 
 const char* gtos_last_error(void) { return g_err; }
-int gtos_abi_version(void) { return 2; }
+int gtos_abi_version(void) { return 3; }
 uint64_t gtos_launch_count(void) { return __atomic_load_n(&g_kernel_launches, __ATOMIC_RELAXED); }
 
 int gtos_device_check(void) {
@@ -189,12 +189,12 @@ int gtos_rel_dw_bank(const void* Sb, int64_t lds, const void* bankb, float* dW, 
   return launch_gemm_nn(a, S(stream));
 }
 
-int gtos_rel_dqk(const void* G, float* dq, float* dk, int64_t ld, int32_t N, int32_t B, int32_t D, int32_t H,
-                 void* stream) {
+int gtos_rel_dqk(const void* G, float* dq, float* dk, int64_t ld, void* dq_bf16, void* dk_bf16, int32_t N, int32_t B,
+                 int32_t D, int32_t H, void* stream) {
   RelTiling rt;
   int e = choose_rel_tiling(&rt, N, B, D, H);
   if (e) return e;
-  return rel_dqk(G, rt, dq, dk, ld, S(stream));
+  return rel_dqk(G, rt, dq, dk, ld, dq_bf16, dk_bf16, S(stream));
 }
 
 static void fill_attn(const gtos_attn_desc* d, AttnArgs* a) {
@@ -220,6 +220,7 @@ int gtos_attn_bwd(const gtos_attn_desc* d, void* stream) {
   g.dout = d->dout; g.lddo = d->lddo; g.dprobs_extra = d->dprobs_extra;
   g.dscores_jt = d->dscores_jt; g.dscores_ts = d->dscores_ts;
   g.dq = d->dq; g.lddq = d->lddq; g.dk = d->dk; g.lddk = d->lddk; g.dv = d->dv; g.lddv = d->lddv;
+  g.dq_bf16 = d->dq_bf16; g.dk_bf16 = d->dk_bf16; g.dv_bf16 = d->dv_bf16;
   GTOS_REQUIRE(!g.dq || (d->q && d->k && g.dk), "attn_bwd: decoder mode needs q, k, dq and dk");
   return attn_bwd(g, S(stream));
 }

@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(AT_THREADS, AT_MIN_CTAS) attn_bwd_q_kernel(con
       __syncthreads();
       tile_mm<false>(s.pb, s.lstr, s.yb, s.dstr, s.sc, s.lstr, s.R16, dc16, s.L16, false);
       __syncthreads();
-      store_rows_f32(g.dq, nullptr, g.lddq, a.B, b, hoff + c0, t0, nrows, dc, s.sc, s.lstr, a.scale);
+      store_rows_f32(g.dq, reinterpret_cast<__nv_bfloat16*>(g.dq_bf16), g.lddq, a.B, b, hoff + c0, t0, nrows, dc, s.sc, s.lstr, a.scale);
     }
   }
 }
@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(AT_THREADS, AT_MIN_CTAS) attn_bwd_kv_kernel(co
     tile_mm<false>(s.pb, s.lstr, s.yb, s.dstr, s.sc, s.lstr, s.R16, dc16, s.L16, false);
     __syncthreads();
     ATT_TRACE(2, 3);
-    store_rows_f32(g.dv, nullptr, g.lddv, a.B, b, hoff + c0, j0, nrows, dc, s.sc, s.lstr, 1.f);
+    store_rows_f32(g.dv, reinterpret_cast<__nv_bfloat16*>(g.dv_bf16), g.lddv, a.B, b, hoff + c0, j0, nrows, dc, s.sc, s.lstr, 1.f);
   }
   ATT_TRACE(2, 4);
   if (g.dk) {
@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(AT_THREADS, AT_MIN_CTAS) attn_bwd_kv_kernel(co
       __syncthreads();
       tile_mm<false>(s.pb, s.lstr, s.yb, s.dstr, s.sc, s.lstr, s.R16, dc16, s.L16, false);
       __syncthreads();
-      store_rows_f32(g.dk, nullptr, g.lddk, a.B, b, hoff + c0, j0, nrows, dc, s.sc, s.lstr, 1.f);
+      store_rows_f32(g.dk, reinterpret_cast<__nv_bfloat16*>(g.dk_bf16), g.lddk, a.B, b, hoff + c0, j0, nrows, dc, s.sc, s.lstr, 1.f);
     }
   }
 }

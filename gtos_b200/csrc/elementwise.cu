@@ -849,7 +849,8 @@ int bank_scatter_add(const float* d_rel, const long long* idx, long P, int D, fl
 }
 
 __global__ void rel_dqk_kernel(const __nv_bfloat16* __restrict__ G, RelTiling rt, float* __restrict__ dq,
-                               float* __restrict__ dk, long ld) {
+                               float* __restrict__ dk, long ld, __nv_bfloat16* __restrict__ dq_b,
+                               __nv_bfloat16* __restrict__ dk_b) {
   GTOS_PDL_PROLOGUE();
   // block = (node n, batch b); thread = one 8-column (16-byte) chunk of the 2D-wide G row.
   // chunks inside the d(q+ra) half of a head sum over keys j (-> dq[n]); chunks inside the d(k+rb) half sum
@@ -895,16 +896,27 @@ __global__ void rel_dqk_kernel(const __nv_bfloat16* __restrict__ G, RelTiling rt
       acc[2 * t + 1] += f.y;
     }
   }
-  float* dst = (is_x ? dq : dk) + ((long)n * rt.B + b) * ld + h * hd + (is_x ? w : w - hd);
+  const long off = ((long)n * rt.B + b) * ld + h * hd + (is_x ? w : w - hd);
+  float* dst = (is_x ? dq : dk) + off;
 #pragma unroll
   for (int t = 0; t < 8; ++t) dst[t] = acc[t];
+  __nv_bfloat16* dst_b = is_x ? dq_b : dk_b;      // optional operand copy for the in_proj backward GEMMs (same layout)
+  if (dst_b)
+    *reinterpret_cast<uint4*>(dst_b + off) = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
+                                                        pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
 }
 
-int rel_dqk(const void* G, const RelTiling& rt, float* dq, float* dk, long ld, cudaStream_t st) {
+int rel_dqk(const void* G, const RelTiling& rt, float* dq, float* dk, long ld, void* dq_bf16, void* dk_bf16,
+            cudaStream_t st) {
   dim3 grid(rt.N, rt.B);
   const int thr = 2 * rt.D / 8;
   GTOS_REQUIRE(thr <= 1024 && rt.hd % 8 == 0, "rel_dqk: unsupported D=%d hd=%d", rt.D, rt.hd);
-  GTOS_KLAUNCH(rel_dqk_kernel, dim3(grid), dim3(thr), 0, st, reinterpret_cast<const __nv_bfloat16*>(G), rt, dq, dk, ld);
+  GTOS_REQUIRE((dq_bf16 == nullptr) == (dk_bf16 == nullptr), "rel_dqk: the bf16 copies go together");
+  GTOS_REQUIRE(!dq_bf16 || (ld % 8 == 0 && (reinterpret_cast<uintptr_t>(dq_bf16) & 15) == 0 &&
+                            (reinterpret_cast<uintptr_t>(dk_bf16) & 15) == 0),
+               "rel_dqk: bf16 copies need 16-byte aligned rows");
+  GTOS_KLAUNCH(rel_dqk_kernel, dim3(grid), dim3(thr), 0, st, reinterpret_cast<const __nv_bfloat16*>(G), rt, dq, dk, ld,
+               reinterpret_cast<__nv_bfloat16*>(dq_bf16), reinterpret_cast<__nv_bfloat16*>(dk_bf16));
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
 }

@@ -31,7 +31,8 @@ int token_nll_bwd(const float* dloss_row, const float* logits, long ldl, int V, 
                   const float* stats, float* dlogits, long lddl, float* dgate_logits, float* dalign, cudaStream_t st);
 int bank_gather(const float* bank, const long long* idx, long P, int D, float* out_f32, void* out_bf16, cudaStream_t st);
 int bank_scatter_add(const float* d_rel, const long long* idx, long P, int D, float* d_bank, long R, cudaStream_t st);
-int rel_dqk(const void* G, const RelTiling& rt, float* dq, float* dk, long ld, cudaStream_t st);
+int rel_dqk(const void* G, const RelTiling& rt, float* dq, float* dk, long ld, void* dq_bf16, void* dk_bf16,
+            cudaStream_t st);
 int rel_pair_keys(const long long* idx, const RelTiling& rt, int R, int* keys, cudaStream_t st);
 int rel_segsum(const void* G, const int* order, const int* keys, long n, int C, void* out_bf16, long ldo, float* spill,
                cudaStream_t st);
@@ -66,6 +67,7 @@ struct AttnBwdArgs {
   float* dq; long lddq;           // decoder mode outs
   float* dk; long lddk;
   float* dv; long lddv;
+  void* dq_bf16; void* dk_bf16; void* dv_bf16;   // optional bf16 copies, same element layout as dq / dk / dv
 };
 int attn_bwd(const AttnBwdArgs& a, cudaStream_t st);
 int attn_debug_read_trace(unsigned long long* host_out, int enable);   // 3 kernels x 16 clock64 slots of CTA 0

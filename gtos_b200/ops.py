@@ -161,6 +161,23 @@ class _NoFork:
         pass
 
 
+# the attention backward kernels (and rel_dqk) write bf16 copies of dq / dk / dv next to the fp32 gradients, so the
+# in_proj backward GEMMs start without a cast pass; the bias-gradient column sums move to the side stream
+_grad_copies = _side_enabled and os.environ.get("GTOS_GRAD_COPIES", "0") == "1"
+_grad_tags = os.environ.get("GTOS_GRAD_TAG", "1") == "1"
+
+
+def operand_or_cast(x2d, xb):
+    """(bf16 operand, fp32 column sums, fork to join) of x2d; xb = the bf16 copy its producer wrote, or None."""
+    if xb is None:
+        xb, sums = cast_colsum(x2d)
+        return xb, sums, _NoFork()
+    sums = torch.empty(x2d.shape[1], dtype=torch.float32, device=x2d.device)
+    with fork() as f:
+        colsum(x2d, out=sums)
+    return xb, sums, f
+
+
 stats = {"grad_operand_tagged": 0, "grad_operand_cast": 0}      # which path incoming gradients took (tests, tools)
 
 
@@ -171,7 +188,7 @@ def grad_operand(dy, dy2):
     run on the side stream; any other gradient (an autograd accumulation, a user tensor) takes the fused cast_colsum."""
     tag = getattr(dy, "_gtos_bf16", None)
     rows, cols = dy2.shape
-    if (_side_enabled and tag is not None and tag[1] == dy._version and tuple(tag[0].shape) == (rows, cols)
+    if (_side_enabled and _grad_tags and tag is not None and tag[1] == dy._version and tuple(tag[0].shape) == (rows, cols)
             and cols % 8 == 0 and dy2.data_ptr() == dy.data_ptr()):
         sums = torch.empty(cols, dtype=torch.float32, device=dy2.device)
         with fork() as f:
@@ -550,6 +567,9 @@ class RelAttnFn(torch.autograd.Function):
             gemm_nn(doutb, attb, D, D, out=dW_out)
         datt, _ = gemm_tn(doutb, Wot, D)                                           # [NB, D]
         dqkv = torch.empty(NB, 3 * D, dtype=torch.float32, device=dev)
+        dqkv_b = torch.empty(NB, 3 * D, dtype=torch.bfloat16, device=dev) if (_grad_copies and D % 8 == 0) else None
+        dqb_p = dqkv_b.data_ptr() if dqkv_b is not None else None
+        dkb_p = dqkv_b.data_ptr() + 2 * D if dqkv_b is not None else None
         ds_jt = torch.empty(B, H, N, N, dtype=torch.float32, device=dev)
         ds_ts = torch.empty(B, H, N, N, dtype=torch.float32, device=dev)
         d = _attn_desc(N, N, B, H, hd)
@@ -562,6 +582,7 @@ class RelAttnFn(torch.autograd.Function):
         d.dprobs_extra = _p(dwts.contiguous()) if dwts is not None else None
         d.dscores_jt, d.dscores_ts = _p(ds_jt), _p(ds_ts)
         d.dv, d.lddv = dqkv.data_ptr() + 8 * D, 3 * D
+        d.dv_bf16 = dqkv_b.data_ptr() + 4 * D if dqkv_b is not None else None
         _lib.check(lib.gtos_attn_bwd(C.byref(d), _st()), "attn_bwd(enc)")
         tiles = rel_tiling(N, B, D, H)["tiles"]
         G = torch.empty(tiles * 128, 2 * D, dtype=torch.bfloat16, device=dev)
@@ -595,9 +616,9 @@ class RelAttnFn(torch.autograd.Function):
                                                _p(acc.spill), _st()), "rel_segsum")
                 _lib.check(lib.gtos_rel_dw_bank(s_ptr, L * 2 * D, _p(bk.bankb), _p(dW_rel), R, D, H, _st()), "rel_dw_bank")
                 acc.Wcat[:, c0:c0 + 2 * D].copy_(WpermT[:, :2 * D])
-            _lib.check(lib.gtos_rel_dqk(_p(G), dqkv.data_ptr(), dqkv.data_ptr() + 4 * D, 3 * D, N, B, D, H, _st()),
-                       "rel_dqk")
-            dqkvb, db_in = cast_colsum(dqkv)
+            _lib.check(lib.gtos_rel_dqk(_p(G), dqkv.data_ptr(), dqkv.data_ptr() + 4 * D, 3 * D, dqb_p, dkb_p, N, B, D, H,
+                                        _st()), "rel_dqk")
+            dqkvb, db_in, f_dbin = operand_or_cast(dqkv, dqkv_b)
             with fork() as f_in:
                 gemm_nn(dqkvb, xb2, 3 * D, D, out=dW_in)
             dx, _ = gemm_tn(dqkvb, Wit, D)
@@ -605,9 +626,10 @@ class RelAttnFn(torch.autograd.Function):
             f_rel.join()
             f_in.join()
             f_db.join()
+            f_dbin.join()
             return (dx.view(N, B, D), None, None, None, None, None, dW_in, db_in, dW_rel, dW_out, db_out, None, None,
                     None, None, None)
-        _lib.check(lib.gtos_rel_dqk(_p(G), dqkv.data_ptr(), dqkv.data_ptr() + 4 * D, 3 * D, N, B, D, H, _st()),
+        _lib.check(lib.gtos_rel_dqk(_p(G), dqkv.data_ptr(), dqkv.data_ptr() + 4 * D, 3 * D, dqb_p, dkb_p, N, B, D, H, _st()),
                    "rel_dqk")
         if ctx.rel_acc is not None:
             # all layers share one relation tensor: reduce this layer's gradient straight into the shared buffer
@@ -624,11 +646,12 @@ class RelAttnFn(torch.autograd.Function):
         ws = None
         dW_rel = torch.empty(2 * D, D, dtype=torch.float32, device=dev)
         _lib.check(lib.gtos_rel_dw(_p(G), _p(relb), _p(dW_rel), _p(ws), ws_elems, N, B, D, H, _st()), "rel_dw")
-        dqkvb, db_in = cast_colsum(dqkv)
+        dqkvb, db_in, f_dbin = operand_or_cast(dqkv, dqkv_b)
         dW_in = gemm_nn(dqkvb, xb2, 3 * D, D)
         dx, _ = gemm_tn(dqkvb, Wit, D)
         f_out.join()
         f_db.join()
+        f_dbin.join()
         return (dx.view(N, B, D), None, d_rel, None, None, None, dW_in, db_in, dW_rel, dW_out, db_out, None, None,
                 None, None, None)
 
@@ -816,9 +839,13 @@ class MHAFn(torch.autograd.Function):
         if off2:
             dropout_f32(datt, p, seed, off2, out=datt)
         d = _attn_desc(T, S, B, H, hd)
+        copies = _grad_copies and D % 8 == 0
         if self_attn:
             (proj,) = keep
             dproj = torch.empty(T * B, 3 * D, dtype=torch.float32, device=dev)
+            dproj_b = torch.empty(T * B, 3 * D, dtype=torch.bfloat16, device=dev) if copies else None
+            if copies:
+                d.dq_bf16, d.dk_bf16, d.dv_bf16 = dproj_b.data_ptr(), dproj_b.data_ptr() + 2 * D, dproj_b.data_ptr() + 4 * D
             d.q, d.ldq, d.k, d.ldk, d.v, d.ldv = (proj.data_ptr(), 3 * D, proj.data_ptr() + 4 * D, 3 * D,
                                                   proj.data_ptr() + 8 * D, 3 * D)
             d.dq, d.lddq, d.dk, d.lddk, d.dv, d.lddv = (dproj.data_ptr(), 3 * D, dproj.data_ptr() + 4 * D, 3 * D,
@@ -827,6 +854,10 @@ class MHAFn(torch.autograd.Function):
             pq, pkv = keep
             dpq = torch.empty(T * B, D, dtype=torch.float32, device=dev)
             dpkv = torch.empty(S * B, 2 * D, dtype=torch.float32, device=dev)
+            dpq_b = torch.empty(T * B, D, dtype=torch.bfloat16, device=dev) if copies else None
+            dpkv_b = torch.empty(S * B, 2 * D, dtype=torch.bfloat16, device=dev) if copies else None
+            if copies:
+                d.dq_bf16, d.dk_bf16, d.dv_bf16 = dpq_b.data_ptr(), dpkv_b.data_ptr(), dpkv_b.data_ptr() + 2 * D
             d.q, d.ldq, d.k, d.ldk, d.v, d.ldv = pq.data_ptr(), D, pkv.data_ptr(), 2 * D, pkv.data_ptr() + 4 * D, 2 * D
             d.dq, d.lddq, d.dk, d.lddk, d.dv, d.lddv = (dpq.data_ptr(), D, dpkv.data_ptr(), 2 * D,
                                                         dpkv.data_ptr() + 4 * D, 2 * D)
@@ -841,13 +872,16 @@ class MHAFn(torch.autograd.Function):
         _lib.check(lib.gtos_attn_bwd(C.byref(d), _st()), "attn_bwd(dec)")
         dW_in = torch.empty(3 * D, D, dtype=torch.float32, device=dev)
         if self_attn:
-            dprojb, db_in = cast_colsum(dproj)
+            dprojb, db_in, f_dbin = operand_or_cast(dproj, dproj_b)
             with fork() as f_in:
                 gemm_nn(dprojb, qb2, 3 * D, D, out=dW_in)
             dq_in, _ = gemm_tn(dprojb, Wit, D)
             dk_in = None
         else:
-            (dpqb, dbq), (dpkvb, dbkv) = cast_colsum(dpq), cast_colsum(dpkv)
+            dpqb, dbq, f_dbin = operand_or_cast(dpq, dpq_b)
+            dpkvb, dbkv, f_dbkv = operand_or_cast(dpkv, dpkv_b)
+            f_dbin.join()
+            f_dbkv.join()
             db_in = torch.cat([dbq, dbkv])
             with fork() as f_in:
                 gemm_nn(dpqb, qb2, D, D, out=dW_in[:D])
@@ -858,6 +892,7 @@ class MHAFn(torch.autograd.Function):
         f_out.join()
         f_in.join()
         f_db.join()
+        f_dbin.join()
         return (dq_in.view(T, B, D), None, dk_in, None, None, None, None, dW_in, db_in, dW_out, db_out, None, None,
                 None, None)
 

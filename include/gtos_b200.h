@@ -87,9 +87,10 @@ int gtos_rel_drel(const void* G, const void* WpermT, float* d_relation, int32_t 
 int64_t gtos_rel_dw_workspace(int32_t N, int32_t B, int32_t D, int32_t H);
 int gtos_rel_dw(const void* G, const void* relb, float* dW, float* workspace, int64_t workspace_elems, int32_t N,
                 int32_t B, int32_t D, int32_t H, void* stream);
-/* dq[i,b,:] = sum_j G_x, dk[j,b,:] = sum_i G_y ; written with row stride ld (into the QKV grad buffer) */
-int gtos_rel_dqk(const void* G, float* dq, float* dk, int64_t ld, int32_t N, int32_t B, int32_t D, int32_t H,
-                 void* stream);
+/* dq[i,b,:] = sum_j G_x, dk[j,b,:] = sum_i G_y ; written with row stride ld (into the QKV grad buffer).
+ * dq_bf16 / dk_bf16: optional bf16 copies with the same element layout (operand of the in_proj backward GEMMs). */
+int gtos_rel_dqk(const void* G, float* dq, float* dk, int64_t ld, void* dq_bf16, void* dk_bf16, int32_t N, int32_t B,
+                 int32_t D, int32_t H, void* stream);
 
 /* ---- bank-factorised backward of the relation terms (caller generator/generator.py:76-79) ----
  * When relation = bank[idx] (bank [R,D], idx [N,N,B] int64, layout idx[j][i][b]) the two P-row GEMMs of the backward
@@ -132,6 +133,9 @@ typedef struct gtos_attn_desc {
   float* dq; int64_t lddq;
   float* dk; int64_t lddk;
   float* dv; int64_t lddv;
+  /* optional bf16 copies of dq / dk / dv (same element layout and row strides as the fp32 outputs): the operand of
+   * the in_proj backward GEMMs, so no separate cast pass sits between this kernel and them */
+  void* dq_bf16; void* dk_bf16; void* dv_bf16;
 } gtos_attn_desc;
 int gtos_attn_fwd(const gtos_attn_desc* d, void* stream);
 int gtos_attn_bwd(const gtos_attn_desc* d, void* stream);

@@ -131,7 +131,7 @@ def test_rel_backward_pieces(dev, N, B, D, H):
     _lib.check(lib.gtos_rel_grad(relb.data_ptr(), Wperm.data_ptr(), qkv.data_ptr(), qkv.data_ptr() + 2 * D, 2 * D,
                                  ds.data_ptr(), G.data_ptr(), N, B, D, H, st), "rel_grad")
     dqkv = torch.zeros(N * B, 3 * D, device=dev)
-    _lib.check(lib.gtos_rel_dqk(G.data_ptr(), dqkv.data_ptr(), dqkv.data_ptr() + 4 * D, 3 * D, N, B, D, H, st), "dqk")
+    _lib.check(lib.gtos_rel_dqk(G.data_ptr(), dqkv.data_ptr(), dqkv.data_ptr() + 4 * D, 3 * D, None, None, N, B, D, H, st), "dqk")
     drel = torch.full((N, N, B, D), float("nan"), device=dev)
     _lib.check(lib.gtos_rel_drel(G.data_ptr(), WpermT.data_ptr(), drel.data_ptr(), 0, N, B, D, H, st), "drel")
     ws_n = lib.gtos_rel_dw_workspace(N, B, D, H)

@@ -138,3 +138,51 @@ def test_config3_shard_shape_vs_oracle(dev):
         with torch.no_grad():
             ref = O.graph_transformer(P, "", g["x"][:, b:b + 1], relb, 4, H, self_padding_mask=g["node_mask"][:, b:b + 1])
         assert rel_err(out[:, b:b + 1], ref) < TOL
+
+
+def test_hot_path_streams_and_planned_weight_copies_match_the_serial_schedule(dev, monkeypatch):
+    """The step runs the GRU directions, the bank-side relation backward, weight-gradient GEMMs, LayerNorm parameter
+    gradients and the weight operand copies on extra streams (ops.fork, ops.WeightPrepPlan).  Same kernels, same inputs:
+    the loss must be bit-identical to the single-stream schedule and every gradient equal up to the summation order of
+    the split-K / column-sum atomics; the second forward of a model (copies made ahead of time) must equal the first
+    (copies made where they are used); an optimizer-style in-place weight update between two forwards must be seen."""
+    from gtos_b200 import hotpath, ops, synthetic
+    from conftest import l2_err
+    cfg = hotpath.HotPathConfig(embed_dim=128, ff_embed_dim=256, num_heads=8, graph_layers=2, snt_layers=1,
+                                inference_layers=1, rnn_hidden_size=64, dropout=0.0, vocab_size=500)
+    torch.manual_seed(SEED)
+    model = hotpath.HotPath(cfg).to(dev)
+    g = synthetic.make_batch(8, 16, 128, T_max=12, T_min=6, V=500, seed=SEED)
+    batch = {k: v.to(dev) for k, v in hotpath.batch_tensors(g).items()}
+    params = list(model.parameters())
+
+    def run():
+        for p in params:
+            p.grad = None
+        loss = model(batch)
+        loss.backward()
+        torch.cuda.synchronize()
+        return loss.detach().clone(), [None if p.grad is None else p.grad.clone() for p in params]
+
+    with monkeypatch.context() as mp:
+        for flag in ("_side_enabled", "_gru_streams", "_rel_streams", "_prep_ahead"):
+            mp.setattr(ops, flag, False)
+        loss_serial, grads_serial = run()
+    model._prep_plan = ops.WeightPrepPlan()
+    loss_first, grads_first = run()                 # records the plan, copies made in place
+    assert model._prep_plan.items, "the first forward did not record the weight copies it used"
+    loss_ahead, grads_ahead = run()                 # copies issued ahead on the third stream
+    assert torch.equal(loss_first, loss_serial) and torch.equal(loss_ahead, loss_serial)
+    for a, b, c in zip(grads_serial, grads_first, grads_ahead):
+        assert (a is None) == (b is None) == (c is None)
+        if a is not None:
+            assert l2_err(b, a) < 1e-3 and l2_err(c, a) < 1e-3       # a race would be a gross error, not 1e-3
+    with torch.no_grad():
+        for p in params:
+            p.mul_(1.25)                            # what an optimizer step does: same storage, new values
+    loss_new, _ = run()
+    with monkeypatch.context() as mp:
+        for flag in ("_side_enabled", "_gru_streams", "_rel_streams", "_prep_ahead"):
+            mp.setattr(ops, flag, False)
+        loss_new_serial, _ = run()
+    assert torch.equal(loss_new, loss_new_serial) and not torch.equal(loss_new, loss_serial)

@@ -143,6 +143,14 @@ def test_rel_backward_pieces(dev, N, B, D, H):
     # G is rounded to bf16 once, so downstream tolerances are bf16-level (1e-2 relative)
     assert rel_err(dqkv[:, :D], q32.grad[:, :D]) < 1e-2
     assert rel_err(dqkv[:, D:2 * D], q32.grad[:, D:2 * D]) < 1e-2
+    # optional bf16 operand copies: the same sums, rounded once
+    dqkv2 = torch.zeros(N * B, 3 * D, device=dev)
+    dqkv_b = torch.zeros(N * B, 3 * D, dtype=torch.bfloat16, device=dev)
+    _lib.check(lib.gtos_rel_dqk(G.data_ptr(), dqkv2.data_ptr(), dqkv2.data_ptr() + 4 * D, 3 * D, dqkv_b.data_ptr(),
+                                dqkv_b.data_ptr() + 2 * D, N, B, D, H, st), "dqk(bf16)")
+    torch.cuda.synchronize()
+    assert torch.equal(dqkv2, dqkv)
+    assert torch.equal(dqkv_b[:, :2 * D], bf(dqkv[:, :2 * D])) and float(dqkv_b[:, 2 * D:].float().abs().max()) == 0.0
     assert rel_err(drel, r32.grad) < 1e-2
     assert rel_err(dW, W32.grad) < 1e-2
 
@@ -203,6 +211,17 @@ def test_attention_core(dev, T, S, B, H, hd, causal):
     _lib.check(lib.gtos_attn_bwd(C.byref(d), st), "attn_bwd")
     torch.cuda.synchronize()
     assert rel_err(dq, gq) < 2e-2 and rel_err(dk, gk) < 2e-2 and rel_err(dv, gv) < 2e-2
+    # optional bf16 operand copies of dq / dk / dv: bit-identical fp32 outputs, copies = those values rounded once
+    dq2, dk2, dv2 = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    dqb, dkb, dvb = (torch.empty(t.shape, dtype=torch.bfloat16, device=dev) for t in (q, k, v))
+    d.dq, d.dk, d.dv = dq2.data_ptr(), dk2.data_ptr(), dv2.data_ptr()
+    d.dq_bf16, d.dk_bf16, d.dv_bf16 = dqb.data_ptr(), dkb.data_ptr(), dvb.data_ptr()
+    _lib.check(lib.gtos_attn_bwd(C.byref(d), st), "attn_bwd(bf16 copies)")
+    torch.cuda.synchronize()
+    assert torch.equal(dq2, dq) and torch.equal(dk2, dk) and torch.equal(dv2, dv)
+    assert torch.equal(dqb, bf(dq)) and torch.equal(dkb, bf(dk)) and torch.equal(dvb, bf(dv))
+    d.dq, d.dk, d.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
+    d.dq_bf16 = d.dk_bf16 = d.dv_bf16 = None
     # extra gradient flowing into the returned weights
     q.grad = k.grad = v.grad = None
     ((ref * dout).sum() + (pref * dw).sum()).backward()
@@ -243,6 +262,59 @@ def test_add_ln_and_ffn(dev):
     rs = torch.autograd.grad((hr * w).sum(), [xr, W1r, b1r, W2r, b2r])
     for a, r in zip(gs, rs):
         assert rel_err(a, r) < 1e-2
+
+
+def test_ln_param_grad_alone_and_tagged_gradient(dev):
+    """gtos_ln_param_grad (the LayerNorm weight / bias gradients as their own entry point) vs torch, and the bf16
+    operand copy the LayerNorm backward attaches to its result: exactly bf16(dx), dropped when the tensor is modified."""
+    from gtos_b200 import _lib, ops
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    rows, D = 777, 256
+    x = torch.randn(rows, D, device=dev)
+    g = (1 + 0.1 * torch.randn(D, device=dev)).requires_grad_()
+    b = (0.1 * torch.randn(D, device=dev)).requires_grad_()
+    dy = torch.randn(rows, D, device=dev)
+    mean, var = x.mean(1), x.var(1, unbiased=False)
+    rstd = (var + 1e-5).rsqrt()
+    dgamma, dbeta = torch.full((D,), float("nan"), device=dev), torch.full((D,), float("nan"), device=dev)
+    _lib.check(lib.gtos_ln_param_grad(dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dgamma.data_ptr(),
+                                      dbeta.data_ptr(), rows, D, st), "ln_param_grad")
+    ref = torch.nn.functional.layer_norm(x, (D,), g, b)
+    rg, rb = torch.autograd.grad((ref * dy).sum(), [g, b])
+    torch.cuda.synchronize()
+    assert rel_err(dgamma, rg) < 1e-4 and rel_err(dbeta, rb) < 1e-4
+    # tagged gradient
+    xi = x.clone().requires_grad_()
+    res = torch.randn(rows, D, device=dev, requires_grad=True)
+    seen = {}
+
+    class Probe(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, t):
+            return t.clone()
+
+        @staticmethod
+        def backward(ctx, gr):
+            seen["tag"] = getattr(gr, "_gtos_bf16", None)
+            seen["grad"] = gr
+            return gr
+
+    y, _ = ops.add_layer_norm(Probe.apply(xi), res, g, b, 0.0)
+    (y * dy).sum().backward()
+    torch.cuda.synchronize()
+    assert seen["tag"] is not None, "the LayerNorm backward did not tag its result"
+    copy, ver = seen["tag"]
+    assert ver == seen["grad"]._version and torch.equal(copy.view_as(seen["grad"]), bf(seen["grad"]))
+    d2 = seen["grad"].view(rows, D)
+    for k in ops.stats:
+        ops.stats[k] = 0
+    ops.grad_operand(seen["grad"], d2)[2].join()
+    seen["grad"].add_(1.0)                                  # a modified tensor must not use the stale copy
+    ops.grad_operand(seen["grad"], d2)[2].join()
+    torch.cuda.synchronize()
+    assert ops.stats == {"grad_operand_tagged": 1 if ops._side_enabled and ops._grad_tags else 0,
+                         "grad_operand_cast": 1 if ops._side_enabled and ops._grad_tags else 2}
 
 
 def test_dropout_statistics(dev):

@@ -404,10 +404,11 @@ def main_ours(args):
         extra = breakdown(args, w, cfg, model, static, meta, dev, lib)
     total_pairs = meta["pairs"] * world
     total_tokens = meta["tokens"] * world
+    total_valid = meta["valid_pairs"] * world
     if world > 1:
-        t = torch.tensor([float(meta["pairs"]), float(meta["tokens"])], device=dev)
+        t = torch.tensor([float(meta["pairs"]), float(meta["tokens"]), float(meta["valid_pairs"])], device=dev)
         dist.all_reduce(t)
-        total_pairs, total_tokens = t[0].item(), t[1].item()
+        total_pairs, total_tokens, total_valid = t[0].item(), t[1].item(), t[2].item()
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -419,6 +420,7 @@ def main_ours(args):
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "decoder_tokens_per_sec": total_tokens / (ms * 1e-3),
+        "valid_node_pairs_per_sec": total_valid / (ms * 1e-3),      # sum_b (n_b + 1)^2: pairs of un-padded nodes only
         "config": {"workload": f"{args.workload}: gtos generator/ default (4 graph + 1 snt + 3 inference layers, "
                                f"{w['D']} dim, {w['H']} heads), synthetic <= {w['n_max']}-node graphs, fwd+bwd, "
                                f"dropout {args.dropout}", "graphs_per_gpu": w["B"], "global_batch": w["B"] * world,

@@ -5,6 +5,7 @@
 #include "../../include/gtos_b200.h"
 #include "elementwise.cuh"
 #include "gemm.cuh"
+#include "graph_paths_core.h"
 
 namespace gtos {
 static thread_local char g_err[512] = "";
@@ -353,6 +354,18 @@ int gtos_grad_sumsq(const float* g, int64_t n, float* out, float* workspace, voi
 int gtos_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int64_t n_decay, const float* lr_ptr, float beta1,
                    float beta2, float eps, float weight_decay, const float* norm_sq, float max_norm, void* stream) {
   return adam_step(p, g, m, v, n, n_decay, lr_ptr, beta1, beta2, eps, weight_decay, norm_sq, max_norm, S(stream));
+}
+
+
+int gtos_graph_paths(const int32_t* n_nodes, const int32_t* deg, const int32_t* nbr, const int32_t* lab, int32_t B,
+                     int32_t n_max, int32_t deg_max, int32_t max_len, int32_t self_id, int32_t tl_id, const void* seed_ptr,
+                     uint64_t seed_off, int32_t* paths, int32_t* plen, void* stream) {
+  GraphPathsArgs a;
+  a.n_nodes = n_nodes; a.deg = deg; a.nbr = nbr; a.lab = lab;
+  a.B = B; a.n_max = n_max; a.deg_max = deg_max; a.max_len = max_len;
+  a.self_id = self_id; a.tl_id = tl_id; a.seed = 0;
+  a.paths = paths; a.plen = plen;
+  return graph_paths(a, seed_ptr, seed_off, S(stream));
 }
 
 }  // extern "C"

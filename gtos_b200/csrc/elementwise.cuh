@@ -103,4 +103,8 @@ int adam_step(float* p, const float* g, float* m, float* v, long n, long n_decay
               float eps, float wd, const float* norm_sq, float max_norm, cudaStream_t st);
 int beam_ancestry(const int* old_anc, int* new_anc, long ld, const int* parent, int t, int Hyp, cudaStream_t st);
 
+// ---- shortest label paths of a graph batch (graph_paths.cu / graph_paths_core.h) ----
+struct GraphPathsArgs;
+int graph_paths(const GraphPathsArgs& a, const void* seed_ptr, unsigned long long seed_off, cudaStream_t st);
+
 }  // namespace gtos

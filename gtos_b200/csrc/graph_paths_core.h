@@ -1,0 +1,198 @@
+// gtos_b200 -- SURVEY.md §8 f-3: all-pairs shortest label paths of a batch of small graphs, one path per ordered pair
+// sampled uniformly among the equally short ones.
+//
+// Reference: AMRGraph.collect_concepts_and_relations (generator/AMRGraph.py:100-115) enumerates, with networkx, every
+// shortest NODE path src -> tgt of the bidirected labelled graph (each edge has a `_reverse_` twin, AMRGraph.py:76-80;
+// `_r_` in translator/dependencyGraph.py:30-34) and keeps the edge labels; batchify (generator/data.py:148-154) then
+// draws one of them with random.choice, replaces the empty path by <SELF> and a path of more than `max_len` labels by
+// <TL>.  Enumeration is exponential in the worst case; the same distribution comes from counting:
+//   sigma[v] = number of shortest paths v -> tgt  (BFS from tgt; the structure is symmetric, so dist(v -> tgt) is the BFS
+//              depth of v), and a walk from src that moves from v to a neighbour u one level closer with probability
+//   sigma[u] / sum of sigma over such neighbours
+// visits every shortest path src -> tgt with probability 1 / sigma[src].
+//
+// One CTA owns one (graph, target) and produces the paths of ALL sources to that target.  The code below is written in
+// barrier-separated phases (GTOS_PHASE ... GTOS_PHASE_END) so that the SAME source also compiles as plain C++, where a
+// phase is a loop over the emulated thread ids (tests/emu/graph_paths_emu.cpp: the CPU check of this very code against
+// the oracle; the CUDA build is what ships).  Phases are pull-based - a thread writes only its own nodes / sources - so
+// there is no intra-phase ordering to get wrong, and the floating-point sums run in adjacency order: results are
+// bit-identical on both sides and reproducible from (seed, pair).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define GTOS_HD __host__ __device__ __forceinline__
+#else
+#define GTOS_HD inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define GTOS_PHASE(tid, nthr) { const int tid = (int)threadIdx.x; const int nthr = (int)blockDim.x;
+#define GTOS_PHASE_END } __syncthreads();
+#else
+#ifndef GTOS_EMU_THREADS
+#define GTOS_EMU_THREADS 128
+#endif
+#define GTOS_PHASE(tid, nthr) for (int tid = 0, nthr = GTOS_EMU_THREADS; tid < nthr; ++tid) {
+#define GTOS_PHASE_END }
+#endif
+
+namespace gtos {
+
+// the library's counter-based uniform (common.cuh rng_uniform), usable from host code too
+GTOS_HD float paths_uniform(uint64_t seed, uint64_t idx) {
+  uint64_t z = seed + idx * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return static_cast<float>(static_cast<uint32_t>(z >> 40)) * (1.0f / 16777216.0f);
+}
+
+struct GraphPathsArgs {
+  const int32_t* n_nodes;   // [B]
+  const int32_t* deg;       // [B, n_max]            out-degree of every node (<= deg_max)
+  const int32_t* nbr;       // [B, n_max, deg_max]   neighbour of edge k of node v
+  const int32_t* lab;       // [B, n_max, deg_max]   label id of the edge v -> nbr
+  int32_t B, n_max, deg_max, max_len;
+  int32_t self_id, tl_id;
+  uint64_t seed;            // already combined: *seed_ptr + seed_off
+  int32_t* paths;           // [B, n_max, n_max, max_len]  labels of the path i -> j in walking order, 0 padded
+  int32_t* plen;            // [B, n_max, n_max]           number of labels (1 for <SELF> / <TL>); 0 = pair outside the graph
+};
+
+// shared-memory working set of one CTA: dist [n_max] int32, sigma [n_max] float, mark [n_max] int32, flag [2] int32
+GTOS_HD size_t graph_paths_smem_bytes(int n_max) { return (size_t)n_max * 12 + 16; }
+
+// everything one CTA does for (graph b, target j); `smem` = graph_paths_smem_bytes(n_max) bytes, 4-byte aligned
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline void graph_paths_cta(const GraphPathsArgs& a, int b, int j, void* smem) {
+  int32_t* dist = reinterpret_cast<int32_t*>(smem);
+  float* sigma = reinterpret_cast<float*>(dist + a.n_max);
+  int32_t* mark = reinterpret_cast<int32_t*>(sigma + a.n_max);
+  int32_t* flag = mark + a.n_max;                                   // flag[0]: the next level is not empty
+  const int n = a.n_nodes[b];
+  const int32_t* deg = a.deg + (long)b * a.n_max;
+  const int32_t* nbr = a.nbr + (long)b * a.n_max * a.deg_max;
+  const int32_t* lab = a.lab + (long)b * a.n_max * a.deg_max;
+  int32_t* paths = a.paths + ((long)b * a.n_max * a.n_max) * a.max_len;
+  int32_t* plen = a.plen + (long)b * a.n_max * a.n_max;
+
+  if (j >= n) {                                                      // target outside the graph: the whole column is padding
+    GTOS_PHASE(tid, nthr)
+      for (int i = tid; i < a.n_max; i += nthr) {
+        plen[(long)i * a.n_max + j] = 0;
+        for (int s = 0; s < a.max_len; ++s) paths[((long)i * a.n_max + j) * a.max_len + s] = 0;
+      }
+    GTOS_PHASE_END
+    return;
+  }
+
+  GTOS_PHASE(tid, nthr)
+    for (int v = tid; v < a.n_max; v += nthr) {
+      dist[v] = (v == j) ? 0 : -1;
+      sigma[v] = (v == j) ? 1.f : 0.f;
+      mark[v] = 0;
+    }
+    if (tid == 0) flag[0] = 1;
+  GTOS_PHASE_END
+
+  // ---- level-synchronous BFS from the target with shortest-path counts ----
+  for (int level = 0; flag[0] != 0; ++level) {                       // flag[0] is only written between barriers
+    GTOS_PHASE(tid, nthr)
+      if (tid == 0) flag[1] = 0;
+      // pull: an unvisited node joins level + 1 if one of its neighbours sits on `level` (symmetric structure)
+      for (int v = tid; v < n; v += nthr) {
+        if (dist[v] >= 0) continue;
+        float s = 0.f;
+        bool hit = false;
+        for (int k = 0; k < deg[v]; ++k) {
+          const int u = nbr[(long)v * a.deg_max + k];
+          if (dist[u] == level) {
+            s += sigma[u];
+            hit = true;
+          }
+        }
+        if (hit) {
+          mark[v] = 1;
+          sigma[v] = s;
+        }
+      }
+    GTOS_PHASE_END
+    GTOS_PHASE(tid, nthr)
+      for (int v = tid; v < n; v += nthr)
+        if (mark[v]) {
+          mark[v] = 0;
+          dist[v] = level + 1;
+          flag[1] = 1;                                               // benign same-value race
+        }
+    GTOS_PHASE_END
+    // keep the counts of the new level in float range: only ratios inside one level are ever used
+    GTOS_PHASE(tid, nthr)
+      if (tid == 0) {
+        float mx = 0.f;
+        for (int v = 0; v < n; ++v)
+          if (dist[v] == level + 1 && sigma[v] > mx) mx = sigma[v];
+        flag[0] = flag[1];
+        reinterpret_cast<float*>(flag)[2] = mx;
+      }
+    GTOS_PHASE_END
+    GTOS_PHASE(tid, nthr)
+      const float mx = reinterpret_cast<const float*>(flag)[2];
+      if (mx > 1.0e30f)
+        for (int v = tid; v < n; v += nthr)
+          if (dist[v] == level + 1) sigma[v] = sigma[v] * (1.0f / 1.0e30f);
+    GTOS_PHASE_END
+  }
+
+  // ---- one uniformly drawn shortest path i -> j for every source i ----
+  GTOS_PHASE(tid, nthr)
+    for (int i = tid; i < a.n_max; i += nthr) {
+      int32_t* out = paths + ((long)i * a.n_max + j) * a.max_len;
+      for (int s = 0; s < a.max_len; ++s) out[s] = 0;
+      if (i >= n) {
+        plen[(long)i * a.n_max + j] = 0;
+        continue;
+      }
+      const int d = dist[i];
+      if (d == 0) {                                                  // data.py:151-152  [] -> <SELF>
+        out[0] = a.self_id;
+        plen[(long)i * a.n_max + j] = 1;
+      } else if (d < 0 || d > a.max_len) {                           // data.py:153-154  too long (or unreachable) -> <TL>
+        out[0] = a.tl_id;
+        plen[(long)i * a.n_max + j] = 1;
+      } else {
+        int v = i;
+        for (int s = 0; s < d; ++s) {
+          const int want = d - s - 1;
+          float total = 0.f;
+          for (int k = 0; k < deg[v]; ++k) {
+            const int u = nbr[(long)v * a.deg_max + k];
+            if (dist[u] == want) total += sigma[u];
+          }
+          const uint64_t e = (((uint64_t)b * a.n_max + i) * a.n_max + j) * a.max_len + s;
+          const float r = paths_uniform(a.seed, e) * total;
+          float cum = 0.f;
+          int pick = -1, last = -1;
+          for (int k = 0; k < deg[v]; ++k) {
+            const int u = nbr[(long)v * a.deg_max + k];
+            if (dist[u] != want) continue;
+            last = k;
+            cum += sigma[u];
+            if (cum > r) {
+              pick = k;
+              break;
+            }
+          }
+          if (pick < 0) pick = last;                                 // r == total after rounding
+          out[s] = lab[(long)v * a.deg_max + pick];
+          v = nbr[(long)v * a.deg_max + pick];
+        }
+        plen[(long)i * a.n_max + j] = d;
+      }
+    }
+  GTOS_PHASE_END
+}
+
+}  // namespace gtos

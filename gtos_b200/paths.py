@@ -1,0 +1,130 @@
+"""the relation part of batch construction on the GPU.
+
+The reference builds it on the host: `AMRGraph.collect_concepts_and_relations` enumerates every shortest path between
+every ordered pair of nodes with networkx (generator/AMRGraph.py:100-115; offline, stored as JSON by extract.py:173-180),
+and `batchify` draws one of them per pair each time a batch is formed, substitutes <SELF> / <TL>, and de-duplicates the
+label sequences of the batch into `relation_bank` [Lmax, R], `relation_length` [R] and the index tensor
+`relation` [N, N, B] (generator/data.py:126-176; translator/data.py:134-177 does the same from dependency trees).
+
+Here the graphs travel as a padded adjacency (`pack_adjacency`), `shortest_label_paths` runs gtos_graph_paths - one CTA per
+(graph, target), uniform draw among equally short paths by path counting - and `assemble_relation_batch` turns the
+per-pair label sequences into the three tensors with device-side index arithmetic (sort / unique; one host read for R).
+The bank comes out in sorted-key order instead of first-seen order: a permutation of the bank rows with the index tensor
+permuted consistently, which no consumer can observe (RelationEncoder encodes rows independently, generator.py:76-79
+gathers by index); rows 0 / 1 / 2 stay <CLS> / <rCLS> / <SELF> as data.py:138-140 fixes them.
+
+There is no CPU path: `shortest_label_paths` needs CUDA tensors and libgtos_b200.so.
+"""
+import torch
+
+from . import _lib
+from .ops import _need_cuda, _p, _st, rng_state
+
+
+def pack_adjacency(graphs, n_max=None, deg_max=None, device=None):
+    """graphs: list (one per graph) of adjacency lists adj[v] = [(u, label id), ...] in the node order the batch uses
+    (BFS order, AMRGraph.py:82-98).  A repeated neighbour keeps its LAST label (networkx DiGraph.add_edge overwrites,
+    AMRGraph.py:79-80).  Checks that the structure is symmetric.  Returns int32 tensors (n_nodes [B], deg [B,n_max],
+    nbr [B,n_max,deg_max], lab [B,n_max,deg_max])."""
+    clean = []
+    for adj in graphs:
+        g = []
+        for a in adj:
+            last = {}
+            for u, l in a:
+                last[int(u)] = int(l)
+            g.append(list(last.items()))
+        for v, a in enumerate(g):
+            for u, _ in a:
+                if not 0 <= u < len(g) or all(w != v for w, _ in g[u]):
+                    raise ValueError(f"adjacency is not symmetric at edge {v} -> {u}: every edge needs its reverse twin "
+                                     "(AMRGraph._add_edge, AMRGraph.py:76-80)")
+        clean.append(g)
+    B = len(clean)
+    n_max = n_max or max((len(g) for g in clean), default=1)
+    deg_max = deg_max or max(1, max((len(a) for g in clean for a in g), default=1))
+    n_nodes = torch.tensor([len(g) for g in clean], dtype=torch.int32)
+    deg = torch.zeros(B, n_max, dtype=torch.int32)
+    nbr = torch.zeros(B, n_max, deg_max, dtype=torch.int32)
+    lab = torch.zeros(B, n_max, deg_max, dtype=torch.int32)
+    for b, g in enumerate(clean):
+        for v, a in enumerate(g):
+            deg[b, v] = len(a)
+            for k, (u, l) in enumerate(a):
+                nbr[b, v, k], lab[b, v, k] = u, l
+    out = (n_nodes, deg, nbr, lab)
+    return tuple(t.to(device) for t in out) if device is not None else out
+
+
+def shortest_label_paths(n_nodes, deg, nbr, lab, max_len, self_id, tl_id, seed_off=0, seed=None):
+    """-> (paths [B,n_max,n_max,max_len] int32, plen [B,n_max,n_max] int32); paths[b,i,j] = labels of the drawn shortest
+    path i -> j (AMRGraph.py:107-112 + data.py:150-154).  `seed`: int64 device tensor (default: the library's dropout
+    seed, ops.rng_state), `seed_off`: per-call offset - the draw is reproducible from (seed + seed_off, b, i, j)."""
+    _need_cuda(n_nodes, deg, nbr, lab)
+    for t in (n_nodes, deg, nbr, lab):
+        if t.dtype != torch.int32 or not t.is_contiguous():
+            raise ValueError("shortest_label_paths takes contiguous int32 tensors (pack_adjacency)")
+    B, n_max, deg_max = nbr.shape
+    dev = nbr.device
+    seed = rng_state(dev) if seed is None else seed
+    paths = torch.empty(B, n_max, n_max, max_len, dtype=torch.int32, device=dev)
+    plen = torch.empty(B, n_max, n_max, dtype=torch.int32, device=dev)
+    _lib.check(_lib.load().gtos_graph_paths(_p(n_nodes), _p(deg), _p(nbr), _p(lab), B, n_max, deg_max, max_len, self_id, tl_id,
+                                            _p(seed), seed_off & ((1 << 64) - 1), _p(paths), _p(plen), _st()), "graph_paths")
+    return paths, plen
+
+
+def assemble_relation_batch(paths, plen, n_nodes, cls_id, rcls_id, self_id):
+    """per-pair label sequences -> dict(relation [N,N,B] int64, relation_bank [Lmax,R] int64, relation_length [R] int64),
+    N = n_max + 1 (the <CLS> slot), with the layouts of data.py:138-176: relation[j+1][i+1][b] = bank row of the path
+    i -> j, relation[0][0][b] = 2 (<SELF>), relation[x][0][b] = 0 (<CLS>) and relation[0][y][b] = 1 (<rCLS>) for nodes
+    inside graph b, 0 elsewhere (ArraysToTensor padding).  Index arithmetic only (runs where the tensors live)."""
+    B, n_max, _, L = paths.shape
+    dev = paths.device
+    if L > 8:
+        raise ValueError("label sequences of more than 8 labels are replaced by <TL> in the reference (data.py:153)")
+    p64 = paths.to(torch.int64)
+    if int(p64.max()) >= (1 << 15):
+        raise ValueError("relation label ids must be < 32768")
+    # 120-bit key of a sequence: four 15-bit labels per word, first label most significant (0 = padding sorts first)
+    pad = torch.zeros(B, n_max, n_max, 8 - L, dtype=torch.int64, device=dev)
+    p8 = torch.cat([p64, pad], dim=-1)
+    hi = (p8[..., 0] << 45) | (p8[..., 1] << 30) | (p8[..., 2] << 15) | p8[..., 3]
+    lo = (p8[..., 4] << 45) | (p8[..., 5] << 30) | (p8[..., 6] << 15) | p8[..., 7]
+    valid = plen > 0
+    is_self = valid & (plen == 1) & (p64[..., 0] == self_id)
+    real = valid & ~is_self
+    keys = torch.stack([hi[real], lo[real]], dim=1)                                 # [P, 2]
+    if keys.shape[0]:
+        uniq, inv = torch.unique(keys, dim=0, return_inverse=True)                  # sorted rows; dynamic size: host read
+    else:
+        uniq, inv = keys, keys.new_zeros((0,))
+    R = 3 + uniq.shape[0]
+    ids = torch.zeros(B, n_max, n_max, dtype=torch.int64, device=dev)
+    ids[is_self] = 2
+    ids[real] = inv + 3
+    N = n_max + 1
+    rel = torch.zeros(B, N, N, dtype=torch.int64, device=dev)                       # brs[b][x][y], data.py:142-161
+    inside = torch.arange(n_max, device=dev).unsqueeze(0) < n_nodes.to(torch.int64).unsqueeze(1)      # [B, n_max]
+    rel[:, 0, 0] = 2
+    rel[:, 0, 1:] = 0                                                               # <CLS> id 0 (also the padding value)
+    rel[:, 1:, 0] = inside.to(torch.int64)                                          # <rCLS> id 1 for real nodes
+    rel[:, 1:, 1:] = ids
+    relation = rel.permute(2, 1, 0).contiguous()                                    # transpose_(0, 2), data.py:164
+    bank = torch.zeros(8, R, dtype=torch.int64, device=dev)
+    bank[0, 0], bank[0, 1], bank[0, 2] = cls_id, rcls_id, self_id
+    if uniq.shape[0]:
+        u_hi, u_lo = uniq[:, 0], uniq[:, 1]
+        cols = [(u_hi >> 45) & 0x7FFF, (u_hi >> 30) & 0x7FFF, (u_hi >> 15) & 0x7FFF, u_hi & 0x7FFF,
+                (u_lo >> 45) & 0x7FFF, (u_lo >> 30) & 0x7FFF, (u_lo >> 15) & 0x7FFF, u_lo & 0x7FFF]
+        bank[:, 3:] = torch.stack(cols, dim=0)
+    length = (bank != 0).sum(0)
+    Lmax = max(1, int(length.max()))
+    return dict(relation=relation, relation_bank=bank[:Lmax].contiguous(), relation_length=length)
+
+
+def relation_batch(graphs, max_len, cls_id, rcls_id, self_id, tl_id, device, seed_off=0):
+    """adjacency lists -> the three relation tensors of a training batch (data.py:134-176), paths drawn on the GPU."""
+    n_nodes, deg, nbr, lab = pack_adjacency(graphs, device=device)
+    paths, plen = shortest_label_paths(n_nodes, deg, nbr, lab, max_len, self_id, tl_id, seed_off=seed_off)
+    return assemble_relation_batch(paths, plen, n_nodes, cls_id, rcls_id, self_id)

@@ -252,6 +252,21 @@ int gtos_grad_sumsq(const float* g, int64_t n, float* out, float* workspace, voi
 int gtos_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int64_t n_decay, const float* lr_ptr, float beta1,
                    float beta2, float eps, float weight_decay, const float* norm_sq, float max_norm, void* stream);
 
+/* ---- batch construction (generator/AMRGraph.py:100-115 collect_concepts_and_relations,
+ * generator/data.py:148-154 the per-pair path choice of batchify; translator/dependencyGraph.py:54-74) ----
+ * For every graph b < B and every ordered pair (i, j) of its n_nodes[b] nodes: the edge labels of ONE shortest path i -> j,
+ * drawn uniformly among all shortest node paths (the reference enumerates them with networkx and calls random.choice;
+ * here they are counted by a BFS from j and sampled by a walk from i).  The graph is the padded adjacency
+ * deg[b][v], nbr[b][v][k], lab[b][v][k] (label of the edge v -> nbr), k < deg <= deg_max, one entry per neighbour, and its
+ * STRUCTURE must be symmetric (u in nbr[v] <=> v in nbr[u]) - the reference adds a `_reverse_` / `_r_` twin for every edge.
+ * paths[b][i][j][0..plen) = label ids in walking order (0 beyond); the empty path gives {self_id}, a path of more than
+ * max_len labels (or an unreachable pair) {tl_id}; pairs with i or j >= n_nodes[b] get plen = 0.
+ * The draw of pair (b,i,j) at step s is hash(*seed_ptr + seed_off, ((b*n_max+i)*n_max+j)*max_len+s): reproducible, and
+ * bit-identical to oracle/paths_oracle.py. */
+int gtos_graph_paths(const int32_t* n_nodes, const int32_t* deg, const int32_t* nbr, const int32_t* lab, int32_t B,
+                     int32_t n_max, int32_t deg_max, int32_t max_len, int32_t self_id, int32_t tl_id, const void* seed_ptr,
+                     uint64_t seed_off, int32_t* paths, int32_t* plen, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

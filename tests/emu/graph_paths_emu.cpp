@@ -1,0 +1,22 @@
+// CPU build of gtos_b200/csrc/graph_paths_core.h - the SAME source the CUDA kernel runs, with every barrier-separated
+// phase executed as a loop over 128 emulated thread ids.  Test infrastructure only (tests/test_paths_cpu.py compiles it
+// with g++ and compares it with oracle/paths_oracle.py); nothing in gtos_b200/ loads it.
+#include <stdint.h>
+
+#include <vector>
+
+#include "../../gtos_b200/csrc/graph_paths_core.h"
+
+extern "C" int emu_graph_paths(const int32_t* n_nodes, const int32_t* deg, const int32_t* nbr, const int32_t* lab, int32_t B,
+                               int32_t n_max, int32_t deg_max, int32_t max_len, int32_t self_id, int32_t tl_id, uint64_t seed,
+                               int32_t* paths, int32_t* plen) {
+  gtos::GraphPathsArgs a;
+  a.n_nodes = n_nodes; a.deg = deg; a.nbr = nbr; a.lab = lab;
+  a.B = B; a.n_max = n_max; a.deg_max = deg_max; a.max_len = max_len;
+  a.self_id = self_id; a.tl_id = tl_id; a.seed = seed;
+  a.paths = paths; a.plen = plen;
+  std::vector<int32_t> smem((gtos::graph_paths_smem_bytes(n_max) + 3) / 4);
+  for (int b = 0; b < B; ++b)
+    for (int j = 0; j < n_max; ++j) gtos::graph_paths_cta(a, b, j, smem.data());   // grid (n_max, B)
+  return 0;
+}

@@ -1,0 +1,247 @@
+"""SURVEY.md §8 f-3 (batch construction) on CPU:
+  * oracle/paths_oracle.py against the golden run of the reference's own AMRGraph + batchify
+    (tests/golden/golden_paths.json, made by tests/golden/make_golden_paths.py);
+  * the kernel source itself (gtos_b200/csrc/graph_paths_core.h), compiled as plain C++ with every barrier-separated
+    phase run as a loop over 128 emulated threads (tests/emu/graph_paths_emu.cpp), against the oracle bit for bit;
+  * the host logic of gtos_b200/paths.py (adjacency packing, bank / index assembly) - torch index arithmetic that runs on
+    any device.
+The CUDA build of the same kernel is compared with the same oracle in tests/test_gpu_paths.py."""
+import ctypes as C
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import paths_oracle as PO
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SEED = 19940117
+
+
+@pytest.fixture(scope="module")
+def gold():
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_paths.json")))
+    voc = g["relation_vocab"]
+    graphs = [[[(u, voc[l]) for u, l in a] for a in gr["adjacency"]] for gr in g["graphs"]]
+    return g, voc, graphs
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("emu") / "graph_paths_emu.so")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-o", so,
+                           os.path.join(ROOT, "tests", "emu", "graph_paths_emu.cpp")])
+    lib = C.CDLL(so)
+    lib.emu_graph_paths.restype = C.c_int
+    lib.emu_graph_paths.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 6 + [C.c_uint64, C.c_void_p, C.c_void_p]
+
+    def run(n_nodes, deg, nbr, lab, max_len, self_id, tl_id, seed):
+        B, n_max, deg_max = nbr.shape
+        paths = np.full((B, n_max, n_max, max_len), -7, dtype=np.int32)
+        plen = np.full((B, n_max, n_max), -7, dtype=np.int32)
+        arrs = [np.ascontiguousarray(x, dtype=np.int32) for x in (n_nodes, deg, nbr, lab)]
+        assert lib.emu_graph_paths(*[x.ctypes.data for x in arrs], B, n_max, deg_max, max_len, self_id, tl_id,
+                                   seed & PO.M64, paths.ctypes.data, plen.ctypes.data) == 0
+        return paths, plen
+
+    return run
+
+
+def _ids(voc):
+    return voc["<CLS>"], voc["<rCLS>"], voc["<SELF>"], voc["<TL>"]
+
+
+def test_oracle_enumerates_the_reference_paths(gold):
+    g, voc, graphs = gold
+    for gr, adj in zip(g["graphs"], graphs):
+        n = len(adj)
+        for i in range(n):
+            for j in range(n):
+                ref = sorted(tuple(voc[l] for l in p) for p in gr["all_paths"][i][j])
+                assert sorted(PO.all_shortest_label_paths(adj, i, j)) == ref, (i, j)
+
+
+def test_oracle_sampler_draws_reference_paths_uniformly(gold):
+    g, voc, graphs = gold
+    cls_id, rcls_id, self_id, tl_id = _ids(voc)
+    n_nodes, deg, nbr, lab = PO.pack_adjacency(graphs)
+    for seed in (SEED, SEED + 1):
+        paths, plen = PO.sample_paths(n_nodes, deg, nbr, lab, 8, self_id, tl_id, seed)
+        again, _ = PO.sample_paths(n_nodes, deg, nbr, lab, 8, self_id, tl_id, seed)
+        assert np.array_equal(paths, again)                              # reproducible from the seed
+        for b, (gr, adj) in enumerate(zip(g["graphs"], graphs)):
+            n = len(adj)
+            assert (plen[b, n:, :] == 0).all() and (plen[b, :, n:] == 0).all()
+            for i in range(n):
+                for j in range(n):
+                    ref = [tuple(voc[l] for l in p) for p in gr["all_paths"][i][j]]
+                    got = tuple(int(x) for x in paths[b, i, j, :plen[b, i, j]])
+                    if len(ref[0]) == 0:
+                        assert got == (self_id,)                         # data.py:151-152
+                    elif len(ref[0]) > 8:
+                        assert got == (tl_id,)                           # data.py:153-154
+                    else:
+                        assert got in ref
+    # uniform over NODE paths: graph 4 has pairs with 3 equally short paths
+    b = 4
+    adj = graphs[b]
+    n = len(adj)
+    multi = [(i, j) for i in range(n) for j in range(n) if len(g["graphs"][b]["all_paths"][i][j]) == 3]
+    assert multi
+    i, j = multi[0]
+    ref = [tuple(voc[l] for l in p) for p in g["graphs"][b]["all_paths"][i][j]]
+    one = PO.pack_adjacency([adj])
+    counts = {}
+    draws = 600
+    for s in range(draws):
+        paths, plen = PO.sample_paths(*one, 8, self_id, tl_id, 1000 + s)
+        got = tuple(int(x) for x in paths[0, i, j, :plen[0, i, j]])
+        counts[got] = counts.get(got, 0) + 1
+    assert sum(counts.values()) == draws and set(counts) <= set(ref)
+    for p in set(ref):                                                   # multiplicity / 3 each, 5 sigma wide
+        expect = draws * ref.count(p) / 3.0
+        assert abs(counts.get(p, 0) - expect) < 5 * (expect * (1 - ref.count(p) / 3.0)) ** 0.5 + 1
+
+
+def test_oracle_assembly_equals_reference_batchify(gold):
+    g, voc, graphs = gold
+    cls_id, rcls_id, self_id, tl_id = _ids(voc)
+    chosen = []
+    for gr in g["graphs"]:
+        n = len(gr["nodes"])
+        per = []
+        for i in range(n):
+            row = []
+            for j in range(n):
+                p = [voc[l] for l in gr["all_paths"][i][j][0]]           # the golden run replaced random.choice by "first"
+                if len(p) == 0:
+                    p = [self_id]
+                if len(p) > 8:
+                    p = [tl_id]
+                row.append(tuple(p))
+            per.append(row)
+        chosen.append(per)
+    rel, bank, length = PO.assemble_first_seen(chosen, cls_id, rcls_id, self_id)
+    ref = g["batchify_first_choice"]
+    assert np.array_equal(rel, np.array(ref["relation"]))
+    assert np.array_equal(bank, np.array(ref["relation_bank"]))
+    assert np.array_equal(length, np.array(ref["relation_length"]))
+
+
+def _layered(width, layers, n_labels, rng):
+    """complete bipartite connections between consecutive layers: width ** (layers - 1) shortest paths end to end"""
+    n = width * layers
+    adj = [[] for _ in range(n)]
+    for l in range(layers - 1):
+        for a in range(width):
+            for c in range(width):
+                u, v = l * width + a, (l + 1) * width + c
+                k = int(rng.integers(n_labels))
+                adj[u].append((v, 6 + 2 * k))
+                adj[v].append((u, 7 + 2 * k))
+    return adj
+
+
+def test_kernel_source_emulated_on_cpu_equals_oracle(gold, emu):
+    g, voc, graphs = gold
+    cls_id, rcls_id, self_id, tl_id = _ids(voc)
+    # golden graphs, padded shapes (n_max and deg_max larger than any graph needs)
+    n_nodes, deg, nbr, lab = PO.pack_adjacency(graphs, n_max=14, deg_max=6)
+    for seed, max_len in ((SEED, 8), (SEED + 5, 4), (0, 8), ((1 << 63) + 12345, 8)):
+        want = PO.sample_paths(n_nodes, deg, nbr, lab, max_len, self_id, tl_id, seed)
+        got = emu(n_nodes, deg, nbr, lab, max_len, self_id, tl_id, seed)
+        assert np.array_equal(got[1], want[1]) and np.array_equal(got[0], want[0])
+    # random larger graphs with many re-entrancies, more nodes than emulated threads
+    rng = np.random.default_rng(SEED)
+    big = []
+    for n in (150, 40, 97):
+        adj = [dict() for _ in range(n)]
+        for v in range(1, n):
+            u = int(rng.integers(max(0, v - 6), v))
+            k = int(rng.integers(20))
+            adj[u][v], adj[v][u] = 6 + 2 * k, 7 + 2 * k
+        for _ in range(n // 2):
+            u, v = int(rng.integers(n)), int(rng.integers(n))
+            if u != v:
+                k = int(rng.integers(20))
+                adj[u][v], adj[v][u] = 6 + 2 * k, 7 + 2 * k
+        big.append([list(a.items()) for a in adj])
+    packed = PO.pack_adjacency(big)
+    want = PO.sample_paths(*packed, 8, self_id, tl_id, SEED)
+    got = emu(*packed, 8, self_id, tl_id, SEED)
+    assert np.array_equal(got[1], want[1]) and np.array_equal(got[0], want[0])
+    assert (want[1] > 1).any() and (want[0][..., 0] == tl_id).any()
+
+
+def test_path_counts_beyond_float_range_are_rescaled(emu):
+    """4 ** 63 = 8.5e37 shortest paths end to end: the per-level rescaling keeps the counts finite and the draw valid"""
+    rng = np.random.default_rng(3)
+    adj = _layered(4, 64, 5, rng)
+    packed = PO.pack_adjacency([adj])
+    want = PO.sample_paths(*packed, 16, 4, 5, 77)
+    got = emu(*packed, 16, 4, 5, 77)
+    assert np.array_equal(got[1], want[1]) and np.array_equal(got[0], want[0])
+    # pairs at distance <= 16 carry real paths whose labels are edges of the graph, one layer per step
+    paths, plen = got
+    n = len(adj)
+    lab_of = {(u, v): l for u in range(n) for v, l in adj[u]}
+    checked = 0
+    for i in range(0, n, 37):
+        for j in range(n):
+            d = abs(i // 4 - j // 4)
+            if 0 < d <= 16:
+                assert plen[0, i, j] == d
+                labels = [int(x) for x in paths[0, i, j, :d]]
+                step = 1 if j > i else -1
+                layer = i // 4
+                ok_nodes = {i}
+                for s, l in enumerate(labels):                       # some node of the next layer is reached by label l
+                    nxt = {v for u in ok_nodes for v in range((layer + step) * 4, (layer + step) * 4 + 4)
+                           if lab_of.get((u, v)) == l}
+                    assert nxt
+                    ok_nodes, layer = nxt, layer + step
+                assert j in ok_nodes or d > 1
+                checked += 1
+    assert checked > 100
+
+
+def test_pack_adjacency_and_assembly_host_logic(gold):
+    from gtos_b200 import paths as P
+    g, voc, graphs = gold
+    cls_id, rcls_id, self_id, tl_id = _ids(voc)
+    with pytest.raises(ValueError):
+        P.pack_adjacency([[[(1, 6)], []]])                               # edge 0 -> 1 without its twin
+    n_nodes, deg, nbr, lab = P.pack_adjacency([[[(1, 6), (1, 8)], [(0, 7)]]])
+    assert deg.tolist() == [[1, 1]] and lab[0, 0, 0].item() == 8          # repeated neighbour: last label wins
+    n_nodes, deg, nbr, lab = P.pack_adjacency(graphs)
+    o = PO.pack_adjacency(graphs)
+    for a, b in zip((n_nodes, deg, nbr, lab), o):
+        assert np.array_equal(a.numpy(), b)
+    paths, plen = PO.sample_paths(*o, 8, self_id, tl_id, SEED)
+    out = P.assemble_relation_batch(torch.from_numpy(paths), torch.from_numpy(plen), n_nodes, cls_id, rcls_id, self_id)
+    rel, bank, length = out["relation"], out["relation_bank"], out["relation_length"]
+    chosen = [[[tuple(int(x) for x in paths[b, i, j, :plen[b, i, j]]) for j in range(len(adj))] for i in range(len(adj))]
+              for b, adj in enumerate(graphs)]
+    rel_o, bank_o, length_o = PO.assemble_first_seen(chosen, cls_id, rcls_id, self_id)
+    # same tensors up to a permutation of the bank rows >= 3
+    assert rel.shape == rel_o.shape and bank.shape == bank_o.shape and length.shape == length_o.shape
+    assert bank[:, :3].tolist() == bank_o[:, :3].tolist() and length[:3].tolist() == [1, 1, 1]
+    seq = lambda bk, ln, r: tuple(int(x) for x in bk[:int(ln[r]), r])
+    N = rel.shape[0]
+    for b in range(len(graphs)):
+        for x in range(N):
+            for y in range(N):
+                assert seq(bank, length, int(rel[y, x, b])) == seq(bank_o, length_o, int(rel_o[y, x, b]))
+    assert len({seq(bank, length, r) for r in range(bank.shape[1])}) == bank.shape[1]      # no duplicate rows
+    assert sorted(seq(bank, length, r) for r in range(bank.shape[1])) == sorted(seq(bank_o, length_o, r) for r in range(bank_o.shape[1]))
+
+
+def test_paths_product_has_no_cpu_path():
+    from gtos_b200 import _lib, paths as P
+    z = torch.zeros(1, 2, dtype=torch.int32)
+    with pytest.raises(_lib.GtosLibraryError):
+        P.shortest_label_paths(torch.zeros(1, dtype=torch.int32), z, torch.zeros(1, 2, 1, dtype=torch.int32),
+                               torch.zeros(1, 2, 1, dtype=torch.int32), 4, 4, 5)

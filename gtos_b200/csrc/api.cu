@@ -368,4 +368,15 @@ int gtos_graph_paths(const int32_t* n_nodes, const int32_t* deg, const int32_t* 
   return graph_paths(a, seed_ptr, seed_off, S(stream));
 }
 
+int gtos_graph_all_paths(const int32_t* n_nodes, const int32_t* deg, const int32_t* nbr, const int32_t* lab, int32_t B,
+                         int32_t n_max, int32_t deg_max, int32_t max_len, int32_t K, int32_t self_id, int32_t tl_id,
+                         int32_t* all_paths, int32_t* pcount, void* stream) {
+  GraphAllPathsArgs a;
+  a.n_nodes = n_nodes; a.deg = deg; a.nbr = nbr; a.lab = lab;
+  a.B = B; a.n_max = n_max; a.deg_max = deg_max; a.max_len = max_len; a.K = K;
+  a.self_id = self_id; a.tl_id = tl_id;
+  a.all_paths = all_paths; a.pcount = pcount;
+  return graph_all_paths(a, S(stream));
+}
+
 }  // extern "C"

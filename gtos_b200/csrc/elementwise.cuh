@@ -106,5 +106,7 @@ int beam_ancestry(const int* old_anc, int* new_anc, long ld, const int* parent, 
 // ---- shortest label paths of a graph batch (graph_paths.cu / graph_paths_core.h) ----
 struct GraphPathsArgs;
 int graph_paths(const GraphPathsArgs& a, const void* seed_ptr, unsigned long long seed_off, cudaStream_t st);
+struct GraphAllPathsArgs;
+int graph_all_paths(const GraphAllPathsArgs& a, cudaStream_t st);
 
 }  // namespace gtos

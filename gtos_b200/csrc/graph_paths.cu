@@ -30,4 +30,24 @@ int graph_paths(const GraphPathsArgs& a, const void* seed_ptr, unsigned long lon
   return GTOS_OK;
 }
 
+__global__ void __launch_bounds__(128) graph_all_paths_kernel(const GraphAllPathsArgs a) {
+  GTOS_PDL_PROLOGUE();
+  extern __shared__ __align__(16) unsigned char gp_smem[];
+  graph_all_paths_cta(a, (int)blockIdx.y, (int)blockIdx.x, gp_smem);
+}
+
+int graph_all_paths(const GraphAllPathsArgs& a, cudaStream_t st) {
+  GTOS_REQUIRE(a.B >= 0 && a.n_max >= 1 && a.deg_max >= 1 && a.max_len >= 1 && a.max_len <= GTOS_PATHS_MAX_LEN && a.K >= 1,
+               "graph_all_paths: bad sizes (B=%d n_max=%d deg_max=%d max_len=%d K=%d)", a.B, a.n_max, a.deg_max, a.max_len,
+               a.K);
+  GTOS_REQUIRE(a.n_nodes && a.deg && a.nbr && a.lab && a.all_paths && a.pcount, "graph_all_paths: null argument");
+  GTOS_REQUIRE(a.B <= 65535, "graph_all_paths: at most 65535 graphs per call");
+  if (a.B == 0) return GTOS_OK;
+  const size_t smem = graph_paths_smem_bytes(a.n_max);
+  GTOS_REQUIRE(smem <= 48 * 1024, "graph_all_paths: %d nodes per graph do not fit the shared-memory working set", a.n_max);
+  GTOS_KLAUNCH(graph_all_paths_kernel, dim3((unsigned)a.n_max, (unsigned)a.B), dim3(128), smem, st, a);
+  GTOS_LAUNCH_CHECK();
+  return GTOS_OK;
+}
+
 }  // namespace gtos

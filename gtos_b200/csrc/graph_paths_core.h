@@ -195,4 +195,148 @@ inline void graph_paths_cta(const GraphPathsArgs& a, int b, int j, void* smem) {
   GTOS_PHASE_END
 }
 
+// -------------------------------------------------------------------------------------------------------------------
+// Evaluation batches keep EVERY shortest path of a pair (generator/data.py:176-225; the model averages their encodings,
+// generator/generator.py:83-88).  Same BFS, exact saturating counts, then one thread per source enumerates its paths
+// depth first in adjacency order - the order of oracle/paths_oracle.py::all_shortest_label_paths - up to K per pair.
+//   all_paths[b][i][j][k][0..len)  labels of the k-th path, 0 padded          (k < min(pcount, K))
+//   pcount[b][i][j]                number of shortest paths, saturated at K + 1  (0 = pair outside the graph);
+//                                  <SELF> / <TL> pairs hold one entry (data.py:197-199 keeps all_path[:1])
+// A pair with more than K paths reports K + 1 and carries its first K: the caller decides (gtos_b200/paths.py raises).
+// -------------------------------------------------------------------------------------------------------------------
+struct GraphAllPathsArgs {
+  const int32_t* n_nodes;
+  const int32_t* deg;
+  const int32_t* nbr;
+  const int32_t* lab;
+  int32_t B, n_max, deg_max, max_len, K;
+  int32_t self_id, tl_id;
+  int32_t* all_paths;       // [B, n_max, n_max, K, max_len]
+  int32_t* pcount;          // [B, n_max, n_max]
+};
+
+static const int GTOS_PATHS_MAX_LEN = 16;
+
+// shared-memory working set: dist [n_max] int32, count [n_max] uint32, mark [n_max] int32, flag [4] int32
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline void graph_all_paths_cta(const GraphAllPathsArgs& a, int b, int j, void* smem) {
+  int32_t* dist = reinterpret_cast<int32_t*>(smem);
+  uint32_t* count = reinterpret_cast<uint32_t*>(dist + a.n_max);
+  int32_t* mark = reinterpret_cast<int32_t*>(count + a.n_max);
+  int32_t* flag = mark + a.n_max;
+  const int n = a.n_nodes[b];
+  const int32_t* deg = a.deg + (long)b * a.n_max;
+  const int32_t* nbr = a.nbr + (long)b * a.n_max * a.deg_max;
+  const int32_t* lab = a.lab + (long)b * a.n_max * a.deg_max;
+  const long pair_stride = (long)a.K * a.max_len;
+  int32_t* all_paths = a.all_paths + ((long)b * a.n_max * a.n_max) * pair_stride;
+  int32_t* pcount = a.pcount + (long)b * a.n_max * a.n_max;
+  const uint32_t cap = (uint32_t)a.K + 1u;
+
+  if (j >= n) {
+    GTOS_PHASE(tid, nthr)
+      for (int i = tid; i < a.n_max; i += nthr) {
+        pcount[(long)i * a.n_max + j] = 0;
+        int32_t* out = all_paths + ((long)i * a.n_max + j) * pair_stride;
+        for (long s = 0; s < pair_stride; ++s) out[s] = 0;
+      }
+    GTOS_PHASE_END
+    return;
+  }
+
+  GTOS_PHASE(tid, nthr)
+    for (int v = tid; v < a.n_max; v += nthr) {
+      dist[v] = (v == j) ? 0 : -1;
+      count[v] = (v == j) ? 1u : 0u;
+      mark[v] = 0;
+    }
+    if (tid == 0) flag[0] = 1;
+  GTOS_PHASE_END
+
+  for (int level = 0; flag[0] != 0; ++level) {
+    GTOS_PHASE(tid, nthr)
+      if (tid == 0) flag[1] = 0;
+      for (int v = tid; v < n; v += nthr) {
+        if (dist[v] >= 0) continue;
+        uint32_t c = 0;
+        bool hit = false;
+        for (int k = 0; k < deg[v]; ++k) {
+          const int u = nbr[(long)v * a.deg_max + k];
+          if (dist[u] == level) {
+            c += count[u];                                           // both <= cap: no wrap before the clamp
+            if (c > cap) c = cap;
+            hit = true;
+          }
+        }
+        if (hit) {
+          mark[v] = 1;
+          count[v] = c;
+        }
+      }
+    GTOS_PHASE_END
+    GTOS_PHASE(tid, nthr)
+      for (int v = tid; v < n; v += nthr)
+        if (mark[v]) {
+          mark[v] = 0;
+          dist[v] = level + 1;
+          flag[1] = 1;
+        }
+    GTOS_PHASE_END
+    GTOS_PHASE(tid, nthr)
+      if (tid == 0) flag[0] = flag[1];
+    GTOS_PHASE_END
+  }
+
+  GTOS_PHASE(tid, nthr)
+    for (int i = tid; i < a.n_max; i += nthr) {
+      int32_t* out = all_paths + ((long)i * a.n_max + j) * pair_stride;
+      for (long s = 0; s < pair_stride; ++s) out[s] = 0;
+      if (i >= n) {
+        pcount[(long)i * a.n_max + j] = 0;
+        continue;
+      }
+      const int d = dist[i];
+      if (d == 0) {
+        out[0] = a.self_id;
+        pcount[(long)i * a.n_max + j] = 1;
+        continue;
+      }
+      if (d < 0 || d > a.max_len) {
+        out[0] = a.tl_id;
+        pcount[(long)i * a.n_max + j] = 1;
+        continue;
+      }
+      // depth-first enumeration in adjacency order; the stack is at most max_len deep
+      int node[GTOS_PATHS_MAX_LEN + 1], next_k[GTOS_PATHS_MAX_LEN + 1], labs[GTOS_PATHS_MAX_LEN];
+      int depth = 0, found = 0;
+      node[0] = i;
+      next_k[0] = 0;
+      while (depth >= 0 && found < a.K) {
+        const int v = node[depth];
+        if (depth == d) {                                            // v == j
+          for (int s = 0; s < d; ++s) out[(long)found * a.max_len + s] = labs[s];
+          ++found;
+          --depth;
+          continue;
+        }
+        int k = next_k[depth];
+        const int want = d - depth - 1;
+        while (k < deg[v] && dist[nbr[(long)v * a.deg_max + k]] != want) ++k;
+        if (k >= deg[v]) {
+          --depth;
+          continue;
+        }
+        next_k[depth] = k + 1;
+        labs[depth] = lab[(long)v * a.deg_max + k];
+        node[depth + 1] = nbr[(long)v * a.deg_max + k];
+        next_k[depth + 1] = 0;
+        ++depth;
+      }
+      pcount[(long)i * a.n_max + j] = (int32_t)count[i];
+    }
+  GTOS_PHASE_END
+}
+
 }  // namespace gtos

@@ -123,6 +123,77 @@ def assemble_relation_batch(paths, plen, n_nodes, cls_id, rcls_id, self_id):
     return dict(relation=relation, relation_bank=bank[:Lmax].contiguous(), relation_length=length)
 
 
+def all_shortest_label_paths(n_nodes, deg, nbr, lab, max_len, K, self_id, tl_id):
+    """-> (all_paths [B,n_max,n_max,K,max_len] int32, pcount [B,n_max,n_max] int32): every shortest path of every pair
+    (evaluation batches, data.py:176-225), at most K per pair; raises if a pair has more (one host read)."""
+    _need_cuda(n_nodes, deg, nbr, lab)
+    for t in (n_nodes, deg, nbr, lab):
+        if t.dtype != torch.int32 or not t.is_contiguous():
+            raise ValueError("all_shortest_label_paths takes contiguous int32 tensors (pack_adjacency)")
+    B, n_max, deg_max = nbr.shape
+    dev = nbr.device
+    all_paths = torch.empty(B, n_max, n_max, K, max_len, dtype=torch.int32, device=dev)
+    pcount = torch.empty(B, n_max, n_max, dtype=torch.int32, device=dev)
+    _lib.check(_lib.load().gtos_graph_all_paths(_p(n_nodes), _p(deg), _p(nbr), _p(lab), B, n_max, deg_max, max_len, K, self_id,
+                                                tl_id, _p(all_paths), _p(pcount), _st()), "graph_all_paths")
+    worst = int(pcount.max()) if pcount.numel() else 0
+    if worst > K:
+        raise ValueError(f"a node pair has more than K={K} shortest paths; call again with a larger K")
+    return all_paths, pcount
+
+
+def assemble_eval_relation_batch(all_paths, pcount, n_nodes, pad_id, cls_id, rcls_id, self_id):
+    """all paths per pair -> dict(relation [N,N,B,Kb] int64, relation_bank [Lmax,R] int64, relation_length [R] int64) with
+    the layouts of the evaluation branch of batchify (data.py:176-225): bank rows 0..3 = <PAD>, <CLS>, <rCLS>, <SELF>;
+    relation[j+1][i+1][b][k] = bank row of the k-th shortest path i -> j, 0 (<PAD>) beyond the pair's count; Kb = the
+    largest count in the batch.  Bank rows >= 4 come out in sorted-key order (a permutation of the reference's first-seen
+    order; generator.py:83-88 only gathers rows by index and averages)."""
+    B, n_max, _, K, L = all_paths.shape
+    dev = all_paths.device
+    if L > 8:
+        raise ValueError("label sequences of more than 8 labels are replaced by <TL> in the reference (data.py:203)")
+    p64 = all_paths.to(torch.int64)
+    if p64.numel() and int(p64.max()) >= (1 << 15):
+        raise ValueError("relation label ids must be < 32768")
+    pad = torch.zeros(B, n_max, n_max, K, 8 - L, dtype=torch.int64, device=dev)
+    p8 = torch.cat([p64, pad], dim=-1)
+    hi = (p8[..., 0] << 45) | (p8[..., 1] << 30) | (p8[..., 2] << 15) | p8[..., 3]
+    lo = (p8[..., 4] << 45) | (p8[..., 5] << 30) | (p8[..., 6] << 15) | p8[..., 7]
+    cnt = pcount.to(torch.int64).clamp(max=K)
+    present = torch.arange(K, device=dev).view(1, 1, 1, K) < cnt.unsqueeze(-1)                 # [B,n,n,K]
+    is_self = present & (p64[..., 0] == self_id) & (p64[..., 1:].sum(-1) == 0) if L > 1 else present & (p64[..., 0] == self_id)
+    real = present & ~is_self
+    keys = torch.stack([hi[real], lo[real]], dim=1)
+    if keys.shape[0]:
+        uniq, inv = torch.unique(keys, dim=0, return_inverse=True)
+    else:
+        uniq, inv = keys, keys.new_zeros((0,))
+    R = 4 + uniq.shape[0]
+    ids = torch.zeros(B, n_max, n_max, K, dtype=torch.int64, device=dev)
+    ids[is_self] = 3
+    ids[real] = inv + 4
+    Kb = max(1, int(cnt.max())) if cnt.numel() else 1
+    N = n_max + 1
+    rel = torch.zeros(B, N, N, Kb, dtype=torch.int64, device=dev)                              # [b][x][y][k], data.py:194-219
+    inside = (torch.arange(n_max, device=dev).unsqueeze(0) < n_nodes.to(torch.int64).unsqueeze(1)).to(torch.int64)
+    rel[:, 0, 0, 0] = 3                                                                        # <SELF>
+    rel[:, 0, 1:, 0] = inside                                                                  # <CLS> id 1 for real nodes
+    rel[:, 1:, 0, 0] = 2 * inside                                                              # <rCLS> id 2
+    rel[:, 1:, 1:, :] = ids[..., :Kb]
+    relation = rel.permute(2, 1, 0, 3).contiguous()                                            # transpose_(0, 2), data.py:221
+    bank = torch.zeros(8, R, dtype=torch.int64, device=dev)
+    bank[0, 0], bank[0, 1], bank[0, 2], bank[0, 3] = pad_id, cls_id, rcls_id, self_id
+    if uniq.shape[0]:
+        u_hi, u_lo = uniq[:, 0], uniq[:, 1]
+        cols = [(u_hi >> 45) & 0x7FFF, (u_hi >> 30) & 0x7FFF, (u_hi >> 15) & 0x7FFF, u_hi & 0x7FFF,
+                (u_lo >> 45) & 0x7FFF, (u_lo >> 30) & 0x7FFF, (u_lo >> 15) & 0x7FFF, u_lo & 0x7FFF]
+        bank[:, 4:] = torch.stack(cols, dim=0)
+    length = (bank != 0).sum(0)
+    length[0] = 1                                                                              # the <PAD> row is (pad_id,), length 1 (data.py:183)
+    Lmax = max(1, int(length.max()))
+    return dict(relation=relation, relation_bank=bank[:Lmax].contiguous(), relation_length=length)
+
+
 def relation_batch(graphs, max_len, cls_id, rcls_id, self_id, tl_id, device, seed_off=0):
     """adjacency lists -> the three relation tensors of a training batch (data.py:134-176), paths drawn on the GPU."""
     n_nodes, deg, nbr, lab = pack_adjacency(graphs, device=device)

@@ -267,6 +267,15 @@ int gtos_graph_paths(const int32_t* n_nodes, const int32_t* deg, const int32_t* 
                      int32_t n_max, int32_t deg_max, int32_t max_len, int32_t self_id, int32_t tl_id, const void* seed_ptr,
                      uint64_t seed_off, int32_t* paths, int32_t* plen, void* stream);
 
+/* Evaluation batches keep EVERY shortest path of a pair (generator/data.py:176-225; generator.py:83-88 averages their
+ * encodings).  Same graph format as gtos_graph_paths.  all_paths[b][i][j][k][0..len) = labels of the k-th shortest path
+ * i -> j in depth-first adjacency order, k < min(pcount, K); pcount[b][i][j] = number of shortest paths saturated at K + 1
+ * (a pair that reports K + 1 carries its first K paths), 1 for the <SELF> / <TL> pairs (data.py:197-199), 0 outside the
+ * graph.  max_len <= 16. */
+int gtos_graph_all_paths(const int32_t* n_nodes, const int32_t* deg, const int32_t* nbr, const int32_t* lab, int32_t B,
+                         int32_t n_max, int32_t deg_max, int32_t max_len, int32_t K, int32_t self_id, int32_t tl_id,
+                         int32_t* all_paths, int32_t* pcount, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

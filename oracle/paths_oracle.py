@@ -186,3 +186,69 @@ def assemble_first_seen(chosen, cls_id, rcls_id, self_id):
         bank_t[:len(k), v] = k
         lengths[v] = len(k)
     return rel, bank_t, lengths
+
+
+def enumerate_paths(graphs, max_len, K, self_id, tl_id, n_max=None):
+    """what gtos_graph_all_paths writes: all_paths [B,n_max,n_max,K,max_len] int32 (depth-first adjacency order),
+    pcount [B,n_max,n_max] int32 saturated at K + 1; <SELF> / <TL> pairs hold a single entry (data.py:197-199)."""
+    B = len(graphs)
+    n_max = n_max or max(len(g) for g in graphs)
+    all_paths = np.zeros((B, n_max, n_max, K, max_len), dtype=np.int32)
+    pcount = np.zeros((B, n_max, n_max), dtype=np.int32)
+    for b, adj in enumerate(graphs):
+        n = len(adj)
+        for j in range(n):
+            dj = _bfs_dist_to(adj, j)
+            for i in range(n):
+                d = dj[i]
+                if d == 0:
+                    all_paths[b, i, j, 0, 0], pcount[b, i, j] = self_id, 1
+                elif d < 0 or d > max_len:
+                    all_paths[b, i, j, 0, 0], pcount[b, i, j] = tl_id, 1
+                else:
+                    ps = all_shortest_label_paths(adj, i, j)
+                    pcount[b, i, j] = min(len(ps), K + 1)
+                    for k, p in enumerate(ps[:K]):
+                        all_paths[b, i, j, k, :len(p)] = p
+    return all_paths, pcount
+
+
+def assemble_eval_first_seen(all_chosen, pad_id, cls_id, rcls_id, self_id):
+    """the evaluation branch of batchify, data.py:176-225: all_chosen[b][i][j] = list of label tuples (substitutions done,
+    <SELF> / <TL> pairs already cut to one entry).  Returns (relation [N,N,B,K], relation_bank [Lmax,R],
+    relation_length [R]) numpy int64; bank rows 0..3 = <PAD>, <CLS>, <rCLS>, <SELF> (data.py:183-186)."""
+    bank = {(pad_id,): 0, (cls_id,): 1, (rcls_id,): 2, (self_id,): 3}
+    per_graph, num_concepts, num_paths = [], 0, 0
+    for g in all_chosen:
+        n = len(g)
+        num_concepts = max(n + 1, num_concepts)
+        brs = [[[3]] + [[1]] * n]                                           # data.py:194
+        for i in range(n):
+            rs = [[2]]                                                      # data.py:196
+            for j in range(n):
+                all_r = []
+                for p in g[i][j]:
+                    p = tuple(p)
+                    r = bank.get(p, len(bank))
+                    if r == len(bank):
+                        bank[p] = r
+                    all_r.append(r)
+                num_paths = max(len(all_r), num_paths)
+                rs.append(all_r)
+            brs.append(rs)
+        per_graph.append(brs)
+    mat = np.zeros((len(per_graph), num_concepts, num_concepts, num_paths), dtype=np.int64)
+    for b, x in enumerate(per_graph):
+        for i, y in enumerate(x):
+            for j, z in enumerate(y):
+                for k, r in enumerate(z):
+                    mat[b, i, j, k] = r
+    rel = mat.transpose(2, 1, 0, 3).copy()                                   # transpose_(0, 2), data.py:221
+    R = len(bank)
+    Lmax = max(len(k) for k in bank)
+    bank_t = np.zeros((Lmax, R), dtype=np.int64)
+    lengths = np.zeros(R, dtype=np.int64)
+    for k, v in bank.items():
+        bank_t[:len(k), v] = k
+        lengths[v] = len(k)
+    return rel, bank_t, lengths

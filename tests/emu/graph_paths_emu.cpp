@@ -20,3 +20,17 @@ extern "C" int emu_graph_paths(const int32_t* n_nodes, const int32_t* deg, const
     for (int j = 0; j < n_max; ++j) gtos::graph_paths_cta(a, b, j, smem.data());   // grid (n_max, B)
   return 0;
 }
+
+extern "C" int emu_graph_all_paths(const int32_t* n_nodes, const int32_t* deg, const int32_t* nbr, const int32_t* lab, int32_t B,
+                                   int32_t n_max, int32_t deg_max, int32_t max_len, int32_t K, int32_t self_id, int32_t tl_id,
+                                   int32_t* all_paths, int32_t* pcount) {
+  gtos::GraphAllPathsArgs a;
+  a.n_nodes = n_nodes; a.deg = deg; a.nbr = nbr; a.lab = lab;
+  a.B = B; a.n_max = n_max; a.deg_max = deg_max; a.max_len = max_len; a.K = K;
+  a.self_id = self_id; a.tl_id = tl_id;
+  a.all_paths = all_paths; a.pcount = pcount;
+  std::vector<int32_t> smem((gtos::graph_paths_smem_bytes(n_max) + 3) / 4);
+  for (int b = 0; b < B; ++b)
+    for (int j = 0; j < n_max; ++j) gtos::graph_all_paths_cta(a, b, j, smem.data());
+  return 0;
+}

@@ -100,9 +100,12 @@ def main():
 
     ref_data.random.choice = lambda xs: xs[0]                                            # deterministic choice
     batch = ref_data.batchify(items, vocabs, train=True)                                  # the reference, unmodified
+    ev = ref_data.batchify(items, vocabs, train=False)                                    # evaluation branch: all paths
     out = dict(relation_vocab=rel_vocab, graphs=out_graphs,
                batchify_first_choice=dict(relation=batch["relation"].tolist(), relation_bank=batch["relation_bank"].tolist(),
-                                          relation_length=batch["relation_length"].tolist()))
+                                          relation_length=batch["relation_length"].tolist()),
+               batchify_eval=dict(relation=ev["relation"].tolist(), relation_bank=ev["relation_bank"].tolist(),
+                                  relation_length=ev["relation_length"].tolist()))
     with open(os.path.join(HERE, "golden_paths.json"), "w") as f:
         json.dump(out, f)
     print("graphs", [len(g["nodes"]) for g in out_graphs], "bank", len(out["batchify_first_choice"]["relation_length"]),

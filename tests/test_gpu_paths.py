@@ -136,3 +136,34 @@ def test_graph_paths_full_batch_properties_and_assembly(dev):
                     assert here == {j}
         assert (rel[0, 1:n + 1, b] == 1).all() and (rel[1:n + 1, 0, b] == 0).all() and rel[0, 0, b] == 2
         assert (rel[n + 1:, :, b] == 0).all() and (rel[:, n + 1:, b] == 0).all()
+
+
+def test_graph_all_paths_equals_oracle_and_eval_assembly(dev):
+    """evaluation batches (data.py:176-225): every shortest path of a pair, depth-first adjacency order, saturating count"""
+    from gtos_b200 import paths as P
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_paths.json")))
+    voc = g["relation_vocab"]
+    graphs = [[[(u, voc[l]) for u, l in a] for a in gr["adjacency"]] for gr in g["graphs"]]
+    packed = [torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in PO.pack_adjacency(graphs, n_max=14, deg_max=6)]
+    for max_len, K in ((8, 4), (4, 3)):
+        want = PO.enumerate_paths(graphs, max_len, K, SELF, TL, n_max=14)
+        allp, cnt = P.all_shortest_label_paths(*packed, max_len, K, SELF, TL)
+        torch.cuda.synchronize()
+        assert np.array_equal(cnt.cpu().numpy(), want[1]) and np.array_equal(allp.cpu().numpy(), want[0])
+    with pytest.raises(ValueError):
+        P.all_shortest_label_paths(*packed, 8, 1, SELF, TL)              # pairs with 2-3 paths: K = 1 is too small
+    allp, cnt = P.all_shortest_label_paths(*packed, 8, 4, SELF, TL)
+    out = P.assemble_eval_relation_batch(allp, cnt, packed[0], voc["<PAD>"], CLS, RCLS, SELF)
+    ref = g["batchify_eval"]
+    rel, bank, length = (out[k].cpu().numpy() for k in ("relation", "relation_bank", "relation_length"))
+    rel_o, bank_o, length_o = np.array(ref["relation"]), np.array(ref["relation_bank"]), np.array(ref["relation_length"])
+    # n_max was padded to 14 here: compare the part the reference has
+    N = rel_o.shape[0]
+    assert rel.shape[3] == rel_o.shape[3] and (rel[N:] == 0).all() and (rel[:, N:] == 0).all()
+    seq = lambda bk, ln, r: tuple(int(x) for x in bk[:int(ln[r]), r])
+    for b in range(len(graphs)):
+        for x in range(N):
+            for y in range(N):
+                mine = sorted(seq(bank, length, int(r)) for r in rel[y, x, b] if int(r) != 0)
+                theirs = sorted(seq(bank_o, length_o, int(r)) for r in rel_o[y, x, b] if int(r) != 0)
+                assert mine == theirs, (b, x, y)

@@ -245,3 +245,121 @@ def test_paths_product_has_no_cpu_path():
     with pytest.raises(_lib.GtosLibraryError):
         P.shortest_label_paths(torch.zeros(1, dtype=torch.int32), z, torch.zeros(1, 2, 1, dtype=torch.int32),
                                torch.zeros(1, 2, 1, dtype=torch.int32), 4, 4, 5)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# evaluation batches: every shortest path of a pair (data.py:176-225)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def emu_all(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("emu_all") / "graph_paths_emu.so")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-o", so,
+                           os.path.join(ROOT, "tests", "emu", "graph_paths_emu.cpp")])
+    lib = C.CDLL(so)
+    lib.emu_graph_all_paths.restype = C.c_int
+    lib.emu_graph_all_paths.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 7 + [C.c_void_p, C.c_void_p]
+
+    def run(n_nodes, deg, nbr, lab, max_len, K, self_id, tl_id):
+        B, n_max, deg_max = nbr.shape
+        allp = np.full((B, n_max, n_max, K, max_len), -7, dtype=np.int32)
+        cnt = np.full((B, n_max, n_max), -7, dtype=np.int32)
+        arrs = [np.ascontiguousarray(x, dtype=np.int32) for x in (n_nodes, deg, nbr, lab)]
+        assert lib.emu_graph_all_paths(*[x.ctypes.data for x in arrs], B, n_max, deg_max, max_len, K, self_id, tl_id,
+                                       allp.ctypes.data, cnt.ctypes.data) == 0
+        return allp, cnt
+
+    return run
+
+
+def _golden_all_chosen(g, voc, self_id, tl_id):
+    out = []
+    for gr in g["graphs"]:
+        n = len(gr["nodes"])
+        per = []
+        for i in range(n):
+            row = []
+            for j in range(n):
+                ps = [[voc[l] for l in p] for p in gr["all_paths"][i][j]]
+                if len(ps[0]) == 0 or len(ps[0]) > 8:                    # data.py:197-199
+                    ps = ps[:1]
+                row.append([tuple([self_id] if len(p) == 0 else [tl_id] if len(p) > 8 else p) for p in ps])
+            per.append(row)
+        out.append(per)
+    return out
+
+
+def test_oracle_eval_assembly_equals_reference_batchify(gold):
+    g, voc, graphs = gold
+    cls_id, rcls_id, self_id, tl_id = _ids(voc)
+    rel, bank, length = PO.assemble_eval_first_seen(_golden_all_chosen(g, voc, self_id, tl_id), voc["<PAD>"], cls_id, rcls_id,
+                                                    self_id)
+    ref = g["batchify_eval"]
+    assert np.array_equal(rel, np.array(ref["relation"]))
+    assert np.array_equal(bank, np.array(ref["relation_bank"]))
+    assert np.array_equal(length, np.array(ref["relation_length"]))
+
+
+def test_all_paths_kernel_source_emulated_on_cpu_equals_oracle(gold, emu_all):
+    g, voc, graphs = gold
+    cls_id, rcls_id, self_id, tl_id = _ids(voc)
+    packed = PO.pack_adjacency(graphs, n_max=14, deg_max=6)
+    for max_len, K in ((8, 4), (4, 3), (8, 1)):                          # K = 1: pairs with 2-3 paths saturate at K + 1
+        want = PO.enumerate_paths(graphs, max_len, K, self_id, tl_id, n_max=14)
+        got = emu_all(*packed, max_len, K, self_id, tl_id)
+        assert np.array_equal(got[1], want[1]) and np.array_equal(got[0], want[0])
+    assert (want[1] == 2).any()
+    # the enumerated sets are the reference's (as multisets of label sequences), pair by pair
+    allp, cnt = emu_all(*packed, 8, 4, self_id, tl_id)
+    for b, (gr, adj) in enumerate(zip(g["graphs"], graphs)):
+        for i in range(len(adj)):
+            for j in range(len(adj)):
+                ref = sorted(tuple(voc[l] for l in p) for p in gr["all_paths"][i][j])
+                if len(ref[0]) == 0:
+                    ref = [(self_id,)]
+                elif len(ref[0]) > 8:
+                    ref = [(tl_id,)]
+                got = sorted(tuple(int(x) for x in allp[b, i, j, k] if x != 0) for k in range(cnt[b, i, j]))
+                assert got == ref
+    # many re-entrancies, more nodes than emulated threads
+    rng = np.random.default_rng(SEED + 2)
+    n = 140
+    adj = [dict() for _ in range(n)]
+    for v in range(1, n):
+        u = int(rng.integers(max(0, v - 5), v))
+        k = int(rng.integers(20))
+        adj[u][v], adj[v][u] = 6 + 2 * k, 7 + 2 * k
+    for _ in range(n):
+        u, v = int(rng.integers(n)), int(rng.integers(n))
+        if u != v:
+            k = int(rng.integers(20))
+            adj[u][v], adj[v][u] = 6 + 2 * k, 7 + 2 * k
+    big = [[list(a.items()) for a in adj]]
+    want = PO.enumerate_paths(big, 6, 8, self_id, tl_id)
+    got = emu_all(*PO.pack_adjacency(big), 6, 8, self_id, tl_id)
+    assert np.array_equal(got[1], want[1]) and np.array_equal(got[0], want[0])
+    assert want[1].max() >= 3
+
+
+def test_eval_assembly_host_logic(gold):
+    from gtos_b200 import paths as P
+    g, voc, graphs = gold
+    cls_id, rcls_id, self_id, tl_id = _ids(voc)
+    K = 4
+    allp, cnt = PO.enumerate_paths(graphs, 8, K, self_id, tl_id)
+    n_nodes = torch.tensor([len(a) for a in graphs], dtype=torch.int32)
+    out = P.assemble_eval_relation_batch(torch.from_numpy(allp), torch.from_numpy(cnt), n_nodes, voc["<PAD>"], cls_id, rcls_id,
+                                         self_id)
+    rel, bank, length = out["relation"], out["relation_bank"], out["relation_length"]
+    ref = g["batchify_eval"]
+    rel_o, bank_o, length_o = np.array(ref["relation"]), np.array(ref["relation_bank"]), np.array(ref["relation_length"])
+    assert tuple(rel.shape) == rel_o.shape and tuple(bank.shape) == bank_o.shape
+    assert bank[:, :4].tolist() == bank_o[:, :4].tolist() and length[:4].tolist() == length_o[:4].tolist()
+    seq = lambda bk, ln, r: tuple(int(x) for x in bk[:int(ln[r]), r])
+    N = rel.shape[0]
+    for b in range(len(graphs)):
+        for x in range(N):
+            for y in range(N):
+                mine = sorted(seq(bank, length, int(r)) for r in rel[y, x, b] if int(r) != 0)
+                theirs = sorted(seq(bank_o, length_o, int(r)) for r in rel_o[y, x, b] if int(r) != 0)
+                assert mine == theirs, (b, x, y)
+    assert sorted(seq(bank, length, r) for r in range(bank.shape[1])) == sorted(seq(bank_o, length_o, r) for r in range(bank_o.shape[1]))

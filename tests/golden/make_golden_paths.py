@@ -53,6 +53,28 @@ def build(names, edges):
     return g
 
 
+def translator_trees(rng):
+    """translator/dependencyGraph.py (the reference's own constructor, _add_edge with `_r_` twins, bfs and
+    collect_concepts_and_relations, dependencyGraph.py:8-74): dependency trees, ONE path per pair
+    (nx.single_source_shortest_path) - unique in a tree, so the GPU draw must reproduce it exactly."""
+    sys.path.append("/root/reference/translator")
+    import dependencyGraph as ref_dep              # noqa: E402
+    out = []
+    for n in (1, 6, 13, 10):
+        head = [0] + [rng.randrange(1, v + 1) for v in range(1, n)]          # head[v] in 1..v (1-based), 0 = root
+        dep = ["root"] + [f"dep{rng.randrange(5)}" for _ in range(1, n)]
+        tok = [f"t{k}" for k in range(n)]
+        g = ref_dep.dependencyGraph(dep, head, tok, ["x"])                   # the reference, unmodified
+        concepts, _, relations, connected = g.collect_concepts_and_relations()
+        assert connected
+        order, _, _ = g.bfs()
+        pos = {name: k for k, name in enumerate(order)}
+        adj = [[(pos[u], g.graph[v][u]["label"]) for u in g.graph.neighbors(v)] for v in order]
+        paths = [[relations[i][j][0]["edge"] for j in range(n)] for i in range(n)]
+        out.append(dict(head=head, dep=dep, nodes=order, adjacency=adj, paths=paths))
+    return out
+
+
 def main():
     rng = random.Random(19940117)
     specs = [(5, 1), (9, 3), (12, 5), (11, 0), (7, 4), (1, 0)]
@@ -106,6 +128,7 @@ def main():
                                           relation_length=batch["relation_length"].tolist()),
                batchify_eval=dict(relation=ev["relation"].tolist(), relation_bank=ev["relation_bank"].tolist(),
                                   relation_length=ev["relation_length"].tolist()))
+    out["translator_trees"] = translator_trees(rng)
     with open(os.path.join(HERE, "golden_paths.json"), "w") as f:
         json.dump(out, f)
     print("graphs", [len(g["nodes"]) for g in out_graphs], "bank", len(out["batchify_first_choice"]["relation_length"]),

@@ -363,3 +363,26 @@ def test_eval_assembly_host_logic(gold):
                 theirs = sorted(seq(bank_o, length_o, int(r)) for r in rel_o[y, x, b] if int(r) != 0)
                 assert mine == theirs, (b, x, y)
     assert sorted(seq(bank, length, r) for r in range(bank.shape[1])) == sorted(seq(bank_o, length_o, r) for r in range(bank_o.shape[1]))
+
+
+def test_translator_dependency_trees_are_reproduced_exactly(gold, emu):
+    """translator/dependencyGraph.py:54-74 keeps the one path nx.single_source_shortest_path returns; in a tree it is the
+    only shortest path, so enumeration, the uniform draw (any seed) and the emulated kernel must all return exactly it."""
+    g, _, _ = gold
+    trees = g["translator_trees"]
+    labels = sorted({l for t in trees for a in t["adjacency"] for _, l in a})
+    voc = {l: 6 + k for k, l in enumerate(labels)}
+    graphs = [[[(u, voc[l]) for u, l in a] for a in t["adjacency"]] for t in trees]
+    packed = PO.pack_adjacency(graphs)
+    for seed in (1, SEED):
+        paths, plen = PO.sample_paths(*packed, 8, 4, 5, seed)
+        got = emu(*packed, 8, 4, 5, seed)
+        assert np.array_equal(got[0], paths) and np.array_equal(got[1], plen)
+        for b, (t, adj) in enumerate(zip(trees, graphs)):
+            n = len(adj)
+            for i in range(n):
+                for j in range(n):
+                    ref = tuple(voc[l] for l in t["paths"][i][j])
+                    assert PO.all_shortest_label_paths(adj, i, j) == [ref]
+                    want = (4,) if len(ref) == 0 else (5,) if len(ref) > 8 else ref      # translator/data.py:151-155
+                    assert tuple(int(x) for x in paths[b, i, j, :plen[b, i, j]]) == want

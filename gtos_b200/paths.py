@@ -56,6 +56,51 @@ def pack_adjacency(graphs, n_max=None, deg_max=None, device=None):
     return tuple(t.to(device) for t in out) if device is not None else out
 
 
+def pack_edges(n_nodes, graph, src, dst, label, n_max=None, deg_max=None, device=None):
+    """Vectorised pack_adjacency for large batches.  One row per DIRECTED edge in insertion order: graph[e], src[e], dst[e],
+    label[e] (the caller lists both the edge and its reverse twin, as AMRGraph._add_edge does).  A pair (src, dst) listed
+    more than once keeps its LAST label.  Returns the same int32 tensors as pack_adjacency; neighbours of a node are
+    ordered by destination index."""
+    import numpy as np
+    n_nodes = np.asarray(n_nodes, dtype=np.int64)
+    g, u, v, l = (np.asarray(x, dtype=np.int64) for x in (graph, src, dst, label))
+    B = len(n_nodes)
+    n_max = int(n_max or (n_nodes.max() if B else 1))
+    if len(g):
+        if (u < 0).any() or (v < 0).any() or (u >= n_nodes[g]).any() or (v >= n_nodes[g]).any():
+            raise ValueError("edge endpoint outside its graph")
+        key = (g * n_max + u) * n_max + v
+        order = np.lexsort((np.arange(len(key)), key))                  # by (graph, src, dst), insertion order inside
+        key, l = key[order], l[order]
+        last = np.ones(len(key), dtype=bool)
+        last[:-1] = key[1:] != key[:-1]                                 # last occurrence of every (graph, src, dst)
+        key, l = key[last], l[last]
+        rev = (key // (n_max * n_max)) * n_max * n_max + (key % n_max) * n_max + (key // n_max) % n_max
+        if not np.isin(rev, key).all():
+            raise ValueError("adjacency is not symmetric: every edge needs its reverse twin (AMRGraph._add_edge, "
+                             "AMRGraph.py:76-80)")
+        node = key // n_max                                             # graph * n_max + src
+        start = np.r_[True, node[1:] != node[:-1]]
+        first = np.flatnonzero(start)
+        slot = np.arange(len(key)) - np.repeat(first, np.diff(np.r_[first, len(key)]))
+        dmax = int(slot.max()) + 1
+    else:
+        key = l = node = slot = np.zeros(0, dtype=np.int64)
+        dmax = 1
+    deg_max = int(deg_max or dmax)
+    if dmax > deg_max:
+        raise ValueError(f"a node has {dmax} neighbours, deg_max is {deg_max}")
+    deg = np.zeros(B * n_max, dtype=np.int32)
+    np.add.at(deg, node, 1)
+    nbr = np.zeros((B * n_max, deg_max), dtype=np.int32)
+    lab = np.zeros((B * n_max, deg_max), dtype=np.int32)
+    nbr[node, slot] = key % n_max
+    lab[node, slot] = l
+    out = (torch.from_numpy(n_nodes.astype(np.int32)), torch.from_numpy(deg).view(B, n_max),
+           torch.from_numpy(nbr).view(B, n_max, deg_max), torch.from_numpy(lab).view(B, n_max, deg_max))
+    return tuple(t.to(device) for t in out) if device is not None else out
+
+
 def shortest_label_paths(n_nodes, deg, nbr, lab, max_len, self_id, tl_id, seed_off=0, seed=None):
     """-> (paths [B,n_max,n_max,max_len] int32, plen [B,n_max,n_max] int32); paths[b,i,j] = labels of the drawn shortest
     path i -> j (AMRGraph.py:107-112 + data.py:150-154).  `seed`: int64 device tensor (default: the library's dropout

@@ -386,3 +386,37 @@ def test_translator_dependency_trees_are_reproduced_exactly(gold, emu):
                     assert PO.all_shortest_label_paths(adj, i, j) == [ref]
                     want = (4,) if len(ref) == 0 else (5,) if len(ref) > 8 else ref      # translator/data.py:151-155
                     assert tuple(int(x) for x in paths[b, i, j, :plen[b, i, j]]) == want
+
+
+def test_pack_edges_matches_pack_adjacency(gold):
+    """vectorised edge-list packing: same graph as the adjacency-list packer up to the order of a node's neighbours (which
+    the path distribution does not depend on), last label wins, asymmetric input is rejected"""
+    from gtos_b200 import paths as P
+    g, voc, graphs = gold
+    gi, src, dst, lab = [], [], [], []
+    for b, adj in enumerate(graphs):
+        for v, a in enumerate(adj):
+            for u, l in a:
+                gi.append(b); src.append(v); dst.append(u); lab.append(l)
+    n_nodes = [len(a) for a in graphs]
+    t = P.pack_edges(n_nodes, gi, src, dst, lab)
+    ref = P.pack_adjacency(graphs)
+    assert torch.equal(t[0], ref[0]) and torch.equal(t[1], ref[1])
+    for b, adj in enumerate(graphs):
+        for v in range(len(adj)):
+            d = int(t[1][b, v])
+            assert sorted(zip(t[2][b, v, :d].tolist(), t[3][b, v, :d].tolist())) == sorted((int(u), int(l)) for u, l in adj[v])
+    # same shortest paths (as sets) whichever neighbour order
+    a1 = [[(int(u), int(l)) for u, l in zip(t[2][1, v, :int(t[1][1, v])].tolist(), t[3][1, v, :int(t[1][1, v])].tolist())]
+          for v in range(n_nodes[1])]
+    for i in range(n_nodes[1]):
+        for j in range(n_nodes[1]):
+            assert sorted(PO.all_shortest_label_paths(a1, i, j)) == sorted(PO.all_shortest_label_paths(graphs[1], i, j))
+    dup = P.pack_edges([2], [0, 0, 0], [0, 0, 1], [1, 1, 0], [6, 8, 7])
+    assert dup[1].tolist() == [[1, 1]] and dup[3][0, 0, 0].item() == 8
+    with pytest.raises(ValueError):
+        P.pack_edges([2], [0], [0], [1], [6])
+    with pytest.raises(ValueError):
+        P.pack_edges([2], [0, 0], [0, 2], [2, 0], [6, 7])
+    empty = P.pack_edges([1, 1], [], [], [], [])
+    assert empty[1].tolist() == [[0], [0]] and tuple(empty[2].shape) == (2, 1, 1)

@@ -420,3 +420,38 @@ def test_pack_edges_matches_pack_adjacency(gold):
         P.pack_edges([2], [0, 0], [0, 2], [2, 0], [6, 7])
     empty = P.pack_edges([1, 1], [], [], [], [])
     assert empty[1].tolist() == [[0], [0]] and tuple(empty[2].shape) == (2, 1, 1)
+
+
+def test_emulated_kernel_draw_is_uniform_over_the_reference_lists(gold, emu):
+    """random.choice over the reference's enumerated list (data.py:150) = every NODE path equally likely.  3000 seeds through
+    the kernel source: for every pair with more than one shortest path, each label sequence must come up in proportion to
+    the number of node paths that spell it (5 sigma of the binomial)."""
+    g, voc, graphs = gold
+    cls_id, rcls_id, self_id, tl_id = _ids(voc)
+    packed = PO.pack_adjacency(graphs)
+    draws = 3000
+    counts = {}
+    for s in range(draws):
+        paths, plen = emu(*packed, 8, self_id, tl_id, 7_000_000 + 977 * s)
+        for b, gr in enumerate(g["graphs"]):
+            n = len(gr["nodes"])
+            for i in range(n):
+                for j in range(n):
+                    if len(gr["all_paths"][i][j]) > 1:
+                        key = (b, i, j, tuple(int(x) for x in paths[b, i, j, :plen[b, i, j]]))
+                        counts[key] = counts.get(key, 0) + 1
+    pairs = 0
+    for b, gr in enumerate(g["graphs"]):
+        n = len(gr["nodes"])
+        for i in range(n):
+            for j in range(n):
+                ref = [tuple(voc[l] for l in p) for p in gr["all_paths"][i][j]]
+                if len(ref) < 2:
+                    continue
+                pairs += 1
+                assert sum(c for k, c in counts.items() if k[:3] == (b, i, j)) == draws
+                for p in set(ref):
+                    q = ref.count(p) / len(ref)
+                    got = counts.get((b, i, j, p), 0)
+                    assert abs(got - draws * q) < 5 * (draws * q * (1 - q)) ** 0.5 + 1, (b, i, j, p, got, q)
+    assert pairs >= 30

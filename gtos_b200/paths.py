@@ -56,6 +56,24 @@ def pack_adjacency(graphs, n_max=None, deg_max=None, device=None):
     return tuple(t.to(device) for t in out) if device is not None else out
 
 
+def adjacency_from_reference_item(item, token2idx):
+    """The reference's preprocessed JSON (generator/extract.py:173-180) stores, per graph, `relation[i][j]` = the list of
+    all shortest paths i -> j with their edge labels - not the edges.  The edges are the paths of length one:
+    adj[i] = [(j, id of the label of i -> j)].  `item` = one entry of that JSON (keys may be str after the JSON round trip,
+    data.py:149), `token2idx` = vocabs['relation'].token2idx (data.py:48-51)."""
+    rel = item["relation"]
+    n = len(item["concept"])
+    adj = [[] for _ in range(n)]
+    for i in range(n):
+        row = rel[str(i)] if str(i) in rel else rel[i]
+        for j in range(n):
+            paths = row[str(j)] if str(j) in row else row[j]
+            edge = paths[0]["edge"]
+            if len(edge) == 1:                      # a direct edge: every shortest path i -> j is that edge
+                adj[i].append((j, int(token2idx(edge[0]))))
+    return adj
+
+
 def pack_edges(n_nodes, graph, src, dst, label, n_max=None, deg_max=None, device=None):
     """Vectorised pack_adjacency for large batches.  One row per DIRECTED edge in insertion order: graph[e], src[e], dst[e],
     label[e] (the caller lists both the edge and its reverse twin, as AMRGraph._add_edge does).  A pair (src, dst) listed

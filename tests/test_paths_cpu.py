@@ -455,3 +455,16 @@ def test_emulated_kernel_draw_is_uniform_over_the_reference_lists(gold, emu):
                     got = counts.get((b, i, j, p), 0)
                     assert abs(got - draws * q) < 5 * (draws * q * (1 - q)) ** 0.5 + 1, (b, i, j, p, got, q)
     assert pairs >= 30
+
+
+def test_adjacency_recovered_from_the_reference_json_item(gold):
+    """the reference's JSON keeps enumerated paths, not edges (extract.py:173-180): the edges are the one-label paths"""
+    from gtos_b200 import paths as P
+    g, voc, graphs = gold
+    for gr, adj in zip(g["graphs"], graphs):
+        n = len(gr["nodes"])
+        item = dict(concept=gr["nodes"],
+                    relation={str(i): {str(j): [dict(edge=p, length=len(p)) for p in gr["all_paths"][i][j]] for j in range(n)}
+                              for i in range(n)})
+        got = P.adjacency_from_reference_item(item, lambda t: voc[t])
+        assert [sorted(a) for a in got] == [sorted((int(u), int(l)) for u, l in a) for a in adj]

@@ -60,7 +60,7 @@ struct GraphPathsArgs {
   int32_t* plen;            // [B, n_max, n_max]           number of labels (1 for <SELF> / <TL>); 0 = pair outside the graph
 };
 
-// shared-memory working set of one CTA: dist [n_max] int32, sigma [n_max] float, mark [n_max] int32, flag [2] int32
+// shared-memory working set of one CTA: dist [n_max] int32, sigma [n_max] float, mark [n_max] int32, flag [4] int32
 GTOS_HD size_t graph_paths_smem_bytes(int n_max) { return (size_t)n_max * 12 + 16; }
 
 // everything one CTA does for (graph b, target j); `smem` = graph_paths_smem_bytes(n_max) bytes, 4-byte aligned
@@ -95,13 +95,16 @@ inline void graph_paths_cta(const GraphPathsArgs& a, int b, int j, void* smem) {
       sigma[v] = (v == j) ? 1.f : 0.f;
       mark[v] = 0;
     }
-    if (tid == 0) flag[0] = 1;
+    if (tid == 0) {
+      flag[0] = 1;
+      flag[1] = 0;                                                   // a node joined the next level
+      flag[2] = 0;                                                   // a count of the next level left the safe range
+    }
   GTOS_PHASE_END
 
   // ---- level-synchronous BFS from the target with shortest-path counts ----
-  for (int level = 0; flag[0] != 0; ++level) {                       // flag[0] is only written between barriers
+  for (int level = 0; flag[0] != 0; ++level) {                       // flags are only written between barriers
     GTOS_PHASE(tid, nthr)
-      if (tid == 0) flag[1] = 0;
       // pull: an unvisited node joins level + 1 if one of its neighbours sits on `level` (symmetric structure)
       for (int v = tid; v < n; v += nthr) {
         if (dist[v] >= 0) continue;
@@ -117,6 +120,7 @@ inline void graph_paths_cta(const GraphPathsArgs& a, int b, int j, void* smem) {
         if (hit) {
           mark[v] = 1;
           sigma[v] = s;
+          if (s > 1.0e30f) flag[2] = 1;                              // benign same-value race
         }
       }
     GTOS_PHASE_END
@@ -130,19 +134,16 @@ inline void graph_paths_cta(const GraphPathsArgs& a, int b, int j, void* smem) {
     GTOS_PHASE_END
     // keep the counts of the new level in float range: only ratios inside one level are ever used
     GTOS_PHASE(tid, nthr)
-      if (tid == 0) {
-        float mx = 0.f;
-        for (int v = 0; v < n; ++v)
-          if (dist[v] == level + 1 && sigma[v] > mx) mx = sigma[v];
-        flag[0] = flag[1];
-        reinterpret_cast<float*>(flag)[2] = mx;
-      }
-    GTOS_PHASE_END
-    GTOS_PHASE(tid, nthr)
-      const float mx = reinterpret_cast<const float*>(flag)[2];
-      if (mx > 1.0e30f)
+      if (flag[2] != 0)
         for (int v = tid; v < n; v += nthr)
           if (dist[v] == level + 1) sigma[v] = sigma[v] * (1.0f / 1.0e30f);
+    GTOS_PHASE_END
+    GTOS_PHASE(tid, nthr)
+      if (tid == 0) {
+        flag[0] = flag[1];
+        flag[1] = 0;
+        flag[2] = 0;
+      }
     GTOS_PHASE_END
   }
 

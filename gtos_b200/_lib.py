@@ -52,6 +52,7 @@ SIGNATURES = {
     "gtos_rel_dw_workspace": (i64, [i32, i32, i32, i32]),
     "gtos_rel_dw": (i32, [vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]),
     "gtos_graph_all_paths": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp]),
+    "gtos_graph_bfs": (i32, [vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]),
     "gtos_graph_paths": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, u64, vp, vp, vp]),
     "gtos_rel_dqk": (i32, [vp, vp, vp, i64, vp, vp, i32, i32, i32, i32, vp]),
     "gtos_rel_pair_keys": (i32, [vp, i32, i32, i32, i32, i32, vp, vp]),

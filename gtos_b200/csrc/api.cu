@@ -379,4 +379,13 @@ int gtos_graph_all_paths(const int32_t* n_nodes, const int32_t* deg, const int32
   return graph_all_paths(a, S(stream));
 }
 
+int gtos_graph_bfs(const int32_t* n_nodes, const int32_t* deg, const int32_t* nbr, const int32_t* root, int32_t B, int32_t n_max,
+                   int32_t deg_max, int32_t* order, int32_t* depth, int32_t* pos, int32_t* reached, void* stream) {
+  GraphBfsArgs a;
+  a.n_nodes = n_nodes; a.deg = deg; a.nbr = nbr; a.root = root;
+  a.B = B; a.n_max = n_max; a.deg_max = deg_max;
+  a.order = order; a.depth = depth; a.pos = pos; a.reached = reached;
+  return graph_bfs(a, S(stream));
+}
+
 }  // extern "C"

@@ -108,5 +108,7 @@ struct GraphPathsArgs;
 int graph_paths(const GraphPathsArgs& a, const void* seed_ptr, unsigned long long seed_off, cudaStream_t st);
 struct GraphAllPathsArgs;
 int graph_all_paths(const GraphAllPathsArgs& a, cudaStream_t st);
+struct GraphBfsArgs;
+int graph_bfs(const GraphBfsArgs& a, cudaStream_t st);
 
 }  // namespace gtos

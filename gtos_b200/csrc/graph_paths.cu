@@ -50,4 +50,20 @@ int graph_all_paths(const GraphAllPathsArgs& a, cudaStream_t st) {
   return GTOS_OK;
 }
 
+__global__ void __launch_bounds__(128) graph_bfs_kernel(const GraphBfsArgs a) {
+  GTOS_PDL_PROLOGUE();
+  const int b = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (b < a.B) graph_bfs_one(a, b);
+}
+
+int graph_bfs(const GraphBfsArgs& a, cudaStream_t st) {
+  GTOS_REQUIRE(a.B >= 0 && a.n_max >= 1 && a.deg_max >= 1, "graph_bfs: bad sizes (B=%d n_max=%d deg_max=%d)", a.B, a.n_max,
+               a.deg_max);
+  GTOS_REQUIRE(a.n_nodes && a.deg && a.nbr && a.root && a.order && a.depth && a.pos && a.reached, "graph_bfs: null argument");
+  if (a.B == 0) return GTOS_OK;
+  GTOS_KLAUNCH(graph_bfs_kernel, dim3((unsigned)((a.B + 127) / 128)), dim3(128), 0, st, a);
+  GTOS_LAUNCH_CHECK();
+  return GTOS_OK;
+}
+
 }  // namespace gtos

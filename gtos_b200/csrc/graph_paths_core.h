@@ -340,4 +340,62 @@ inline void graph_all_paths_cta(const GraphAllPathsArgs& a, int b, int j, void* 
   GTOS_PHASE_END
 }
 
+// -------------------------------------------------------------------------------------------------------------------
+// Node order of a batch: AMRGraph.bfs (generator/AMRGraph.py:82-98; translator/dependencyGraph.py:36-52) - a queue BFS
+// from the root that visits neighbours in adjacency (insertion) order; the batch uses the queue order as node order and
+// the BFS depths as `concept_depth` (data.py:129).  The queue discipline is sequential by definition, the graphs are
+// tiny: one THREAD per graph replays it exactly.
+//   order[b][k] = k-th node of the queue, depth[b][k] = its depth, pos[b][v] = position of node v (-1: not reached),
+//   reached[b]  = queue length (== n_nodes[b] iff the graph is connected, the reference's `is_connected`)
+// -------------------------------------------------------------------------------------------------------------------
+struct GraphBfsArgs {
+  const int32_t* n_nodes;   // [B]
+  const int32_t* deg;       // [B, n_max]
+  const int32_t* nbr;       // [B, n_max, deg_max]
+  const int32_t* root;      // [B]
+  int32_t B, n_max, deg_max;
+  int32_t* order;           // [B, n_max]  (-1 beyond the queue)
+  int32_t* depth;           // [B, n_max]  (0 beyond the queue)
+  int32_t* pos;             // [B, n_max]
+  int32_t* reached;         // [B]
+};
+
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline void graph_bfs_one(const GraphBfsArgs& a, int b) {
+  const int n = a.n_nodes[b];
+  const int32_t* deg = a.deg + (long)b * a.n_max;
+  const int32_t* nbr = a.nbr + (long)b * a.n_max * a.deg_max;
+  int32_t* order = a.order + (long)b * a.n_max;
+  int32_t* depth = a.depth + (long)b * a.n_max;
+  int32_t* pos = a.pos + (long)b * a.n_max;
+  for (int v = 0; v < a.n_max; ++v) {
+    order[v] = -1;
+    depth[v] = 0;
+    pos[v] = -1;
+  }
+  int tail = 0;
+  const int r = a.root[b];
+  if (n > 0 && r >= 0 && r < n) {
+    order[0] = r;
+    pos[r] = 0;
+    tail = 1;
+  }
+  for (int head = 0; head < tail; ++head) {                          // AMRGraph.py:88-96
+    const int u = order[head];
+    const int du = depth[head];
+    for (int k = 0; k < deg[u]; ++k) {
+      const int v = nbr[(long)u * a.deg_max + k];
+      if (pos[v] < 0) {
+        pos[v] = tail;
+        order[tail] = v;
+        depth[tail] = du + 1;
+        ++tail;
+      }
+    }
+  }
+  a.reached[b] = tail;
+}
+
 }  // namespace gtos

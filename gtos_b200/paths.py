@@ -119,6 +119,39 @@ def pack_edges(n_nodes, graph, src, dst, label, n_max=None, deg_max=None, device
     return tuple(t.to(device) for t in out) if device is not None else out
 
 
+def bfs_order(n_nodes, deg, nbr, root):
+    """AMRGraph.bfs on the device (AMRGraph.py:82-98): -> (order [B,n_max], depth [B,n_max], pos [B,n_max], reached [B]),
+    int32.  order[b][k] = k-th node of the root's BFS queue, depth[b][k] = its depth (`concept_depth`, data.py:129),
+    pos = inverse permutation (-1: not reached), reached[b] == n_nodes[b] iff graph b is connected."""
+    _need_cuda(n_nodes, deg, nbr, root)
+    for t in (n_nodes, deg, nbr, root):
+        if t.dtype != torch.int32 or not t.is_contiguous():
+            raise ValueError("bfs_order takes contiguous int32 tensors (pack_adjacency)")
+    B, n_max, deg_max = nbr.shape
+    dev = nbr.device
+    order, depth, pos = (torch.empty(B, n_max, dtype=torch.int32, device=dev) for _ in range(3))
+    reached = torch.empty(B, dtype=torch.int32, device=dev)
+    _lib.check(_lib.load().gtos_graph_bfs(_p(n_nodes), _p(deg), _p(nbr), _p(root), B, n_max, deg_max, _p(order), _p(depth),
+                                          _p(pos), _p(reached), _st()), "graph_bfs")
+    return order, depth, pos, reached
+
+
+def relabel_adjacency(deg, nbr, lab, order, pos):
+    """the padded adjacency renumbered by a node order (index arithmetic, any device): node order[b][k] becomes node k.
+    Graphs must be connected (every node has a position)."""
+    B, n_max, deg_max = nbr.shape
+    o = order.to(torch.int64).clamp(min=0)                                             # [B, n_max]; -1 rows are padding
+    live = (order >= 0)
+    deg2 = torch.where(live, torch.gather(deg.to(torch.int64), 1, o), torch.zeros_like(o)).to(torch.int32)
+    rows = o.unsqueeze(-1).expand(B, n_max, deg_max)
+    nbr_old = torch.gather(nbr.to(torch.int64), 1, rows)                               # neighbours of node order[b][k], old ids
+    lab2 = torch.gather(lab.to(torch.int64), 1, rows)
+    used = torch.arange(deg_max, device=nbr.device).view(1, 1, deg_max) < deg2.unsqueeze(-1).to(torch.int64)
+    nbr2 = torch.gather(pos.to(torch.int64), 1, nbr_old.reshape(B, -1)).reshape(B, n_max, deg_max)
+    zero = torch.zeros_like(nbr2)
+    return deg2, torch.where(used, nbr2, zero).to(torch.int32), torch.where(used, lab2, zero).to(torch.int32)
+
+
 def shortest_label_paths(n_nodes, deg, nbr, lab, max_len, self_id, tl_id, seed_off=0, seed=None):
     """-> (paths [B,n_max,n_max,max_len] int32, plen [B,n_max,n_max] int32); paths[b,i,j] = labels of the drawn shortest
     path i -> j (AMRGraph.py:107-112 + data.py:150-154).  `seed`: int64 device tensor (default: the library's dropout

@@ -276,6 +276,13 @@ int gtos_graph_all_paths(const int32_t* n_nodes, const int32_t* deg, const int32
                          int32_t n_max, int32_t deg_max, int32_t max_len, int32_t K, int32_t self_id, int32_t tl_id,
                          int32_t* all_paths, int32_t* pcount, void* stream);
 
+/* Node order of a batch: AMRGraph.bfs (generator/AMRGraph.py:82-98; translator/dependencyGraph.py:36-52) - the queue BFS
+ * from root[b] that visits neighbours in adjacency order.  order[b][k] = k-th node of the queue (-1 beyond it),
+ * depth[b][k] = its BFS depth (the `concept_depth` input, data.py:129), pos[b][v] = position of node v (-1 = not reached),
+ * reached[b] = queue length (== n_nodes[b] iff connected).  One thread per graph replays the sequential queue exactly. */
+int gtos_graph_bfs(const int32_t* n_nodes, const int32_t* deg, const int32_t* nbr, const int32_t* root, int32_t B, int32_t n_max,
+                   int32_t deg_max, int32_t* order, int32_t* depth, int32_t* pos, int32_t* reached, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -252,3 +252,24 @@ def assemble_eval_first_seen(all_chosen, pad_id, cls_id, rcls_id, self_id):
         bank_t[:len(k), v] = k
         lengths[v] = len(k)
     return rel, bank_t, lengths
+
+
+def bfs_order(adj, root):
+    """AMRGraph.bfs, generator/AMRGraph.py:82-98: (queue order, depths, is_connected); adj[v] in neighbour iteration order"""
+    queue, depths, visited = [root], [0], {root}
+    step = 0
+    while step < len(queue):
+        u, depth = queue[step], depths[step]
+        step += 1
+        for v, _ in adj[u]:
+            if v not in visited:
+                queue.append(v)
+                depths.append(depth + 1)
+                visited.add(v)
+    return queue, depths, len(queue) == len(adj)
+
+
+def relabel(adj, order):
+    """adjacency renumbered by the BFS order (what collect_concepts_and_relations indexes its relations by, AMRGraph.py:103)"""
+    pos = {v: k for k, v in enumerate(order)}
+    return [[(pos[u], l) for u, l in adj[v]] for v in order]

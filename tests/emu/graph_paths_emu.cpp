@@ -34,3 +34,13 @@ extern "C" int emu_graph_all_paths(const int32_t* n_nodes, const int32_t* deg, c
     for (int j = 0; j < n_max; ++j) gtos::graph_all_paths_cta(a, b, j, smem.data());
   return 0;
 }
+
+extern "C" int emu_graph_bfs(const int32_t* n_nodes, const int32_t* deg, const int32_t* nbr, const int32_t* root, int32_t B,
+                             int32_t n_max, int32_t deg_max, int32_t* order, int32_t* depth, int32_t* pos, int32_t* reached) {
+  gtos::GraphBfsArgs a;
+  a.n_nodes = n_nodes; a.deg = deg; a.nbr = nbr; a.root = root;
+  a.B = B; a.n_max = n_max; a.deg_max = deg_max;
+  a.order = order; a.depth = depth; a.pos = pos; a.reached = reached;
+  for (int b = 0; b < B; ++b) gtos::graph_bfs_one(a, b);                      // one thread per graph
+  return 0;
+}

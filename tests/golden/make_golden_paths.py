@@ -116,7 +116,12 @@ def main():
         adj = [[(pos[u], g.graph[v][u]["label"]) for u in g.graph.neighbors(v)] for v in order]
         n = len(order)
         all_paths = [[[p["edge"] for p in relations[i][j]] for j in range(n)] for i in range(n)]
-        out_graphs.append(dict(nodes=order, edges=edges, adjacency=adj, all_paths=all_paths))
+        # the graph as the reference holds it BEFORE the BFS renumbering: node k = names[k], neighbours in networkx order
+        idx = {name: k for k, name in enumerate(names)}
+        orig_adj = [[(idx[u], g.graph[v][u]["label"]) for u in g.graph.neighbors(v)] for v in names]
+        _, bfs_depths, _ = g.bfs()
+        out_graphs.append(dict(nodes=order, edges=edges, adjacency=adj, all_paths=all_paths, orig_adjacency=orig_adj,
+                               root=idx[g.root], bfs_order=[idx[v] for v in order], bfs_depths=bfs_depths))
         items.append(dict(concept=concepts, depth=depths, relation=json.loads(json.dumps(relations)), token=["w"],
                           token2idx={}, idx2token={}, cp_seq=concepts, abstract=[]))
 

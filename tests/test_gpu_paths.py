@@ -167,3 +167,28 @@ def test_graph_all_paths_equals_oracle_and_eval_assembly(dev):
                 mine = sorted(seq(bank, length, int(r)) for r in rel[y, x, b] if int(r) != 0)
                 theirs = sorted(seq(bank_o, length_o, int(r)) for r in rel_o[y, x, b] if int(r) != 0)
                 assert mine == theirs, (b, x, y)
+
+
+def test_graph_bfs_equals_reference_order(dev):
+    """AMRGraph.bfs on the device: the reference's own node order and depths (golden), connectivity flag, relabelling"""
+    from gtos_b200 import paths as P
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_paths.json")))
+    voc = g["relation_vocab"]
+    orig = [[[(u, voc[l]) for u, l in a] for a in gr["orig_adjacency"]] for gr in g["graphs"]]
+    orig.append([[(1, 6)], [(0, 7), (2, 6)], [(1, 7)], []])                   # node 3 is not connected
+    roots = [gr["root"] for gr in g["graphs"]] + [1]
+    n_nodes, deg, nbr, lab = (torch.from_numpy(x).to(dev) for x in PO.pack_adjacency(orig, n_max=14, deg_max=6))
+    order, depth, pos, reached = P.bfs_order(n_nodes, deg, nbr, torch.tensor(roots, dtype=torch.int32, device=dev))
+    torch.cuda.synchronize()
+    for b, adj in enumerate(orig):
+        want_o, want_d, ok = PO.bfs_order(adj, roots[b])
+        m = len(want_o)
+        assert int(reached[b]) == m and order[b, :m].tolist() == want_o and depth[b, :m].tolist() == want_d
+        assert (order[b, m:] == -1).all() and (int(reached[b]) == len(adj)) == ok
+    for b, gr in enumerate(g["graphs"]):
+        assert order[b, :len(gr["nodes"])].tolist() == gr["bfs_order"] and depth[b, :len(gr["nodes"])].tolist() == gr["bfs_depths"]
+    deg2, nbr2, lab2 = P.relabel_adjacency(deg[:-1], nbr[:-1], lab[:-1], order[:-1], pos[:-1])
+    for b, gr in enumerate(g["graphs"]):
+        for k in range(len(gr["nodes"])):
+            d = int(deg2[b, k])
+            assert sorted(zip(nbr2[b, k, :d].tolist(), lab2[b, k, :d].tolist())) == sorted((u, voc[l]) for u, l in gr["adjacency"][k])

@@ -468,3 +468,49 @@ def test_adjacency_recovered_from_the_reference_json_item(gold):
                               for i in range(n)})
         got = P.adjacency_from_reference_item(item, lambda t: voc[t])
         assert [sorted(a) for a in got] == [sorted((int(u), int(l)) for u, l in a) for a in adj]
+
+
+def test_bfs_order_oracle_emulation_and_relabelling(gold, tmp_path):
+    """AMRGraph.bfs (AMRGraph.py:82-98): node order, depths and connectivity of the reference's own run; the kernel source
+    (one thread per graph) equals it; the relabelled adjacency equals the adjacency the reference's relations are indexed by"""
+    from gtos_b200 import paths as P
+    g, voc, graphs = gold
+    so = str(tmp_path / "emu.so")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-o", so,
+                           os.path.join(ROOT, "tests", "emu", "graph_paths_emu.cpp")])
+    lib = C.CDLL(so)
+    lib.emu_graph_bfs.restype = C.c_int
+    lib.emu_graph_bfs.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 3 + [C.c_void_p] * 4
+    orig = [[[(u, voc[l]) for u, l in a] for a in gr["orig_adjacency"]] for gr in g["graphs"]]
+    for gr, adj in zip(g["graphs"], orig):
+        order, depths, ok = PO.bfs_order(adj, gr["root"])
+        assert order == gr["bfs_order"] and depths == gr["bfs_depths"] and ok
+        assert [sorted(a) for a in PO.relabel(adj, order)] == [sorted((u, voc[l]) for u, l in a) for a in gr["adjacency"]]
+    # a disconnected graph: node 3 has no edges
+    orig.append([[(1, 6)], [(0, 7), (2, 6)], [(1, 7)], []])
+    roots = [gr["root"] for gr in g["graphs"]] + [1]
+    n_nodes, deg, nbr, lab = PO.pack_adjacency(orig, n_max=14, deg_max=6)
+    B = len(orig)
+    root = np.array(roots, dtype=np.int32)
+    order, depth, pos = (np.full((B, 14), -9, dtype=np.int32) for _ in range(3))
+    reached = np.full(B, -9, dtype=np.int32)
+    assert lib.emu_graph_bfs(n_nodes.ctypes.data, deg.ctypes.data, nbr.ctypes.data, root.ctypes.data, B, 14, 6, order.ctypes.data,
+                             depth.ctypes.data, pos.ctypes.data, reached.ctypes.data) == 0
+    for b, adj in enumerate(orig):
+        want_o, want_d, ok = PO.bfs_order(adj, roots[b])
+        m = len(want_o)
+        assert reached[b] == m and (reached[b] == len(adj)) == ok
+        assert order[b, :m].tolist() == want_o and depth[b, :m].tolist() == want_d
+        assert (order[b, m:] == -1).all() and (depth[b, m:] == 0).all()
+        for v in range(14):
+            assert pos[b, v] == (want_o.index(v) if v in want_o else -1)
+    assert reached[-1] == 3 and pos[-1, 3] == -1
+    # relabelling on tensors == the oracle's relabel == the adjacency the golden relations are indexed by (connected graphs)
+    t = [torch.from_numpy(x[:-1].copy()) for x in (deg, nbr, lab, order, pos)]
+    deg2, nbr2, lab2 = P.relabel_adjacency(*t)
+    for b, gr in enumerate(g["graphs"]):
+        for k in range(len(gr["nodes"])):
+            d = int(deg2[b, k])
+            got = sorted(zip(nbr2[b, k, :d].tolist(), lab2[b, k, :d].tolist()))
+            assert got == sorted((u, voc[l]) for u, l in gr["adjacency"][k])
+        assert int(deg2[b, len(gr["nodes"]):].sum()) == 0

@@ -40,3 +40,13 @@ def fake_all(n_nodes, deg, nbr, lab, max_len, K, self_id, tl_id):
     return torch.from_numpy(allp), torch.from_numpy(cnt)
 P.all_shortest_label_paths = fake_all
 T.test_graph_all_paths_equals_oracle_and_eval_assembly(dev); print("all paths ok")
+lib.emu_graph_bfs.restype = C.c_int
+lib.emu_graph_bfs.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 3 + [C.c_void_p] * 4
+def fake_bfs(n_nodes, deg, nbr, root):
+    B, n_max, deg_max = nbr.shape
+    arrs = [np.ascontiguousarray(t.cpu().numpy(), dtype=np.int32) for t in (n_nodes, deg, nbr, root)]
+    order, depth, pos = (np.zeros((B, n_max), dtype=np.int32) for _ in range(3)); reached = np.zeros(B, dtype=np.int32)
+    lib.emu_graph_bfs(*[x.ctypes.data for x in arrs], B, n_max, deg_max, order.ctypes.data, depth.ctypes.data, pos.ctypes.data, reached.ctypes.data)
+    return tuple(torch.from_numpy(x) for x in (order, depth, pos, reached))
+P.bfs_order = fake_bfs
+T.test_graph_bfs_equals_reference_order(dev); print("bfs ok")

@@ -180,7 +180,7 @@ def assemble_relation_batch(paths, plen, n_nodes, cls_id, rcls_id, self_id):
     if L > 8:
         raise ValueError("label sequences of more than 8 labels are replaced by <TL> in the reference (data.py:153)")
     p64 = paths.to(torch.int64)
-    if int(p64.max()) >= (1 << 15):
+    if p64.numel() and int(p64.max()) >= (1 << 15):
         raise ValueError("relation label ids must be < 32768")
     # 120-bit key of a sequence: four 15-bit labels per word, first label most significant (0 = padding sorts first)
     pad = torch.zeros(B, n_max, n_max, 8 - L, dtype=torch.int64, device=dev)

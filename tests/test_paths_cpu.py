@@ -514,3 +514,28 @@ def test_bfs_order_oracle_emulation_and_relabelling(gold, tmp_path):
             got = sorted(zip(nbr2[b, k, :d].tolist(), lab2[b, k, :d].tolist()))
             assert got == sorted((u, voc[l]) for u, l in gr["adjacency"][k])
         assert int(deg2[b, len(gr["nodes"]):].sum()) == 0
+
+
+def test_empty_and_degenerate_batches(emu):
+    """an empty graph inside a batch, a batch of single nodes, two isolated nodes (unreachable pair -> <TL>)"""
+    from gtos_b200 import paths as P
+    graphs = [[], [[]], [[], []], [[(1, 6)], [(0, 7)]]]
+    packed = PO.pack_adjacency(graphs, n_max=3, deg_max=2)
+    paths, plen = emu(*packed, 4, 4, 5, 1)
+    want = PO.sample_paths(*packed, 4, 4, 5, 1)
+    assert np.array_equal(paths, want[0]) and np.array_equal(plen, want[1])
+    assert (plen[0] == 0).all() and (paths[0] == 0).all()                               # empty graph: all padding
+    assert plen[1, 0, 0] == 1 and paths[1, 0, 0, 0] == 4 and plen[1].sum() == 1          # single node: <SELF>
+    assert paths[2, 0, 1, 0] == 5 and paths[2, 1, 0, 0] == 5                             # isolated nodes: <TL>
+    assert paths[3, 0, 1].tolist() == [6, 0, 0, 0] and paths[3, 1, 0].tolist() == [7, 0, 0, 0]
+    n_nodes = torch.tensor([0, 1, 2, 2], dtype=torch.int32)
+    out = P.assemble_relation_batch(torch.from_numpy(paths), torch.from_numpy(plen), n_nodes, 2, 3, 4)
+    rel, bank, length = out["relation"], out["relation_bank"], out["relation_length"]
+    assert bank[0, :3].tolist() == [2, 3, 4] and sorted(bank[0, 3:].tolist()) == [5, 6, 7] and length.tolist() == [1] * 6
+    assert rel[:, :, 0].tolist() == [[2, 0, 0, 0], [0, 0, 0, 0], [0, 0, 0, 0], [0, 0, 0, 0]]   # only the <SELF> corner
+    assert rel[1, 1, 1].item() == 2 and rel[0, 1, 1].item() == 1 and rel[1, 0, 1].item() == 0
+    tl = (bank[0] == 5).nonzero().item()
+    assert rel[2, 1, 2].item() == tl and rel[1, 2, 2].item() == tl
+    none = P.assemble_relation_batch(torch.zeros(0, 3, 3, 4, dtype=torch.int32), torch.zeros(0, 3, 3, dtype=torch.int32),
+                                     torch.zeros(0, dtype=torch.int32), 2, 3, 4)
+    assert tuple(none["relation"].shape) == (4, 4, 0) and none["relation_bank"].shape[1] == 3

@@ -170,6 +170,25 @@ def shortest_label_paths(n_nodes, deg, nbr, lab, max_len, self_id, tl_id, seed_o
     return paths, plen
 
 
+def _unique_keys(hi, lo):
+    """distinct (hi, lo) pairs in lexicographic order + the index of every input pair in that list - what
+    torch.unique(stack([hi, lo], 1), dim=0, return_inverse=True) returns, from two stable radix sorts instead of a
+    comparator sort over rows (which is the slow part of that call on the GPU at ~1e5 keys)."""
+    n = hi.numel()
+    if n == 0:
+        return torch.stack([hi, lo], dim=1), hi.new_zeros((0,))
+    o1 = torch.sort(lo, stable=True).indices
+    o2 = torch.sort(hi[o1], stable=True).indices
+    order = o1[o2]                                                    # lexicographic by (hi, lo)
+    h, l = hi[order], lo[order]
+    new = torch.ones(n, dtype=torch.bool, device=hi.device)
+    new[1:] = (h[1:] != h[:-1]) | (l[1:] != l[:-1])
+    gid = torch.cumsum(new.to(torch.int64), 0) - 1                    # group of every sorted element
+    inv = torch.empty(n, dtype=torch.int64, device=hi.device)
+    inv[order] = gid
+    return torch.stack([h[new], l[new]], dim=1), inv
+
+
 def assemble_relation_batch(paths, plen, n_nodes, cls_id, rcls_id, self_id):
     """per-pair label sequences -> dict(relation [N,N,B] int64, relation_bank [Lmax,R] int64, relation_length [R] int64),
     N = n_max + 1 (the <CLS> slot), with the layouts of data.py:138-176: relation[j+1][i+1][b] = bank row of the path
@@ -190,11 +209,7 @@ def assemble_relation_batch(paths, plen, n_nodes, cls_id, rcls_id, self_id):
     valid = plen > 0
     is_self = valid & (plen == 1) & (p64[..., 0] == self_id)
     real = valid & ~is_self
-    keys = torch.stack([hi[real], lo[real]], dim=1)                                 # [P, 2]
-    if keys.shape[0]:
-        uniq, inv = torch.unique(keys, dim=0, return_inverse=True)                  # sorted rows; dynamic size: host read
-    else:
-        uniq, inv = keys, keys.new_zeros((0,))
+    uniq, inv = _unique_keys(hi[real], lo[real])                                    # sorted keys; dynamic size: host read
     R = 3 + uniq.shape[0]
     ids = torch.zeros(B, n_max, n_max, dtype=torch.int64, device=dev)
     ids[is_self] = 2
@@ -259,11 +274,7 @@ def assemble_eval_relation_batch(all_paths, pcount, n_nodes, pad_id, cls_id, rcl
     present = torch.arange(K, device=dev).view(1, 1, 1, K) < cnt.unsqueeze(-1)                 # [B,n,n,K]
     is_self = present & (p64[..., 0] == self_id) & (p64[..., 1:].sum(-1) == 0) if L > 1 else present & (p64[..., 0] == self_id)
     real = present & ~is_self
-    keys = torch.stack([hi[real], lo[real]], dim=1)
-    if keys.shape[0]:
-        uniq, inv = torch.unique(keys, dim=0, return_inverse=True)
-    else:
-        uniq, inv = keys, keys.new_zeros((0,))
+    uniq, inv = _unique_keys(hi[real], lo[real])
     R = 4 + uniq.shape[0]
     ids = torch.zeros(B, n_max, n_max, K, dtype=torch.int64, device=dev)
     ids[is_self] = 3

@@ -539,3 +539,17 @@ def test_empty_and_degenerate_batches(emu):
     none = P.assemble_relation_batch(torch.zeros(0, 3, 3, 4, dtype=torch.int32), torch.zeros(0, 3, 3, dtype=torch.int32),
                                      torch.zeros(0, dtype=torch.int32), 2, 3, 4)
     assert tuple(none["relation"].shape) == (4, 4, 0) and none["relation_bank"].shape[1] == 3
+
+
+def test_unique_keys_equals_torch_unique_rows():
+    from gtos_b200 import paths as P
+    gen = torch.Generator().manual_seed(5)
+    for n, span in ((0, 5), (1, 5), (2000, 7), (5000, 1 << 40)):
+        hi = torch.randint(0, span, (n,), generator=gen)
+        lo = torch.randint(0, span, (n,), generator=gen)
+        uniq, inv = P._unique_keys(hi, lo)
+        if n == 0:
+            assert tuple(uniq.shape) == (0, 2) and inv.numel() == 0
+            continue
+        ref_u, ref_i = torch.unique(torch.stack([hi, lo], 1), dim=0, return_inverse=True)
+        assert torch.equal(uniq, ref_u) and torch.equal(inv, ref_i)

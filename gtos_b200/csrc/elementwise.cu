@@ -124,7 +124,8 @@ int cast_colsum(const float* src, long lds, void* dst, long ldd, float* sums, lo
   if (cols % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
     const int rpb = 32;
-    static const int ny = getenv("GTOS_CC_NY") ? atoi(getenv("GTOS_CC_NY")) : 4;   // 1, 2 or 4 row groups per CTA
+    static const int ny_env = getenv("GTOS_CC_NY") ? atoi(getenv("GTOS_CC_NY")) : 4;   // 1, 2 or 4 row groups per CTA
+    const int ny = (ny_env == 1 || ny_env == 2) ? ny_env : 4;                          // anything else: the default
     dim3 grid((unsigned)((ldd / 4 + 127) / 128), (unsigned)((rows + rpb - 1) / rpb));
     GTOS_KLAUNCH(cast_colsum_vec4_kernel, dim3(grid), dim3(128, ny), 0, st, src, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldd, sums, rows, cols, rpb);
     GTOS_LAUNCH_CHECK();

@@ -3,9 +3,7 @@ bar is bit-exact - on the golden graphs of the reference (tests/golden/golden_pa
 nodes than threads, on path counts beyond float range, and at config-2 batch size through size-independent properties
 (every drawn sequence has the BFS distance as its length and walks real edges; the assembled bank decodes back to it).
 
-The kernel was written after this round's GPU budget was spent: its SOURCE is checked on the CPU (tests/test_paths_cpu.py
-runs csrc/graph_paths_core.h as plain C++ against the same oracle), the CUDA build has not run yet.  Until it has, these
-tests only run with GTOS_TEST_EXPERIMENTAL=1 so that an unvalidated kernel cannot turn the suite red."""
+First run on a B200 in round 2 (gpurun_out/r2a, profiles/r02_paths_probe.txt): all five tests green, bit-exact."""
 import json
 import os
 
@@ -15,9 +13,7 @@ import torch
 
 from oracle import paths_oracle as PO
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("GTOS_TEST_EXPERIMENTAL") != "1",
-                                 reason="gtos_graph_paths has not run on a GPU yet (set GTOS_TEST_EXPERIMENTAL=1)")]
+pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SEED = 19940117
 CLS, RCLS, SELF, TL = 2, 3, 4, 5

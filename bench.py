@@ -29,11 +29,26 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (B per GPU, n_max nodes, T_max, T_min, max relation path len)
-    "cfg1": dict(B=8, n_max=16, T_max=20, T_min=10, path=4, D=128, F=256, H=8, gl=2, sl=1, il=1, rnn=64, V=2000),
-    "cfg2": dict(B=64, n_max=40, T_max=60, T_min=20, path=4, D=512, F=1024, H=8, gl=4, sl=1, il=3, rnn=256, V=10000),
+    # B = graphs per GPU (weak scaling) | global = fixed global batch split over the ranks (strong scaling);
+    # micro = graphs per forward/backward pass (gradients accumulate over the micro-batches of a step)
+    "cfg1": dict(B=8, n_max=16, T_max=20, T_min=10, path=4, D=128, F=256, H=8, gl=2, sl=1, il=1, rnn=64, V=2000,
+                 what="plumbing config (BASELINE.json configs[0])"),
+    "cfg2": dict(B=64, n_max=40, T_max=60, T_min=20, path=4, D=512, F=1024, H=8, gl=4, sl=1, il=3, rnn=256, V=10000,
+                 what="gtos generator/ default (4 graph + 1 snt + 3 inference layers, 512 dim, 8 heads)"),
+    "cfg3": dict(**{"global": 128}, n_max=60, T_max=60, T_min=10, path=8, D=512, F=1024, H=8, gl=4, sl=1, il=3, rnn=256,
+                 V=10000, what="gtos translator/ default (translator/train.sh:28-37: same architecture; paths <= 8 labels, "
+                               "translator/data.py:154), global batch 128"),
+    "cfg4": dict(**{"global": 256}, micro=32, n_max=256, T_max=60, T_min=20, path=8, D=512, F=1024, H=8, gl=4, sl=1, il=3,
+                 rnn=256, V=10000, relation_mode="banked", device_paths=True,
+                 what="large-graph stress: 256-node graphs, paths <= 8 labels, global batch 256, relation stored bf16 "
+                      "(bank-factorised, SURVEY 8 f-0)"),
 }
 METRIC = "encoder_node_pairs_per_sec"
+REL_MODE_NOTE = {
+    "index_select": "dense fp32 bank.index_select(...) built by the caller's own line (generator.py:79): unchanged caller",
+    "gather": "dense fp32 + bf16 copy from ops.bank_gather (1-line caller change)",
+    "banked": "bank-factorised (SURVEY 8 f-0, 2-line caller change): bf16 gather fwd, bank-row GEMMs bwd",
+}
 
 
 def parse():
@@ -45,12 +60,15 @@ def parse():
     ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
     ap.add_argument("--dropout", type=float, default=0.2)
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of one CUDA graph")
-    ap.add_argument("--cpu-sample-graphs", type=int, default=4, help="graphs per CPU-baseline step")
+    ap.add_argument("--cpu-sample-graphs", type=int, default=0,
+                    help="graphs per CPU-baseline step (0 = the workload's full per-GPU batch, same config as the GPU arm)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true", help="only the headline step timing (quick A/B runs)")
-    ap.add_argument("--dense-relation", action="store_true",
-                    help="build relation = bank[idx] as a dense fp32 tensor exactly as generator.py:79 does "
-                         "(default: keep it factorised, SURVEY §8 f-0)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the cfg3 / cfg4 strong-scaling legs and the f-0 / f-3 legs")
+    ap.add_argument("--relation-mode", default=None, choices=list(REL_MODE_NOTE),
+                    help="how relation = bank[idx] reaches the graph encoder (default: index_select = the unchanged caller; "
+                         "cfg4 defaults to banked)")
+    ap.add_argument("--dense-relation", action="store_true", help="(kept for old command lines) same as --relation-mode gather")
     ap.add_argument("--profile-step", action="store_true",
                     help="run ONE eager step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     return ap.parse_args()
@@ -63,10 +81,16 @@ def make_cfg(w, dropout):
                          vocab_size=w["V"])
 
 
-def make_host_batch(w, B, seed):
+def make_host_batch(w, B, seed, device_paths=None):
+    """device_paths: a CUDA device -> the relation tensors are built ON THE GPU (gtos_graph_paths +
+    index assembly) from the same synthetic graphs; None -> host BFS (gtos_b200/synthetic.py)."""
     from gtos_b200 import hotpath, synthetic
-    g = synthetic.make_batch(B, w["n_max"], w["D"], T_max=w["T_max"], T_min=w["T_min"], V=w["V"],
-                             max_path_len=w["path"], seed=seed)
+    if device_paths is not None:
+        g = synthetic.make_batch(B, w["n_max"], w["D"], T_max=w["T_max"], T_min=w["T_min"], V=w["V"],
+                                 max_path_len=w["path"], seed=seed, device_paths=device_paths)
+    else:
+        g = synthetic.make_batch(B, w["n_max"], w["D"], T_max=w["T_max"], T_min=w["T_min"], V=w["V"],
+                                 max_path_len=w["path"], seed=seed)
     b = hotpath.batch_tensors(g)
     meta = dict(N=g["N"], T=g["T"], B=B, R=int(g["relation_bank"].shape[1]),
                 tokens=int(g["t_len"].sum()), pairs=B * g["N"] * g["N"],
@@ -129,15 +153,45 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference path on the host cores
+# CPU arm: the reference's own modules (staged under oracle/_ref by oracle/ref_loader.py::build_ref) wired exactly like
+# the GPU arm's HotPath, on the host cores; the oracle port only if the staged reference is missing
 # ------------------------------------------------------------------------------------------------
+def reference_modules():
+    """the reference's four hot-path classes, or None when neither oracle/_ref nor /root/reference exists"""
+    import types
+    from oracle import ref_loader as RL
+    if not RL.have_ref("generator"):
+        return None
+    ns = RL.load("generator")
+    return types.SimpleNamespace(RelationEncoder=ns.encoder.RelationEncoder,
+                                 GraphTransformer=ns.graph_transformer.GraphTransformer,
+                                 Transformer=ns.transformer.Transformer, DecodeLayer=ns.decoder.DecodeLayer)
+
+
 def cpu_step_fn(w, cfg, B, seed):
+    """-> (step function, batch meta, kind).  kind "reference": gtos_b200.hotpath.HotPath built from the UNMODIFIED
+    reference modules (same wiring, same batch dictionary, relation = bank.index_select as generator.py:79);
+    kind "port": the oracle restatement."""
     from gtos_b200 import hotpath
-    from oracle import hotpath_oracle as HO
     torch.manual_seed(seed)
+    b, meta = make_host_batch(w, B, seed)
+    mods = reference_modules()
+    if mods is not None:
+        m = hotpath.HotPath(cfg, modules=mods)
+        m.train(cfg.dropout > 0)
+        params = [v for v in m.parameters()]
+
+        def step():
+            for v in params:
+                v.grad = None
+            loss = m(b)
+            loss.backward()
+            return float(loss.detach())
+
+        return step, meta, "reference"
+    from oracle import hotpath_oracle as HO
     m = hotpath.HotPath(cfg)
     P = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in m.state_dict().items()}
-    b, meta = make_host_batch(w, B, seed)
     params = [v for v in P.values() if v.requires_grad]
 
     def step():
@@ -147,7 +201,7 @@ def cpu_step_fn(w, cfg, B, seed):
         loss.backward()
         return float(loss.detach())
 
-    return step, meta
+    return step, meta, "port"
 
 
 def host_threads():
@@ -164,14 +218,14 @@ def host_threads():
 
 def run_cpu(w, cfg, B, steps, warmup, seed):
     torch.set_num_threads(host_threads())
-    step, meta = cpu_step_fn(w, cfg, B, seed)
+    step, meta, kind = cpu_step_fn(w, cfg, B, seed)
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / steps
-    return dt, meta
+    return dt, meta, kind
 
 
 def cpu_model_name():
@@ -184,26 +238,51 @@ def cpu_model_name():
     return "unknown"
 
 
+def per_gpu_graphs(w, world):
+    if "global" in w:
+        if w["global"] % world:
+            raise SystemExit(f"global batch {w['global']} does not divide over {world} ranks")
+        return w["global"] // world
+    return w["B"]
+
+
+def workload_text(name, w, dropout):
+    return f"{name}: {w['what']}, synthetic <= {w['n_max']}-node graphs, fwd+bwd, dropout {dropout}"
+
+
+def kind_text(kind):
+    return ("the reference's own modules (oracle/_ref: unmodified generator/{encoder,graph_transformer,transformer,decoder}.py"
+            ", CPU fp32)" if kind == "reference" else "CPU oracle port of the reference path")
+
+
 def main_reference(args):
+    """The reference's CPU implementation of the same step on the same batch as the GPU arm's rank 0 (same config:
+    the full per-GPU batch unless --cpu-sample-graphs is given)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     w = WORKLOADS[args.workload]
     cfg = make_cfg(w, args.dropout)
-    B = args.cpu_sample_graphs
-    dt, meta = run_cpu(w, cfg, B, args.steps, max(1, min(args.warmup, 2)), 19940117)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    full = min(per_gpu_graphs(w, max(1, world)), w.get("micro", 1 << 30))
+    B = args.cpu_sample_graphs or full
+    warm = min(args.warmup, 2)                        # a full-batch reference step takes ~10 s of host time
+    dt, meta, kind = run_cpu(w, cfg, B, args.steps, warm, 19940117)
     val = meta["pairs"] / dt
     cores = host_threads()
+    sample = (f"the full per-GPU batch of the GPU arm ({B} graphs)" if B == full else f"{B} of {full} graphs per step")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "node-pairs/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "steps": args.steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "strong" if "global" in w else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "decoder_tokens_per_sec": meta["tokens"] / dt,
-            "config": {"workload": f"{args.workload}: gtos generator/ default (4 graph + 1 snt + 3 inference layers, "
-                                   f"{w['D']} dim, {w['H']} heads), synthetic <= {w['n_max']}-node graphs, fwd+bwd, "
-                                   f"dropout {args.dropout}", "graphs_per_step": B, "nodes_incl_cls": meta["N"]},
-            "cpu_baseline": {"value": val, "unit": "node-pairs/s", "cores": cores, "kind": "port",
-                             "sample": f"{B} of {w['B']} graphs per step (CPU oracle port of the reference path, "
-                                       f"{cpu_model_name()})"},
+            "config": {"workload": workload_text(args.workload, w, args.dropout), "graphs_per_step": B,
+                       "nodes_incl_cls": meta["N"], "tgt_len": meta["T"], "distinct_relation_paths": meta["R"],
+                       "relation": REL_MODE_NOTE["index_select"],
+                       "step": "RelationEncoder+gather+GraphTransformer+snt+DecodeLayer fwd+bwd on the host cores "
+                               "(rank 0 only; one replica's batch - the reference has no CPU data-parallel path)"},
+            "cpu_baseline": {"value": val, "unit": "node-pairs/s", "cores": cores, "kind": kind,
+                             "sample": f"{sample}, {args.steps} steps after {warm} warm-up; {kind_text(kind)}; "
+                                       f"{cpu_model_name()}"},
             "e2e": {"value": val, "unit": "node-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -212,10 +291,353 @@ def main_reference(args):
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
+class StepRunner:
+    """One workload on this rank: host batch -> ONE flat pinned buffer -> device buffers the captured step reads;
+    `step_device()` = the whole hot-path step (all micro-batches fwd+bwd, gradient pack, data-parallel all-reduce)."""
+
+    def __init__(self, name, model, dropout, dev, rank, world, relation_mode=None, use_graph=True, seed=19940117):
+        import torch.distributed as dist
+        from gtos_b200 import _lib, ops
+        from gtos_b200.dp import FlatGradBucket, OverlappedGradBuckets
+        self.dist, self.ops, self.lib = dist, ops, _lib.load()
+        self.name, self.model, self.dev, self.rank, self.world = name, model, dev, rank, world
+        w = self.w = WORKLOADS[name]
+        per_gpu = per_gpu_graphs(w, world)
+        self.micro = min(per_gpu, w.get("micro", per_gpu))
+        if per_gpu % self.micro:
+            raise SystemExit(f"{name}: {per_gpu} graphs per GPU is not a multiple of the micro-batch {self.micro}")
+        self.n_micro = per_gpu // self.micro
+        self.per_gpu = per_gpu
+        self.relation_mode = relation_mode or w.get("relation_mode", "index_select")
+        t0 = time.perf_counter()
+        host, meta = make_host_batch(w, self.micro, seed + rank, device_paths=dev if w.get("device_paths") else None)
+        self.batch_build_s = time.perf_counter() - t0
+        self.meta = meta
+        self.h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+        offs, total = {}, 0
+        for k, v in host.items():
+            offs[k] = total
+            total += (v.numel() * v.element_size() + 255) // 256 * 256
+        self.flat_pinned = torch.empty(total, dtype=torch.uint8).pin_memory()
+        self.flat_stage = torch.empty(total, dtype=torch.uint8, device=dev)
+        self.flat_static = torch.empty(total, dtype=torch.uint8, device=dev)
+
+        def _views(flat):
+            return {k: flat[offs[k]:offs[k] + v.numel() * v.element_size()].view(v.dtype).view(v.shape) for k, v in host.items()}
+
+        pinned, self.static = _views(self.flat_pinned), _views(self.flat_static)
+        for k, v in host.items():
+            pinned[k].copy_(v)
+        self.bucket = FlatGradBucket(model.parameters(), bind=False)
+        self.loss_buf = torch.zeros((), device=dev)
+        self.loss_host = torch.zeros((), pin_memory=True)
+        # data parallel: one flat all-reduce after the step, or (GTOS_DP_OVERLAP=1) three buckets all-reduced from
+        # backward hooks WHILE the backward runs, inside the step's CUDA graph (dp.OverlappedGradBuckets)
+        self.overlap = None
+        if world > 1 and os.environ.get("GTOS_DP_OVERLAP", "0") == "1" and self.n_micro == 1:
+            self.overlap = OverlappedGradBuckets([
+                list(model.decoder.parameters()) + list(model.snt_encoder.parameters()),
+                list(model.graph_encoder.parameters()) + list(model.probe_generator.parameters()),
+                list(model.relation_encoder.parameters())])
+        self.use_graph = use_graph and self.n_micro == 1
+        self.graph = None
+        self.launches_per_step = 0
+        self.copy_stream = torch.cuda.Stream()
+        self.ev_staged, self.ev_taken = torch.cuda.Event(), torch.cuda.Event()
+        self.dropout = dropout
+
+    # -- one step ---------------------------------------------------------------------------------
+    def upload(self):
+        self.flat_static.copy_(self.flat_pinned, non_blocking=True)
+
+    def compute(self):
+        model, ops = self.model, self.ops
+        model.relation_mode = self.relation_mode
+        model.decoder.token_generator.static_tot_ext = self.meta["tot_ext"]   # known on the host: no .item() sync
+        if self.overlap is not None:
+            self.overlap.zero()
+        else:
+            self.bucket.zero()
+        for _ in range(self.n_micro):                 # micro-batches: gradients accumulate in .grad
+            ops.advance_rng(self.dev)
+            loss = model(self.static)
+            if self.n_micro > 1:
+                loss = loss / self.n_micro
+            loss.backward()
+        if self.overlap is not None:
+            self.overlap.finish()                     # joins the bucket all-reduces issued during backward
+        elif self.world > 1:
+            self.bucket.pack()                        # one multi-tensor copy into the flat all-reduce buffer
+        self.loss_buf.copy_(loss.detach())
+
+    def prepare(self):
+        """eager warm-up (counts kernel launches of one step), then capture the step as one CUDA graph"""
+        dist, lib = self.dist, self.lib
+        self.upload()
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self.compute()
+            side.synchronize()
+            l0 = lib.gtos_launch_count()
+            self.compute()
+            self.launches_per_step = lib.gtos_launch_count() - l0
+            side.synchronize()
+            if self.use_graph:
+                ok = 1
+                try:
+                    self.graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(self.graph, stream=side):
+                        self.compute()
+                except Exception as e:                # e.g. a collective that cannot be captured on this stack
+                    ok = 0
+                    self.graph = None
+                    sys.stderr.write(f"[bench] rank {self.rank}: graph capture with in-graph collectives failed: {e!r}\n")
+                if self.overlap is not None:          # every rank must take the same path
+                    flag = torch.tensor([ok], device=self.dev)
+                    torch.cuda.synchronize()
+                    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                    if int(flag.item()) == 0:
+                        self.overlap.remove()
+                        self.overlap = None
+                        for _ in range(2):
+                            self.compute()
+                        side.synchronize()
+                        self.graph = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(self.graph, stream=side):
+                            self.compute()
+                elif not ok:
+                    raise RuntimeError("CUDA graph capture of the step failed")
+        torch.cuda.synchronize()
+
+    @property
+    def dp_mode(self):
+        if self.world == 1:
+            return "single"
+        return ("3 buckets all-reduced during backward, inside the step's CUDA graph" if self.overlap is not None
+                else "one flat all-reduce after the step")
+
+    def step_device(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.compute()
+        if self.overlap is None:
+            self.bucket.all_reduce_mean()
+
+    def stage_next(self):
+        """H2D of the next step's inputs on the copy stream (overlaps the current step's kernels)."""
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.ev_taken)   # the previous contents have been moved out of the staging buffer
+            self.flat_stage.copy_(self.flat_pinned, non_blocking=True)
+            self.ev_staged.record(self.copy_stream)
+
+    def step_e2e(self):
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self.ev_staged)                # this step's inputs have arrived
+        self.flat_static.copy_(self.flat_stage, non_blocking=True)
+        self.ev_taken.record(cur)
+        self.stage_next()                             # one H2D of all inputs per step, inside the timed region
+        self.step_device()
+        self.loss_host.copy_(self.loss_buf, non_blocking=True)  # D2H of the step's result
+
+    def step_e2e_serial(self):
+        self.upload()
+        self.step_device()
+        self.loss_host.copy_(self.loss_buf, non_blocking=True)
+
+    # -- timing -------------------------------------------------------------------------------------
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, fn, steps, warmup, clocks=None):
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        if clocks:
+            clocks.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        self.barrier()
+        ck = clocks.stop() if clocks else None
+        ms = e0.elapsed_time(e1) / steps
+        if self.world > 1:
+            t = torch.tensor([ms], device=self.dev)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, ck
+
+    def timed_e2e(self, steps, warmup=3):
+        self.ev_taken.record(torch.cuda.current_stream())
+        self.stage_next()                             # pipeline prologue: the first timed step's inputs
+        return self.timed(self.step_e2e, steps, warmup)[0]
+
+    def totals(self):
+        """(pairs, tokens, valid pairs) of one step summed over all ranks and micro-batches"""
+        m = self.meta
+        t = torch.tensor([float(m["pairs"]), float(m["tokens"]), float(m["valid_pairs"])], device=self.dev) * self.n_micro
+        if self.world > 1:
+            self.dist.all_reduce(t)
+        return t[0].item(), t[1].item(), t[2].item()
+
+    def check_gradient_average(self):
+        """a10 (train.py:74-79) on the real transport: after the all-reduce every rank must hold the mean of the ranks'
+        local flat gradients.  One eager step with dropout as configured; compared against an all_gather-computed mean."""
+        dist = self.dist
+        if self.world == 1:
+            return None
+        if self.overlap is not None:
+            self.overlap.enabled = False
+        self.bucket.zero()
+        for _ in range(self.n_micro):
+            loss = self.model(self.static)
+            (loss / self.n_micro if self.n_micro > 1 else loss).backward()
+        self.bucket.pack()
+        local = self.bucket.flat.clone()
+        self.bucket.all_reduce_mean()
+        gathered = [torch.empty_like(local) for _ in range(self.world)]
+        dist.all_gather(gathered, local)
+        mean = torch.stack(gathered).mean(0)
+        err = (self.bucket.flat - mean).abs().max()
+        scale = mean.abs().max().clamp_min(1e-30)
+        differ = (gathered[0] - gathered[-1]).abs().max()          # ranks own different shards: locals must differ
+        t = torch.stack([err / scale, differ / scale])
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        rel, dif = t[0].item(), t[1].item()
+        if self.overlap is not None:
+            self.overlap.enabled = True
+        if not (rel < 1e-5 and dif > 0):
+            raise RuntimeError(f"gradient average check failed: max |allreduce - mean of locals| / max|mean| = {rel:.3e}, "
+                               f"local gradients differ by {dif:.3e}")
+        return {"max_rel_err_vs_allgather_mean": rel, "local_gradients_differ_rel": dif, "flat_elements": int(local.numel()),
+                "checked_on": "every rank (asserted); reference: train.py:74-79"}
+
+
+def strong_leg(name, args, model, dev, rank, world, steps):
+    """a fixed-global-batch workload (BASELINE.json configs[2], [3]) on the same replica: ms per global step, max over
+    ranks.  Compare the values of the N = 1, 2, 4, 8 runs for strong scaling."""
+    r = StepRunner(name, model, args.dropout, dev, rank, world, use_graph=not args.no_graph)
+    r.prepare()
+    ms, _ = r.timed(r.step_device, steps, 2)
+    pairs, tokens, valid = r.totals()
+    w = r.w
+    out = {"workload": workload_text(name, w, args.dropout), "scaling": "strong", "global_batch": w["global"],
+           "graphs_per_gpu": r.per_gpu, "micro_batch": r.micro, "micro_batches_per_step": r.n_micro,
+           "nodes_incl_cls": r.meta["N"], "distinct_relation_paths_per_micro_batch": r.meta["R"],
+           "ms_per_step": ms, "node_pairs_per_sec": pairs / (ms * 1e-3), "decoder_tokens_per_sec": tokens / (ms * 1e-3),
+           "relation": REL_MODE_NOTE[r.relation_mode], "cuda_graph": r.graph is not None, "steps": steps,
+           "gradient_exchange": r.dp_mode, "gpu_launches_per_step": int(r.launches_per_step),
+           "batch_build_s": r.batch_build_s,
+           "relation_tensors_built_on": "gpu (gtos_graph_paths + assemble_relation_batch, SURVEY 8 f-3)"
+           if w.get("device_paths") else "host"}
+    del r
+    torch.cuda.empty_cache()
+    return out
+
+
+def device_batch_leg(args, runner, dev, steps=10):
+    """SURVEY 8 f-3 wired into the step: the relation tensors of every step are built ON THE GPU from the graphs'
+    padded adjacency (H2D of the adjacency only) - fresh shortest-path draws per step like data.py:150 - and handed to
+    the same hot-path step.  Eager (R, the number of distinct paths, changes from step to step)."""
+    from gtos_b200 import paths as P, synthetic as S
+    w, model, ops = runner.w, runner.model, runner.ops
+    graphs, counts, _ = S.make_graphs(runner.micro, w["n_max"], seed=19940117 + runner.rank)
+    packed_host = P.pack_edges(counts, *S.edge_arrays(graphs), n_max=w["n_max"])
+    pinned = [t.pin_memory() for t in packed_host]
+    adj_bytes = sum(t.numel() * t.element_size() for t in pinned)
+    batch = dict(runner.static)
+    times = {"construct": 0.0}
+
+    def construct(i):
+        packed = [t.to(dev, non_blocking=True) for t in pinned]
+        sl, pl = P.shortest_label_paths(*packed, w["path"], S.SELF, S.TL, seed_off=ops.new_seed_off())
+        out = P.assemble_relation_batch(sl, pl, packed[0], S.CLS, S.RCLS, S.SELF)
+        return out
+
+    def step(i):
+        out = construct(i)
+        batch.update(out)
+        runner.bucket.zero()
+        ops.advance_rng(dev)
+        loss = model(batch)
+        loss.backward()
+        runner.loss_host.copy_(loss.detach(), non_blocking=True)
+        return out
+
+    def timeit(fn, n):
+        for i in range(2):
+            fn(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    ms_c = timeit(construct, steps)
+    ms_s = timeit(step, steps)
+    out = construct(0)
+    pairs = int((torch.tensor(counts, dtype=torch.int64) ** 2).sum())
+    written = pairs * (w["path"] * 4 + 4)
+    return {"construct_ms": ms_c, "graph_pairs_per_sec": pairs / (ms_c * 1e-3), "adjacency_h2d_bytes": adj_bytes,
+            "algorithmic_bytes_written": written, "distinct_paths_last_step": int(out["relation_bank"].shape[1]),
+            "eager_step_with_construction_ms": ms_s,
+            "note": "per step: H2D of the padded adjacency, gtos_graph_paths (one uniformly drawn shortest label path per "
+                    "ordered pair), assemble_relation_batch (bank de-duplication, one host read for R), then the same "
+                    "hot-path step eagerly (no CUDA graph: R varies per step); replaces AMRGraph.py:100-115 + "
+                    "data.py:134-176 on the host"}
+
+
+def reference_on_gpu_leg(args, w, cfg, runner, dev, steps=3):
+    """informational library baseline: the reference's own modules under PyTorch eager on the same B200,
+    same batch, fp32 (TF32 off)."""
+    from gtos_b200 import hotpath
+    mods = reference_modules()
+    if mods is None:
+        return {"unavailable": "oracle/_ref not staged"}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(19940117)
+    m = hotpath.HotPath(cfg, modules=mods).to(dev)
+    m.train(args.dropout > 0)
+    params = list(m.parameters())
+    batch = runner.static
+
+    def step():
+        for v in params:
+            v.grad = None
+        loss = m(batch)
+        loss.backward()
+        return loss
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del m
+    torch.cuda.empty_cache()
+    return {"ms_per_step": ms, "node_pairs_per_sec": runner.meta["pairs"] / (ms * 1e-3), "dtype": "f32 (TF32 off)",
+            "note": "unmodified reference modules, PyTorch eager (cuBLAS / cuDNN) on this GPU, same batch and step; "
+                    "informational - the graded baseline is the CPU run"}
+
+
 def main_ours(args):
     import torch.distributed as dist
-    from gtos_b200 import _lib, hotpath, ops
-    from gtos_b200.dp import FlatGradBucket
+    from gtos_b200 import _lib, hotpath
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -229,237 +651,134 @@ def main_ours(args):
     cfg = make_cfg(w, args.dropout)
     torch.manual_seed(19940117)                       # identical replicas on every rank
     model = hotpath.HotPath(cfg).to(dev)
-    model.banked_relation = not args.dense_relation
     model.train(args.dropout > 0)
-    host, meta = make_host_batch(w, w["B"], 19940117 + rank)          # each rank owns its shard of the global batch
-    model.decoder.token_generator.static_tot_ext = meta["tot_ext"]   # known on the host: no .item() sync
-    # All inputs of a step travel as ONE flat pinned buffer -> ONE H2D copy.  The e2e loop is double-buffered like a real
-    # input pipeline: while step i computes, the copy engine uploads step i+1's inputs into a device staging buffer; at
-    # the start of step i+1 one device-to-device copy moves them into the buffers the captured graph reads.
-    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
-    offs, total = {}, 0
-    for k, v in host.items():
-        offs[k] = total
-        total += (v.numel() * v.element_size() + 255) // 256 * 256
-    flat_pinned = torch.empty(total, dtype=torch.uint8).pin_memory()
-    flat_stage = torch.empty(total, dtype=torch.uint8, device=dev)
-    flat_static = torch.empty(total, dtype=torch.uint8, device=dev)
-
-    def _views(flat):
-        return {k: flat[offs[k]:offs[k] + v.numel() * v.element_size()].view(v.dtype).view(v.shape) for k, v in host.items()}
-
-    pinned, static = _views(flat_pinned), _views(flat_static)
-    for k, v in host.items():
-        pinned[k].copy_(v)
-    bucket = FlatGradBucket(model.parameters(), bind=False)
-    loss_buf = torch.zeros((), device=dev)
-    loss_host = torch.zeros((), pin_memory=True)
-    # data parallel: one flat all-reduce after the step (default).  GTOS_DP_OVERLAP=1 splits it into three buckets launched
-    # from backward hooks and captured in the step's CUDA graph (dp.OverlappedGradBuckets).  Measured at N=2 on B200:
-    # 10.83 ms with the overlap vs 10.56 ms without (N=1: 10.34 ms) - the 118 MB exchange costs only ~0.2 ms over NVLink 5
-    # and the in-graph NCCL kernels take SMs from the latency-bound backward, so it is off by default.
-    from gtos_b200.dp import OverlappedGradBuckets
-    overlap = None
-    if world > 1 and os.environ.get("GTOS_DP_OVERLAP", "0") == "1":
-        overlap = OverlappedGradBuckets([
-            list(model.decoder.parameters()) + list(model.snt_encoder.parameters()),
-            list(model.graph_encoder.parameters()) + list(model.probe_generator.parameters()),
-            list(model.relation_encoder.parameters())])
-
-    def upload():
-        flat_static.copy_(flat_pinned, non_blocking=True)
-
-    def compute():
-        if overlap is not None:
-            overlap.zero()
-        else:
-            bucket.zero()
-        ops.advance_rng(dev)
-        loss = model(static)
-        loss.backward()
-        if overlap is not None:
-            overlap.finish()                          # joins the bucket all-reduces issued during backward
-        elif world > 1:
-            bucket.pack()                             # one multi-tensor copy into the flat all-reduce buffer
-        loss_buf.copy_(loss.detach())
-
-    upload()
-    torch.cuda.synchronize()
+    rel_mode = args.relation_mode or ("gather" if args.dense_relation else None)
+    run = StepRunner(args.workload, model, args.dropout, dev, rank, world, relation_mode=rel_mode,
+                     use_graph=not args.no_graph)
     if args.profile_step:
+        run.upload()
+        torch.cuda.synchronize()
         for _ in range(2):
-            compute()
+            run.compute()
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStart()
-        compute()
+        run.compute()
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStop()
         return
-    # --- warm-up eagerly (also counts kernel launches of one step), then capture the step as one CUDA graph ---
-    side = torch.cuda.Stream()
-    with torch.cuda.stream(side):
-        for _ in range(2):
-            compute()
-        side.synchronize()
-        l0 = lib.gtos_launch_count()
-        compute()
-        launches_per_step = lib.gtos_launch_count() - l0
-        side.synchronize()
-        graph = None
-        if not args.no_graph:
-            ok = 1
-            try:
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph, stream=side):
-                    compute()
-            except Exception as e:                    # e.g. a collective that cannot be captured on this stack
-                ok = 0
-                graph = None
-                sys.stderr.write(f"[bench] rank {rank}: graph capture with in-graph collectives failed: {e!r}\n")
-            if overlap is not None:                   # every rank must take the same path
-                flag = torch.tensor([ok], device=dev)
-                torch.cuda.synchronize()
-                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-                if int(flag.item()) == 0:
-                    overlap.remove()
-                    overlap = None
-                    for _ in range(2):
-                        compute()
-                    side.synchronize()
-                    graph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(graph, stream=side):
-                        compute()
-            elif not ok:
-                raise RuntimeError("CUDA graph capture of the step failed")
-    torch.cuda.synchronize()
-    dp_mode = "single" if world == 1 else ("3 buckets all-reduced during backward, inside the step's CUDA graph"
-                                           if overlap is not None else "one flat all-reduce after the step")
+    run.prepare()
+    grad_check = run.check_gradient_average()
+    steps = args.steps if run.n_micro == 1 else max(2, min(args.steps, 5))
+    ms, clocks = run.timed(run.step_device, steps, max(3, args.warmup), Clocks(local) if rank == 0 else None)
+    ms_e2e_serial, _ = run.timed(run.step_e2e_serial, steps, 3)
+    ms_e2e = run.timed_e2e(steps)
+    loss_val = float(run.loss_buf.item())
+    meta = run.meta
+    total_pairs, total_tokens, total_valid = run.totals()
 
-    def step_device():
-        if graph is not None:
-            graph.replay()
-        else:
-            compute()
-        if overlap is None:
-            bucket.all_reduce_mean()
-
-    copy_stream = torch.cuda.Stream()
-    ev_staged, ev_taken = torch.cuda.Event(), torch.cuda.Event()
-
-    def stage_next():
-        """H2D of the next step's inputs on the copy stream (overlaps the current step's kernels)."""
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(ev_taken)          # the previous contents have been moved out of the staging buffer
-            flat_stage.copy_(flat_pinned, non_blocking=True)
-            ev_staged.record(copy_stream)
-
-    def step_e2e():
-        cur = torch.cuda.current_stream()
-        cur.wait_event(ev_staged)                     # this step's inputs have arrived
-        flat_static.copy_(flat_stage, non_blocking=True)
-        ev_taken.record(cur)
-        stage_next()                                  # one H2D of all inputs per step, inside the timed region
-        step_device()
-        loss_host.copy_(loss_buf, non_blocking=True)  # D2H of the step's result
-
-    def step_e2e_serial():
-        upload()
-        step_device()
-        loss_host.copy_(loss_buf, non_blocking=True)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps, warmup, clocks=None):
-        for _ in range(warmup):
-            fn()
-        barrier()
-        if clocks:
-            clocks.start()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        barrier()
-        ck = clocks.stop() if clocks else None
-        ms = e0.elapsed_time(e1) / steps
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = t.item()
-        return ms, ck
-
-    ms, clocks = timed(step_device, args.steps, max(3, args.warmup), Clocks(local) if rank == 0 else None)
-    ms_e2e_serial, _ = timed(step_e2e_serial, args.steps, 3)
-    ev_taken.record(torch.cuda.current_stream())
-    stage_next()                                      # pipeline prologue: the first timed step's inputs
-    ms_e2e, _ = timed(step_e2e, args.steps, 3)
-    loss_val = float(loss_buf.item())
-
-    # --- breakdown on rank 0: encoder-only and decoder-only steps, and the dominant kernel alone ---
     extra = {}
+    if not args.no_extras and args.workload == "cfg2":
+        # the same step with the relation kept factorised (a 2-line caller change, so not the headline)
+        r2 = StepRunner("cfg2", model, args.dropout, dev, rank, world, relation_mode="banked", use_graph=not args.no_graph)
+        r2.prepare()
+        ms_b, _ = r2.timed(r2.step_device, steps, 3)
+        extra["f0_banked_step"] = {"ms_per_step": ms_b, "node_pairs_per_sec": total_pairs / (ms_b * 1e-3),
+                                   "relation": REL_MODE_NOTE["banked"], "gpu_launches_per_step": int(r2.launches_per_step)}
+        del r2
+        torch.cuda.empty_cache()
+        strong = {}
+        for name in ("cfg3", "cfg4"):
+            try:
+                strong[name] = strong_leg(name, args, model, dev, rank, world, 5 if name == "cfg3" else 2)
+            except Exception as e:                    # the headline line must survive a failure of an extra leg
+                strong[name] = {"error": repr(e)[:300]}
+                if world > 1:
+                    raise
+        extra["strong_scaling"] = strong
+    # --- breakdown on rank 0: encoder-only and decoder-only steps, and the dominant kernels alone ---
     if rank == 0 and not args.no_breakdown:
-        extra = breakdown(args, w, cfg, model, static, meta, dev, lib)
-    total_pairs = meta["pairs"] * world
-    total_tokens = meta["tokens"] * world
-    total_valid = meta["valid_pairs"] * world
-    if world > 1:
-        t = torch.tensor([float(meta["pairs"]), float(meta["tokens"]), float(meta["valid_pairs"])], device=dev)
-        dist.all_reduce(t)
-        total_pairs, total_tokens, total_valid = t[0].item(), t[1].item(), t[2].item()
+        extra.update(breakdown(args, w, cfg, model, run.static, meta, dev, lib, ms))
+        if not args.no_extras and world == 1:
+            for key, fn in (("batch_construction_f3", lambda: device_batch_leg(args, run, dev)),
+                            ("reference_on_gpu_eager", lambda: reference_on_gpu_leg(args, w, cfg, run, dev))):
+                try:
+                    extra[key] = fn()
+                except Exception as e:
+                    extra[key] = {"error": repr(e)[:300]}
     if rank != 0:
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
         return
     pk = peaks()
+    strong_mode = "global" in w
     line = {
         "metric": METRIC, "value": total_pairs / (ms * 1e-3), "unit": "node-pairs/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "steps": steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong" if strong_mode else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "decoder_tokens_per_sec": total_tokens / (ms * 1e-3),
         "valid_node_pairs_per_sec": total_valid / (ms * 1e-3),      # sum_b (n_b + 1)^2: pairs of un-padded nodes only
-        "config": {"workload": f"{args.workload}: gtos generator/ default (4 graph + 1 snt + 3 inference layers, "
-                               f"{w['D']} dim, {w['H']} heads), synthetic <= {w['n_max']}-node graphs, fwd+bwd, "
-                               f"dropout {args.dropout}", "graphs_per_gpu": w["B"], "global_batch": w["B"] * world,
+        "config": {"workload": workload_text(args.workload, w, args.dropout), "graphs_per_gpu": run.per_gpu,
+                   "global_batch": run.per_gpu * world, "micro_batch": run.micro,
                    "nodes_incl_cls": meta["N"], "tgt_len": meta["T"], "distinct_relation_paths": meta["R"],
-                   "parallelism": f"dp{world}", "relation": "dense fp32 bank[idx] (generator.py:79)" if args.dense_relation else
-                   "bank-factorised (SURVEY 8 f-0): bf16 gather fwd, bank-row GEMMs bwd",
+                   "parallelism": f"dp{world}", "relation": REL_MODE_NOTE[run.relation_mode],
+                   "arithmetic": "bf16 tensor-core operands, fp32 accumulation, fp32 activations / parameters / gradients "
+                                 "at module boundaries (tolerance 1e-2, the north star's bf16 mode)",
                    "step": "RelationEncoder+gather+GraphTransformer+snt+DecodeLayer "
                    "fwd+bwd (+ flat-gradient all-reduce when dp>1); optimizer outside the hot path",
-                   "cuda_graph": graph is not None, "gradient_exchange": dp_mode,
+                   "cuda_graph": run.graph is not None, "gradient_exchange": run.dp_mode,
                    "l2": "per-step working set (dense relation fp32+bf16 = %d MB) exceeds the 126 MB L2"
                          % (meta["pairs"] * w["D"] * 6 // 2 ** 20)},
         "e2e": {"value": total_pairs / (ms_e2e * 1e-3), "unit": "node-pairs/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                "h2d_bytes_per_step": run.h2d_bytes * run.n_micro if run.n_micro == 1 else run.h2d_bytes,
+                "d2h_bytes_per_step": 4,
                 "decoder_tokens_per_sec": total_tokens / (ms_e2e * 1e-3),
                 "input_pipeline": "double-buffered: the H2D of step i+1's inputs (one flat pinned buffer, copy stream) "
                                   "overlaps step i; every timed step issues one H2D of all inputs and one D2H of the loss",
                 "ms_per_step_serial_upload": ms_e2e_serial},
-        "gpu_launches": int(launches_per_step) * args.steps,
-        "gpu_launches_per_step": int(launches_per_step),
+        "gpu_launches": int(run.launches_per_step) * steps,
+        "gpu_launches_per_step": int(run.launches_per_step),
         "loss": loss_val, "clocks": clocks, "peaks": pk,
     }
+    if grad_check is not None:
+        line["gradient_average_check"] = grad_check
     line.update(extra)
     if not args.skip_cpu_baseline and world == 1:
-        Bc = args.cpu_sample_graphs
-        dt, mc = run_cpu(w, cfg, Bc, 3, 1, 19940117)
+        Bc = args.cpu_sample_graphs or run.micro
+        dt, mc, kind = run_cpu(w, cfg, Bc, 1, 1, 19940117)
         line["cpu_baseline"] = {"value": mc["pairs"] / dt, "unit": "node-pairs/s", "cores": host_threads(),
-                                "kind": "port", "ms_per_step": dt * 1e3,
+                                "kind": kind, "ms_per_step": dt * 1e3,
                                 "decoder_tokens_per_sec": mc["tokens"] / dt,
-                                "sample": f"{Bc} of {w['B']} graphs per step, 3 steps after 1 warm-up "
-                                          f"(CPU oracle port of the reference path, {cpu_model_name()})"}
+                                "sample": (f"the full batch of the GPU arm ({Bc} graphs)" if Bc == run.micro else
+                                           f"{Bc} of {run.micro} graphs per step") +
+                                          f", 1 step after 1 warm-up; {kind_text(kind)}; {cpu_model_name()}"}
     print(json.dumps(line), flush=True)
     if world > 1:
-        graph = None                                  # drop captured collectives before the communicator goes away
+        run.graph = None                              # drop captured collectives before the communicator goes away
         torch.cuda.synchronize()
         dist.barrier()
         dist.destroy_process_group()
 
 
-def breakdown(args, w, cfg, model, static, meta, dev, lib):
+def step_flops(w, meta, static):
+    """algorithmic FLOPs of one training step (fwd + bwd = 3 x fwd) as exact GEMM sums of the reference's path"""
+    D, F, H, V = w["D"], w["F"], w["H"], w["V"]
+    N, B, T = meta["N"], meta["B"], meta["T"]
+    P, Mn, Mt, Ms = meta["pairs"], N * B, T * B, (N - 1) * B
+    enc_layer = P * (4 * D * D + 4 * D) + Mn * (8 * D * D + 4 * D * F)
+    enc = w["gl"] * enc_layer
+    Ltot = int(static["relation_length"].sum().item())
+    R = meta["R"]
+    rnn = w["rnn"]
+    relenc = Ltot * (2 * 3 * rnn * (100 + rnn) * 2 + 2 * 3 * rnn * (2 * rnn + rnn) * 2) + R * 2 * (2 * rnn) * D
+    layer = Mt * (8 * D * D + 4 * D * T) + Mt * 4 * D * D + Ms * 4 * D * D + Mt * 4 * D * (N - 1) + Mt * 4 * D * F
+    tokgen = Mt * 4 * D * D + Ms * 4 * D * D + Mt * 4 * D * (N - 1) + Mt * 2 * D * 300 + Mt * 2 * 300 * V + Mt * 2 * 300 * 2
+    dec = (w["sl"] + w["il"]) * layer + tokgen
+    return {"encoder": 3.0 * enc, "relation_encoder": 3.0 * relenc, "decoder": 3.0 * dec,
+            "total": 3.0 * (enc + relenc + dec)}
+
+
+def breakdown(args, w, cfg, model, static, meta, dev, lib, ms_step=None):
     """Encoder-only / decoder-only step times and the dominant kernel (fused relation projection+score) timed
     alone with CUDA events on its launch stream -> roofline."""
     from gtos_b200 import _lib, ops
@@ -590,19 +909,48 @@ def breakdown(args, w, cfg, model, static, meta, dev, lib):
     ms_k = time_fn(k_score, steps=20, warmup=3)
     kflops = meta["pairs"] * (4 * D * D + 2 * D)
     pk = peaks()
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tp) and args.workload == "cfg2":
-        tj = json.load(open(tp))
-        traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+    traffic, traffic_src = None, None
+    for tp in ("r02_traffic.json", "r01_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", tp)
+        if os.path.exists(tpath) and args.workload == "cfg2":
+            tj = json.load(open(tpath))
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+            traffic_src = f"static: read from the committed ncu --set full capture profiles/{tp} (not measured by this run)"
+            break
     ach = kflops / (ms_k * 1e-3) / 1e12
     out["roofline"] = {"kernel": "gemm_tn_kernel<256, MODE_SCORE> (gtos_rel_score: relation_in_proj GEMM + score epilogue)",
                        "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                       "frac": ach / pk["bf16_tflops"], "traffic": traffic, "ms_per_launch": ms_k,
+                       "frac": ach / pk["bf16_tflops"], "traffic": traffic, "traffic_source": traffic_src,
+                       "ms_per_launch": ms_k,
                        "algorithmic_flops_per_launch": kflops,
                        "algorithmic_bytes_per_launch": meta["pairs"] * D * 2,
                        "peak_source": pk["source"] + ", burst bf16 cuBLAS (kernel timed alone)",
-                       "tile_utilisation": meta["pairs"] / (ops.rel_tiling(N, B, D, H)["tiles"] * 128)}
+                       "tile_utilisation": meta["pairs"] / (ops.rel_tiling(N, B, D, H)["tiles"] * 128),
+                       "why_this_kernel": "dominant by FLOPs (75 % of the step's algorithmic work with its three backward "
+                                          "siblings); see roofline_time_dominant for the kernel family with the largest "
+                                          "share of device TIME"}
+    # the kernel family with the largest share of the step's device time: the plain projection GEMM (every Linear),
+    # timed alone at the encoder's shape [N*B, D] x [D, D]^T
+    xa = torch.randn(N * B, D, device=dev).to(torch.bfloat16)
+    wb = torch.randn(D, D, device=dev).to(torch.bfloat16)
+    yo = torch.empty(N * B, D, device=dev)
+    ms_p = time_fn(lambda: ops.gemm_tn(xa, wb, D, out=yo), steps=50, warmup=5)
+    pflops = 2.0 * N * B * D * D
+    out["roofline_time_dominant"] = {
+        "kernel": "gemm_tn_kernel<BN, MODE_PLAIN> (gtos_gemm_tn: every Linear) at [%d, %d] x [%d, %d]^T" % (N * B, D, D, D),
+        "bound": "tensor (latency-bound at this size)", "achieved": pflops / (ms_p * 1e-3) / 1e12, "peak": pk["bf16_tflops"],
+        "unit": "TFLOP/s", "frac": pflops / (ms_p * 1e-3) / 1e12 / pk["bf16_tflops"], "ms_per_launch": ms_p,
+        "algorithmic_flops_per_launch": pflops, "traffic": None,
+        "note": "back-to-back launches on one stream (programmatic dependent launch overlaps prologues)"}
+    if ms_step is not None:
+        fl = step_flops(w, meta, static)
+        sus = pk.get("bf16_tflops_sustained") or pk["bf16_tflops"]
+        out["step_roofline"] = {"algorithmic_flops_per_step": fl["total"], "parts": fl,
+                                "achieved": fl["total"] / (ms_step * 1e-3) / 1e12, "peak": sus, "unit": "TFLOP/s",
+                                "frac": fl["total"] / (ms_step * 1e-3) / 1e12 / sus,
+                                "peak_source": pk["source"] + ", sustained bf16 cuBLAS (whole step)",
+                                "note": "exact GEMM M*N*K sums of the reference's path (SURVEY 8d), fwd+bwd = 3x fwd, "
+                                        "recomputation not counted; padded rows counted like the metric counts padded pairs"}
     # the other three relation GEMMs of the backward
     tiles = ops.rel_tiling(N, B, D, H)["tiles"]
     G = torch.empty(tiles * 128, 2 * D, dtype=torch.bfloat16, device=dev)

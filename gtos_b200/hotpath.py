@@ -33,20 +33,37 @@ class _V:
 
 
 class HotPath(nn.Module):
-    def __init__(self, cfg: HotPathConfig):
+    """`modules`: where the four hot-path classes come from - None = this package (the B200 implementation); tests and
+    bench.py's CPU arm pass the reference's own modules (same constructor calls as generator.py:27-42, same wiring), so
+    both arms run literally the same caller code.
+
+    `relation_mode`: how `relation = bank[idx]` reaches the graph encoder -
+      "index_select"  the caller's own line, generator.py:79: a dense fp32 [N,N,B,D] tensor built by torch (the
+                      unchanged-caller contract; the only mode the reference modules understand)
+      "gather"        ops.bank_gather: same dense fp32 tensor + its bf16 operand copy in one pass (1-line caller change)
+      "banked"        ops.BankedRelation: kept factorised (SURVEY.md 8 f-0, 2-line caller change)"""
+
+    def __init__(self, cfg: HotPathConfig, modules=None, relation_mode="banked"):
         super().__init__()
         c = self.cfg = cfg
         vocabs = {"relation": _V(c.rel_vocab_size), "predictable_token": _V(c.vocab_size)}
         self.vocabs = vocabs
-        self.relation_encoder = RelationEncoder(vocabs["relation"], c.rel_dim, c.embed_dim, c.rnn_hidden_size,
-                                                c.rnn_num_layers, c.dropout)
-        self.graph_encoder = GraphTransformer(c.graph_layers, c.embed_dim, c.ff_embed_dim, c.num_heads, c.dropout)
-        self.snt_encoder = Transformer(c.snt_layers, c.embed_dim, c.ff_embed_dim, c.num_heads, c.dropout,
-                                       with_external=True)
-        self.decoder = DecodeLayer(vocabs, c.inference_layers, c.embed_dim, c.ff_embed_dim, c.num_heads,
-                                   c.concept_dim, c.rel_dim, c.dropout)
+        RelEnc = modules.RelationEncoder if modules is not None else RelationEncoder
+        GraphTf = modules.GraphTransformer if modules is not None else GraphTransformer
+        Tf = modules.Transformer if modules is not None else Transformer
+        DecL = modules.DecodeLayer if modules is not None else DecodeLayer
+        self.native = modules is None
+        self.relation_encoder = RelEnc(vocabs["relation"], c.rel_dim, c.embed_dim, c.rnn_hidden_size,
+                                       c.rnn_num_layers, c.dropout)
+        self.graph_encoder = GraphTf(c.graph_layers, c.embed_dim, c.ff_embed_dim, c.num_heads, c.dropout)
+        self.snt_encoder = Tf(c.snt_layers, c.embed_dim, c.ff_embed_dim, c.num_heads, c.dropout, with_external=True)
+        self.decoder = DecL(vocabs, c.inference_layers, c.embed_dim, c.ff_embed_dim, c.num_heads,
+                            c.concept_dim, c.rel_dim, c.dropout)
         self._prep_plan = ops.WeightPrepPlan()
-        self.banked_relation = True      # False: dense `relation_bank[idx]` exactly as generator.py:79 builds it
+        if not self.native:
+            relation_mode = "index_select"
+        assert relation_mode in ("index_select", "gather", "banked")
+        self.relation_mode = relation_mode
         self.probe_generator = nn.Linear(c.embed_dim, c.embed_dim)
         nn.init.normal_(self.probe_generator.weight, std=0.02)
         nn.init.constant_(self.probe_generator.bias, 0.)
@@ -55,18 +72,22 @@ class HotPath(nn.Module):
         """generator.py:76-94: relation bank -> dense relation -> graph encoder -> probe / node states."""
         bank = self.relation_encoder(batch["relation_bank"], batch["relation_length"])
         idx = batch["relation"]
-        if self.banked_relation:
+        if self.relation_mode == "banked":
             # §8 f-0: keep relation = bank[idx] factorised (the 2-line caller change, INTEGRATION.md): no fp32
             # [N,N,B,D] tensor, bank-row GEMMs in the backward
             relation = ops.BankedRelation(bank, idx)
-        else:
+        elif self.relation_mode == "gather":
             relation = ops.bank_gather(bank, idx)                                   # generator.py:79 (+ bf16 copy)
+        else:
+            relation = bank.index_select(0, idx.view(-1)).view(*idx.size(), -1)     # generator.py:79, verbatim
         h = self.graph_encoder(batch["x"], relation, self_padding_mask=batch["node_mask"])
         probe = torch.tanh(self.probe_generator(h[:1]))
         return h[1:], batch["node_mask"][1:], probe
 
     def forward(self, batch):
         """generator.py:169-182 -> scalar loss."""
+        if not self.native:
+            return self._forward(batch)
         with self._prep_plan.step():             # weight operand copies issued ahead, beside the RelationEncoder
             return self._forward(batch)
 

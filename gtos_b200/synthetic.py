@@ -76,6 +76,43 @@ def _shortest_label_paths(adj, src):
     return path
 
 
+def make_graphs(B, n_max, n_labels=100, seed=SEED, full=False):
+    """the synthetic graphs alone: (adjacency lists, node counts, vocabulary) - same graphs as make_graph_batch draws"""
+    rng = np.random.default_rng(seed)
+    vocab = RelVocab(n_labels)
+    graphs, counts = [], []
+    for b in range(B):
+        n = n_max if (b == 0 or full) else int(rng.integers(math.ceil(0.5 * n_max), n_max + 1))
+        counts.append(n)
+        graphs.append(_random_graph(n, rng, vocab))
+    return graphs, counts, vocab
+
+
+def edge_arrays(graphs):
+    """adjacency lists -> (graph, src, dst, label) rows, one per directed edge in insertion order (paths.pack_edges)"""
+    g_, u_, v_, l_ = [], [], [], []
+    for b, adj in enumerate(graphs):
+        for u, a in enumerate(adj):
+            for v, lab in a:
+                g_.append(b); u_.append(u); v_.append(v); l_.append(lab)
+    return (np.asarray(g_, dtype=np.int64), np.asarray(u_, dtype=np.int64), np.asarray(v_, dtype=np.int64),
+            np.asarray(l_, dtype=np.int64))
+
+
+def make_graph_batch_device(B, n_max, device, max_path_len=4, n_labels=100, seed=SEED, full=False, seed_off=0):
+    """make_graph_batch with the relation tensors built ON THE GPU: the synthetic graphs travel as a
+    padded adjacency, gtos_graph_paths draws one shortest label path per ordered pair, assemble_relation_batch
+    de-duplicates them into bank / lengths / index.  Returns the same dictionary (tensors on the host)."""
+    from . import paths as P
+    graphs, counts, vocab = make_graphs(B, n_max, n_labels, seed, full)
+    packed = P.pack_edges(counts, *edge_arrays(graphs), n_max=n_max, device=device)
+    sl, pl = P.shortest_label_paths(*packed, max_path_len, SELF, TL, seed_off=seed_off)
+    out = P.assemble_relation_batch(sl, pl, packed[0], CLS, RCLS, SELF)
+    return dict(relation_bank=out["relation_bank"].cpu(), relation_length=out["relation_length"].cpu(),
+                relation=out["relation"].cpu(), node_counts=torch.tensor(counts), N=n_max + 1, rel_vocab=vocab,
+                packed_adjacency=packed)
+
+
 def make_graph_batch(B, n_max, max_path_len=4, n_labels=100, seed=SEED, full=False):
     """Returns dict(relation_bank [Lmax,R] int64, relation_length [R] int64, relation [N,N,B] int64,
     node_counts [B], N) with N = n_max + 1 (the <CLS> slot)."""
@@ -116,10 +153,14 @@ def make_graph_batch(B, n_max, max_path_len=4, n_labels=100, seed=SEED, full=Fal
                 node_counts=torch.tensor(counts), N=N, rel_vocab=vocab)
 
 
-def make_batch(B, n_max, D, T_max=60, T_min=20, V=10000, max_path_len=4, seed=SEED, full=False):
+def make_batch(B, n_max, D, T_max=60, T_min=20, V=10000, max_path_len=4, seed=SEED, full=False, device_paths=None):
     """Graph batch + the dense inputs of the hot path: node features x [N,B,D] = LayerNorm(randn),
-    padding mask [N,B], teacher-forced token states [T,B,D], token padding mask, copy_seq [N-1,B], target [T,B]."""
-    g = make_graph_batch(B, n_max, max_path_len=max_path_len, seed=seed, full=full)
+    padding mask [N,B], teacher-forced token states [T,B,D], token padding mask, copy_seq [N-1,B], target [T,B].
+    device_paths = a CUDA device: the relation tensors come from the GPU path builder (make_graph_batch_device)."""
+    if device_paths is not None:
+        g = make_graph_batch_device(B, n_max, device_paths, max_path_len=max_path_len, seed=seed, full=full)
+    else:
+        g = make_graph_batch(B, n_max, max_path_len=max_path_len, seed=seed, full=full)
     gen = torch.Generator().manual_seed(seed)
     N = g["N"]
     x = torch.nn.functional.layer_norm(torch.randn(N, B, D, generator=gen), (D,))

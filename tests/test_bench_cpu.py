@@ -1,5 +1,6 @@
-"""bench.py contract on CPU: the reference arm (`--impl reference`, the oracle port on the host cores) prints ONE JSON line
-with the keys the driver reads, and - launched as a non-zero rank - prints nothing and exits 0."""
+"""bench.py contract on CPU: the reference arm (`--impl reference`: the reference's own modules staged under oracle/_ref,
+or the oracle port when they are absent) prints ONE JSON line with the keys the driver reads, and - launched as a
+non-zero rank - prints nothing and exits 0."""
 import json
 import os
 import subprocess
@@ -22,7 +23,9 @@ def test_reference_arm_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "encoder_node_pairs_per_sec" and d["unit"] == "node-pairs/s"
     assert d["value"] > 0 and d["higher_is_better"] is True and d["steps"] == 1
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    from oracle import ref_loader as RL
+    want_kind = "reference" if RL.have_ref("generator") else "port"
+    assert d["cpu_baseline"]["kind"] == want_kind and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "node-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
 

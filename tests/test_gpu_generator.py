@@ -1,0 +1,113 @@
+"""-m gpu: the reference's UNMODIFIED caller over the drop-in modules (SURVEY.md §4 test-plan items 4 and 5).
+
+`oracle/_ref/generator/generator.py` (staged copy of the reference, oracle/ref_loader.py) is imported twice: once over
+the reference's own modules (CPU, fp32 - the checker) and once with gtos_b200/dropin in front of it on sys.path, so its
+`Generator` is assembled from the B200 modules exactly as INTEGRATION.md describes.  Same state_dict, same batch:
+  * Generator.forward loss and parameter gradients (generator.py:169-182), tolerance 1e-2 (bf16 tensor-core operands)
+  * Generator.work -> search_by_batch beam search (generator.py:97-112, search.py:114-168): same token sequences
+  * Generator.encoder_attn (get_attn_weights over the evaluation multi-path relation mean, generator.py:53-69)
+Skipped when the staged reference is absent (build() stages it; it travels to the GPU box with the snapshot)."""
+import os
+import sys
+
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import gen_harness as GH                         # noqa: E402
+from conftest import l2_err                      # noqa: E402
+from oracle import ref_loader as RL              # noqa: E402
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not RL.have_ref("generator"), reason="oracle/_ref not staged")]
+SEED = 19940117
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a B200")
+    from gtos_b200 import _lib
+    _lib.check(_lib.load().gtos_device_check(), "device_check")
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def pair(dev):
+    """(reference Generator on the CPU, reference Generator class over the drop-in modules on the GPU), same weights"""
+    ref_ns, our_ns = RL.load("generator"), RL.load("generator", dropin=True)
+    assert our_ns.generator.GraphTransformer.__module__ == "gtos_b200.graph_transformer"
+    assert our_ns.generator.DecodeLayer.__module__ == "gtos_b200.decoder"
+    assert ref_ns.generator.GraphTransformer.__module__ == "graph_transformer"
+    vocabs = GH.make_vocabs()
+    torch.manual_seed(SEED)
+    ref = GH.build_generator(ref_ns.generator, vocabs, 0.0, "cpu")
+    torch.nn.init.normal_(ref.concept_depth.weight, std=0.02)       # zero-initialised in the reference (generator.py:51)
+    GH.boost(ref, 3.0)
+    with torch.no_grad():
+        ref.decoder.token_generator.generator.bias[3] += 2.0        # <END> likely enough that some hypotheses complete
+    ours = GH.build_generator(our_ns.generator, vocabs, 0.0, 0)
+    missing = ours.load_state_dict(ref.state_dict())
+    assert not missing.missing_keys and not missing.unexpected_keys
+    ours = ours.to(dev)
+    return ref, ours, vocabs, ref_ns, our_ns
+
+
+def test_generator_forward_loss_and_gradients(pair, dev):
+    ref, ours, vocabs, _, _ = pair
+    ref.train()
+    ours.train()                                                    # dropout probability is 0: the exact path
+    data = GH.make_data(vocabs, B=6, n_max=12, T=9)
+    loss_ref = ref(data)
+    loss_ref.backward()
+    loss = ours(GH.to_device(data, dev))
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - loss_ref.item()) / abs(loss_ref.item()) < 1e-2, (loss.item(), loss_ref.item())
+    gr = dict(ref.named_parameters())
+    worst = {}
+    for n, p in ours.named_parameters():
+        if gr[n].grad is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, n
+            continue
+        worst[n] = l2_err(p.grad, gr[n].grad)
+    bad = {n: e for n, e in worst.items() if e > 5e-2}
+    assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:8]
+    # the front-end (reference TokenEncoder on both sides) receives its gradient through the hot path
+    assert worst["concept_encoder.out_proj.weight"] < 5e-2 and worst["token_encoder.out_proj.weight"] < 5e-2
+    for p in list(ref.parameters()) + list(ours.parameters()):
+        p.grad = None
+
+
+@pytest.mark.parametrize("beam", [1, 3])
+def test_generator_beam_search_tokens(pair, dev, beam):
+    ref, ours, vocabs, _, _ = pair
+    ref.eval()
+    ours.eval()
+    data = GH.make_data(vocabs, B=5, n_max=10, T=6, seed=SEED + beam, eval_paths=3)
+    with RL.cpu_cuda_noop():
+        beams_ref = ref.work(data, beam, 8)
+    beams = ours.work(GH.to_device(data, dev), beam, 8)
+    same = 0
+    for b_ref, b_our in zip(beams_ref, beams):
+        h_ref, h_our = b_ref.get_k_best(1, 0.6)[0], b_our.get_k_best(1, 0.6)[0]
+        if h_ref.seq == h_our.seq:
+            same += 1
+            assert abs(h_ref.score - h_our.score) < 2e-2 * max(1.0, abs(h_ref.score)), (h_ref.score, h_our.score)
+        else:
+            # a different winner is only acceptable as a near-tie under the reference's own scoring
+            sc = {tuple(h.seq): h.score for h in b_ref.completed_hypotheses + b_ref.hypotheses}
+            assert tuple(h_our.seq) in sc and abs(sc[tuple(h_our.seq)] - h_ref.score) < 2e-2 * max(1.0, abs(h_ref.score)), \
+                (h_ref.seq, h_our.seq)
+    assert same >= len(beams_ref) - 1, f"only {same} of {len(beams_ref)} best hypotheses agree"
+
+
+def test_generator_encoder_attention_weights(pair, dev):
+    ref, ours, vocabs, _, _ = pair
+    ref.eval()
+    ours.eval()
+    data = GH.make_data(vocabs, B=4, n_max=11, T=5, seed=SEED + 7, eval_paths=2)
+    a_ref = ref.encoder_attn(data)
+    a = ours.encoder_attn(GH.to_device(data, dev))
+    assert a.shape == a_ref.shape
+    assert (a.cpu() - a_ref).abs().max().item() < 1e-2

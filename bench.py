@@ -102,45 +102,87 @@ def make_host_batch(w, B, seed, device_paths=None):
 # clocks sampler (B200_PROFILING.md): nvidia-smi during the timed region
 # ------------------------------------------------------------------------------------------------
 class Clocks:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle-reason samples DURING the timed region (B200_PROFILING.md clocks line).  NVML is polled from a
+    thread every few milliseconds (nvidia-smi -lms takes longer to start than a 0.2 s timed region lasts); the sampler
+    is started before the warm-up steps and `mark()` / `stop()` bracket the timed region - only samples between the two
+    count.  Falls back to one nvidia-smi query per sample if pynvml is unavailable."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.idx, self.rows, self.proc = gpu_index, [], None
+    def __init__(self, gpu_index, period_s=0.004):
+        self.idx, self.rows, self.period = gpu_index, [], period_s
+        self._stop = threading.Event()
+        self.t0 = None
+        self.thread = None
+        self.h = None
+        self.src = "nvml"
 
-    def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm = sorted(int(r[1]) for r in self.rows if len(r) >= 9 and r[1].isdigit())
-        mx = max([int(r[2]) for r in self.rows if len(r) >= 9 and r[2].isdigit()] or [0])
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower() == "active"})
-        pw = []
-        for r in self.rows:
+    def _phys_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
             try:
-                pw.append(float(r[3]))
+                return int(vis.split(",")[self.idx])
             except (ValueError, IndexError):
                 pass
-        pw.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons,
-                "samples": len(sm), "power_w": pw[len(pw) // 2] if pw else None}
+        return self.idx
+
+    def _sample_nvml(self):
+        import pynvml as N
+        sm = N.nvmlDeviceGetClockInfo(self.h, N.NVML_CLOCK_SM)
+        mx = N.nvmlDeviceGetMaxClockInfo(self.h, N.NVML_CLOCK_SM)
+        pw = N.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+        rs = N.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(N, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else N.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        return (time.perf_counter(), sm, mx, pw, [n for bit, n in self.REASONS.items() if rs & bit])
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self._phys_index()), f"--query-gpu={self.Q}",
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+        c = [x.strip() for x in out.strip().split(",")]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        return (time.perf_counter(), int(c[0]), int(c[1]), float(c[2]), [n for n, v in zip(names, c[3:7]) if v.lower() == "active"])
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                self.rows.append(self._sample_nvml() if self.src == "nvml" else self._sample_smi())
+            except Exception:
+                if self.src == "nvml":
+                    self.src = "nvidia-smi"
+                else:
+                    return
+            time.sleep(self.period)
+
+    def start(self):
+        """start polling (call before the warm-up steps)"""
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            self.h = N.nvmlDeviceGetHandleByIndex(self._phys_index())
+        except Exception:
+            self.src = "nvidia-smi"
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
+
+    def mark(self):
+        """the timed region starts now"""
+        self.t0 = time.perf_counter()
+
+    def stop(self):
+        t1 = time.perf_counter()
+        self._stop.set()
+        if self.thread is not None:
+            self.thread.join(timeout=15)
+        rows = [r for r in self.rows if self.t0 is not None and self.t0 <= r[0] <= t1]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples inside the timed region"], "samples": 0,
+                    "source": self.src}
+        sm = sorted(r[1] for r in rows)
+        pw = sorted(r[3] for r in rows)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(r[2] for r in rows),
+                "reasons": sorted({n for r in rows for n in r[4]}), "samples": len(rows), "power_w": pw[len(pw) // 2],
+                "source": self.src}
 
 
 def peaks():
@@ -454,11 +496,13 @@ class StepRunner:
         torch.cuda.synchronize()
 
     def timed(self, fn, steps, warmup, clocks=None):
+        if clocks:
+            clocks.start()
         for _ in range(warmup):
             fn()
         self.barrier()
         if clocks:
-            clocks.start()
+            clocks.mark()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
@@ -969,11 +1013,12 @@ def breakdown(args, w, cfg, model, static, meta, dev, lib, ms_step=None):
     # the same score kernel launched back to back for ~1.5 s with the clocks sampler on: the burst number above is
     # taken over 20 launches (2 ms); this one shows what power / clock management leaves of it
     n_sus = max(50, int(1500.0 / ms_k))
-    ck = Clocks(torch.cuda.current_device())
+    ck = Clocks(torch.cuda.current_device(), period_s=0.05)
+    ck.start()
     for _ in range(20):
         k_score()
     torch.cuda.synchronize()
-    ck.start()
+    ck.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(n_sus):

@@ -276,6 +276,10 @@ int gtos_bank_gather(const float* bank, const int64_t* idx, int64_t P, int32_t D
                      void* stream) {
   return bank_gather(bank, reinterpret_cast<const long long*>(idx), P, D, out_f32, out_bf16, S(stream));
 }
+int gtos_bank_gather_mean(const float* bank, const int64_t* idx, int64_t P, int32_t K, int32_t D, float* out_f32,
+                          void* out_bf16, void* stream) {
+  return bank_gather_mean(bank, reinterpret_cast<const long long*>(idx), P, K, D, out_f32, out_bf16, S(stream));
+}
 int gtos_bank_scatter_add(const float* d_rel, const int64_t* idx, int64_t P, int32_t D, float* d_bank, int64_t R,
                           void* stream) {
   return bank_scatter_add(d_rel, reinterpret_cast<const long long*>(idx), P, D, d_bank, R, S(stream));

@@ -828,6 +828,47 @@ __global__ void bank_scatter_add_kernel(const float* __restrict__ d_rel, const l
   }
 }
 
+// evaluation batches (generator.py:83-88): relation[p] = mean over the pair's shortest paths of bank rows, where index 0
+// (<PAD>) marks an empty slot: sum_k [idx[p][k] != 0] bank[idx[p][k]] / max(1, #{k: idx[p][k] != 0}).  One warp per pair.
+__global__ void bank_gather_mean_kernel(const float* __restrict__ bank, const long long* __restrict__ idx, long P, int K, int D,
+                                        float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16) {
+  GTOS_PDL_PROLOGUE();
+  const int lane = threadIdx.x & 31;
+  const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+  for (long p = warp; p < P; p += nwarps) {
+    const long long* ip = idx + p * K;
+    int cnt = 0;
+    for (int k = 0; k < K; ++k) cnt += (ip[k] != 0);
+    const float inv = 1.f / (float)(cnt > 0 ? cnt : 1);
+    for (int c = lane; c < D / 4; c += 32) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < K; ++k) {
+        const long long r = ip[k];
+        if (r != 0) {
+          const float4 v = reinterpret_cast<const float4*>(bank + r * D)[c];
+          a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+      }
+      a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv;
+      if (out_f32) reinterpret_cast<float4*>(out_f32 + p * D)[c] = a;
+      if (out_bf16) reinterpret_cast<uint2*>(out_bf16 + p * D)[c] = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+    }
+  }
+}
+
+int bank_gather_mean(const float* bank, const long long* idx, long P, int K, int D, float* out_f32, void* out_bf16,
+                     cudaStream_t st) {
+  GTOS_REQUIRE(D % 4 == 0 && K >= 1, "bank_gather_mean: D must be a multiple of 4 and K >= 1");
+  if (P == 0) return GTOS_OK;
+  long blocks = (P + 7) / 8;
+  if (blocks > 148L * 16) blocks = 148L * 16;
+  GTOS_KLAUNCH(bank_gather_mean_kernel, dim3((unsigned)blocks), dim3(256), 0, st, bank, idx, P, K, D, out_f32,
+               reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  GTOS_LAUNCH_CHECK();
+  return GTOS_OK;
+}
+
 int bank_gather(const float* bank, const long long* idx, long P, int D, float* out_f32, void* out_bf16, cudaStream_t st) {
   GTOS_REQUIRE(D % 4 == 0, "bank_gather: D must be a multiple of 4");
   if (P == 0) return GTOS_OK;

@@ -30,6 +30,8 @@ int token_nll_bwd(const float* dloss_row, const float* logits, long ldl, int V, 
                   const long long* copy_seq, const long long* target, long rows, int B, long long pad_idx,
                   const float* stats, float* dlogits, long lddl, float* dgate_logits, float* dalign, cudaStream_t st);
 int bank_gather(const float* bank, const long long* idx, long P, int D, float* out_f32, void* out_bf16, cudaStream_t st);
+int bank_gather_mean(const float* bank, const long long* idx, long P, int K, int D, float* out_f32, void* out_bf16,
+                     cudaStream_t st);
 int bank_scatter_add(const float* d_rel, const long long* idx, long P, int D, float* d_bank, long R, cudaStream_t st);
 int rel_dqk(const void* G, const RelTiling& rt, float* dq, float* dk, long ld, void* dq_bf16, void* dk_bf16,
             cudaStream_t st);

@@ -130,6 +130,9 @@ class DecodeEngine:
             W = max(int(table_width), self.V)
             m = self.mem
             if m is None or (m["S"], m["B"], m["W"]) != (S, B, W):
+                # new buffers: CUDA graphs captured against the old ones (BeamSearchDevice) must not be replayed -
+                # they carry the old pointers and the old S; `mem_epoch` lets their owner notice
+                self.mem_epoch = getattr(self, "mem_epoch", 0) + 1
                 m = self.mem = dict(S=S, B=B, W=W, ld=width,
                                     kv=torch.empty(S * B, width, dtype=torch.bfloat16, device=self.dev),
                                     pad=torch.zeros(S, B, dtype=torch.uint8, device=self.dev),
@@ -405,8 +408,15 @@ class BeamSearchDevice:
         self.embed_fn = embed_fn
         self.use_graphs, self.check_every = use_graphs, check_every
         self._graphs, self._pool, self.state = {}, None, None
+        self._graph_epoch = getattr(engine, "mem_epoch", 0)
 
     def _alloc(self, B):
+        epoch = getattr(self.eng, "mem_epoch", 0)
+        if self._graph_epoch != epoch:
+            # DecodeEngine.set_memory replaced its buffers (another S, B or table width): the captured per-position
+            # graphs point at the freed buffers and have the old S baked in - drop them (run() falls back to eager
+            # steps until capture() is called again)
+            self._graphs, self._graph_epoch = {}, epoch
         if self.state is not None and self.state.B == B:
             return
         dev, K = self.eng.dev, self.K

@@ -25,6 +25,15 @@ class GraphTransformer(nn.Module):
         # every layer reads the SAME relation tensor (:16-17): stage its bf16 copy once (or reuse the one
         # ops.bank_gather made while building the tensor)
         acc, token = None, None
+        if kv is not None and kv is not x:
+            # never used by gtos (generator.py:90); computed on the composed path layer by layer
+            if isinstance(relation, ops.BankedRelation):
+                relation = relation.dense()
+            for layer in self.layers:
+                x, _ = layer(x, relation, kv, self_padding_mask, self_attn_mask)
+            return x
+        if isinstance(relation, ops.BankedRelation) and relation.multi and torch.is_grad_enabled() and relation.requires_grad:
+            relation = relation.dense()            # gradients through the evaluation multi-path mean: dense autograd path
         if isinstance(relation, ops.BankedRelation):
             # bank-factorised relation: dense bf16 operand for the fused kernels, bank-row GEMMs
             # in the backward
@@ -46,6 +55,14 @@ class GraphTransformer(nn.Module):
         return x
 
     def get_attn_weights(self, x, relation, kv=None, self_padding_mask=None, self_attn_mask=None):
+        if kv is not None and kv is not x:
+            if isinstance(relation, ops.BankedRelation):
+                relation = relation.dense()
+            attns = []
+            for layer in self.layers:
+                x, attn = layer(x, relation, kv, self_padding_mask, self_attn_mask, need_weights=True)
+                attns.append(attn)
+            return torch.stack(attns)
         if isinstance(relation, ops.BankedRelation):
             relation, relb = None, relation.relb
         else:
@@ -87,9 +104,13 @@ class GraphTransformerLayer(nn.Module):
                  rel_acc=None):
         p = self.dropout if self.training else 0.0
         if kv is not None and kv is not x:
-            raise NotImplementedError("GraphTransformerLayer: kv != x is never used by gtos (generator.py:90)")
-        a, w = self.self_attn._forward(x, xb, relation, relb, self_padding_mask, self_attn_mask, need_weights,
-                                       rel_token, rel_acc)
+            # graph_transformer.py:52-55 `self_attn(query=x, key=kv, value=kv, ...)`: never used by gtos
+            # (generator.py:90); the general entry point computes it on the composed path
+            a, w = self.self_attn(x, kv, kv, relation, key_padding_mask=self_padding_mask, attn_mask=self_attn_mask,
+                                  need_weights=need_weights)
+        else:
+            a, w = self.self_attn._forward(x, xb, relation, relb, self_padding_mask, self_attn_mask, need_weights,
+                                           rel_token, rel_acc)
         x, xb = ops.add_layer_norm(a, x, self.attn_layer_norm.weight, self.attn_layer_norm.bias, p)
         h = ops.ffn(x, xb, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, p)
         x, xb = ops.add_layer_norm(h, x, self.ff_layer_norm.weight, self.ff_layer_norm.bias, p)
@@ -126,13 +147,11 @@ class RelationMultiheadAttention(nn.Module):
         nn.init.constant_(self.out_proj.bias, 0.)
 
     def _forward(self, x, xb, relation, relb, key_padding_mask, attn_mask, need_weights, rel_token=None, rel_acc=None):
-        if not self.weights_dropout:
-            raise NotImplementedError("RelationMultiheadAttention(weights_dropout=False) is never built by gtos")
         p = self.dropout if self.training else 0.0
         out, w = ops.RelAttnFn.apply(x, xb, relation, relb, ops.as_u8(key_padding_mask), ops.as_u8(attn_mask),
                                      self.in_proj_weight, self.in_proj_bias, self.relation_in_proj.weight,
                                      self.out_proj.weight, self.out_proj.bias, self.num_heads, float(p),
-                                     bool(need_weights), rel_token, rel_acc)
+                                     bool(need_weights), rel_token, rel_acc, bool(self.weights_dropout))
         if w is not None:
             w = w.permute(2, 3, 0, 1)           # [B,H,T,S] -> [tgt, src, bsz, heads]   (:168-170)
         return out, w
@@ -141,7 +160,16 @@ class RelationMultiheadAttention(nn.Module):
         """Input shape: Time x Batch x Channel; relation: tgt_len x src_len x bsz x dim (:94-98)."""
         if not (key is query and value is query) and not (
                 key.data_ptr() == query.data_ptr() == value.data_ptr() and key.shape == query.shape):
-            raise NotImplementedError("relation attention is self-attention in gtos (query is key is value)")
+            # the `kv_same` / general branches of graph_transformer.py:108-116: gtos always passes query = key = value
+            # (generator.py:90), so these run on the composed path (projections on the tcgen05 GEMM) instead of the
+            # fused kernel
+            if isinstance(relation, ops.BankedRelation):
+                relation = relation.dense()
+            p = self.dropout if self.training else 0.0
+            return ops.rel_attention_composed(query, key, value, relation, key_padding_mask, attn_mask,
+                                              self.in_proj_weight, self.in_proj_bias, self.relation_in_proj.weight,
+                                              self.out_proj.weight, self.out_proj.bias, self.num_heads, float(p),
+                                              bool(self.weights_dropout), bool(need_weights))
         return self._forward(query, None, relation, None, key_padding_mask, attn_mask, need_weights)
 
     # projection helpers kept for API parity (:176-197); they run the tcgen05 GEMM

@@ -502,7 +502,7 @@ class RelAttnFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, xb, relation, relb, key_pad, attn_mask, W_in, b_in, W_rel, W_out, b_out, H, p, need_weights,
-                rel_token=None, rel_acc=None):
+                rel_token=None, rel_acc=None, weights_dropout=True):
         _need_cuda(x, relation if relation is not None else relb, W_in)
         lib = _lib.load()
         N, B, D = x.shape
@@ -532,17 +532,23 @@ class RelAttnFn(torch.autograd.Function):
         att = torch.empty(NB, D, dtype=torch.float32, device=dev)
         attb = torch.empty(NB, D, dtype=torch.bfloat16, device=dev)
         seed, off = (rng_state(dev), new_seed_off()) if p > 0 else (None, 0)
+        p_w = p if weights_dropout else 0.0         # graph_transformer.py:154-161: dropout on the weights OR on the output
         d = _attn_desc(N, N, B, H, hd)
         d.v, d.ldv = vproj.data_ptr(), D
-        d.scale, d.p_drop = 1.0, p
+        d.scale, d.p_drop = 1.0, p_w
         d.scores_jt, d.key_pad, d.attn_mask = _p(scores), _p(key_pad), _p(attn_mask)
         d.seed_ptr, d.seed_off = _p(seed), off
         d.probs, d.probs_dropped = _p(probs), _p(wts)
         d.out, d.ldo, d.out_bf16 = _p(att), D, _p(attb)
         _lib.check(lib.gtos_attn_fwd(C.byref(d), _st()), "attn_fwd(enc)")
+        off2 = 0
+        if not weights_dropout and p > 0:
+            off2 = new_seed_off()
+            dropout_f32(att, p, seed, off2, out=att)
+            attb = cast_bf16(att)
         out, _ = gemm_tn(attb, Wob, D, bias=b_out)
         ctx.save_for_backward(xb2, relb, qkb, vproj, probs, attb, Wperm, WpermT, Wit, Wot, key_pad, attn_mask)
-        ctx.meta = (N, B, D, H, p, seed, off)
+        ctx.meta = (N, B, D, H, p, seed, off, p_w, off2)
         ctx.rel_acc = rel_acc if (rel_token is not None and rel_token.requires_grad) else None
         ctx.set_materialize_grads(False)            # unused attention weights: no zero-filled [B,H,N,N] gradient
         if wts is None:
@@ -553,7 +559,7 @@ class RelAttnFn(torch.autograd.Function):
     @once_differentiable
     def backward(ctx, dout, dwts):
         xb2, relb, qkb, vproj, probs, attb, Wperm, WpermT, Wit, Wot, key_pad, attn_mask = ctx.saved_tensors
-        N, B, D, H, p, seed, off = ctx.meta
+        N, B, D, H, p, seed, off, p_w, off2 = ctx.meta
         lib = _lib.load()
         hd = D // H
         if dout is None:
@@ -566,6 +572,8 @@ class RelAttnFn(torch.autograd.Function):
         with fork() as f_out:
             gemm_nn(doutb, attb, D, D, out=dW_out)
         datt, _ = gemm_tn(doutb, Wot, D)                                           # [NB, D]
+        if off2:
+            dropout_f32(datt, p, seed, off2, out=datt)
         dqkv = torch.empty(NB, 3 * D, dtype=torch.float32, device=dev)
         dqkv_b = torch.empty(NB, 3 * D, dtype=torch.bfloat16, device=dev) if (_grad_copies and D % 8 == 0) else None
         dqb_p = dqkv_b.data_ptr() if dqkv_b is not None else None
@@ -574,7 +582,7 @@ class RelAttnFn(torch.autograd.Function):
         ds_ts = torch.empty(B, H, N, N, dtype=torch.float32, device=dev)
         d = _attn_desc(N, N, B, H, hd)
         d.v, d.ldv = vproj.data_ptr(), D
-        d.scale, d.p_drop = 1.0, p
+        d.scale, d.p_drop = 1.0, p_w
         d.key_pad, d.attn_mask = _p(key_pad), _p(attn_mask)
         d.seed_ptr, d.seed_off = _p(seed), off
         d.probs = _p(probs)
@@ -628,7 +636,7 @@ class RelAttnFn(torch.autograd.Function):
             f_db.join()
             f_dbin.join()
             return (dx.view(N, B, D), None, None, None, None, None, dW_in, db_in, dW_rel, dW_out, db_out, None, None,
-                    None, None, None)
+                    None, None, None, None)
         _lib.check(lib.gtos_rel_dqk(_p(G), dqkv.data_ptr(), dqkv.data_ptr() + 4 * D, 3 * D, dqb_p, dkb_p, N, B, D, H, _st()),
                    "rel_dqk")
         if ctx.rel_acc is not None:
@@ -653,7 +661,76 @@ class RelAttnFn(torch.autograd.Function):
         f_db.join()
         f_dbin.join()
         return (dx.view(N, B, D), None, d_rel, None, None, None, dW_in, db_in, dW_rel, dW_out, db_out, None, None,
-                None, None, None)
+                None, None, None, None)
+
+
+def rel_attention_composed(query, key, value, relation, key_padding_mask, attn_mask, W_in, b_in, W_rel, W_out, b_out, H, p,
+                           weights_dropout, need_weights):
+    """RelationMultiheadAttention.forward for the argument combinations gtos itself never uses (key / value that are
+    not the query tensor): the five projections run on the tcgen05 GEMM (LinearFn), the small remainder is written with
+    PyTorch CUDA ops exactly as graph_transformer.py:118-172 states it.  CUDA only."""
+    import torch.nn.functional as F
+    T, B, D = query.shape
+    S = key.shape[0]
+    hd = D // H
+    q = linear(query, W_in[:D], b_in[:D])
+    k = linear(key, W_in[D:2 * D], b_in[D:2 * D])
+    v = linear(value, W_in[2 * D:], b_in[2 * D:])
+    q = q.contiguous().view(T, B * H, hd)
+    k = k.contiguous().view(S, B * H, hd)
+    v = v.contiguous().view(S, B * H, hd)
+    ra, rb = linear(relation, W_rel).chunk(2, dim=-1)
+    ra = ra.contiguous().view(T, S, B * H, hd).transpose(0, 1)
+    rb = rb.contiguous().view(T, S, B * H, hd).transpose(0, 1)
+    q = (q.unsqueeze(1) + ra) * (hd ** -0.5)
+    k = k.unsqueeze(0) + rb
+    w = torch.einsum('ijbn,ijbn->ijb', q, k)
+    if attn_mask is not None:
+        w = w.masked_fill(attn_mask.bool().unsqueeze(-1), float('-inf'))
+    if key_padding_mask is not None:
+        w = w.view(T, S, B, H).masked_fill(key_padding_mask.bool().unsqueeze(0).unsqueeze(-1), float('-inf')).view(T, S, B * H)
+    w = F.softmax(w, dim=1)
+    if weights_dropout:
+        w = F.dropout(w, p=p, training=p > 0)
+    attn = torch.einsum('ijb,jbn->bin', w, v)
+    if not weights_dropout:
+        attn = F.dropout(attn, p=p, training=p > 0)
+    attn = attn.transpose(0, 1).contiguous().view(T, B, D)
+    out = linear(attn, W_out, b_out)
+    return out, (w.view(T, S, B, H) if need_weights else None)
+
+
+def mha_composed(query, key, value, key_padding_mask, attn_mask, W_in, b_in, W_out, b_out, H, p, weights_dropout,
+                 need_weights):
+    """MultiheadAttention.forward with `key is not value` (transformer.py:113-118, never used by gtos): projections on
+    the tcgen05 GEMM, the rest as transformer.py:119-171 states it, in PyTorch CUDA ops.  CUDA only."""
+    import torch.nn.functional as F
+    T, B, D = query.shape
+    hd = D // H
+    q = linear(query, W_in[:D], b_in[:D]) * (hd ** -0.5)
+    k = linear(key, W_in[D:2 * D], b_in[D:2 * D])
+    v = linear(value, W_in[2 * D:], b_in[2 * D:])
+    q = q.contiguous().view(T, B * H, hd).transpose(0, 1)
+    k = k.contiguous().view(-1, B * H, hd).transpose(0, 1)
+    v = v.contiguous().view(-1, B * H, hd).transpose(0, 1)
+    S = k.size(1)
+    w = torch.bmm(q, k.transpose(1, 2))
+    if attn_mask is not None:
+        w = w.masked_fill(attn_mask.bool().unsqueeze(0), float('-inf'))
+    if key_padding_mask is not None:
+        w = w.view(B, H, T, S).masked_fill(key_padding_mask.bool().transpose(0, 1).unsqueeze(1).unsqueeze(2),
+                                           float('-inf')).view(B * H, T, S)
+    w = F.softmax(w, dim=-1)
+    if weights_dropout:
+        w = F.dropout(w, p=p, training=p > 0)
+    attn = torch.bmm(w, v)
+    if not weights_dropout:
+        attn = F.dropout(attn, p=p, training=p > 0)
+    attn = attn.transpose(0, 1).contiguous().view(T, B, D)
+    out = linear(attn, W_out, b_out)
+    if need_weights:
+        return out, w.view(B, H, T, S).max(dim=1)[0].transpose(0, 1)
+    return out, None
 
 
 class RelGradAcc:
@@ -679,17 +756,26 @@ class BankedRelation:
 
     def __init__(self, bank, idx):
         _need_cuda(bank, idx)
-        if bank.dim() != 2 or idx.dim() != 3 or idx.shape[0] != idx.shape[1]:
-            raise ValueError(f"BankedRelation: bank [R,D] and idx [N,N,B] expected, got {tuple(bank.shape)}, {tuple(idx.shape)}")
+        if bank.dim() != 2 or idx.dim() not in (3, 4) or idx.shape[0] != idx.shape[1]:
+            raise ValueError(f"BankedRelation: bank [R,D] and idx [N,N,B] (or [N,N,B,K], evaluation batches) expected, "
+                             f"got {tuple(bank.shape)}, {tuple(idx.shape)}")
         self.bank = bank
         self.idx = idx.contiguous()
+        # evaluation batches carry up to K shortest paths per pair, 0 = empty slot (data.py:176-225); the relation of a
+        # pair is the mean of their encodings (generator.py:83-88) - gather + mean fused, bf16 operand only
+        self.multi = idx.dim() == 4
         R, D = bank.shape
         with torch.no_grad():
             bank_c = bank.detach().contiguous()
             self.bankb = cast_bf16(bank_c)
-            self.relb = torch.empty(*idx.shape, D, dtype=torch.bfloat16, device=bank.device)
-            _lib.check(_lib.load().gtos_bank_gather(_p(bank_c), _p(self.idx), self.idx.numel(), D, None, _p(self.relb),
-                                                    _st()), "bank_gather")
+            self.relb = torch.empty(*idx.shape[:3], D, dtype=torch.bfloat16, device=bank.device)
+            if self.multi:
+                K = idx.shape[3]
+                _lib.check(_lib.load().gtos_bank_gather_mean(_p(bank_c), _p(self.idx), self.idx.numel() // K, K, D, None,
+                                                             _p(self.relb), _st()), "bank_gather_mean")
+            else:
+                _lib.check(_lib.load().gtos_bank_gather(_p(bank_c), _p(self.idx), self.idx.numel(), D, None, _p(self.relb),
+                                                        _st()), "bank_gather")
         self.keys = self.order = None
         self._heads = None
 
@@ -699,7 +785,7 @@ class BankedRelation:
 
     @property
     def shape(self):
-        return (*self.idx.shape, self.bank.shape[1])
+        return (*self.idx.shape[:3], self.bank.shape[1])
 
     def prepare(self, H):
         """sort the G rows (tile-major pair rows of gtos_rel_grad) by bank row - once per batch"""
@@ -715,8 +801,13 @@ class BankedRelation:
         self._heads = H
 
     def dense(self):
-        """the fp32 tensor the reference would build (bank[idx]) - for callers that need it materialised"""
-        return self.bank[self.idx]
+        """the fp32 tensor the reference would build - bank[idx] (generator.py:79), or for evaluation batches the mean
+        over a pair's paths with row 0 zeroed (generator.py:83-88) - for callers that need it materialised"""
+        if not self.multi:
+            return self.bank[self.idx]
+        bank0 = torch.cat([torch.zeros_like(self.bank[:1]), self.bank[1:]], 0)
+        cnt = self.idx.ne(0).sum(dim=3).clamp_(min=1).unsqueeze(-1).to(self.bank.dtype)
+        return bank0[self.idx].sum(dim=3) / cnt
 
 
 class BankTokenFn(torch.autograd.Function):

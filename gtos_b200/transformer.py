@@ -122,7 +122,11 @@ class MultiheadAttention(nn.Module):
         qkv_same = query.data_ptr() == key.data_ptr() == value.data_ptr() and query.shape == key.shape
         kv_same = key.data_ptr() == value.data_ptr() and key.shape == value.shape
         if not kv_same:
-            raise NotImplementedError("MultiheadAttention with key is not value is never used by gtos")
+            # transformer.py:113-118 (separate k and v inputs): never used by gtos - composed path
+            p = self.dropout if self.training else 0.0
+            return ops.mha_composed(query, key, value, key_padding_mask, attn_mask, self.in_proj_weight, self.in_proj_bias,
+                                    self.out_proj.weight, self.out_proj.bias, self.num_heads, float(p),
+                                    bool(self.weights_dropout), bool(need_weights))
         return self._forward(query, None, key, None, qkv_same, key_padding_mask, attn_mask, need_weights)
 
     def _in_proj(self, input, start=0, end=None):

@@ -183,6 +183,10 @@ int gtos_bank_gather(const float* bank, const int64_t* idx, int64_t P, int32_t D
                      void* stream);
 int gtos_bank_scatter_add(const float* d_rel, const int64_t* idx, int64_t P, int32_t D, float* d_bank, int64_t R,
                           void* stream);
+/* evaluation batches (generator.py:83-88: `relation[0,:] = 0; relation[idx].sum(3) / count(idx != 0).clamp(min=1)`):
+ * idx [P,K] with 0 = empty slot; out[p] = mean of the bank rows of the pair's shortest paths (fp32 and / or bf16). */
+int gtos_bank_gather_mean(const float* bank, const int64_t* idx, int64_t P, int32_t K, int32_t D, float* out_f32,
+                          void* out_bf16, void* stream);
 
 /* ---- RelationEncoder (encoder.py:90-119): embedding + GRU gate math; GEMMs via gtos_gemm_* ---- */
 int gtos_embed_gather(const float* table, const int64_t* idx, int64_t n, int32_t dim, float* out_f32, void* out_bf16,

@@ -299,6 +299,20 @@ def test_beam_search_device_scores_are_consistent_and_graphs_are_exact(dev):
     bs2.capture()
     best2 = bs2.run().k_best(K, 0.6)
     assert best2 == best
+    # a new batch with the same B but another memory length S: set_memory replaces the engine's buffers, so the graphs
+    # captured above (old pointers, old S) must be dropped, not replayed
+    S2 = S + 3
+    graph2 = torch.randn(S2, B, D, generator=gen).to(dev)
+    gmask2 = (torch.arange(S2).unsqueeze(1) >= torch.tensor([10, 3, 5, 8, 2, 6]).unsqueeze(0)).to(dev)
+    copy2 = torch.randint(4, c["V"] + 5, (S2, B), generator=gen).to(dev)
+    eng.set_memory(graph2, gmask2, probe, copy2, table_width=W)
+    got = bs2.run().k_best(K, 0.6)                             # would replay stale graphs without the epoch check
+    assert not bs2._graphs
+    want = BeamSearchDevice(eng, K, Tmax, 1, END, UNK, START, _embed_fn(emb, pos)).run().k_best(K, 0.6)
+    assert got == want
+    bs2.capture()
+    assert bs2.run().k_best(K, 0.6) == want
+    eng.set_memory(graph, gmask, probe, copy_seq, table_width=W)
     # the unfused bookkeeping (full table + torch.topk + BeamState) finds the same hypotheses
     bs3 = BeamSearchDevice(eng, K, Tmax, 1, END, UNK, START, _embed_fn(emb, pos), fused=False)
     best3 = bs3.run().k_best(K, 0.6)

@@ -71,8 +71,12 @@ def test_generator_forward_loss_and_gradients(pair, dev):
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, n
             continue
         worst[n] = l2_err(p.grad, gr[n].grad)
-    bad = {n: e for n, e in worst.items() if e > 5e-2}
+    # bf16 tensor-core operands against the fp32 reference, weights inflated x3: rel-L2 of every parameter gradient
+    # < 8e-2 (ReLU units whose pre-activation is within bf16 rounding of zero flip), median < 2e-2
+    bad = {n: e for n, e in worst.items() if e > 8e-2}
     assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:8]
+    errs = sorted(worst.values())
+    assert errs[len(errs) // 2] < 2e-2, errs[len(errs) // 2]
     # the front-end (reference TokenEncoder on both sides) receives its gradient through the hot path
     assert worst["concept_encoder.out_proj.weight"] < 5e-2 and worst["token_encoder.out_proj.weight"] < 5e-2
     for p in list(ref.parameters()) + list(ours.parameters()):

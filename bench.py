@@ -687,10 +687,17 @@ def main_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    dp_overlap = world > 1 and os.environ.get("GTOS_DP_OVERLAP", "0") == "1"
+    if dp_overlap:
+        # gradient buckets are all-reduced WHILE the backward runs: give NCCL a few SMs of its own (the persistent
+        # tcgen05 GEMMs leave them free) instead of letting its CTAs displace GEMM CTAs
+        os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("GTOS_SM_RESERVE", "8"))
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     _lib.check(lib.gtos_device_check(), "device_check")
+    if dp_overlap:
+        _lib.check(lib.gtos_set_sm_reserve(int(os.environ.get("GTOS_SM_RESERVE", "8"))), "set_sm_reserve")
     w = WORKLOADS[args.workload]
     cfg = make_cfg(w, args.dropout)
     torch.manual_seed(19940117)                       # identical replicas on every rank

@@ -35,6 +35,7 @@ SIGNATURES = {
     "gtos_last_error": (C.c_char_p, []),
     "gtos_abi_version": (i32, []),
     "gtos_launch_count": (u64, []),
+    "gtos_set_sm_reserve": (i32, [i32]),
     "gtos_device_check": (i32, []),
     "gtos_debug_read_trace": (i32, [vp, i32]),
     "gtos_debug_attn_trace": (i32, [vp, i32]),

@@ -789,13 +789,25 @@ int choose_rel_tiling(RelTiling* t, int N, int B, int D, int H) {
 }
 
 static int g_num_sms = 0;
+static int g_sm_reserve = -1;   // SMs the persistent tcgen05 kernels leave free (for NCCL CTAs running beside them)
 static int num_sms() {
   if (g_num_sms == 0) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 148;
     if (cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) g_num_sms = 148;
   }
-  return g_num_sms;
+  if (g_sm_reserve < 0) g_sm_reserve = getenv("GTOS_SM_RESERVE") ? atoi(getenv("GTOS_SM_RESERVE")) : 0;
+  int n = g_num_sms - g_sm_reserve;
+  n &= ~1;                      // CTA pairs
+  return n < 2 ? 2 : n;
+}
+int set_sm_reserve(int n) {
+  if (n < 0 || n > 128) {
+    set_error("sm_reserve must be in [0, 128] (got %d)", n);
+    return GTOS_ERR_ARG;
+  }
+  g_sm_reserve = n;
+  return GTOS_OK;
 }
 
 int make_rel_tmaps(const RelTiling& rt, const void* relb, const void* q, const void* k, long ldqk,

@@ -86,6 +86,7 @@ struct GemmNnArgs {
   long workspace_elems;
 };
 long gemm_nn_workspace_elems(int M, int N, int Kd, int rel);
+int set_sm_reserve(int n);   // persistent GEMM grids use (SM count - n) CTAs
 int launch_gemm_nn(const GemmNnArgs& a, cudaStream_t stream);
 
 // permuted row order of relation_in_proj.weight: per head h, [ra_h (hd rows) | rb_h (hd rows)]

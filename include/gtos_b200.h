@@ -34,6 +34,11 @@ const char* gtos_last_error(void);
 int gtos_abi_version(void);
 /* number of CUDA kernels this library has enqueued so far in this process (bench.py's gpu_launches) */
 uint64_t gtos_launch_count(void);
+/* The persistent tcgen05 GEMMs launch one CTA per SM, and each CTA owns its SM (~200 KB of shared memory).  A collective
+ * that runs BESIDE them (data-parallel gradient buckets reduced during the backward pass, train.py:74-79) needs SMs of
+ * its own, or every GEMM launched meanwhile waits a second wave for the CTAs NCCL displaced.  n SMs are left free
+ * (default 0, or the GTOS_SM_RESERVE environment variable). */
+int gtos_set_sm_reserve(int32_t n);
 /* 0 if the current device is sm_100 and the TMA driver entry point resolves */
 int gtos_device_check(void);
 /* timing experiments only: with GTOS_DBG=2 in the environment the plain GEMM records 16 clock64 timestamps per CTA

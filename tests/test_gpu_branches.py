@@ -12,7 +12,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
-from conftest import rel_err                     # noqa: E402
+from conftest import l2_err, rel_err             # noqa: E402
 from oracle import ref_loader as RL              # noqa: E402
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not RL.have_ref("generator"), reason="oracle/_ref not staged")]
@@ -66,10 +66,11 @@ def test_relation_attention_with_separate_kv_matches_reference(dev):
     y, w = ours(xo, relo, kv=kvo, self_padding_mask=mask.to(dev), need_weights=True)
     (y * y).sum().backward()
     assert rel_err(y, y_ref) < 1e-2 and rel_err(w, w_ref) < 1e-2
-    assert rel_err(kvo.grad, kvr.grad) < 5e-2 and rel_err(relo.grad, relr.grad) < 5e-2
+    # gradients: relative L2 (weights inflated x4, bf16 operands vs the fp32 reference: single elements near ReLU kinks move more)
+    assert l2_err(kvo.grad, kvr.grad) < 5e-2 and l2_err(relo.grad, relr.grad) < 5e-2 and l2_err(xo.grad, xr.grad) < 5e-2
     g_ref = dict(ref.named_parameters())
     for n, p in ours.named_parameters():
-        assert rel_err(p.grad, g_ref[n].grad) < 6e-2, n
+        assert l2_err(p.grad, g_ref[n].grad) < 5e-2, n
     # the stack-level entry point takes the same branch
     enc_ref = ref_gt.GraphTransformer(2, D, F, H, 0.0)
     _boost(enc_ref)

@@ -400,12 +400,13 @@ class StepRunner:
             self.overlap.zero()
         else:
             self.bucket.zero()
+        from gtos_b200 import hotpath
         for _ in range(self.n_micro):                 # micro-batches: gradients accumulate in .grad
             ops.advance_rng(self.dev)
             loss = model(self.static)
             if self.n_micro > 1:
                 loss = loss / self.n_micro
-            loss.backward()
+            hotpath.backward(loss, fresh_grads=self.n_micro == 1)
         if self.overlap is not None:
             self.overlap.finish()                     # joins the bucket all-reduces issued during backward
         elif self.world > 1:

@@ -56,6 +56,9 @@ SIGNATURES = {
     "gtos_graph_bfs": (i32, [vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]),
     "gtos_graph_paths": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, u64, vp, vp, vp]),
     "gtos_rel_dqk": (i32, [vp, vp, vp, i64, vp, vp, i32, i32, i32, i32, vp]),
+    "gtos_rel_attn_banked_fwd": (i32, [vp, i64, vp, vp, vp, i64, vp, i64, vp, vp, f32, vp, u64, vp, vp, vp, i64, vp, i32, i32,
+                                       i32, i32, i32, vp]),
+    "gtos_rel_grad_banked": (i32, [vp, i64, vp, vp, vp, i64, vp, vp, i32, i32, i32, i32, i32, vp]),
     "gtos_rel_pair_keys": (i32, [vp, i32, i32, i32, i32, i32, vp, vp]),
     "gtos_rel_segsum": (i32, [vp, vp, vp, i64, i32, vp, i64, vp, vp]),
     "gtos_rel_dw_bank": (i32, [vp, i64, vp, vp, i32, i32, i32, vp]),

@@ -199,6 +199,30 @@ int gtos_rel_dqk(const void* G, float* dq, float* dk, int64_t ld, void* dq_bf16,
   return rel_dqk(G, rt, dq, dk, ld, dq_bf16, dk_bf16, S(stream));
 }
 
+int gtos_rel_attn_banked_fwd(const void* PB, int64_t ldpb, const int64_t* idx, const void* q, const void* k, int64_t ldqk,
+                             const float* v, int64_t ldv, const uint8_t* key_pad, const uint8_t* attn_mask, float p_drop,
+                             const void* seed_ptr, uint64_t seed_off, float* probs, float* probs_dropped, float* out,
+                             int64_t ldo, void* out_bf16, int32_t N, int32_t B, int32_t D, int32_t H, int32_t R,
+                             void* stream) {
+  RelBankedArgs a;
+  memset(&a, 0, sizeof(a));
+  a.PB = PB; a.ldpb = ldpb; a.idx = reinterpret_cast<const long long*>(idx); a.q = q; a.k = k; a.ldqk = ldqk;
+  a.v = v; a.ldv = ldv; a.key_pad = key_pad; a.attn_mask = attn_mask; a.p_drop = p_drop; a.seed_ptr = seed_ptr;
+  a.seed_off = seed_off; a.probs = probs; a.probs_dropped = probs_dropped; a.out = out; a.ldo = ldo; a.out_bf16 = out_bf16;
+  a.N = N; a.B = B; a.D = D; a.H = H; a.R = R;
+  return rel_attn_banked_fwd(a, S(stream));
+}
+
+int gtos_rel_grad_banked(const void* PB, int64_t ldpb, const int64_t* idx, const void* q, const void* k, int64_t ldqk,
+                         const float* dscores, void* G, int32_t N, int32_t B, int32_t D, int32_t H, int32_t R,
+                         void* stream) {
+  RelBankedArgs a;
+  memset(&a, 0, sizeof(a));
+  a.PB = PB; a.ldpb = ldpb; a.idx = reinterpret_cast<const long long*>(idx); a.q = q; a.k = k; a.ldqk = ldqk;
+  a.dscores = dscores; a.G = G; a.N = N; a.B = B; a.D = D; a.H = H; a.R = R;
+  return rel_grad_banked(a, S(stream));
+}
+
 static void fill_attn(const gtos_attn_desc* d, AttnArgs* a) {
   a->T = d->T; a->S = d->S; a->B = d->B; a->H = d->H; a->hd = d->hd;
   a->q = d->q; a->ldq = d->ldq; a->k = d->k; a->ldk = d->ldk; a->v = d->v; a->ldv = d->ldv;

@@ -1169,6 +1169,14 @@ static void nn_plan(int M, int N, int Kd, int rel, int* BN, int* KB, int* splits
   if (want < 1) want = 1;
   int per = (kblocks + want - 1) / want;
   if (per < 1) per = 1;
+  // Small contractions (the weight gradients of a 2.6-3.8 k row Linear: 41-60 k-blocks over 8 tiles) used to be split 18
+  // ways: 144 CTAs of 3-4 k-blocks each, every one of them reducing its whole 128 x BN fp32 tile into the output with
+  // vector atomics - 18 MB of atomic traffic for a 1 MB result (CUPTI timeline: 24.5 us per launch, atomics-bound) on
+  // all SMs, while the kernel only runs BESIDE the critical chain (side stream).  At least NN_MIN_KB k-blocks per CTA:
+  // 6-8 splits, a third of the atomics, and more than half of the SMs stay with the main chain.  Large contractions
+  // (GRU weight gradients: 1 541 k-blocks) keep one full wave.
+  static const int min_kb = getenv("GTOS_NN_MIN_KB") ? atoi(getenv("GTOS_NN_MIN_KB")) : 8;
+  if (!rel && per < min_kb) per = kblocks < min_kb ? kblocks : min_kb;
   *kb_per = per;
   *splits = (kblocks + per - 1) / per;
   if (*splits < 1) *splits = 1;

@@ -85,6 +85,21 @@ struct GemmNnArgs {
   float* workspace;    // >= splits*M*N floats
   long workspace_elems;
 };
+// bank-factorised relation attention (rel_banked.cu)
+struct RelBankedArgs {
+  const void* PB; long ldpb;                 // bf16 [R, 2D] = bank * Wperm^T (head-interleaved [ra_h | rb_h] columns)
+  const long long* idx;                      // int64 [N,N,B]: idx[j][i][b] = bank row of the pair (query i, key j)
+  const void* q; const void* k; long ldqk;   // bf16 [N*B, .] projected queries / keys
+  const float* v; long ldv;                  // fp32 [N*B, D] projected values
+  const uint8_t* key_pad; const uint8_t* attn_mask;
+  float p_drop; const void* seed_ptr; unsigned long long seed_off;
+  float* probs; float* probs_dropped;        // [B,H,N,N]
+  float* out; long ldo; void* out_bf16;      // [N*B, D]
+  const float* dscores; void* G;             // backward: d(score) [B,H,N(j),N(i)] -> G [tiles*128, 2D] bf16
+  int N, B, D, H, R;
+};
+int rel_attn_banked_fwd(const RelBankedArgs& a, cudaStream_t st);
+int rel_grad_banked(const RelBankedArgs& a, cudaStream_t st);
 long gemm_nn_workspace_elems(int M, int N, int Kd, int rel);
 int set_sm_reserve(int n);   // persistent GEMM grids use (SM count - n) CTAs
 int launch_gemm_nn(const GemmNnArgs& a, cudaStream_t stream);

@@ -1,0 +1,327 @@
+// gtos_b200 -- bank-factorised relation attention (forward half; caller generator/generator.py:76-90).
+//
+// relation = bank[idx] and relation_in_proj has no bias (generator/graph_transformer.py:80), so
+//     [ra_ij | rb_ij] = relation_in_proj(relation[j][i]) = PB[idx[j][i][b]],      PB = bank * W_r^T   ([R, 2D], one GEMM)
+// and the P-row projection GEMM of graph_transformer.py:122 (4 D^2 FLOP per node pair) collapses to an R-row GEMM plus a
+// gather of one 2D-wide bf16 row per pair out of an L2-resident table.  With the tensor work gone, the whole attention
+// of graph_transformer.py:122-159 fits ONE kernel per layer:
+//
+//   rel_attn_banked_fwd   CTA = (graph b, QI queries i, all keys j): gather PB rows, s_ij = hd^-1/2 <q_i + ra, k_j + rb>
+//                         per head, key-padding / attention mask, softmax over j, dropout, o_i = sum_j w_ij v_j.
+//                         Scores live in shared memory only.  L2-gather bound: 2 * 2D bytes per pair.
+//   rel_grad_banked       the backward's per-pair gradient rows G = hd^-1/2 ds_ij [k_j + rb | q_i + ra] from the same gather
+//                         (replaces the P-row recompute GEMM of gtos_rel_grad), written in gtos_rel_grad's tile-major
+//                         layout so rel_segsum / rel_dqk / rel_dw_bank consume it unchanged.
+//
+// Lane layout (both kernels): lane l of a warp owns DL = D/32 consecutive features of head h = l / (32/H); it loads the
+// matching DL-element pieces of ra and rb (2 * DL * 2 bytes), so one warp instruction pair covers a whole 2D-wide row and
+// a head's dot product is finished with log2(32/H) shuffles.
+#include "elementwise.cuh"
+#include "gemm.cuh"
+
+namespace gtos {
+
+struct RelBankedDev {
+  const __nv_bfloat16* PB; long ldpb;
+  const long long* idx;
+  const __nv_bfloat16* q; const __nv_bfloat16* k; long ldqk;
+  const float* v; long ldv;
+  const uint8_t* key_pad; const uint8_t* attn_mask;
+  float p_drop; const void* seed_ptr; unsigned long long seed_off;
+  float* probs; float* probs_dropped;
+  float* out; long ldo; __nv_bfloat16* out_bf16;
+  const float* dscores;        // [B,H,N(j),N(i)]
+  __nv_bfloat16* G;
+  RelTiling rt;
+  int N, B, D, H, hd, R, Npad;
+  float scale;
+};
+
+template <int DL>
+__device__ __forceinline__ void ld_bf16_raw(const __nv_bfloat16* p, uint32_t* r) {   // DL bf16 -> DL/2 packed words
+  if constexpr (DL == 4) {
+    const uint2 v = *reinterpret_cast<const uint2*>(p);
+    r[0] = v.x; r[1] = v.y;
+  } else {
+#pragma unroll
+    for (int t = 0; t < DL / 8; ++t) {
+      const uint4 v = *reinterpret_cast<const uint4*>(p + 8 * t);
+      r[4 * t] = v.x; r[4 * t + 1] = v.y; r[4 * t + 2] = v.z; r[4 * t + 3] = v.w;
+    }
+  }
+}
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+template <int DL, int QI>
+__global__ void __launch_bounds__(256) rel_attn_banked_fwd_kernel(const RelBankedDev a) {
+  GTOS_PDL_PROLOGUE();
+  extern __shared__ float sm[];
+  float* sc = sm;                                                   // [QI][H][Npad] scores -> (dropped) probabilities
+  int* s_idx = reinterpret_cast<int*>(sm + QI * a.H * a.Npad);      // [N][QI] bank rows
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i0 = blockIdx.x * QI, b = blockIdx.y;
+  const int N = a.N, B = a.B, H = a.H, hd = a.hd;
+  const int lph = 32 / H;                      // lanes per head
+  const int h = lane / lph, sub = lane - h * lph;
+  const int dcol = h * hd + sub * DL;          // this lane's features inside D (q, k)
+  const int pcol = h * 2 * hd + sub * DL;      // its ra piece inside the head-interleaved PB row; rb piece at + hd
+
+  float qv[QI][DL];
+#pragma unroll
+  for (int qi = 0; qi < QI; ++qi) {
+    const int i = i0 + qi;
+    uint32_t raw[DL / 2];
+#pragma unroll
+    for (int t = 0; t < DL / 2; ++t) raw[t] = 0u;
+    if (i < N) ld_bf16_raw<DL>(a.q + ((long)i * B + b) * a.ldqk + dcol, raw);
+#pragma unroll
+    for (int t = 0; t < DL / 2; ++t) { qv[qi][2 * t] = bf_lo(raw[t]); qv[qi][2 * t + 1] = bf_hi(raw[t]); }
+  }
+  for (int t = threadIdx.x; t < N * QI; t += 256) {
+    const int j = t / QI, qi = t - j * QI, i = i0 + qi;
+    long long r = (i < N) ? a.idx[((long)j * N + i) * B + b] : 0;
+    s_idx[t] = (r >= 0 && r < a.R) ? (int)r : 0;
+  }
+  __syncthreads();
+
+  // ---- scores: one warp per key j, all QI queries ----
+  for (int j = warp; j < N; j += 8) {
+    uint32_t kraw[DL / 2];
+    ld_bf16_raw<DL>(a.k + ((long)j * B + b) * a.ldqk + dcol, kraw);
+    uint32_t ra[QI][DL / 2], rb[QI][DL / 2];
+#pragma unroll
+    for (int qi = 0; qi < QI; ++qi) {
+      const __nv_bfloat16* pr = a.PB + (long)s_idx[j * QI + qi] * a.ldpb + pcol;
+      ld_bf16_raw<DL>(pr, ra[qi]);
+      ld_bf16_raw<DL>(pr + hd, rb[qi]);
+    }
+#pragma unroll
+    for (int qi = 0; qi < QI; ++qi) {
+      float acc = 0.f;
+#pragma unroll
+      for (int t = 0; t < DL / 2; ++t) {
+        acc = fmaf(qv[qi][2 * t] + bf_lo(ra[qi][t]), bf_lo(kraw[t]) + bf_lo(rb[qi][t]), acc);
+        acc = fmaf(qv[qi][2 * t + 1] + bf_hi(ra[qi][t]), bf_hi(kraw[t]) + bf_hi(rb[qi][t]), acc);
+      }
+      for (int o = lph >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (sub == 0) sc[(qi * H + h) * a.Npad + j] = acc * a.scale;
+    }
+  }
+  __syncthreads();
+
+  // ---- masks, softmax over keys, dropout (same counter-based draw as the attention core, so gtos_attn_bwd replays it) ----
+  const unsigned long long seed = a.p_drop > 0.f ? reinterpret_cast<const unsigned long long*>(a.seed_ptr)[0] + a.seed_off : 0ull;
+  const float ks = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
+  for (int r = warp; r < QI * H; r += 8) {
+    const int qi = r / H, hh = r - qi * H, i = i0 + qi;
+    float* w = sc + r * a.Npad;
+    if (i >= N) {
+      for (int j = lane; j < N; j += 32) w[j] = 0.f;
+      continue;
+    }
+    float mx = -INFINITY;
+    for (int j = lane; j < N; j += 32) {
+      const bool masked = (a.key_pad && a.key_pad[(long)j * B + b]) || (a.attn_mask && a.attn_mask[(long)i * N + j]);
+      const float v = masked ? -INFINITY : w[j];
+      w[j] = v;
+      mx = fmaxf(mx, v);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < N; j += 32) {
+      const float e = (w[j] == -INFINITY) ? 0.f : __expf(w[j] - mx);
+      w[j] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = sum > 0.f ? 1.f / sum : 0.f;
+    const long prow = (((long)b * H + hh) * N + i) * N;
+    for (int j = lane; j < N; j += 32) {
+      float p = w[j] * inv;
+      a.probs[prow + j] = p;
+      if (a.p_drop > 0.f) p = (rng_uniform(seed, (unsigned long long)(prow + j)) >= a.p_drop) ? p * ks : 0.f;
+      if (a.probs_dropped) a.probs_dropped[prow + j] = p;
+      w[j] = p;
+    }
+  }
+  __syncthreads();
+
+  // ---- PV: o_i = sum_j w_ij v_j; a thread owns two adjacent features (a warp = 64 features = inside one head when hd >= 64) ----
+  for (int f2 = threadIdx.x; f2 < a.D / 2; f2 += 256) {
+    const int f = 2 * f2, hh = f / hd;
+    float acc[QI][2];
+#pragma unroll
+    for (int qi = 0; qi < QI; ++qi) acc[qi][0] = acc[qi][1] = 0.f;
+    const float* vp = a.v + (long)b * a.ldv + f;
+    const float* wp = sc + hh * a.Npad;
+#pragma unroll 4
+    for (int j = 0; j < N; ++j) {
+      const float2 vv = *reinterpret_cast<const float2*>(vp + (long)j * B * a.ldv);
+#pragma unroll
+      for (int qi = 0; qi < QI; ++qi) {
+        const float p = wp[qi * H * a.Npad + j];
+        acc[qi][0] = fmaf(p, vv.x, acc[qi][0]);
+        acc[qi][1] = fmaf(p, vv.y, acc[qi][1]);
+      }
+    }
+#pragma unroll
+    for (int qi = 0; qi < QI; ++qi) {
+      const int i = i0 + qi;
+      if (i < N) {
+        const long o = ((long)i * B + b);
+        *reinterpret_cast<float2*>(a.out + o * a.ldo + f) = make_float2(acc[qi][0], acc[qi][1]);
+        if (a.out_bf16) *reinterpret_cast<uint32_t*>(a.out_bf16 + o * a.D + f) = pack_bf16x2(acc[qi][0], acc[qi][1]);
+      }
+    }
+  }
+}
+
+template <int DL, int QI>
+__global__ void __launch_bounds__(256) rel_grad_banked_kernel(const RelBankedDev a) {
+  GTOS_PDL_PROLOGUE();
+  extern __shared__ float sm[];
+  int* s_idx = reinterpret_cast<int*>(sm);                          // [N][QI]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i0 = blockIdx.x * QI, b = blockIdx.y;
+  const int N = a.N, B = a.B, H = a.H, hd = a.hd;
+  const int lph = 32 / H;
+  const int h = lane / lph, sub = lane - h * lph;
+  const int dcol = h * hd + sub * DL;
+  const int pcol = h * 2 * hd + sub * DL;
+  float qv[QI][DL];
+#pragma unroll
+  for (int qi = 0; qi < QI; ++qi) {
+    const int i = i0 + qi;
+    uint32_t raw[DL / 2];
+#pragma unroll
+    for (int t = 0; t < DL / 2; ++t) raw[t] = 0u;
+    if (i < N) ld_bf16_raw<DL>(a.q + ((long)i * B + b) * a.ldqk + dcol, raw);
+#pragma unroll
+    for (int t = 0; t < DL / 2; ++t) { qv[qi][2 * t] = bf_lo(raw[t]); qv[qi][2 * t + 1] = bf_hi(raw[t]); }
+  }
+  for (int t = threadIdx.x; t < N * QI; t += 256) {
+    const int j = t / QI, qi = t - j * QI, i = i0 + qi;
+    long long r = (i < N) ? a.idx[((long)j * N + i) * B + b] : 0;
+    s_idx[t] = (r >= 0 && r < a.R) ? (int)r : 0;
+  }
+  __syncthreads();
+  const RelTiling& rt = a.rt;
+  for (int j = warp; j < N; j += 8) {
+    uint32_t kraw[DL / 2];
+    ld_bf16_raw<DL>(a.k + ((long)j * B + b) * a.ldqk + dcol, kraw);
+    const int jb = j / rt.bj, jj = j - jb * rt.bj;
+    const float* dsp = a.dscores + (((long)b * H + h) * N + j) * N;
+#pragma unroll
+    for (int qi = 0; qi < QI; ++qi) {
+      const int i = i0 + qi;
+      if (i >= N) continue;                                        // warp-uniform
+      const __nv_bfloat16* pr = a.PB + (long)s_idx[j * QI + qi] * a.ldpb + pcol;
+      uint32_t ra[DL / 2], rb[DL / 2];
+      ld_bf16_raw<DL>(pr, ra);
+      ld_bf16_raw<DL>(pr + hd, rb);
+      const float g = dsp[i] * a.scale;
+      const int ib = i / rt.bi, ii = i - ib * rt.bi;
+      const long row = (((long)b * rt.nj_blk + jb) * rt.ni_blk + ib) * 128 + jj * rt.bi + ii;
+      __nv_bfloat16* gx = a.G + row * (2L * a.D) + pcol;           // d(q+ra) = g (k+rb) | d(k+rb) = g (q+ra)
+      uint32_t wx[DL / 2], wy[DL / 2];
+#pragma unroll
+      for (int t = 0; t < DL / 2; ++t) {
+        wx[t] = pack_bf16x2(g * (bf_lo(kraw[t]) + bf_lo(rb[t])), g * (bf_hi(kraw[t]) + bf_hi(rb[t])));
+        wy[t] = pack_bf16x2(g * (qv[qi][2 * t] + bf_lo(ra[t])), g * (qv[qi][2 * t + 1] + bf_hi(ra[t])));
+      }
+      if constexpr (DL == 4) {
+        *reinterpret_cast<uint2*>(gx) = make_uint2(wx[0], wx[1]);
+        *reinterpret_cast<uint2*>(gx + hd) = make_uint2(wy[0], wy[1]);
+      } else {
+#pragma unroll
+        for (int t = 0; t < DL / 8; ++t) {
+          *reinterpret_cast<uint4*>(gx + 8 * t) = make_uint4(wx[4 * t], wx[4 * t + 1], wx[4 * t + 2], wx[4 * t + 3]);
+          *reinterpret_cast<uint4*>(gx + hd + 8 * t) = make_uint4(wy[4 * t], wy[4 * t + 1], wy[4 * t + 2], wy[4 * t + 3]);
+        }
+      }
+    }
+  }
+}
+
+static int banked_check(const RelBankedArgs& a, RelBankedDev* d) {
+  GTOS_REQUIRE(a.N > 0 && a.B > 0 && a.H > 0 && a.D % a.H == 0, "rel_banked: bad shape N=%d B=%d D=%d H=%d", a.N, a.B, a.D, a.H);
+  const int hd = a.D / a.H;
+  GTOS_REQUIRE(a.D % 32 == 0 && 32 % a.H == 0 && (a.D / 32 == 4 || a.D / 32 == 8 || a.D / 32 == 16 || a.D / 32 == 32),
+               "rel_banked: needs D in {128,256,512,1024} and H dividing 32 (got D=%d H=%d)", a.D, a.H);
+  GTOS_REQUIRE(a.ldpb % 8 == 0 && a.ldqk % 8 == 0 && (reinterpret_cast<uintptr_t>(a.PB) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(a.q) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.k) & 15) == 0,
+               "rel_banked: PB / q / k rows must be 16-byte aligned");
+  memset(d, 0, sizeof(*d));
+  d->PB = reinterpret_cast<const __nv_bfloat16*>(a.PB); d->ldpb = a.ldpb;
+  d->idx = a.idx;
+  d->q = reinterpret_cast<const __nv_bfloat16*>(a.q); d->k = reinterpret_cast<const __nv_bfloat16*>(a.k); d->ldqk = a.ldqk;
+  d->v = a.v; d->ldv = a.ldv;
+  d->key_pad = a.key_pad; d->attn_mask = a.attn_mask;
+  d->p_drop = a.p_drop; d->seed_ptr = a.seed_ptr; d->seed_off = a.seed_off;
+  d->probs = a.probs; d->probs_dropped = a.probs_dropped;
+  d->out = a.out; d->ldo = a.ldo; d->out_bf16 = reinterpret_cast<__nv_bfloat16*>(a.out_bf16);
+  d->dscores = a.dscores; d->G = reinterpret_cast<__nv_bfloat16*>(a.G);
+  d->N = a.N; d->B = a.B; d->D = a.D; d->H = a.H; d->hd = hd; d->R = a.R;
+  d->Npad = (a.N + 3) & ~3;
+  d->scale = 1.0f / sqrtf((float)hd);
+  return GTOS_OK;
+}
+
+static constexpr int BANKED_QI = 4;
+
+template <int DL>
+static int launch_banked_fwd(const RelBankedDev& d, cudaStream_t st) {
+  constexpr int QI = BANKED_QI;
+  const size_t smem = sizeof(float) * QI * d.H * d.Npad + sizeof(int) * d.N * QI;
+  GTOS_REQUIRE(smem <= 200 * 1024, "rel_attn_banked_fwd: N=%d needs %zu bytes of shared memory", d.N, smem);
+  auto kern = rel_attn_banked_fwd_kernel<DL, QI>;
+  GTOS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((d.N + QI - 1) / QI, d.B);
+  GTOS_KLAUNCH(kern, grid, dim3(256), smem, st, d);
+  GTOS_LAUNCH_CHECK();
+  return GTOS_OK;
+}
+
+int rel_attn_banked_fwd(const RelBankedArgs& a, cudaStream_t st) {
+  RelBankedDev d;
+  int e = banked_check(a, &d);
+  if (e) return e;
+  GTOS_REQUIRE(a.v && a.probs && a.out && a.ldv % 2 == 0 && a.ldo % 2 == 0, "rel_attn_banked_fwd: v / probs / out are required");
+  GTOS_REQUIRE(a.p_drop == 0.f || a.seed_ptr, "rel_attn_banked_fwd: dropout needs a device seed pointer");
+  switch (a.D / 32) {
+    case 4: return launch_banked_fwd<4>(d, st);
+    case 8: return launch_banked_fwd<8>(d, st);
+    case 16: return launch_banked_fwd<16>(d, st);
+    default: return launch_banked_fwd<32>(d, st);
+  }
+}
+
+template <int DL>
+static int launch_banked_grad(const RelBankedDev& d, cudaStream_t st) {
+  constexpr int QI = BANKED_QI;
+  const size_t smem = sizeof(int) * d.N * QI;
+  auto kern = rel_grad_banked_kernel<DL, QI>;
+  GTOS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((d.N + QI - 1) / QI, d.B);
+  GTOS_KLAUNCH(kern, grid, dim3(256), smem, st, d);
+  GTOS_LAUNCH_CHECK();
+  return GTOS_OK;
+}
+
+int rel_grad_banked(const RelBankedArgs& a, cudaStream_t st) {
+  RelBankedDev d;
+  int e = banked_check(a, &d);
+  if (e) return e;
+  GTOS_REQUIRE(a.dscores && a.G, "rel_grad_banked: dscores and G are required");
+  e = choose_rel_tiling(&d.rt, a.N, a.B, a.D, a.H);
+  if (e) return e;
+  switch (a.D / 32) {
+    case 4: return launch_banked_grad<4>(d, st);
+    case 8: return launch_banked_grad<8>(d, st);
+    case 16: return launch_banked_grad<16>(d, st);
+    default: return launch_banked_grad<32>(d, st);
+  }
+}
+
+}  // namespace gtos

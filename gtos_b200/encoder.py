@@ -54,6 +54,8 @@ class RelationEncoder(nn.Module):
         """src_tokens [Lmax, R] int64, src_lengths [R] int64 -> [R, embed_dim]  (encoder.py:90-119).
         No host sync: lengths stay on the device (the reference calls .tolist(), encoder.py:99)."""
         p = self.dropout if self.training else 0.0
-        return ops.GRUBankFn.apply(src_tokens, src_lengths, self.rel_embed.weight, self.out_proj.weight,
+        bank = ops.GRUBankFn.apply(src_tokens, src_lengths, self.rel_embed.weight, self.out_proj.weight,
                                    self.out_proj.bias, self.num_layers, self.hidden_size, float(p),
                                    *self._gru_weights())
+        # a tensor whose dim-0 index_select (the caller's own gather, generator.py:79) runs on this library's kernels
+        return ops.as_bank_tensor(bank)

@@ -37,12 +37,13 @@ class GraphTransformer(nn.Module):
         if isinstance(relation, ops.BankedRelation):
             # bank-factorised relation: dense bf16 operand for the fused kernels, bank-row GEMMs
             # in the backward
-            banked, relation, relb = relation, None, relation.relb
+            banked, relation, relb = relation, None, None
             if torch.is_grad_enabled() and banked.requires_grad:
                 banked.prepare(self.layers[0].self_attn.num_heads)
                 acc = ops.RelGradAcc(banked, len(self.layers))
                 token = ops.BankTokenFn.apply(banked.bank, acc)
         else:
+            banked = None
             relb = _staged_bf16(relation)
             # one shared gradient buffer for the relation tensor instead of L per-layer tensors summed by autograd
             if torch.is_grad_enabled() and relation.requires_grad:
@@ -51,7 +52,7 @@ class GraphTransformer(nn.Module):
         xb = None
         for layer in self.layers:
             x, xb, _ = layer._forward(x, xb, relation, relb, kv, self_padding_mask, self_attn_mask, False,
-                                      rel_token=token, rel_acc=acc)
+                                      rel_token=token, rel_acc=acc, banked=banked)
         return x
 
     def get_attn_weights(self, x, relation, kv=None, self_padding_mask=None, self_attn_mask=None):
@@ -63,20 +64,21 @@ class GraphTransformer(nn.Module):
                 x, attn = layer(x, relation, kv, self_padding_mask, self_attn_mask, need_weights=True)
                 attns.append(attn)
             return torch.stack(attns)
+        banked = None
         if isinstance(relation, ops.BankedRelation):
-            relation, relb = None, relation.relb
+            banked, relation, relb = relation, None, None
         else:
             relb = _staged_bf16(relation)
         attns, xb = [], None
         for layer in self.layers:
-            x, xb, attn = layer._forward(x, xb, relation, relb, kv, self_padding_mask, self_attn_mask, True)
+            x, xb, attn = layer._forward(x, xb, relation, relb, kv, self_padding_mask, self_attn_mask, True, banked=banked)
             attns.append(attn)
         return torch.stack(attns)
 
 
 def _staged_bf16(relation):
-    relb = getattr(relation, "_gtos_bf16", None)
-    if relb is not None and relb.shape == relation.shape and relb.device == relation.device:
+    relb = ops.staged_relation_bf16(relation)
+    if relb is not None:
         return relb
     return ops.relation_to_bf16(relation.detach().contiguous())
 
@@ -101,7 +103,7 @@ class GraphTransformerLayer(nn.Module):
         nn.init.constant_(self.fc2.bias, 0.)
 
     def _forward(self, x, xb, relation, relb, kv, self_padding_mask, self_attn_mask, need_weights, rel_token=None,
-                 rel_acc=None):
+                 rel_acc=None, banked=None):
         p = self.dropout if self.training else 0.0
         if kv is not None and kv is not x:
             # graph_transformer.py:52-55 `self_attn(query=x, key=kv, value=kv, ...)`: never used by gtos
@@ -110,14 +112,17 @@ class GraphTransformerLayer(nn.Module):
                                   need_weights=need_weights)
         else:
             a, w = self.self_attn._forward(x, xb, relation, relb, self_padding_mask, self_attn_mask, need_weights,
-                                           rel_token, rel_acc)
+                                           rel_token, rel_acc, banked)
         x, xb = ops.add_layer_norm(a, x, self.attn_layer_norm.weight, self.attn_layer_norm.bias, p)
         h = ops.ffn(x, xb, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, p)
         x, xb = ops.add_layer_norm(h, x, self.ff_layer_norm.weight, self.ff_layer_norm.bias, p)
         return x, xb, w
 
     def forward(self, x, relation, kv=None, self_padding_mask=None, self_attn_mask=None, need_weights=False):
-        x, _, w = self._forward(x, None, relation, None, kv, self_padding_mask, self_attn_mask, need_weights)
+        if isinstance(relation, ops.BankedRelation) and (kv is None or kv is x):
+            x, _, w = self._forward(x, None, None, None, kv, self_padding_mask, self_attn_mask, need_weights, banked=relation)
+        else:
+            x, _, w = self._forward(x, None, relation, None, kv, self_padding_mask, self_attn_mask, need_weights)
         return x, w
 
 
@@ -146,12 +151,13 @@ class RelationMultiheadAttention(nn.Module):
         nn.init.constant_(self.in_proj_bias, 0.)
         nn.init.constant_(self.out_proj.bias, 0.)
 
-    def _forward(self, x, xb, relation, relb, key_padding_mask, attn_mask, need_weights, rel_token=None, rel_acc=None):
+    def _forward(self, x, xb, relation, relb, key_padding_mask, attn_mask, need_weights, rel_token=None, rel_acc=None,
+                 banked=None):
         p = self.dropout if self.training else 0.0
         out, w = ops.RelAttnFn.apply(x, xb, relation, relb, ops.as_u8(key_padding_mask), ops.as_u8(attn_mask),
                                      self.in_proj_weight, self.in_proj_bias, self.relation_in_proj.weight,
                                      self.out_proj.weight, self.out_proj.bias, self.num_heads, float(p),
-                                     bool(need_weights), rel_token, rel_acc, bool(self.weights_dropout))
+                                     bool(need_weights), rel_token, rel_acc, bool(self.weights_dropout), banked)
         if w is not None:
             w = w.permute(2, 3, 0, 1)           # [B,H,T,S] -> [tgt, src, bsz, heads]   (:168-170)
         return out, w
@@ -170,6 +176,8 @@ class RelationMultiheadAttention(nn.Module):
                                               self.in_proj_weight, self.in_proj_bias, self.relation_in_proj.weight,
                                               self.out_proj.weight, self.out_proj.bias, self.num_heads, float(p),
                                               bool(self.weights_dropout), bool(need_weights))
+        if isinstance(relation, ops.BankedRelation):
+            return self._forward(query, None, None, None, key_padding_mask, attn_mask, need_weights, banked=relation)
         return self._forward(query, None, relation, None, key_padding_mask, attn_mask, need_weights)
 
     # projection helpers kept for API parity (:176-197); they run the tcgen05 GEMM

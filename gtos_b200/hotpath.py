@@ -102,6 +102,17 @@ class HotPath(nn.Module):
                             batch["copy_seq"], target=batch["target"])
 
 
+def backward(loss, fresh_grads=True):
+    """`loss.backward()` of the training loop (train.py:148).  fresh_grads=True (every .grad is None or will be
+    overwritten, i.e. not a gradient accumulation step): the weight / bias / LayerNorm gradient kernels that run on the side
+    stream are joined once at the end of the pass instead of after every sub-layer (ops.deferred_param_grads)."""
+    if fresh_grads:
+        with ops.deferred_param_grads():
+            loss.backward()
+    else:
+        loss.backward()
+
+
 BATCH_KEYS = ("relation_bank", "relation_length", "relation", "x", "node_mask", "token_repr", "token_mask",
               "copy_seq", "target", "causal_mask")
 

@@ -98,6 +98,43 @@ class _Fork:
             self.main.wait_stream(self.side)
             self.used = False
 
+    def join_param(self, *keep):
+        """join for side work whose only products are PARAMETER gradients (weight / bias / LayerNorm gradients).  Inside a
+        `with deferred_param_grads():` block the caller's stream does not wait here: the join moves to the end of the
+        block, so a weight-gradient GEMM never stalls the dependent chain of the backward pass.  `keep`: the tensors the
+        side kernels read - held until the deferred join so the caching allocator cannot hand their memory out."""
+        if self.used and _deferred["on"]:
+            _deferred["streams"][id(self.side)] = (self.main, self.side)
+            _deferred["keep"].extend(keep)
+            self.used = False
+            return
+        self.join()
+
+
+_deferred = {"on": False, "streams": {}, "keep": []}
+_defer_enabled = os.environ.get("GTOS_DEFER_GRADS", "1") == "1"
+
+
+class deferred_param_grads:
+    """`with ops.deferred_param_grads(): loss.backward()` - parameter-gradient work forked to the side stream during the
+    backward pass is joined ONCE, when the block ends, instead of at the end of every autograd Function.  Contract: inside
+    the block nothing on the caller's stream may read a parameter's .grad - so use it only when the gradients start as
+    None (a fresh backward, not an accumulation into existing .grad tensors).  GTOS_DEFER_GRADS=0 makes it a no-op."""
+
+    def __enter__(self):
+        self.prev = _deferred["on"]
+        _deferred["on"] = _defer_enabled and _side_enabled
+        return self
+
+    def __exit__(self, *exc):
+        _deferred["on"] = self.prev
+        if not self.prev:
+            for main, side in _deferred["streams"].values():
+                main.wait_stream(side)
+            _deferred["streams"].clear()
+            _deferred["keep"].clear()
+        return False
+
 
 def fork(enabled=None, which=0):
     """with fork() as f: <launches on the side stream> ... f.join() before the results are handed on.
@@ -158,6 +195,9 @@ def cast_colsum(x2d):
 
 class _NoFork:
     def join(self):
+        pass
+
+    def join_param(self, *keep):
         pass
 
 
@@ -428,7 +468,7 @@ class AddLayerNormFn(torch.autograd.Function):
         dxb = torch.empty(rows, D, dtype=torch.bfloat16, device=z.device) if D % 8 == 0 else None
         _lib.check(_lib.load().gtos_add_ln_bwd(_p(dy2), _p(z), _p(mean), _p(rstd), _p(gamma), _p(dres), _p(dx), _p(dxb),
                                                None, None, rows, D, p, _p(seed), off, _st()), "add_ln_bwd")
-        f_par.join()
+        f_par.join_param(dy2, z, mean, rstd)
         dres = dres.view(shape)
         dxo = dres if dx is None else dx.view(shape)
         if dxb is not None:
@@ -484,9 +524,9 @@ class FFNFn(torch.autograd.Function):
             gemm_nn(dhb, xb2, Fd, D, out=dW1)
             colsum(dhb, out=db1f)
         dx, _ = gemm_tn(dhb, W1t, D)
-        f2.join()
-        f1.join()
-        f_db.join()
+        f2.join_param(dyb, hb)
+        f1.join_param(dhb, xb2)
+        f_db.join_param(dy2)
         return dx.view(shape), None, dW1, db1f[:Fd], dW2, db2, None
 
 
@@ -502,18 +542,22 @@ class RelAttnFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, xb, relation, relb, key_pad, attn_mask, W_in, b_in, W_rel, W_out, b_out, H, p, need_weights,
-                rel_token=None, rel_acc=None, weights_dropout=True):
-        _need_cuda(x, relation if relation is not None else relb, W_in)
+                rel_token=None, rel_acc=None, weights_dropout=True, banked=None):
+        _need_cuda(x, W_in)
         lib = _lib.load()
         N, B, D = x.shape
-        rshape = tuple((relation if relation is not None else relb).shape)
-        if rshape != (N, N, B, D):
-            raise ValueError(f"relation must be [N,N,B,D]=[{N},{N},{B},{D}], got {rshape}")
+        fused_bank = banked is not None and banked_fwd_supported(banked, N, B, D, H)
+        if not fused_bank:
+            if banked is not None and relb is None:
+                relb = banked.relb
+            rshape = tuple((relation if relation is not None else relb).shape)
+            if rshape != (N, N, B, D):
+                raise ValueError(f"relation must be [N,N,B,D]=[{N},{N},{B},{D}], got {rshape}")
         hd = D // H
         dev = x.device
         NB = N * B
         xb2 = (xb if xb is not None else cast_bf16(x.contiguous().view(NB, D))).view(NB, D)
-        if relb is None:
+        if relb is None and not fused_bank:
             relb = relation_to_bf16(relation.detach().contiguous())
         Wib, Wit = weight_prep(W_in)
         Wperm, WpermT = weight_prep(W_rel, rel_heads=H)
@@ -523,24 +567,36 @@ class RelAttnFn(torch.autograd.Function):
         vproj = torch.empty(NB, D, dtype=torch.float32, device=dev)
         with fork() as f_v:                         # v is first read by the attention core, after the score kernel
             gemm_tn(xb2, Wib, D, bias=b_in[2 * D:], K=D, b_off=2 * D * Wib.stride(0), out=vproj)   # [NB, D] fp32
-        scores = torch.empty(B, H, N, N, dtype=torch.float32, device=dev)          # [b,h,j,i]
-        _lib.check(lib.gtos_rel_score(_p(relb), _p(Wperm), qkb.data_ptr(), qkb.data_ptr() + 2 * D, 2 * D, _p(scores),
-                                      N, B, D, H, _st()), "rel_score")
-        f_v.join()
         probs = torch.empty(B, H, N, N, dtype=torch.float32, device=dev)           # [b,h,i,j]
         wts = torch.empty(B, H, N, N, dtype=torch.float32, device=dev) if need_weights else None
         att = torch.empty(NB, D, dtype=torch.float32, device=dev)
         attb = torch.empty(NB, D, dtype=torch.bfloat16, device=dev)
         seed, off = (rng_state(dev), new_seed_off()) if p > 0 else (None, 0)
         p_w = p if weights_dropout else 0.0         # graph_transformer.py:154-161: dropout on the weights OR on the output
-        d = _attn_desc(N, N, B, H, hd)
-        d.v, d.ldv = vproj.data_ptr(), D
-        d.scale, d.p_drop = 1.0, p_w
-        d.scores_jt, d.key_pad, d.attn_mask = _p(scores), _p(key_pad), _p(attn_mask)
-        d.seed_ptr, d.seed_off = _p(seed), off
-        d.probs, d.probs_dropped = _p(probs), _p(wts)
-        d.out, d.ldo, d.out_bf16 = _p(att), D, _p(attb)
-        _lib.check(lib.gtos_attn_fwd(C.byref(d), _st()), "attn_fwd(enc)")
+        PB = None
+        if fused_bank:
+            # SURVEY 8 f-0, forward half: [ra | rb] of a pair is a ROW of the projected bank - one R-row GEMM, then ONE
+            # kernel for gather + scores + masks + softmax + dropout + PV (graph_transformer.py:122-159)
+            _, PB = gemm_tn(banked.bankb, Wperm, 2 * D, f32=False, bf16=True)       # [R, 2D] bf16
+            f_v.join()
+            _lib.check(lib.gtos_rel_attn_banked_fwd(_p(PB), PB.stride(0), _p(banked.idx), qkb.data_ptr(),
+                                                    qkb.data_ptr() + 2 * D, 2 * D, _p(vproj), D, _p(key_pad), _p(attn_mask),
+                                                    p_w, _p(seed), off, _p(probs), _p(wts), _p(att), D, _p(attb), N, B, D, H,
+                                                    banked.bankb.shape[0], _st()), "rel_attn_banked_fwd")
+            relb = PB                               # saved in relb's slot for the backward
+        else:
+            scores = torch.empty(B, H, N, N, dtype=torch.float32, device=dev)      # [b,h,j,i]
+            _lib.check(lib.gtos_rel_score(_p(relb), _p(Wperm), qkb.data_ptr(), qkb.data_ptr() + 2 * D, 2 * D, _p(scores),
+                                          N, B, D, H, _st()), "rel_score")
+            f_v.join()
+            d = _attn_desc(N, N, B, H, hd)
+            d.v, d.ldv = vproj.data_ptr(), D
+            d.scale, d.p_drop = 1.0, p_w
+            d.scores_jt, d.key_pad, d.attn_mask = _p(scores), _p(key_pad), _p(attn_mask)
+            d.seed_ptr, d.seed_off = _p(seed), off
+            d.probs, d.probs_dropped = _p(probs), _p(wts)
+            d.out, d.ldo, d.out_bf16 = _p(att), D, _p(attb)
+            _lib.check(lib.gtos_attn_fwd(C.byref(d), _st()), "attn_fwd(enc)")
         off2 = 0
         if not weights_dropout and p > 0:
             off2 = new_seed_off()
@@ -549,6 +605,7 @@ class RelAttnFn(torch.autograd.Function):
         out, _ = gemm_tn(attb, Wob, D, bias=b_out)
         ctx.save_for_backward(xb2, relb, qkb, vproj, probs, attb, Wperm, WpermT, Wit, Wot, key_pad, attn_mask)
         ctx.meta = (N, B, D, H, p, seed, off, p_w, off2)
+        ctx.fused_bank = banked if fused_bank else None
         ctx.rel_acc = rel_acc if (rel_token is not None and rel_token.requires_grad) else None
         ctx.set_materialize_grads(False)            # unused attention weights: no zero-filled [B,H,N,N] gradient
         if wts is None:
@@ -594,8 +651,14 @@ class RelAttnFn(torch.autograd.Function):
         _lib.check(lib.gtos_attn_bwd(C.byref(d), _st()), "attn_bwd(enc)")
         tiles = rel_tiling(N, B, D, H)["tiles"]
         G = torch.empty(tiles * 128, 2 * D, dtype=torch.bfloat16, device=dev)
-        _lib.check(lib.gtos_rel_grad(_p(relb), _p(Wperm), qkb.data_ptr(), qkb.data_ptr() + 2 * D, 2 * D, _p(ds_jt),
-                                     _p(G), N, B, D, H, _st()), "rel_grad")
+        if ctx.fused_bank is not None:
+            bk = ctx.fused_bank                     # relb's slot holds the projected bank PB [R, 2D]
+            _lib.check(lib.gtos_rel_grad_banked(_p(relb), relb.stride(0), _p(bk.idx), qkb.data_ptr(), qkb.data_ptr() + 2 * D,
+                                                2 * D, _p(ds_jt), _p(G), N, B, D, H, bk.bankb.shape[0], _st()),
+                       "rel_grad_banked")
+        else:
+            _lib.check(lib.gtos_rel_grad(_p(relb), _p(Wperm), qkb.data_ptr(), qkb.data_ptr() + 2 * D, 2 * D, _p(ds_jt),
+                                         _p(G), N, B, D, H, _st()), "rel_grad")
         d_rel = None
         if ctx.rel_acc is not None and ctx.rel_acc.banked is not None:
             # relation = bank[idx]: segmented sum of G over bank rows, then R-row GEMMs instead of
@@ -619,7 +682,7 @@ class RelAttnFn(torch.autograd.Function):
             dW_in = torch.empty(3 * D, D, dtype=torch.float32, device=dev)
             # The bank side (segmented sum -> dW_rel, both off the critical path) and the node side (dq/dk segment sums ->
             # in_proj backward -> dx) both stream G from HBM and are independent: two streams (GTOS_REL_STREAMS=0: one).
-            with fork(_rel_streams or None) as f_rel:
+            with fork(_rel_streams or None, which=2) as f_rel:
                 _lib.check(lib.gtos_rel_segsum(_p(G), _p(bk.order), _p(bk.keys), N * N * B, 2 * D, s_ptr, L * 2 * D,
                                                _p(acc.spill), _st()), "rel_segsum")
                 _lib.check(lib.gtos_rel_dw_bank(s_ptr, L * 2 * D, _p(bk.bankb), _p(dW_rel), R, D, H, _st()), "rel_dw_bank")
@@ -630,13 +693,13 @@ class RelAttnFn(torch.autograd.Function):
             with fork() as f_in:
                 gemm_nn(dqkvb, xb2, 3 * D, D, out=dW_in)
             dx, _ = gemm_tn(dqkvb, Wit, D)
-            f_out.join()
-            f_rel.join()
-            f_in.join()
-            f_db.join()
-            f_dbin.join()
+            f_out.join_param(doutb, attb)
+            f_rel.join()                        # the segment sums feed BankTokenFn's d-bank GEMM on the caller's stream
+            f_in.join_param(dqkvb, xb2)
+            f_db.join_param(dout2)
+            f_dbin.join_param(dqkv)
             return (dx.view(N, B, D), None, None, None, None, None, dW_in, db_in, dW_rel, dW_out, db_out, None, None,
-                    None, None, None, None)
+                    None, None, None, None, None)
         _lib.check(lib.gtos_rel_dqk(_p(G), dqkv.data_ptr(), dqkv.data_ptr() + 4 * D, 3 * D, dqb_p, dkb_p, N, B, D, H, _st()),
                    "rel_dqk")
         if ctx.rel_acc is not None:
@@ -655,13 +718,16 @@ class RelAttnFn(torch.autograd.Function):
         dW_rel = torch.empty(2 * D, D, dtype=torch.float32, device=dev)
         _lib.check(lib.gtos_rel_dw(_p(G), _p(relb), _p(dW_rel), _p(ws), ws_elems, N, B, D, H, _st()), "rel_dw")
         dqkvb, db_in, f_dbin = operand_or_cast(dqkv, dqkv_b)
-        dW_in = gemm_nn(dqkvb, xb2, 3 * D, D)
+        dW_in = torch.empty(3 * D, D, dtype=torch.float32, device=dev)
+        with fork() as f_in:
+            gemm_nn(dqkvb, xb2, 3 * D, D, out=dW_in)
         dx, _ = gemm_tn(dqkvb, Wit, D)
-        f_out.join()
-        f_db.join()
-        f_dbin.join()
+        f_out.join_param(doutb, attb)
+        f_in.join_param(dqkvb, xb2)
+        f_db.join_param(dout2)
+        f_dbin.join_param(dqkv)
         return (dx.view(N, B, D), None, d_rel, None, None, None, dW_in, db_in, dW_rel, dW_out, db_out, None, None,
-                None, None, None, None)
+                None, None, None, None, None)
 
 
 def rel_attention_composed(query, key, value, relation, key_padding_mask, attn_mask, W_in, b_in, W_rel, W_out, b_out, H, p,
@@ -733,6 +799,20 @@ def mha_composed(query, key, value, key_padding_mask, attn_mask, W_in, b_in, W_o
     return out, None
 
 
+# SURVEY 8 f-0 forward half: gtos_rel_attn_banked_fwd / gtos_rel_grad_banked instead of the P-row tcgen05 kernels when the
+# relation arrives factorised.  GTOS_BANKED_FWD=0 keeps the dense bf16 gather + gtos_rel_score / gtos_rel_grad.
+_banked_fwd = os.environ.get("GTOS_BANKED_FWD", "1") == "1"
+
+
+def banked_fwd_supported(banked, N, B, D, H):
+    if not _banked_fwd or banked is None or banked.multi:
+        return False
+    if D not in (128, 256, 512) or 32 % H != 0 or D % H != 0:
+        return False
+    npad = (N + 3) // 4 * 4
+    return 4 * H * npad * 4 + 4 * N * 4 <= 200 * 1024 and tuple(banked.idx.shape) == (N, N, B)
+
+
 class RelGradAcc:
     """holds the shared d_relation buffer of one GraphTransformer pass (dense relation), or - when the relation is a
     BankedRelation - the shared d_bank buffer and the segment-sum scratch"""
@@ -764,20 +844,29 @@ class BankedRelation:
         # evaluation batches carry up to K shortest paths per pair, 0 = empty slot (data.py:176-225); the relation of a
         # pair is the mean of their encodings (generator.py:83-88) - gather + mean fused, bf16 operand only
         self.multi = idx.dim() == 4
-        R, D = bank.shape
         with torch.no_grad():
-            bank_c = bank.detach().contiguous()
-            self.bankb = cast_bf16(bank_c)
-            self.relb = torch.empty(*idx.shape[:3], D, dtype=torch.bfloat16, device=bank.device)
-            if self.multi:
-                K = idx.shape[3]
-                _lib.check(_lib.load().gtos_bank_gather_mean(_p(bank_c), _p(self.idx), self.idx.numel() // K, K, D, None,
-                                                             _p(self.relb), _st()), "bank_gather_mean")
-            else:
-                _lib.check(_lib.load().gtos_bank_gather(_p(bank_c), _p(self.idx), self.idx.numel(), D, None, _p(self.relb),
-                                                        _st()), "bank_gather")
+            self._bank_c = bank.detach().contiguous()
+            self.bankb = cast_bf16(self._bank_c)
+        self._relb = None
         self.keys = self.order = None
         self._heads = None
+
+    @property
+    def relb(self):
+        """the dense bf16 operand [N,N,B,D] of the tcgen05 score kernel - gathered on first use (the fused banked forward
+        never needs it)"""
+        if self._relb is None:
+            idx, D = self.idx, self.bank.shape[1]
+            with torch.no_grad():
+                self._relb = torch.empty(*idx.shape[:3], D, dtype=torch.bfloat16, device=self.bank.device)
+                if self.multi:
+                    K = idx.shape[3]
+                    _lib.check(_lib.load().gtos_bank_gather_mean(_p(self._bank_c), _p(idx), idx.numel() // K, K, D, None,
+                                                                 _p(self._relb), _st()), "bank_gather_mean")
+                else:
+                    _lib.check(_lib.load().gtos_bank_gather(_p(self._bank_c), _p(idx), idx.numel(), D, None, _p(self._relb),
+                                                            _st()), "bank_gather")
+        return self._relb
 
     @property
     def requires_grad(self):
@@ -980,10 +1069,10 @@ class MHAFn(torch.autograd.Function):
             dq_in, _ = gemm_tn(dpqb, Wit, D, K=D)                                   # Wt[:, :D]
             dk_in, _ = gemm_tn(dpkvb, Wit, D, K=2 * D, b_off=D)                     # Wt[:, D:3D]
             dk_in = dk_in.view(S, B, D)
-        f_out.join()
-        f_in.join()
-        f_db.join()
-        f_dbin.join()
+        f_out.join_param(doutb, attb)
+        f_in.join_param(qb2, kb2, *(([dprojb] if self_attn else [dpqb, dpkvb])))
+        f_db.join_param(dout2)
+        f_dbin.join_param(dproj if self_attn else dpq)
         return (dq_in.view(T, B, D), None, dk_in, None, None, None, None, dW_in, db_in, dW_out, db_out, None, None,
                 None, None)
 
@@ -1184,7 +1273,7 @@ class LinearFn(torch.autograd.Function):
             gemm_nn(dyb, xb, N, K, out=dW)
         db = db if has_b else None
         dx, _ = gemm_tn(dyb, Wt, K)
-        f.join()
+        f.join_param(dyb, xb)
         return dx.view(shape), dW, db
 
 
@@ -1226,11 +1315,88 @@ class BankGatherFn(torch.autograd.Function):
 
 
 def bank_gather(bank, idx):
-    """relation = bank[idx] as (fp32 dense tensor, bf16 copy).  The dense tensor carries the bf16 copy as
-    `._gtos_bf16` so GraphTransformer.forward does not stage it again."""
+    """relation = bank[idx] as (fp32 dense tensor, bf16 copy).  The dense tensor carries the bf16 copy (it survives
+    .view / .reshape / .contiguous, see GatheredRelation) so GraphTransformer.forward does not stage it again."""
     rel, relb = BankGatherFn.apply(bank, idx)
-    rel._gtos_bf16 = relb
+    rel = rel.as_subclass(GatheredRelation)
+    rel._gtos_bf16 = (relb, rel._version)
     return rel
+
+
+_VIEW_FUNCS = None
+
+
+def _view_funcs():
+    global _VIEW_FUNCS
+    if _VIEW_FUNCS is None:
+        T = torch.Tensor
+        _VIEW_FUNCS = {T.view, T.reshape, T.contiguous, T.view_as, T.reshape_as, torch.reshape}
+    return _VIEW_FUNCS
+
+
+class GatheredRelation(torch.Tensor):
+    """The dense fp32 relation tensor bank[idx] as ops.bank_gather builds it.  An ordinary tensor for every consumer; the
+    only extra is that the bf16 operand copy made in the same pass rides along through shape-only views
+    (`.view(*idx.size(), -1)`, generator.py:79), so the graph encoder does not have to re-read 4 bytes per element to
+    re-make it.  The tag records the tensor's version counter: any in-place write invalidates it."""
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        kwargs = kwargs or {}
+        with torch._C.DisableTorchFunctionSubclass():
+            out = func(*args, **kwargs)
+        if func in _view_funcs() and isinstance(out, torch.Tensor) and args and isinstance(args[0], GatheredRelation):
+            src = args[0]
+            tag = getattr(src, "_gtos_bf16", None)
+            if (tag is not None and tag[1] == src._version and out.numel() == src.numel() and out.dtype == src.dtype
+                    and out.is_contiguous() and out.data_ptr() == src.data_ptr()):
+                if out is not src:
+                    out = out.as_subclass(GatheredRelation)
+                out._gtos_bf16 = (tag[0].view(out.shape), tag[1])
+        return out
+
+
+def staged_relation_bf16(relation):
+    """the bf16 operand copy a GatheredRelation carries, if it is still valid for `relation`"""
+    tag = getattr(relation, "_gtos_bf16", None)
+    if tag is None:
+        return None
+    relb, version = tag
+    if version != relation._version or relb.shape != relation.shape or relb.device != relation.device:
+        return None
+    return relb
+
+
+_bank_tensor = os.environ.get("GTOS_BANK_TENSOR", "1") == "1"
+
+
+class BankTensor(torch.Tensor):
+    """RelationEncoder's output [R, D].  The reference's caller turns it into the dense relation tensor with
+    `relation.index_select(0, inp['relation'].view(-1)).view(*inp['relation'].size(), -1)` (generator.py:79;
+    translator/generator.py:73).  That line keeps working unchanged: index_select along dim 0 of a BankTensor runs
+    gtos_bank_gather (same fp32 values, plus the bf16 operand copy in the same pass) and its backward runs
+    gtos_bank_scatter_add instead of ATen's index_add_ (CUPTI timeline at config 2: 478 us -> the <TL> row alone receives
+    41 % of the pairs).  Every other operation sees a plain tensor.  GTOS_BANK_TENSOR=0 returns a plain tensor."""
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        kwargs = kwargs or {}
+        if func in (torch.Tensor.index_select, torch.index_select) and not kwargs.get("out"):
+            bank = args[0] if args else kwargs.get("input")
+            dim = args[1] if len(args) > 1 else kwargs.get("dim")
+            index = args[2] if len(args) > 2 else kwargs.get("index")
+            if True:
+                if (isinstance(bank, BankTensor) and dim in (0, -2) and bank.dim() == 2 and bank.is_cuda
+                        and torch.is_tensor(index) and index.dim() == 1 and index.dtype == torch.int64 and index.is_cuda
+                        and bank.dtype == torch.float32 and bank.shape[1] % 4 == 0):
+                    with torch._C.DisableTorchFunctionSubclass():
+                        return bank_gather(bank.as_subclass(torch.Tensor), index)
+        with torch._C.DisableTorchFunctionSubclass():
+            return func(*args, **kwargs)
+
+
+def as_bank_tensor(bank):
+    return bank.as_subclass(BankTensor) if (_bank_tensor and bank.is_cuda) else bank
 
 
 # --------------------------------------------------------------------------------------------

@@ -97,6 +97,23 @@ int gtos_rel_dw(const void* G, const void* relb, float* dW, float* workspace, in
 int gtos_rel_dqk(const void* G, float* dq, float* dk, int64_t ld, void* dq_bf16, void* dk_bf16, int32_t N, int32_t B,
                  int32_t D, int32_t H, void* stream);
 
+/* ---- bank-factorised relation attention, forward half (caller generator/generator.py:76-90) ----
+ * relation = bank[idx] and relation_in_proj has no bias (graph_transformer.py:80), so [ra_ij | rb_ij] is row idx[j][i][b]
+ * of PB = bank * Wperm^T (bf16 [R, 2D], head-interleaved columns; one R-row gtos_gemm_tn per layer).
+ * gtos_rel_attn_banked_fwd is graph_transformer.py:122-159 as ONE kernel: gather, per-head scores hd^-1/2 <q_i + ra, k_j + rb>,
+ * key-padding [N,B] / attention [N,N] masks, softmax over keys, dropout (same counter-based draw as gtos_attn_fwd, so
+ * gtos_attn_bwd replays it), o_i = sum_j w_ij v_j.  probs [B,H,N,N] (pre-dropout, saved for the backward), out fp32
+ * [N*B, D] (+ bf16 copy).  gtos_rel_grad_banked writes the per-pair gradient rows G exactly as gtos_rel_grad lays them
+ * out (tile-major rows, head-interleaved [d(q+ra) | d(k+rb)] columns) from the same gather instead of a P-row GEMM. */
+int gtos_rel_attn_banked_fwd(const void* PB, int64_t ldpb, const int64_t* idx, const void* q, const void* k, int64_t ldqk,
+                             const float* v, int64_t ldv, const uint8_t* key_pad, const uint8_t* attn_mask, float p_drop,
+                             const void* seed_ptr, uint64_t seed_off, float* probs, float* probs_dropped, float* out,
+                             int64_t ldo, void* out_bf16, int32_t N, int32_t B, int32_t D, int32_t H, int32_t R,
+                             void* stream);
+int gtos_rel_grad_banked(const void* PB, int64_t ldpb, const int64_t* idx, const void* q, const void* k, int64_t ldqk,
+                         const float* dscores, void* G, int32_t N, int32_t B, int32_t D, int32_t H, int32_t R,
+                         void* stream);
+
 /* ---- bank-factorised backward of the relation terms (caller generator/generator.py:76-79) ----
  * When relation = bank[idx] (bank [R,D], idx [N,N,B] int64, layout idx[j][i][b]) the two P-row GEMMs of the backward
  * collapse to R-row GEMMs after ONE segmented sum of the per-pair gradient rows G (from gtos_rel_grad):

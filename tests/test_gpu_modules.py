@@ -109,14 +109,17 @@ def test_graph_transformer_vs_oracle(dev, N, B, D, H, F, L, wf):
     assert attn.shape == aref.shape and rel_err(attn, aref) < TOL
 
 
+@pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("N,B,D,H,F,L,R", [(17, 8, 128, 8, 256, 2, 200), (41, 6, 512, 8, 1024, 2, 3000)])
-def test_graph_transformer_banked_relation_vs_oracle(dev, N, B, D, H, F, L, R):
+def test_graph_transformer_banked_relation_vs_oracle(dev, N, B, D, H, F, L, R, fused, monkeypatch):
     """§8 f-0: relation = bank[idx] passed factorised (ops.BankedRelation).  Output and every gradient (incl. d bank,
     d relation_in_proj of each layer) against the oracle run on the dense bank[idx] tensor, and against this repo's own
-    dense path (same forward kernels: outputs bit-identical; gradients differ only by the bf16 rounding of the
-    per-bank-row sums)."""
+    dense path.  fused=True: the forward projects the BANK and one kernel gathers / scores / soft-maxes / applies V
+    (gtos_rel_attn_banked_fwd), the backward's G rows come from the same gather (gtos_rel_grad_banked); fused=False:
+    dense bf16 gather + the tcgen05 pair kernels (outputs then bit-identical to the dense path)."""
     from gtos_b200 import ops
     from gtos_b200.graph_transformer import GraphTransformer
+    monkeypatch.setattr(ops, "_banked_fwd", fused)
     gen = torch.Generator().manual_seed(SEED)
     m = GraphTransformer(L, D, F, H, 0.0)
     boost(m, 2.0, gen)
@@ -142,17 +145,23 @@ def test_graph_transformer_banked_relation_vs_oracle(dev, N, B, D, H, F, L, R):
     # dense path of this repo on the same operands
     xd, bd = x.to(dev).requires_grad_(), bank.to(dev).requires_grad_()
     out_d = m(xd, ops.bank_gather(bd, idx.to(dev)), self_padding_mask=mask.to(dev))
-    assert torch.equal(out, out_d)
+    if fused:
+        assert rel_err(out, out_d) < 5e-3          # ra / rb pass through one extra bf16 rounding (the projected bank)
+    else:
+        assert torch.equal(out, out_d)
     names = [n for n, _ in m.named_parameters()]
     params = [p for _, p in m.named_parameters()]
     ga = torch.autograd.grad((out * wo.to(dev)).sum(), [xg, bg] + params)
     gb = torch.autograd.grad((out_d * wo.to(dev)).sum(), [xd, bd] + params)
     for lab, a, b in zip(["x", "bank"] + names, ga, gb):
-        assert l2_err(a, b) < 5e-3, f"banked vs dense grad {lab}: {l2_err(a, b):.3e}"
+        assert l2_err(a, b) < (2e-2 if fused else 5e-3), f"banked vs dense grad {lab}: {l2_err(a, b):.3e}"
     with torch.no_grad():
         attn = m.get_attn_weights(xg, ops.BankedRelation(bg, idx.to(dev)), self_padding_mask=mask.to(dev))
         attn_d = m.get_attn_weights(xg, bg[idx.to(dev)], self_padding_mask=mask.to(dev))
-    assert torch.equal(attn, attn_d)
+    if fused:
+        assert (attn - attn_d).abs().max().item() < 5e-3
+    else:
+        assert torch.equal(attn, attn_d)
 
 
 def test_rel_mha_weights_grad(dev):

@@ -73,9 +73,10 @@ SIGNATURES = {
     "gtos_dropout_f32": (i32, [vp, vp, i64, f32, vp, u64, vp]),
     "gtos_relu_drop_bwd": (i32, [vp, vp, vp, vp, i64, f32, vp]),
     "gtos_token_nll_fwd": (i32, [vp, i64, i32, vp, vp, i32, vp, vp, i64, i32, i64, vp, vp, vp]),
-    "gtos_token_nll_bwd": (i32, [vp, vp, i64, i32, vp, i32, vp, vp, i64, i32, i64, vp, vp, i64, vp, vp, vp]),
+    "gtos_token_nll_bwd": (i32, [vp, vp, i64, i32, vp, i32, vp, vp, i64, i32, i64, vp, vp, i64, vp, vp, vp, i64, vp]),
     "gtos_bank_gather": (i32, [vp, vp, i64, i32, vp, vp, vp]),
     "gtos_bank_scatter_add": (i32, [vp, vp, i64, i32, vp, i64, vp]),
+    "gtos_bank_segsum": (i32, [vp, vp, vp, i64, i32, vp, i64, vp]),
     "gtos_bank_gather_mean": (i32, [vp, vp, i64, i32, i32, vp, vp, vp]),
     "gtos_embed_gather": (i32, [vp, vp, i64, i32, vp, vp, i64, f32, vp, u64, vp]),
     "gtos_embed_scatter_add": (i32, [vp, vp, i64, i32, vp, f32, vp, u64, vp]),

@@ -292,14 +292,19 @@ int gtos_token_nll_fwd(const float* logits, int64_t ldl, int32_t V, const float*
 int gtos_token_nll_bwd(const float* dloss_row, const float* logits, int64_t ldl, int32_t V, const float* align, int32_t S,
                        const int64_t* copy_seq, const int64_t* target, int64_t rows, int32_t B, int64_t pad_idx,
                        const float* stats, float* dlogits, int64_t lddl, float* dgate_logits, float* dalign,
-                       void* stream) {
+                       void* dlogits_bf16, int64_t lddb, void* stream) {
   return token_nll_bwd(dloss_row, logits, ldl, V, align, S, reinterpret_cast<const long long*>(copy_seq),
                        reinterpret_cast<const long long*>(target), rows, B, pad_idx, stats, dlogits, lddl, dgate_logits,
-                       dalign, S_(stream));
+                       dalign, dlogits_bf16, lddb, S_(stream));
 }
 int gtos_bank_gather(const float* bank, const int64_t* idx, int64_t P, int32_t D, float* out_f32, void* out_bf16,
                      void* stream) {
   return bank_gather(bank, reinterpret_cast<const long long*>(idx), P, D, out_f32, out_bf16, S(stream));
+}
+int gtos_bank_segsum(const float* d_rel, const int64_t* order, const int64_t* keys, int64_t P, int32_t D, float* d_bank,
+                     int64_t R, void* stream) {
+  return bank_segsum_f32(d_rel, reinterpret_cast<const long long*>(order), reinterpret_cast<const long long*>(keys), P, D,
+                         d_bank, R, S(stream));
 }
 int gtos_bank_gather_mean(const float* bank, const int64_t* idx, int64_t P, int32_t K, int32_t D, float* out_f32,
                           void* out_bf16, void* stream) {

@@ -743,7 +743,8 @@ __global__ void token_nll_bwd_kernel(const float* __restrict__ dloss_row, const 
                                      const float* __restrict__ align, int S, const long long* __restrict__ copy_seq,
                                      const long long* __restrict__ target, int B, long long pad_idx,
                                      const float* __restrict__ stats, float* __restrict__ dlogits, long lddl,
-                                     float* __restrict__ dgate_logits, float* __restrict__ dalign) {
+                                     float* __restrict__ dgate_logits, float* __restrict__ dalign,
+                                     __nv_bfloat16* __restrict__ dlogits_b, long lddb) {
   GTOS_PDL_PROLOGUE();
   const long row = blockIdx.x;
   const int b = (int)(row % B);
@@ -756,9 +757,24 @@ __global__ void token_nll_bwd_kernel(const float* __restrict__ dloss_row, const 
   float* dl = dlogits + row * lddl;
   const float coef = dp * gen;
   const float inv = 1.f / se;
-  for (int v = threadIdx.x; v < V; v += blockDim.x) {
-    const float sm = __expf(lr[v] - mx) * inv;
-    dl[v] = coef * sm * ((v == tgt ? 1.f : 0.f) - sm_t);
+  if (dlogits_b && (V & 1) == 0) {
+    // two columns per thread: the bf16 operand copy of d logits for the vocabulary projection's backward GEMMs is made
+    // here, so that layer does not re-read the fp32 [T*B, V] tensor just to cast it
+    __nv_bfloat16* db = dlogits_b + row * lddb;
+    for (int v = 2 * threadIdx.x; v < V; v += 2 * blockDim.x) {
+      const float2 l2 = *reinterpret_cast<const float2*>(lr + v);
+      const float s0 = __expf(l2.x - mx) * inv, s1 = __expf(l2.y - mx) * inv;
+      const float g0 = coef * s0 * ((v == tgt ? 1.f : 0.f) - sm_t), g1 = coef * s1 * ((v + 1 == tgt ? 1.f : 0.f) - sm_t);
+      *reinterpret_cast<float2*>(dl + v) = make_float2(g0, g1);
+      *reinterpret_cast<uint32_t*>(db + v) = pack_bf16x2(g0, g1);
+    }
+  } else {
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+      const float sm = __expf(lr[v] - mx) * inv;
+      const float gv = coef * sm * ((v == tgt ? 1.f : 0.f) - sm_t);
+      dl[v] = gv;
+      if (dlogits_b) dlogits_b[row * lddb + v] = __float2bfloat16(gv);
+    }
   }
   for (int s = threadIdx.x; s < S; s += blockDim.x)
     dalign[row * S + s] = (copy_seq[(long)s * B + b] == tgt) ? dp * cpy : 0.f;
@@ -782,10 +798,14 @@ int token_nll_fwd(const float* logits, long ldl, int V, const float* gate_logits
 
 int token_nll_bwd(const float* dloss_row, const float* logits, long ldl, int V, const float* align, int S,
                   const long long* copy_seq, const long long* target, long rows, int B, long long pad_idx,
-                  const float* stats, float* dlogits, long lddl, float* dgate_logits, float* dalign, cudaStream_t st) {
+                  const float* stats, float* dlogits, long lddl, float* dgate_logits, float* dalign, void* dlogits_bf16,
+                  long lddb, cudaStream_t st) {
   if (rows == 0) return GTOS_OK;
+  GTOS_REQUIRE(!dlogits_bf16 || ((V & 1) || (ldl % 2 == 0 && lddl % 2 == 0 && lddb % 2 == 0)),
+               "token_nll_bwd: even row strides are needed for the bf16 gradient copy");
   GTOS_KLAUNCH(token_nll_bwd_kernel, dim3((unsigned)rows), dim3(256), 0, st, dloss_row, logits, ldl, V, align, S, copy_seq, target, B, pad_idx,
-                                                       stats, dlogits, lddl, dgate_logits, dalign);
+                                                       stats, dlogits, lddl, dgate_logits, dalign,
+                                                       reinterpret_cast<__nv_bfloat16*>(dlogits_bf16), lddb);
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
 }
@@ -826,6 +846,84 @@ __global__ void bank_scatter_add_kernel(const float* __restrict__ d_rel, const l
                    : "memory");
     }
   }
+}
+
+// backward of the gather, sorted: d_bank[r] = sum of d_rel rows whose index is r.  The plain scatter above issues one vector
+// reduction per pair and chunk; at config 2 the <TL> row alone receives 41 % of the pairs and the L2 serialises them (417 us
+// for 220 MB).  Here the pairs arrive sorted by bank row (`order` = pair indices, `keys` = their rows, one radix sort per
+// batch made during the forward pass): a warp walks 32 consecutive sorted pairs, keeps the running sum of the current row
+// in registers and issues ONE reduction per (row, window) - 32x fewer reductions on the hot rows, every d_rel byte read once.
+template <int U>
+__global__ void __launch_bounds__(256) bank_segsum_f32_kernel(const float* __restrict__ d_rel, const long long* __restrict__ order,
+                                                              const long long* __restrict__ keys, long P, int D,
+                                                              float* __restrict__ d_bank) {
+  GTOS_PDL_PROLOGUE();
+  const int lane = threadIdx.x & 31;
+  const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long p0 = warp * 32;
+  if (p0 >= P) return;
+  const int cnt = (int)((P - p0) < 32 ? (P - p0) : 32);
+  const long long my_row = lane < cnt ? order[p0 + lane] : 0;
+  const long long my_key = lane < cnt ? keys[p0 + lane] : -1;
+  const int nch = D / 4;
+  float4 acc[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+  long long cur = __shfl_sync(0xffffffffu, my_key, 0);
+  auto flush = [&](long long r) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int ch = lane + 32 * u;
+      if (ch < nch) {
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d_bank + r * D + 4 * ch), "f"(acc[u].x),
+                     "f"(acc[u].y), "f"(acc[u].z), "f"(acc[u].w) : "memory");
+        acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  };
+  constexpr int RIF = 4;                       // rows in flight per lane
+  for (int q0 = 0; q0 < cnt; q0 += RIF) {
+    float4 v[RIF][U];
+#pragma unroll
+    for (int t = 0; t < RIF; ++t) {
+      const long long row = __shfl_sync(0xffffffffu, my_row, (q0 + t) & 31);
+      const float4* src = reinterpret_cast<const float4*>(d_rel + row * D);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int ch = lane + 32 * u;
+        v[t][u] = (q0 + t < cnt && ch < nch) ? src[ch] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < RIF; ++t) {
+      if (q0 + t < cnt) {
+        const long long key = __shfl_sync(0xffffffffu, my_key, (q0 + t) & 31);
+        if (key != cur) {
+          flush(cur);
+          cur = key;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) { acc[u].x += v[t][u].x; acc[u].y += v[t][u].y; acc[u].z += v[t][u].z; acc[u].w += v[t][u].w; }
+      }
+    }
+  }
+  flush(cur);
+}
+
+int bank_segsum_f32(const float* d_rel, const long long* order, const long long* keys, long P, int D, float* d_bank, long R,
+                    cudaStream_t st) {
+  GTOS_REQUIRE(D % 4 == 0 && D <= 1024, "bank_segsum: D must be a multiple of 4 and <= 1024 (got %d)", D);
+  GTOS_CHECK_CUDA(cudaMemsetAsync(d_bank, 0, sizeof(float) * (size_t)R * D, st));
+  if (P == 0) return GTOS_OK;
+  const long warps = (P + 31) / 32;
+  const unsigned blocks = (unsigned)((warps + 7) / 8);
+  const int U = (D / 4 + 31) / 32;
+  if (U <= 1) GTOS_KLAUNCH(bank_segsum_f32_kernel<1>, dim3(blocks), dim3(256), 0, st, d_rel, order, keys, P, D, d_bank);
+  else if (U <= 2) GTOS_KLAUNCH(bank_segsum_f32_kernel<2>, dim3(blocks), dim3(256), 0, st, d_rel, order, keys, P, D, d_bank);
+  else if (U <= 4) GTOS_KLAUNCH(bank_segsum_f32_kernel<4>, dim3(blocks), dim3(256), 0, st, d_rel, order, keys, P, D, d_bank);
+  else GTOS_KLAUNCH(bank_segsum_f32_kernel<8>, dim3(blocks), dim3(256), 0, st, d_rel, order, keys, P, D, d_bank);
+  GTOS_LAUNCH_CHECK();
+  return GTOS_OK;
 }
 
 // evaluation batches (generator.py:83-88): relation[p] = mean over the pair's shortest paths of bank rows, where index 0

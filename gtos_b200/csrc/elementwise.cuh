@@ -28,8 +28,11 @@ int token_nll_fwd(const float* logits, long ldl, int V, const float* gate_logits
                   float* loss_row, float* stats, cudaStream_t st);
 int token_nll_bwd(const float* dloss_row, const float* logits, long ldl, int V, const float* align, int S,
                   const long long* copy_seq, const long long* target, long rows, int B, long long pad_idx,
-                  const float* stats, float* dlogits, long lddl, float* dgate_logits, float* dalign, cudaStream_t st);
+                  const float* stats, float* dlogits, long lddl, float* dgate_logits, float* dalign, void* dlogits_bf16, long lddb,
+                  cudaStream_t st);
 int bank_gather(const float* bank, const long long* idx, long P, int D, float* out_f32, void* out_bf16, cudaStream_t st);
+int bank_segsum_f32(const float* d_rel, const long long* order, const long long* keys, long P, int D, float* d_bank, long R,
+                    cudaStream_t st);
 int bank_gather_mean(const float* bank, const long long* idx, long P, int K, int D, float* out_f32, void* out_bf16,
                      cudaStream_t st);
 int bank_scatter_add(const float* d_rel, const long long* idx, long P, int D, float* d_bank, long R, cudaStream_t st);

@@ -1267,13 +1267,14 @@ class LinearFn(torch.autograd.Function):
         xb, Wt = ctx.saved_tensors
         shape, N, K, has_b = ctx.meta
         dy2 = dy.contiguous().view(-1, N)
-        dyb, db = cast_colsum(dy2)
+        dyb, db, f_db = grad_operand(dy, dy2)
         dW = torch.empty(N, K, dtype=torch.float32, device=dy.device)
         with fork() as f:
             gemm_nn(dyb, xb, N, K, out=dW)
         db = db if has_b else None
         dx, _ = gemm_tn(dyb, Wt, K)
         f.join_param(dyb, xb)
+        f_db.join_param(dy2)
         return dx.view(shape), dW, db
 
 
@@ -1284,6 +1285,9 @@ def linear(x, W, b=None):
 # --------------------------------------------------------------------------------------------
 # bank -> dense relation gather (generator.py:79) with the bf16 operand copy made in the same pass
 # --------------------------------------------------------------------------------------------
+_bank_sorted_bwd = os.environ.get("GTOS_BANK_SORTED_BWD", "1") == "1"
+
+
 class BankGatherFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, bank, idx):
@@ -1295,7 +1299,15 @@ class BankGatherFn(torch.autograd.Function):
         rel = torch.empty(*idx.shape, D, dtype=torch.float32, device=bank.device)
         relb = torch.empty(*idx.shape, D, dtype=torch.bfloat16, device=bank.device)
         _lib.check(_lib.load().gtos_bank_gather(_p(bank), _p(idx), P, D, _p(rel), _p(relb), _st()), "bank_gather")
-        ctx.save_for_backward(idx)
+        ctx.sorted = None
+        if _bank_sorted_bwd and ctx.needs_input_grad[0] and P > 0:
+            # the backward sums d_rel rows per bank row: sort the pairs by bank row now, beside the encoder's forward
+            with fork(True, which=3) as f_sort:
+                keys, order = torch.sort(idx.view(-1), stable=False)
+            ctx.sorted = f_sort                     # joined by the backward (the sort overlaps the encoder's forward)
+            ctx.save_for_backward(idx, keys, order)
+        else:
+            ctx.save_for_backward(idx)
         ctx.meta = (R, D, P)
         ctx.mark_non_differentiable(relb)
         ctx.set_materialize_grads(False)            # no zero-filled [N,N,B,D] "gradient" for the bf16 copy
@@ -1304,13 +1316,18 @@ class BankGatherFn(torch.autograd.Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, d_rel, _d_relb):
-        (idx,) = ctx.saved_tensors
+        idx = ctx.saved_tensors[0]
         R, D, P = ctx.meta
         if d_rel is None:
             return torch.zeros(R, D, dtype=torch.float32, device=idx.device), None
         d_rel = d_rel.contiguous()
         d_bank = torch.empty(R, D, dtype=torch.float32, device=d_rel.device)
-        _lib.check(_lib.load().gtos_bank_scatter_add(_p(d_rel), _p(idx), P, D, _p(d_bank), R, _st()), "bank_scatter_add")
+        if ctx.sorted is not None:
+            _, keys, order = ctx.saved_tensors
+            ctx.sorted.join()
+            _lib.check(_lib.load().gtos_bank_segsum(_p(d_rel), _p(order), _p(keys), P, D, _p(d_bank), R, _st()), "bank_segsum")
+        else:
+            _lib.check(_lib.load().gtos_bank_scatter_add(_p(d_rel), _p(idx), P, D, _p(d_bank), R, _st()), "bank_scatter_add")
         return d_bank, None
 
 
@@ -1431,9 +1448,14 @@ class TokenNLLFn(torch.autograd.Function):
         dlogits = torch.empty(T, B, V, dtype=torch.float32, device=dev)
         dgate = torch.empty(T, B, 2, dtype=torch.float32, device=dev)
         dalign = torch.empty(T, B, S, dtype=torch.float32, device=dev)
+        # the bf16 operand copy of d logits for the vocabulary projection's backward GEMMs is written in the same pass
+        # (tagged on the gradient like AddLayerNormFn's, see grad_operand): no cast pass over the [T*B, V] tensor
+        dlb = torch.empty(T * B, V, dtype=torch.bfloat16, device=dev) if (V % 8 == 0 and _grad_tags) else None
         _lib.check(_lib.load().gtos_token_nll_bwd(_p(dloss), _p(logits), V, V, _p(align), S, _p(copy_seq), _p(target), T * B,
-                                                  B, pad_idx, _p(stats), _p(dlogits), V, _p(dgate), _p(dalign), _st()),
-                   "token_nll_bwd")
+                                                  B, pad_idx, _p(stats), _p(dlogits), V, _p(dgate), _p(dalign), _p(dlb), V,
+                                                  _st()), "token_nll_bwd")
+        if dlb is not None:
+            dlogits._gtos_bf16 = (dlb, dlogits._version)
         return dlogits, dgate, dalign, None, None, None
 
 

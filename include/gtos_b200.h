@@ -196,7 +196,7 @@ int gtos_token_nll_fwd(const float* logits, int64_t ldl, int32_t V, const float*
 int gtos_token_nll_bwd(const float* dloss_row, const float* logits, int64_t ldl, int32_t V, const float* align, int32_t S,
                        const int64_t* copy_seq, const int64_t* target, int64_t rows, int32_t B, int64_t pad_idx,
                        const float* stats, float* dlogits, int64_t lddl, float* dgate_logits, float* dalign,
-                       void* stream);
+                       void* dlogits_bf16 /* optional bf16 copy of dlogits, row stride lddb */, int64_t lddb, void* stream);
 
 /* ---- bank -> dense relation gather (generator.py:79: relation = bank.index_select(0, idx)) and its backward ----
  * forward emits the fp32 [P,D] tensor of the caller's contract and (optionally) the bf16 copy the fused kernels read;
@@ -205,6 +205,11 @@ int gtos_bank_gather(const float* bank, const int64_t* idx, int64_t P, int32_t D
                      void* stream);
 int gtos_bank_scatter_add(const float* d_rel, const int64_t* idx, int64_t P, int32_t D, float* d_bank, int64_t R,
                           void* stream);
+/* the same backward from pairs SORTED by bank row (order = pair indices, keys = idx[order], both int64 [P]; one stable sort
+ * per batch): running sums in registers, one vector reduction per (bank row, 32-pair window) instead of one per pair - the
+ * plain scatter serialises on hot rows (config 2: the <TL> path holds 41 % of the pairs). */
+int gtos_bank_segsum(const float* d_rel, const int64_t* order, const int64_t* keys, int64_t P, int32_t D, float* d_bank,
+                     int64_t R, void* stream);
 /* evaluation batches (generator.py:83-88: `relation[0,:] = 0; relation[idx].sum(3) / count(idx != 0).clamp(min=1)`):
  * idx [P,K] with 0 = empty slot; out[p] = mean of the bank rows of the pair's shortest paths (fp32 and / or bf16). */
 int gtos_bank_gather_mean(const float* bank, const int64_t* idx, int64_t P, int32_t K, int32_t D, float* out_f32,

@@ -131,7 +131,11 @@ def test_config3_shard_shape_vs_oracle(dev):
         outb = m(x, ops.BankedRelation(bank.to(dev), idx), self_padding_mask=mask)
         perm = torch.randperm(B, generator=gen).to(dev)
         outp = m(x[:, perm], ops.bank_gather(bank.to(dev), idx[:, :, perm].contiguous()), self_padding_mask=mask[:, perm])
-    assert torch.equal(out, outb) and torch.equal(out[:, perm], outp)
+    assert torch.equal(out[:, perm], outp)
+    # factorised relation: the fused gather kernel rounds ra / rb once more (projected bank in bf16); with
+    # GTOS_BANKED_FWD=0 the dense bf16 operand feeds the same tcgen05 kernel and the outputs are bit-identical
+    assert torch.equal(out, outb) if not ops.banked_fwd_supported(ops.BankedRelation(bank.to(dev), idx), N, B, D, H) \
+        else rel_err(outb, out) < 5e-3
     P = {k: v.clone() for k, v in cpu.state_dict().items()}
     for b in (0, 11):
         relb = bank.index_select(0, g["relation"][:, :, b].reshape(-1)).view(N, N, 1, D)

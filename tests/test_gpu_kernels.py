@@ -342,11 +342,48 @@ def test_bank_gather_and_scatter(dev):
     rel = ops.bank_gather(bank, idx)
     ref = bank.index_select(0, idx.reshape(-1)).view(N, N, B, D)
     assert torch.equal(rel, ref)
-    assert torch.equal(rel._gtos_bf16, ref.to(torch.bfloat16))
+    assert torch.equal(ops.staged_relation_bf16(rel), ref.to(torch.bfloat16))
     w = torch.randn_like(ref)
     (g,) = torch.autograd.grad((rel * w).sum(), bank)
     (gr,) = torch.autograd.grad((ref * w).sum(), bank)
     assert rel_err(g, gr) < 1e-5
+
+
+@pytest.mark.parametrize("sorted_bwd", [True, False])
+@pytest.mark.parametrize("R,D,N,B", [(300, 128, 9, 4), (5000, 512, 41, 6), (50, 100, 7, 3)])
+def test_bank_tensor_index_select_is_the_callers_gather(dev, R, D, N, B, sorted_bwd, monkeypatch):
+    """RelationEncoder returns a BankTensor: the reference caller's own line (generator.py:79)
+    `relation.index_select(0, idx.view(-1)).view(*idx.size(), -1)` then runs gtos_bank_gather - bit-identical values, the bf16
+    operand copy riding along through .view - and its backward is the sorted segmented sum (or the plain scatter),
+    equal to ATen's index_add_ up to fp32 summation order.  Hot rows, unused rows and a width that is not a multiple of
+    128 are covered."""
+    from gtos_b200 import ops
+    monkeypatch.setattr(ops, "_bank_sorted_bwd", sorted_bwd)
+    g = torch.Generator().manual_seed(SEED + R)
+    plain = torch.randn(R, D, generator=g).to(dev).requires_grad_()
+    idx = torch.randint(0, R // 2, (N, N, B), generator=g)
+    idx[torch.rand(N, N, B, generator=g) < 0.4] = 5                        # a hot row (the <TL> path)
+    idx[0] = 2
+    idx = idx.to(dev)
+    bank = ops.as_bank_tensor(plain * 1.0)
+    assert isinstance(bank, ops.BankTensor)
+    rel = bank.index_select(0, idx.view(-1)).view(*idx.size(), -1)          # the caller's line, verbatim
+    ref = (plain * 1.0).as_subclass(torch.Tensor).index_select(0, idx.view(-1)).view(*idx.size(), -1)
+    assert torch.equal(rel.as_subclass(torch.Tensor), ref)
+    relb = ops.staged_relation_bf16(rel)
+    assert relb is not None and torch.equal(relb, ref.to(torch.bfloat16))
+    w = torch.randn(ref.shape, generator=g).to(dev)
+    (ga,) = torch.autograd.grad((rel * w).sum(), plain)
+    (gb,) = torch.autograd.grad((ref * w).sum(), plain)
+    assert rel_err(ga, gb) < 1e-5
+    assert float(ga[R // 2:].abs().max()) == 0.0                           # rows no pair uses
+    # translator/generator.py:73 spelling, and an in-place write invalidates the bf16 tag
+    rel2 = bank.index_select(0, idx.contiguous().view(-1)).contiguous().view(*idx.size(), -1)
+    assert ops.staged_relation_bf16(rel2) is not None
+    rel2.add_(1.0)
+    assert ops.staged_relation_bf16(rel2) is None
+    # anything else behaves like a plain tensor
+    assert type(bank * 2) is torch.Tensor and torch.equal(bank[idx[..., 0]].as_subclass(torch.Tensor), plain.detach()[idx[..., 0]])
 
 
 @pytest.mark.parametrize("N,B,D,H,R", [(9, 4, 128, 8, 300), (41, 6, 512, 8, 5000), (17, 3, 128, 4, 40)])

@@ -62,8 +62,48 @@ def main():
     dbk = torch.empty(R, D, device=dev)
     res["bank_scatter_add (dense)"] = t(lambda: _lib.check(lib.gtos_bank_scatter_add(drel.data_ptr(), idx.data_ptr(), N * N * B, D,
                                                                                      dbk.data_ptr(), R, st)))
-    for k, v in res.items():
-        print(f"{k:36s} {v:8.1f} us")
+    # ---- forward half: projected bank + gather kernels vs the P-row tcgen05 kernels ----
+    NB = N * B
+    hd = D // H
+    qk = (torch.randn(NB, 2 * D, device=dev)).to(torch.bfloat16)
+    v = torch.randn(NB, D, device=dev)
+    pad = (torch.arange(N, device=dev).unsqueeze(1) >= (g["node_counts"].to(dev) + 1).unsqueeze(0)).to(torch.uint8).contiguous()
+    scores = torch.empty(B, H, N, N, device=dev)
+    probs = torch.empty(B, H, N, N, device=dev)
+    att = torch.empty(NB, D, device=dev)
+    attb = torch.empty(NB, D, dtype=torch.bfloat16, device=dev)
+    seed = ops.rng_state(dev)
+    relb = br.relb
+    res["--- forward half ---"] = 0.0
+    res["rel_score (P-row tcgen05 GEMM + score epilogue)"] = t(lambda: _lib.check(lib.gtos_rel_score(
+        relb.data_ptr(), Wperm.data_ptr(), qk.data_ptr(), qk.data_ptr() + 2 * D, 2 * D, scores.data_ptr(), N, B, D, H, st)))
+    import ctypes as C
+    d = ops._attn_desc(N, N, B, H, hd)
+    d.v, d.ldv = v.data_ptr(), D
+    d.scale, d.p_drop = 1.0, 0.2
+    d.scores_jt, d.key_pad = scores.data_ptr(), pad.data_ptr()
+    d.seed_ptr, d.seed_off = seed.data_ptr(), 12345
+    d.probs = probs.data_ptr()
+    d.out, d.ldo, d.out_bf16 = att.data_ptr(), D, attb.data_ptr()
+    res["attn_fwd (mask+softmax+dropout+PV, encoder)"] = t(lambda: _lib.check(lib.gtos_attn_fwd(C.byref(d), st)))
+    PB = torch.empty(R, 2 * D, dtype=torch.bfloat16, device=dev)
+    res["bank projection gemm_tn [R,D]x[D,2D] -> bf16"] = t(lambda: ops.gemm_tn(br.bankb, Wperm, 2 * D, f32=False, bf16=True))
+    _, PB = ops.gemm_tn(br.bankb, Wperm, 2 * D, f32=False, bf16=True)
+    res["rel_attn_banked_fwd (gather+score+softmax+PV)"] = t(lambda: _lib.check(lib.gtos_rel_attn_banked_fwd(
+        PB.data_ptr(), PB.stride(0), idx.data_ptr(), qk.data_ptr(), qk.data_ptr() + 2 * D, 2 * D, v.data_ptr(), D, pad.data_ptr(), None,
+        0.2, seed.data_ptr(), 12345, probs.data_ptr(), None, att.data_ptr(), D, attb.data_ptr(), N, B, D, H, R, st)))
+    ds = torch.randn(B, H, N, N, device=dev)
+    res["rel_grad (P-row recompute GEMM + G epilogue)"] = t(lambda: _lib.check(lib.gtos_rel_grad(
+        relb.data_ptr(), Wperm.data_ptr(), qk.data_ptr(), qk.data_ptr() + 2 * D, 2 * D, ds.data_ptr(), G.data_ptr(), N, B, D, H, st)))
+    res["rel_grad_banked (gather + G rows)"] = t(lambda: _lib.check(lib.gtos_rel_grad_banked(
+        PB.data_ptr(), PB.stride(0), idx.data_ptr(), qk.data_ptr(), qk.data_ptr() + 2 * D, 2 * D, ds.data_ptr(), G.data_ptr(),
+        N, B, D, H, R, st)))
+    res["bank bf16 gather (dense operand of rel_score)"] = t(lambda: (setattr(br, "_relb", None), br.relb))
+    pairs = N * N * B
+    print(f"gather traffic per launch: {pairs * 2 * D * 2 / 1e6:.0f} MB of PB rows (table {R * 2 * D * 2 / 1e6:.0f} MB); "
+          f"G written: {pairs * 2 * D * 2 / 1e6:.0f} MB")
+    for k, v_ in res.items():
+        print(f"{k:52s} {v_:8.1f} us")
 
 
 if __name__ == "__main__":

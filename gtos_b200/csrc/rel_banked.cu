@@ -53,59 +53,69 @@ __device__ __forceinline__ void ld_bf16_raw(const __nv_bfloat16* p, uint32_t* r)
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
+// bank row of pair (query i, key j, graph b); out-of-range rows read row 0 (never happens with a well-formed batch)
+__device__ __forceinline__ int bank_row(const RelBankedDev& a, int j, int i, int b) {
+  if (i >= a.N) return 0;
+  const long long r = a.idx[((long)j * a.N + i) * a.B + b];
+  return (r >= 0 && r < a.R) ? (int)r : 0;
+}
+
 template <int DL, int QI>
-__global__ void __launch_bounds__(256) rel_attn_banked_fwd_kernel(const RelBankedDev a) {
+__global__ void __launch_bounds__(256, 2) rel_attn_banked_fwd_kernel(const RelBankedDev a) {
   GTOS_PDL_PROLOGUE();
   extern __shared__ float sm[];
   float* sc = sm;                                                   // [QI][H][Npad] scores -> (dropped) probabilities
-  int* s_idx = reinterpret_cast<int*>(sm + QI * a.H * a.Npad);      // [N][QI] bank rows
+  float* part = sm + QI * a.H * a.Npad;                             // [8 warps][QI][D] partial outputs of the PV pass
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int i0 = blockIdx.x * QI, b = blockIdx.y;
   const int N = a.N, B = a.B, H = a.H, hd = a.hd;
   const int lph = 32 / H;                      // lanes per head
   const int h = lane / lph, sub = lane - h * lph;
-  const int dcol = h * hd + sub * DL;          // this lane's features inside D (q, k)
+  const int dcol = h * hd + sub * DL;          // this lane's features inside D (q, k, v)
   const int pcol = h * 2 * hd + sub * DL;      // its ra piece inside the head-interleaved PB row; rb piece at + hd
 
-  float qv[QI][DL];
+  uint32_t qraw[QI][DL / 2];                   // q_i pieces, packed bf16 (unpacked where they are used: fewer live registers)
 #pragma unroll
   for (int qi = 0; qi < QI; ++qi) {
-    const int i = i0 + qi;
-    uint32_t raw[DL / 2];
 #pragma unroll
-    for (int t = 0; t < DL / 2; ++t) raw[t] = 0u;
-    if (i < N) ld_bf16_raw<DL>(a.q + ((long)i * B + b) * a.ldqk + dcol, raw);
-#pragma unroll
-    for (int t = 0; t < DL / 2; ++t) { qv[qi][2 * t] = bf_lo(raw[t]); qv[qi][2 * t + 1] = bf_hi(raw[t]); }
+    for (int t = 0; t < DL / 2; ++t) qraw[qi][t] = 0u;
+    if (i0 + qi < N) ld_bf16_raw<DL>(a.q + ((long)(i0 + qi) * B + b) * a.ldqk + dcol, qraw[qi]);
   }
-  for (int t = threadIdx.x; t < N * QI; t += 256) {
-    const int j = t / QI, qi = t - j * QI, i = i0 + qi;
-    long long r = (i < N) ? a.idx[((long)j * N + i) * B + b] : 0;
-    s_idx[t] = (r >= 0 && r < a.R) ? (int)r : 0;
-  }
-  __syncthreads();
 
-  // ---- scores: one warp per key j, all QI queries ----
+  // ---- scores: one warp per key j, QI queries two at a time; the bank rows of the next key are fetched a step ahead ----
+  int rows_next[QI];
+#pragma unroll
+  for (int qi = 0; qi < QI; ++qi) rows_next[qi] = warp < N ? bank_row(a, warp, i0 + qi, b) : 0;
   for (int j = warp; j < N; j += 8) {
+    int rows[QI];
+#pragma unroll
+    for (int qi = 0; qi < QI; ++qi) rows[qi] = rows_next[qi];
+    if (j + 8 < N) {
+#pragma unroll
+      for (int qi = 0; qi < QI; ++qi) rows_next[qi] = bank_row(a, j + 8, i0 + qi, b);
+    }
     uint32_t kraw[DL / 2];
     ld_bf16_raw<DL>(a.k + ((long)j * B + b) * a.ldqk + dcol, kraw);
-    uint32_t ra[QI][DL / 2], rb[QI][DL / 2];
 #pragma unroll
-    for (int qi = 0; qi < QI; ++qi) {
-      const __nv_bfloat16* pr = a.PB + (long)s_idx[j * QI + qi] * a.ldpb + pcol;
-      ld_bf16_raw<DL>(pr, ra[qi]);
-      ld_bf16_raw<DL>(pr + hd, rb[qi]);
-    }
+    for (int q0 = 0; q0 < QI; q0 += 2) {
+      uint32_t ra[2][DL / 2], rb[2][DL / 2];
 #pragma unroll
-    for (int qi = 0; qi < QI; ++qi) {
-      float acc = 0.f;
-#pragma unroll
-      for (int t = 0; t < DL / 2; ++t) {
-        acc = fmaf(qv[qi][2 * t] + bf_lo(ra[qi][t]), bf_lo(kraw[t]) + bf_lo(rb[qi][t]), acc);
-        acc = fmaf(qv[qi][2 * t + 1] + bf_hi(ra[qi][t]), bf_hi(kraw[t]) + bf_hi(rb[qi][t]), acc);
+      for (int u = 0; u < 2; ++u) {
+        const __nv_bfloat16* pr = a.PB + (long)rows[q0 + u] * a.ldpb + pcol;
+        ld_bf16_raw<DL>(pr, ra[u]);
+        ld_bf16_raw<DL>(pr + hd, rb[u]);
       }
-      for (int o = lph >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (sub == 0) sc[(qi * H + h) * a.Npad + j] = acc * a.scale;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        float acc = 0.f;
+#pragma unroll
+        for (int t = 0; t < DL / 2; ++t) {
+          acc = fmaf(bf_lo(qraw[q0 + u][t]) + bf_lo(ra[u][t]), bf_lo(kraw[t]) + bf_lo(rb[u][t]), acc);
+          acc = fmaf(bf_hi(qraw[q0 + u][t]) + bf_hi(ra[u][t]), bf_hi(kraw[t]) + bf_hi(rb[u][t]), acc);
+        }
+        for (int o = lph >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (sub == 0) sc[((q0 + u) * H + h) * a.Npad + j] = acc * a.scale;
+      }
     }
   }
   __syncthreads();
@@ -147,41 +157,56 @@ __global__ void __launch_bounds__(256) rel_attn_banked_fwd_kernel(const RelBanke
   }
   __syncthreads();
 
-  // ---- PV: o_i = sum_j w_ij v_j; a thread owns two adjacent features (a warp = 64 features = inside one head when hd >= 64) ----
-  for (int f2 = threadIdx.x; f2 < a.D / 2; f2 += 256) {
-    const int f = 2 * f2, hh = f / hd;
-    float acc[QI][2];
+  // ---- PV: o_i = sum_j w_ij v_j.  Same split as the scores (warp = keys j = warp, warp + 8, ..; lane = DL features of its
+  // head): every v row is read once per CTA with all of a warp's loads independent; the 8 partial sums meet in shared memory
+  {
+    float acc[QI][DL];
 #pragma unroll
-    for (int qi = 0; qi < QI; ++qi) acc[qi][0] = acc[qi][1] = 0.f;
-    const float* vp = a.v + (long)b * a.ldv + f;
-    const float* wp = sc + hh * a.Npad;
-#pragma unroll 4
-    for (int j = 0; j < N; ++j) {
-      const float2 vv = *reinterpret_cast<const float2*>(vp + (long)j * B * a.ldv);
+    for (int qi = 0; qi < QI; ++qi)
+#pragma unroll
+      for (int t = 0; t < DL; ++t) acc[qi][t] = 0.f;
+    for (int j = warp; j < N; j += 8) {
+      float vv[DL];
+      const float4* vp = reinterpret_cast<const float4*>(a.v + ((long)j * B + b) * a.ldv + dcol);
+#pragma unroll
+      for (int t = 0; t < DL / 4; ++t) {
+        const float4 f = vp[t];
+        vv[4 * t] = f.x; vv[4 * t + 1] = f.y; vv[4 * t + 2] = f.z; vv[4 * t + 3] = f.w;
+      }
 #pragma unroll
       for (int qi = 0; qi < QI; ++qi) {
-        const float p = wp[qi * H * a.Npad + j];
-        acc[qi][0] = fmaf(p, vv.x, acc[qi][0]);
-        acc[qi][1] = fmaf(p, vv.y, acc[qi][1]);
+        const float p = sc[(qi * H + h) * a.Npad + j];
+#pragma unroll
+        for (int t = 0; t < DL; ++t) acc[qi][t] = fmaf(p, vv[t], acc[qi][t]);
       }
     }
 #pragma unroll
     for (int qi = 0; qi < QI; ++qi) {
-      const int i = i0 + qi;
-      if (i < N) {
-        const long o = ((long)i * B + b);
-        *reinterpret_cast<float2*>(a.out + o * a.ldo + f) = make_float2(acc[qi][0], acc[qi][1]);
-        if (a.out_bf16) *reinterpret_cast<uint32_t*>(a.out_bf16 + o * a.D + f) = pack_bf16x2(acc[qi][0], acc[qi][1]);
-      }
+      float4* dst = reinterpret_cast<float4*>(part + ((long)warp * QI + qi) * a.D + dcol);
+#pragma unroll
+      for (int t = 0; t < DL / 4; ++t) dst[t] = make_float4(acc[qi][4 * t], acc[qi][4 * t + 1], acc[qi][4 * t + 2], acc[qi][4 * t + 3]);
     }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < QI * (a.D / 2); e += 256) {
+    const int qi = e / (a.D / 2), f = 2 * (e - qi * (a.D / 2));
+    const int i = i0 + qi;
+    if (i >= N) continue;
+    float2 s2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) {
+      const float2 t2 = *reinterpret_cast<const float2*>(part + ((long)w8 * QI + qi) * a.D + f);
+      s2.x += t2.x; s2.y += t2.y;
+    }
+    const long o = ((long)i * B + b);
+    *reinterpret_cast<float2*>(a.out + o * a.ldo + f) = s2;
+    if (a.out_bf16) *reinterpret_cast<uint32_t*>(a.out_bf16 + o * a.D + f) = pack_bf16x2(s2.x, s2.y);
   }
 }
 
 template <int DL, int QI>
-__global__ void __launch_bounds__(256) rel_grad_banked_kernel(const RelBankedDev a) {
+__global__ void __launch_bounds__(256, 2) rel_grad_banked_kernel(const RelBankedDev a) {
   GTOS_PDL_PROLOGUE();
-  extern __shared__ float sm[];
-  int* s_idx = reinterpret_cast<int*>(sm);                          // [N][QI]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int i0 = blockIdx.x * QI, b = blockIdx.y;
   const int N = a.N, B = a.B, H = a.H, hd = a.hd;
@@ -189,55 +214,62 @@ __global__ void __launch_bounds__(256) rel_grad_banked_kernel(const RelBankedDev
   const int h = lane / lph, sub = lane - h * lph;
   const int dcol = h * hd + sub * DL;
   const int pcol = h * 2 * hd + sub * DL;
-  float qv[QI][DL];
+  uint32_t qraw[QI][DL / 2];
 #pragma unroll
   for (int qi = 0; qi < QI; ++qi) {
-    const int i = i0 + qi;
-    uint32_t raw[DL / 2];
 #pragma unroll
-    for (int t = 0; t < DL / 2; ++t) raw[t] = 0u;
-    if (i < N) ld_bf16_raw<DL>(a.q + ((long)i * B + b) * a.ldqk + dcol, raw);
-#pragma unroll
-    for (int t = 0; t < DL / 2; ++t) { qv[qi][2 * t] = bf_lo(raw[t]); qv[qi][2 * t + 1] = bf_hi(raw[t]); }
+    for (int t = 0; t < DL / 2; ++t) qraw[qi][t] = 0u;
+    if (i0 + qi < N) ld_bf16_raw<DL>(a.q + ((long)(i0 + qi) * B + b) * a.ldqk + dcol, qraw[qi]);
   }
-  for (int t = threadIdx.x; t < N * QI; t += 256) {
-    const int j = t / QI, qi = t - j * QI, i = i0 + qi;
-    long long r = (i < N) ? a.idx[((long)j * N + i) * B + b] : 0;
-    s_idx[t] = (r >= 0 && r < a.R) ? (int)r : 0;
-  }
-  __syncthreads();
   const RelTiling& rt = a.rt;
+  int rows_next[QI];
+#pragma unroll
+  for (int qi = 0; qi < QI; ++qi) rows_next[qi] = warp < N ? bank_row(a, warp, i0 + qi, b) : 0;
   for (int j = warp; j < N; j += 8) {
+    int rows[QI];
+#pragma unroll
+    for (int qi = 0; qi < QI; ++qi) rows[qi] = rows_next[qi];
+    if (j + 8 < N) {
+#pragma unroll
+      for (int qi = 0; qi < QI; ++qi) rows_next[qi] = bank_row(a, j + 8, i0 + qi, b);
+    }
     uint32_t kraw[DL / 2];
     ld_bf16_raw<DL>(a.k + ((long)j * B + b) * a.ldqk + dcol, kraw);
     const int jb = j / rt.bj, jj = j - jb * rt.bj;
     const float* dsp = a.dscores + (((long)b * H + h) * N + j) * N;
 #pragma unroll
-    for (int qi = 0; qi < QI; ++qi) {
-      const int i = i0 + qi;
-      if (i >= N) continue;                                        // warp-uniform
-      const __nv_bfloat16* pr = a.PB + (long)s_idx[j * QI + qi] * a.ldpb + pcol;
-      uint32_t ra[DL / 2], rb[DL / 2];
-      ld_bf16_raw<DL>(pr, ra);
-      ld_bf16_raw<DL>(pr + hd, rb);
-      const float g = dsp[i] * a.scale;
-      const int ib = i / rt.bi, ii = i - ib * rt.bi;
-      const long row = (((long)b * rt.nj_blk + jb) * rt.ni_blk + ib) * 128 + jj * rt.bi + ii;
-      __nv_bfloat16* gx = a.G + row * (2L * a.D) + pcol;           // d(q+ra) = g (k+rb) | d(k+rb) = g (q+ra)
-      uint32_t wx[DL / 2], wy[DL / 2];
+    for (int q0 = 0; q0 < QI; q0 += 2) {
+      uint32_t ra[2][DL / 2], rb[2][DL / 2];
+      float g[2];
 #pragma unroll
-      for (int t = 0; t < DL / 2; ++t) {
-        wx[t] = pack_bf16x2(g * (bf_lo(kraw[t]) + bf_lo(rb[t])), g * (bf_hi(kraw[t]) + bf_hi(rb[t])));
-        wy[t] = pack_bf16x2(g * (qv[qi][2 * t] + bf_lo(ra[t])), g * (qv[qi][2 * t + 1] + bf_hi(ra[t])));
+      for (int u = 0; u < 2; ++u) {
+        const __nv_bfloat16* pr = a.PB + (long)rows[q0 + u] * a.ldpb + pcol;
+        ld_bf16_raw<DL>(pr, ra[u]);
+        ld_bf16_raw<DL>(pr + hd, rb[u]);
+        g[u] = (i0 + q0 + u < N) ? dsp[i0 + q0 + u] * a.scale : 0.f;
       }
-      if constexpr (DL == 4) {
-        *reinterpret_cast<uint2*>(gx) = make_uint2(wx[0], wx[1]);
-        *reinterpret_cast<uint2*>(gx + hd) = make_uint2(wy[0], wy[1]);
-      } else {
 #pragma unroll
-        for (int t = 0; t < DL / 8; ++t) {
-          *reinterpret_cast<uint4*>(gx + 8 * t) = make_uint4(wx[4 * t], wx[4 * t + 1], wx[4 * t + 2], wx[4 * t + 3]);
-          *reinterpret_cast<uint4*>(gx + hd + 8 * t) = make_uint4(wy[4 * t], wy[4 * t + 1], wy[4 * t + 2], wy[4 * t + 3]);
+      for (int u = 0; u < 2; ++u) {
+        const int i = i0 + q0 + u;
+        if (i >= N) continue;                                      // warp-uniform
+        const int ib = i / rt.bi, ii = i - ib * rt.bi;
+        const long row = (((long)b * rt.nj_blk + jb) * rt.ni_blk + ib) * 128 + jj * rt.bi + ii;
+        __nv_bfloat16* gx = a.G + row * (2L * a.D) + pcol;         // d(q+ra) = g (k+rb) | d(k+rb) = g (q+ra)
+        uint32_t wx[DL / 2], wy[DL / 2];
+#pragma unroll
+        for (int t = 0; t < DL / 2; ++t) {
+          wx[t] = pack_bf16x2(g[u] * (bf_lo(kraw[t]) + bf_lo(rb[u][t])), g[u] * (bf_hi(kraw[t]) + bf_hi(rb[u][t])));
+          wy[t] = pack_bf16x2(g[u] * (bf_lo(qraw[q0 + u][t]) + bf_lo(ra[u][t])), g[u] * (bf_hi(qraw[q0 + u][t]) + bf_hi(ra[u][t])));
+        }
+        if constexpr (DL == 4) {
+          *reinterpret_cast<uint2*>(gx) = make_uint2(wx[0], wx[1]);
+          *reinterpret_cast<uint2*>(gx + hd) = make_uint2(wy[0], wy[1]);
+        } else {
+#pragma unroll
+          for (int t = 0; t < DL / 8; ++t) {
+            *reinterpret_cast<uint4*>(gx + 8 * t) = make_uint4(wx[4 * t], wx[4 * t + 1], wx[4 * t + 2], wx[4 * t + 3]);
+            *reinterpret_cast<uint4*>(gx + hd + 8 * t) = make_uint4(wy[4 * t], wy[4 * t + 1], wy[4 * t + 2], wy[4 * t + 3]);
+          }
         }
       }
     }
@@ -273,7 +305,7 @@ static constexpr int BANKED_QI = 4;
 template <int DL>
 static int launch_banked_fwd(const RelBankedDev& d, cudaStream_t st) {
   constexpr int QI = BANKED_QI;
-  const size_t smem = sizeof(float) * QI * d.H * d.Npad + sizeof(int) * d.N * QI;
+  const size_t smem = sizeof(float) * ((size_t)QI * d.H * d.Npad + (size_t)8 * QI * d.D);
   GTOS_REQUIRE(smem <= 200 * 1024, "rel_attn_banked_fwd: N=%d needs %zu bytes of shared memory", d.N, smem);
   auto kern = rel_attn_banked_fwd_kernel<DL, QI>;
   GTOS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -300,9 +332,8 @@ int rel_attn_banked_fwd(const RelBankedArgs& a, cudaStream_t st) {
 template <int DL>
 static int launch_banked_grad(const RelBankedDev& d, cudaStream_t st) {
   constexpr int QI = BANKED_QI;
-  const size_t smem = sizeof(int) * d.N * QI;
+  const size_t smem = 0;
   auto kern = rel_grad_banked_kernel<DL, QI>;
-  GTOS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((d.N + QI - 1) / QI, d.B);
   GTOS_KLAUNCH(kern, grid, dim3(256), smem, st, d);
   GTOS_LAUNCH_CHECK();

@@ -810,7 +810,7 @@ def banked_fwd_supported(banked, N, B, D, H):
     if D not in (128, 256, 512) or 32 % H != 0 or D % H != 0:
         return False
     npad = (N + 3) // 4 * 4
-    return 4 * H * npad * 4 + 4 * N * 4 <= 200 * 1024 and tuple(banked.idx.shape) == (N, N, B)
+    return 4 * (4 * H * npad + 8 * 4 * D) <= 200 * 1024 and tuple(banked.idx.shape) == (N, N, B)
 
 
 class RelGradAcc:

@@ -140,7 +140,9 @@ def test_graph_transformer_banked_relation_vs_oracle(dev, N, B, D, H, F, L, R, f
     xg, bg = x.to(dev).requires_grad_(), bank.to(dev).requires_grad_()
     out = m(xg, ops.BankedRelation(bg, idx.to(dev)), self_padding_mask=mask.to(dev))
     assert rel_err(out, ref) < TOL
-    compare_grads(m, P, (out * wo.to(dev)).sum(), (ref16 * wo).sum(), [xg, bg], [xc, bc], tol=4 * TOL, tol_max=0.2)
+    # fused: ra / rb additionally pass through bf16 (the projected bank), which the oracle's emulation mode does not model
+    compare_grads(m, P, (out * wo.to(dev)).sum(), (ref16 * wo).sum(), [xg, bg], [xc, bc], tol=(6 if fused else 4) * TOL,
+                  tol_max=0.25 if fused else 0.2)
     compare_grads(m, P, (out * wo.to(dev)).sum(), (ref * wo).sum(), [xg, bg], [xc, bc], tol=0.15, tol_max=0.5)
     # dense path of this repo on the same operands
     xd, bd = x.to(dev).requires_grad_(), bank.to(dev).requires_grad_()

@@ -93,6 +93,7 @@ def make_host_batch(w, B, seed, device_paths=None):
                                  max_path_len=w["path"], seed=seed)
     b = hotpath.batch_tensors(g)
     meta = dict(N=g["N"], T=g["T"], B=B, R=int(g["relation_bank"].shape[1]),
+                row_counts=hotpath.relation_row_counts(g["relation_length"], g["relation_bank"].shape[0]),
                 tokens=int(g["t_len"].sum()), pairs=B * g["N"] * g["N"],
                 valid_pairs=int(((g["node_counts"] + 1) ** 2).sum()), tot_ext=1 + int(g["copy_seq"].max()))
     return b, meta
@@ -370,6 +371,7 @@ class StepRunner:
         pinned, self.static = _views(self.flat_pinned), _views(self.flat_static)
         for k, v in host.items():
             pinned[k].copy_(v)
+        self.static["relation_row_counts"] = meta["row_counts"]      # host-side list (known to the data loader)
         self.bucket = FlatGradBucket(model.parameters(), bind=False)
         self.loss_buf = torch.zeros((), device=dev)
         self.loss_host = torch.zeros((), pin_memory=True)
@@ -597,6 +599,7 @@ def device_batch_leg(args, runner, dev, steps=10):
     pinned = [t.pin_memory() for t in packed_host]
     adj_bytes = sum(t.numel() * t.element_size() for t in pinned)
     batch = dict(runner.static)
+    batch.pop("relation_row_counts", None)            # belongs to the static batch; eager steps read the counts back
     times = {"construct": 0.0}
 
     def construct(i):
@@ -918,6 +921,7 @@ def breakdown(args, w, cfg, model, static, meta, dev, lib, ms_step=None):
     def relenc_step():
         for prm in model.relation_encoder.parameters():
             prm.grad = None
+        model.relation_encoder.row_counts = static.get("relation_row_counts")
         bk = model.relation_encoder(static["relation_bank"], static["relation_length"])
         bk.backward(bk)
 

@@ -8,8 +8,13 @@ The TokenEncoder / CNN / Highway embedding front-end of the same reference file 
 import torch
 from torch import nn
 
+import os
+
 from . import ops
 from .transformer import Embedding
+
+# GTOS_GRU_LEN_SORT=0: every path at every time step (masked in the kernels) instead of the length-sorted prefix schedule
+_LEN_SORT = os.environ.get("GTOS_GRU_LEN_SORT", "1") == "1"
 
 
 def AMREmbedding(vocab, embedding_dim, pretrained_file=None, amr=False, dump_file=None):
@@ -37,6 +42,10 @@ class RelationEncoder(nn.Module):
                           dropout=self.dropout if num_layers > 1 else 0., bidirectional=bidirectional)
         tot_dim = 2 * hidden_size
         self.out_proj = nn.Linear(tot_dim, embed_dim)
+        # [number of paths longer than t for t in range(Lmax)] of the NEXT forward call, if the caller knows it on the host
+        # (the data loader builds relation_length there): lets the packed-sequence schedule skip finished paths without
+        # reading the lengths back from the device.  Consumed (reset to None) by forward.
+        self.row_counts = None
 
     def reset_parameters(self):
         nn.init.normal_(self.out_proj.weight, std=0.02)
@@ -54,8 +63,14 @@ class RelationEncoder(nn.Module):
         """src_tokens [Lmax, R] int64, src_lengths [R] int64 -> [R, embed_dim]  (encoder.py:90-119).
         No host sync: lengths stay on the device (the reference calls .tolist(), encoder.py:99)."""
         p = self.dropout if self.training else 0.0
+        counts, self.row_counts = self.row_counts, None
+        if not _LEN_SORT:
+            counts = None
+        elif counts is None and src_tokens.is_cuda and not torch.cuda.is_current_stream_capturing():
+            # like the reference (encoder.py:99 reads every length back for pack_padded_sequence), but Lmax integers
+            counts = ops.gru_row_counts(src_lengths, src_tokens.shape[0])
         bank = ops.GRUBankFn.apply(src_tokens, src_lengths, self.rel_embed.weight, self.out_proj.weight,
-                                   self.out_proj.bias, self.num_layers, self.hidden_size, float(p),
+                                   self.out_proj.bias, self.num_layers, self.hidden_size, float(p), counts,
                                    *self._gru_weights())
         # a tensor whose dim-0 index_select (the caller's own gather, generator.py:79) runs on this library's kernels
         return ops.as_bank_tensor(bank)

@@ -70,6 +70,8 @@ class HotPath(nn.Module):
 
     def encode(self, batch):
         """generator.py:76-94: relation bank -> dense relation -> graph encoder -> probe / node states."""
+        if self.native and batch.get("relation_row_counts") is not None:
+            self.relation_encoder.row_counts = batch["relation_row_counts"]       # host-known: no device read-back
         bank = self.relation_encoder(batch["relation_bank"], batch["relation_length"])
         idx = batch["relation"]
         if self.relation_mode == "banked":
@@ -123,3 +125,10 @@ def batch_tensors(g):
     out = {k: g[k] for k in BATCH_KEYS if k in g}
     out["causal_mask"] = torch.ones(T, T, dtype=torch.bool).triu_(1)
     return out
+
+
+def relation_row_counts(relation_length, Lmax):
+    """[number of paths longer than t for t in range(Lmax)] from the HOST copy of relation_length (data.py:170-176 builds
+    it there) - put it into the batch dictionary as "relation_row_counts" (a plain list, it does not travel to the GPU)"""
+    ln = relation_length.cpu()
+    return [int((ln > t).sum()) for t in range(int(Lmax))]

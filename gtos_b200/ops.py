@@ -1084,6 +1084,14 @@ def _up64(n):
     return (n + 63) // 64 * 64
 
 
+def gru_row_counts(lengths, Lmax):
+    """[#(len > t) for t in range(Lmax)] as Python ints - one small device-to-host read (the reference reads ALL lengths
+    back here: `src_lengths.tolist()`, encoder.py:99).  Callers that know the lengths on the host (the data loader
+    builds them there) pass the counts in instead and keep the step free of host syncs."""
+    t = torch.arange(Lmax, device=lengths.device).unsqueeze(1)
+    return [int(v) for v in (lengths.unsqueeze(0) > t).sum(1).tolist()]
+
+
 class GRUBankFn(torch.autograd.Function):
     """tokens [Lmax,R] int64 (0 = pad), lengths [R] int64 -> [R, embed_dim].  `weights` is the flat list
     (w_ih, w_hh, b_ih, b_hh) per (layer, direction) in nn.GRU order.
@@ -1091,10 +1099,15 @@ class GRUBankFn(torch.autograd.Function):
     Forward: per (layer, direction, time step) ONE tcgen05 GEMM [x_t | h] x Wcat^T whose epilogue does the gate
     math, packed-sequence masking and writes h (fp32 + bf16 operand copy), the layer output and the saved gates
     (gtos_gru_step_fwd) - no gi / gh round trips through HBM.  Backward: BPTT with a gate kernel + accumulate
-    GEMM per step, then three big GEMMs per (layer, direction) for dW_ih, dW_hh and dx."""
+    GEMM per step, then three big GEMMs per (layer, direction) for dW_ih, dW_hh and dx.
+
+    `counts` (list of Lmax ints, counts[t] = number of paths longer than t, or None): like pack_padded_sequence
+    (encoder.py:93-99) the paths are sorted by length (on the device, stable) so that the live rows of time step t are the
+    first counts[t] rows, and every per-step kernel runs on that prefix only - at config 2 (lengths 1..4) 21 % fewer
+    row-steps, at translator settings (lengths 1..8) 37 %.  None: every row at every step (masked in the kernels)."""
 
     @staticmethod
-    def forward(ctx, tokens, lengths, embed_w, out_w, out_b, num_layers, hidden, p, *weights):
+    def forward(ctx, tokens, lengths, embed_w, out_w, out_b, num_layers, hidden, p, counts, *weights):
         _need_cuda(tokens, lengths, embed_w)
         lib = _lib.load()
         dev = embed_w.device
@@ -1104,6 +1117,20 @@ class GRUBankFn(torch.autograd.Function):
         rows = Lmax * R
         tokens = tokens.contiguous()
         lengths = lengths.contiguous()
+        order = inv = None
+        if counts is not None:
+            counts = [min(int(c), R) for c in counts] + [0]
+            if len(counts) != Lmax + 1 or any(counts[t] < counts[t + 1] for t in range(Lmax)) or (R > 0 and counts[0] > R):
+                raise ValueError(f"GRUBankFn: row counts {counts[:-1]} are not a non-increasing list of {Lmax} values <= {R}")
+            if all(c == R for c in counts[:-1]):
+                counts = None                                                      # nothing to skip
+        if counts is not None:
+            order = torch.sort(lengths, descending=True, stable=True).indices      # longest first
+            inv = torch.empty_like(order)
+            inv[order] = torch.arange(R, device=dev)
+            tokens = tokens.index_select(1, order).contiguous()
+            lengths = lengths.index_select(0, order).contiguous()
+        n_at = (lambda t: counts[t]) if counts is not None else (lambda t: R)
         seed = rng_state(dev) if p > 0 else None
         off_e = new_seed_off() if p > 0 else 0
         xb = torch.empty(rows, _up8(E), dtype=torch.bfloat16, device=dev)
@@ -1114,6 +1141,10 @@ class GRUBankFn(torch.autograd.Function):
         Kin = E
         for l in range(num_layers):
             outb = torch.empty(rows, 2 * Hh, dtype=torch.bfloat16, device=dev) if l < num_layers - 1 else None
+            if outb is not None and counts is not None:
+                for t in range(Lmax):                                              # rows no kernel writes: zero (they are
+                    if counts[t] < R:                                              # operands of the next layer's GEMMs)
+                        outb[t * R + counts[t]:(t + 1) * R].zero_()
             Kx = _up64(Kin)
             ldw = Kx + _up8(Hh)
             per_dir = []
@@ -1132,6 +1163,15 @@ class GRUBankFn(torch.autograd.Function):
                 hsb = torch.empty(Lmax + 1, R, Hh, dtype=torch.bfloat16, device=dev)
                 hs[0].zero_()
                 hsb[0].zero_()
+                if counts is not None:
+                    # rows of hs / hsb[s] that step s - 1 does not write: a path that becomes live at step s (reverse
+                    # direction) starts from h = 0, and hsb[s] as a whole is an operand of the dW_hh GEMM
+                    for s_ in range(1, Lmax):
+                        wrote = counts[s_ - 1] if d == 0 else counts[Lmax - s_]
+                        if wrote < R:
+                            hsb[s_, wrote:].zero_()
+                            if d == 1:
+                                hs[s_, wrote:counts[Lmax - 1 - s_]].zero_()
                 per_dir.append((Wcat, bcat, gates, hs, hsb))
                 saved += [xb, gates, hs, hsb, Wih_t, Whh_t]
 
@@ -1139,14 +1179,23 @@ class GRUBankFn(torch.autograd.Function):
                 Wcat, bcat, gates, hs, hsb = per_dir[d]
                 for s in range(Lmax):
                     t = s if d == 0 else Lmax - 1 - s
+                    n = n_at(t)
+                    if n == 0:
+                        continue
                     x_t = xb[t * R:(t + 1) * R]
                     out_t = outb[t * R:(t + 1) * R, d * Hh:(d + 1) * Hh] if not last else None
                     _lib.check(lib.gtos_gru_step_fwd(_p(x_t), x_t.stride(0), Kin, _p(hsb[s]), Hh, _p(hs[s]), _p(Wcat), ldw,
                                                      Kx, _p(bcat), _p(lengths), t, _p(hs[s + 1]), _p(hsb[s + 1]), Hh,
-                                                     _p(out_t), 2 * Hh, _p(gates[s]), 4 * Hh, R, Hh, _st()),
+                                                     _p(out_t), 2 * Hh, _p(gates[s]), 4 * Hh, n, Hh, _st()),
                                "gru_step_fwd")
                 if last:
-                    finals_b[:, d * Hh:(d + 1) * Hh].copy_(hsb[Lmax])
+                    if counts is None or d == 1:
+                        finals_b[:, d * Hh:(d + 1) * Hh].copy_(hsb[Lmax])
+                    else:
+                        for t in range(Lmax):                                      # a path's final state: its last live step
+                            lo, hi = counts[t + 1], counts[t]
+                            if hi > lo:
+                                finals_b[lo:hi, :Hh].copy_(hsb[t + 1, lo:hi])
 
             with fork(_gru_streams) as f_rev:                                      # reverse direction on the second stream
                 run_dir(1)
@@ -1159,17 +1208,19 @@ class GRUBankFn(torch.autograd.Function):
             layer_offs.append(off_l)
             xb = outb
             Kin = 2 * Hh
+        if inv is not None:
+            finals_b = finals_b.index_select(0, inv)                               # back to the caller's row order
         Wo_b, Wo_t = weight_prep(out_w)
         out, _ = gemm_tn(finals_b, Wo_b, out_w.shape[0], bias=out_b)
         ctx.save_for_backward(tokens, lengths, finals_b, Wo_t, *saved)
-        ctx.meta = (Lmax, R, E, Hh, num_layers, p, seed, off_e, layer_offs, out_w.shape[0], embed_w.shape[0])
+        ctx.meta = (Lmax, R, E, Hh, num_layers, p, seed, off_e, layer_offs, out_w.shape[0], embed_w.shape[0], counts, order)
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dout):
         tokens, lengths, finals_b, Wo_t, *saved = ctx.saved_tensors
-        Lmax, R, E, Hh, num_layers, p, seed, off_e, layer_offs, Dout, V = ctx.meta
+        Lmax, R, E, Hh, num_layers, p, seed, off_e, layer_offs, Dout, V, counts, order = ctx.meta
         lib = _lib.load()
         dev = dout.device
         rows = Lmax * R
@@ -1177,6 +1228,9 @@ class GRUBankFn(torch.autograd.Function):
         doutb, db_out = cast_colsum(dout)
         dW_out = gemm_nn(doutb, finals_b, Dout, 2 * Hh)
         dfinals, _ = gemm_tn(doutb, Wo_t, 2 * Hh)                                   # [R, 2H]
+        if order is not None:
+            dfinals = dfinals.index_select(0, order)                               # into the length-sorted row order
+        n_at = (lambda t: counts[t]) if counts is not None else (lambda t: R)
         wgrads = [None] * (num_layers * 8)
         d_layer_out = None                                                         # [rows, 2H] fp32
         for l in range(num_layers - 1, -1, -1):
@@ -1192,32 +1246,45 @@ class GRUBankFn(torch.autograd.Function):
                 wgrads[base + 2] = torch.zeros(3 * Hh, dtype=torch.float32, device=dev)
                 wgrads[base + 3] = torch.zeros(3 * Hh, dtype=torch.float32, device=dev)
                 dgh = torch.empty(rows, 3 * Hh, dtype=torch.bfloat16, device=dev)      # rows in step order s
+                if counts is not None:
+                    for s_ in range(Lmax):                                             # rows the gate kernel skips: zero,
+                        n_ = counts[s_ if d == 0 else Lmax - 1 - s_]                   # they are operands of the dW GEMMs
+                        if n_ < R:
+                            dgh[s_ * R + n_:(s_ + 1) * R].zero_()
                 per_dir.append(dgh)
                 Wih_t_cat.append(Wih_t)
+            if counts is not None:
+                for t in range(Lmax):
+                    if counts[t] < R:
+                        dgi_cat[t * R + counts[t]:(t + 1) * R].zero_()
 
             def run_dir(d, l=l, per_dir=per_dir, dgi_cat=dgi_cat, d_layer_out=d_layer_out):
                 xb, gates, hs, hsb, Wih_t, Whh_t = saved[(l * 2 + d) * 6:(l * 2 + d) * 6 + 6]
                 Kin = Wih_t.shape[0]
                 base = (l * 2 + d) * 4
                 dgh, db_ih, db_hh = per_dir[d], wgrads[base + 2], wgrads[base + 3]
+                # ONE dh buffer updated in place on the live prefix: a path whose last live step is still to come (in
+                # this backward order) keeps the gradient of its final state until then
                 if l == num_layers - 1:
                     dh = dfinals[:, d * Hh:(d + 1) * Hh].contiguous()
                 else:
                     dh = torch.zeros(R, Hh, dtype=torch.float32, device=dev)
+                dh_part = torch.empty_like(dh)                                         # dh * z (pass-through for finished rows)
                 dgi = dgi_cat[:, d * 3 * Hh:(d + 1) * 3 * Hh]                          # rows in time order t
                 for s in range(Lmax - 1, -1, -1):
                     t = s if d == 0 else Lmax - 1 - s
+                    n = n_at(t)
+                    if n == 0:
+                        continue
                     dout_t = d_layer_out[t * R:(t + 1) * R, d * Hh:(d + 1) * Hh] if d_layer_out is not None else None
-                    dh_part = torch.empty_like(dh)                                     # dh * z (pass-through for finished rows)
                     dgi_t, dgh_s = dgi[t * R:(t + 1) * R], dgh[s * R:(s + 1) * R]
                     _lib.check(lib.gtos_gru_gate_bwd(_p(dh), _p(dout_t), dout_t.stride(0) if dout_t is not None else 0,
                                                      _p(gates[s]), _p(hs[s]), _p(lengths), t, _p(dh_part),
                                                      _p(dgi_t), dgi_t.stride(0), _p(dgh_s), 3 * Hh, _p(db_ih), _p(db_hh),
-                                                     R, Hh, _st()), "gru_gate_bwd")
-                    dh_prev = torch.empty_like(dh)                                     # = dgh @ W_hh + dh * z
+                                                     n, Hh, _st()), "gru_gate_bwd")
+                    # dh <- dgh @ W_hh + dh * z   (rows of the prefix; the kernel reads dh_part and dgh only)
                     _lib.check(lib.gtos_gemm_tn_add(_p(dgh_s), 3 * Hh, _p(Whh_t), Whh_t.stride(0), None, _p(dh_part), Hh,
-                                                    _p(dh_prev), Hh, R, Hh, 3 * Hh, _st()), "gemm_tn_add")
-                    dh = dh_prev
+                                                    _p(dh), Hh, n, Hh, 3 * Hh, _st()), "gemm_tn_add")
                 gemm_nn(dgi, xb, 3 * Hh, Kin, out=wgrads[base + 0])
                 gemm_nn(dgh, hsb[:Lmax].view(rows, Hh), 3 * Hh, Hh, out=wgrads[base + 1])
 
@@ -1241,7 +1308,7 @@ class GRUBankFn(torch.autograd.Function):
                 d_embed = torch.zeros(V, E, dtype=torch.float32, device=dev)
                 _lib.check(lib.gtos_embed_scatter_add(_p(dx), _p(tokens), rows, E, _p(d_embed), p, _p(seed), off_e,
                                                       _st()), "embed_scatter_add")
-        return (None, None, d_embed, dW_out, db_out, None, None, None, *wgrads)
+        return (None, None, d_embed, dW_out, db_out, None, None, None, None, *wgrads)
 
 
 # --------------------------------------------------------------------------------------------

@@ -16,7 +16,7 @@ vp, i32, i64, u64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float
 class AttnDesc(C.Structure):
     """mirror of gtos_attn_desc"""
     _fields_ = [
-        ("T", i32), ("S", i32), ("B", i32), ("H", i32), ("hd", i32), ("pad0", i32),
+        ("T", i32), ("S", i32), ("B", i32), ("H", i32), ("hd", i32), ("bwd_part", i32),
         ("q", vp), ("ldq", i64), ("k", vp), ("ldk", i64), ("v", vp), ("ldv", i64),
         ("scale", f32), ("p_drop", f32),
         ("scores_jt", vp), ("key_pad", vp), ("attn_mask", vp),

@@ -248,7 +248,8 @@ int gtos_attn_bwd(const gtos_attn_desc* d, void* stream) {
   g.dq = d->dq; g.lddq = d->lddq; g.dk = d->dk; g.lddk = d->lddk; g.dv = d->dv; g.lddv = d->lddv;
   g.dq_bf16 = d->dq_bf16; g.dk_bf16 = d->dk_bf16; g.dv_bf16 = d->dv_bf16;
   GTOS_REQUIRE(!g.dq || (d->q && d->k && g.dk), "attn_bwd: decoder mode needs q, k, dq and dk");
-  return attn_bwd(g, S(stream));
+  GTOS_REQUIRE(d->bwd_part >= 0 && d->bwd_part <= 2, "attn_bwd: bwd_part must be 0, 1 or 2");
+  return attn_bwd(g, d->bwd_part, S(stream));
 }
 
 int gtos_add_ln_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* y, void* y_bf16,

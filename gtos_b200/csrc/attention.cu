@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(AT_THREADS, AT_MIN_CTAS) attn_bwd_kv_kernel(co
   }
 }
 
-int attn_bwd(const AttnBwdArgs& g, cudaStream_t st) {
+int attn_bwd(const AttnBwdArgs& g, int part, cudaStream_t st) {
   const AttnArgs& a = g.f;
   GTOS_REQUIRE(a.hd >= 1 && (a.hd <= AT_DC || a.hd % AT_DC == 0), "attention: unsupported head_dim %d", a.hd);
   if (a.T == 0 || a.B == 0) return GTOS_OK;
@@ -452,12 +452,16 @@ int attn_bwd(const AttnBwdArgs& g, cudaStream_t st) {
   GTOS_REQUIRE(smq <= 227 * 1024 && smk <= 227 * 1024, "attention: sequence too long for shared memory");
   GTOS_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smq));
   GTOS_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smk));
-  dim3 gq(a.B * a.H, (a.T + rq - 1) / rq);
-  GTOS_KLAUNCH(attn_bwd_q_kernel, dim3(gq), dim3(AT_THREADS), smq, st, g, rq);
-  GTOS_LAUNCH_CHECK();
-  dim3 gk(a.B * a.H, (a.S + rk - 1) / rk);
-  GTOS_KLAUNCH(attn_bwd_kv_kernel, dim3(gk), dim3(AT_THREADS), smk, st, g, rk);
-  GTOS_LAUNCH_CHECK();
+  if (part != 2) {
+    dim3 gq(a.B * a.H, (a.T + rq - 1) / rq);
+    GTOS_KLAUNCH(attn_bwd_q_kernel, dim3(gq), dim3(AT_THREADS), smq, st, g, rq);
+    GTOS_LAUNCH_CHECK();
+  }
+  if (part != 1) {
+    dim3 gk(a.B * a.H, (a.S + rk - 1) / rk);
+    GTOS_KLAUNCH(attn_bwd_kv_kernel, dim3(gk), dim3(AT_THREADS), smk, st, g, rk);
+    GTOS_LAUNCH_CHECK();
+  }
   return GTOS_OK;
 }
 

@@ -74,7 +74,7 @@ struct AttnBwdArgs {
   float* dv; long lddv;
   void* dq_bf16; void* dk_bf16; void* dv_bf16;   // optional bf16 copies, same element layout as dq / dk / dv
 };
-int attn_bwd(const AttnBwdArgs& a, cudaStream_t st);
+int attn_bwd(const AttnBwdArgs& a, int part, cudaStream_t st);
 int attn_debug_read_trace(unsigned long long* host_out, int enable);   // 3 kernels x 16 clock64 slots of CTA 0
 
 // ---- GRU gate kernels (gru.cu) ------------------------------------------------------------

@@ -648,7 +648,13 @@ class RelAttnFn(torch.autograd.Function):
         d.dscores_jt, d.dscores_ts = _p(ds_jt), _p(ds_ts)
         d.dv, d.lddv = dqkv.data_ptr() + 8 * D, 3 * D
         d.dv_bf16 = dqkv_b.data_ptr() + 4 * D if dqkv_b is not None else None
-        _lib.check(lib.gtos_attn_bwd(C.byref(d), _st()), "attn_bwd(enc)")
+        # dV = Pd^T dO needs nothing from the query-side kernel and nothing reads it before the in_proj backward GEMMs:
+        # it runs beside the query side and the relation gradient kernels
+        with fork(which=4) as f_dv:
+            d.bwd_part = 2
+            _lib.check(lib.gtos_attn_bwd(C.byref(d), _st()), "attn_bwd(enc, key side)")
+        d.bwd_part = 1
+        _lib.check(lib.gtos_attn_bwd(C.byref(d), _st()), "attn_bwd(enc, query side)")
         tiles = rel_tiling(N, B, D, H)["tiles"]
         G = torch.empty(tiles * 128, 2 * D, dtype=torch.bfloat16, device=dev)
         if ctx.fused_bank is not None:
@@ -689,6 +695,7 @@ class RelAttnFn(torch.autograd.Function):
                 acc.Wcat[:, c0:c0 + 2 * D].copy_(WpermT[:, :2 * D])
             _lib.check(lib.gtos_rel_dqk(_p(G), dqkv.data_ptr(), dqkv.data_ptr() + 4 * D, 3 * D, dqb_p, dkb_p, N, B, D, H,
                                         _st()), "rel_dqk")
+            f_dv.join()
             dqkvb, db_in, f_dbin = operand_or_cast(dqkv, dqkv_b)
             with fork() as f_in:
                 gemm_nn(dqkvb, xb2, 3 * D, D, out=dW_in)
@@ -717,6 +724,7 @@ class RelAttnFn(torch.autograd.Function):
         ws = None
         dW_rel = torch.empty(2 * D, D, dtype=torch.float32, device=dev)
         _lib.check(lib.gtos_rel_dw(_p(G), _p(relb), _p(dW_rel), _p(ws), ws_elems, N, B, D, H, _st()), "rel_dw")
+        f_dv.join()
         dqkvb, db_in, f_dbin = operand_or_cast(dqkv, dqkv_b)
         dW_in = torch.empty(3 * D, D, dtype=torch.float32, device=dev)
         with fork() as f_in:

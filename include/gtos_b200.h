@@ -135,7 +135,9 @@ int gtos_rel_dw_bank(const void* S, int64_t lds, const void* bankb, float* dW, i
 /* ---- attention core: masks, softmax, dropout, PV (graph_transformer.py:136-159; transformer.py:131-155) ---- */
 typedef struct gtos_attn_desc {
   int32_t T, S, B, H, hd;
-  int32_t pad0;
+  int32_t bwd_part;  /* gtos_attn_bwd only: 0 = both kernels; 1 = query side only (dS, dq); 2 = key side only (dV, dK).
+                      * The key side's dV needs nothing from the query side (its dK reads dscores_ts), so a caller that does
+                      * not ask for dK (relation attention: dk comes from G) may run the two parts on different streams. */
   const float* q; int64_t ldq;          /* element (t,b,h,d) at q[(t*B+b)*ldq + h*hd + d]; NULL in encoder mode */
   const float* k; int64_t ldk;
   const float* v; int64_t ldv;

@@ -55,26 +55,94 @@ __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 
 
 // bank row of pair (query i, key j, graph b); out-of-range rows read row 0 (never happens with a well-formed batch)
 __device__ __forceinline__ int bank_row(const RelBankedDev& a, int j, int i, int b) {
-  if (i >= a.N) return 0;
   const long long r = a.idx[((long)j * a.N + i) * a.B + b];
   return (r >= 0 && r < a.R) ? (int)r : 0;
 }
 
+// ---- the gather pipeline shared by both kernels ------------------------------------------------------------------------
+// A CTA owns (graph b, QI consecutive queries) and walks the keys in batches of KB = 8: the QI * KB projected-bank rows of a
+// batch are fetched by 32 one-instruction TMA bulk copies (lane l of warp 0: key l / QI, query l % QI) into a shared-memory
+// stage that completes on an mbarrier; two stages, so the rows of batch t + 1 are in flight while batch t is consumed
+// (warp w = key w of the batch).  Gather latency is decoupled from registers: the first version kept the rows of a key
+// in registers and ran at 13 bytes / clk / SM, long-scoreboard bound (profiles/r02_ncu_banked.txt).
+static constexpr int BK_KEYS = 8;
+
+struct GatherPipe {
+  uint8_t* stage[2];
+  uint64_t* full;        // [2]
+  int row_bytes;
+};
+
+template <int QI>
+__device__ __forceinline__ void gather_issue(const RelBankedDev& a, const GatherPipe& gp, int bt, int i0, int b, int lane) {
+  const int s = bt & 1;
+  const int kk = lane / QI, qi = lane - kk * QI;
+  const int j = bt * BK_KEYS + kk, i = i0 + qi;
+  const bool valid = (kk < BK_KEYS) && (j < a.N) && (i < a.N);
+  const unsigned m = __ballot_sync(0xffffffffu, valid);
+  fence_proxy_async();                 // generic reads of this stage (previous batch) are ordered before the async writes
+  if (lane == 0) mbar_expect_tx(&gp.full[s], (uint32_t)(__popc(m) * gp.row_bytes));
+  __syncwarp();
+  if (valid) {
+    const int r = bank_row(a, j, i, b);
+    bulk_copy_g2s(gp.stage[s] + (size_t)lane * gp.row_bytes, a.PB + (long)r * a.ldpb, (uint32_t)gp.row_bytes, &gp.full[s]);
+  }
+}
+
+__device__ __forceinline__ void gather_wait(const GatherPipe& gp, int bt) {
+  const int s = bt & 1;
+  const uint32_t parity = (uint32_t)((bt >> 1) & 1);
+  while (!mbar_try_wait(&gp.full[s], parity)) {
+  }
+}
+
+template <int DL>
+__device__ __forceinline__ void lds_bf16_raw(const uint8_t* p, uint32_t* r) {
+  if constexpr (DL == 4) {
+    const uint2 v = *reinterpret_cast<const uint2*>(p);
+    r[0] = v.x; r[1] = v.y;
+  } else {
+#pragma unroll
+    for (int t = 0; t < DL / 8; ++t) {
+      const uint4 v = *reinterpret_cast<const uint4*>(p + 16 * t);
+      r[4 * t] = v.x; r[4 * t + 1] = v.y; r[4 * t + 2] = v.z; r[4 * t + 3] = v.w;
+    }
+  }
+}
+
 template <int DL, int QI>
-__global__ void __launch_bounds__(256, 2) rel_attn_banked_fwd_kernel(const RelBankedDev a) {
+__global__ void __launch_bounds__(256) rel_attn_banked_fwd_kernel(const RelBankedDev a) {
+  static_assert(QI * BK_KEYS == 32, "one bulk copy per lane of the producer warp");
   GTOS_PDL_PROLOGUE();
-  extern __shared__ float sm[];
-  float* sc = sm;                                                   // [QI][H][Npad] scores -> (dropped) probabilities
-  float* part = sm + QI * a.H * a.Npad;                             // [8 warps][QI][D] partial outputs of the PV pass
+  extern __shared__ __align__(128) uint8_t smem_u8[];
+  const int N = a.N, B = a.B, H = a.H, hd = a.hd;
+  GatherPipe gp;
+  gp.row_bytes = 4 * a.D;                                            // 2D bf16
+  const size_t stage_bytes = (size_t)32 * gp.row_bytes;
+  gp.stage[0] = smem_u8;
+  gp.stage[1] = smem_u8 + stage_bytes;
+  float* sc = reinterpret_cast<float*>(smem_u8 + 2 * stage_bytes);  // [QI][H][Npad] scores -> (dropped) probabilities
+  gp.full = reinterpret_cast<uint64_t*>(sc + QI * H * a.Npad);
+  float* part = reinterpret_cast<float*>(smem_u8);                   // [8 warps][QI][D] PV partials: reuses the stages
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int i0 = blockIdx.x * QI, b = blockIdx.y;
-  const int N = a.N, B = a.B, H = a.H, hd = a.hd;
   const int lph = 32 / H;                      // lanes per head
   const int h = lane / lph, sub = lane - h * lph;
   const int dcol = h * hd + sub * DL;          // this lane's features inside D (q, k, v)
   const int pcol = h * 2 * hd + sub * DL;      // its ra piece inside the head-interleaved PB row; rb piece at + hd
+  const int nb = (N + BK_KEYS - 1) / BK_KEYS;
 
-  uint32_t qraw[QI][DL / 2];                   // q_i pieces, packed bf16 (unpacked where they are used: fewer live registers)
+  if (threadIdx.x == 0) {
+    mbar_init(&gp.full[0], 1);
+    mbar_init(&gp.full[1], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    gather_issue<QI>(a, gp, 0, i0, b, lane);
+    if (nb > 1) gather_issue<QI>(a, gp, 1, i0, b, lane);
+  }
+  uint32_t qraw[QI][DL / 2];                   // q_i pieces, packed bf16
 #pragma unroll
   for (int qi = 0; qi < QI; ++qi) {
 #pragma unroll
@@ -82,43 +150,34 @@ __global__ void __launch_bounds__(256, 2) rel_attn_banked_fwd_kernel(const RelBa
     if (i0 + qi < N) ld_bf16_raw<DL>(a.q + ((long)(i0 + qi) * B + b) * a.ldqk + dcol, qraw[qi]);
   }
 
-  // ---- scores: one warp per key j, QI queries two at a time; the bank rows of the next key are fetched a step ahead ----
-  int rows_next[QI];
-#pragma unroll
-  for (int qi = 0; qi < QI; ++qi) rows_next[qi] = warp < N ? bank_row(a, warp, i0 + qi, b) : 0;
-  for (int j = warp; j < N; j += 8) {
-    int rows[QI];
-#pragma unroll
-    for (int qi = 0; qi < QI; ++qi) rows[qi] = rows_next[qi];
-    if (j + 8 < N) {
-#pragma unroll
-      for (int qi = 0; qi < QI; ++qi) rows_next[qi] = bank_row(a, j + 8, i0 + qi, b);
-    }
+  // ---- scores ----
+  for (int bt = 0; bt < nb; ++bt) {
+    const int j = bt * BK_KEYS + warp;
     uint32_t kraw[DL / 2];
-    ld_bf16_raw<DL>(a.k + ((long)j * B + b) * a.ldqk + dcol, kraw);
 #pragma unroll
-    for (int q0 = 0; q0 < QI; q0 += 2) {
-      uint32_t ra[2][DL / 2], rb[2][DL / 2];
+    for (int t = 0; t < DL / 2; ++t) kraw[t] = 0u;
+    if (j < N) ld_bf16_raw<DL>(a.k + ((long)j * B + b) * a.ldqk + dcol, kraw);
+    gather_wait(gp, bt);
+    if (j < N) {
+      const uint8_t* rows = gp.stage[bt & 1] + (size_t)(warp * QI) * gp.row_bytes + pcol * 2;
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const __nv_bfloat16* pr = a.PB + (long)rows[q0 + u] * a.ldpb + pcol;
-        ld_bf16_raw<DL>(pr, ra[u]);
-        ld_bf16_raw<DL>(pr + hd, rb[u]);
-      }
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int qi = 0; qi < QI; ++qi) {
+        uint32_t ra[DL / 2], rb[DL / 2];
+        lds_bf16_raw<DL>(rows + (size_t)qi * gp.row_bytes, ra);
+        lds_bf16_raw<DL>(rows + (size_t)qi * gp.row_bytes + hd * 2, rb);
         float acc = 0.f;
 #pragma unroll
         for (int t = 0; t < DL / 2; ++t) {
-          acc = fmaf(bf_lo(qraw[q0 + u][t]) + bf_lo(ra[u][t]), bf_lo(kraw[t]) + bf_lo(rb[u][t]), acc);
-          acc = fmaf(bf_hi(qraw[q0 + u][t]) + bf_hi(ra[u][t]), bf_hi(kraw[t]) + bf_hi(rb[u][t]), acc);
+          acc = fmaf(bf_lo(qraw[qi][t]) + bf_lo(ra[t]), bf_lo(kraw[t]) + bf_lo(rb[t]), acc);
+          acc = fmaf(bf_hi(qraw[qi][t]) + bf_hi(ra[t]), bf_hi(kraw[t]) + bf_hi(rb[t]), acc);
         }
         for (int o = lph >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (sub == 0) sc[((q0 + u) * H + h) * a.Npad + j] = acc * a.scale;
+        if (sub == 0) sc[(qi * H + h) * a.Npad + j] = (i0 + qi < N) ? acc * a.scale : 0.f;
       }
     }
+    __syncthreads();                           // every warp is done with this stage
+    if (warp == 0 && bt + 2 < nb) gather_issue<QI>(a, gp, bt + 2, i0, b, lane);
   }
-  __syncthreads();
 
   // ---- masks, softmax over keys, dropout (same counter-based draw as the attention core, so gtos_attn_bwd replays it) ----
   const unsigned long long seed = a.p_drop > 0.f ? reinterpret_cast<const unsigned long long*>(a.seed_ptr)[0] + a.seed_off : 0ull;
@@ -165,6 +224,7 @@ __global__ void __launch_bounds__(256, 2) rel_attn_banked_fwd_kernel(const RelBa
     for (int qi = 0; qi < QI; ++qi)
 #pragma unroll
       for (int t = 0; t < DL; ++t) acc[qi][t] = 0.f;
+#pragma unroll 2
     for (int j = warp; j < N; j += 8) {
       float vv[DL];
       const float4* vp = reinterpret_cast<const float4*>(a.v + ((long)j * B + b) * a.ldv + dcol);
@@ -204,72 +264,92 @@ __global__ void __launch_bounds__(256, 2) rel_attn_banked_fwd_kernel(const RelBa
   }
 }
 
-// One CTA per SM with all four queries' gathers of a key in flight per lane measured faster here (86 us) than two CTAs per SM
-// with the queries taken in pairs (100 us): the kernel is bound by loads in flight per warp, not by resident warps.
 template <int DL, int QI>
 __global__ void __launch_bounds__(256) rel_grad_banked_kernel(const RelBankedDev a) {
+  static_assert(QI * BK_KEYS == 32, "one bulk copy per lane of the producer warp");
   GTOS_PDL_PROLOGUE();
-  extern __shared__ float sm[];
-  int* s_idx = reinterpret_cast<int*>(sm);                          // [N][QI]
+  extern __shared__ __align__(128) uint8_t smem_u8[];
+  const int N = a.N, B = a.B, H = a.H, hd = a.hd;
+  GatherPipe gp;
+  gp.row_bytes = 4 * a.D;
+  const size_t stage_bytes = (size_t)32 * gp.row_bytes;
+  gp.stage[0] = smem_u8;
+  gp.stage[1] = smem_u8 + stage_bytes;
+  gp.full = reinterpret_cast<uint64_t*>(smem_u8 + 2 * stage_bytes);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int i0 = blockIdx.x * QI, b = blockIdx.y;
-  const int N = a.N, B = a.B, H = a.H, hd = a.hd;
   const int lph = 32 / H;
   const int h = lane / lph, sub = lane - h * lph;
   const int dcol = h * hd + sub * DL;
   const int pcol = h * 2 * hd + sub * DL;
-  float qv[QI][DL];
-#pragma unroll
-  for (int qi = 0; qi < QI; ++qi) {
-    const int i = i0 + qi;
-    uint32_t raw[DL / 2];
-#pragma unroll
-    for (int t = 0; t < DL / 2; ++t) raw[t] = 0u;
-    if (i < N) ld_bf16_raw<DL>(a.q + ((long)i * B + b) * a.ldqk + dcol, raw);
-#pragma unroll
-    for (int t = 0; t < DL / 2; ++t) { qv[qi][2 * t] = bf_lo(raw[t]); qv[qi][2 * t + 1] = bf_hi(raw[t]); }
-  }
-  for (int t = threadIdx.x; t < N * QI; t += 256) {
-    const int j = t / QI, qi = t - j * QI, i = i0 + qi;
-    long long r = (i < N) ? a.idx[((long)j * N + i) * B + b] : 0;
-    s_idx[t] = (r >= 0 && r < a.R) ? (int)r : 0;
+  const int nb = (N + BK_KEYS - 1) / BK_KEYS;
+  if (threadIdx.x == 0) {
+    mbar_init(&gp.full[0], 1);
+    mbar_init(&gp.full[1], 1);
+    fence_barrier_init();
   }
   __syncthreads();
+  if (warp == 0) {
+    gather_issue<QI>(a, gp, 0, i0, b, lane);
+    if (nb > 1) gather_issue<QI>(a, gp, 1, i0, b, lane);
+  }
+  uint32_t qraw[QI][DL / 2];
+#pragma unroll
+  for (int qi = 0; qi < QI; ++qi) {
+#pragma unroll
+    for (int t = 0; t < DL / 2; ++t) qraw[qi][t] = 0u;
+    if (i0 + qi < N) ld_bf16_raw<DL>(a.q + ((long)(i0 + qi) * B + b) * a.ldqk + dcol, qraw[qi]);
+  }
   const RelTiling& rt = a.rt;
-  for (int j = warp; j < N; j += 8) {
+  for (int bt = 0; bt < nb; ++bt) {
+    const int j = bt * BK_KEYS + warp;
     uint32_t kraw[DL / 2];
-    ld_bf16_raw<DL>(a.k + ((long)j * B + b) * a.ldqk + dcol, kraw);
-    const int jb = j / rt.bj, jj = j - jb * rt.bj;
-    const float* dsp = a.dscores + (((long)b * H + h) * N + j) * N;
+    float g[QI];
 #pragma unroll
-    for (int qi = 0; qi < QI; ++qi) {
-      const int i = i0 + qi;
-      if (i >= N) continue;                                        // warp-uniform
-      const __nv_bfloat16* pr = a.PB + (long)s_idx[j * QI + qi] * a.ldpb + pcol;
-      uint32_t ra[DL / 2], rb[DL / 2];
-      ld_bf16_raw<DL>(pr, ra);
-      ld_bf16_raw<DL>(pr + hd, rb);
-      const float g = dsp[i] * a.scale;
-      const int ib = i / rt.bi, ii = i - ib * rt.bi;
-      const long row = (((long)b * rt.nj_blk + jb) * rt.ni_blk + ib) * 128 + jj * rt.bi + ii;
-      __nv_bfloat16* gx = a.G + row * (2L * a.D) + pcol;           // d(q+ra) = g (k+rb) | d(k+rb) = g (q+ra)
-      uint32_t wx[DL / 2], wy[DL / 2];
+    for (int t = 0; t < DL / 2; ++t) kraw[t] = 0u;
 #pragma unroll
-      for (int t = 0; t < DL / 2; ++t) {
-        wx[t] = pack_bf16x2(g * (bf_lo(kraw[t]) + bf_lo(rb[t])), g * (bf_hi(kraw[t]) + bf_hi(rb[t])));
-        wy[t] = pack_bf16x2(g * (qv[qi][2 * t] + bf_lo(ra[t])), g * (qv[qi][2 * t + 1] + bf_hi(ra[t])));
-      }
-      if constexpr (DL == 4) {
-        *reinterpret_cast<uint2*>(gx) = make_uint2(wx[0], wx[1]);
-        *reinterpret_cast<uint2*>(gx + hd) = make_uint2(wy[0], wy[1]);
-      } else {
+    for (int qi = 0; qi < QI; ++qi) g[qi] = 0.f;
+    if (j < N) {
+      ld_bf16_raw<DL>(a.k + ((long)j * B + b) * a.ldqk + dcol, kraw);
+      const float* dsp = a.dscores + (((long)b * H + h) * N + j) * N;
 #pragma unroll
-        for (int t = 0; t < DL / 8; ++t) {
-          *reinterpret_cast<uint4*>(gx + 8 * t) = make_uint4(wx[4 * t], wx[4 * t + 1], wx[4 * t + 2], wx[4 * t + 3]);
-          *reinterpret_cast<uint4*>(gx + hd + 8 * t) = make_uint4(wy[4 * t], wy[4 * t + 1], wy[4 * t + 2], wy[4 * t + 3]);
+      for (int qi = 0; qi < QI; ++qi)
+        if (i0 + qi < N) g[qi] = dsp[i0 + qi] * a.scale;
+    }
+    gather_wait(gp, bt);
+    if (j < N) {
+      const uint8_t* rows = gp.stage[bt & 1] + (size_t)(warp * QI) * gp.row_bytes + pcol * 2;
+      const int jb = j / rt.bj, jj = j - jb * rt.bj;
+#pragma unroll
+      for (int qi = 0; qi < QI; ++qi) {
+        const int i = i0 + qi;
+        if (i >= N) continue;                                      // warp-uniform
+        uint32_t ra[DL / 2], rb[DL / 2];
+        lds_bf16_raw<DL>(rows + (size_t)qi * gp.row_bytes, ra);
+        lds_bf16_raw<DL>(rows + (size_t)qi * gp.row_bytes + hd * 2, rb);
+        const int ib = i / rt.bi, ii = i - ib * rt.bi;
+        const long row = (((long)b * rt.nj_blk + jb) * rt.ni_blk + ib) * 128 + jj * rt.bi + ii;
+        __nv_bfloat16* gx = a.G + row * (2L * a.D) + pcol;         // d(q+ra) = g (k+rb) | d(k+rb) = g (q+ra)
+        uint32_t wx[DL / 2], wy[DL / 2];
+#pragma unroll
+        for (int t = 0; t < DL / 2; ++t) {
+          wx[t] = pack_bf16x2(g[qi] * (bf_lo(kraw[t]) + bf_lo(rb[t])), g[qi] * (bf_hi(kraw[t]) + bf_hi(rb[t])));
+          wy[t] = pack_bf16x2(g[qi] * (bf_lo(qraw[qi][t]) + bf_lo(ra[t])), g[qi] * (bf_hi(qraw[qi][t]) + bf_hi(ra[t])));
+        }
+        if constexpr (DL == 4) {
+          *reinterpret_cast<uint2*>(gx) = make_uint2(wx[0], wx[1]);
+          *reinterpret_cast<uint2*>(gx + hd) = make_uint2(wy[0], wy[1]);
+        } else {
+#pragma unroll
+          for (int t = 0; t < DL / 8; ++t) {
+            *reinterpret_cast<uint4*>(gx + 8 * t) = make_uint4(wx[4 * t], wx[4 * t + 1], wx[4 * t + 2], wx[4 * t + 3]);
+            *reinterpret_cast<uint4*>(gx + hd + 8 * t) = make_uint4(wy[4 * t], wy[4 * t + 1], wy[4 * t + 2], wy[4 * t + 3]);
+          }
         }
       }
     }
+    __syncthreads();
+    if (warp == 0 && bt + 2 < nb) gather_issue<QI>(a, gp, bt + 2, i0, b, lane);
   }
 }
 
@@ -302,8 +382,9 @@ static constexpr int BANKED_QI = 4;
 template <int DL>
 static int launch_banked_fwd(const RelBankedDev& d, cudaStream_t st) {
   constexpr int QI = BANKED_QI;
-  const size_t smem = sizeof(float) * ((size_t)QI * d.H * d.Npad + (size_t)8 * QI * d.D);
-  GTOS_REQUIRE(smem <= 200 * 1024, "rel_attn_banked_fwd: N=%d needs %zu bytes of shared memory", d.N, smem);
+  // two gather stages of 32 rows (reused for the PV partials: 8 * QI * D floats fit), the score block, two mbarriers
+  const size_t smem = (size_t)2 * 32 * 4 * d.D + sizeof(float) * (size_t)QI * d.H * d.Npad + 64;
+  GTOS_REQUIRE(smem <= 220 * 1024, "rel_attn_banked_fwd: N=%d needs %zu bytes of shared memory", d.N, smem);
   auto kern = rel_attn_banked_fwd_kernel<DL, QI>;
   GTOS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((d.N + QI - 1) / QI, d.B);
@@ -329,7 +410,7 @@ int rel_attn_banked_fwd(const RelBankedArgs& a, cudaStream_t st) {
 template <int DL>
 static int launch_banked_grad(const RelBankedDev& d, cudaStream_t st) {
   constexpr int QI = BANKED_QI;
-  const size_t smem = sizeof(int) * d.N * QI;
+  const size_t smem = (size_t)2 * 32 * 4 * d.D + 64;
   auto kern = rel_grad_banked_kernel<DL, QI>;
   GTOS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((d.N + QI - 1) / QI, d.B);

@@ -135,6 +135,9 @@ class OverlappedGradBuckets:
 
     def _launch(self, gi):
         g = self.groups[gi]
+        if self.slices[gi].is_cuda:
+            from . import ops
+            ops.join_deferred_now()          # weight-gradient kernels still running on the side stream (ops.deferred_param_grads)
         parts = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in g]
         torch.cat(parts, out=self.slices[gi])
         self._done[gi] = True

@@ -136,6 +136,17 @@ class deferred_param_grads:
         return False
 
 
+def join_deferred_now():
+    """make the current stream wait for the parameter-gradient work deferred so far (a consumer that reads .grad tensors
+    in the middle of a `deferred_param_grads` block - e.g. a gradient bucket that is reduced during the backward pass)"""
+    if _deferred["streams"]:
+        cur = torch.cuda.current_stream()
+        for _main, side in _deferred["streams"].values():
+            cur.wait_stream(side)
+        _deferred["streams"].clear()
+        _deferred["keep"].clear()
+
+
 def fork(enabled=None, which=0):
     """with fork() as f: <launches on the side stream> ... f.join() before the results are handed on.
     Outputs written inside the block must be allocated BEFORE it (on the caller's stream)."""
@@ -818,7 +829,7 @@ def banked_fwd_supported(banked, N, B, D, H):
     if D not in (128, 256, 512) or 32 % H != 0 or D % H != 0:
         return False
     npad = (N + 3) // 4 * 4
-    return 4 * (4 * H * npad + 8 * 4 * D) <= 200 * 1024 and tuple(banked.idx.shape) == (N, N, B)
+    return 2 * 32 * 4 * D + 4 * 4 * H * npad + 64 <= 220 * 1024 and tuple(banked.idx.shape) == (N, N, B)
 
 
 class RelGradAcc:

@@ -9,6 +9,6 @@ for v in "$@"; do
     for tok in $v; do case "$tok" in --*) flags="$flags $tok";; *=*) envs="$envs $tok";; *) flags="$flags $tok";; esac; done
   fi
   name=$(echo "$v" | tr ' =/' '___')
-  ms=$(env $envs timeout 300 python bench.py --steps 20 --warmup 5 --no-extras --no-breakdown --skip-cpu-baseline $flags 2> "$out/$name.err" | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('%.3f ms  e2e %.3f ms  launches %d' % (d['ms_per_step'], d['e2e']['ms_per_step'], d['gpu_launches_per_step']))")
+  ms=$(env $envs timeout 150 python bench.py --steps 20 --warmup 5 --no-extras --no-breakdown --skip-cpu-baseline $flags 2> "$out/$name.err" | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('%.3f ms  e2e %.3f ms  launches %d' % (d['ms_per_step'], d['e2e']['ms_per_step'], d['gpu_launches_per_step']))")
   echo "$v : $ms" | tee -a "$out/ab.txt"
 done

@@ -48,6 +48,8 @@ SIGNATURES = {
     "gtos_gemm_nn": (i32, [vp, i64, vp, i64, vp, i64, i32, i32, i32, vp, i64, vp]),
     "gtos_rel_tiling": (i32, [i32, i32, i32, i32, C.POINTER(i32)]),
     "gtos_rel_score": (i32, [vp, vp, vp, vp, i64, vp, i32, i32, i32, i32, vp]),
+    "gtos_rel_attn_fusable": (i32, [i32, i32, i32, i32]),
+    "gtos_rel_attn_fwd": (i32, [vp, vp, vp, vp, i64, vp, i64, vp, f32, vp, u64, vp, vp, vp, i64, vp, i32, i32, i32, i32, vp]),
     "gtos_rel_grad": (i32, [vp, vp, vp, vp, i64, vp, vp, i32, i32, i32, i32, vp]),
     "gtos_rel_drel": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "gtos_rel_dw_workspace": (i64, [i32, i32, i32, i32]),

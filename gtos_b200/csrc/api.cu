@@ -128,6 +128,31 @@ int gtos_rel_score(const void* relb, const void* Wperm, const void* q, const voi
   return launch_gemm_tn(MODE_SCORE, a, S(stream));
 }
 
+int gtos_rel_attn_fusable(int32_t N, int32_t B, int32_t D, int32_t H) {
+  RelTiling rt;
+  if (choose_rel_tiling(&rt, N, B, D, H)) return 0;
+  return rel_attn_fusable(rt) ? 1 : 0;
+}
+
+int gtos_rel_attn_fwd(const void* relb, const void* Wperm, const void* q, const void* k, int64_t ldqk, const void* v,
+                      int64_t ldv, const uint8_t* key_pad, float p_drop, const void* seed_ptr, uint64_t seed_off,
+                      float* probs, float* probs_dropped, float* att, int64_t ldatt, void* att_bf16, int32_t N, int32_t B,
+                      int32_t D, int32_t H, void* stream) {
+  GemmTnArgs a;
+  int e = rel_args(&a, N, B, D, H);
+  if (e) return e;
+  GTOS_REQUIRE(ldqk % 8 == 0, "rel_attn_fwd: q/k row stride must be a multiple of 8 bf16 elements");
+  if (!rel_attn_fusable(a.rt)) {
+    set_error("rel_attn_fwd: N=%d D=%d H=%d is not fusable (needs all keys of a query in one 128-pair tile and head_dim 64); "
+              "use gtos_rel_score + gtos_attn_fwd", N, D, H);
+    return GTOS_ERR_UNSUPPORTED;
+  }
+  a.A = relb; a.lda = D; a.Bm = Wperm; a.ldb = D; a.q = q; a.k = k; a.ldqk = ldqk;
+  a.fuse = 1; a.v = v; a.ldv = ldv; a.key_pad = key_pad; a.p_drop = p_drop; a.seed_ptr = seed_ptr; a.seed_off = seed_off;
+  a.probs = probs; a.probs_dropped = probs_dropped; a.att = att; a.ldatt = ldatt; a.att_bf16 = att_bf16;
+  return launch_gemm_tn(MODE_SCORE, a, S(stream));
+}
+
 int gtos_rel_grad(const void* relb, const void* Wperm, const void* q, const void* k, int64_t ldqk,
                   const float* dscores, void* G, int32_t N, int32_t B, int32_t D, int32_t H, void* stream) {
   GemmTnArgs a;

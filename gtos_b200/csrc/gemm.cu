@@ -71,6 +71,17 @@ struct TnDev {
   int qk_stage_bytes;  // 4*(bi8+bj8)*128
   int tma_out;         // epilogue stages tiles in shared memory and writes them with TMA stores
   int dbg;             // GTOS_DBG bit 0: relation epilogues skip their body (pipeline-rate experiment, wrong results)
+  // MODE_SCORE with the attention tail fused in (fuse != 0): masks + softmax + dropout + PV in the epilogue
+  int fuse;
+  const uint8_t* key_pad;
+  float p_drop;
+  const void* seed_ptr;
+  unsigned long long seed_off;
+  float* probs;
+  float* probs_dropped;
+  float* att;
+  long ldatt;
+  __nv_bfloat16* att_b;
   // MODE_GRU
   int kx_blocks;       // k-blocks that come from x_t (tmA); the rest come from h_prev (tmQ slot)
   int gru_H, gru_t;
@@ -146,7 +157,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* qk_base = smem + p.stages * STAGE_BYTES;
   uint8_t* out_stage = qk_base + (REL ? 2 * p.qk_stage_bytes : 0);  // 1024-aligned (all regions are multiples of 1 KB)
   [[maybe_unused]] uint8_t* gru_stage = out_stage + 2 * BN * 4;   // MODE_GRU: 8 warp-private 8 KB store-staging tiles
-  PipeBars* bars = reinterpret_cast<PipeBars*>(out_stage + (p.tma_out ? OUT_STAGE_BYTES : (MODE == MODE_GRU ? 2 * BN * 4 + 8 * 8192 : 0)));
+  PipeBars* bars = reinterpret_cast<PipeBars*>(out_stage + ((p.tma_out || p.fuse) ? OUT_STAGE_BYTES : (MODE == MODE_GRU ? 2 * BN * 4 + 8 * 8192 : 0)));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -155,7 +166,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if (p.tma_out) tma_prefetch_desc(&tmO);
+    if (p.tma_out || p.fuse) tma_prefetch_desc(&tmO);
     if (REL) {
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmK);
@@ -199,13 +210,16 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           rel_tile_decode(p.rt, m_blk, b, j0, i0);   // a dummy tile past the end decodes to b == B: TMA zero-fills it
           // q / k slices for this (tile, head group): dims [n_blk*BN/2, +BN/2)
           wait_bar(&bars->qempty[qs], qph ^ 1);
-          mbar_expect_tx(&bars->qfull[qs], (uint32_t)((BN / 128) * (p.rt.bi + p.rt.bj) * 128));
+          const bool fuse_v = (MODE == MODE_SCORE) && p.fuse;
+          mbar_expect_tx(&bars->qfull[qs], (uint32_t)((BN / 128) * (p.rt.bi + p.rt.bj * (fuse_v ? 2 : 1)) * 128));
           uint8_t* qb = qk_base + qs * p.qk_stage_bytes;
           const int d0 = n_blk * (BN / 2);
 #pragma unroll
           for (int c = 0; c < BN / 128; ++c) {   // bf16 q/k: one 128-byte box row = 64 dims
             tma_load_3d(&tmQ, &bars->qfull[qs], qb + c * p.bi8 * 128, d0 + c * 64, b, i0);
             tma_load_3d(&tmK, &bars->qfull[qs], qb + (BN / 128) * p.bi8 * 128 + c * p.bj8 * 128, d0 + c * 64, b, j0);
+            if (fuse_v)                          // the value rows of the tile's keys, same box shape as k (tmO = v map)
+              tma_load_3d(&tmO, &bars->qfull[qs], qb + (BN / 128) * (p.bi8 + p.bj8) * 128 + c * p.bj8 * 128, d0 + c * 64, b, j0);
           }
           if (++qs == 2) { qs = 0; qph ^= 1; }
         }
@@ -637,6 +651,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         [[maybe_unused]] const bool issuer = (quarter == 2 && lane == 0);   // first warp of each warpgroup
         float acc = 0.f;
         float g = 0.f;
+        [[maybe_unused]] float s_val = 0.f;     // fused attention: the finished score of this warpgroup's head
         float ra[2][16], rb[2][16];
         // software pipeline: the TMEM loads of chunk t+1 are in flight while chunk t is being computed
         auto issue_ld = [&](int it, float* a_, float* b_) {
@@ -669,7 +684,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if constexpr (MODE == MODE_SCORE) {
 #pragma unroll
               for (int u = 0; u < 16; ++u) acc = fmaf(qv[u] + ra_[u], kv[u] + rb__[u], acc);
-              if (c + 16 == hd && valid) p.scores[rs0 + (long)hh * hstride] = acc * p.rt.scale;
+              if (c + 16 == hd) {
+                if (p.fuse) s_val = acc * p.rt.scale;
+                else if (valid) p.scores[rs0 + (long)hh * hstride] = acc * p.rt.scale;
+              }
             } else {
               // G columns (permuted order): [d(q+ra) = g*(k+rb) | d(k+rb) = g*(q+ra)]
               uint32_t wx[8], wy[8];
@@ -716,6 +734,56 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 *reinterpret_cast<uint4*>(grow + hd) = make_uint4(wy[0], wy[1], wy[2], wy[3]);
                 *reinterpret_cast<uint4*>(grow + hd + 8) = make_uint4(wy[4], wy[5], wy[6], wy[7]);
               }
+            }
+          }
+        }
+        if constexpr (MODE == MODE_SCORE) {
+          if (p.fuse) {
+            // ---- attention tail (graph_transformer.py:136-159) on the tile's complete softmax rows: the tile holds ALL
+            // keys of its bi queries (bj == N) and this warpgroup owns ONE head (hd = 64, BN = 256), so mask, softmax,
+            // dropout and P.V finish here - the [B,H,N,N] scores never reach HBM and no second kernel runs.
+            float* ssm = reinterpret_cast<float*>(out_stage) + wg * 256;      // [128 scores | 128 dropped probabilities]
+            const int bi = p.rt.bi, bj = p.rt.bj, Nn = p.rt.N, Bb = p.rt.B;
+            const int head = n_blk * 2 + wg;
+            const int qi_ = ri0 + rii, kj_ = rj0 + rjj;
+            const bool live = valid && !(p.key_pad && p.key_pad[(long)kj_ * Bb + rb_]);
+            ssm[r] = live ? s_val : -INFINITY;
+            named_bar_sync(1 + 2 * wg, 128);
+            float mx = -INFINITY;
+            for (int jj = 0; jj < bj; ++jj) mx = fmaxf(mx, ssm[jj * bi + rii]);
+            float sum = 0.f;
+            for (int jj = 0; jj < bj; ++jj) {
+              const float sv = ssm[jj * bi + rii];
+              sum += (sv == -INFINITY) ? 0.f : __expf(sv - mx);
+            }
+            float pr = (live && sum > 0.f) ? __expf(s_val - mx) / sum : 0.f;
+            if (valid) {
+              const long pidx = (((long)rb_ * p.rt.H + head) * Nn + qi_) * Nn + kj_;
+              p.probs[pidx] = pr;
+              if (p.p_drop > 0.f) {
+                const unsigned long long seed = reinterpret_cast<const unsigned long long*>(p.seed_ptr)[0] + p.seed_off;
+                pr = (rng_uniform(seed, (unsigned long long)pidx) >= p.p_drop) ? pr * (1.f / (1.f - p.p_drop)) : 0.f;
+              }
+              if (p.probs_dropped) p.probs_dropped[pidx] = pr;
+            }
+            ssm[128 + r] = valid ? pr : 0.f;
+            named_bar_sync(2 + 2 * wg, 128);
+            // o_i = sum_j w_ij v_j for the head's 64 features: thread = (query ii = r / 32, feature pair r % 32)
+            const int ii2 = r >> 5, d2 = r & 31;
+            if (ii2 < bi && ri0 + ii2 < Nn && m_blk < p.m_tiles) {
+              const uint8_t* vbx = qb + (BN / 128) * (p.bi8 + p.bj8) * 128 + wg * p.bj8 * 128;   // 64-dim chunk of head wg
+              const int e = 2 * d2;
+              float o0 = 0.f, o1 = 0.f;
+              for (int jj = 0; jj < bj; ++jj) {
+                const float w = ssm[128 + jj * bi + ii2];
+                const __nv_bfloat162 v2 = *reinterpret_cast<const __nv_bfloat162*>(vbx + jj * 128 + (((e >> 3) ^ (jj & 7)) << 4) + (e & 7) * 2);
+                const float2 vf = __bfloat1622float2(v2);
+                o0 = fmaf(w, vf.x, o0);
+                o1 = fmaf(w, vf.y, o1);
+              }
+              const long orow = (long)(ri0 + ii2) * Bb + rb_;
+              *reinterpret_cast<float2*>(p.att + orow * p.ldatt + head * 64 + e) = make_float2(o0, o1);
+              if (p.att_b) *reinterpret_cast<uint32_t*>(p.att_b + orow * p.ldatt + head * 64 + e) = pack_bf16x2(o0, o1);
             }
           }
         }
@@ -810,6 +878,12 @@ int set_sm_reserve(int n) {
   return GTOS_OK;
 }
 
+bool rel_attn_fusable(const RelTiling& rt) {
+  // all keys of a query in one tile (softmax rows complete), one 64-wide head per epilogue warpgroup of a 256-column unit,
+  // and one thread per (query, feature pair) of the head for the P.V product
+  return rt.nj_blk == 1 && rt.bj == rt.N && rt.hd == 64 && rt.bi * 32 <= 128 && rt.D % 128 == 0;
+}
+
 int make_rel_tmaps(const RelTiling& rt, const void* relb, const void* q, const void* k, long ldqk,
                    CUtensorMap* tmA, CUtensorMap* tmQ, CUtensorMap* tmK) {
   {
@@ -848,11 +922,29 @@ static int launch_tn(const GemmTnArgs& a, cudaStream_t stream) {
   p.dbg = dbg;
   CUtensorMap tmA, tmB, tmQ, tmK;
   int e;
+  CUtensorMap tmV;
+  bool have_v = false;
   if (REL) {
     p.m_tiles = a.rt.tiles;
     p.bi8 = (a.rt.bi + 7) & ~7;
     p.bj8 = (a.rt.bj + 7) & ~7;
-    p.qk_stage_bytes = (BN / 128) * (p.bi8 + p.bj8) * 128;
+    if (MODE == MODE_SCORE && a.fuse) {
+      GTOS_REQUIRE(rel_attn_fusable(a.rt) && BN == 256, "rel_attn_fwd: shape not fusable (N=%d D=%d H=%d)", a.rt.N, a.rt.D, a.rt.H);
+      GTOS_REQUIRE(a.v && a.probs && a.att && a.ldv % 8 == 0 && a.ldatt % 2 == 0, "rel_attn_fwd: v / probs / att are required");
+      GTOS_REQUIRE(a.p_drop == 0.f || a.seed_ptr, "rel_attn_fwd: dropout needs a device seed pointer");
+      p.fuse = 1;
+      p.key_pad = a.key_pad; p.p_drop = a.p_drop; p.seed_ptr = a.seed_ptr; p.seed_off = a.seed_off;
+      p.probs = a.probs; p.probs_dropped = a.probs_dropped; p.att = a.att; p.ldatt = a.ldatt;
+      p.att_b = reinterpret_cast<__nv_bfloat16*>(a.att_bf16);
+      const RelTiling& rt = a.rt;
+      uint64_t dims[3] = {(uint64_t)rt.D, (uint64_t)rt.B, (uint64_t)rt.N};
+      uint64_t str[3] = {0, (uint64_t)a.ldv * 2, (uint64_t)rt.B * a.ldv * 2};
+      uint32_t boxv[3] = {64, 1, (uint32_t)rt.bj};
+      e = make_tmap_nd(&tmV, a.v, 2, 3, dims, str, boxv, true);
+      if (e) return e;
+      have_v = true;
+    }
+    p.qk_stage_bytes = (BN / 128) * (p.bi8 + p.bj8 * (p.fuse ? 2 : 1)) * 128;
     e = make_rel_tmaps(a.rt, a.A, a.q, a.k, a.ldqk, &tmA, &tmQ, &tmK);
     if (e) return e;
   } else {
@@ -866,7 +958,7 @@ static int launch_tn(const GemmTnArgs& a, cudaStream_t stream) {
   if (e) return e;
   p.units = ((p.m_tiles + CG - 1) / CG) * p.n_tiles;   // CG = 2: units are (tile pair, n block)
   // ---- output path: TMA stores from swizzled staging tiles where the layout allows it ----
-  CUtensorMap tmO = tmB;
+  CUtensorMap tmO = have_v ? tmV : tmB;
   constexpr int OUT_STAGE_BYTES = tn_out_stage_bytes<MODE>();
   p.tma_out = 0;
   static const bool grad_tma = !(getenv("GTOS_GRAD_TMA") && getenv("GTOS_GRAD_TMA")[0] == '0');
@@ -907,7 +999,7 @@ static int launch_tn(const GemmTnArgs& a, cudaStream_t stream) {
   }
   constexpr int STAGE_BYTES = A_STAGE_BYTES + (BN / CG) * BK * 2;
   const int budget = 227 * 1024 - 1024 /*align*/ - (int)sizeof(PipeBars) - (REL ? 2 * p.qk_stage_bytes : 0) -
-                     (p.tma_out ? OUT_STAGE_BYTES : 0);
+                     ((p.tma_out || p.fuse) ? OUT_STAGE_BYTES : 0);
   int stages = budget / STAGE_BYTES;
   if (stages > 6) stages = 6;
   if (stages < 2) {
@@ -916,7 +1008,7 @@ static int launch_tn(const GemmTnArgs& a, cudaStream_t stream) {
   }
   p.stages = stages;
   const int smem_bytes = 1024 + stages * STAGE_BYTES + (REL ? 2 * p.qk_stage_bytes : 0) +
-                         (p.tma_out ? OUT_STAGE_BYTES : 0) + (int)sizeof(PipeBars);
+                         ((p.tma_out || p.fuse) ? OUT_STAGE_BYTES : 0) + (int)sizeof(PipeBars);
   auto kern = gemm_tn_kernel<BN, MODE, CG>;
   GTOS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   int grid = p.units * CG < num_sms() ? p.units * CG : (num_sms() / CG) * CG;

@@ -47,11 +47,24 @@ struct GemmTnArgs {
   const void* q;       // bf16 [N,B,D] (bias included, unscaled), row stride ldqk elements
   const void* k;       // bf16 [N,B,D]
   long ldqk;
-  float* scores;       // SCORE out: [B,H,N(j),N(i)]
+  float* scores;       // SCORE out: [B,H,N(j),N(i)]  (null when the attention tail is fused)
+  // SCORE with the attention tail fused into the epilogue (fuse != 0; see rel_attn_fusable)
+  int fuse;
+  const void* v;       // bf16 [N,B,D] projected values, row stride ldv elements
+  long ldv;
+  const uint8_t* key_pad;                // [N,B] or null
+  float p_drop; const void* seed_ptr; unsigned long long seed_off;
+  float* probs;        // [B,H,N(i),N(j)] softmax (pre-dropout), saved for the backward
+  float* probs_dropped;                  // optional: the weights after dropout (need_weights)
+  float* att;          // [N*B, D] attention output, row stride ldatt
+  long ldatt;
+  void* att_bf16;      // optional bf16 copy (same row stride)
   const float* dscores;  // GRAD in : [B,H,N(j),N(i)]
   void* G;             // GRAD out: bf16 [tiles*128, 2D] (permuted feature order)
 };
 int launch_gemm_tn(int mode, const GemmTnArgs& a, cudaStream_t stream);
+// the fused relation-attention forward needs a tile that holds every key of its queries and one head per epilogue warpgroup
+bool rel_attn_fusable(const RelTiling& rt);
 int debug_read_trace(unsigned long long* host_out, int n);   // GTOS_DBG=2 timestamps, 16 slots per CTA
 
 // One packed-sequence GRU step (generator/encoder.py:105-106, nn.GRU cell) as a GEMM with a fused gate epilogue.

@@ -573,11 +573,29 @@ class RelAttnFn(torch.autograd.Function):
         Wib, Wit = weight_prep(W_in)
         Wperm, WpermT = weight_prep(W_rel, rel_heads=H)
         Wob, Wot = weight_prep(W_out)
-        # q,k feed only the fused relation kernels (staged there by TMA as bf16); v feeds the attention core
-        _, qkb = gemm_tn(xb2, Wib, 2 * D, bias=b_in[:2 * D], f32=False, bf16=True)  # [NB, 2D] bf16
-        vproj = torch.empty(NB, D, dtype=torch.float32, device=dev)
-        with fork() as f_v:                         # v is first read by the attention core, after the score kernel
-            gemm_tn(xb2, Wib, D, bias=b_in[2 * D:], K=D, b_off=2 * D * Wib.stride(0), out=vproj)   # [NB, D] fp32
+        # One kernel per layer on the dense relation tensor (the north star): projection GEMM + scores + mask + softmax +
+        # dropout + P.V (gtos_rel_attn_fwd) when a 128-pair tile holds all keys of its queries; otherwise the score
+        # kernel writes [B,H,N,N] scores and the attention core finishes (gtos_rel_score + gtos_attn_fwd).
+        fused_dense = (not fused_bank and _rel_fused_fwd and attn_mask is None
+                       and lib.gtos_rel_attn_fusable(N, B, D, H) == 1)
+        need_grad = any(ctx.needs_input_grad)
+        vproj = None
+        f_v = _NoFork()
+        if fused_dense:
+            # q | k | v in ONE bf16 GEMM; the fp32 copy of v that the backward's attention core reads is made beside it
+            _, qkb = gemm_tn(xb2, Wib, 3 * D, bias=b_in, f32=False, bf16=True)      # [NB, 3D] bf16
+            ldqk = 3 * D
+            if need_grad:
+                vproj = torch.empty(NB, D, dtype=torch.float32, device=dev)
+                with fork() as f_v:
+                    gemm_tn(xb2, Wib, D, bias=b_in[2 * D:], K=D, b_off=2 * D * Wib.stride(0), out=vproj)
+        else:
+            # q,k feed only the fused relation kernels (staged there by TMA as bf16); v feeds the attention core
+            _, qkb = gemm_tn(xb2, Wib, 2 * D, bias=b_in[:2 * D], f32=False, bf16=True)  # [NB, 2D] bf16
+            ldqk = 2 * D
+            vproj = torch.empty(NB, D, dtype=torch.float32, device=dev)
+            with fork() as f_v:                     # v is first read by the attention core, after the score kernel
+                gemm_tn(xb2, Wib, D, bias=b_in[2 * D:], K=D, b_off=2 * D * Wib.stride(0), out=vproj)   # [NB, D] fp32
         probs = torch.empty(B, H, N, N, dtype=torch.float32, device=dev)           # [b,h,i,j]
         wts = torch.empty(B, H, N, N, dtype=torch.float32, device=dev) if need_weights else None
         att = torch.empty(NB, D, dtype=torch.float32, device=dev)
@@ -591,13 +609,18 @@ class RelAttnFn(torch.autograd.Function):
             _, PB = gemm_tn(banked.bankb, Wperm, 2 * D, f32=False, bf16=True)       # [R, 2D] bf16
             f_v.join()
             _lib.check(lib.gtos_rel_attn_banked_fwd(_p(PB), PB.stride(0), _p(banked.idx), qkb.data_ptr(),
-                                                    qkb.data_ptr() + 2 * D, 2 * D, _p(vproj), D, _p(key_pad), _p(attn_mask),
+                                                    qkb.data_ptr() + 2 * D, ldqk, _p(vproj), D, _p(key_pad), _p(attn_mask),
                                                     p_w, _p(seed), off, _p(probs), _p(wts), _p(att), D, _p(attb), N, B, D, H,
                                                     banked.bankb.shape[0], _st()), "rel_attn_banked_fwd")
             relb = PB                               # saved in relb's slot for the backward
+        elif fused_dense:
+            _lib.check(lib.gtos_rel_attn_fwd(_p(relb), _p(Wperm), qkb.data_ptr(), qkb.data_ptr() + 2 * D, ldqk,
+                                             qkb.data_ptr() + 4 * D, ldqk, _p(key_pad), p_w, _p(seed), off, _p(probs), _p(wts),
+                                             _p(att), D, _p(attb), N, B, D, H, _st()), "rel_attn_fwd")
+            f_v.join()
         else:
             scores = torch.empty(B, H, N, N, dtype=torch.float32, device=dev)      # [b,h,j,i]
-            _lib.check(lib.gtos_rel_score(_p(relb), _p(Wperm), qkb.data_ptr(), qkb.data_ptr() + 2 * D, 2 * D, _p(scores),
+            _lib.check(lib.gtos_rel_score(_p(relb), _p(Wperm), qkb.data_ptr(), qkb.data_ptr() + 2 * D, ldqk, _p(scores),
                                           N, B, D, H, _st()), "rel_score")
             f_v.join()
             d = _attn_desc(N, N, B, H, hd)
@@ -615,7 +638,7 @@ class RelAttnFn(torch.autograd.Function):
             attb = cast_bf16(att)
         out, _ = gemm_tn(attb, Wob, D, bias=b_out)
         ctx.save_for_backward(xb2, relb, qkb, vproj, probs, attb, Wperm, WpermT, Wit, Wot, key_pad, attn_mask)
-        ctx.meta = (N, B, D, H, p, seed, off, p_w, off2)
+        ctx.meta = (N, B, D, H, p, seed, off, p_w, off2, ldqk)
         ctx.fused_bank = banked if fused_bank else None
         ctx.rel_acc = rel_acc if (rel_token is not None and rel_token.requires_grad) else None
         ctx.set_materialize_grads(False)            # unused attention weights: no zero-filled [B,H,N,N] gradient
@@ -627,7 +650,7 @@ class RelAttnFn(torch.autograd.Function):
     @once_differentiable
     def backward(ctx, dout, dwts):
         xb2, relb, qkb, vproj, probs, attb, Wperm, WpermT, Wit, Wot, key_pad, attn_mask = ctx.saved_tensors
-        N, B, D, H, p, seed, off, p_w, off2 = ctx.meta
+        N, B, D, H, p, seed, off, p_w, off2, ldqk = ctx.meta
         lib = _lib.load()
         hd = D // H
         if dout is None:
@@ -671,10 +694,10 @@ class RelAttnFn(torch.autograd.Function):
         if ctx.fused_bank is not None:
             bk = ctx.fused_bank                     # relb's slot holds the projected bank PB [R, 2D]
             _lib.check(lib.gtos_rel_grad_banked(_p(relb), relb.stride(0), _p(bk.idx), qkb.data_ptr(), qkb.data_ptr() + 2 * D,
-                                                2 * D, _p(ds_jt), _p(G), N, B, D, H, bk.bankb.shape[0], _st()),
+                                                ldqk, _p(ds_jt), _p(G), N, B, D, H, bk.bankb.shape[0], _st()),
                        "rel_grad_banked")
         else:
-            _lib.check(lib.gtos_rel_grad(_p(relb), _p(Wperm), qkb.data_ptr(), qkb.data_ptr() + 2 * D, 2 * D, _p(ds_jt),
+            _lib.check(lib.gtos_rel_grad(_p(relb), _p(Wperm), qkb.data_ptr(), qkb.data_ptr() + 2 * D, ldqk, _p(ds_jt),
                                          _p(G), N, B, D, H, _st()), "rel_grad")
         d_rel = None
         if ctx.rel_acc is not None and ctx.rel_acc.banked is not None:
@@ -821,6 +844,9 @@ def mha_composed(query, key, value, key_padding_mask, attn_mask, W_in, b_in, W_o
 # SURVEY 8 f-0 forward half: gtos_rel_attn_banked_fwd / gtos_rel_grad_banked instead of the P-row tcgen05 kernels when the
 # relation arrives factorised.  GTOS_BANKED_FWD=0 keeps the dense bf16 gather + gtos_rel_score / gtos_rel_grad.
 _banked_fwd = os.environ.get("GTOS_BANKED_FWD", "1") == "1"
+# dense relation tensor: projection GEMM + scores + softmax + dropout + P.V as one kernel (gtos_rel_attn_fwd) where the
+# tiling allows it; GTOS_REL_FUSED_FWD=0 keeps gtos_rel_score + gtos_attn_fwd
+_rel_fused_fwd = os.environ.get("GTOS_REL_FUSED_FWD", "1") == "1"
 
 
 def banked_fwd_supported(banked, N, B, D, H):
@@ -829,7 +855,7 @@ def banked_fwd_supported(banked, N, B, D, H):
     if D not in (128, 256, 512) or 32 % H != 0 or D % H != 0:
         return False
     npad = (N + 3) // 4 * 4
-    return 2 * 32 * 4 * D + 4 * 4 * H * npad + 64 <= 220 * 1024 and tuple(banked.idx.shape) == (N, N, B)
+    return 4 * (4 * H * npad + 8 * 4 * D) <= 200 * 1024 and tuple(banked.idx.shape) == (N, N, B)
 
 
 class RelGradAcc:

@@ -83,6 +83,18 @@ int gtos_rel_tiling(int32_t N, int32_t B, int32_t D, int32_t H, int32_t* out5);
 int gtos_rel_score(const void* relb, const void* Wperm, const void* q, const void* k, int64_t ldqk, float* scores,
                    int32_t N, int32_t B, int32_t D, int32_t H, void* stream);
 /* backward of the above w.r.t. the per-pair projections: G[tile-major pair, 2D] (bf16) = hd^-1/2 dscores * [k+rb | q+ra] */
+/* graph_transformer.py:122-159 as ONE kernel on the dense relation tensor (the north star's fused relation attention):
+ * gtos_rel_score's projection GEMM + score epilogue, then - in the same epilogue, on the tile's complete softmax rows - the
+ * key-padding mask, softmax over keys, dropout (same counter-based draw as gtos_attn_fwd) and o_i = sum_j w_ij v_j.  Scores
+ * never reach HBM.  v: bf16 [N*B, .] projected values (row stride ldv); probs [B,H,N,N] pre-dropout (saved for
+ * gtos_attn_bwd); att fp32 [N*B, D] (+ optional bf16 copy, same stride).  Needs every key of a query inside one 128-pair tile
+ * and head_dim 64 (gtos_rel_attn_fusable: configs 2 and 3; not the 257-node stress config, not an attention mask) -
+ * otherwise GTOS_ERR_UNSUPPORTED and the caller runs gtos_rel_score + gtos_attn_fwd. */
+int gtos_rel_attn_fusable(int32_t N, int32_t B, int32_t D, int32_t H);
+int gtos_rel_attn_fwd(const void* relb, const void* Wperm, const void* q, const void* k, int64_t ldqk, const void* v,
+                      int64_t ldv, const uint8_t* key_pad, float p_drop, const void* seed_ptr, uint64_t seed_off,
+                      float* probs, float* probs_dropped, float* att, int64_t ldatt, void* att_bf16, int32_t N, int32_t B,
+                      int32_t D, int32_t H, void* stream);
 int gtos_rel_grad(const void* relb, const void* Wperm, const void* q, const void* k, int64_t ldqk,
                   const float* dscores, void* G, int32_t N, int32_t B, int32_t D, int32_t H, void* stream);
 /* d_relation[j,i,b,:] (+)= G * Wperm  (WpermT = transposed prep output [D,2D]) */

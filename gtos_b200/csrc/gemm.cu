@@ -748,13 +748,31 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int qi_ = ri0 + rii, kj_ = rj0 + rjj;
             const bool live = valid && !(p.key_pad && p.key_pad[(long)kj_ * Bb + rb_]);
             ssm[r] = live ? s_val : -INFINITY;
+            // the accumulator is consumed: hand the TMEM stage back so the next unit's MMAs run under the softmax / P.V tail
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (CG == 2 && !leader) mbar_arrive_remote(&bars->tempty[as], 0); else mbar_arrive(&bars->tempty[as]);
+            }
             named_bar_sync(1 + 2 * wg, 128);
-            float mx = -INFINITY;
-            for (int jj = 0; jj < bj; ++jj) mx = fmaxf(mx, ssm[jj * bi + rii]);
-            float sum = 0.f;
-            for (int jj = 0; jj < bj; ++jj) {
-              const float sv = ssm[jj * bi + rii];
-              sum += (sv == -INFINITY) ? 0.f : __expf(sv - mx);
+            // row statistics: every warp computes them for all bi (<= 4) queries, 8 lanes per query striding the keys,
+            // and a thread picks the pair of its own query with one shuffle (no second barrier)
+            float mx = -INFINITY, sum = 0.f;
+            {
+              const int sq = lane >> 3, su = lane & 7;
+              const int sqc = sq < bi ? sq : bi - 1;
+              for (int jj = su; jj < bj; jj += 8) mx = fmaxf(mx, ssm[jj * bi + sqc]);
+#pragma unroll
+              for (int o = 1; o < 8; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+              for (int jj = su; jj < bj; jj += 8) {
+                const float sv = ssm[jj * bi + sqc];
+                sum += (sv == -INFINITY) ? 0.f : __expf(sv - mx);
+              }
+#pragma unroll
+              for (int o = 1; o < 8; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+              const int src = (rii < bi ? rii : 0) * 8;
+              mx = __shfl_sync(0xffffffffu, mx, src);
+              sum = __shfl_sync(0xffffffffu, sum, src);
             }
             float pr = (live && sum > 0.f) ? __expf(s_val - mx) / sum : 0.f;
             if (valid) {
@@ -774,6 +792,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const uint8_t* vbx = qb + (BN / 128) * (p.bi8 + p.bj8) * 128 + wg * p.bj8 * 128;   // 64-dim chunk of head wg
               const int e = 2 * d2;
               float o0 = 0.f, o1 = 0.f;
+#pragma unroll 8
               for (int jj = 0; jj < bj; ++jj) {
                 const float w = ssm[128 + jj * bi + ii2];
                 const __nv_bfloat162 v2 = *reinterpret_cast<const __nv_bfloat162*>(vbx + jj * 128 + (((e >> 3) ^ (jj & 7)) << 4) + (e & 7) * 2);
@@ -792,7 +811,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (CG == 2 && !leader) mbar_arrive_remote(&bars->tempty[as], 0); else mbar_arrive(&bars->tempty[as]);
+        if (!(MODE == MODE_SCORE && p.fuse)) {      // fused attention: released before the softmax / P.V tail
+          if (CG == 2 && !leader) mbar_arrive_remote(&bars->tempty[as], 0); else mbar_arrive(&bars->tempty[as]);
+        }
         if (REL) mbar_arrive(&bars->qempty[qs]);
       }
       if (++as == 2) { as = 0; aph ^= 1; }

@@ -25,7 +25,7 @@ static inline cudaStream_t S_(void* s) { return reinterpret_cast<cudaStream_t>(s
 extern "C" {
 
 const char* gtos_last_error(void) { return g_err; }
-int gtos_abi_version(void) { return 3; }
+int gtos_abi_version(void) { return 4; }
 int gtos_set_sm_reserve(int32_t n) { return set_sm_reserve(n); }
 uint64_t gtos_launch_count(void) { return __atomic_load_n(&g_kernel_launches, __ATOMIC_RELAXED); }
 

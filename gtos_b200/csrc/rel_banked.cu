@@ -608,7 +608,7 @@ static int launch_banked_fwd(const RelBankedDev& d, cudaStream_t st) {
   constexpr int QI = BANKED_QI;
   const size_t smem = sizeof(float) * ((size_t)QI * d.H * d.Npad + (size_t)8 * QI * d.D);
   GTOS_REQUIRE(smem <= 200 * 1024, "rel_attn_banked_fwd: N=%d needs %zu bytes of shared memory", d.N, smem);
-  static const bool ca = !(getenv("GTOS_BANKED_CPASYNC") && getenv("GTOS_BANKED_CPASYNC")[0] == '0');
+  static const bool ca = getenv("GTOS_BANKED_CPASYNC") && getenv("GTOS_BANKED_CPASYNC")[0] == '1';   // measured slower (133 / 163 us vs 84 / 85 us): off
   if (ca) {
     const size_t sm2 = (size_t)2 * 32 * 4 * d.D + sizeof(float) * (size_t)QI * d.H * d.Npad + sizeof(int) * (size_t)d.N * QI;
     if (sm2 <= 220 * 1024) {
@@ -646,7 +646,7 @@ template <int DL>
 static int launch_banked_grad(const RelBankedDev& d, cudaStream_t st) {
   constexpr int QI = BANKED_QI;
   const size_t smem = sizeof(int) * d.N * QI;
-  static const bool ca = !(getenv("GTOS_BANKED_CPASYNC") && getenv("GTOS_BANKED_CPASYNC")[0] == '0');
+  static const bool ca = getenv("GTOS_BANKED_CPASYNC") && getenv("GTOS_BANKED_CPASYNC")[0] == '1';   // measured slower (133 / 163 us vs 84 / 85 us): off
   if (ca) {
     const size_t sm2 = (size_t)2 * 32 * 4 * d.D + sizeof(int) * (size_t)d.N * QI;
     if (sm2 <= 220 * 1024) {

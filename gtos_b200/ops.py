@@ -537,7 +537,7 @@ class FFNFn(torch.autograd.Function):
         dx, _ = gemm_tn(dhb, W1t, D)
         f2.join_param(dyb, hb)
         f1.join_param(dhb, xb2)
-        f_db.join_param(dy2)
+        f_db.join()                                 # reads the incoming gradient itself (autograd may accumulate into that tensor later)
         return dx.view(shape), None, dW1, db1f[:Fd], dW2, db2, None
 
 
@@ -737,7 +737,7 @@ class RelAttnFn(torch.autograd.Function):
             f_out.join_param(doutb, attb)
             f_rel.join()                        # the segment sums feed BankTokenFn's d-bank GEMM on the caller's stream
             f_in.join_param(dqkvb, xb2)
-            f_db.join_param(dout2)
+            f_db.join()
             f_dbin.join_param(dqkv)
             return (dx.view(N, B, D), None, None, None, None, None, dW_in, db_in, dW_rel, dW_out, db_out, None, None,
                     None, None, None, None, None)
@@ -766,7 +766,7 @@ class RelAttnFn(torch.autograd.Function):
         dx, _ = gemm_tn(dqkvb, Wit, D)
         f_out.join_param(doutb, attb)
         f_in.join_param(dqkvb, xb2)
-        f_db.join_param(dout2)
+        f_db.join()
         f_dbin.join_param(dqkv)
         return (dx.view(N, B, D), None, d_rel, None, None, None, dW_in, db_in, dW_rel, dW_out, db_out, None, None,
                 None, None, None, None, None)
@@ -1116,7 +1116,7 @@ class MHAFn(torch.autograd.Function):
             dk_in = dk_in.view(S, B, D)
         f_out.join_param(doutb, attb)
         f_in.join_param(qb2, kb2, *(([dprojb] if self_attn else [dpqb, dpkvb])))
-        f_db.join_param(dout2)
+        f_db.join()
         f_dbin.join_param(dproj if self_attn else dpq)
         return (dq_in.view(T, B, D), None, dk_in, None, None, None, None, dW_in, db_in, dW_out, db_out, None, None,
                 None, None)
@@ -1386,7 +1386,7 @@ class LinearFn(torch.autograd.Function):
         db = db if has_b else None
         dx, _ = gemm_tn(dyb, Wt, K)
         f.join_param(dyb, xb)
-        f_db.join_param(dy2)
+        f_db.join()
         return dx.view(shape), dW, db
 
 

@@ -868,6 +868,23 @@ int choose_rel_tiling(RelTiling* t, int N, int B, int D, int H) {
       }
     }
   }
+  // A tile that holds EVERY key of its queries (bj = N, up to four queries) lets the score kernel finish the attention
+  // in its epilogue (gtos_rel_attn_fwd: softmax rows are complete inside the tile).  Take it whenever it costs no extra
+  // tiles - it needs a larger q / k / v staging area (the 48-row budget above does not apply), paid for with fewer
+  // stages of the main A/B ring.  N = 41 -> 3 x 41 (14 tiles per graph, same as 6 x 21), N = 61 -> 2 x 61.
+  if (N <= 128) {
+    int bif = 128 / N;
+    if (bif > 4) bif = 4;
+    if (bif > N) bif = N;
+    if (bif >= 1) {
+      long tiles = (long)((N + bif - 1) / bif);
+      if (tiles <= best_tiles && (((bif + 7) & ~7) + 2 * ((N + 7) & ~7)) * 256 * 2 <= 96 * 1024) {
+        best_tiles = tiles;
+        best_bi = bif;
+        best_bj = N;
+      }
+    }
+  }
   t->N = N; t->B = B; t->D = D; t->H = H; t->hd = hd;
   t->bi = best_bi; t->bj = best_bj;
   t->ni_blk = (N + best_bi - 1) / best_bi;

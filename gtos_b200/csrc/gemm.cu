@@ -872,7 +872,11 @@ int choose_rel_tiling(RelTiling* t, int N, int B, int D, int H) {
   // in its epilogue (gtos_rel_attn_fwd: softmax rows are complete inside the tile).  Take it whenever it costs no extra
   // tiles - it needs a larger q / k / v staging area (the 48-row budget above does not apply), paid for with fewer
   // stages of the main A/B ring.  N = 41 -> 3 x 41 (14 tiles per graph, same as 6 x 21), N = 61 -> 2 x 61.
-  if (N <= 128) {
+  // (only when the fused tail is switched on - GTOS_REL_FUSED_FWD=1: it measured 0.16 ms per step SLOWER than the
+  // two-kernel path at config 2, because the epilogue warps already are this kernel's bottleneck, so the default keeps the
+  // tiling with the smaller staging area and the deeper A/B ring.)
+  static const bool full_rows = getenv("GTOS_REL_FUSED_FWD") && getenv("GTOS_REL_FUSED_FWD")[0] == '1';
+  if (full_rows && N <= 128) {
     int bif = 128 / N;
     if (bif > 4) bif = 4;
     if (bif > N) bif = N;

@@ -44,7 +44,8 @@ def test_rel_tiling_host_logic(lib):
         bi8, bj8 = (t["bi"] + 7) // 8 * 8, (t["bj"] + 7) // 8 * 8
         full_rows = t["bj"] == N and t["bi"] <= 4             # every key of a query in one tile: the fused attention tail
         assert bi8 + bj8 <= 48 or (full_rows and (bi8 + 2 * bj8) * 512 <= 96 * 1024)
-        assert full_rows == (N in (41, 61, 1)), (N, t)         # configs 2 and 3 fuse, the 257-node stress config cannot
+        fused_on = os.environ.get("GTOS_REL_FUSED_FWD", "0") == "1"
+        assert full_rows == (fused_on and N in (41, 61, 1)) or N == 1, (N, t)   # configs 2 and 3 can fuse, the 257-node config cannot
         assert t["ni_blk"] * t["bi"] >= N and t["nj_blk"] * t["bj"] >= N
         assert t["tiles"] == B * t["ni_blk"] * t["nj_blk"]
         util = N * N / (t["ni_blk"] * t["nj_blk"] * 128)

@@ -5,6 +5,8 @@ oracle is too slow to be the checker.  Parity is shown through size-independent 
   * attention weights are a distribution over the un-padded keys;
   * the synthetic-batch relation bank round-trips through bank_gather / index_select exactly;
 and one sampled graph of the full batch is checked against the oracle run on that graph alone."""
+import os
+
 import pytest
 import torch
 
@@ -78,7 +80,8 @@ def test_padding_is_inert_and_weights_are_distributions(setup):
         outp = m(xp, relp, self_padding_mask=maskp)
         attn = m.get_attn_weights(x, rel, self_padding_mask=mask)          # [L, tgt, src, B, H]
     valid = ~mask                                                           # [N,B]
-    assert rel_err(outp[:N][valid], out[valid]) < 1e-5
+    # with GTOS_REL_FUSED_FWD=1 the 41-node run takes the fused kernel and the 48-node run cannot (P.V with fp32 vs bf16 P)
+    assert rel_err(outp[:N][valid], out[valid]) < (2e-3 if os.environ.get("GTOS_REL_FUSED_FWD") == "1" else 1e-5)
     assert torch.allclose(attn.sum(2), torch.ones_like(attn.sum(2)), atol=1e-5)
     assert attn.permute(0, 1, 4, 2, 3)[:, :, :, mask].abs().max().item() == 0.0
 

@@ -10,6 +10,8 @@ tolerance applies: 1e-2.
     because bf16 rounding flips ReLU units whose pre-activation is within 2^-8 of zero (measured with the
     emulated oracle alone); the distance to the fp32 oracle is therefore only bounded loosely (L2 < 0.15).
 """
+import os
+
 import pytest
 import torch
 
@@ -101,6 +103,8 @@ def test_graph_transformer_vs_oracle(dev, N, B, D, H, F, L, wf):
     assert rel_err(out, ref16) < TOL / 2
     # inflated weights make the net ill-conditioned: a 1e-3 rounding difference is amplified ~10x
     gtol = 1.5 * TOL if wf == 1.0 else 4 * TOL      # split-K / column-sum atomics: the summation order varies run to run
+    if os.environ.get("GTOS_REL_FUSED_FWD") == "1":      # fused tail: P stays fp32 for P.V, the emulation rounds it to bf16
+        gtol *= 1.7
     compare_grads(m, P, (out * wo.to(dev)).sum(), (ref16 * wo).sum(), [xg, rg], [xc, rc], tol=gtol, tol_max=0.2)
     compare_grads(m, P, (out * wo.to(dev)).sum(), (ref * wo).sum(), [xg, rg], [xc, rc], tol=0.15, tol_max=0.5)
     with torch.no_grad():
@@ -141,7 +145,8 @@ def test_graph_transformer_banked_relation_vs_oracle(dev, N, B, D, H, F, L, R, f
     out = m(xg, ops.BankedRelation(bg, idx.to(dev)), self_padding_mask=mask.to(dev))
     assert rel_err(out, ref) < TOL
     # fused: ra / rb additionally pass through bf16 (the projected bank), which the oracle's emulation mode does not model
-    compare_grads(m, P, (out * wo.to(dev)).sum(), (ref16 * wo).sum(), [xg, bg], [xc, bc], tol=(6 if fused else 4) * TOL,
+    compare_grads(m, P, (out * wo.to(dev)).sum(), (ref16 * wo).sum(), [xg, bg], [xc, bc],
+                  tol=(6 if (fused or os.environ.get("GTOS_REL_FUSED_FWD") == "1") else 4) * TOL,
                   tol_max=0.25 if fused else 0.2)
     compare_grads(m, P, (out * wo.to(dev)).sum(), (ref * wo).sum(), [xg, bg], [xc, bc], tol=0.15, tol_max=0.5)
     # dense path of this repo on the same operands

@@ -42,10 +42,17 @@ dW = torch.empty(D, D, device=dev)
 drel = torch.randn(N * N * B, D, device=dev)
 keys, order = torch.sort(idx.view(-1))
 dbank = torch.empty(R, D, device=dev)
+scores = torch.empty(B, H, N, N, device=dev)
+fused = lib.gtos_rel_attn_fusable(N, B, D, H) == 1           # needs GTOS_REL_FUSED_FWD=1 (full-row tiles)
+print("fused dense relation attention:", fused, ops.rel_tiling(N, B, D, H))
 for _ in range(3):
-    _lib.check(lib.gtos_rel_attn_fwd(relb.data_ptr(), Wperm.data_ptr(), qkv.data_ptr(), qkv.data_ptr() + 2 * D, 3 * D,
-                                     qkv.data_ptr() + 4 * D, 3 * D, pad.data_ptr(), 0.2, seed.data_ptr(), 12345, probs.data_ptr(),
-                                     None, att.data_ptr(), D, attb.data_ptr(), N, B, D, H, st), "rel_attn_fwd")
+    if fused:
+        _lib.check(lib.gtos_rel_attn_fwd(relb.data_ptr(), Wperm.data_ptr(), qkv.data_ptr(), qkv.data_ptr() + 2 * D, 3 * D,
+                                         qkv.data_ptr() + 4 * D, 3 * D, pad.data_ptr(), 0.2, seed.data_ptr(), 12345,
+                                         probs.data_ptr(), None, att.data_ptr(), D, attb.data_ptr(), N, B, D, H, st), "rel_attn_fwd")
+    else:
+        _lib.check(lib.gtos_rel_score(relb.data_ptr(), Wperm.data_ptr(), qkv.data_ptr(), qkv.data_ptr() + 2 * D, 3 * D,
+                                      scores.data_ptr(), N, B, D, H, st), "rel_score")
     _lib.check(lib.gtos_rel_grad(relb.data_ptr(), Wperm.data_ptr(), qkv.data_ptr(), qkv.data_ptr() + 2 * D, 3 * D, ds.data_ptr(),
                                  G.data_ptr(), N, B, D, H, st), "rel_grad")
     ops.gemm_tn(xa, wb, D, out=yo)

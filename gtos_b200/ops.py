@@ -1172,7 +1172,9 @@ class GRUBankFn(torch.autograd.Function):
             if all(c == R for c in counts[:-1]):
                 counts = None                                                      # nothing to skip
         if counts is not None:
-            order = torch.sort(lengths, descending=True, stable=True).indices      # longest first
+            # longest first; 8-bit keys = ONE radix pass (path lengths are <= 8 labels, data.py:153; int64 keys take 8)
+            key = lengths.clamp(max=255).to(torch.uint8) if Lmax <= 255 else lengths
+            order = torch.sort(key, descending=True, stable=True).indices
             inv = torch.empty_like(order)
             inv[order] = torch.arange(R, device=dev)
             tokens = tokens.index_select(1, order).contiguous()
@@ -1417,7 +1419,8 @@ class BankGatherFn(torch.autograd.Function):
         if _bank_sorted_bwd and ctx.needs_input_grad[0] and P > 0:
             # the backward sums d_rel rows per bank row: sort the pairs by bank row now, beside the encoder's forward
             with fork(True, which=3) as f_sort:
-                keys, order = torch.sort(idx.view(-1), stable=False)
+                k32, order = torch.sort(idx.view(-1).to(torch.int32), stable=False)     # 4 radix passes instead of 8
+                keys = k32.to(torch.int64)
             ctx.sorted = f_sort                     # joined by the backward (the sort overlaps the encoder's forward)
             ctx.save_for_backward(idx, keys, order)
         else:

@@ -13,5 +13,8 @@ mkdir -p $o
 # launch list of ONE eager step (cold-cache, serialised: compare SHARES)
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $o/launches_step.csv python bench.py --profile-step > $o/ncu_launches.log 2>&1
 # full captures of the kernels the profiles discuss
-timeout 500 ncu --set full --clock-control none --import-source on -k regex:"gemm_tn_kernel|gemm_nn_kernel|banked|bank_segsum" -s 7 -c 7 -o $o/kernels python tools/kernel_probe.py > $o/ncu_kernels.log 2>&1
+timeout 500 ncu --set full --clock-control none --import-source on -k regex:"gemm_tn_kernel|gemm_nn_kernel|banked|bank_segsum" -s 8 -c 7 -o $o/kernels python tools/kernel_probe.py > $o/ncu_kernels.log 2>&1
 grep -E "passed|failed" $o/gputests.log; tail -2 $o/smoke.log; head -c 400 $o/bench_n1.json; echo; head -c 300 $o/bench_ref.json; echo; tail -3 $o/ncu_kernels.log
+# the score kernel with the attention tail fused in (opt-in), for the comparison in DESIGN.md 4b
+GTOS_REL_FUSED_FWD=1 timeout 300 ncu --set full --clock-control none --import-source on -k regex:gemm_tn_kernel -s 4 -c 1 -o $o/score_fused python tools/kernel_probe.py > $o/ncu_fused.log 2>&1
+tail -2 $o/ncu_fused.log

@@ -40,7 +40,10 @@ class FlatGradBucket:
     def pack(self):
         """gather the per-parameter gradients into the flat buffer (no-op when bound)"""
         if not self.bound:
-            torch.cat([p.grad.reshape(-1) for p in self.params], out=self.flat)
+            # a trainable parameter that took no part in this step has no gradient: it contributes zeros (the reference's
+            # average_gradients skips it, train.py:76-77)
+            torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in self.params],
+                      out=self.flat)
 
     def unpack(self):
         """scatter the (averaged) flat buffer back into the per-parameter gradients (no-op when bound)"""
@@ -59,6 +62,27 @@ class FlatGradBucket:
             if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + off * self.flat.element_size():
                 p.grad = self.flat[off:off + n].view_as(p)
             off += n
+
+    def adopt(self):
+        """bound buckets only: a backward pass that ran after `model.zero_grad()` (set_to_none=True is torch's default)
+        wrote FRESH .grad tensors instead of accumulating into the views.  Copy those into the flat buffer and re-attach
+        the views; a parameter without a gradient gets a zero slice.  Returns the number of parameters that had strayed."""
+        if not self.bound:
+            return 0
+        off, strayed = 0, 0
+        for p in self.params:
+            n = p.numel()
+            view = self.flat[off:off + n].view_as(p)
+            if p.grad is None:
+                view.zero_()
+                p.grad = view
+                strayed += 1
+            elif p.grad.data_ptr() != view.data_ptr():
+                view.copy_(p.grad)
+                p.grad = view
+                strayed += 1
+            off += n
+        return strayed
 
     def all_reduce_mean(self, group=None):
         """average_gradients (train.py:74-79) as one collective."""

@@ -68,6 +68,10 @@ class FlatAdam:
         self.lr_dev.copy_(self._lr_host, non_blocking=True)
 
     def zero_grad(self):
+        """use this instead of model.zero_grad(): it keeps every .grad a view of the flat buffer (a stray fresh .grad is
+        still picked up by step(), at the cost of one copy per parameter).  Unlike the reference (adam.py:41-43, which
+        skips parameters whose grad is None) a parameter that received no gradient still gets its weight decay and moment
+        decay: the flat kernel has no per-parameter skip."""
         self.bucket.zero()
 
     def step(self):
@@ -75,6 +79,7 @@ class FlatAdam:
         (Call bucket.all_reduce_mean() first when data parallel.)"""
         lib = _lib.load()
         self.bucket.pack()
+        self.bucket.adopt()          # gradients written outside the flat views (zero_grad(set_to_none=True)) are copied in
         g = self.bucket.flat
         nsq = None
         if self.max_norm is not None:

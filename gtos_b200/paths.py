@@ -152,11 +152,35 @@ def relabel_adjacency(deg, nbr, lab, order, pos):
     return deg2, torch.where(used, nbr2, zero).to(torch.int32), torch.where(used, lab2, zero).to(torch.int32)
 
 
-def shortest_label_paths(n_nodes, deg, nbr, lab, max_len, self_id, tl_id, seed_off=0, seed=None):
+def _check_graph(n_nodes, deg, nbr):
+    """GTOS_CHECK_GRAPH=1: range check of a padded adjacency that did not come from pack_adjacency / pack_edges (the
+    kernels index shared memory with these values and trust them).  Costs a device read-back."""
+    import os
+    if os.environ.get("GTOS_CHECK_GRAPH") != "1":
+        return
+    B, n_max, deg_max = nbr.shape
+    n = n_nodes.to(torch.int64).view(B, 1)
+    if int((n_nodes < 0).any() | (n_nodes > n_max).any()):
+        raise ValueError("n_nodes outside [0, n_max]")
+    inside = torch.arange(n_max, device=nbr.device).view(1, n_max) < n
+    if int(((deg < 0) | (deg > deg_max))[inside].any()):
+        raise ValueError("a node degree is outside [0, deg_max]")
+    used = torch.arange(deg_max, device=nbr.device).view(1, 1, deg_max) < deg.to(torch.int64).unsqueeze(-1)
+    bad = ((nbr < 0) | (nbr.to(torch.int64) >= n.view(B, 1, 1))) & used & inside.unsqueeze(-1)
+    if int(bad.any()):
+        raise ValueError("a neighbour index is outside its graph")
+
+
+def shortest_label_paths(n_nodes, deg, nbr, lab, max_len, self_id, tl_id, seed_off=None, seed=None):
     """-> (paths [B,n_max,n_max,max_len] int32, plen [B,n_max,n_max] int32); paths[b,i,j] = labels of the drawn shortest
     path i -> j (AMRGraph.py:107-112 + data.py:150-154).  `seed`: int64 device tensor (default: the library's dropout
-    seed, ops.rng_state), `seed_off`: per-call offset - the draw is reproducible from (seed + seed_off, b, i, j)."""
+    seed, ops.rng_state), `seed_off`: per-call offset - the draw is reproducible from (seed + seed_off, b, i, j); None
+    (default) takes a fresh offset per call, like the reference's fresh random.choice per batch (data.py:150)."""
     _need_cuda(n_nodes, deg, nbr, lab)
+    _check_graph(n_nodes, deg, nbr)
+    if seed_off is None:
+        from .ops import new_seed_off
+        seed_off = new_seed_off()
     for t in (n_nodes, deg, nbr, lab):
         if t.dtype != torch.int32 or not t.is_contiguous():
             raise ValueError("shortest_label_paths takes contiguous int32 tensors (pack_adjacency)")
@@ -301,7 +325,7 @@ def assemble_eval_relation_batch(all_paths, pcount, n_nodes, pad_id, cls_id, rcl
     return dict(relation=relation, relation_bank=bank[:Lmax].contiguous(), relation_length=length)
 
 
-def relation_batch(graphs, max_len, cls_id, rcls_id, self_id, tl_id, device, seed_off=0):
+def relation_batch(graphs, max_len, cls_id, rcls_id, self_id, tl_id, device, seed_off=None):
     """adjacency lists -> the three relation tensors of a training batch (data.py:134-176), paths drawn on the GPU."""
     n_nodes, deg, nbr, lab = pack_adjacency(graphs, device=device)
     paths, plen = shortest_label_paths(n_nodes, deg, nbr, lab, max_len, self_id, tl_id, seed_off=seed_off)

@@ -352,6 +352,27 @@ def test_flat_adam_matches_reference_optimizer(dev):
             off += p.numel()
 
 
+def test_flat_adam_picks_up_gradients_written_outside_the_flat_views(dev):
+    """after model.zero_grad() (set_to_none=True is torch's default) backward writes FRESH .grad tensors; the
+    step must use them, not the stale zeroed flat buffer."""
+    from gtos_b200.optim import FlatAdam
+    gen = torch.Generator().manual_seed(SEED + 5)
+    lin_a, lin_b = torch.nn.Linear(16, 8).to(dev), torch.nn.Linear(16, 8).to(dev)
+    lin_b.load_state_dict(lin_a.state_dict())
+    x = torch.randn(4, 16, generator=gen).to(dev)
+    opt_a = FlatAdam(list(lin_a.named_parameters()), lr=0.01, max_norm=None)
+    opt_b = FlatAdam(list(lin_b.named_parameters()), lr=0.01, max_norm=None)
+    opt_a.zero_grad()
+    lin_a(x).pow(2).sum().backward()                      # accumulates into the views
+    lin_b.zero_grad()                                     # torch default: grads become None
+    lin_b(x).pow(2).sum().backward()                      # fresh .grad tensors
+    assert lin_b.weight.grad.data_ptr() != opt_b.bucket.flat.data_ptr()
+    opt_a.step()
+    opt_b.step()
+    assert torch.equal(lin_a.weight, lin_b.weight) and torch.equal(lin_a.bias, lin_b.bias)
+    assert lin_b.weight.grad.data_ptr() == opt_b.bucket.flat.data_ptr()      # re-attached
+
+
 def test_flat_adam_large_buffer_property(dev):
     """38.6 M parameters (the reference model's size): one step equals the elementwise formula on a random sample"""
     from gtos_b200.optim import FlatAdam

@@ -56,8 +56,8 @@ def main():
         root = torch.zeros(B, dtype=torch.int32, device=dev)
         seed = torch.tensor([19940117], dtype=torch.int64, device=dev)
         us_bfs = timeit(lambda: P.bfs_order(n_nodes, deg, nbr, root))
-        us_paths = timeit(lambda: P.shortest_label_paths(n_nodes, deg, nbr, lab, max_len, SELF, TL, seed=seed))
-        paths, plen = P.shortest_label_paths(n_nodes, deg, nbr, lab, max_len, SELF, TL, seed=seed)
+        us_paths = timeit(lambda: P.shortest_label_paths(n_nodes, deg, nbr, lab, max_len, SELF, TL, seed=seed, seed_off=0))
+        paths, plen = P.shortest_label_paths(n_nodes, deg, nbr, lab, max_len, SELF, TL, seed=seed, seed_off=0)
         us_asm = timeit(lambda: P.assemble_relation_batch(paths, plen, n_nodes, CLS, RCLS, SELF), n=5)
         K = 8
         us_all = timeit(lambda: P.all_shortest_label_paths(n_nodes, deg, nbr, lab, max_len, K, SELF, TL), n=5)

@@ -47,7 +47,8 @@ METRIC = "encoder_node_pairs_per_sec"
 REL_MODE_NOTE = {
     "index_select": "dense fp32 bank.index_select(...) built by the caller's own line (generator.py:79): unchanged caller",
     "gather": "dense fp32 + bf16 copy from ops.bank_gather (1-line caller change)",
-    "banked": "bank-factorised (SURVEY 8 f-0, 2-line caller change): bf16 gather fwd, bank-row GEMMs bwd",
+    "banked": "bank-factorised (SURVEY 8 f-0, 2-line caller change): projected bank + one gather kernel per layer fwd "
+              "(scores, softmax, dropout, PV), gather gradient kernel + bank-row GEMMs bwd",
 }
 
 

@@ -132,3 +132,97 @@ def test_large_graph_257_nodes(setup):
     with torch.no_grad():
         ref = O.graph_transformer(P, "", g["x"][:, :1], relc, 1, H, self_padding_mask=g["node_mask"][:, :1])
     assert rel_err(out[:, :1], ref) < 1e-2
+
+
+def _boost_(model, factor, seed):
+    gen = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if p.dim() >= 2 and "layer_norm" not in n:
+                p.mul_(factor)
+            elif n.endswith("bias") and "layer_norm" not in n:
+                p.copy_(torch.randn(p.shape, generator=gen) * 0.05)
+
+
+@pytest.mark.parametrize("banked", [False, True])
+def test_full_batch_gradients_of_one_graph_vs_oracle(setup, banked):
+    """Gradients at the FULL config-2 batch (B = 64, all tiles / waves / split-K paths of the real size), x3 weights: a loss
+    that reads only graph b's outputs has, by batch independence, exactly the gradients of the oracle run on graph b
+    alone - for the node features, for the relation bank rows and for every parameter.  Dense contract and the factorised
+    relation (bf16 relation storage, gather kernels)."""
+    from conftest import l2_err
+    from gtos_b200 import ops
+    from gtos_b200.graph_transformer import GraphTransformer
+    s = setup
+    g, dev, N, B, D = s["g"], s["dev"], s["N"], s["B"], s["D"]
+    cpu = GraphTransformer(2, D, 1024, 8, 0.0)
+    _boost_(cpu, 3.0, SEED + 11)
+    m = GraphTransformer(2, D, 1024, 8, 0.0).to(dev)
+    m.load_state_dict(cpu.state_dict())
+    b = 5
+    gen = torch.Generator().manual_seed(SEED + 12)
+    wo = torch.randn(N, D, generator=gen)
+    idx = g["relation"]
+    xg = g["x"].to(dev).requires_grad_()
+    bank_g = s["bank"].to(dev).requires_grad_()
+    rel = ops.BankedRelation(bank_g, idx.to(dev)) if banked else ops.bank_gather(bank_g, idx.to(dev))
+    out = m(xg, rel, self_padding_mask=g["node_mask"].to(dev))
+    (out[:, b] * wo.to(dev)).sum().backward()
+    # the oracle on graph b alone, bf16 matmul mode (same rounding points as the kernels)
+    P = {k: v.clone().requires_grad_() for k, v in cpu.state_dict().items()}
+    xc = g["x"][:, b:b + 1].clone().requires_grad_()
+    bank_c = s["bank"].clone().requires_grad_()
+    relc = bank_c.index_select(0, idx[:, :, b].reshape(-1)).view(N, N, 1, D)
+    O.set_matmul_precision("bf16")
+    try:
+        ref = O.graph_transformer(P, "", xc, relc, 2, 8, self_padding_mask=g["node_mask"][:, b:b + 1])
+    finally:
+        O.set_matmul_precision("fp32")
+    (ref[:, 0] * wo).sum().backward()
+    assert rel_err(out[:, b:b + 1], ref) < 1e-2
+    tol = 8e-2 if banked else 5e-2
+    assert l2_err(xg.grad[:, b], xc.grad[:, 0]) < tol
+    assert float(xg.grad[:, [i for i in range(B) if i != b]].abs().max()) == 0.0      # other graphs receive nothing
+    assert l2_err(bank_g.grad, bank_c.grad) < tol
+    worst = {n: l2_err(p.grad, P[n].grad) for n, p in m.named_parameters()}
+    bad = {n: e for n, e in worst.items() if e > tol}
+    assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:6]
+
+
+def test_large_graph_257_nodes_factorised_relation_gradients(setup):
+    """BASELINE.json config 4's storage contract: the relation never exists as a dense fp32 tensor (bank + index, bf16
+    gather).  One 257-node graph of a 2-graph batch, one layer, forward AND gradients (node features, bank, parameters)
+    against the oracle run on that graph's dense fp32 relation tensor."""
+    from conftest import l2_err
+    from gtos_b200 import ops, synthetic
+    from gtos_b200.graph_transformer import GraphTransformer
+    dev = setup["dev"]
+    D, H, B = 512, 8, 2
+    g = synthetic.make_batch(B, 256, D, max_path_len=8, seed=SEED + 9)
+    N = g["N"]
+    gen = torch.Generator().manual_seed(SEED + 9)
+    bank = torch.randn(g["relation_bank"].shape[1], D, generator=gen) * 0.5
+    cpu = GraphTransformer(1, D, 1024, H, 0.0)
+    _boost_(cpu, 2.0, SEED + 13)
+    m = GraphTransformer(1, D, 1024, H, 0.0).to(dev)
+    m.load_state_dict(cpu.state_dict())
+    wo = torch.randn(N, D, generator=gen)
+    xg = g["x"].to(dev).requires_grad_()
+    bank_g = bank.to(dev).requires_grad_()
+    out = m(xg, ops.BankedRelation(bank_g, g["relation"].to(dev)), self_padding_mask=g["node_mask"].to(dev))
+    (out[:, 0] * wo.to(dev)).sum().backward()
+    P = {k: v.clone().requires_grad_() for k, v in cpu.state_dict().items()}
+    xc = g["x"][:, :1].clone().requires_grad_()
+    bank_c = bank.clone().requires_grad_()
+    relc = bank_c.index_select(0, g["relation"][:, :, 0].reshape(-1)).view(N, N, 1, D)
+    O.set_matmul_precision("bf16")
+    try:
+        ref = O.graph_transformer(P, "", xc, relc, 1, H, self_padding_mask=g["node_mask"][:, :1])
+    finally:
+        O.set_matmul_precision("fp32")
+    (ref[:, 0] * wo).sum().backward()
+    assert rel_err(out[:, :1], ref) < 1e-2
+    assert l2_err(xg.grad[:, 0], xc.grad[:, 0]) < 8e-2 and l2_err(bank_g.grad, bank_c.grad) < 8e-2
+    worst = {n: l2_err(p.grad, P[n].grad) for n, p in m.named_parameters()}
+    bad = {n: e for n, e in worst.items() if e > 8e-2}
+    assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:6]

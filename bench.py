@@ -744,6 +744,23 @@ def main_ours(args):
                                    "relation": REL_MODE_NOTE["banked"], "gpu_launches_per_step": int(r2.launches_per_step)}
         del r2
         torch.cuda.empty_cache()
+        # the UNCHANGED caller again, with the opt-in provenance switch: the dense tensor its index_select builds (on the
+        # drop-in's BankTensor) remembers (bank, idx) and the graph encoder takes the factorised kernels by itself
+        ops_mod = run.ops
+        ops_mod._rel_provenance = True
+        try:
+            r3 = StepRunner("cfg2", model, args.dropout, dev, rank, world, relation_mode="index_select",
+                            use_graph=not args.no_graph)
+            r3.prepare()
+            ms_p, _ = r3.timed(r3.step_device, steps, 3)
+            extra["unchanged_caller_with_provenance_step"] = {
+                "ms_per_step": ms_p, "node_pairs_per_sec": total_pairs / (ms_p * 1e-3),
+                "note": "GTOS_REL_PROVENANCE=1: same caller code as the headline (generator.py:79 index_select); the dense "
+                        "tensor is still built, but the encoder recognises it as bank[idx] and runs the f-0 kernels"}
+            del r3
+        finally:
+            ops_mod._rel_provenance = False
+        torch.cuda.empty_cache()
         strong = {}
         for name in ("cfg3", "cfg4"):
             try:

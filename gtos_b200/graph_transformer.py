@@ -32,6 +32,10 @@ class GraphTransformer(nn.Module):
             for layer in self.layers:
                 x, _ = layer(x, relation, kv, self_padding_mask, self_attn_mask)
             return x
+        if not isinstance(relation, ops.BankedRelation):
+            src = ops.factorised_source(relation)       # opt-in: a dense tensor that still knows it is bank[idx]
+            if src is not None:
+                relation = src
         if isinstance(relation, ops.BankedRelation) and relation.multi and torch.is_grad_enabled() and relation.requires_grad:
             relation = relation.dense()            # gradients through the evaluation multi-path mean: dense autograd path
         if isinstance(relation, ops.BankedRelation):

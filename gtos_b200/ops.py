@@ -1454,6 +1454,7 @@ def bank_gather(bank, idx):
     rel, relb = BankGatherFn.apply(bank, idx)
     rel = rel.as_subclass(GatheredRelation)
     rel._gtos_bf16 = (relb, rel._version)
+    rel._gtos_src = (bank, idx, rel._version)       # provenance: this tensor IS bank[idx] while its version stands
     return rel
 
 
@@ -1487,6 +1488,9 @@ class GatheredRelation(torch.Tensor):
                 if out is not src:
                     out = out.as_subclass(GatheredRelation)
                 out._gtos_bf16 = (tag[0].view(out.shape), tag[1])
+                prov = getattr(src, "_gtos_src", None)
+                if prov is not None and prov[2] == src._version:
+                    out._gtos_src = prov
         return out
 
 
@@ -1502,6 +1506,25 @@ def staged_relation_bf16(relation):
 
 
 _bank_tensor = os.environ.get("GTOS_BANK_TENSOR", "1") == "1"
+# GTOS_REL_PROVENANCE=1 (opt-in): a dense relation tensor that ops.bank_gather built - e.g. through the unchanged caller's
+# index_select on a BankTensor - remembers (bank, idx).  While nobody has written to it, GraphTransformer may treat it as
+# the factorised relation it is without any caller change: same function of (bank, idx), gradient delivered
+# to the bank directly.  Off by default: the dense kernels are the contract the headline is measured on.
+_rel_provenance = os.environ.get("GTOS_REL_PROVENANCE", "0") == "1"
+
+
+def factorised_source(relation):
+    """BankedRelation equivalent of a dense relation tensor with valid provenance, or None"""
+    if not _rel_provenance:
+        return None
+    prov = getattr(relation, "_gtos_src", None)
+    if prov is None or prov[2] != relation._version or relation.dim() != 4:
+        return None
+    bank, idx, _ = prov
+    N1, N2, B, D = relation.shape
+    if idx.numel() != N1 * N2 * B or N1 != N2 or bank.dim() != 2 or bank.shape[1] != D:
+        return None
+    return BankedRelation(bank, idx.view(N1, N2, B))
 
 
 class BankTensor(torch.Tensor):

@@ -83,6 +83,35 @@ def test_generator_forward_loss_and_gradients(pair, dev):
         p.grad = None
 
 
+def test_generator_forward_with_provenance_takes_the_factorised_kernels(pair, dev, monkeypatch):
+    """GTOS_REL_PROVENANCE (opt-in): the unchanged Generator.forward, whose index_select builds the dense relation tensor,
+    runs the f-0 kernels because that tensor remembers (bank, idx) - same loss, same gradients (incl. the RelationEncoder's,
+    which now receive d bank from the bank-row GEMMs instead of the gather's backward)."""
+    from gtos_b200 import ops
+    ref, ours, vocabs, _, _ = pair
+    ref.train()
+    ours.train()
+    data = GH.make_data(vocabs, B=6, n_max=12, T=9, seed=SEED + 3)
+    loss_ref = ref(data)
+    loss_ref.backward()
+    monkeypatch.setattr(ops, "_rel_provenance", True)
+    seen = []
+    orig = ops.factorised_source
+    monkeypatch.setattr(ops, "factorised_source", lambda r: seen.append(orig(r)) or seen[-1])
+    loss = ours(GH.to_device(data, dev))
+    loss.backward()
+    torch.cuda.synchronize()
+    assert seen and seen[0] is not None                              # the encoder did switch to the factorised path
+    assert abs(loss.item() - loss_ref.item()) / abs(loss_ref.item()) < 1e-2
+    gr = dict(ref.named_parameters())
+    worst = {n: l2_err(p.grad, gr[n].grad) for n, p in ours.named_parameters() if gr[n].grad is not None}
+    bad = {n: e for n, e in worst.items() if e > 8e-2}
+    assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:8]
+    assert worst["relation_encoder.out_proj.weight"] < 8e-2 and worst["relation_encoder.rnn.weight_hh_l0"] < 8e-2
+    for p in list(ref.parameters()) + list(ours.parameters()):
+        p.grad = None
+
+
 @pytest.mark.parametrize("beam", [1, 3])
 def test_generator_beam_search_tokens(pair, dev, beam):
     ref, ours, vocabs, _, _ = pair

@@ -382,6 +382,16 @@ def test_bank_tensor_index_select_is_the_callers_gather(dev, R, D, N, B, sorted_
     assert ops.staged_relation_bf16(rel2) is not None
     rel2.add_(1.0)
     assert ops.staged_relation_bf16(rel2) is None
+    # opt-in provenance: the dense tensor is recognised as bank[idx] while nobody has written to it
+    monkeypatch.setattr(ops, "_rel_provenance", True)
+    rel3 = bank.index_select(0, idx.view(-1)).view(*idx.size(), -1)
+    src = ops.factorised_source(rel3) if D % 128 == 0 else None
+    if D % 128 == 0:
+        assert src is not None and src.bank.data_ptr() == bank.data_ptr() and torch.equal(src.idx, idx)
+    rel3.mul_(2.0)
+    assert ops.factorised_source(rel3) is None
+    monkeypatch.setattr(ops, "_rel_provenance", False)
+    assert ops.factorised_source(bank.index_select(0, idx.view(-1)).view(*idx.size(), -1)) is None
     # anything else behaves like a plain tensor
     assert type(bank * 2) is torch.Tensor and torch.equal(bank[idx[..., 0]].as_subclass(torch.Tensor), plain.detach()[idx[..., 0]])
 

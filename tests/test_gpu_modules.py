@@ -105,7 +105,8 @@ def test_graph_transformer_vs_oracle(dev, N, B, D, H, F, L, wf):
     gtol = 1.5 * TOL if wf == 1.0 else 4 * TOL      # split-K / column-sum atomics: the summation order varies run to run
     if os.environ.get("GTOS_REL_FUSED_FWD") == "1":      # fused tail: P stays fp32 for P.V, the emulation rounds it to bf16
         gtol *= 1.7
-    compare_grads(m, P, (out * wo.to(dev)).sum(), (ref16 * wo).sum(), [xg, rg], [xc, rc], tol=gtol, tol_max=0.2)
+    tmax = 0.3 if os.environ.get("GTOS_REL_FUSED_FWD") == "1" else 0.2
+    compare_grads(m, P, (out * wo.to(dev)).sum(), (ref16 * wo).sum(), [xg, rg], [xc, rc], tol=gtol, tol_max=tmax)
     compare_grads(m, P, (out * wo.to(dev)).sum(), (ref * wo).sum(), [xg, rg], [xc, rc], tol=0.15, tol_max=0.5)
     with torch.no_grad():
         attn = m.get_attn_weights(xg, rg, self_padding_mask=mask.to(dev))

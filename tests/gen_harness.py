@@ -95,7 +95,8 @@ def make_data(vocabs, B=6, n_max=12, T=9, seed=19940117, chars=7, eval_paths=0):
     token_char_in = token_char_in.masked_fill(tok_pad.unsqueeze(-1), 0)
     n_ext = 4
     cp_seq = torch.randint(2, Vp + n_ext, (N - 1, B), generator=gen).masked_fill(node_pad[1:], 0)
-    token_out = torch.randint(2, Vp + n_ext, (T, B), generator=gen).masked_fill(tok_pad, 0)
+    token_out = torch.randint(2, Vp + n_ext, (T, B), generator=gen)
+    token_out = torch.minimum(token_out, cp_seq.max()).masked_fill(tok_pad, 0)        # targets inside the extended vocabulary
     local_idx2token = [{Vp + k: f"cp{b}_{k}" for k in range(n_ext)} for b in range(B)]
     local_token2idx = [{v: k for k, v in d.items()} for d in local_idx2token]
     rel, bank, length = g["relation"], g["relation_bank"], g["relation_length"]

@@ -180,7 +180,7 @@ def test_full_batch_gradients_of_one_graph_vs_oracle(setup, banked):
         O.set_matmul_precision("fp32")
     (ref[:, 0] * wo).sum().backward()
     assert rel_err(out[:, b:b + 1], ref) < 1e-2
-    tol = 8e-2 if banked else 5e-2
+    tol = 8e-2 if (banked or os.environ.get("GTOS_REL_FUSED_FWD") == "1") else 5e-2      # fused paths: P stays fp32 for P.V, the emulation rounds it
     assert l2_err(xg.grad[:, b], xc.grad[:, 0]) < tol
     assert float(xg.grad[:, [i for i in range(B) if i != b]].abs().max()) == 0.0      # other graphs receive nothing
     assert l2_err(bank_g.grad, bank_c.grad) < tol

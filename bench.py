@@ -70,6 +70,9 @@ def parse():
                     help="how relation = bank[idx] reaches the graph encoder (default: index_select = the unchanged caller; "
                          "cfg4 defaults to banked)")
     ap.add_argument("--dense-relation", action="store_true", help="(kept for old command lines) same as --relation-mode gather")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
+                    help="arithmetic mode of the GPU arm: bf16 operands (1e-2 tolerance, default) or fp32 mode (split-bf16 "
+                         "operands, three tensor-core passes per product, 1e-3 tolerance)")
     ap.add_argument("--profile-step", action="store_true",
                     help="run ONE eager step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     return ap.parse_args()
@@ -703,6 +706,9 @@ def main_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     _lib.check(lib.gtos_device_check(), "device_check")
+    if args.precision == "fp32":
+        from gtos_b200 import ops as _ops
+        _ops.set_precision("fp32")
     if dp_overlap:
         _lib.check(lib.gtos_set_sm_reserve(int(os.environ.get("GTOS_SM_RESERVE", "8"))), "set_sm_reserve")
     w = WORKLOADS[args.workload]
@@ -761,6 +767,30 @@ def main_ours(args):
         finally:
             ops_mod._rel_provenance = False
         torch.cuda.empty_cache()
+        # the same step in fp32 mode (north star: 1e-3 against the fp32 reference): every GEMM on split-bf16 operands
+        # (three tensor-core passes), fp32 values between all kernels (gtos_b200/ops32.py)
+        if args.precision != "fp32":
+            ops_mod.set_precision("fp32")
+            try:
+                r4 = StepRunner("cfg2", model, args.dropout, dev, rank, world, relation_mode="index_select",
+                                use_graph=not args.no_graph)
+                r4.prepare()
+                ms_f, _ = r4.timed(r4.step_device, max(3, steps // 4), 3)
+                extra["fp32_mode"] = {
+                    "ms_per_step": ms_f, "node_pairs_per_sec": total_pairs / (ms_f * 1e-3),
+                    "decoder_tokens_per_sec": total_tokens / (ms_f * 1e-3), "loss": float(r4.loss_buf.item()),
+                    "gpu_launches_per_step": int(r4.launches_per_step), "cuda_graph": r4.graph is not None,
+                    "arithmetic": "split-bf16 operands (x = hi + lo), A_hi B_hi + A_lo B_hi + A_hi B_lo on tcgen05 / warp MMA "
+                                  "with fp32 accumulation; fp32 values between all kernels; parity tests at 1e-3 against the "
+                                  "fp32 oracle, outputs and gradients (tests/test_gpu_fp32_mode.py)",
+                    "note": "same workload, batch and caller contract as the headline; switch: GTOS_PRECISION=fp32 / "
+                            "ops.set_precision('fp32') / --precision fp32"}
+                del r4
+            except Exception as e:
+                extra["fp32_mode"] = {"error": repr(e)[:300]}
+            finally:
+                ops_mod.set_precision("bf16")
+            torch.cuda.empty_cache()
         strong = {}
         for name in ("cfg3", "cfg4"):
             try:
@@ -789,15 +819,19 @@ def main_ours(args):
     line = {
         "metric": METRIC, "value": total_pairs / (ms * 1e-3), "unit": "node-pairs/s", "n_gpus": world,
         "steps": steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "strong" if strong_mode else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "scaling": "strong" if strong_mode else "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.precision != "fp32" else "f32 (3 x bf16 split operands)", "data": "synthetic",
         "decoder_tokens_per_sec": total_tokens / (ms * 1e-3),
         "valid_node_pairs_per_sec": total_valid / (ms * 1e-3),      # sum_b (n_b + 1)^2: pairs of un-padded nodes only
         "config": {"workload": workload_text(args.workload, w, args.dropout), "graphs_per_gpu": run.per_gpu,
                    "global_batch": run.per_gpu * world, "micro_batch": run.micro,
                    "nodes_incl_cls": meta["N"], "tgt_len": meta["T"], "distinct_relation_paths": meta["R"],
                    "parallelism": f"dp{world}", "relation": REL_MODE_NOTE[run.relation_mode],
-                   "arithmetic": "bf16 tensor-core operands, fp32 accumulation, fp32 activations / parameters / gradients "
-                                 "at module boundaries (tolerance 1e-2, the north star's bf16 mode)",
+                   "arithmetic": ("bf16 tensor-core operands, fp32 accumulation, fp32 activations / parameters / gradients "
+                                  "at module boundaries (tolerance 1e-2, the north star's bf16 mode)"
+                                  if args.precision != "fp32" else
+                                  "fp32 mode: split-bf16 operands, three tensor-core passes per product, fp32 values between "
+                                  "kernels (tolerance 1e-3 against the fp32 reference)"),
                    "step": "RelationEncoder+gather+GraphTransformer+snt+DecodeLayer "
                    "fwd+bwd (+ flat-gradient all-reduce when dp>1); optimizer outside the hot path",
                    "cuda_graph": run.graph is not None, "gradient_exchange": run.dp_mode,

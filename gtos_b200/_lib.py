@@ -27,6 +27,7 @@ class AttnDesc(C.Structure):
         ("dscores_jt", vp), ("dscores_ts", vp),
         ("dq", vp), ("lddq", i64), ("dk", vp), ("lddk", i64), ("dv", vp), ("lddv", i64),
         ("dq_bf16", vp), ("dk_bf16", vp), ("dv_bf16", vp),
+        ("precise", i32),
     ]
 
 
@@ -64,6 +65,13 @@ SIGNATURES = {
     "gtos_rel_pair_keys": (i32, [vp, i32, i32, i32, i32, i32, vp, vp]),
     "gtos_rel_segsum": (i32, [vp, vp, vp, i64, i32, vp, i64, vp, vp]),
     "gtos_rel_dw_bank": (i32, [vp, i64, vp, vp, i32, i32, i32, vp]),
+    "gtos_split3": (i32, [vp, i64, i64, i64, i32, vp, i64, i32, i32, vp]),
+    "gtos_rel_score_f32": (i32, [vp, i64, vp, vp, i64, vp, i32, i32, i32, i32, vp]),
+    "gtos_rel_grad_f32": (i32, [vp, i64, vp, vp, i64, vp, vp, i64, i32, i32, i32, i32, vp]),
+    "gtos_rel_dqk_f32": (i32, [vp, i64, vp, vp, i64, i32, i32, i32, vp]),
+    "gtos_relu_drop_bwd_f32": (i32, [vp, vp, vp, i64, f32, vp]),
+    "gtos_gru_gate_fwd_f32": (i32, [vp, i64, vp, i64, vp, vp, i32, vp, vp, i64, vp, i64, i32, vp]),
+    "gtos_gru_gate_bwd_f32": (i32, [vp, vp, i64, vp, vp, vp, i32, vp, vp, i64, vp, i64, i64, i32, vp]),
     "gtos_attn_fwd": (i32, [C.POINTER(AttnDesc), vp]),
     "gtos_attn_bwd": (i32, [C.POINTER(AttnDesc), vp]),
     "gtos_add_ln_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, f32, vp, u64, vp]),

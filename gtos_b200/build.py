@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgtos_b200.so")
-SOURCES = ["api.cu", "tmap.cu", "gemm.cu", "elementwise.cu", "attention.cu", "gru.cu", "decode.cu", "graph_paths.cu", "rel_banked.cu"]
+SOURCES = ["api.cu", "tmap.cu", "gemm.cu", "elementwise.cu", "attention.cu", "gru.cu", "decode.cu", "graph_paths.cu", "rel_banked.cu", "precise.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xcudafe", "--diag_suppress=177"]

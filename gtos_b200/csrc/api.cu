@@ -25,7 +25,7 @@ static inline cudaStream_t S_(void* s) { return reinterpret_cast<cudaStream_t>(s
 extern "C" {
 
 const char* gtos_last_error(void) { return g_err; }
-int gtos_abi_version(void) { return 4; }
+int gtos_abi_version(void) { return 5; }
 int gtos_set_sm_reserve(int32_t n) { return set_sm_reserve(n); }
 uint64_t gtos_launch_count(void) { return __atomic_load_n(&g_kernel_launches, __ATOMIC_RELAXED); }
 
@@ -254,6 +254,7 @@ static void fill_attn(const gtos_attn_desc* d, AttnArgs* a) {
   a->scale = d->scale; a->scores_jt = d->scores_jt; a->key_pad = d->key_pad; a->attn_mask = d->attn_mask;
   a->p_drop = d->p_drop; a->seed_ptr = d->seed_ptr; a->seed_off = d->seed_off;
   a->probs = d->probs; a->probs_dropped = d->probs_dropped; a->out = d->out; a->ldo = d->ldo; a->out_bf16 = d->out_bf16;
+  a->precise = d->precise;
 }
 
 int gtos_attn_fwd(const gtos_attn_desc* d, void* stream) {
@@ -275,6 +276,38 @@ int gtos_attn_bwd(const gtos_attn_desc* d, void* stream) {
   GTOS_REQUIRE(!g.dq || (d->q && d->k && g.dk), "attn_bwd: decoder mode needs q, k, dq and dk");
   GTOS_REQUIRE(d->bwd_part >= 0 && d->bwd_part <= 2, "attn_bwd: bwd_part must be 0, 1 or 2");
   return attn_bwd(g, d->bwd_part, S(stream));
+}
+
+int gtos_split3(const float* src, int64_t ld_r, int64_t ld_c, int64_t rows, int32_t cols, void* dst, int64_t ldd,
+                int32_t kp, int32_t role, void* stream) {
+  return split3(src, ld_r, ld_c, rows, cols, dst, ldd, kp, role, S(stream));
+}
+int gtos_rel_score_f32(const float* PR, int64_t ldpr, const float* q, const float* k, int64_t ldqk, float* scores,
+                       int32_t N, int32_t B, int32_t D, int32_t H, void* stream) {
+  return rel_score_f32(PR, ldpr, q, k, ldqk, scores, N, B, D, H, S(stream));
+}
+int gtos_rel_grad_f32(const float* PR, int64_t ldpr, const float* q, const float* k, int64_t ldqk, const float* dscores,
+                      float* G, int64_t ldg, int32_t N, int32_t B, int32_t D, int32_t H, void* stream) {
+  return rel_grad_f32(PR, ldpr, q, k, ldqk, dscores, G, ldg, N, B, D, H, S(stream));
+}
+int gtos_rel_dqk_f32(const float* G, int64_t ldg, float* dq, float* dk, int64_t ld, int32_t N, int32_t B, int32_t D,
+                     void* stream) {
+  return rel_dqk_f32(G, ldg, dq, dk, ld, N, B, D, S(stream));
+}
+int gtos_relu_drop_bwd_f32(const float* dh_in, const float* act, float* dh_out, int64_t n, float p, void* stream) {
+  return relu_drop_bwd_f32(dh_in, act, dh_out, n, p, S(stream));
+}
+int gtos_gru_gate_fwd_f32(const float* gi, int64_t ldgi, const float* gh, int64_t ldgh, const float* h_prev,
+                          const int64_t* lengths, int32_t t, float* h_new, float* out_t, int64_t ldout, float* gates,
+                          int64_t R, int32_t H, void* stream) {
+  return gru_gate_fwd_f32(gi, ldgi, gh, ldgh, h_prev, reinterpret_cast<const long long*>(lengths), t, h_new, out_t, ldout,
+                          gates, R, H, S(stream));
+}
+int gtos_gru_gate_bwd_f32(const float* dh, const float* dout_t, int64_t lddout, const float* gates, const float* h_prev,
+                          const int64_t* lengths, int32_t t, float* dh_part, float* dgi, int64_t lddgi, float* dgh,
+                          int64_t lddgh, int64_t R, int32_t H, void* stream) {
+  return gru_gate_bwd_f32(dh, dout_t, lddout, gates, h_prev, reinterpret_cast<const long long*>(lengths), t, dh_part, dgi,
+                          lddgi, dgh, lddgh, R, H, S(stream));
 }
 
 int gtos_add_ln_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* y, void* y_bf16,

@@ -39,32 +39,56 @@ __host__ __device__ inline int r16(int n) { return (n + 15) & ~15; }
 //   xb [R16][dstr]  bf16  query-side chunk (q or dO)
 //   yb [L16][dstr]  bf16  key-side chunk (K, V, dO or q)
 //   pb [R16][lstr]  bf16  probabilities / dS as MMA operand
+//
+// fp32 mode (AttnArgs::precise, north star: 1e-3 against the fp32 reference): every MMA operand x is staged as a PAIR of
+// bf16 planes, x_hi = bf16(x) and x_lo = bf16(x - x_hi) (16 significand bits together), and every product runs as three
+// tensor-core passes into the same fp32 accumulator: A_hi B_hi + A_lo B_hi + A_hi B_lo (the dropped A_lo B_lo term is
+// ~2^-18 relative).  xl / yl / pl are the lo planes (null in bf16 mode); softmax uses expf instead of __expf.
 struct AttnSmem {
   __nv_bfloat16* xb;
   __nv_bfloat16* yb;
   __nv_bfloat16* pb;
+  __nv_bfloat16* xl;
+  __nv_bfloat16* yl;
+  __nv_bfloat16* pl;
   float* sc;
   int dstr, lstr, L16, R16;
 };
 
-__host__ __device__ inline size_t attn_smem_layout(int L, int dc, int rows, int* dstr, int* lstr, int* L16, int* R16) {
+__host__ __device__ inline size_t attn_smem_layout(int L, int dc, int rows, int* dstr, int* lstr, int* L16, int* R16,
+                                                   bool split = false) {
   *dstr = r16(dc) + 8;
   *L16 = r16(L);
   *R16 = r16(rows);
   int ls = *L16 > r16(dc) ? *L16 : r16(dc);   // sc doubles as the [R16 x dc16] output staging tile
   *lstr = ls + 8;
-  return (size_t)(*R16) * (*dstr) * 2 + (size_t)(*L16) * (*dstr) * 2 + (size_t)(*R16) * (*lstr) * 2 +
-         (size_t)(*R16) * (*lstr) * 4;
+  const size_t planes = (size_t)(*R16) * (*dstr) * 2 + (size_t)(*L16) * (*dstr) * 2 + (size_t)(*R16) * (*lstr) * 2;
+  return planes * (split ? 2 : 1) + (size_t)(*R16) * (*lstr) * 4;
 }
 
+template <bool SPLIT>
 __device__ __forceinline__ AttnSmem carve(uint8_t* base, int L, int dc, int rows) {
   AttnSmem s;
-  attn_smem_layout(L, dc, rows, &s.dstr, &s.lstr, &s.L16, &s.R16);
+  attn_smem_layout(L, dc, rows, &s.dstr, &s.lstr, &s.L16, &s.R16, SPLIT);
   s.sc = reinterpret_cast<float*>(base);
   s.xb = reinterpret_cast<__nv_bfloat16*>(s.sc + (size_t)s.R16 * s.lstr);
   s.yb = s.xb + (size_t)s.R16 * s.dstr;
   s.pb = s.yb + (size_t)s.L16 * s.dstr;
+  s.xl = s.yl = s.pl = nullptr;
+  if (SPLIT) {
+    s.xl = s.pb + (size_t)s.R16 * s.lstr;
+    s.yl = s.xl + (size_t)s.R16 * s.dstr;
+    s.pl = s.yl + (size_t)s.L16 * s.dstr;
+  }
   return s;
+}
+
+// one probability / dS value as MMA operand: hi plane (and lo plane in fp32 mode)
+template <bool SPLIT>
+__device__ __forceinline__ void put_operand(__nv_bfloat16* hi, __nv_bfloat16* lo, int j, float v) {
+  const __nv_bfloat16 h = __float2bfloat16(v);
+  hi[j] = h;
+  if (SPLIT) lo[j] = __float2bfloat16(v - __bfloat162float(h));
 }
 
 // These kernels are instruction-bound (ncu: ~14 M warp instructions per launch, 40 % of them integer division of
@@ -75,7 +99,8 @@ __device__ __forceinline__ int log2_ceil(int n) { return n <= 1 ? 0 : 32 - __clz
 // rows [r0, r0+nr16) x dims [c0, c0+dc) of a [len, B, ld] fp32 projection for (b, h) -> bf16 dst[nr16][dstr];
 // rows >= len and columns >= dc (up to r16(dc)) are zero-filled.  16-byte global loads when alignment allows.
 __device__ __forceinline__ void load_rows_bf16(__nv_bfloat16* dst, int dstr, const float* src, long ld, int B, int b,
-                                               int hoff, int r0, int nr16, int len, int c0, int dc) {
+                                               int hoff, int r0, int nr16, int len, int c0, int dc,
+                                               __nv_bfloat16* dst_lo = nullptr) {
   const int dc16 = r16(dc);
   const bool vec = ((dc & 3) == 0) && ((ld & 3) == 0) && (((hoff + c0) & 3) == 0) &&
                    ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
@@ -100,7 +125,14 @@ __device__ __forceinline__ void load_rows_bf16(__nv_bfloat16* dst, int dstr, con
         if (d + 3 < dc) v.w = p[3];
       }
     }
-    *reinterpret_cast<uint2*>(dst + (size_t)r * dstr + d) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    const uint2 hi = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    *reinterpret_cast<uint2*>(dst + (size_t)r * dstr + d) = hi;
+    if (dst_lo) {                                  // fp32 mode: the residual plane x - bf16(x)
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&hi);
+      const float2 h01 = __bfloat1622float2(h2[0]), h23 = __bfloat1622float2(h2[1]);
+      *reinterpret_cast<uint2*>(dst_lo + (size_t)r * dstr + d) =
+          make_uint2(pack_bf16x2(v.x - h01.x, v.y - h01.y), pack_bf16x2(v.z - h23.x, v.w - h23.y));
+    }
   }
 }
 
@@ -137,9 +169,11 @@ __device__ __forceinline__ void store_rows_f32(float* dst, __nv_bfloat16* dst_b,
 // C[M16 x N16] (fp32, ldc) (+)= A[M16 x K16] (bf16 row-major, lda) * B
 //   B_COL = true : B given as Y[N16 x K16] row-major (i.e. C = A * Y^T)
 //   B_COL = false: B given as Y[K16 x N16] row-major
+//   Alo / Blo: the residual planes of the operands (fp32 mode: three passes hi*hi + lo*hi + hi*lo), or null
 template <bool B_COL>
 __device__ __forceinline__ void tile_mm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* Bm, int ldb, float* C, int ldc,
-                                        int M16, int N16, int K16, bool accumulate) {
+                                        int M16, int N16, int K16, bool accumulate, const __nv_bfloat16* Alo = nullptr,
+                                        const __nv_bfloat16* Blo = nullptr) {
   const int warp = threadIdx.x >> 5;
   const int nt = N16 >> 4, tiles = (M16 >> 4) * nt;
   for (int tile = warp; tile < tiles; tile += AT_WARPS) {
@@ -156,10 +190,24 @@ __device__ __forceinline__ void tile_mm(const __nv_bfloat16* A, int lda, const _
         wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::col_major> fb;
         wmma::load_matrix_sync(fb, Bm + (size_t)n0 * ldb + k0, ldb);
         wmma::mma_sync(acc, fa, fb, acc);
+        if (Alo) {
+          wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::col_major> fl;
+          wmma::load_matrix_sync(fl, Blo + (size_t)n0 * ldb + k0, ldb);
+          wmma::mma_sync(acc, fa, fl, acc);                                  // hi * lo
+          wmma::load_matrix_sync(fa, Alo + (size_t)m0 * lda + k0, lda);
+          wmma::mma_sync(acc, fa, fb, acc);                                  // lo * hi
+        }
       } else {
         wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::row_major> fb;
         wmma::load_matrix_sync(fb, Bm + (size_t)k0 * ldb + n0, ldb);
         wmma::mma_sync(acc, fa, fb, acc);
+        if (Alo) {
+          wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::row_major> fl;
+          wmma::load_matrix_sync(fl, Blo + (size_t)k0 * ldb + n0, ldb);
+          wmma::mma_sync(acc, fa, fl, acc);
+          wmma::load_matrix_sync(fa, Alo + (size_t)m0 * lda + k0, lda);
+          wmma::mma_sync(acc, fa, fb, acc);
+        }
       }
     }
     wmma::store_matrix_sync(C + (size_t)m0 * ldc + n0, acc, ldc, wmma::mem_row_major);
@@ -175,12 +223,13 @@ __device__ __forceinline__ bool is_masked(const AttnArgs& a, int b, int t, int j
 // ============================================================================================
 // forward
 // ============================================================================================
-__global__ void __launch_bounds__(AT_THREADS, AT_MIN_CTAS) attn_fwd_kernel(const AttnArgs a, const int rows) {
+template <bool SPLIT>
+__global__ void __launch_bounds__(AT_THREADS, SPLIT ? 2 : AT_MIN_CTAS) attn_fwd_kernel(const AttnArgs a, const int rows) {
   GTOS_PDL_PROLOGUE();
   extern __shared__ __align__(128) uint8_t smem_u8[];
   const int dc = a.hd < AT_DC ? a.hd : AT_DC;
   const int dc16 = r16(dc);
-  const AttnSmem s = carve(smem_u8, a.S, dc, rows);
+  const AttnSmem s = carve<SPLIT>(smem_u8, a.S, dc, rows);
   const int bh = blockIdx.x, b = bh / a.H, h = bh % a.H;
   const int t0 = blockIdx.y * rows;
   const int nrows = (a.T - t0) < rows ? (a.T - t0) : rows;
@@ -197,10 +246,10 @@ __global__ void __launch_bounds__(AT_THREADS, AT_MIN_CTAS) attn_fwd_kernel(const
   } else {
     for (int c0 = 0; c0 < a.hd; c0 += dc) {
       __syncthreads();
-      load_rows_bf16(s.xb, s.dstr, a.q, a.ldq, a.B, b, hoff, t0, s.R16, a.T, c0, dc);
-      load_rows_bf16(s.yb, s.dstr, a.k, a.ldk, a.B, b, hoff, 0, s.L16, S, c0, dc);
+      load_rows_bf16(s.xb, s.dstr, a.q, a.ldq, a.B, b, hoff, t0, s.R16, a.T, c0, dc, s.xl);
+      load_rows_bf16(s.yb, s.dstr, a.k, a.ldk, a.B, b, hoff, 0, s.L16, S, c0, dc, s.yl);
       __syncthreads();
-      tile_mm<true>(s.xb, s.dstr, s.yb, s.dstr, s.sc, s.lstr, s.R16, s.L16, dc16, c0 > 0);
+      tile_mm<true>(s.xb, s.dstr, s.yb, s.dstr, s.sc, s.lstr, s.R16, s.L16, dc16, c0 > 0, s.xl, s.yl);
     }
   }
   __syncthreads();
@@ -213,8 +262,9 @@ __global__ void __launch_bounds__(AT_THREADS, AT_MIN_CTAS) attn_fwd_kernel(const
   for (int r = warp; r < s.R16; r += AT_WARPS) {
     float* w = s.sc + (size_t)r * s.lstr;
     __nv_bfloat16* pw = s.pb + (size_t)r * s.lstr;
+    __nv_bfloat16* pl = SPLIT ? s.pl + (size_t)r * s.lstr : nullptr;
     if (r >= nrows) {
-      for (int j = lane; j < s.L16; j += 32) pw[j] = __float2bfloat16(0.f);
+      for (int j = lane; j < s.L16; j += 32) put_operand<SPLIT>(pw, pl, j, 0.f);
       continue;
     }
     const int t = t0 + r;
@@ -227,7 +277,7 @@ __global__ void __launch_bounds__(AT_THREADS, AT_MIN_CTAS) attn_fwd_kernel(const
     mx = warp_max(mx);
     float sum = 0.f;
     for (int j = lane; j < S; j += 32) {
-      float e = (w[j] == -INFINITY) ? 0.f : __expf(w[j] - mx);
+      float e = (w[j] == -INFINITY) ? 0.f : (SPLIT ? expf(w[j] - mx) : __expf(w[j] - mx));
       w[j] = e;
       sum += e;
     }
@@ -242,7 +292,7 @@ __global__ void __launch_bounds__(AT_THREADS, AT_MIN_CTAS) attn_fwd_kernel(const
         if (a.p_drop > 0.f) p = (rng_uniform(seed, (unsigned long long)(prow + j)) >= a.p_drop) ? p * ks : 0.f;
         if (a.probs_dropped) a.probs_dropped[prow + j] = p;
       }
-      pw[j] = __float2bfloat16(p);
+      put_operand<SPLIT>(pw, pl, j, p);
     }
   }
 
@@ -251,10 +301,10 @@ __global__ void __launch_bounds__(AT_THREADS, AT_MIN_CTAS) attn_fwd_kernel(const
   ATT_TRACE(0, 2);
   for (int c0 = 0; c0 < a.hd; c0 += dc) {
     __syncthreads();
-    load_rows_bf16(s.yb, s.dstr, a.v, a.ldv, a.B, b, hoff, 0, s.L16, S, c0, dc);
+    load_rows_bf16(s.yb, s.dstr, a.v, a.ldv, a.B, b, hoff, 0, s.L16, S, c0, dc, s.yl);
     __syncthreads();
     ATT_TRACE(0, 3);
-    tile_mm<false>(s.pb, s.lstr, s.yb, s.dstr, s.sc, s.lstr, s.R16, dc16, s.L16, false);
+    tile_mm<false>(s.pb, s.lstr, s.yb, s.dstr, s.sc, s.lstr, s.R16, dc16, s.L16, false, s.pl, s.yl);
     __syncthreads();
     ATT_TRACE(0, 4);
     store_rows_f32(a.out, ob, a.ldo, a.B, b, hoff + c0, t0, nrows, dc, s.sc, s.lstr, 1.f);
@@ -271,10 +321,10 @@ static int attn_rows(int len, int bh) {
   if (rows > AT_ROWS_MAX) rows = 32;
   return rows;
 }
-static size_t attn_smem_bytes(int L, int hd, int rows) {
+static size_t attn_smem_bytes(int L, int hd, int rows, bool split) {
   int dc = hd < AT_DC ? hd : AT_DC;
   int a, b2, c, d;
-  return attn_smem_layout(L, dc, rows, &a, &b2, &c, &d) + 128;
+  return attn_smem_layout(L, dc, rows, &a, &b2, &c, &d, split) + 128;
 }
 
 int attn_debug_read_trace(unsigned long long* host_out, int enable) {
@@ -287,12 +337,22 @@ int attn_fwd(const AttnArgs& a, cudaStream_t st) {
   GTOS_REQUIRE(a.hd >= 1 && (a.hd <= AT_DC || a.hd % AT_DC == 0), "attention: unsupported head_dim %d", a.hd);
   GTOS_REQUIRE(a.p_drop == 0.f || a.seed_ptr, "attention dropout needs a device seed pointer");
   if (a.T == 0 || a.B == 0) return GTOS_OK;
-  const int rows = attn_rows(a.T, a.B * a.H);
-  size_t smem = attn_smem_bytes(a.S, a.hd, rows);
+  const bool split = a.precise != 0;
+  int rows = attn_rows(a.T, a.B * a.H);
+  size_t smem = attn_smem_bytes(a.S, a.hd, rows, split);
+  if (split && smem > 227 * 1024 && rows > 16) {      // the lo planes double the operand tiles: fall back to 16-row blocks
+    rows = 16;
+    smem = attn_smem_bytes(a.S, a.hd, rows, split);
+  }
   GTOS_REQUIRE(smem <= 227 * 1024, "attention: source length %d too long for shared memory", a.S);
-  GTOS_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(a.B * a.H, (a.T + rows - 1) / rows);
-  GTOS_KLAUNCH(attn_fwd_kernel, dim3(grid), dim3(AT_THREADS), smem, st, a, rows);
+  if (split) {
+    GTOS_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GTOS_KLAUNCH(attn_fwd_kernel<true>, dim3(grid), dim3(AT_THREADS), smem, st, a, rows);
+  } else {
+    GTOS_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GTOS_KLAUNCH(attn_fwd_kernel<false>, dim3(grid), dim3(AT_THREADS), smem, st, a, rows);
+  }
   GTOS_LAUNCH_CHECK();
   return GTOS_OK;
 }
@@ -300,13 +360,14 @@ int attn_fwd(const AttnArgs& a, cudaStream_t st) {
 // ============================================================================================
 // backward, query side: dS (and dq in decoder mode)
 // ============================================================================================
-__global__ void __launch_bounds__(AT_THREADS, AT_MIN_CTAS) attn_bwd_q_kernel(const AttnBwdArgs g, const int rows) {
+template <bool SPLIT>
+__global__ void __launch_bounds__(AT_THREADS, SPLIT ? 2 : AT_MIN_CTAS) attn_bwd_q_kernel(const AttnBwdArgs g, const int rows) {
   GTOS_PDL_PROLOGUE();
   extern __shared__ __align__(128) uint8_t smem_u8[];
   const AttnArgs& a = g.f;
   const int dc = a.hd < AT_DC ? a.hd : AT_DC;
   const int dc16 = r16(dc);
-  const AttnSmem s = carve(smem_u8, a.S, dc, rows);
+  const AttnSmem s = carve<SPLIT>(smem_u8, a.S, dc, rows);
   const int bh = blockIdx.x, b = bh / a.H, h = bh % a.H;
   const int t0 = blockIdx.y * rows;
   const int nrows = (a.T - t0) < rows ? (a.T - t0) : rows;
@@ -318,11 +379,11 @@ __global__ void __launch_bounds__(AT_THREADS, AT_MIN_CTAS) attn_bwd_q_kernel(con
   ATT_TRACE(1, 0);
   for (int c0 = 0; c0 < a.hd; c0 += dc) {
     __syncthreads();
-    load_rows_bf16(s.xb, s.dstr, g.dout, g.lddo, a.B, b, hoff, t0, s.R16, a.T, c0, dc);
-    load_rows_bf16(s.yb, s.dstr, a.v, a.ldv, a.B, b, hoff, 0, s.L16, S, c0, dc);
+    load_rows_bf16(s.xb, s.dstr, g.dout, g.lddo, a.B, b, hoff, t0, s.R16, a.T, c0, dc, s.xl);
+    load_rows_bf16(s.yb, s.dstr, a.v, a.ldv, a.B, b, hoff, 0, s.L16, S, c0, dc, s.yl);
     __syncthreads();
     ATT_TRACE(1, 1);
-    tile_mm<true>(s.xb, s.dstr, s.yb, s.dstr, s.sc, s.lstr, s.R16, s.L16, dc16, c0 > 0);
+    tile_mm<true>(s.xb, s.dstr, s.yb, s.dstr, s.sc, s.lstr, s.R16, s.L16, dc16, c0 > 0, s.xl, s.yl);
   }
   __syncthreads();
   ATT_TRACE(1, 2);
@@ -332,9 +393,10 @@ __global__ void __launch_bounds__(AT_THREADS, AT_MIN_CTAS) attn_bwd_q_kernel(con
   for (int r = warp; r < s.R16; r += AT_WARPS) {
     float* w = s.sc + (size_t)r * s.lstr;
     __nv_bfloat16* pw = s.pb + (size_t)r * s.lstr;
+    __nv_bfloat16* pl = SPLIT ? s.pl + (size_t)r * s.lstr : nullptr;
     if (r >= nrows) {
       for (int j = lane; j < s.L16; j += 32) {
-        pw[j] = __float2bfloat16(0.f);
+        put_operand<SPLIT>(pw, pl, j, 0.f);
         w[j] = 0.f;
       }
       continue;
@@ -358,7 +420,7 @@ __global__ void __launch_bounds__(AT_THREADS, AT_MIN_CTAS) attn_bwd_q_kernel(con
         g.dscores_ts[prow + j] = ds;
       }
       w[j] = ds;
-      pw[j] = __float2bfloat16(ds);
+      put_operand<SPLIT>(pw, pl, j, ds);
     }
   }
   __syncthreads();
@@ -373,9 +435,9 @@ __global__ void __launch_bounds__(AT_THREADS, AT_MIN_CTAS) attn_bwd_q_kernel(con
   if (g.dq) {
     for (int c0 = 0; c0 < a.hd; c0 += dc) {
       __syncthreads();
-      load_rows_bf16(s.yb, s.dstr, a.k, a.ldk, a.B, b, hoff, 0, s.L16, S, c0, dc);
+      load_rows_bf16(s.yb, s.dstr, a.k, a.ldk, a.B, b, hoff, 0, s.L16, S, c0, dc, s.yl);
       __syncthreads();
-      tile_mm<false>(s.pb, s.lstr, s.yb, s.dstr, s.sc, s.lstr, s.R16, dc16, s.L16, false);
+      tile_mm<false>(s.pb, s.lstr, s.yb, s.dstr, s.sc, s.lstr, s.R16, dc16, s.L16, false, s.pl, s.yl);
       __syncthreads();
       store_rows_f32(g.dq, reinterpret_cast<__nv_bfloat16*>(g.dq_bf16), g.lddq, a.B, b, hoff + c0, t0, nrows, dc, s.sc, s.lstr, a.scale);
     }
@@ -385,14 +447,15 @@ __global__ void __launch_bounds__(AT_THREADS, AT_MIN_CTAS) attn_bwd_q_kernel(con
 // ============================================================================================
 // backward, key side: dV = Pd^T dO ; dK = scale * dS^T q      (CTA = `rows` key rows of one (b,h))
 // ============================================================================================
-__global__ void __launch_bounds__(AT_THREADS, AT_MIN_CTAS) attn_bwd_kv_kernel(const AttnBwdArgs g, const int rows) {
+template <bool SPLIT>
+__global__ void __launch_bounds__(AT_THREADS, SPLIT ? 2 : AT_MIN_CTAS) attn_bwd_kv_kernel(const AttnBwdArgs g, const int rows) {
   GTOS_PDL_PROLOGUE();
   extern __shared__ __align__(128) uint8_t smem_u8[];
   const AttnArgs& a = g.f;
   const int dc = a.hd < AT_DC ? a.hd : AT_DC;
   const int dc16 = r16(dc);
   const int T = a.T, S = a.S;
-  const AttnSmem s = carve(smem_u8, T, dc, rows);   // L = T: the contraction runs over the queries
+  const AttnSmem s = carve<SPLIT>(smem_u8, T, dc, rows);   // L = T: the contraction runs over the queries
   const int bh = blockIdx.x, b = bh / a.H, h = bh % a.H;
   const int j0 = blockIdx.y * rows;
   const int nrows = (S - j0) < rows ? (S - j0) : rows;
@@ -411,15 +474,15 @@ __global__ void __launch_bounds__(AT_THREADS, AT_MIN_CTAS) attn_bwd_kv_kernel(co
         p = a.probs[pi];
         if (a.p_drop > 0.f) p = (rng_uniform(seed, (unsigned long long)pi) >= a.p_drop) ? p * ks : 0.f;
       }
-      s.pb[(size_t)jr * s.lstr + t] = __float2bfloat16(p);
+      put_operand<SPLIT>(s.pb, s.pl, jr * s.lstr + t, p);
     }
   ATT_TRACE(2, 1);
   for (int c0 = 0; c0 < a.hd; c0 += dc) {
     __syncthreads();
-    load_rows_bf16(s.yb, s.dstr, g.dout, g.lddo, a.B, b, hoff, 0, s.L16, T, c0, dc);
+    load_rows_bf16(s.yb, s.dstr, g.dout, g.lddo, a.B, b, hoff, 0, s.L16, T, c0, dc, s.yl);
     __syncthreads();
     ATT_TRACE(2, 2);
-    tile_mm<false>(s.pb, s.lstr, s.yb, s.dstr, s.sc, s.lstr, s.R16, dc16, s.L16, false);
+    tile_mm<false>(s.pb, s.lstr, s.yb, s.dstr, s.sc, s.lstr, s.R16, dc16, s.L16, false, s.pl, s.yl);
     __syncthreads();
     ATT_TRACE(2, 3);
     store_rows_f32(g.dv, reinterpret_cast<__nv_bfloat16*>(g.dv_bf16), g.lddv, a.B, b, hoff + c0, j0, nrows, dc, s.sc, s.lstr, 1.f);
@@ -430,13 +493,13 @@ __global__ void __launch_bounds__(AT_THREADS, AT_MIN_CTAS) attn_bwd_kv_kernel(co
     for (int t = warp; t < s.L16; t += AT_WARPS)
       for (int jr = lane; jr < s.R16; jr += 32) {
         const float v = (jr < nrows && t < T) ? g.dscores_ts[((long)bh * T + t) * S + j0 + jr] * a.scale : 0.f;
-        s.pb[(size_t)jr * s.lstr + t] = __float2bfloat16(v);
+        put_operand<SPLIT>(s.pb, s.pl, jr * s.lstr + t, v);
       }
     for (int c0 = 0; c0 < a.hd; c0 += dc) {
       __syncthreads();
-      load_rows_bf16(s.yb, s.dstr, a.q, a.ldq, a.B, b, hoff, 0, s.L16, T, c0, dc);
+      load_rows_bf16(s.yb, s.dstr, a.q, a.ldq, a.B, b, hoff, 0, s.L16, T, c0, dc, s.yl);
       __syncthreads();
-      tile_mm<false>(s.pb, s.lstr, s.yb, s.dstr, s.sc, s.lstr, s.R16, dc16, s.L16, false);
+      tile_mm<false>(s.pb, s.lstr, s.yb, s.dstr, s.sc, s.lstr, s.R16, dc16, s.L16, false, s.pl, s.yl);
       __syncthreads();
       store_rows_f32(g.dk, reinterpret_cast<__nv_bfloat16*>(g.dk_bf16), g.lddk, a.B, b, hoff + c0, j0, nrows, dc, s.sc, s.lstr, 1.f);
     }
@@ -447,19 +510,32 @@ int attn_bwd(const AttnBwdArgs& g, int part, cudaStream_t st) {
   const AttnArgs& a = g.f;
   GTOS_REQUIRE(a.hd >= 1 && (a.hd <= AT_DC || a.hd % AT_DC == 0), "attention: unsupported head_dim %d", a.hd);
   if (a.T == 0 || a.B == 0) return GTOS_OK;
-  const int rq = attn_rows(a.T, a.B * a.H), rk = attn_rows(a.S, a.B * a.H);
-  size_t smq = attn_smem_bytes(a.S, a.hd, rq), smk = attn_smem_bytes(a.T, a.hd, rk);
+  const bool split = a.precise != 0;
+  int rq = attn_rows(a.T, a.B * a.H), rk = attn_rows(a.S, a.B * a.H);
+  size_t smq = attn_smem_bytes(a.S, a.hd, rq, split), smk = attn_smem_bytes(a.T, a.hd, rk, split);
+  if (split && smq > 227 * 1024 && rq > 16) { rq = 16; smq = attn_smem_bytes(a.S, a.hd, rq, split); }
+  if (split && smk > 227 * 1024 && rk > 16) { rk = 16; smk = attn_smem_bytes(a.T, a.hd, rk, split); }
   GTOS_REQUIRE(smq <= 227 * 1024 && smk <= 227 * 1024, "attention: sequence too long for shared memory");
-  GTOS_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smq));
-  GTOS_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smk));
   if (part != 2) {
     dim3 gq(a.B * a.H, (a.T + rq - 1) / rq);
-    GTOS_KLAUNCH(attn_bwd_q_kernel, dim3(gq), dim3(AT_THREADS), smq, st, g, rq);
+    if (split) {
+      GTOS_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_q_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smq));
+      GTOS_KLAUNCH(attn_bwd_q_kernel<true>, dim3(gq), dim3(AT_THREADS), smq, st, g, rq);
+    } else {
+      GTOS_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_q_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smq));
+      GTOS_KLAUNCH(attn_bwd_q_kernel<false>, dim3(gq), dim3(AT_THREADS), smq, st, g, rq);
+    }
     GTOS_LAUNCH_CHECK();
   }
   if (part != 1) {
     dim3 gk(a.B * a.H, (a.S + rk - 1) / rk);
-    GTOS_KLAUNCH(attn_bwd_kv_kernel, dim3(gk), dim3(AT_THREADS), smk, st, g, rk);
+    if (split) {
+      GTOS_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smk));
+      GTOS_KLAUNCH(attn_bwd_kv_kernel<true>, dim3(gk), dim3(AT_THREADS), smk, st, g, rk);
+    } else {
+      GTOS_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smk));
+      GTOS_KLAUNCH(attn_bwd_kv_kernel<false>, dim3(gk), dim3(AT_THREADS), smk, st, g, rk);
+    }
     GTOS_LAUNCH_CHECK();
   }
   return GTOS_OK;

@@ -60,8 +60,24 @@ struct AttnArgs {
   float* probs_dropped;           // optional [B,H,T,S] post-dropout weights (need_weights)
   float* out; long ldo;           // [T,B,H*hd] fp32
   void* out_bf16;                 // optional bf16 copy (same ld)
+  int precise;                    // fp32 mode: split-bf16 operand planes, three MMA passes per product (attention.cu)
 };
 int attn_fwd(const AttnArgs& a, cudaStream_t st);
+
+// ---- fp32 mode (precise.cu) ----
+int split3(const float* src, long ld_r, long ld_c, long rows, int cols, void* dst, long ldd, int kp, int role,
+           cudaStream_t st);
+int rel_score_f32(const float* PR, long ldpr, const float* q, const float* k, long ldqk, float* scores, int N, int B,
+                  int D, int H, cudaStream_t st);
+int rel_grad_f32(const float* PR, long ldpr, const float* q, const float* k, long ldqk, const float* dscores, float* G,
+                 long ldg, int N, int B, int D, int H, cudaStream_t st);
+int rel_dqk_f32(const float* G, long ldg, float* dq, float* dk, long ld, int N, int B, int D, cudaStream_t st);
+int relu_drop_bwd_f32(const float* dh_in, const float* act, float* dh_out, long n, float p, cudaStream_t st);
+int gru_gate_fwd_f32(const float* gi, long ldgi, const float* gh, long ldgh, const float* h_prev, const long long* lengths,
+                     int t, float* h_new, float* out_t, long ldout, float* gates, long R, int Hh, cudaStream_t st);
+int gru_gate_bwd_f32(const float* dh, const float* dout_t, long lddout, const float* gates, const float* h_prev,
+                     const long long* lengths, int t, float* dh_part, float* dgi, long lddgi, float* dgh, long lddgh,
+                     long R, int Hh, cudaStream_t st);
 
 struct AttnBwdArgs {
   AttnArgs f;                     // forward description (q,k,v,probs,masks,...)

@@ -63,6 +63,13 @@ class RelationEncoder(nn.Module):
         """src_tokens [Lmax, R] int64, src_lengths [R] int64 -> [R, embed_dim]  (encoder.py:90-119).
         No host sync: lengths stay on the device (the reference calls .tolist(), encoder.py:99)."""
         p = self.dropout if self.training else 0.0
+        if ops.fp32_mode():
+            from . import ops32
+            self.row_counts = None
+            bank = ops32.GRUBank32Fn.apply(src_tokens, src_lengths, self.rel_embed.weight, self.out_proj.weight,
+                                           self.out_proj.bias, self.num_layers, self.hidden_size, float(p),
+                                           *self._gru_weights())
+            return ops.as_bank_tensor(bank)
         counts, self.row_counts = self.row_counts, None
         if not _LEN_SORT:
             counts = None

@@ -32,6 +32,8 @@ class GraphTransformer(nn.Module):
             for layer in self.layers:
                 x, _ = layer(x, relation, kv, self_padding_mask, self_attn_mask)
             return x
+        if ops.fp32_mode():
+            return self._forward_fp32(x, relation, self_padding_mask, self_attn_mask, False)
         if not isinstance(relation, ops.BankedRelation):
             src = ops.factorised_source(relation)       # opt-in: a dense tensor that still knows it is bank[idx]
             if src is not None:
@@ -59,6 +61,25 @@ class GraphTransformer(nn.Module):
                                       rel_token=token, rel_acc=acc, banked=banked)
         return x
 
+    def _forward_fp32(self, x, relation, self_padding_mask, self_attn_mask, need_weights):
+        """fp32 mode (ops.set_precision("fp32"), 1e-3 against the fp32 reference): the dense relation tensor, staged ONCE as
+        the split-bf16 operand all layers' K-tripled projection GEMMs read; a factorised relation is gathered first."""
+        from . import ops32
+        if isinstance(relation, ops.BankedRelation):
+            relation = relation.dense() if relation.multi else ops.bank_gather(relation.bank, relation.idx)
+        N1, N2, B, D = relation.shape
+        rel3 = ops32.split3(relation.detach().contiguous().view(N1 * N2 * B, D), 0)
+        acc = token = None
+        if torch.is_grad_enabled() and relation.requires_grad:
+            acc = ops.RelGradAcc()
+            token = ops.RelTokenFn.apply(relation, acc)
+        attns = []
+        for layer in self.layers:
+            x, _, w = layer._forward(x, None, relation, rel3, None, self_padding_mask, self_attn_mask, need_weights,
+                                     rel_token=token, rel_acc=acc)
+            attns.append(w)
+        return torch.stack(attns) if need_weights else x
+
     def get_attn_weights(self, x, relation, kv=None, self_padding_mask=None, self_attn_mask=None):
         if kv is not None and kv is not x:
             if isinstance(relation, ops.BankedRelation):
@@ -68,6 +89,8 @@ class GraphTransformer(nn.Module):
                 x, attn = layer(x, relation, kv, self_padding_mask, self_attn_mask, need_weights=True)
                 attns.append(attn)
             return torch.stack(attns)
+        if ops.fp32_mode():
+            return self._forward_fp32(x, relation, self_padding_mask, self_attn_mask, True)
         banked = None
         if isinstance(relation, ops.BankedRelation):
             banked, relation, relb = relation, None, None
@@ -123,6 +146,8 @@ class GraphTransformerLayer(nn.Module):
         return x, xb, w
 
     def forward(self, x, relation, kv=None, self_padding_mask=None, self_attn_mask=None, need_weights=False):
+        if ops.fp32_mode() and isinstance(relation, ops.BankedRelation):
+            relation = relation.dense() if relation.multi else ops.bank_gather(relation.bank, relation.idx)
         if isinstance(relation, ops.BankedRelation) and (kv is None or kv is x):
             x, _, w = self._forward(x, None, None, None, kv, self_padding_mask, self_attn_mask, need_weights, banked=relation)
         else:
@@ -158,6 +183,21 @@ class RelationMultiheadAttention(nn.Module):
     def _forward(self, x, xb, relation, relb, key_padding_mask, attn_mask, need_weights, rel_token=None, rel_acc=None,
                  banked=None):
         p = self.dropout if self.training else 0.0
+        if ops.fp32_mode():
+            # fp32 mode: `relb` carries the staged split operand of the relation (or None), never a bf16 copy
+            from . import ops32
+            if banked is not None:
+                relation = banked.dense() if banked.multi else ops.bank_gather(banked.bank, banked.idx)
+                relb = None
+            if relb is not None and relb.dim() != 2:
+                relb = None
+            out, w = ops32.RelAttn32Fn.apply(x, relation, relb, ops.as_u8(key_padding_mask), ops.as_u8(attn_mask),
+                                             self.in_proj_weight, self.in_proj_bias, self.relation_in_proj.weight,
+                                             self.out_proj.weight, self.out_proj.bias, self.num_heads, float(p),
+                                             bool(need_weights), rel_token, rel_acc, bool(self.weights_dropout))
+            if w is not None:
+                w = w.permute(2, 3, 0, 1)
+            return out, w
         out, w = ops.RelAttnFn.apply(x, xb, relation, relb, ops.as_u8(key_padding_mask), ops.as_u8(attn_mask),
                                      self.in_proj_weight, self.in_proj_bias, self.relation_in_proj.weight,
                                      self.out_proj.weight, self.out_proj.bias, self.num_heads, float(p),
@@ -189,6 +229,9 @@ class RelationMultiheadAttention(nn.Module):
         end = 3 * self.embed_dim if end is None else end
         W, b = self.in_proj_weight[start:end].contiguous(), self.in_proj_bias[start:end].contiguous()
         shp = input.shape
+        if ops.fp32_mode():
+            from . import ops32
+            return ops32.mm3(input.reshape(-1, shp[-1]), W, b).view(*shp[:-1], end - start)
         Wb, _ = ops.weight_prep(W, want_t=False)
         y, _ = ops.gemm_tn(ops.cast_bf16(input.reshape(-1, shp[-1])), Wb, end - start, bias=b)
         return y.view(*shp[:-1], end - start)

@@ -45,6 +45,47 @@ def as_u8(mask):
     return m.view(torch.uint8) if m.dtype == torch.bool else m.to(torch.uint8)
 
 
+# ---- arithmetic mode -----------------------------------------------------------------------------
+# "bf16" (default): bf16 tensor-core operands, fp32 accumulation - the north star's 1e-2 tolerance.
+# "fp32": every matrix product on split-bf16 operands (three tensor-core passes, ~2^-17 relative error), fp32 values
+# between all kernels - the north star's 1e-3 tolerance against the fp32 reference (gtos_b200/ops32.py, csrc/precise.cu).
+# Read on every module forward, so it can be switched between calls; a backward pass uses the mode its forward ran in.
+_precision = os.environ.get("GTOS_PRECISION", "bf16")
+if _precision not in ("bf16", "fp32"):
+    raise ValueError(f"GTOS_PRECISION must be bf16 or fp32, got {_precision!r}")
+
+
+def precision():
+    return _precision
+
+
+def set_precision(mode):
+    global _precision
+    if mode not in ("bf16", "fp32"):
+        raise ValueError(f"precision must be 'bf16' or 'fp32', got {mode!r}")
+    _precision = mode
+
+
+class precision_mode:
+    """`with ops.precision_mode("fp32"): loss = model(batch)` - forward passes inside the block run in that mode"""
+
+    def __init__(self, mode):
+        self.mode = mode
+
+    def __enter__(self):
+        self.prev = _precision
+        set_precision(self.mode)
+        return self
+
+    def __exit__(self, *exc):
+        set_precision(self.prev)
+        return False
+
+
+def fp32_mode():
+    return _precision == "fp32"
+
+
 # ---- second stream for work that is off the critical path of a backward pass -----------------
 # The weight-gradient GEMM of a Linear (dW = dY^T X) and its input-gradient GEMM (dX = dY W) are independent and
 # each is latency-bound at this path's sizes (M = 2.6-3.8 k rows: 120 CTAs, 8 k-blocks).  `fork()` lets the dW side
@@ -542,6 +583,9 @@ class FFNFn(torch.autograd.Function):
 
 
 def ffn(x, xb, W1, b1, W2, b2, p=0.0):
+    if _precision == "fp32":
+        from . import ops32
+        return ops32.FFN32Fn.apply(x, W1, b1, W2, b2, float(p))
     return FFNFn.apply(x, xb, W1, b1, W2, b2, float(p))
 
 
@@ -1395,6 +1439,9 @@ class LinearFn(torch.autograd.Function):
 
 
 def linear(x, W, b=None):
+    if _precision == "fp32":
+        from . import ops32
+        return ops32.Linear32Fn.apply(x, W, b)
     return LinearFn.apply(x, W, b)
 
 
@@ -1592,7 +1639,8 @@ class TokenNLLFn(torch.autograd.Function):
         dalign = torch.empty(T, B, S, dtype=torch.float32, device=dev)
         # the bf16 operand copy of d logits for the vocabulary projection's backward GEMMs is written in the same pass
         # (tagged on the gradient like AddLayerNormFn's, see grad_operand): no cast pass over the [T*B, V] tensor
-        dlb = torch.empty(T * B, V, dtype=torch.bfloat16, device=dev) if (V % 8 == 0 and _grad_tags) else None
+        dlb = torch.empty(T * B, V, dtype=torch.bfloat16, device=dev) if (V % 8 == 0 and _grad_tags
+                                                                          and _precision != "fp32") else None
         _lib.check(_lib.load().gtos_token_nll_bwd(_p(dloss), _p(logits), V, V, _p(align), S, _p(copy_seq), _p(target), T * B,
                                                   B, pad_idx, _p(stats), _p(dlogits), V, _p(dgate), _p(dalign), _p(dlb), V,
                                                   _st()), "token_nll_bwd")

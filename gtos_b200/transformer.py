@@ -60,13 +60,13 @@ class TransformerLayer(nn.Module):
         if kv is None:
             a, sw = self.self_attn._forward(x, xb, x, xb, True, self_padding_mask, self_attn_mask, need_weights)
         else:
-            if kvb is None:
+            if kvb is None and not ops.fp32_mode():
                 kvb = ops.cast_bf16(kv.contiguous().view(-1, kv.shape[-1])).view(kv.shape)
             a, sw = self.self_attn._forward(x, xb, kv, kvb, False, self_padding_mask, self_attn_mask, need_weights)
         x, xb = ops.add_layer_norm(a, x, self.attn_layer_norm.weight, self.attn_layer_norm.bias, p)
         ew = None
         if self.with_external:
-            if memb is None:
+            if memb is None and not ops.fp32_mode():
                 memb = ops.cast_bf16(external_memories.contiguous().view(-1, external_memories.shape[-1])).view(
                     external_memories.shape)
             a, ew = self.external_attn._forward(x, xb, external_memories, memb, False, external_padding_mask, None,
@@ -108,6 +108,14 @@ class MultiheadAttention(nn.Module):
 
     def _forward(self, query, qb, key, kb, self_attn, key_padding_mask, attn_mask, need_weights):
         p = self.dropout if self.training else 0.0
+        if ops.fp32_mode():
+            from . import ops32
+            out, w = ops32.MHA32Fn.apply(query, key, bool(self_attn), ops.as_u8(key_padding_mask), ops.as_u8(attn_mask),
+                                         self.in_proj_weight, self.in_proj_bias, self.out_proj.weight, self.out_proj.bias,
+                                         self.num_heads, float(p), bool(self.weights_dropout), bool(need_weights))
+            if w is not None:
+                w = w.max(dim=1)[0].transpose(0, 1)
+            return out, w
         out, w = ops.MHAFn.apply(query, qb, key, kb, bool(self_attn), ops.as_u8(key_padding_mask),
                                  ops.as_u8(attn_mask), self.in_proj_weight, self.in_proj_bias, self.out_proj.weight,
                                  self.out_proj.bias, self.num_heads, float(p), bool(self.weights_dropout),
@@ -133,6 +141,9 @@ class MultiheadAttention(nn.Module):
         end = 3 * self.embed_dim if end is None else end
         W, b = self.in_proj_weight[start:end].contiguous(), self.in_proj_bias[start:end].contiguous()
         shp = input.shape
+        if ops.fp32_mode():
+            from . import ops32
+            return ops32.mm3(input.reshape(-1, shp[-1]), W, b).view(*shp[:-1], end - start)
         Wb, _ = ops.weight_prep(W, want_t=False)
         y, _ = ops.gemm_tn(ops.cast_bf16(input.reshape(-1, shp[-1])), Wb, end - start, bias=b)
         return y.view(*shp[:-1], end - start)

@@ -172,6 +172,10 @@ typedef struct gtos_attn_desc {
   /* optional bf16 copies of dq / dk / dv (same element layout and row strides as the fp32 outputs): the operand of
    * the in_proj backward GEMMs, so no separate cast pass sits between this kernel and them */
   void* dq_bf16; void* dk_bf16; void* dv_bf16;
+  /* fp32 mode (north star: 1e-3 against the fp32 reference): non-zero = every MMA operand is staged as a split-bf16 pair
+   * (x_hi = bf16(x), x_lo = bf16(x - x_hi)) and every product runs as three tensor-core passes hi*hi + lo*hi + hi*lo
+   * with fp32 accumulation; softmax with expf.  The bf16 output copies are still written when asked for. */
+  int32_t precise;
 } gtos_attn_desc;
 int gtos_attn_fwd(const gtos_attn_desc* d, void* stream);
 int gtos_attn_bwd(const gtos_attn_desc* d, void* stream);
@@ -248,6 +252,41 @@ int gtos_gru_step_fwd(const void* x, int64_t ldx, int32_t Kin, const void* hb, i
 int gtos_gru_gate_bwd(const float* dh, const float* dout_t, int64_t lddout, const void* gates, const float* h_prev,
                       const int64_t* lengths, int32_t t, float* dh_prev, void* dgi_bf16, int64_t lddgi, void* dgh_bf16,
                       int64_t lddgh, float* db_ih, float* db_hh, int64_t R, int32_t Hh, void* stream);
+
+/* ---- fp32 mode (BASELINE north star: "within 1e-3 fp32"; the reference computes in fp32 end to end,
+ *      graph_transformer.py:122-133, transformer.py:111-162, encoder.py:90-119) ----
+ * Every matrix product still runs on the tcgen05 GEMMs above, on SPLIT operands: x = x_hi + x_lo, x_hi = bf16(x),
+ * x_lo = bf16(x - x_hi), and A B^T ~= A_hi B_hi^T + A_lo B_hi^T + A_hi B_lo^T is ONE gtos_gemm_tn call with K tripled:
+ * [A_hi | A_lo | A_hi] (role 0) against [B_hi | B_hi | B_lo] (role 1), fp32 accumulation (error ~2^-17 relative).
+ * gtos_split3 stages such an operand: src fp32, element (r, c) at src[r * ld_r + c * ld_c] (a transposed view is free),
+ * dst bf16 [rows, 3 kp] with row stride ldd; kp = cols rounded up to 8, pad columns zero.  With ldd == 3 kp the same buffer
+ * viewed as [3 rows, kp] is the row-stacked operand of gtos_gemm_nn (weight gradients), pairing role 0 with role 1.
+ * The attention core has the same three-pass variant (gtos_attn_desc.precise). */
+int gtos_split3(const float* src, int64_t ld_r, int64_t ld_c, int64_t rows, int32_t cols, void* dst, int64_t ldd,
+                int32_t kp, int32_t role, void* stream);
+/* relation scores and their gradient on fp32 values (graph_transformer.py:122-133).  PR fp32 [P = N*N*B, 2D] (row stride
+ * ldpr) = relation_in_proj(relation), reference column order [ra | rb], row (j*N + i)*B + b (query i, key j);
+ * q / k fp32 rows (n*B + b) with row stride ldqk.
+ *   scores[b,h,j,i] = hd^-1/2 <q[i,b,h] + ra, k[j,b,h] + rb>              (layout of gtos_attn_desc.scores_jt)
+ *   G[p] = hd^-1/2 dscores[b,h,j,i] * [k + rb | q + ra]                   (fp32 [P, 2D]: d ra | d rb)
+ *   dq[i,b] = sum_j G[(j,i,b), 0:D]      dk[j,b] = sum_i G[(j,i,b), D:2D]   (fixed summation order) */
+int gtos_rel_score_f32(const float* PR, int64_t ldpr, const float* q, const float* k, int64_t ldqk, float* scores,
+                       int32_t N, int32_t B, int32_t D, int32_t H, void* stream);
+int gtos_rel_grad_f32(const float* PR, int64_t ldpr, const float* q, const float* k, int64_t ldqk, const float* dscores,
+                      float* G, int64_t ldg, int32_t N, int32_t B, int32_t D, int32_t H, void* stream);
+int gtos_rel_dqk_f32(const float* G, int64_t ldg, float* dq, float* dk, int64_t ld, int32_t N, int32_t B, int32_t D,
+                     void* stream);
+/* FFN backward through dropout(relu(.)) from the fp32 post-dropout activation (graph_transformer.py:60-61) */
+int gtos_relu_drop_bwd_f32(const float* dh_in, const float* act, float* dh_out, int64_t n, float p, void* stream);
+/* GRU cell on fp32 gate pre-activations (nn.GRU r,z,n; encoder.py:105-106): gi = x_t W_ih^T + b_ih, gh = h W_hh^T + b_hh
+ * (both [R, 3H], from K-tripled GEMMs); rows with lengths[row] <= t keep h and emit a zero output.
+ * gates fp32 [R, 4H] = [r | z | n | gh_n].  Backward: dgi / dgh fp32 [R, 3H], dh_part = (dh + dout_t) * z. */
+int gtos_gru_gate_fwd_f32(const float* gi, int64_t ldgi, const float* gh, int64_t ldgh, const float* h_prev,
+                          const int64_t* lengths, int32_t t, float* h_new, float* out_t, int64_t ldout, float* gates,
+                          int64_t R, int32_t H, void* stream);
+int gtos_gru_gate_bwd_f32(const float* dh, const float* dout_t, int64_t lddout, const float* gates, const float* h_prev,
+                          const int64_t* lengths, int32_t t, float* dh_part, float* dgi, int64_t lddgi, float* dgh,
+                          int64_t lddgh, int64_t R, int32_t H, void* stream);
 
 /* ---- incremental beam decode (callers generator/generator.py:120-167, generator/search.py:57-168) ----
  * Single-query attention over a bf16 K/V cache (MultiheadAttention.forward with T_q = 1, transformer.py:98-173).

@@ -29,7 +29,7 @@ def test_header_symbols_are_exported_and_bound(lib):
 
 def test_abi_version_and_error_channel(lib):
     from gtos_b200 import _lib
-    assert lib.gtos_abi_version() == 4
+    assert lib.gtos_abi_version() == 5
     if not torch.cuda.is_available():
         assert lib.gtos_device_check() != 0
         assert "CUDA" in _lib.last_error() or "device" in _lib.last_error()

@@ -148,7 +148,7 @@ def test_graph_transformer_banked_relation_vs_oracle(dev, N, B, D, H, F, L, R, f
     # fused: ra / rb additionally pass through bf16 (the projected bank), which the oracle's emulation mode does not model
     compare_grads(m, P, (out * wo.to(dev)).sum(), (ref16 * wo).sum(), [xg, bg], [xc, bc],
                   tol=(6 if (fused or os.environ.get("GTOS_REL_FUSED_FWD") == "1") else 4) * TOL,
-                  tol_max=0.25 if fused else 0.2)
+                  tol_max=0.3 if os.environ.get("GTOS_REL_FUSED_FWD") == "1" else (0.25 if fused else 0.2))
     compare_grads(m, P, (out * wo.to(dev)).sum(), (ref * wo).sum(), [xg, bg], [xc, bc], tol=0.15, tol_max=0.5)
     # dense path of this repo on the same operands
     xd, bd = x.to(dev).requires_grad_(), bank.to(dev).requires_grad_()

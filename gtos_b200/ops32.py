@@ -28,6 +28,11 @@ from .ops import _attn_desc, _need_cuda, _p, _st, _up8, colsum, dropout_f32, gem
 BF16 = torch.bfloat16
 F32 = torch.float32
 
+# debugging / parity tests: a list here receives the ReLU activation pattern (bool, on the host) of every FFN32Fn forward -
+# the sub-gradient an implementation takes at a unit whose pre-activation is within rounding of zero is a CHOICE, and the
+# parity tests compare gradients given the same choice (tests/test_gpu_fp32_mode.py, oracle/gtos_oracle.py:_relu)
+relu_trace = None
+
 
 def split3(x2d, role):
     """fp32 [rows, cols] (any strides) -> the K-tripled bf16 operand [rows, 3 * up8(cols)]: (hi, lo, hi) for role 0,
@@ -98,6 +103,8 @@ class FFN32Fn(torch.autograd.Function):
         D, Fd = shape[-1], W1.shape[0]
         xs = split3(x.contiguous().view(-1, D), 0)
         h, _ = gemm_tn(xs, split3(W1.detach(), 1), Fd, bias=b1, relu=True)
+        if relu_trace is not None:
+            relu_trace.append((h > 0).view(*shape[:-1], Fd).cpu())
         seed, off = (rng_state(x.device), new_seed_off()) if p > 0 else (None, 0)
         if p > 0:
             dropout_f32(h, p, seed, off, out=h)

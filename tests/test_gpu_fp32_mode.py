@@ -4,6 +4,15 @@ Every assertion here is against the TRUE fp32 oracle (oracle/gtos_oracle.py in i
 reference's own arithmetic, pinned by tests/golden), outputs AND gradients, at 1e-3: max-norm error relative to the largest
 reference value, and relative L2.  Weights are inflated x2 / x3 like the bf16-mode tests (errors hide at the default
 std 0.02).  No bf16-emulation oracle is involved anywhere in this file.
+
+ReLU sub-gradients.  Outputs need no care.  Gradients do: relu'(0) is a jump, so two correct fp32 implementations whose
+FFN pre-activations differ by 1e-5 of the layer's scale take different sub-gradients at the handful of units (about one in
+10^5) that sit that close to zero, and one such unit moves its row of the input gradient by percents (first run of this
+file: outputs at 1e-5, gradients at 2e-3 L2 / 1e-2 max-norm on exactly the D = 512, x3-weight cases, one row each).  The
+tests therefore fix the CHOICE, not the arithmetic (class Kinks): the GPU run reports its activation pattern; the oracle
+takes the GPU's choice for units with |pre-activation| < 1e-4 x the layer's largest one, its own everywhere else; the test
+asserts that the two patterns agree on every unit outside that band and that the band holds < 0.1 % of the units.  Given
+the same choice, every gradient has to agree at 1e-3.
 """
 import pytest
 import torch
@@ -25,6 +34,60 @@ def dev():
     from gtos_b200 import _lib
     _lib.check(_lib.load().gtos_device_check(), "device_check")
     return torch.device("cuda:0")
+
+
+class Kinks:
+    """the ReLU sub-gradient protocol described in the module docstring"""
+    BAND = 1e-4
+
+    def __init__(self):
+        self.masks, self.units, self.in_band, self.flipped, self.outside = [], 0, 0, 0, 0
+
+    def gpu(self):
+        return _KinkRecord(self)
+
+    def oracle(self):
+        return _KinkReplay(self)
+
+    def check(self):
+        assert self.units > 0 and not self.masks, "the oracle consumed a different number of FFN calls than the GPU ran"
+        assert self.outside == 0, f"{self.outside} ReLU units disagree OUTSIDE the rounding band"
+        assert self.in_band <= max(3, 1e-3 * self.units), (self.in_band, self.units)
+
+
+class _KinkRecord:
+    def __init__(self, k):
+        self.k = k
+
+    def __enter__(self):
+        from gtos_b200 import ops32
+        ops32.relu_trace = self.k.masks
+
+    def __exit__(self, *a):
+        from gtos_b200 import ops32
+        ops32.relu_trace = None
+
+
+class _KinkReplay:
+    def __init__(self, k):
+        self.k = k
+
+    def _hook(self, pre):
+        k = self.k
+        m_gpu = k.masks.pop(0).view_as(pre)
+        own = pre.detach() > 0
+        band = pre.detach().abs() < k.BAND * pre.detach().abs().max()
+        k.units += pre.numel()
+        k.in_band += int(band.sum())
+        k.flipped += int(((m_gpu != own) & band).sum())
+        k.outside += int(((m_gpu != own) & ~band).sum())
+        return pre * torch.where(band, m_gpu, own).to(pre.dtype)
+
+    def __enter__(self):
+        O._RELU_HOOK = self._hook
+
+    def __exit__(self, *a):
+        O._RELU_HOOK = None
 
 
 @pytest.fixture()
@@ -104,9 +167,10 @@ def test_attention_core_three_pass_mode_vs_float64(dev, T, S, B, H, hd, causal):
     pr = torch.softmax(w, -1)
     o = (pr @ vh).permute(2, 0, 1, 3).reshape(T * B, D)
     gq, gk, gv = torch.autograd.grad((o * do.double().view(T * B, D)).sum(), [q6, k6, v6])
-    assert rel_err(probs, pr) < 1e-5 and rel_err(out, o) < 1e-5
+    # split operands carry 16 significand bits: score errors of ~1e-5 absolute, amplified by p (1 - p) in the softmax
+    assert rel_err(probs, pr) < 1e-4 and rel_err(out, o) < 1e-4, (rel_err(probs, pr), rel_err(out, o))
     for a, b_ in ((dq, gq), (dk, gk), (dv, gv)):
-        assert rel_err(a, b_) < 2e-5 and l2_err(a, b_) < 2e-5
+        assert rel_err(a, b_) < 2e-4 and l2_err(a, b_) < 2e-4, (rel_err(a, b_), l2_err(a, b_))
 
 
 @pytest.mark.parametrize("N,B,D,H,F,L,wf", [(17, 8, 128, 8, 256, 2, 1.0), (17, 8, 128, 8, 256, 2, 3.0),
@@ -123,11 +187,16 @@ def test_graph_transformer_fp32_mode_vs_fp32_oracle(dev, fp32_mode, N, B, D, H, 
     wo = torch.randn(N, B, D, generator=gen)
     P = oracle_params(m)
     xc, rc = x.clone().requires_grad_(), rel.clone().requires_grad_()
-    ref = O.graph_transformer(P, "", xc, rc, L, H, self_padding_mask=mask)
+    plain = O.graph_transformer(P, "", xc, rc, L, H, self_padding_mask=mask).detach()     # no protocol: plain relu
     m = m.to(dev)
     xg, rg = x.to(dev).requires_grad_(), rel.to(dev).requires_grad_()
-    out = m(xg, rg, self_padding_mask=mask.to(dev))
-    assert rel_err(out, ref) < TOL32, rel_err(out, ref)
+    kinks = Kinks()
+    with kinks.gpu():
+        out = m(xg, rg, self_padding_mask=mask.to(dev))
+    with kinks.oracle():
+        ref = O.graph_transformer(P, "", xc, rc, L, H, self_padding_mask=mask)
+    kinks.check()
+    assert rel_err(out, plain) < TOL32 and rel_err(out, ref) < TOL32, (rel_err(out, plain), rel_err(out, ref))
     compare_grads(m, P, (out * wo.to(dev)).sum(), (ref * wo).sum(), [xg, rg], [xc, rc], tol=TOL32, tol_max=TOL32)
     with torch.no_grad():
         attn = m.get_attn_weights(xg, rg, self_padding_mask=mask.to(dev))
@@ -151,10 +220,14 @@ def test_graph_transformer_fp32_mode_factorised_relation_and_weights_grad(dev, f
     wo = torch.randn(N, B, D, generator=gen)
     P = oracle_params(m)
     xc, bc = x.clone().requires_grad_(), bank.clone().requires_grad_()
-    ref = O.graph_transformer(P, "", xc, O.bank_to_dense(bc, idx), L, H, self_padding_mask=mask)
     m = m.to(dev)
     xg, bg = x.to(dev).requires_grad_(), bank.to(dev).requires_grad_()
-    out = m(xg, ops.BankedRelation(bg, idx.to(dev)), self_padding_mask=mask.to(dev))
+    kinks = Kinks()
+    with kinks.gpu():
+        out = m(xg, ops.BankedRelation(bg, idx.to(dev)), self_padding_mask=mask.to(dev))
+    with kinks.oracle():
+        ref = O.graph_transformer(P, "", xc, O.bank_to_dense(bc, idx), L, H, self_padding_mask=mask)
+    kinks.check()
     assert rel_err(out, ref) < TOL32
     compare_grads(m, P, (out * wo.to(dev)).sum(), (ref * wo).sum(), [xg, bg], [xc, bc], tol=TOL32, tol_max=TOL32)
 
@@ -188,18 +261,26 @@ def test_transformer_fp32_mode_vs_fp32_oracle(dev, fp32_mode, T, S, B, D, H, F, 
     wo = torch.randn(T, B, D, generator=gen)
     P = oracle_params(m)
     xc, kc, mc = (t.clone().requires_grad_() for t in (x, kv, mem))
-    ref = O.transformer(P, "", xc, L, H, kv=kc, self_padding_mask=tmask, self_attn_mask=cm, external_memories=mc,
-                        external_padding_mask=smask, with_external=True)
-    ref2 = O.transformer(P, "", xc, L, H, self_padding_mask=tmask, self_attn_mask=cm, external_memories=mc,
-                         external_padding_mask=smask, with_external=True)
     m = m.to(dev)
     xg, kg, mg = (t.to(dev).requires_grad_() for t in (x, kv, mem))
-    out = m(xg, kv=kg, self_padding_mask=tmask.to(dev), self_attn_mask=cm.to(dev), external_memories=mg,
-            external_padding_mask=smask.to(dev))
+    kinks = Kinks()
+    with kinks.gpu():
+        out = m(xg, kv=kg, self_padding_mask=tmask.to(dev), self_attn_mask=cm.to(dev), external_memories=mg,
+                external_padding_mask=smask.to(dev))
+    with kinks.oracle():
+        ref = O.transformer(P, "", xc, L, H, kv=kc, self_padding_mask=tmask, self_attn_mask=cm, external_memories=mc,
+                            external_padding_mask=smask, with_external=True)
+    kinks.check()
     assert rel_err(out, ref) < TOL32
     compare_grads(m, P, (out * wo.to(dev)).sum(), (ref * wo).sum(), [xg, kg, mg], [xc, kc, mc], tol=TOL32, tol_max=TOL32)
-    out2 = m(xg, self_padding_mask=tmask.to(dev), self_attn_mask=cm.to(dev), external_memories=mg,
-             external_padding_mask=smask.to(dev))
+    kinks = Kinks()
+    with kinks.gpu():
+        out2 = m(xg, self_padding_mask=tmask.to(dev), self_attn_mask=cm.to(dev), external_memories=mg,
+                 external_padding_mask=smask.to(dev))
+    with kinks.oracle():
+        ref2 = O.transformer(P, "", xc, L, H, self_padding_mask=tmask, self_attn_mask=cm, external_memories=mc,
+                             external_padding_mask=smask, with_external=True)
+    kinks.check()
     assert rel_err(out2, ref2) < TOL32
     compare_grads(m, P, (out2 * wo.to(dev)).sum(), (ref2 * wo).sum(), [xg, mg], [xc, mc], tol=TOL32, tol_max=TOL32)
 
@@ -241,10 +322,14 @@ def test_decode_layer_fp32_mode_vs_fp32_oracle(dev, fp32_mode, T, S, B, D, H, F,
     target = torch.randint(2, V, (T, B), generator=gen).masked_fill(tmask, 0)
     P = oracle_params(m)
     pc, gc, sc = (t.clone().requires_grad_() for t in (probe, graph, snt))
-    ref = O.decode_layer(P, "", pc, gc, sc, smask, tmask, cm, copy_seq, L, H, 0, target=target)
     m = m.to(dev)
     pg, gg, sg = (t.to(dev).requires_grad_() for t in (probe, graph, snt))
-    loss = m(pg, gg, sg, smask.to(dev), tmask.to(dev), cm.to(dev), copy_seq.to(dev), target=target.to(dev))
+    kinks = Kinks()
+    with kinks.gpu():
+        loss = m(pg, gg, sg, smask.to(dev), tmask.to(dev), cm.to(dev), copy_seq.to(dev), target=target.to(dev))
+    with kinks.oracle():
+        ref = O.decode_layer(P, "", pc, gc, sc, smask, tmask, cm, copy_seq, L, H, 0, target=target)
+    kinks.check()
     assert abs(loss.item() - ref.item()) < 1e-4 * abs(ref.item())
     compare_grads(m, P, loss, ref, [pg, gg, sg], [pc, gc, sc], tol=TOL32, tol_max=TOL32)
     with torch.no_grad():
@@ -267,12 +352,16 @@ def test_hot_path_fp32_mode_loss_and_every_gradient_vs_fp32_oracle(dev, fp32_mod
     g = synthetic.make_batch(6, 20, D, T_max=14, T_min=7, V=1000, seed=SEED + 3)
     batch = hotpath.batch_tensors(g)
     P = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in model.state_dict().items()}
-    ref = HO.hotpath_loss(P, batch, cfg)
     names = [n for n, _ in model.named_parameters()]
-    g_cpu = torch.autograd.grad(ref, [P[n] for n in names], allow_unused=True)
     model = model.to(dev)
     dbatch = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in batch.items()}
-    loss = model(dbatch)
+    kinks = Kinks()
+    with kinks.gpu():
+        loss = model(dbatch)
+    with kinks.oracle():
+        ref = HO.hotpath_loss(P, batch, cfg)
+    kinks.check()
+    g_cpu = torch.autograd.grad(ref, [P[n] for n in names], allow_unused=True)
     assert abs(loss.item() - ref.item()) < 1e-4 * abs(ref.item()), (loss.item(), ref.item())
     g_gpu = torch.autograd.grad(loss, [p for _, p in model.named_parameters()], allow_unused=True)
     worst = 0.0
@@ -283,6 +372,27 @@ def test_hot_path_fp32_mode_loss_and_every_gradient_vs_fp32_oracle(dev, fp32_mod
         e2, em = l2_err(a, b), rel_err(a, b)
         worst = max(worst, e2, em)
         assert e2 < TOL32 and em < TOL32, f"{n}: rel L2 {e2:.2e}, max-norm {em:.2e}"
+    # for the record (profiles/): the same model and batch in the default bf16 mode against the same oracle gradients
+    import json
+    import os
+    with ops.precision_mode("bf16"):
+        loss16 = model(dbatch)
+        g16 = torch.autograd.grad(loss16, [p for _, p in model.named_parameters()], allow_unused=True)
+    pairs = [(a, b, c) for a, b, c in zip(g_gpu, g16, g_cpu) if a is not None]
+    report = {
+        "what": "HotPath (2 graph + 1 snt + 2 inference layers, D=512, weights x2.5, 6 graphs) vs the fp32 oracle",
+        "relu_units": kinks.units, "relu_units_in_band": kinks.in_band, "relu_choices_taken_from_gpu": kinks.flipped,
+        "fp32_mode": {"loss_rel_err": abs(loss.item() - ref.item()) / abs(ref.item()),
+                      "grad_rel_l2_worst": max(l2_err(a, c) for a, _, c in pairs),
+                      "grad_max_norm_worst": max(rel_err(a, c) for a, _, c in pairs)},
+        "bf16_mode": {"loss_rel_err": abs(loss16.item() - ref.item()) / abs(ref.item()),
+                      "grad_rel_l2_worst": max(l2_err(b, c) for _, b, c in pairs),
+                      "grad_max_norm_worst": max(rel_err(b, c) for _, b, c in pairs)}}
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "fp32_mode_errors.json"), "w") as f:
+            json.dump(report, f, indent=1)
+    assert report["bf16_mode"]["grad_rel_l2_worst"] > 10 * report["fp32_mode"]["grad_rel_l2_worst"]
     # training mode (dropout 0.2 everywhere): finite, reproducible from the device seed
     model.train()
     for mod in model.modules():

@@ -74,6 +74,7 @@ SIGNATURES = {
     "gtos_gru_gate_bwd_f32": (i32, [vp, vp, i64, vp, vp, vp, i32, vp, vp, i64, vp, i64, i64, i32, vp]),
     "gtos_attn_fwd": (i32, [C.POINTER(AttnDesc), vp]),
     "gtos_attn_bwd": (i32, [C.POINTER(AttnDesc), vp]),
+    "gtos_attn_bwd_dk_on_query_side": (i32, [C.POINTER(AttnDesc)]),
     "gtos_add_ln_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, f32, vp, u64, vp]),
     "gtos_add_ln_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, f32, vp, u64, vp]),
     "gtos_ln_param_grad": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, vp]),

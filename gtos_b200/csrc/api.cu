@@ -265,9 +265,17 @@ int gtos_attn_fwd(const gtos_attn_desc* d, void* stream) {
   return attn_fwd(a, S(stream));
 }
 
+int gtos_attn_bwd_dk_on_query_side(const gtos_attn_desc* d) {
+  if (!d) return 0;
+  AttnArgs a;
+  fill_attn(d, &a);
+  return attn_bwd_dk_on_query_side(a, d->q != nullptr && d->k != nullptr);
+}
+
 int gtos_attn_bwd(const gtos_attn_desc* d, void* stream) {
   GTOS_REQUIRE(d && d->v && d->probs && d->dout && d->dscores_ts && d->dv, "attn_bwd: null argument");
   AttnBwdArgs g;
+  memset(&g, 0, sizeof(g));
   fill_attn(d, &g.f);
   g.dout = d->dout; g.lddo = d->lddo; g.dprobs_extra = d->dprobs_extra;
   g.dscores_jt = d->dscores_jt; g.dscores_ts = d->dscores_ts;

@@ -214,6 +214,35 @@ __device__ __forceinline__ void tile_mm(const __nv_bfloat16* A, int lda, const _
   }
 }
 
+// C[M16 x N16] (fp32, ldc) = A^T * B with A given as [K16 x M16] row-major (the dS block as stored: rows = queries) and
+// B as [K16 x N16] row-major: the dS^T q product of the key gradient, taken straight from the query-side tiles
+__device__ __forceinline__ void tile_mm_at(const __nv_bfloat16* A, int lda, const __nv_bfloat16* Bm, int ldb, float* C, int ldc,
+                                           int M16, int N16, int K16, const __nv_bfloat16* Alo = nullptr,
+                                           const __nv_bfloat16* Blo = nullptr) {
+  const int warp = threadIdx.x >> 5;
+  const int nt = N16 >> 4, tiles = (M16 >> 4) * nt;
+  for (int tile = warp; tile < tiles; tile += AT_WARPS) {
+    const int m0 = (tile / nt) << 4, n0 = (tile % nt) << 4;
+    wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc;
+    wmma::fill_fragment(acc, 0.f);
+    for (int k0 = 0; k0 < K16; k0 += 16) {
+      wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::col_major> fa;
+      wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::row_major> fb;
+      wmma::load_matrix_sync(fa, A + (size_t)k0 * lda + m0, lda);
+      wmma::load_matrix_sync(fb, Bm + (size_t)k0 * ldb + n0, ldb);
+      wmma::mma_sync(acc, fa, fb, acc);
+      if (Alo) {
+        wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::row_major> fl;
+        wmma::load_matrix_sync(fl, Blo + (size_t)k0 * ldb + n0, ldb);
+        wmma::mma_sync(acc, fa, fl, acc);
+        wmma::load_matrix_sync(fa, Alo + (size_t)k0 * lda + m0, lda);
+        wmma::mma_sync(acc, fa, fb, acc);
+      }
+    }
+    wmma::store_matrix_sync(C + (size_t)m0 * ldc + n0, acc, ldc, wmma::mem_row_major);
+  }
+}
+
 __device__ __forceinline__ bool is_masked(const AttnArgs& a, int b, int t, int j) {
   if (a.key_pad && a.key_pad[(long)j * a.B + b]) return true;
   if (a.attn_mask && a.attn_mask[(long)t * a.S + j]) return true;
@@ -442,6 +471,19 @@ __global__ void __launch_bounds__(AT_THREADS, SPLIT ? 2 : AT_MIN_CTAS) attn_bwd_
       store_rows_f32(g.dq, reinterpret_cast<__nv_bfloat16*>(g.dq_bf16), g.lddq, a.B, b, hoff + c0, t0, nrows, dc, s.sc, s.lstr, a.scale);
     }
   }
+  // dK = scale * dS^T q right here when this CTA holds EVERY query row of its (batch, head) (a single row block, and the
+  // [keys x dc] result fits the score tile): the key-side kernel is then left with dV = Pd^T dO, which needs nothing from
+  // this kernel - the two run side by side instead of one after the other (attn_bwd_dk_on_query_side)
+  if (g.dk_in_q && g.dk) {
+    for (int c0 = 0; c0 < a.hd; c0 += dc) {
+      __syncthreads();
+      load_rows_bf16(s.xb, s.dstr, a.q, a.ldq, a.B, b, hoff, 0, s.R16, a.T, c0, dc, s.xl);
+      __syncthreads();
+      tile_mm_at(s.pb, s.lstr, s.xb, s.dstr, s.sc, s.lstr, s.L16, dc16, s.R16, s.pl, s.xl);
+      __syncthreads();
+      store_rows_f32(g.dk, reinterpret_cast<__nv_bfloat16*>(g.dk_bf16), g.lddk, a.B, b, hoff + c0, 0, S, dc, s.sc, s.lstr, a.scale);
+    }
+  }
 }
 
 // ============================================================================================
@@ -506,8 +548,24 @@ __global__ void __launch_bounds__(AT_THREADS, SPLIT ? 2 : AT_MIN_CTAS) attn_bwd_
   }
 }
 
-int attn_bwd(const AttnBwdArgs& g, int part, cudaStream_t st) {
+// 1 if gtos_attn_bwd's query-side kernel also produces dK for this shape (decoder mode, one query block per (batch, head))
+int attn_bwd_dk_on_query_side(const AttnArgs& a, bool decoder_mode) {
+  if (!decoder_mode || a.T == 0 || a.B == 0) return 0;
+  static const bool enabled = !(getenv("GTOS_ATTN_DK_Q") && getenv("GTOS_ATTN_DK_Q")[0] == '0');
+  if (!enabled) return 0;
+  const bool split = a.precise != 0;
+  int rq = attn_rows(a.T, a.B * a.H);
+  if (split && attn_smem_bytes(a.S, a.hd, rq, split) > 227 * 1024 && rq > 16) rq = 16;
+  return (rq >= a.T && r16(a.S) <= r16(rq)) ? 1 : 0;
+}
+
+int attn_bwd(const AttnBwdArgs& g_in, int part, cudaStream_t st) {
+  AttnBwdArgs g = g_in;
   const AttnArgs& a = g.f;
+  // part 0 / 1: the query side takes dK when it can; part 0: the key side then skips it.  part 2 alone computes whatever
+  // the caller asks for (dk == NULL: dV only)
+  const int dk_q = (part != 2 && g.dq && g.dk) ? attn_bwd_dk_on_query_side(a, true) : 0;
+  g.dk_in_q = dk_q;
   GTOS_REQUIRE(a.hd >= 1 && (a.hd <= AT_DC || a.hd % AT_DC == 0), "attention: unsupported head_dim %d", a.hd);
   if (a.T == 0 || a.B == 0) return GTOS_OK;
   const bool split = a.precise != 0;
@@ -528,6 +586,10 @@ int attn_bwd(const AttnBwdArgs& g, int part, cudaStream_t st) {
     GTOS_LAUNCH_CHECK();
   }
   if (part != 1) {
+    if (dk_q) {                                   // dK came from the query side
+      g.dk = nullptr;
+      g.dk_bf16 = nullptr;
+    }
     dim3 gk(a.B * a.H, (a.S + rk - 1) / rk);
     if (split) {
       GTOS_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smk));

@@ -89,7 +89,9 @@ struct AttnBwdArgs {
   float* dk; long lddk;
   float* dv; long lddv;
   void* dq_bf16; void* dk_bf16; void* dv_bf16;   // optional bf16 copies, same element layout as dq / dk / dv
+  int dk_in_q;                    // set by attn_bwd: the query-side kernel also writes dK (see attn_bwd_dk_on_query_side)
 };
+int attn_bwd_dk_on_query_side(const AttnArgs& a, bool decoder_mode);
 int attn_bwd(const AttnBwdArgs& a, int part, cudaStream_t st);
 int attn_debug_read_trace(unsigned long long* host_out, int enable);   // 3 kernels x 16 clock64 slots of CTA 0
 

@@ -1029,6 +1029,25 @@ class RelTokenFn(torch.autograd.Function):
 # --------------------------------------------------------------------------------------------
 # vanilla multi-head attention (transformer.py:98-173)
 # --------------------------------------------------------------------------------------------
+def attn_bwd_decoder(lib, d):
+    """gtos_attn_bwd in decoder mode (dq, dk, dv all wanted).  Where one CTA holds every query row of a (batch, head) - all
+    of gtos's decoder shapes except the 1-head alignment attention - the query-side kernel also produces dK, and the
+    key side is left with dV = Pd^T dO, which needs nothing from the query side: it runs on a second stream BESIDE it
+    (the dependent chain of a decoder attention backward is one kernel instead of two).  Returns the fork to join before
+    dv is read."""
+    if _side_enabled and lib.gtos_attn_bwd_dk_on_query_side(C.byref(d)) == 1:
+        dq, dk, dqb, dkb = d.dq, d.dk, d.dq_bf16, d.dk_bf16
+        with fork(which=4) as f_dv:
+            d.bwd_part, d.dq, d.dk, d.dq_bf16, d.dk_bf16 = 2, None, None, None, None
+            _lib.check(lib.gtos_attn_bwd(C.byref(d), _st()), "attn_bwd(dec, dV)")
+        d.bwd_part, d.dq, d.dk, d.dq_bf16, d.dk_bf16 = 1, dq, dk, dqb, dkb
+        _lib.check(lib.gtos_attn_bwd(C.byref(d), _st()), "attn_bwd(dec, dS dq dK)")
+        return f_dv
+    d.bwd_part = 0
+    _lib.check(lib.gtos_attn_bwd(C.byref(d), _st()), "attn_bwd(dec)")
+    return _NoFork()
+
+
 class MHAFn(torch.autograd.Function):
     """query [T,B,D]; key [S,B,D] (value is key); returns (out, weights[B,H,T,S] | None)."""
 
@@ -1140,8 +1159,9 @@ class MHAFn(torch.autograd.Function):
         d.dout, d.lddo = _p(datt), D
         d.dprobs_extra = _p(dwts.contiguous()) if dwts is not None else None
         d.dscores_ts = _p(ds_ts)
-        _lib.check(lib.gtos_attn_bwd(C.byref(d), _st()), "attn_bwd(dec)")
+        f_dv = attn_bwd_decoder(lib, d)
         dW_in = torch.empty(3 * D, D, dtype=torch.float32, device=dev)
+        f_dv.join()                                 # dV (key side) ran beside dS / dq / dK
         if self_attn:
             dprojb, db_in, f_dbin = operand_or_cast(dproj, dproj_b)
             with fork() as f_in:

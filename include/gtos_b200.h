@@ -179,6 +179,11 @@ typedef struct gtos_attn_desc {
 } gtos_attn_desc;
 int gtos_attn_fwd(const gtos_attn_desc* d, void* stream);
 int gtos_attn_bwd(const gtos_attn_desc* d, void* stream);
+/* 1 if, for this shape, the query-side kernel of gtos_attn_bwd (bwd_part 0 or 1, decoder mode with dq and dk) also writes
+ * dK = scale dS^T q - it does when one CTA holds every query row of its (batch, head).  The key side is then only
+ * dV = Pd^T dO, which depends on nothing the query side produces: a caller may launch bwd_part = 2 with dq = dk = NULL on a
+ * second stream BESIDE bwd_part = 1 instead of after it.  0: the key side needs the query side's dscores_ts (run part 0). */
+int gtos_attn_bwd_dk_on_query_side(const gtos_attn_desc* d);
 
 /* ---- residual + dropout + LayerNorm (graph_transformer.py:57-58,64-65; transformer.py:56-57,63,70-71) ---- */
 int gtos_add_ln_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* y, void* y_bf16,

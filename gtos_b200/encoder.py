@@ -18,17 +18,16 @@ _LEN_SORT = os.environ.get("GTOS_GRU_LEN_SORT", "1") == "1"
 
 
 def AMREmbedding(vocab, embedding_dim, pretrained_file=None, amr=False, dump_file=None):
-    """reference: encoder.py:9-64; only the randomly initialised branch is part of the hot path."""
+    """reference: encoder.py:9-64 (host-side construction; the pretrained branch reads a text file of vectors)."""
     if pretrained_file is not None:
-        raise NotImplementedError("pretrained embedding files belong to the reference's data pipeline")
+        from .host_glue import pretrained_embedding
+        return pretrained_embedding(vocab, embedding_dim, pretrained_file, amr=amr, dump_file=dump_file)
     return Embedding(vocab.size, embedding_dim, vocab.padding_idx)
 
 
 class RelationEncoder(nn.Module):
     def __init__(self, vocab, rel_dim, embed_dim, hidden_size, num_layers, dropout, bidirectional=True):
         super().__init__()
-        if not bidirectional:
-            raise NotImplementedError("gtos always builds the bidirectional RelationEncoder (generator.py:27)")
         self.vocab = vocab
         self.embed_dim = embed_dim
         self.hidden_size = hidden_size
@@ -40,7 +39,7 @@ class RelationEncoder(nn.Module):
         # recurrence itself runs on the tcgen05 GEMM + gate kernels of libgtos_b200.so.
         self.rnn = nn.GRU(input_size=rel_dim, hidden_size=hidden_size, num_layers=num_layers,
                           dropout=self.dropout if num_layers > 1 else 0., bidirectional=bidirectional)
-        tot_dim = 2 * hidden_size
+        tot_dim = 2 * hidden_size if bidirectional else hidden_size
         self.out_proj = nn.Linear(tot_dim, embed_dim)
         # [number of paths longer than t for t in range(Lmax)] of the NEXT forward call, if the caller knows it on the host
         # (the data loader builds relation_length there): lets the packed-sequence schedule skip finished paths without
@@ -54,7 +53,7 @@ class RelationEncoder(nn.Module):
     def _gru_weights(self):
         ws = []
         for l in range(self.num_layers):
-            for sfx in ("", "_reverse"):
+            for sfx in (("", "_reverse") if self.bidirectional else ("",)):
                 ws += [getattr(self.rnn, f"weight_ih_l{l}{sfx}"), getattr(self.rnn, f"weight_hh_l{l}{sfx}"),
                        getattr(self.rnn, f"bias_ih_l{l}{sfx}"), getattr(self.rnn, f"bias_hh_l{l}{sfx}")]
         return ws
@@ -63,7 +62,9 @@ class RelationEncoder(nn.Module):
         """src_tokens [Lmax, R] int64, src_lengths [R] int64 -> [R, embed_dim]  (encoder.py:90-119).
         No host sync: lengths stay on the device (the reference calls .tolist(), encoder.py:99)."""
         p = self.dropout if self.training else 0.0
-        if ops.fp32_mode():
+        if ops.fp32_mode() or not self.bidirectional:
+            # fp32 mode; also the unidirectional encoder (encoder.py:67,83 - gtos itself always builds the bidirectional one,
+            # generator.py:27): it runs on the general (any number of directions) fp32-mode Function in both modes
             from . import ops32
             self.row_counts = None
             bank = ops32.GRUBank32Fn.apply(src_tokens, src_lengths, self.rel_embed.weight, self.out_proj.weight,

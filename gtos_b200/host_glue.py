@@ -17,6 +17,47 @@ def Embedding(num_embeddings, embedding_dim, padding_idx):
     return table
 
 
+def pretrained_embedding(vocab, embedding_dim, pretrained_file, amr=False, dump_file=None):
+    """Embedding table initialised from a text file of `token v1 .. vD` lines (encoder.py:9-64): rows of vocabulary tokens
+    found in the file take the file's vector (with amr=True a sense suffix `-NN` is ignored when matching), the other rows
+    are drawn from N(mean, std) of the vectors that were found, the padding row is zero; the table stays trainable.
+    dump_file: the matching lines are copied there.  Host-side, once per model construction."""
+    import re
+
+    def norm(tok):
+        return re.sub(r"-\d\d$", "", tok) if amr else tok
+
+    wanted = {norm(vocab.idx2token(i)) for i in range(vocab.size)}
+    found = {}
+    dump = open(dump_file, "w", encoding="utf8") if dump_file is not None else None
+    try:
+        with open(pretrained_file, encoding="utf8") as fh:
+            for line in fh:
+                parts = line.rstrip().split(" ")
+                if len(parts) - 1 != embedding_dim or parts[0] not in wanted:
+                    continue
+                if dump is not None:
+                    dump.write(line)
+                found[parts[0]] = torch.tensor([float(v) for v in parts[1:]], dtype=torch.float32)
+    finally:
+        if dump is not None:
+            dump.close()
+    if not found:
+        raise ValueError(f"{pretrained_file}: no {embedding_dim}-dimensional vector of a vocabulary token")
+    stacked = torch.stack(list(found.values()))
+    mean, std = float(stacked.mean()), float(stacked.std(unbiased=False))
+    table = torch.empty(vocab.size, embedding_dim).normal_(mean, std)
+    for i in range(vocab.size):
+        tok = vocab.idx2token(i)
+        vec = found.get(tok)
+        if vec is None and amr:
+            vec = found.get(norm(tok))
+        if vec is not None:
+            table[i] = vec
+    table[vocab.padding_idx].zero_()
+    return nn.Embedding.from_pretrained(table, freeze=False)
+
+
 class SelfAttentionMask(nn.Module):
     """Cached strictly-upper-triangular mask, True = may not attend (transformer.py:204-219; bool, not uint8)."""
 

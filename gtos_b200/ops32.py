@@ -384,7 +384,7 @@ class MHA32Fn(torch.autograd.Function):
 # --------------------------------------------------------------------------------------------
 class GRUBank32Fn(torch.autograd.Function):
     """tokens [Lmax,R] int64 (0 = pad), lengths [R] int64 -> [R, embed_dim]; `weights` = (w_ih, w_hh, b_ih, b_hh) per
-    (layer, direction) in nn.GRU order.  Per (layer, direction): ONE K-tripled GEMM for the input projections of all time
+    (layer, direction) in nn.GRU order - two directions per layer, or one (bidirectional=False, encoder.py:67).  Per (layer, direction): ONE K-tripled GEMM for the input projections of all time
     steps, then per step a K-tripled GEMM h W_hh^T and the fp32 gate kernel (packed-sequence masking by `lengths`: a finished
     path keeps its state, so the state after the last step is the path's final state in both directions)."""
 
@@ -397,6 +397,9 @@ class GRUBank32Fn(torch.autograd.Function):
         E = embed_w.shape[1]
         Hh = hidden
         rows = Lmax * R
+        ndir = len(weights) // (4 * num_layers)
+        if ndir not in (1, 2) or ndir * 4 * num_layers != len(weights):
+            raise ValueError(f"GRUBank32Fn: {len(weights)} weight tensors for {num_layers} layers")
         tokens = tokens.contiguous()
         lengths = lengths.contiguous()
         seed = rng_state(dev) if p > 0 else None
@@ -405,14 +408,14 @@ class GRUBank32Fn(torch.autograd.Function):
         _lib.check(lib.gtos_embed_gather(_p(embed_w), _p(tokens), rows, E, _p(X), None, E, p, _p(seed), off_e, _st()),
                    "embed_gather")
         saved, layer_offs = [], []
-        finals = torch.empty(R, 2 * Hh, dtype=F32, device=dev)
+        finals = torch.empty(R, ndir * Hh, dtype=F32, device=dev)
         Kin = E
         for l in range(num_layers):
             last = l == num_layers - 1
             Xs = split3(X, 0)
-            out_l = torch.empty(rows, 2 * Hh, dtype=F32, device=dev) if not last else None
-            for d in range(2):
-                w_ih, w_hh, b_ih, b_hh = weights[(l * 2 + d) * 4:(l * 2 + d) * 4 + 4]
+            out_l = torch.empty(rows, ndir * Hh, dtype=F32, device=dev) if not last else None
+            for d in range(ndir):
+                w_ih, w_hh, b_ih, b_hh = weights[(l * ndir + d) * 4:(l * ndir + d) * 4 + 4]
                 gi, _ = gemm_tn(Xs, split3(w_ih.detach(), 1), 3 * Hh, bias=b_ih)       # [rows, 3H], every time step
                 Whs = split3(w_hh.detach(), 1)
                 hs = torch.empty(Lmax + 1, R, Hh, dtype=F32, device=dev)               # state before processing step s
@@ -424,7 +427,7 @@ class GRUBank32Fn(torch.autograd.Function):
                     gi_t = gi[t * R:(t + 1) * R]
                     out_t = out_l[t * R:(t + 1) * R, d * Hh:(d + 1) * Hh] if out_l is not None else None
                     _lib.check(lib.gtos_gru_gate_fwd_f32(_p(gi_t), 3 * Hh, _p(gh), 3 * Hh, _p(hs[s]), _p(lengths), t,
-                                                         _p(hs[s + 1]), _p(out_t), 2 * Hh, _p(gates[s]), R, Hh, _st()),
+                                                         _p(hs[s + 1]), _p(out_t), ndir * Hh, _p(gates[s]), R, Hh, _st()),
                                "gru_gate_fwd_f32")
                 finals[:, d * Hh:(d + 1) * Hh].copy_(hs[Lmax])
                 saved += [Xs, gates, hs, w_ih, w_hh]
@@ -434,35 +437,35 @@ class GRUBank32Fn(torch.autograd.Function):
                 dropout_f32(out_l, p, seed, off_l, out=out_l)
             layer_offs.append(off_l)
             X = out_l
-            Kin = 2 * Hh
+            Kin = ndir * Hh
         fs = split3(finals, 0)
         out, _ = gemm_tn(fs, split3(out_w.detach(), 1), out_w.shape[0], bias=out_b)
         ctx.save_for_backward(tokens, lengths, fs, out_w, *saved)
-        ctx.meta = (Lmax, R, E, Hh, num_layers, p, seed, off_e, layer_offs, out_w.shape[0], embed_w.shape[0])
+        ctx.meta = (Lmax, R, E, Hh, num_layers, p, seed, off_e, layer_offs, out_w.shape[0], embed_w.shape[0], ndir)
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dout):
         tokens, lengths, fs, out_w, *saved = ctx.saved_tensors
-        Lmax, R, E, Hh, num_layers, p, seed, off_e, layer_offs, Dout, V = ctx.meta
+        Lmax, R, E, Hh, num_layers, p, seed, off_e, layer_offs, Dout, V, ndir = ctx.meta
         lib = _lib.load()
         dev = dout.device
         rows = Lmax * R
         dout = dout.contiguous()
         douts = split3(dout, 1)
-        dW_out = _wgrad(douts, fs, Dout, 2 * Hh)
+        dW_out = _wgrad(douts, fs, Dout, ndir * Hh)
         db_out = colsum(dout)
-        dfinals, _ = gemm_tn(douts, split3(out_w.detach().t(), 0), 2 * Hh)             # [R, 2H]
-        wgrads = [None] * (num_layers * 8)
+        dfinals, _ = gemm_tn(douts, split3(out_w.detach().t(), 0), ndir * Hh)          # [R, ndir H]
+        wgrads = [None] * (num_layers * ndir * 4)
         d_layer_out = None                                                             # [rows, 2H] fp32
         d_embed = None
         for l in range(num_layers - 1, -1, -1):
             dx = None
-            for d in range(2):
-                Xs, gates, hs, w_ih, w_hh = saved[(l * 2 + d) * 5:(l * 2 + d) * 5 + 5]
+            for d in range(ndir):
+                Xs, gates, hs, w_ih, w_hh = saved[(l * ndir + d) * 5:(l * ndir + d) * 5 + 5]
                 Kin = w_ih.shape[1]
-                base = (l * 2 + d) * 4
+                base = (l * ndir + d) * 4
                 dgi = torch.empty(rows, 3 * Hh, dtype=F32, device=dev)                 # rows in time order t
                 dgh = torch.empty(rows, 3 * Hh, dtype=F32, device=dev)                 # rows in step order s
                 Wht = split3(w_hh.detach().t(), 0)                                     # [H, 3 * 3H]
@@ -475,7 +478,7 @@ class GRUBank32Fn(torch.autograd.Function):
                     t = s if d == 0 else Lmax - 1 - s
                     dout_t = d_layer_out[t * R:(t + 1) * R, d * Hh:(d + 1) * Hh] if d_layer_out is not None else None
                     dgi_t, dgh_s = dgi[t * R:(t + 1) * R], dgh[s * R:(s + 1) * R]
-                    _lib.check(lib.gtos_gru_gate_bwd_f32(_p(dh), _p(dout_t), 2 * Hh, _p(gates[s]), _p(hs[s]), _p(lengths), t,
+                    _lib.check(lib.gtos_gru_gate_bwd_f32(_p(dh), _p(dout_t), ndir * Hh, _p(gates[s]), _p(hs[s]), _p(lengths), t,
                                                          _p(dh_part), _p(dgi_t), 3 * Hh, _p(dgh_s), 3 * Hh, R, Hh, _st()),
                                "gru_gate_bwd_f32")
                     dghs = split3(dgh_s, 1)

@@ -173,3 +173,40 @@ def test_banked_relation_evaluation_multipath_mean(dev):
     enc.train()
     enc(x.to(dev), ops.BankedRelation(bank_g, idx.to(dev)), self_padding_mask=mask.to(dev)).sum().backward()
     assert bank_g.grad is not None and torch.isfinite(bank_g.grad).all() and float(bank_g.grad[0].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+def test_unidirectional_relation_encoder_matches_nn_gru(dev, mode):
+    """RelationEncoder(bidirectional=False) (encoder.py:67,83,112; gtos itself never builds it): runs on the general
+    split-operand Function in both modes, so the bound is the fp32 one.  Checker: torch's own packed nn.GRU on the CPU with
+    the same parameters, exactly the reference's forward (encoder.py:90-119)."""
+    import copy
+    from gtos_b200 import ops
+    from gtos_b200.encoder import RelationEncoder
+
+    class V:
+        size, padding_idx, unk_idx = 31, 0, 1
+
+    torch.manual_seed(SEED + 5)
+    R, Lmax, E, Hh, D = 57, 5, 20, 32, 64
+    m = RelationEncoder(V(), E, D, Hh, 2, 0.0, bidirectional=False)
+    with torch.no_grad():
+        m.rel_embed.weight.mul_(20.0)
+    lengths = torch.randint(1, Lmax + 1, (R,))
+    lengths[0] = Lmax
+    tokens = torch.randint(2, 31, (Lmax, R)).masked_fill(torch.arange(Lmax).unsqueeze(1) >= lengths.unsqueeze(0), 0)
+    wo = torch.randn(R, D)
+    ref = copy.deepcopy(m)
+    ls, order = torch.sort(lengths, descending=True)
+    x = ref.rel_embed(tokens.index_select(1, order))
+    _, h = ref.rnn(torch.nn.utils.rnn.pack_padded_sequence(x, ls.tolist()))
+    out_ref = ref.out_proj(h.view(2, 1, R, Hh)[-1, 0].index_select(0, torch.sort(order)[1]))
+    (out_ref * wo).sum().backward()
+    m = m.to(dev)
+    with ops.precision_mode(mode):
+        out = m(tokens.to(dev), lengths.to(dev))
+        (out * wo.to(dev)).sum().backward()
+    assert out.shape == out_ref.shape and rel_err(out, out_ref) < 1e-3
+    gr = dict(ref.named_parameters())
+    for n, p in m.named_parameters():
+        assert l2_err(p.grad, gr[n].grad) < 1e-3, (n, l2_err(p.grad, gr[n].grad))

@@ -49,6 +49,12 @@ class Kinks:
     def oracle(self):
         return _KinkReplay(self)
 
+    def reference(self, width):
+        """the same protocol for the REAL reference modules (oracle/_ref): torch.nn.functional.relu is wrapped while the
+        reference runs; calls whose last dimension is `width` (the FFN hidden size: graph_transformer.py:61,
+        transformer.py:67) go through the hook, every other relu (the char-CNN front-end) is untouched"""
+        return _KinkReplay(self, functional_width=width)
+
     def check(self):
         assert self.units > 0 and not self.masks, "the oracle consumed a different number of FFN calls than the GPU ran"
         assert self.outside == 0, f"{self.outside} ReLU units disagree OUTSIDE the rounding band"
@@ -69,8 +75,10 @@ class _KinkRecord:
 
 
 class _KinkReplay:
-    def __init__(self, k):
+    def __init__(self, k, functional_width=None):
         self.k = k
+        self.width = functional_width
+        self._orig = None
 
     def _hook(self, pre):
         k = self.k
@@ -84,10 +92,25 @@ class _KinkReplay:
         return pre * torch.where(band, m_gpu, own).to(pre.dtype)
 
     def __enter__(self):
-        O._RELU_HOOK = self._hook
+        if self.width is None:
+            O._RELU_HOOK = self._hook
+            return
+        import torch.nn.functional as F
+        self._orig = F.relu
+
+        def relu(x, inplace=False):
+            if x.dim() == 3 and x.shape[-1] == self.width and self.k.masks:
+                return self._hook(x)
+            return self._orig(x, inplace=inplace)
+
+        F.relu = relu
 
     def __exit__(self, *a):
-        O._RELU_HOOK = None
+        if self.width is None:
+            O._RELU_HOOK = None
+        else:
+            import torch.nn.functional as F
+            F.relu = self._orig
 
 
 @pytest.fixture()

@@ -149,28 +149,32 @@ def test_generator_encoder_attention_weights(pair, dev):
 # ---- fp32 mode (ops.set_precision("fp32")): the same unmodified caller, held to the reference's own fp32 numbers ----
 def test_generator_forward_fp32_mode_against_the_unmodified_reference(pair, dev):
     """Generator.forward (generator.py:169-182) of the UNMODIFIED reference caller over the drop-ins in fp32 mode against
-    the all-reference CPU run: loss at 1e-5, parameter gradients at 1e-3.  The checker here is the reference itself, so the
-    ReLU sub-gradient choice cannot be pinned as in tests/test_gpu_fp32_mode.py: one unit within rounding of zero moves a
-    few gradients by ~1e-3 - hence median < 1e-4, at least 90 % of the parameters < 1e-3 and every one < 5e-3 (the bf16
-    mode's bounds on the same test are 2e-2 median / 8e-2 worst)."""
+    the all-reference CPU run: loss at 1e-5, EVERY parameter gradient (front-end included) at 1e-3 relative L2.  The ReLU
+    sub-gradient choice at units within rounding of zero is pinned as in tests/test_gpu_fp32_mode.py (one such unit moves
+    most gradients of this 128-wide model by ~1e-2): the GPU run reports its FFN activation patterns, and the reference's
+    `F.relu` at its two FFN call sites takes the GPU's choice inside the 1e-4 band, its own outside - with zero
+    disagreement outside the band asserted."""
     from gtos_b200 import ops
+    from test_gpu_fp32_mode import Kinks
     ref, ours, vocabs, _, _ = pair
     ref.train()
     ours.train()
     data = GH.make_data(vocabs, B=6, n_max=12, T=9, seed=SEED + 11)
-    loss_ref = ref(data)
-    loss_ref.backward()
-    with ops.precision_mode("fp32"):
+    kinks = Kinks()
+    with ops.precision_mode("fp32"), kinks.gpu():
         loss = ours(GH.to_device(data, dev))
         loss.backward()
     torch.cuda.synchronize()
+    with kinks.reference(GH.GEN_ARGS["ff_embed_dim"]):
+        loss_ref = ref(data)
+    loss_ref.backward()
+    kinks.check()
     assert abs(loss.item() - loss_ref.item()) / abs(loss_ref.item()) < 1e-5, (loss.item(), loss_ref.item())
     gr = dict(ref.named_parameters())
     worst = {n: l2_err(p.grad, gr[n].grad) for n, p in ours.named_parameters() if gr[n].grad is not None}
-    errs = sorted(worst.values())
-    assert errs[len(errs) // 2] < 1e-4, errs[len(errs) // 2]
-    assert errs[int(len(errs) * 0.9)] < 1e-3, errs[int(len(errs) * 0.9)]
-    assert errs[-1] < 5e-3, sorted(worst.items(), key=lambda kv: -kv[1])[:5]
+    assert len(worst) > 100
+    bad = {n: e for n, e in worst.items() if e > 1e-3}
+    assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:8]
     for p in list(ref.parameters()) + list(ours.parameters()):
         p.grad = None
 

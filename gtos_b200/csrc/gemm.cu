@@ -1081,7 +1081,17 @@ int launch_gemm_tn(int mode, const GemmTnArgs& a, cudaStream_t stream) {
     if (bn > 64 && a.N <= bn / 2) continue;                       // tile mostly empty
     const long units = mt * ((a.N + bn - 1) / bn);
     const long waves = (units + sms - 1) / sms;
-    const double mma = (double)kb * 4 * (bn >= 128 ? bn / 2 : 48);  // UMMA floor M128: N/2 cycles per K=16; N=64 is smem-bound
+    double mma = (double)kb * 4 * (bn >= 128 ? bn / 2 : 48);  // UMMA floor M128: N/2 cycles per K=16; N=64 is smem-bound
+    // operand ingest of a k-block, (128 + bn) x 64 bf16 at ~GTOS_TILE_INGEST_BPC (100) B/clk per SM: the many-wave GEMMs (GRU
+    // layer GEMMs, fp32-mode P-row products) are bound by it at bn = 128 (328 cycles per k-block against 256 of MMA), so
+    // they take bn = 256.  Measured (same box, 2 runs each): cfg2 step 8.99 -> 8.92 ms, fp32-mode step 23.3 -> 21.8 ms.
+    // GTOS_TILE_INGEST=0 restores the MMA-only estimate.
+    static const bool ingest = !(getenv("GTOS_TILE_INGEST") && getenv("GTOS_TILE_INGEST")[0] == '0');
+    static const double ingest_bpc = getenv("GTOS_TILE_INGEST_BPC") ? atof(getenv("GTOS_TILE_INGEST_BPC")) : 100.0;
+    if (ingest) {
+      const double ing = (double)kb * (BM + bn) * BK * 2 / ingest_bpc;
+      if (ing > mma) mma = ing;
+    }
     const double epi = (bn / 32) * 350.0;
     const double cost = waves * (mma > epi ? mma : epi) + 2500.0 + (mma > epi ? epi : mma);
     if (cost < best) { best = cost; best_bn = bn; }

@@ -1069,32 +1069,51 @@ int launch_gemm_tn(int mode, const GemmTnArgs& a, cudaStream_t stream) {
   if (mode == MODE_SCORE) return pair ? launch_tn<256, MODE_SCORE, 2>(a, stream) : launch_tn<256, MODE_SCORE, 1>(a, stream);
   if (mode == MODE_GRAD) return pair ? launch_tn<256, MODE_GRAD, 2>(a, stream) : launch_tn<256, MODE_GRAD, 1>(a, stream);
   if (mode == MODE_DREL) return launch_tn<256, MODE_DREL>(a, stream);
-  // plain: pick the N tile with the lowest estimated time = waves x (mainloop + epilogue + fixed cost), in SM cycles
+  // plain: pick the N tile with the lowest estimated time.  Model fitted to `tools/gemm_probe.py --sweep` on a B200
+  // (profiles/r02_gemm_tile_sweep.txt; CUDA-graph back-to-back launches of every plain-GEMM shape of the step at every tile
+  // width):   t [us] = base(bn) + waves x (k_blocks x ck(bn) + e(bn)),   floored by the HBM time of the operands and the result.
+  // A k-block costs ~0.32-0.36 us whatever the tile width - the pipeline is bound by the latency of the bytes in flight
+  // (6 stages of <= 32 KB per SM), not by the MMA - so the widest tile that still fits ONE wave wins (fewer waves, and a
+  // k-block of a 256-wide tile carries twice the FLOPs of a 128-wide one), unless its larger fixed cost (epilogue of a
+  // 128 x 256 fp32 tile, ramp) outweighs it: [2624,1024] x K=512 takes bn = 256 (9.4 us against 9.8 at 128 and 12.0 at 64,
+  // which the previous cycle-count estimate chose), [2624,512] x K=512 stays at 128 (7.0 against 8.9).
+  // GTOS_TILE_MODEL=0 restores the previous estimate (MMA cycles + operand ingest).
   const long mt = (a.M + BM - 1) / BM;
   const int sms = num_sms();
   const long kb = (a.K + BK - 1) / BK;
   int best_bn = 64;
   double best = 1e30;
-  const int cands[3] = {256, 128, 64};
+  const int cands[3] = {128, 256, 64};                              // ties go to the earlier candidate
+  static const bool fitted = !(getenv("GTOS_TILE_MODEL") && getenv("GTOS_TILE_MODEL")[0] == '0');
+  const double hbm_floor = ((double)a.M * a.N * 4 + (double)a.M * a.K * 2 + (double)a.N * a.K * 2) / 5.0e6;   // us at 5 TB/s
   for (int ci = 0; ci < 3; ++ci) {
     const int bn = cands[ci];
     if (bn > 64 && a.N <= bn / 2) continue;                       // tile mostly empty
     const long units = mt * ((a.N + bn - 1) / bn);
     const long waves = (units + sms - 1) / sms;
-    double mma = (double)kb * 4 * (bn >= 128 ? bn / 2 : 48);  // UMMA floor M128: N/2 cycles per K=16; N=64 is smem-bound
-    // operand ingest of a k-block, (128 + bn) x 64 bf16 at ~GTOS_TILE_INGEST_BPC (100) B/clk per SM: the many-wave GEMMs (GRU
-    // layer GEMMs, fp32-mode P-row products) are bound by it at bn = 128 (328 cycles per k-block against 256 of MMA), so
-    // they take bn = 256.  Measured (same box, 2 runs each): cfg2 step 8.99 -> 8.92 ms, fp32-mode step 23.3 -> 21.8 ms.
-    // GTOS_TILE_INGEST=0 restores the MMA-only estimate.
-    static const bool ingest = !(getenv("GTOS_TILE_INGEST") && getenv("GTOS_TILE_INGEST")[0] == '0');
-    static const double ingest_bpc = getenv("GTOS_TILE_INGEST_BPC") ? atof(getenv("GTOS_TILE_INGEST_BPC")) : 100.0;
-    if (ingest) {
-      const double ing = (double)kb * (BM + bn) * BK * 2 / ingest_bpc;
-      if (ing > mma) mma = ing;
+    double cost;
+    if (fitted) {
+      const double base = bn == 256 ? 5.4 : (bn == 128 ? 3.7 : 3.0);
+      const double ck = bn == 256 ? 0.36 : (bn == 128 ? 0.35 : 0.32);
+      double e = bn == 256 ? 1.4 : (bn == 128 ? 0.4 : 0.35);
+      if (bn == 256 && kb < 8) e += (8 - kb) * 0.4;               // short K: the 128 x 256 epilogue is not hidden by the next tile
+      cost = base + waves * (kb * ck + e);
+      if (cost < hbm_floor) cost = hbm_floor;
+    } else {
+      double mma = (double)kb * 4 * (bn >= 128 ? bn / 2 : 48);  // UMMA floor M128: N/2 cycles per K=16; N=64 is smem-bound
+      static const bool ingest = !(getenv("GTOS_TILE_INGEST") && getenv("GTOS_TILE_INGEST")[0] == '0');
+      if (ingest) {                                               // (128 + bn) x 64 bf16 per k-block at ~100 B/clk per SM
+        const double ing = (double)kb * (BM + bn) * BK * 2 / 100.0;
+        if (ing > mma) mma = ing;
+      }
+      const double epi = (bn / 32) * 350.0;
+      cost = waves * (mma > epi ? mma : epi) + 2500.0 + (mma > epi ? epi : mma);
     }
-    const double epi = (bn / 32) * 350.0;
-    const double cost = waves * (mma > epi ? mma : epi) + 2500.0 + (mma > epi ? epi : mma);
     if (cost < best) { best = cost; best_bn = bn; }
+  }
+  if (const char* f = getenv("GTOS_FORCE_BN")) {               // tools/gemm_probe.py --sweep: time every tile width
+    const int v = atoi(f);
+    if (v == 64 || v == 128 || v == 256) best_bn = v;
   }
   if (best_bn == 256) return launch_tn<256, MODE_PLAIN>(a, stream);
   if (best_bn == 128) return launch_tn<128, MODE_PLAIN>(a, stream);

@@ -23,7 +23,61 @@ SHAPES = [  # (M, N, K, what)
 ]
 
 
+STEP_SHAPES = [  # every plain-GEMM shape of the cfg2 step (M = rows of the activation, N, K)
+    (2624, 1024, 512, "enc QK proj / fc1 / dh"), (2624, 512, 512, "enc V / out_proj / datt"), (2624, 512, 1024, "enc fc2 / FFN dx"),
+    (2624, 512, 1536, "enc in_proj dx"), (3840, 1536, 512, "dec QKV"), (3840, 512, 512, "dec q / out_proj / datt"),
+    (2560, 1024, 512, "dec memory K,V"), (3840, 1024, 512, "dec fc1 / dh"), (3840, 512, 1024, "dec fc2 / FFN dx"),
+    (3840, 512, 1536, "dec self in_proj dx"), (2560, 512, 1024, "dec memory dx"), (3840, 304, 512, "transfer"),
+    (3840, 10000, 304, "vocabulary projection"), (3840, 304, 10000, "d logits x W"), (3840, 512, 304, "transfer dx"),
+    (24659, 512, 512, "bank out_proj"), (24659, 256, 768, "GRU dh GEMM"), (98636, 512, 1536, "GRU layer-1 dx"),
+    (98636, 104, 1536, "GRU layer-0 dx"), (24659, 512, 512, "d finals"),
+]
+
+
+def sweep():
+    """graph back-to-back time of every step shape at every tile width (GTOS_FORCE_BN) next to the chooser's own pick"""
+    dev = torch.device("cuda:0")
+    n = 40
+    for M, N, K, what in STEP_SHAPES:
+        A = torch.randn(M, K, device=dev).to(torch.bfloat16)
+        B = torch.randn(N, K, device=dev).to(torch.bfloat16)
+        bias = torch.randn(N, device=dev)
+        out = torch.empty(M, N, device=dev)
+        res = {}
+        for bn in ("auto", "64", "128", "256"):
+            if bn == "auto":
+                os.environ.pop("GTOS_FORCE_BN", None)
+            else:
+                os.environ["GTOS_FORCE_BN"] = bn
+            try:
+                g = torch.cuda.CUDAGraph()
+                s = torch.cuda.Stream()
+                with torch.cuda.stream(s):
+                    ops.gemm_tn(A, B, N, bias=bias, out=out)
+                    s.synchronize()
+                    with torch.cuda.graph(g, stream=s):
+                        for _ in range(n):
+                            ops.gemm_tn(A, B, N, bias=bias, out=out)
+                torch.cuda.synchronize()
+                g.replay()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                g.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                res[bn] = e0.elapsed_time(e1) / n * 1e3
+            except Exception as e:
+                res[bn] = float("nan")
+        os.environ.pop("GTOS_FORCE_BN", None)
+        best = min((v, k) for k, v in res.items() if k != "auto" and v == v)
+        print(f"{what:28s} M={M:6d} N={N:6d} K={K:5d}: auto {res['auto']:7.1f} | 64: {res['64']:7.1f}  128: {res['128']:7.1f}  "
+              f"256: {res['256']:7.1f} us  -> best {best[1]} ({100 * (res['auto'] - best[0]) / res['auto']:.0f}% under auto)")
+
+
 def main():
+    if "--sweep" in sys.argv:
+        return sweep()
     ncu = "--ncu" in sys.argv
     dev = torch.device("cuda:0")
     lib = _lib.load()

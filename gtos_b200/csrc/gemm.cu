@@ -1324,6 +1324,10 @@ gemm_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 static void nn_plan(int M, int N, int Kd, int rel, int* BN, int* KB, int* splits, int* kb_per) {
   *BN = (N >= 256) ? 256 : ((N > 64 || rel) ? 128 : 64);
+  if (const char* f = getenv("GTOS_FORCE_NN_BN")) {
+    const int v = atoi(f);
+    if (!rel && (v == 64 || v == 128 || v == 256)) *BN = v;
+  }
   *KB = rel ? 128 : 64;
   int tiles = ((M + BM - 1) / BM) * ((N + *BN - 1) / *BN);
   int kblocks = (Kd + *KB - 1) / *KB;
@@ -1340,6 +1344,41 @@ static void nn_plan(int M, int N, int Kd, int rel, int* BN, int* KB, int* splits
   // (GRU weight gradients: 1 541 k-blocks) keep one full wave.
   static const int min_kb = getenv("GTOS_NN_MIN_KB") ? atoi(getenv("GTOS_NN_MIN_KB")) : 8;
   if (!rel && per < min_kb) per = kblocks < min_kb ? kblocks : min_kb;
+  // (tile width, split count) by a cost model fitted to `tools/gemm_probe.py --sweep-nn`
+  // (profiles/r02_gemm_nn_sweep.txt):  t [us] = 2.1 + waves x (k-blocks per CTA x 0.35 + bn x 0.027) + 0.15 x splits,
+  // floored by the HBM time of the operands.  The atomic epilogue costs in proportion to the tile width and a k-block
+  // ~0.35 us whatever the width, so narrow tiles with few splits win at the step's sizes (dW [512,512] over 2624 rows:
+  // 8.3 us at bn 64 / 4 splits against 11.0 us at bn 256 / 6 splits; every weight-gradient shape of the step 5-25 % faster
+  // alone, the cfg2 step 0.04 ms faster).  GTOS_NN_MODEL=0 restores the previous plan (one wave, >= GTOS_NN_MIN_KB k-blocks).
+  static const bool nn_model = !(getenv("GTOS_NN_MODEL") && getenv("GTOS_NN_MODEL")[0] == '0');
+  if (nn_model && !rel) {
+    const int sms = num_sms();
+    const int mt = (M + BM - 1) / BM;
+    const double floor_us = ((double)Kd * (M + N) * 2 + (double)M * N * 4) / 5.0e6;
+    double best = 1e30;
+    int best_bn = *BN, best_per = per;
+    const int cands[3] = {64, 128, 256};
+    for (int ci = 0; ci < 3; ++ci) {
+      const int bn = cands[ci];
+      if (bn > 64 && N <= bn / 2) continue;
+      const int tl = mt * ((N + bn - 1) / bn);
+      for (int sp = 1; sp <= 18 && sp <= kblocks; ++sp) {
+        const int pr = (kblocks + sp - 1) / sp;
+        const int real_sp = (kblocks + pr - 1) / pr;
+        const long ctas = (long)tl * real_sp;
+        const long waves = (ctas + sms - 1) / sms;
+        double c = 2.1 + waves * (pr * 0.35 + bn * 0.027) + 0.15 * real_sp;
+        if (c < floor_us) c = floor_us + 0.01 * real_sp;
+        if (c < best) { best = c; best_bn = bn; best_per = pr; }
+      }
+    }
+    *BN = best_bn;
+    per = best_per;
+  }
+  if (const char* f = getenv("GTOS_FORCE_NN_SPLITS")) {        // tools/gemm_probe.py --sweep-nn
+    const int v = atoi(f);
+    if (v >= 1 && !rel) per = (kblocks + v - 1) / v;
+  }
   *kb_per = per;
   *splits = (kblocks + per - 1) / per;
   if (*splits < 1) *splits = 1;

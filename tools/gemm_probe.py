@@ -75,9 +75,64 @@ def sweep():
               f"256: {res['256']:7.1f} us  -> best {best[1]} ({100 * (res['auto'] - best[0]) / res['auto']:.0f}% under auto)")
 
 
+NN_SHAPES = [  # weight-gradient GEMMs of the cfg2 step: dW [M, N] = dY[Kd, M]^T X[Kd, N]
+    (512, 512, 2624, "enc out_proj / V"), (1536, 512, 2624, "enc in_proj"), (1024, 512, 2624, "enc fc1"), (512, 1024, 2624, "enc fc2"),
+    (512, 512, 3840, "dec out_proj / q"), (1536, 512, 3840, "dec self in_proj"), (1024, 512, 2560, "dec memory K,V"),
+    (1024, 512, 3840, "dec fc1"), (512, 1024, 3840, "dec fc2"), (304, 512, 3840, "transfer"), (10000, 304, 3840, "vocabulary"),
+    (768, 104, 98636, "GRU w_ih l0"), (768, 512, 98636, "GRU w_ih l1"), (768, 256, 98636, "GRU w_hh"), (512, 512, 24659, "bank out_proj"),
+]
+
+
+def sweep_nn():
+    dev = torch.device("cuda:0")
+    n = 30
+    for M, N, Kd, what in NN_SHAPES:
+        A = torch.randn(Kd, (M + 7) // 8 * 8, device=dev).to(torch.bfloat16)
+        B = torch.randn(Kd, (N + 7) // 8 * 8, device=dev).to(torch.bfloat16)
+        out = torch.empty(M, N, device=dev)
+        res = {}
+        for bn in ("auto", "64", "128", "256"):
+            for sp in ("auto", "2", "4", "6", "9", "12", "18"):
+                if (bn == "auto") != (sp == "auto"):
+                    continue
+                for k, v in (("GTOS_FORCE_NN_BN", bn), ("GTOS_FORCE_NN_SPLITS", sp)):
+                    if v == "auto":
+                        os.environ.pop(k, None)
+                    else:
+                        os.environ[k] = v
+                try:
+                    g = torch.cuda.CUDAGraph()
+                    s = torch.cuda.Stream()
+                    with torch.cuda.stream(s):
+                        ops.gemm_nn(A, B, M, N, out=out)
+                        s.synchronize()
+                        with torch.cuda.graph(g, stream=s):
+                            for _ in range(n):
+                                ops.gemm_nn(A, B, M, N, out=out)
+                    torch.cuda.synchronize()
+                    g.replay()
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    g.replay()
+                    e1.record()
+                    torch.cuda.synchronize()
+                    res[(bn, sp)] = e0.elapsed_time(e1) / n * 1e3
+                except Exception:
+                    pass
+        for k in ("GTOS_FORCE_NN_BN", "GTOS_FORCE_NN_SPLITS"):
+            os.environ.pop(k, None)
+        auto = res.pop(("auto", "auto"), float("nan"))
+        top = sorted((v, k) for k, v in res.items())[:4]
+        print(f"{what:18s} M={M:5d} N={N:5d} Kd={Kd:6d}: auto {auto:6.1f} us | best " +
+              ", ".join(f"bn{k[0]}/s{k[1]}: {v:5.1f}" for v, k in top))
+
+
 def main():
     if "--sweep" in sys.argv:
         return sweep()
+    if "--sweep-nn" in sys.argv:
+        return sweep_nn()
     ncu = "--ncu" in sys.argv
     dev = torch.device("cuda:0")
     lib = _lib.load()

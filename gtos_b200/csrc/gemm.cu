@@ -139,7 +139,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmO, const TnDev p) {
   constexpr bool REL = (MODE == MODE_SCORE || MODE == MODE_GRAD);
-  static_assert(CG == 1 || REL, "CTA pairs are only wired up for the relation modes");
+  static_assert(CG == 1 || REL || MODE == MODE_PLAIN, "CTA pairs are wired up for the relation modes and the plain GEMM");
   constexpr int OUT_STAGE_BYTES = tn_out_stage_bytes<MODE>();  // two staging tiles per epilogue warpgroup
   constexpr int EPI_WGS = tn_epi_wgs<MODE>();
   constexpr int B_STAGE_BYTES = (BN / CG) * BK * 2;
@@ -233,6 +233,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // (a membar per k-block) is not needed
             if (leader) mbar_expect_tx(&bars->full[s], (uint32_t)(2 * (p.rt.bi * p.rt.bj * 128 + B_STAGE_BYTES)));
             tma_load_4d_2cta(&tmA, &bars->full[s], sa, kb * BK, b, i0, j0);
+            tma_load_2d_2cta(&tmB, &bars->full[s], sb, kb * BK, n_blk * BN + (int)rank * (BN / 2));
+            if (++s == p.stages) { s = 0; ph ^= 1; }
+            continue;
+          } else if (CG == 2) {
+            // plain GEMM as a CTA pair: own 128 rows of A, half of the BN weight rows; a row block past M (odd number of
+            // row blocks) is zero-filled by TMA and still counts its full box
+            if (leader) mbar_expect_tx(&bars->full[s], (uint32_t)(2 * STAGE_BYTES));
+            tma_load_2d_2cta(&tmA, &bars->full[s], sa, kb * BK, m_blk * BM);
             tma_load_2d_2cta(&tmB, &bars->full[s], sb, kb * BK, n_blk * BN + (int)rank * (BN / 2));
             if (++s == p.stages) { s = 0; ph ^= 1; }
             continue;
@@ -1114,6 +1122,20 @@ int launch_gemm_tn(int mode, const GemmTnArgs& a, cudaStream_t stream) {
   if (const char* f = getenv("GTOS_FORCE_BN")) {               // tools/gemm_probe.py --sweep: time every tile width
     const int v = atoi(f);
     if (v == 64 || v == 128 || v == 256) best_bn = v;
+  }
+  // CTA pairs (cta_group::2: each CTA stages its own A rows and HALF of the weight rows) pay ~1 us of cluster launch / sync
+  // and only win where the L2 -> SM operand traffic is the bound: many waves of 256-wide tiles ([98636,512] x K=1536:
+  // 149 -> 136 us; every small shape of the step is 0.7-1.1 us slower as a pair - profiles/r02_gemm_tile_sweep_pairs.txt)
+  int cg = 1;
+  {
+    const long units256 = mt * ((a.N + 255) / 256);
+    if (best_bn == 256 && units256 >= 8L * sms && kb >= 16) cg = 2;
+  }
+  if (const char* f = getenv("GTOS_FORCE_CG")) cg = atoi(f) == 2 ? 2 : 1;
+  if (cg == 2 && mt >= 2 && !a.accumulate) {
+    if (best_bn == 256) return launch_tn<256, MODE_PLAIN, 2>(a, stream);
+    if (best_bn == 128) return launch_tn<128, MODE_PLAIN, 2>(a, stream);
+    return launch_tn<64, MODE_PLAIN, 2>(a, stream);
   }
   if (best_bn == 256) return launch_tn<256, MODE_PLAIN>(a, stream);
   if (best_bn == 128) return launch_tn<128, MODE_PLAIN>(a, stream);

@@ -44,12 +44,24 @@ def sweep():
         bias = torch.randn(N, device=dev)
         out = torch.empty(M, N, device=dev)
         res = {}
-        for bn in ("auto", "64", "128", "256"):
+        os.environ.pop("GTOS_FORCE_BN", None)
+        os.environ.pop("GTOS_FORCE_CG", None)
+        ops.gemm_tn(A, B, N, bias=bias, out=out)
+        ref = out.clone()
+        for bn in ("auto", "64", "128", "256", "64x2", "128x2", "256x2"):
+            os.environ.pop("GTOS_FORCE_CG", None)
             if bn == "auto":
                 os.environ.pop("GTOS_FORCE_BN", None)
             else:
-                os.environ["GTOS_FORCE_BN"] = bn
+                os.environ["GTOS_FORCE_BN"] = bn.split("x")[0]
+                if bn.endswith("x2"):
+                    os.environ["GTOS_FORCE_CG"] = "2"          # CTA pair (cta_group::2)
             try:
+                out.zero_()
+                ops.gemm_tn(A, B, N, bias=bias, out=out)
+                torch.cuda.synchronize()
+                if not torch.equal(out, ref):
+                    print(f"   !! {what} bn={bn}: result differs from the default tile, max abs {float((out - ref).abs().max()):.3e}")
                 g = torch.cuda.CUDAGraph()
                 s = torch.cuda.Stream()
                 with torch.cuda.stream(s):
@@ -70,9 +82,11 @@ def sweep():
             except Exception as e:
                 res[bn] = float("nan")
         os.environ.pop("GTOS_FORCE_BN", None)
+        os.environ.pop("GTOS_FORCE_CG", None)
         best = min((v, k) for k, v in res.items() if k != "auto" and v == v)
         print(f"{what:28s} M={M:6d} N={N:6d} K={K:5d}: auto {res['auto']:7.1f} | 64: {res['64']:7.1f}  128: {res['128']:7.1f}  "
-              f"256: {res['256']:7.1f} us  -> best {best[1]} ({100 * (res['auto'] - best[0]) / res['auto']:.0f}% under auto)")
+              f"256: {res['256']:7.1f} | pairs 64: {res.get('64x2', float('nan')):7.1f}  128: {res.get('128x2', float('nan')):7.1f}  "
+              f"256: {res.get('256x2', float('nan')):7.1f} us  -> best {best[1]} ({100 * (res['auto'] - best[0]) / res['auto']:.0f}% under auto)")
 
 
 NN_SHAPES = [  # weight-gradient GEMMs of the cfg2 step: dW [M, N] = dY[Kd, M]^T X[Kd, N]

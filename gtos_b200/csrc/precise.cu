@@ -192,6 +192,7 @@ __global__ void __launch_bounds__(256) rel_dqk_f32_kernel(const float* __restric
   float* out = (key_side ? dk : dq) + ((long)n * B + b) * ld;
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
     float acc = 0.f;
+#pragma unroll 8
     for (int m = 0; m < N; ++m) {
       const long p = key_side ? ((long)n * N + m) * B + b : ((long)m * N + n) * B + b;
       acc += G[p * ldg + (key_side ? D : 0) + d];

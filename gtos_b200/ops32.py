@@ -34,7 +34,7 @@ F32 = torch.float32
 relu_trace = None
 
 
-def split3(x2d, role):
+def split3(x2d, role, out=None):
     """fp32 [rows, cols] (any strides) -> the K-tripled bf16 operand [rows, 3 * up8(cols)]: (hi, lo, hi) for role 0,
     (hi, hi, lo) for role 1"""
     _need_cuda(x2d)
@@ -42,7 +42,10 @@ def split3(x2d, role):
         raise TypeError(f"split3 expects fp32, got {x2d.dtype}")
     rows, cols = x2d.shape
     kp = _up8(cols)
-    out = torch.empty(rows, 3 * kp, dtype=BF16, device=x2d.device)
+    if out is None:
+        out = torch.empty(rows, 3 * kp, dtype=BF16, device=x2d.device)
+    elif tuple(out.shape) != (rows, 3 * kp) or out.dtype != BF16 or not out.is_contiguous():
+        raise ValueError("split3: out must be a contiguous bf16 [rows, 3 * up8(cols)] tensor")
     _lib.check(_lib.load().gtos_split3(_p(x2d), x2d.stride(0), x2d.stride(1), rows, cols, _p(out), 3 * kp, kp, role, _st()),
                "split3")
     return out
@@ -420,17 +423,18 @@ class GRUBank32Fn(torch.autograd.Function):
                 Whs = split3(w_hh.detach(), 1)
                 hs = torch.empty(Lmax + 1, R, Hh, dtype=F32, device=dev)               # state before processing step s
                 hs[0].zero_()
-                gates = torch.empty(Lmax, R, 4 * Hh, dtype=F32, device=dev)
+                hs3 = torch.empty(Lmax, R, 3 * _up8(Hh), dtype=BF16, device=dev)       # its staged operand: this step's GEMM
+                gates = torch.empty(Lmax, R, 4 * Hh, dtype=F32, device=dev)            # and the backward's dW_hh GEMM
                 for s in range(Lmax):
                     t = s if d == 0 else Lmax - 1 - s
-                    gh, _ = gemm_tn(split3(hs[s], 0), Whs, 3 * Hh, bias=b_hh)
+                    gh, _ = gemm_tn(split3(hs[s], 0, out=hs3[s]), Whs, 3 * Hh, bias=b_hh)
                     gi_t = gi[t * R:(t + 1) * R]
                     out_t = out_l[t * R:(t + 1) * R, d * Hh:(d + 1) * Hh] if out_l is not None else None
                     _lib.check(lib.gtos_gru_gate_fwd_f32(_p(gi_t), 3 * Hh, _p(gh), 3 * Hh, _p(hs[s]), _p(lengths), t,
                                                          _p(hs[s + 1]), _p(out_t), ndir * Hh, _p(gates[s]), R, Hh, _st()),
                                "gru_gate_fwd_f32")
                 finals[:, d * Hh:(d + 1) * Hh].copy_(hs[Lmax])
-                saved += [Xs, gates, hs, w_ih, w_hh]
+                saved += [Xs, gates, hs, hs3, w_ih, w_hh]
             off_l = 0
             if not last and p > 0:                                                     # nn.GRU inter-layer dropout
                 off_l = new_seed_off()
@@ -463,11 +467,12 @@ class GRUBank32Fn(torch.autograd.Function):
         for l in range(num_layers - 1, -1, -1):
             dx = None
             for d in range(ndir):
-                Xs, gates, hs, w_ih, w_hh = saved[(l * ndir + d) * 5:(l * ndir + d) * 5 + 5]
+                Xs, gates, hs, hs3, w_ih, w_hh = saved[(l * ndir + d) * 6:(l * ndir + d) * 6 + 6]
                 Kin = w_ih.shape[1]
                 base = (l * ndir + d) * 4
                 dgi = torch.empty(rows, 3 * Hh, dtype=F32, device=dev)                 # rows in time order t
                 dgh = torch.empty(rows, 3 * Hh, dtype=F32, device=dev)                 # rows in step order s
+                dgh3 = torch.empty(rows, 3 * _up8(3 * Hh), dtype=BF16, device=dev)     # staged per step, reused by dW_hh
                 Wht = split3(w_hh.detach().t(), 0)                                     # [H, 3 * 3H]
                 if l == num_layers - 1:
                     dh = dfinals[:, d * Hh:(d + 1) * Hh].contiguous()
@@ -481,13 +486,13 @@ class GRUBank32Fn(torch.autograd.Function):
                     _lib.check(lib.gtos_gru_gate_bwd_f32(_p(dh), _p(dout_t), ndir * Hh, _p(gates[s]), _p(hs[s]), _p(lengths), t,
                                                          _p(dh_part), _p(dgi_t), 3 * Hh, _p(dgh_s), 3 * Hh, R, Hh, _st()),
                                "gru_gate_bwd_f32")
-                    dghs = split3(dgh_s, 1)
+                    dghs = split3(dgh_s, 1, out=dgh3[s * R:(s + 1) * R])
                     # dh <- dgh @ W_hh + (dh + dout_t) * z
                     _lib.check(lib.gtos_gemm_tn_add(_p(dghs), dghs.stride(0), _p(Wht), Wht.stride(0), None, _p(dh_part), Hh,
                                                     _p(dh), Hh, R, Hh, dghs.shape[1], _st()), "gemm_tn_add")
                 dgis = split3(dgi, 1)
                 wgrads[base + 0] = _wgrad(dgis, Xs, 3 * Hh, Kin)
-                wgrads[base + 1] = _wgrad(split3(dgh, 1), split3(hs[:Lmax].view(rows, Hh), 0), 3 * Hh, Hh)
+                wgrads[base + 1] = _wgrad(dgh3, hs3.view(rows, hs3.shape[-1]), 3 * Hh, Hh)
                 wgrads[base + 2] = colsum(dgi)
                 wgrads[base + 3] = colsum(dgh)
                 Wit = split3(w_ih.detach().t(), 0)                                     # [Kin, 3 * 3H]

@@ -57,6 +57,43 @@ def test_gemm_tn(dev, M, N, K):
     assert rel_err(o32u, ref_u) < 2e-5 * max(1, K ** 0.5) and rel_err(o16u[:, :N].float(), ref_u) < 1e-2
 
 
+@pytest.mark.parametrize("M,N,K", [(2624, 512, 512), (300, 304, 104), (129, 1024, 1536), (4000, 96, 64)])
+@pytest.mark.parametrize("bn", ["64", "128", "256"])
+def test_gemm_tn_every_tile_width_and_cta_pairs(dev, M, N, K, bn, monkeypatch):
+    """the plain GEMM at a forced tile width, alone and as a CTA pair (cta_group::2: each CTA stages its own 128 rows of A
+    and half of the weight rows; odd numbers of row blocks leave the last pair a zero-filled block).  The pair path only
+    engages by itself for many-wave products (the GRU layer GEMMs, M ~ 10^5), so it is forced here: every epilogue (fp32 TMA
+    store, bf16 TMA store, dual output, addend) must give bit-identical results to the default launch."""
+    from gtos_b200 import _lib, ops
+    A = bf(torch.randn(M, K, device=dev))
+    B = bf(torch.randn(N, K, device=dev))
+    bias = torch.randn(N, device=dev)
+    add = torch.randn(M, N, device=dev)
+
+    def run_all():
+        o32, _ = ops.gemm_tn(A, B, N, bias=bias)
+        _, o16 = ops.gemm_tn(A, B, N, bias=bias, f32=False, bf16=True, relu=True)
+        d32, d16 = ops.gemm_tn(A, B, N, bias=bias, f32=True, bf16=True)
+        oadd = torch.empty(M, N, device=dev)
+        if N % 4 == 0:
+            _lib.check(_lib.load().gtos_gemm_tn_add(A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), None, add.data_ptr(), N,
+                                                    oadd.data_ptr(), N, M, N, K, torch.cuda.current_stream().cuda_stream),
+                       "gemm_tn_add")
+        else:
+            oadd.zero_()
+        torch.cuda.synchronize()
+        return o32, o16, d32, d16, oadd
+
+    ref = run_all()
+    assert rel_err(ref[0], A.float() @ B.float().t() + bias) < 2e-5 * max(1, K ** 0.5)
+    monkeypatch.setenv("GTOS_FORCE_BN", bn)
+    for cg in ("1", "2"):
+        monkeypatch.setenv("GTOS_FORCE_CG", cg)
+        got = run_all()
+        for i, (a, b) in enumerate(zip(got, ref)):
+            assert torch.equal(a, b), f"bn={bn} cg={cg} output {i}: max abs diff {float((a.float() - b.float()).abs().max()):.3e}"
+
+
 @pytest.mark.parametrize("Kd,M,N", [(64, 128, 256), (128, 128, 64), (2624, 1536, 512), (1000, 512, 1024),
                                     (333, 200, 104), (4096, 768, 256)])
 def test_gemm_nn(dev, Kd, M, N):

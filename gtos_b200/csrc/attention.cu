@@ -269,7 +269,6 @@ __global__ void __launch_bounds__(AT_THREADS, SPLIT ? 2 : AT_MIN_CTAS) attn_fwd_
 
   // ---- scores into sc ----
   if (a.scores_jt) {
-#pragma unroll 4
     for (int j = warp; j < s.L16; j += AT_WARPS)
       for (int r = lane; r < s.R16; r += 32)
         s.sc[(size_t)r * s.lstr + j] = (r < nrows && j < S) ? a.scores_jt[((long)bh * S + j) * a.T + t0 + r] : 0.f;
@@ -289,23 +288,6 @@ __global__ void __launch_bounds__(AT_THREADS, SPLIT ? 2 : AT_MIN_CTAS) attn_fwd_
   const unsigned long long seed = a.p_drop > 0.f ? reinterpret_cast<const unsigned long long*>(a.seed_ptr)[0] + a.seed_off : 0ull;
   const float ks = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
   const float sscale = a.scores_jt ? 1.f : a.scale;
-  // masks + scale over the WHOLE tile by all threads first: the mask bytes are global loads, and inside the row loop below
-  // (a warp walks its rows one after the other) every row exposed their latency again - phase trace of CTA 0 at the decoder
-  // shapes: 23 k of the kernel's 39 k cycles sat in the softmax phase.  Here the loads of 16 elements per thread are
-  // independent and in flight together.
-  {
-    const int cs = log2_ceil(S);
-    const int total = nrows << cs;
-#pragma unroll 4
-    for (int idx = threadIdx.x; idx < total; idx += AT_THREADS) {
-      const int r = idx >> cs, j = idx & ((1 << cs) - 1);
-      if (j < S) {
-        float* w = s.sc + (size_t)r * s.lstr + j;
-        *w = is_masked(a, b, t0 + r, j) ? -INFINITY : *w * sscale;
-      }
-    }
-  }
-  __syncthreads();
   for (int r = warp; r < s.R16; r += AT_WARPS) {
     float* w = s.sc + (size_t)r * s.lstr;
     __nv_bfloat16* pw = s.pb + (size_t)r * s.lstr;
@@ -316,7 +298,11 @@ __global__ void __launch_bounds__(AT_THREADS, SPLIT ? 2 : AT_MIN_CTAS) attn_fwd_
     }
     const int t = t0 + r;
     float mx = -INFINITY;
-    for (int j = lane; j < S; j += 32) mx = fmaxf(mx, w[j]);
+    for (int j = lane; j < S; j += 32) {         // masks + scale fused into the max pass (same lane owns w[j] below)
+      const float v = is_masked(a, b, t, j) ? -INFINITY : w[j] * sscale;
+      w[j] = v;
+      mx = fmaxf(mx, v);
+    }
     mx = warp_max(mx);
     float sum = 0.f;
     for (int j = lane; j < S; j += 32) {
@@ -433,23 +419,6 @@ __global__ void __launch_bounds__(AT_THREADS, SPLIT ? 2 : AT_MIN_CTAS) attn_bwd_
 
   const unsigned long long seed = a.p_drop > 0.f ? reinterpret_cast<const unsigned long long*>(a.seed_ptr)[0] + a.seed_off : 0ull;
   const float ks = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
-  // The saved probabilities of this tile, staged in shared memory by all threads at once (the dO / V operand tiles are
-  // dead after the product above and are exactly large enough at the decoder shapes): in the row loop below a warp walks
-  // its rows one after the other, and reading the probabilities from global memory there exposed the load latency once per
-  // row (phase trace: 17 k of the kernel's 25 k cycles).  Falls back to global reads when the tile does not fit.
-  float* ptile = reinterpret_cast<float*>(s.xb);
-  const int pstr = s.L16;
-  const bool staged = (size_t)s.R16 * s.L16 * 4 <= (size_t)(s.R16 + s.L16) * s.dstr * 2;
-  if (staged) {
-    const int cs = log2_ceil(S);
-    const int total = nrows << cs;
-#pragma unroll 4
-    for (int idx = threadIdx.x; idx < total; idx += AT_THREADS) {
-      const int r = idx >> cs, j = idx & ((1 << cs) - 1);
-      if (j < S) ptile[r * pstr + j] = a.probs[((long)bh * a.T + t0 + r) * S + j];
-    }
-    __syncthreads();
-  }
   for (int r = warp; r < s.R16; r += AT_WARPS) {
     float* w = s.sc + (size_t)r * s.lstr;
     __nv_bfloat16* pw = s.pb + (size_t)r * s.lstr;
@@ -463,10 +432,9 @@ __global__ void __launch_bounds__(AT_THREADS, SPLIT ? 2 : AT_MIN_CTAS) attn_bwd_
     }
     const int t = t0 + r;
     const long prow = ((long)bh * a.T + t) * S;
-    const float* pr = staged ? ptile + r * pstr : a.probs + prow;
     float dot = 0.f;
     for (int j = lane; j < S; j += 32) {
-      float p = pr[j];
+      float p = a.probs[prow + j];
       float dp = w[j];
       if (g.dprobs_extra) dp += g.dprobs_extra[prow + j];
       if (a.p_drop > 0.f) dp = (rng_uniform(seed, (unsigned long long)(prow + j)) >= a.p_drop) ? dp * ks : 0.f;
@@ -477,7 +445,7 @@ __global__ void __launch_bounds__(AT_THREADS, SPLIT ? 2 : AT_MIN_CTAS) attn_bwd_
     for (int j = lane; j < s.L16; j += 32) {
       float ds = 0.f;
       if (j < S) {
-        ds = pr[j] * (w[j] - dot);
+        ds = a.probs[prow + j] * (w[j] - dot);
         g.dscores_ts[prow + j] = ds;
       }
       w[j] = ds;
@@ -540,7 +508,6 @@ __global__ void __launch_bounds__(AT_THREADS, SPLIT ? 2 : AT_MIN_CTAS) attn_bwd_
   // pb[jr][t] = Pd[t][j0+jr]  (transposed while loading; coalesced over jr in global)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   ATT_TRACE(2, 0);
-#pragma unroll 4
   for (int t = warp; t < s.L16; t += AT_WARPS)
     for (int jr = lane; jr < s.R16; jr += 32) {
       float p = 0.f;
@@ -565,7 +532,6 @@ __global__ void __launch_bounds__(AT_THREADS, SPLIT ? 2 : AT_MIN_CTAS) attn_bwd_
   ATT_TRACE(2, 4);
   if (g.dk) {
     __syncthreads();
-#pragma unroll 4
     for (int t = warp; t < s.L16; t += AT_WARPS)
       for (int jr = lane; jr < s.R16; jr += 32) {
         const float v = (jr < nrows && t < T) ? g.dscores_ts[((long)bh * T + t) * S + j0 + jr] * a.scale : 0.f;

@@ -139,7 +139,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmO, const TnDev p) {
   constexpr bool REL = (MODE == MODE_SCORE || MODE == MODE_GRAD);
-  static_assert(CG == 1 || REL || MODE == MODE_PLAIN, "CTA pairs are wired up for the relation modes and the plain GEMM");
+  static_assert(CG == 1 || REL || MODE == MODE_PLAIN || MODE == MODE_DREL,
+                "CTA pairs are wired up for the relation modes, d_relation and the plain GEMM");
   constexpr int OUT_STAGE_BYTES = tn_out_stage_bytes<MODE>();  // two staging tiles per epilogue warpgroup
   constexpr int EPI_WGS = tn_epi_wgs<MODE>();
   constexpr int B_STAGE_BYTES = (BN / CG) * BK * 2;
@@ -1076,7 +1077,12 @@ int launch_gemm_tn(int mode, const GemmTnArgs& a, cudaStream_t stream) {
   static const bool pair = !(getenv("GTOS_REL_2CTA") && getenv("GTOS_REL_2CTA")[0] == '0');
   if (mode == MODE_SCORE) return pair ? launch_tn<256, MODE_SCORE, 2>(a, stream) : launch_tn<256, MODE_SCORE, 1>(a, stream);
   if (mode == MODE_GRAD) return pair ? launch_tn<256, MODE_GRAD, 2>(a, stream) : launch_tn<256, MODE_GRAD, 1>(a, stream);
-  if (mode == MODE_DREL) return launch_tn<256, MODE_DREL>(a, stream);
+  if (mode == MODE_DREL) {
+    // d_relation = G Wperm as a CTA pair too: two pair tiles per unit, each CTA stages half of Wperm^T (L2 -> SM operand
+    // traffic per FLOP down by a third): 142 -> 133 us per launch at config 2 (A/B on one box).  GTOS_DREL_CG2=0: single CTAs.
+    static const bool drel_pair = !(getenv("GTOS_DREL_CG2") && getenv("GTOS_DREL_CG2")[0] == '0');
+    return drel_pair ? launch_tn<256, MODE_DREL, 2>(a, stream) : launch_tn<256, MODE_DREL>(a, stream);
+  }
   // plain: pick the N tile with the lowest estimated time.  Model fitted to `tools/gemm_probe.py --sweep` on a B200
   // (profiles/r02_gemm_tile_sweep.txt; CUDA-graph back-to-back launches of every plain-GEMM shape of the step at every tile
   // width):   t [us] = base(bn) + waves x (k_blocks x ck(bn) + e(bn)),   floored by the HBM time of the operands and the result.

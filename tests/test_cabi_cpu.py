@@ -77,3 +77,29 @@ def test_state_dict_keys_match_reference_names():
     assert sd["layers.0.self_attn.relation_in_proj.weight"].shape == (256, 128)
     sd = Transformer(1, 128, 256, 8, 0.1, with_external=True).state_dict()
     assert "layers.0.external_attn.in_proj_weight" in sd and "layers.0.external_layer_norm.bias" in sd
+
+
+def test_precision_switch_host_logic():
+    """ops.set_precision / ops.precision_mode: validation, nesting and restore (the modules read ops.fp32_mode() on every
+    forward; GTOS_PRECISION sets the initial value)"""
+    import pytest
+    from gtos_b200 import ops
+    start = ops.precision()
+    assert start in ("bf16", "fp32")
+    with ops.precision_mode("fp32"):
+        assert ops.fp32_mode() and ops.precision() == "fp32"
+        with ops.precision_mode("bf16"):
+            assert not ops.fp32_mode()
+        assert ops.fp32_mode()
+    assert ops.precision() == start
+    with pytest.raises(ValueError):
+        ops.set_precision("fp16")
+    with pytest.raises(ValueError):
+        with ops.precision_mode("tf32"):
+            pass
+    assert ops.precision() == start
+    # the fp32-mode Functions exist and keep the no-CPU-fallback rule
+    import torch
+    from gtos_b200 import _lib, ops32
+    with pytest.raises(_lib.GtosLibraryError):
+        ops32.split3(torch.zeros(4, 8), 0)

@@ -65,6 +65,7 @@ SIGNATURES = {
     "gtos_rel_pair_keys": (i32, [vp, i32, i32, i32, i32, i32, vp, vp]),
     "gtos_rel_segsum": (i32, [vp, vp, vp, i64, i32, vp, i64, vp, vp]),
     "gtos_rel_dw_bank": (i32, [vp, i64, vp, vp, i32, i32, i32, vp]),
+    "gtos_zero_regions": (i32, [vp, vp, i32, vp]),
     "gtos_split3": (i32, [vp, i64, i64, i64, i32, vp, i64, i32, i32, vp]),
     "gtos_rel_score_f32": (i32, [vp, i64, vp, vp, i64, vp, i32, i32, i32, i32, vp]),
     "gtos_rel_grad_f32": (i32, [vp, i64, vp, vp, i64, vp, vp, i64, i32, i32, i32, i32, vp]),

@@ -286,6 +286,23 @@ int gtos_attn_bwd(const gtos_attn_desc* d, void* stream) {
   return attn_bwd(g, d->bwd_part, S(stream));
 }
 
+int gtos_zero_regions(void* const* ptrs, const int64_t* bytes, int32_t n, void* stream) {
+  GTOS_REQUIRE(n >= 0 && (n == 0 || (ptrs && bytes)), "zero_regions: null argument");
+  for (int32_t i0 = 0; i0 < n; i0 += ZERO_MAX_REGIONS) {              // HOST arrays: chunks of one launch each
+    ZeroRegions z;
+    memset(&z, 0, sizeof(z));
+    const int m = n - i0 < ZERO_MAX_REGIONS ? n - i0 : ZERO_MAX_REGIONS;
+    for (int i = 0; i < m; ++i) {
+      GTOS_REQUIRE(bytes[i0 + i] >= 0 && (bytes[i0 + i] == 0 || ptrs[i0 + i]), "zero_regions: bad region %d", i0 + i);
+      z.ptr[i] = ptrs[i0 + i];
+      z.bytes[i] = bytes[i0 + i];
+    }
+    int e = zero_regions(z, m, S(stream));
+    if (e) return e;
+  }
+  return GTOS_OK;
+}
+
 int gtos_split3(const float* src, int64_t ld_r, int64_t ld_c, int64_t rows, int32_t cols, void* dst, int64_t ldd,
                 int32_t kp, int32_t role, void* stream) {
   return split3(src, ld_r, ld_c, rows, cols, dst, ldd, kp, role, S(stream));

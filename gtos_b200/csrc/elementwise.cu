@@ -570,6 +570,41 @@ int colsum(const float* x, long ld, float* out, long rows, int cols, cudaStream_
 }
 
 // ---------------------------------------------------------------------------------------
+// zero up to ZERO_MAX_REGIONS byte ranges in ONE launch (the GRU's length-sorted schedule clears ~75 small row ranges per
+// step - rows no kernel writes but a later GEMM reads; as separate fills they were 75 launches of ~2.3 us each, 30 of them
+// in front of the first GRU step).  blockIdx.y = region, the blocks of a region stride over it with 16-byte stores.
+// ---------------------------------------------------------------------------------------
+__global__ void zero_regions_kernel(const ZeroRegions z) {
+  GTOS_PDL_PROLOGUE();
+  uint8_t* p = reinterpret_cast<uint8_t*>(z.ptr[blockIdx.y]);
+  const long n = z.bytes[blockIdx.y];
+  if (n <= 0) return;
+  const long head = (16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15;          // bytes up to the first 16-byte boundary
+  const long h = head < n ? head : n;
+  const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = tid; i < h; i += stride) p[i] = 0;
+  const long n16 = (n - h) >> 4;
+  uint4* q = reinterpret_cast<uint4*>(p + h);
+  for (long i = tid; i < n16; i += stride) q[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (long i = h + (n16 << 4) + tid; i < n; i += stride) p[i] = 0;
+}
+
+int zero_regions(const ZeroRegions& z, int n, cudaStream_t st) {
+  if (n <= 0) return GTOS_OK;
+  GTOS_REQUIRE(n <= ZERO_MAX_REGIONS, "zero_regions: at most %d regions per call", ZERO_MAX_REGIONS);
+  long mx = 0;
+  for (int i = 0; i < n; ++i) mx = z.bytes[i] > mx ? z.bytes[i] : mx;
+  if (mx <= 0) return GTOS_OK;
+  long bx = (mx / 16 + 255) / 256;
+  if (bx < 1) bx = 1;
+  if (bx > 64) bx = 64;
+  GTOS_KLAUNCH(zero_regions_kernel, dim3((unsigned)bx, (unsigned)n), dim3(256), 0, st, z);
+  GTOS_LAUNCH_CHECK();
+  return GTOS_OK;
+}
+
+// ---------------------------------------------------------------------------------------
 // elementwise dropout forward on a bf16 activation (FFN hidden), in place; and
 // dh = dh_in * (h > 0) * dropmask/(1-p) -> bf16 (+ optional fp32)      [ReLU/dropout backward]
 // ---------------------------------------------------------------------------------------

@@ -64,6 +64,14 @@ struct AttnArgs {
 };
 int attn_fwd(const AttnArgs& a, cudaStream_t st);
 
+// several byte ranges zeroed by one launch (elementwise.cu)
+constexpr int ZERO_MAX_REGIONS = 48;
+struct ZeroRegions {
+  void* ptr[ZERO_MAX_REGIONS];
+  long bytes[ZERO_MAX_REGIONS];
+};
+int zero_regions(const ZeroRegions& z, int n, cudaStream_t st);
+
 // ---- fp32 mode (precise.cu) ----
 int split3(const float* src, long ld_r, long ld_c, long rows, int cols, void* dst, long ldd, int kp, int role,
            cudaStream_t st);

@@ -438,6 +438,20 @@ def gemm_nn(A, B, M, N, out=None, a_off=0, b_off=0):
     return out
 
 
+def zero_regions(tensors):
+    """zero several (contiguous) tensors / row-range views with ONE kernel launch instead of one fill each"""
+    ts = [t for t in tensors if t is not None and t.numel() > 0]
+    if not ts:
+        return
+    for t in ts:
+        if not t.is_contiguous():
+            raise ValueError("zero_regions: contiguous views only")
+    n = len(ts)
+    ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in ts])
+    sizes = (C.c_int64 * n)(*[t.numel() * t.element_size() for t in ts])
+    _lib.check(_lib.load().gtos_zero_regions(ptrs, sizes, n, _st()), "zero_regions")
+
+
 def colsum(x2d, out=None):
     if out is None:
         out = torch.empty(x2d.shape[1], dtype=torch.float32, device=x2d.device)
@@ -1254,10 +1268,11 @@ class GRUBankFn(torch.autograd.Function):
         Kin = E
         for l in range(num_layers):
             outb = torch.empty(rows, 2 * Hh, dtype=torch.bfloat16, device=dev) if l < num_layers - 1 else None
+            clear = []                                                             # ranges to zero: ONE launch per layer
             if outb is not None and counts is not None:
                 for t in range(Lmax):                                              # rows no kernel writes: zero (they are
                     if counts[t] < R:                                              # operands of the next layer's GEMMs)
-                        outb[t * R + counts[t]:(t + 1) * R].zero_()
+                        clear.append(outb[t * R + counts[t]:(t + 1) * R])
             Kx = _up64(Kin)
             ldw = Kx + _up8(Hh)
             per_dir = []
@@ -1274,19 +1289,19 @@ class GRUBankFn(torch.autograd.Function):
                 gates = torch.empty(Lmax, R, 4 * Hh, dtype=torch.bfloat16, device=dev)
                 hs = torch.empty(Lmax + 1, R, Hh, dtype=torch.float32, device=dev)
                 hsb = torch.empty(Lmax + 1, R, Hh, dtype=torch.bfloat16, device=dev)
-                hs[0].zero_()
-                hsb[0].zero_()
+                clear += [hs[0], hsb[0]]
                 if counts is not None:
                     # rows of hs / hsb[s] that step s - 1 does not write: a path that becomes live at step s (reverse
                     # direction) starts from h = 0, and hsb[s] as a whole is an operand of the dW_hh GEMM
                     for s_ in range(1, Lmax):
                         wrote = counts[s_ - 1] if d == 0 else counts[Lmax - s_]
                         if wrote < R:
-                            hsb[s_, wrote:].zero_()
+                            clear.append(hsb[s_, wrote:])
                             if d == 1:
-                                hs[s_, wrote:counts[Lmax - 1 - s_]].zero_()
+                                clear.append(hs[s_, wrote:counts[Lmax - 1 - s_]])
                 per_dir.append((Wcat, bcat, gates, hs, hsb))
                 saved += [xb, gates, hs, hsb, Wih_t, Whh_t]
+            zero_regions(clear)
 
             def run_dir(d, xb=xb, outb=outb, Kin=Kin, Kx=Kx, ldw=ldw, per_dir=per_dir, last=(l == num_layers - 1)):
                 Wcat, bcat, gates, hs, hsb = per_dir[d]
@@ -1350,28 +1365,37 @@ class GRUBankFn(torch.autograd.Function):
             dgi_cat = torch.empty(rows, 6 * Hh, dtype=torch.bfloat16, device=dev)      # [dgi_fwd | dgi_rev], time order
             Wih_t_cat = []
             per_dir = []
+            clear = []                                                                 # ranges to zero: ONE launch per layer
+            dh0 = []                                                                   # initial dh of each direction
             for d in range(2):                                                         # outputs of both directions first
                 xb, gates, hs, hsb, Wih_t, Whh_t = saved[(l * 2 + d) * 6:(l * 2 + d) * 6 + 6]
                 Kin = Wih_t.shape[0]
                 base = (l * 2 + d) * 4
                 wgrads[base + 0] = torch.empty(3 * Hh, Kin, dtype=torch.float32, device=dev)
                 wgrads[base + 1] = torch.empty(3 * Hh, Hh, dtype=torch.float32, device=dev)
-                wgrads[base + 2] = torch.zeros(3 * Hh, dtype=torch.float32, device=dev)
-                wgrads[base + 3] = torch.zeros(3 * Hh, dtype=torch.float32, device=dev)
+                wgrads[base + 2] = torch.empty(3 * Hh, dtype=torch.float32, device=dev)
+                wgrads[base + 3] = torch.empty(3 * Hh, dtype=torch.float32, device=dev)
+                clear += [wgrads[base + 2], wgrads[base + 3]]
                 dgh = torch.empty(rows, 3 * Hh, dtype=torch.bfloat16, device=dev)      # rows in step order s
                 if counts is not None:
                     for s_ in range(Lmax):                                             # rows the gate kernel skips: zero,
                         n_ = counts[s_ if d == 0 else Lmax - 1 - s_]                   # they are operands of the dW GEMMs
                         if n_ < R:
-                            dgh[s_ * R + n_:(s_ + 1) * R].zero_()
+                            clear.append(dgh[s_ * R + n_:(s_ + 1) * R])
                 per_dir.append(dgh)
                 Wih_t_cat.append(Wih_t)
+                if l == num_layers - 1:
+                    dh0.append(None)
+                else:
+                    dh0.append(torch.empty(R, Hh, dtype=torch.float32, device=dev))
+                    clear.append(dh0[-1])
             if counts is not None:
                 for t in range(Lmax):
                     if counts[t] < R:
-                        dgi_cat[t * R + counts[t]:(t + 1) * R].zero_()
+                        clear.append(dgi_cat[t * R + counts[t]:(t + 1) * R])
+            zero_regions(clear)
 
-            def run_dir(d, l=l, per_dir=per_dir, dgi_cat=dgi_cat, d_layer_out=d_layer_out):
+            def run_dir(d, l=l, per_dir=per_dir, dgi_cat=dgi_cat, d_layer_out=d_layer_out, dh0=dh0):
                 xb, gates, hs, hsb, Wih_t, Whh_t = saved[(l * 2 + d) * 6:(l * 2 + d) * 6 + 6]
                 Kin = Wih_t.shape[0]
                 base = (l * 2 + d) * 4
@@ -1381,7 +1405,7 @@ class GRUBankFn(torch.autograd.Function):
                 if l == num_layers - 1:
                     dh = dfinals[:, d * Hh:(d + 1) * Hh].contiguous()
                 else:
-                    dh = torch.zeros(R, Hh, dtype=torch.float32, device=dev)
+                    dh = dh0[d]                                                        # zeroed with the layer's other ranges
                 dh_part = torch.empty_like(dh)                                         # dh * z (pass-through for finished rows)
                 dgi = dgi_cat[:, d * 3 * Hh:(d + 1) * 3 * Hh]                          # rows in time order t
                 for s in range(Lmax - 1, -1, -1):

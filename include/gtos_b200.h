@@ -258,6 +258,12 @@ int gtos_gru_gate_bwd(const float* dh, const float* dout_t, int64_t lddout, cons
                       const int64_t* lengths, int32_t t, float* dh_prev, void* dgi_bf16, int64_t lddgi, void* dgh_bf16,
                       int64_t lddgh, float* db_ih, float* db_hh, int64_t R, int32_t Hh, void* stream);
 
+/* zero n byte ranges of device memory with one launch per 48 ranges.  ptrs / bytes are HOST arrays of n entries (the
+ * device pointers and their lengths are passed to the kernel by value).  RelationEncoder's length-sorted schedule
+ * (encoder.py:93-99: like pack_padded_sequence, step t runs on the paths longer than t only) clears ~75 short row ranges
+ * per training step that no kernel writes but a later GEMM reads. */
+int gtos_zero_regions(void* const* ptrs, const int64_t* bytes, int32_t n, void* stream);
+
 /* ---- fp32 mode (BASELINE north star: "within 1e-3 fp32"; the reference computes in fp32 end to end,
  *      graph_transformer.py:122-133, transformer.py:111-162, encoder.py:90-119) ----
  * Every matrix product still runs on the tcgen05 GEMMs above, on SPLIT operands: x = x_hi + x_lo, x_hi = bf16(x),

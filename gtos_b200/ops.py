@@ -443,6 +443,7 @@ def zero_regions(tensors):
     ts = [t for t in tensors if t is not None and t.numel() > 0]
     if not ts:
         return
+    _need_cuda(*ts)
     for t in ts:
         if not t.is_contiguous():
             raise ValueError("zero_regions: contiguous views only")

@@ -103,3 +103,6 @@ def test_precision_switch_host_logic():
     from gtos_b200 import _lib, ops32
     with pytest.raises(_lib.GtosLibraryError):
         ops32.split3(torch.zeros(4, 8), 0)
+    with pytest.raises(_lib.GtosLibraryError):
+        ops.zero_regions([torch.ones(4, 8)])
+    ops.zero_regions([])                      # nothing to do: no launch, no error

@@ -39,7 +39,8 @@
 
 namespace gtos {
 
-// the library's counter-based uniform (common.cuh rng_uniform), usable from host code too
+// the path sampler's counter-based uniform (64-bit splitmix finalizer; the dropout generator of common.cuh is a separate,
+// cheaper function) - pinned bit for bit to oracle/paths_oracle.py, usable from host code too
 GTOS_HD float paths_uniform(uint64_t seed, uint64_t idx) {
   uint64_t z = seed + idx * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;

@@ -24,7 +24,7 @@ M64 = (1 << 64) - 1
 
 
 def uniform(seed, idx):
-    """counter-based uniform in [0,1) of the library (csrc/common.cuh rng_uniform), as a float32"""
+    """counter-based uniform in [0,1) of the path sampler (csrc/graph_paths_core.h paths_uniform), as a float32"""
     z = (seed + idx * 0x9E3779B97F4A7C15 + 0x632BE59BD9B4E019) & M64
     z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M64
     z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M64
